@@ -1,0 +1,86 @@
+"""The oracle against golden vectors produced by the reference's own source
+(tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+
+@pytest.mark.parametrize("tag", ["traj_small", "traj_aligned"])
+def test_trajectory_stages(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    nodes, avg = oracle.traj_alignment_and_averaging(
+        g["coords"].copy(), g["masses"], g["node_ptr"], g["atom_idx"], g["align_idx"])
+    # Kabsch rotations go through an SVD in both the shim and the oracle: identical code
+    # path -> identical results; allow a few ulp for BLAS differences
+    np.testing.assert_allclose(nodes, g["node_traj"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(avg, g["avg"], rtol=0, atol=1e-10)
+
+    cov = oracle.cartesian_covariance(g["node_traj"], g["avg"])
+    assert np.array_equal(cov, g["cov"])                       # same loop, same order: bit-exact
+    cov_fast = oracle.cartesian_covariance_fast(g["node_traj"], g["avg"])
+    np.testing.assert_allclose(cov_fast, g["cov"], rtol=0, atol=1e-9 * np.abs(g["cov"]).max())
+
+    var, ncov, corr = oracle.pearson_correlation_analysis(g["cov"])
+    assert np.array_equal(corr, g["corr"])
+    # node_variance / node_covariance went through np.savetxt('%.18e') -> exact round trip
+    assert np.array_equal(var, g["var"])
+    assert np.array_equal(ncov, g["ncov"])
+    var2, ncov2, corr2 = oracle.pearson_correlation_fast(g["cov"])
+    assert np.array_equal(corr2, g["corr"]) and np.array_equal(var2, g["var"])
+    assert np.array_equal(ncov2, g["ncov"])
+    # diagonal is exactly 1
+    assert np.all(np.diagonal(corr) == 1.0)
+
+    binary, avgdist = oracle.calc_contact_map(g["node_traj"], float(g["cutoff"]))
+    assert np.array_equal(binary, g["binary"])
+    assert np.array_equal(avgdist, g["avgdist"])
+    b2, a2 = oracle.calc_contact_map_fast(g["node_traj"], float(g["cutoff"]))
+    assert np.array_equal(b2, g["binary"]) and np.array_equal(a2, g["avgdist"])
+
+    assert np.array_equal(oracle.func_pearson_correlation(g["corr"]), g["w_plain"])
+    assert np.array_equal(oracle.func_pearson_correlation(g["corr"], g["binary"]), g["w_binary"])
+    assert np.array_equal(oracle.func_pearson_correlation(g["corr"], g["avgdist"]), g["w_avg"])
+
+
+def _unpack(g, i):
+    off = g["offsets%d" % i]
+    nodes = g["nodes%d" % i]
+    return [[float(g["lengths%d" % i][k])] + [int(x) for x in nodes[off[k]:off[k + 1]]]
+            for k in range(len(off) - 1)]
+
+
+def test_get_paths_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "get_paths.npz"))
+    n = int(g["n_cases"])
+    assert n >= 10
+    saw_k_plus_1 = False
+    for i in range(n):
+        W = g["W%d" % i]
+        so = [int(x) for x in g["sources%d" % i]]
+        si = [int(x) for x in g["sinks%d" % i]]
+        K = int(g["K%d" % i])
+        want = _unpack(g, i)
+        saw_k_plus_1 |= len(want) == K + 1
+        lit = oracle.get_paths(W, so, si, K, max_passes=500)
+        pru = oracle.get_paths_pruned(W, so, si, K)
+        for got in (lit, pru):
+            assert len(got) == len(want), (i, len(got), len(want))
+            for a, b in zip(got, want):
+                assert [int(x) for x in a[1:]] == b[1:], (i, a, b)
+                assert float(a[0]) == b[0], (i, a, b)       # bit-exact float64 LR lengths
+    assert saw_k_plus_1
+
+
+def test_com_extraction_golden(golden_dir):
+    """COM extraction alone: the reference run with maximum_num_iterations=0 returns the
+    translated, un-rotated node COMs (trajectory_analysis_functions.py:70-87)."""
+    for tag in ("traj_small", "traj_aligned"):
+        g = np.load(os.path.join(golden_dir, tag + ".npz"))
+        nodes, align = oracle.com_nodes(g["coords"], g["masses"], g["node_ptr"], g["atom_idx"],
+                                        g["align_idx"])
+        np.testing.assert_allclose(nodes, g["com_only"], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(nodes.sum(axis=0) / nodes.shape[0], g["com_avg"], rtol=0,
+                                   atol=1e-13)
