@@ -1,0 +1,165 @@
+/* wisp_b200.h -- C ABI of the B200-native WISP hot path (libwisp_b200.so).
+ *
+ * Plain pointers and sizes only; no torch / C++ types cross this boundary.  The reference
+ * (rbdavid/WISP_mdanalysis_implementation) is pure Python and has no FFI of its own, so
+ * each entry point cites the reference *function* it replaces (file:line); the Python
+ * stage modules in wisp_mdanalysis_implementation_b200/ bind these with ctypes and keep
+ * the reference's function names and signatures (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; wisp_last_error() gives
+ *     the message of the last failure on the calling thread;
+ *   - "host" pointers may be pageable or pinned (pinned makes the copies asynchronous);
+ *     "dev" pointers are CUDA device pointers owned by the caller (e.g. torch tensors);
+ *   - matrices are row-major; N = nodes, T = frames, A = atoms;
+ *   - the node trajectory lives on the device as double [Tpad][ld] with
+ *     ld = wisp_node_ld(N) columns (3*N rounded up to whole 128-node tiles, zero padded)
+ *     and Tpad = wisp_frames_pad(T) rows (zero padded);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the context's own stream).
+ */
+#ifndef WISP_B200_H
+#define WISP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wisp_ctx wisp_ctx;
+
+/* ---- context ------------------------------------------------------------------------ */
+int         wisp_ctx_create(int device, wisp_ctx** out);
+void        wisp_ctx_destroy(wisp_ctx* ctx);
+const char* wisp_last_error(void);
+int         wisp_abi_version(void);
+int         wisp_sync(wisp_ctx* ctx);
+/* layout helpers */
+int64_t     wisp_node_ld(int n_nodes);        /* columns of the device node trajectory   */
+int64_t     wisp_frames_pad(int64_t n_frames);/* rows of the device node trajectory       */
+int64_t     wisp_gram_ld(int n_cols);         /* leading dimension of Gram / sum buffers  */
+/* number of launches of this library's kernels since the context was created */
+int64_t     wisp_kernel_launches(wisp_ctx* ctx);
+
+/* ---- host-buffer entry points (what the reference-facing Python modules call) ------- */
+
+/* K1: per-frame translate by -COM(alignment atoms) and per-node mass-weighted COM.
+ * Replaces trajectory_analysis_functions.py:70-79 (inside traj_alignment_and_averaging).
+ * coords [T][A][3] float32; masses [A]; CSR node map node_ptr[N+1]/atom_idx[];
+ * align_idx[n_align].  atomic != 0 selects node_definition 'ATOMIC' (:78).
+ * out_nodes [T][N][3] float64, out_avg [N][3] = (sum_t nodes)/T (:87). */
+int wisp_com_nodes(wisp_ctx* ctx, const float* coords, int64_t T, int A,
+                   const double* masses, const int32_t* node_ptr, const int32_t* atom_idx,
+                   int N, const int32_t* align_idx, int n_align, int atomic,
+                   double* out_nodes, double* out_avg);
+
+/* a1 + alignment: traj_alignment_and_averaging(...) -- trajectory_analysis_functions.py:39-138.
+ * K1 as above, then the iterative alignment of every frame onto the running average of the
+ * alignment landmarks (:86-126) until the landmark-average RMSD between two
+ * iterations is <= threshold or max_iter iterations ran (max_iter = 0: COM extraction only).
+ * out_nodes [T][N][3] aligned node trajectory, out_avg [N][3] its frame mean,
+ * out_log [3*max_iter] = (iteration, landmark RMSD, node RMSD) per iteration (may be NULL). */
+int wisp_traj_alignment_and_averaging(wisp_ctx* ctx, const float* coords, int64_t T, int A,
+                                      const double* masses, const int32_t* node_ptr,
+                                      const int32_t* atom_idx, int N, const int32_t* align_idx,
+                                      int n_align, int atomic, double threshold, int max_iter,
+                                      double* out_nodes, double* out_avg, double* out_log,
+                                      int* out_n_iter);
+
+/* a2: cartesian_covariance(node_trajectory, avg_node_positions, ...) --
+ * trajectory_analysis_functions.py:141-184.  nodes [T][N][3], avg [N][3];
+ * out_cov [3N][3N] = (1/T) sum_t x x^T - avg avg^T. */
+int wisp_cartesian_covariance(wisp_ctx* ctx, const double* nodes, int64_t T, int N,
+                              const double* avg, double* out_cov);
+
+/* a3: pearson_correlation_analysis(cov, ...) -- adjacency_matrix_functions.py:8-59.
+ * cov [3N][3N]; outputs node_variance [N], node_covariance [N][N], node_correlation [N][N]
+ * (any output pointer may be NULL). */
+int wisp_pearson_from_covariance(wisp_ctx* ctx, const double* cov, int N, double* out_var,
+                                 double* out_ncov, double* out_corr);
+
+/* a4: calc_contact_map(trajectory_data, ..., distance_cutoff) --
+ * trajectory_analysis_functions.py:187-236.  out_binary [N][N] int64 (numpy int),
+ * out_avgdist [N][N] float64. */
+int wisp_contact_map(wisp_ctx* ctx, const double* nodes, int64_t T, int N, double cutoff,
+                     int64_t* out_binary, double* out_avgdist);
+
+/* a5: func_pearson_correlation(adjacency, ..., contact_map) --
+ * functionalize_adj_matrix_functions.py:10-24.  map may be NULL; out_w [N][N]. */
+int wisp_func_pearson(wisp_ctx* ctx, const double* corr, int N, const double* contact_map,
+                      double* out_w);
+
+/* Fused a1..a5: coordinates -> node COMs -> centred Gram + mean distances -> correlation,
+ * contact maps, cost matrix, with the node trajectory never leaving the device.
+ * which_map: 0 none, 1 binary, 2 average-distance (wisp_w_mdanalysis.py:98-101,141-144).
+ * Any output pointer may be NULL.  out_nodes [T][N][3] is optional (large). */
+int wisp_pipeline(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
+                  const int32_t* node_ptr, const int32_t* atom_idx, int N,
+                  const int32_t* align_idx, int n_align, int atomic, double cutoff,
+                  int which_map, double* out_avg, double* out_corr, double* out_avgdist,
+                  int64_t* out_binary, double* out_w, double* out_nodes);
+
+/* a6 (north-star APSP; the reference calls Dijkstra, network_analysis_functions.py:30,71-72).
+ * w [N][N] cost matrix (non-zero = edge).  precision 64 or 32 (distances are returned as
+ * float64 either way).  out_dist [N][N], out_pred [N][N] (-1 = none); pred may be NULL. */
+int wisp_apsp(wisp_ctx* ctx, const double* w, int N, int precision, double* out_dist,
+              int32_t* out_pred);
+
+/* a6-a9: get_paths(adjacency_matrix, sources, sinks, number_of_paths) --
+ * network_analysis_functions.py:12-214 (Appendix A of SURVEY.md).  flags bit0: keep the
+ * reference's node-0 quirk (default on), bit1: APSP in float32.  Results are kept in the
+ * context; fetch them with wisp_paths_size / wisp_paths_fetch. */
+int wisp_get_paths(wisp_ctx* ctx, const double* w, int N, const int32_t* sources, int n_sources,
+                   const int32_t* sinks, int n_sinks, int number_of_paths, int flags);
+int wisp_paths_size(wisp_ctx* ctx, int64_t* n_paths, int64_t* n_node_entries);
+int wisp_paths_fetch(wisp_ctx* ctx, double* lengths, int64_t* offsets /* n_paths+1 */,
+                     int32_t* nodes);
+/* statistics of the last wisp_get_paths: [0] passes, [1] expansions, [2] final cutoff,
+ * [3] apsp ms, [4] enumeration ms, [5] host finalize ms */
+int wisp_paths_stats(wisp_ctx* ctx, double* out6);
+
+/* ---- device-buffer entry points (bench, multi-GPU orchestration) --------------------- */
+
+/* K1 on device buffers.  d_nodes: double [wisp_frames_pad(T)][ld] (zeroed by the caller or
+ * by this call when zero_pad != 0); d_colsum [ld] receives sum over frames of every column
+ * (overwritten). */
+int wisp_dev_com(wisp_ctx* ctx, const float* d_coords, int64_t T, int A, const double* d_masses,
+                 const int32_t* d_node_ptr, const int32_t* d_atom_idx, int N,
+                 const int32_t* d_align_idx, int n_align, int atomic, double* d_nodes,
+                 double* d_colsum, void* stream);
+/* X <- X - mean (in place), mean [ld]; pad columns / rows are left at zero. */
+int wisp_dev_center(wisp_ctx* ctx, double* d_nodes, int64_t T, int N, const double* d_mean,
+                    void* stream);
+/* column sums of the (possibly centred) trajectory: d_colsum [ld] */
+int wisp_dev_colsum(wisp_ctx* ctx, const double* d_nodes, int64_t T, int N, double* d_colsum,
+                    void* stream);
+/* K2: node Gram  G[i][j] = sum_t sum_c X[t][3i+c] X[t][3j+c]  (stride 3) or plain
+ * X^T X over columns (stride 1), upper-triangular 128-tiles only.  d_out: double
+ * [n_out_pad][n_out_pad] with n_out_pad = wisp_gram_ld(n_out); overwritten. */
+int wisp_dev_gram(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_out,
+                  int stride, double* d_out, void* stream);
+/* K3: D[i][j] = sum_t |x_i(t) - x_j(t)| for i<=j tiles; d_x is the CENTRED trajectory and
+ * d_mean [ld] the mean that was subtracted.  d_out [Npad][Npad] overwritten. */
+int wisp_dev_contact_sum(wisp_ctx* ctx, const double* d_x, int64_t T, int N,
+                         const double* d_mean, double* d_out, void* stream);
+/* K4: fused epilogue on (all-reduced) sums.  d_gram / d_dsum are [Npad][Npad] upper-tile
+ * sums over T_total frames.  Outputs (each may be NULL) are dense [N][N]:
+ * corr, ncov (=G/T), avgdist, binary (int64), w (= -log|corr| (.) map). d_var [N]. */
+int wisp_dev_epilogue(wisp_ctx* ctx, const double* d_gram, const double* d_dsum,
+                      int64_t T_total, int N, double cutoff, int which_map, double* d_var,
+                      double* d_ncov, double* d_corr, double* d_avgdist, int64_t* d_binary,
+                      double* d_w, void* stream);
+/* K5 on device: d_w [N][N] cost matrix -> d_dist (float64 [N][N]) and d_pred (int32). */
+int wisp_dev_apsp(wisp_ctx* ctx, const double* d_w, int N, int precision, double* d_dist,
+                  int32_t* d_pred, void* stream);
+/* synthetic coordinates generated on the device (bench-scale inputs; synth.py model):
+ * atom_base [A][3] f64, node_of_atom [A], modes [N][M][3] f64, coeff [T][M] f64. */
+int wisp_dev_synth_coords(wisp_ctx* ctx, float* d_coords, int64_t t0, int64_t T, int A,
+                          const double* d_atom_base, const int32_t* d_node_of_atom,
+                          const double* d_modes, int n_modes, const double* d_coeff,
+                          double noise_sigma, uint64_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WISP_B200_H */

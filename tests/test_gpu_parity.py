@@ -1,0 +1,254 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and against the
+golden vectors produced by the reference's own code.  Tolerances (BASELINE.json north_star):
+correlation / contact matrices 1e-6 relative (floor 1e-3 on |C|), path
+lengths 1e-9 relative (bit-exact here), contact topology / predecessors / node sequences
+exact outside ties."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from wisp_mdanalysis_implementation_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from wisp_mdanalysis_implementation_b200 import _lib
+    return _lib.default_context()
+
+
+def assert_corr_close(got, want, rel=1e-6, floor=1e-3):
+    err = np.abs(got - want)
+    tol = rel * np.maximum(np.abs(want), floor)
+    bad = err > tol
+    assert not bad.any(), "max err %.3e (tol %.3e) at %s" % (err.max(), tol.flat[err.argmax()], np.argwhere(bad)[:5])
+
+
+def assert_binary_equal_outside_ties(binary, avgdist_ref, cutoff, binary_ref, rel=1e-6):
+    diff = binary != binary_ref
+    if diff.any():
+        near = np.abs(avgdist_ref - cutoff) <= rel * cutoff
+        assert not (diff & ~near).any(), "contact topology differs away from the cutoff"
+
+
+def _unpack(g, i):
+    off = g["offsets%d" % i]
+    nodes = g["nodes%d" % i]
+    return [[float(g["lengths%d" % i][k])] + [int(x) for x in nodes[off[k]:off[k + 1]]]
+            for k in range(len(off) - 1)]
+
+
+@pytest.mark.parametrize("tag", ["traj_small", "traj_aligned"])
+def test_golden_trajectory_stages(ctx, golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    # K1: translate + COM (reference run with zero alignment iterations)
+    nodes, avg = ctx.com_nodes(g["coords"], g["masses"], g["node_ptr"], g["atom_idx"], g["align_idx"])
+    np.testing.assert_allclose(nodes, g["com_only"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(avg, g["com_avg"], rtol=0, atol=1e-12)
+    # K1 + K7: full traj_alignment_and_averaging
+    nodes_al, avg_al, log = ctx.traj_alignment_and_averaging(
+        g["coords"], g["masses"], g["node_ptr"], g["atom_idx"], g["align_idx"])
+    np.testing.assert_allclose(nodes_al, g["node_traj"], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(avg_al, g["avg"], rtol=0, atol=1e-8)
+    assert len(log) >= 1 and log[-1][1] <= 1e-5
+
+    # K2 (stride 1) + finalize: 3N x 3N covariance
+    cov = ctx.cartesian_covariance(g["node_traj"], g["avg"])
+    scale = np.abs(g["cov"]).max()
+    assert np.abs(cov - g["cov"]).max() <= 1e-9 * scale
+    assert np.array_equal(cov, cov.T)
+    # a3 on the reference's covariance: same IEEE operations -> bit-exact
+    var, ncov, corr = ctx.pearson_from_covariance(g["cov"])
+    assert np.array_equal(var, g["var"])
+    assert np.array_equal(ncov, g["ncov"])
+    assert np.array_equal(corr, g["corr"])
+    # K3 + K4: contact maps
+    binary, avgdist = ctx.contact_map(g["node_traj"], float(g["cutoff"]))
+    np.testing.assert_allclose(avgdist, g["avgdist"], rtol=1e-6, atol=1e-9)
+    assert np.all(np.diagonal(avgdist) == 0.0) and np.all(np.diagonal(binary) == 0)
+    assert_binary_equal_outside_ties(binary, g["avgdist"], float(g["cutoff"]), g["binary"])
+    assert binary.dtype == np.int64
+    # a5: -log|C| (.) map
+    for key, cm in (("w_plain", None), ("w_binary", g["binary"]), ("w_avg", g["avgdist"])):
+        w = ctx.func_pearson(g["corr"], None if cm is None else cm.astype(np.float64))
+        want = g[key]
+        assert np.array_equal(np.isnan(w), np.isnan(want))
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(w), fin)
+        np.testing.assert_allclose(w[fin], want[fin], rtol=1e-13, atol=1e-300)
+        assert np.all(w[np.diag_indices_from(w)] == 0.0)
+
+
+def test_golden_get_paths(ctx, golden_dir):
+    g = np.load(os.path.join(golden_dir, "get_paths.npz"))
+    for i in range(int(g["n_cases"])):
+        W = g["W%d" % i]
+        so = [int(x) for x in g["sources%d" % i]]
+        si = [int(x) for x in g["sinks%d" % i]]
+        K = int(g["K%d" % i])
+        want = _unpack(g, i)
+        got = ctx.get_paths(W, so, si, K)
+        assert len(got) == len(want), (i, len(got), len(want))
+        for a, b in zip(got, want):
+            assert a[1:] == b[1:], (i, a, b)
+            assert a[0] == b[0], (i, a, b)          # bit-exact float64 LR lengths
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+@pytest.mark.parametrize("n", [37, 64, 150, 333])
+def test_apsp_vs_oracle(ctx, n, precision):
+    W = synth.random_cost_matrix(n, seed=100 + n, density=0.08)
+    D, P = oracle.apsp_dijkstra(W)
+    dist, pred = ctx.apsp(W, precision=precision)
+    tol = 1e-12 if precision == 64 else 2e-6
+    np.testing.assert_allclose(dist, D, rtol=tol, atol=1e-300)
+    if precision == 64:
+        # random real weights: shortest paths are unique -> predecessors must agree exactly
+        assert np.array_equal(pred.astype(np.int64), P)
+    # predecessor consistency (holds in both precisions): dist[i][pred] + w[pred][j] ~ dist[i][j]
+    ii, jj = np.nonzero(pred >= 0)
+    pp = pred[ii, jj]
+    np.testing.assert_allclose(dist[ii, pp] + W[pp, jj], dist[ii, jj], rtol=10 * tol, atol=1e-12)
+    assert np.all(np.diagonal(dist) == 0) and np.all(np.diagonal(pred) == -1)
+
+
+def test_apsp_disconnected_and_inf(ctx):
+    W = synth.random_cost_matrix(40, seed=5, density=0.2)
+    W[:, 17] = 0.0
+    W[17, :] = 0.0                      # isolated node
+    W[3, 4] = W[4, 3] = np.inf          # |C| = 0 -> +inf weight: an edge that is never useful
+    dist, pred = ctx.apsp(W)
+    D, P = oracle.apsp_dijkstra(W)
+    assert np.array_equal(np.isinf(dist), np.isinf(D))
+    fin = np.isfinite(D)
+    np.testing.assert_allclose(dist[fin], D[fin], rtol=1e-12)
+    assert np.all(pred[17, np.arange(40) != 17] == -1)
+
+
+@pytest.mark.parametrize("n,t,apn", [(50, 100, 3), (128, 240, 4), (300, 1000, 16), (257, 333, 5)])
+def test_pipeline_vs_oracle(ctx, n, t, apn):
+    system, coords = synth.synth(n, t, apn, seed=7 + n)
+    cutoff = 15.0
+    out = ctx.pipeline(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx,
+                       cutoff=cutoff, which_map=1, want_nodes=True)
+    nodes, _ = oracle.com_nodes(coords, system.masses, system.node_ptr, system.atom_idx,
+                                system.align_idx)
+    np.testing.assert_allclose(out["nodes"], nodes, rtol=0, atol=1e-11)
+    avg = nodes.sum(axis=0) / t
+    np.testing.assert_allclose(out["avg"], avg, rtol=0, atol=1e-11)
+    cov = oracle.cartesian_covariance_fast(nodes, avg)
+    _, _, corr = oracle.pearson_correlation_fast(cov)
+    assert_corr_close(out["corr"], corr)
+    # at least as close to the long-double truth as the reference formula is
+    _, corr_true = oracle.node_gram_truth(nodes)
+    assert np.abs(out["corr"] - corr_true).max() <= max(np.abs(corr - corr_true).max(), 1e-13) * 4
+    assert np.all(np.diagonal(out["corr"]) == 1.0)
+    assert np.array_equal(out["corr"], out["corr"].T)
+    binary, avgdist = oracle.calc_contact_map_fast(nodes, cutoff)
+    np.testing.assert_allclose(out["avgdist"], avgdist, rtol=1e-6, atol=1e-9)
+    assert_binary_equal_outside_ties(out["binary"], avgdist, cutoff, binary)
+    w = oracle.func_pearson_correlation(corr, binary)
+    same_topology = np.array_equal(out["binary"], binary)
+    if same_topology:
+        nz = w != 0
+        assert np.array_equal(out["w"] != 0, nz)
+        # -log|C|: relative error of C (1e-6, floor) becomes absolute error of W
+        np.testing.assert_allclose(out["w"][nz], w[nz], rtol=0, atol=2e-6 + 1e-3 * 0)
+
+
+def test_cartesian_covariance_supplied_average(ctx):
+    """E[xx^T] - a a^T with an average that is NOT the frame mean."""
+    rng = np.random.default_rng(3)
+    nodes = rng.normal(size=(200, 40, 3)) + rng.normal(scale=20, size=(1, 40, 3))
+    a = nodes.mean(axis=0) + rng.normal(scale=0.05, size=(40, 3))
+    cov = ctx.cartesian_covariance(nodes, a)
+    want = oracle.cartesian_covariance(nodes, a)
+    assert np.abs(cov - want).max() <= 1e-9 * np.abs(want).max()
+
+
+def test_get_paths_c1_stagewise(ctx):
+    """Config-1-like run: oracle cost matrix in, K=50 suboptimal paths out, bit-exact."""
+    system, coords = synth.synth(300, 400, 4, seed=1001)
+    nodes, _ = oracle.com_nodes(coords, system.masses, system.node_ptr, system.atom_idx,
+                                system.align_idx)
+    avg = nodes.sum(axis=0) / nodes.shape[0]
+    _, _, corr = oracle.pearson_correlation_fast(oracle.cartesian_covariance_fast(nodes, avg))
+    binary, _ = oracle.calc_contact_map_fast(nodes, 12.0)
+    W = oracle.func_pearson_correlation(corr, binary)
+    D, _ = oracle.apsp_dijkstra(W)
+    # first pair in index order that is 5-8 hops apart
+    hops, _ = oracle.apsp_dijkstra((W != 0).astype(float))
+    s, t = [(i, j) for i in range(300) for j in range(i + 1, 300) if 5 <= hops[i, j] <= 8][0]
+    want = oracle.get_paths_pruned(W, [s], [t], 50)
+    got = ctx.get_paths(W, [s], [t], 50)
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a[1:] == [int(x) for x in b[1:]]
+        assert a[0] == float(b[0])
+    st = ctx.paths_stats()
+    assert st["passes"] >= 1 and st["expansions"] > 0
+
+
+def test_get_paths_multi_pair_and_quirk(ctx):
+    rng = np.random.default_rng(11)
+    for trial in range(6):
+        n = int(rng.integers(14, 30))
+        W = synth.random_cost_matrix(n, seed=int(rng.integers(1 << 30)), density=0.3, lo=0.05, hi=0.7)
+        so = [int(x) for x in rng.choice(n, size=2, replace=False)]
+        si = [int(x) for x in rng.choice(n, size=2, replace=False)]
+        K = int(rng.integers(5, 40))
+        want = oracle.get_paths_pruned(W, so, si, K)
+        got = ctx.get_paths(W, so, si, K)
+        assert [p[1:] for p in got] == [[int(x) for x in p[1:]] for p in want], trial
+        assert [p[0] for p in got] == [float(p[0]) for p in want], trial
+        # quirk off == plain K shortest simple paths
+        want_nq = oracle.get_paths_pruned(W, so, si, K, node0_quirk=False)
+        got_nq = ctx.get_paths(W, so, si, K, node0_quirk=False)
+        assert [p[1:] for p in got_nq] == [[int(x) for x in p[1:]] for p in want_nq], trial
+
+
+def test_get_paths_errors(ctx):
+    from wisp_mdanalysis_implementation_b200 import _lib
+    W = synth.random_cost_matrix(12, seed=2, density=0.3)
+    W[:, 5] = 0
+    W[5, :] = 0
+    with pytest.raises(_lib.WispError):
+        ctx.get_paths(W, [0], [5], 3)           # disconnected: reference raises NetworkXNoPath
+    chain = np.zeros((5, 5))
+    for i in range(4):
+        chain[i, i + 1] = chain[i + 1, i] = 1.0
+    with pytest.raises(_lib.WispError):
+        ctx.get_paths(chain, [0], [4], 3)       # only one simple path exists: reference never returns
+
+
+def test_properties_large(ctx):
+    """Size-independent properties at a size the oracle would take minutes for."""
+    n, t = 1000, 3000
+    system = synth.SynthSystem(n, t, 4, seed=99)
+    coords = system.coords()
+    out = ctx.pipeline(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx,
+                       cutoff=12.0, which_map=2)
+    c = out["corr"]
+    assert np.array_equal(c, c.T) and np.all(np.diagonal(c) == 1.0)
+    assert np.abs(c).max() <= 1.0 + 1e-12
+    ev = np.linalg.eigvalsh(c)
+    assert ev.min() > -1e-8                       # a correlation matrix is PSD
+    d = out["avgdist"]
+    assert np.array_equal(d, d.T) and np.all(np.diagonal(d) == 0)
+    # triangle inequality of mean distances on a sample
+    rng = np.random.default_rng(0)
+    i, j, k = rng.integers(0, n, size=(3, 2000))
+    assert np.all(d[i, j] <= d[i, k] + d[k, j] + 1e-9)
+    # linearity in frames: halves combine to the whole (frame-sharding identity)
+    h = t // 2
+    o1 = ctx.pipeline(coords[:h], system.masses, system.node_ptr, system.atom_idx, system.align_idx, cutoff=12.0)
+    o2 = ctx.pipeline(coords[h:], system.masses, system.node_ptr, system.atom_idx, system.align_idx, cutoff=12.0)
+    np.testing.assert_allclose(0.5 * (o1["avgdist"] + o2["avgdist"]), d, rtol=1e-9)
+    # APSP on the resulting cost matrix: triangle inequality + symmetric
+    W = out["w"]
+    dist, pred = ctx.apsp(W)
+    assert np.allclose(dist, dist.T, rtol=1e-12)
+    assert np.all(dist[i, j] <= dist[i, k] + dist[k, j] + 1e-9)

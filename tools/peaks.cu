@@ -1,0 +1,112 @@
+// Pipe-peak microbenchmarks for the roofline denominators that MEASURED_PEAKS.json lacks
+// (SURVEY.md 8d): FP64 DMMA, FP64 FMA, FP32 FMA, MUFU sqrt.  Register-resident loops,
+// best of 5, CUDA events.  Prints one JSON object.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+__global__ void dmma_peak(double* out, int iters) {
+    double c[8][2];
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+    double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-6;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s;
+}
+__global__ void dfma_peak(double* out, int iters) {
+    double c[8];
+    for (int i = 0; i < 8; ++i) c[i] = i;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0;
+    for (int i = 0; i < 8; ++i) s += c[i];
+    if (s == 123.456) out[0] = s;
+}
+__global__ void ffma_peak(float* out, int iters) {
+    float c[16];
+    for (int i = 0; i < 16; ++i) c[i] = i;
+    float a = 1.0f + threadIdx.x * 1e-7f, b = 1e-7f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fmaf(c[i], a, b);
+    }
+    float s = 0;
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 123.456f) out[0] = s;
+}
+__global__ void mufu_peak(float* out, int iters) {
+    float c[8];
+    for (int i = 0; i < 8; ++i) c[i] = 2.0f + i + threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(c[i]));
+    }
+    float s = 0;
+    for (int i = 0; i < 8; ++i) s += c[i];
+    if (s == 123.456f) out[0] = s;
+}
+// FADD + FMNMX mix (min-plus relaxation without predecessors)
+__global__ void minplus_peak(float* out, int iters) {
+    float c[16];
+    for (int i = 0; i < 16; ++i) c[i] = 1e9f;
+    float a = threadIdx.x, b = 0.5f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { c[i] = fminf(c[i], a + b); a += 1e-3f; }
+    }
+    float s = 0;
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 123.456f) out[0] = s;
+}
+
+template <typename F>
+double best_ms(F launch) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 1e30;
+    for (int r = 0; r < 6; ++r) {
+        cudaEventRecord(e0);
+        launch();
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;
+    }
+    return best;
+}
+
+int main() {
+    cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+    void* buf; CK(cudaMalloc(&buf, 1024));
+    const int sms = p.multiProcessorCount;
+    const int blocks = sms * 4, threads = 256;
+    const double warps = (double)blocks * threads / 32, lanes = (double)blocks * threads;
+    const int it = 20000;
+    double t;
+    t = best_ms([&] { dmma_peak<<<blocks, threads>>>((double*)buf, it); });
+    const double dmma_tf = warps * it * 8 * 512.0 / (t * 1e-3) / 1e12;
+    t = best_ms([&] { dfma_peak<<<blocks, threads>>>((double*)buf, it); });
+    const double dfma_tf = lanes * it * 8 * 2.0 / (t * 1e-3) / 1e12;
+    t = best_ms([&] { ffma_peak<<<blocks, threads>>>((float*)buf, it); });
+    const double ffma_tf = lanes * it * 16 * 2.0 / (t * 1e-3) / 1e12;
+    t = best_ms([&] { mufu_peak<<<blocks, threads>>>((float*)buf, it); });
+    const double mufu_tops = lanes * it * 8.0 / (t * 1e-3) / 1e12;
+    t = best_ms([&] { minplus_peak<<<blocks, threads>>>((float*)buf, it); });
+    const double minplus_trelax = lanes * it * 16.0 / (t * 1e-3) / 1e12;
+    CK(cudaDeviceSynchronize());
+    printf("{\"gpu\": \"%s\", \"sms\": %d, \"fp64_dmma_tflops\": %.2f, \"fp64_fma_tflops\": %.2f, "
+           "\"fp32_fma_tflops\": %.2f, \"mufu_sqrt_tops\": %.3f, \"fp32_minplus_trelax\": %.3f}\n",
+           p.name, sms, dmma_tf, dfma_tf, ffma_tf, mufu_tops, minplus_trelax);
+    return 0;
+}

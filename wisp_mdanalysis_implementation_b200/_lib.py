@@ -1,0 +1,328 @@
+"""ctypes binding of libwisp_b200.so (the C ABI declared in include/wisp_b200.h).
+
+There is NO CPU fallback: importing this module without the built library raises, and
+creating a context without a B200 raises.  numpy arrays are passed as plain pointers; the
+only state is an opaque ``wisp_ctx*`` per device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwisp_b200.so")
+
+# (name, restype, argtypes) -- must list every symbol of include/wisp_b200.h
+_c_ctx = C.c_void_p
+_P = C.c_void_p
+_i64 = C.c_int64
+_int = C.c_int
+_dbl = C.c_double
+SIGNATURES = {
+    "wisp_ctx_create": (_int, [_int, C.POINTER(_c_ctx)]),
+    "wisp_ctx_destroy": (None, [_c_ctx]),
+    "wisp_last_error": (C.c_char_p, []),
+    "wisp_abi_version": (_int, []),
+    "wisp_sync": (_int, [_c_ctx]),
+    "wisp_node_ld": (_i64, [_int]),
+    "wisp_frames_pad": (_i64, [_i64]),
+    "wisp_gram_ld": (_i64, [_int]),
+    "wisp_kernel_launches": (_i64, [_c_ctx]),
+    "wisp_com_nodes": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P, _int, _P, _int, _int, _P, _P]),
+    "wisp_traj_alignment_and_averaging": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P, _int, _P, _int,
+                                                 _int, _dbl, _int, _P, _P, _P, C.POINTER(_int)]),
+    "wisp_cartesian_covariance": (_int, [_c_ctx, _P, _i64, _int, _P, _P]),
+    "wisp_pearson_from_covariance": (_int, [_c_ctx, _P, _int, _P, _P, _P]),
+    "wisp_contact_map": (_int, [_c_ctx, _P, _i64, _int, _dbl, _P, _P]),
+    "wisp_func_pearson": (_int, [_c_ctx, _P, _int, _P, _P]),
+    "wisp_pipeline": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P, _int, _P, _int, _int, _dbl, _int,
+                             _P, _P, _P, _P, _P, _P]),
+    "wisp_apsp": (_int, [_c_ctx, _P, _int, _int, _P, _P]),
+    "wisp_get_paths": (_int, [_c_ctx, _P, _int, _P, _int, _P, _int, _int, _int]),
+    "wisp_paths_size": (_int, [_c_ctx, C.POINTER(_i64), C.POINTER(_i64)]),
+    "wisp_paths_fetch": (_int, [_c_ctx, _P, _P, _P]),
+    "wisp_paths_stats": (_int, [_c_ctx, _P]),
+    "wisp_dev_com": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P, _int, _P, _int, _int, _P, _P, _P]),
+    "wisp_dev_center": (_int, [_c_ctx, _P, _i64, _int, _P, _P]),
+    "wisp_dev_colsum": (_int, [_c_ctx, _P, _i64, _int, _P, _P]),
+    "wisp_dev_gram": (_int, [_c_ctx, _P, _i64, _i64, _int, _int, _P, _P]),
+    "wisp_dev_contact_sum": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P]),
+    "wisp_dev_epilogue": (_int, [_c_ctx, _P, _P, _i64, _int, _dbl, _int, _P, _P, _P, _P, _P, _P, _P]),
+    "wisp_dev_apsp": (_int, [_c_ctx, _P, _int, _int, _P, _P, _P]),
+    "wisp_dev_synth_coords": (_int, [_c_ctx, _P, _i64, _i64, _int, _P, _P, _P, _int, _P, _dbl,
+                                     C.c_uint64, _P]),
+}
+
+
+class WispError(RuntimeError):
+    pass
+
+
+def load_library(path=LIB_PATH):
+    if not os.path.exists(path):
+        raise WispError(
+            "libwisp_b200.so not found at %s -- build it with "
+            "`python -m wisp_mdanalysis_implementation_b200.build` (there is no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = load_library()
+    return _lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+def _arr(a, dtype, name, shape=None):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError("%s: expected shape %s, got %s" % (name, tuple(shape), a.shape))
+    return a
+
+
+class Context:
+    """One ``wisp_ctx`` (streams + scratch memory) on one B200."""
+
+    def __init__(self, device=0):
+        self._lib = lib()
+        self._ctx = _c_ctx()
+        rc = self._lib.wisp_ctx_create(int(device), C.byref(self._ctx))
+        if rc != 0:
+            raise WispError(self._lib.wisp_last_error().decode())
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.wisp_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise WispError(self._lib.wisp_last_error().decode())
+
+    @property
+    def handle(self):
+        return self._ctx
+
+    def kernel_launches(self):
+        return int(self._lib.wisp_kernel_launches(self._ctx))
+
+    def sync(self):
+        self._check(self._lib.wisp_sync(self._ctx))
+
+    # ---- host-buffer API ---------------------------------------------------------------
+    def com_nodes(self, coords, masses, node_ptr, atom_idx, align_idx, atomic=False,
+                  want_nodes=True):
+        coords = _arr(coords, np.float32, "coords")
+        T, A, _ = coords.shape
+        masses = _arr(masses, np.float64, "masses", (A,))
+        node_ptr = _arr(node_ptr, np.int32, "node_ptr")
+        atom_idx = _arr(atom_idx, np.int32, "atom_idx")
+        align_idx = _arr(align_idx, np.int32, "align_idx")
+        N = len(node_ptr) - 1
+        nodes = np.empty((T, N, 3), dtype=np.float64) if want_nodes else None
+        avg = np.empty((N, 3), dtype=np.float64)
+        self._check(self._lib.wisp_com_nodes(
+            self._ctx, _ptr(coords), T, A, _ptr(masses), _ptr(node_ptr), _ptr(atom_idx), N,
+            _ptr(align_idx), len(align_idx), int(bool(atomic)), _ptr(nodes), _ptr(avg)))
+        return nodes, avg
+
+    def traj_alignment_and_averaging(self, coords, masses, node_ptr, atom_idx, align_idx,
+                                     atomic=False, convergence_threshold=1e-5,
+                                     maximum_num_iterations=100):
+        coords = _arr(coords, np.float32, "coords")
+        T, A, _ = coords.shape
+        masses = _arr(masses, np.float64, "masses", (A,))
+        node_ptr = _arr(node_ptr, np.int32, "node_ptr")
+        atom_idx = _arr(atom_idx, np.int32, "atom_idx")
+        align_idx = _arr(align_idx, np.int32, "align_idx")
+        N = len(node_ptr) - 1
+        nodes = np.empty((T, N, 3), dtype=np.float64)
+        avg = np.empty((N, 3), dtype=np.float64)
+        log = np.zeros((max(1, int(maximum_num_iterations)), 3), dtype=np.float64)
+        n_iter = _int(0)
+        self._check(self._lib.wisp_traj_alignment_and_averaging(
+            self._ctx, _ptr(coords), T, A, _ptr(masses), _ptr(node_ptr), _ptr(atom_idx), N,
+            _ptr(align_idx), len(align_idx), int(bool(atomic)), float(convergence_threshold),
+            int(maximum_num_iterations), _ptr(nodes), _ptr(avg), _ptr(log), C.byref(n_iter)))
+        return nodes, avg, [(int(r[0]), float(r[1]), float(r[2])) for r in log[:n_iter.value]]
+
+    def cartesian_covariance(self, nodes, avg):
+        nodes = _arr(nodes, np.float64, "node_trajectory")
+        T, N, _ = nodes.shape
+        avg = _arr(avg, np.float64, "avg_node_positions", (N, 3))
+        cov = np.empty((3 * N, 3 * N), dtype=np.float64)
+        self._check(self._lib.wisp_cartesian_covariance(self._ctx, _ptr(nodes), T, N, _ptr(avg),
+                                                        _ptr(cov)))
+        return cov
+
+    def pearson_from_covariance(self, cov):
+        cov = _arr(cov, np.float64, "cartesian_covariance_matrix")
+        n3 = cov.shape[0]
+        if cov.ndim != 2 or cov.shape[1] != n3 or n3 % 3:
+            raise ValueError("covariance must be (3N, 3N), got %s" % (cov.shape,))
+        N = n3 // 3
+        var = np.empty(N)
+        ncov = np.empty((N, N))
+        corr = np.empty((N, N))
+        self._check(self._lib.wisp_pearson_from_covariance(self._ctx, _ptr(cov), N, _ptr(var),
+                                                           _ptr(ncov), _ptr(corr)))
+        return var, ncov, corr
+
+    def contact_map(self, nodes, cutoff):
+        nodes = _arr(nodes, np.float64, "trajectory_data")
+        T, N, _ = nodes.shape
+        binary = np.empty((N, N), dtype=np.int64)
+        avgdist = np.empty((N, N), dtype=np.float64)
+        self._check(self._lib.wisp_contact_map(self._ctx, _ptr(nodes), T, N, float(cutoff),
+                                               _ptr(binary), _ptr(avgdist)))
+        return binary, avgdist
+
+    def func_pearson(self, corr, contact_map=None):
+        corr = _arr(corr, np.float64, "adjacency_matrix")
+        N = corr.shape[0]
+        cm = None if contact_map is None else _arr(contact_map, np.float64, "contact_map", (N, N))
+        w = np.empty((N, N), dtype=np.float64)
+        self._check(self._lib.wisp_func_pearson(self._ctx, _ptr(corr), N, _ptr(cm), _ptr(w)))
+        return w
+
+    def pipeline(self, coords, masses, node_ptr, atom_idx, align_idx, cutoff=9999.0,
+                 which_map=0, atomic=False, want_nodes=False):
+        """coords -> dict(avg, corr, avgdist, binary, w[, nodes]) in one fused device pass."""
+        coords = _arr(coords, np.float32, "coords")
+        T, A, _ = coords.shape
+        masses = _arr(masses, np.float64, "masses", (A,))
+        node_ptr = _arr(node_ptr, np.int32, "node_ptr")
+        atom_idx = _arr(atom_idx, np.int32, "atom_idx")
+        align_idx = _arr(align_idx, np.int32, "align_idx")
+        N = len(node_ptr) - 1
+        out = dict(avg=np.empty((N, 3)), corr=np.empty((N, N)), avgdist=np.empty((N, N)),
+                   binary=np.empty((N, N), dtype=np.int64), w=np.empty((N, N)))
+        nodes = np.empty((T, N, 3)) if want_nodes else None
+        self._check(self._lib.wisp_pipeline(
+            self._ctx, _ptr(coords), T, A, _ptr(masses), _ptr(node_ptr), _ptr(atom_idx), N,
+            _ptr(align_idx), len(align_idx), int(bool(atomic)), float(cutoff), int(which_map),
+            _ptr(out["avg"]), _ptr(out["corr"]), _ptr(out["avgdist"]), _ptr(out["binary"]),
+            _ptr(out["w"]), _ptr(nodes)))
+        if want_nodes:
+            out["nodes"] = nodes
+        return out
+
+    def apsp(self, w, precision=64, want_pred=True):
+        w = _arr(w, np.float64, "cost matrix")
+        N = w.shape[0]
+        dist = np.empty((N, N), dtype=np.float64)
+        pred = np.empty((N, N), dtype=np.int32) if want_pred else None
+        self._check(self._lib.wisp_apsp(self._ctx, _ptr(w), N, int(precision), _ptr(dist), _ptr(pred)))
+        return dist, pred
+
+    def get_paths(self, w, sources, sinks, number_of_paths, node0_quirk=True, apsp_fp32=False):
+        w = _arr(w, np.float64, "adjacency_matrix")
+        N = w.shape[0]
+        so = _arr(sources, np.int32, "sources")
+        si = _arr(sinks, np.int32, "sinks")
+        flags = (1 if node0_quirk else 0) | (2 if apsp_fp32 else 0)
+        self._check(self._lib.wisp_get_paths(self._ctx, _ptr(w), N, _ptr(so), len(so), _ptr(si),
+                                             len(si), int(number_of_paths), flags))
+        n_paths, n_nodes = _i64(), _i64()
+        self._check(self._lib.wisp_paths_size(self._ctx, C.byref(n_paths), C.byref(n_nodes)))
+        lengths = np.empty(n_paths.value, dtype=np.float64)
+        offsets = np.empty(n_paths.value + 1, dtype=np.int64)
+        nodes = np.empty(n_nodes.value, dtype=np.int32)
+        self._check(self._lib.wisp_paths_fetch(self._ctx, _ptr(lengths), _ptr(offsets), _ptr(nodes)))
+        return [[float(lengths[k])] + [int(x) for x in nodes[offsets[k]:offsets[k + 1]]]
+                for k in range(n_paths.value)]
+
+    def paths_stats(self):
+        s = np.empty(6)
+        self._check(self._lib.wisp_paths_stats(self._ctx, _ptr(s)))
+        return dict(passes=int(s[0]), expansions=int(s[1]), final_cutoff=float(s[2]),
+                    apsp_ms=float(s[3]), enumerate_ms=float(s[4]), host_ms=float(s[5]))
+
+    # ---- device-buffer API (pointers are ints, e.g. torch.Tensor.data_ptr()) -----------
+    def dev_com(self, d_coords, T, A, d_masses, d_node_ptr, d_atom_idx, N, d_align_idx, n_align,
+                d_nodes, d_colsum=None, atomic=False, stream=None):
+        self._check(self._lib.wisp_dev_com(self._ctx, _ptr(d_coords), T, A, _ptr(d_masses),
+                                           _ptr(d_node_ptr), _ptr(d_atom_idx), N, _ptr(d_align_idx),
+                                           n_align, int(bool(atomic)), _ptr(d_nodes), _ptr(d_colsum),
+                                           _ptr(stream)))
+
+    def dev_center(self, d_nodes, T, N, d_mean, stream=None):
+        self._check(self._lib.wisp_dev_center(self._ctx, _ptr(d_nodes), T, N, _ptr(d_mean), _ptr(stream)))
+
+    def dev_colsum(self, d_nodes, T, N, d_colsum, stream=None):
+        self._check(self._lib.wisp_dev_colsum(self._ctx, _ptr(d_nodes), T, N, _ptr(d_colsum), _ptr(stream)))
+
+    def dev_gram(self, d_x, T, ld, n_out, stride, d_out, stream=None):
+        self._check(self._lib.wisp_dev_gram(self._ctx, _ptr(d_x), T, ld, n_out, stride, _ptr(d_out),
+                                            _ptr(stream)))
+
+    def dev_contact_sum(self, d_x, T, N, d_mean, d_out, stream=None):
+        self._check(self._lib.wisp_dev_contact_sum(self._ctx, _ptr(d_x), T, N, _ptr(d_mean),
+                                                   _ptr(d_out), _ptr(stream)))
+
+    def dev_epilogue(self, d_gram, d_dsum, T_total, N, cutoff, which_map, d_var=None, d_ncov=None,
+                     d_corr=None, d_avgdist=None, d_binary=None, d_w=None, stream=None):
+        self._check(self._lib.wisp_dev_epilogue(self._ctx, _ptr(d_gram), _ptr(d_dsum), T_total, N,
+                                                float(cutoff), int(which_map), _ptr(d_var),
+                                                _ptr(d_ncov), _ptr(d_corr), _ptr(d_avgdist),
+                                                _ptr(d_binary), _ptr(d_w), _ptr(stream)))
+
+    def dev_apsp(self, d_w, N, precision, d_dist, d_pred, stream=None):
+        self._check(self._lib.wisp_dev_apsp(self._ctx, _ptr(d_w), N, int(precision), _ptr(d_dist),
+                                            _ptr(d_pred), _ptr(stream)))
+
+    def dev_synth_coords(self, d_coords, t0, T, A, d_atom_base, d_node_of_atom, d_modes, n_modes,
+                         d_coeff, noise_sigma, seed, stream=None):
+        self._check(self._lib.wisp_dev_synth_coords(self._ctx, _ptr(d_coords), t0, T, A,
+                                                    _ptr(d_atom_base), _ptr(d_node_of_atom),
+                                                    _ptr(d_modes), n_modes, _ptr(d_coeff),
+                                                    float(noise_sigma), int(seed), _ptr(stream)))
+
+
+def node_ld(n_nodes):
+    return int(lib().wisp_node_ld(int(n_nodes)))
+
+
+def frames_pad(n_frames):
+    return int(lib().wisp_frames_pad(int(n_frames)))
+
+
+def gram_ld(n_cols):
+    return int(lib().wisp_gram_ld(int(n_cols)))
+
+
+_default_ctx = {}
+
+
+def default_context(device=None):
+    """Process-wide context per device (device defaults to $LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("WISP_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

@@ -1,0 +1,117 @@
+// common.cuh -- shared declarations for libwisp_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+#include <string>
+
+#include "../../include/wisp_b200.h"
+
+#define WISP_ABI_VERSION 1
+
+// ---- layout constants --------------------------------------------------------------------
+// Node tile shared by K2 (Gram) / K3 (contact) / K4 (epilogue): 128 nodes.
+constexpr int kTile = 128;
+// K2 pipeline: one stage holds 24 k-values for both operands (8 frames x 3 components in
+// node-trace mode, 24 frames in plain X^T X mode).  Frames are padded to a multiple of 24.
+constexpr int kFramePad = 24;
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// ---- error handling ----------------------------------------------------------------------
+void wisp_set_error(const char* fmt, ...);
+
+#define WISP_CUDA(call)                                                                  \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            wisp_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,            \
+                           cudaGetErrorString(e__));                                     \
+            return 1;                                                                    \
+        }                                                                                \
+    } while (0)
+
+#define WISP_CHECK(cond, ...)                                                            \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            wisp_set_error(__VA_ARGS__);                                                 \
+            return 1;                                                                    \
+        }                                                                                \
+    } while (0)
+
+#define WISP_TRY(call)                                                                   \
+    do {                                                                                 \
+        int r__ = (call);                                                                \
+        if (r__ != 0) return r__;                                                        \
+    } while (0)
+
+// ---- context -----------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct wisp_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;   // compute
+    cudaStream_t copy_stream = nullptr;
+    int64_t launches = 0;
+    // grow-only scratch buffers, keyed by slot
+    DevBuf scratch[24];
+    // get_paths results
+    std::vector<double> path_len;
+    std::vector<int64_t> path_off;
+    std::vector<int32_t> path_nodes;
+    double path_stats[6] = {0, 0, 0, 0, 0, 0};
+};
+
+int wisp_scratch(wisp_ctx* ctx, int slot, size_t bytes, void** out);   // grow-only device buffer
+static inline cudaStream_t wisp_stream(wisp_ctx* ctx, void* s) {
+    return s ? (cudaStream_t)s : ctx->stream;
+}
+
+enum ScratchSlot {
+    SCR_GRAM_PART = 0, SCR_CONTACT_PART, SCR_COLSUM_PART, SCR_X, SCR_COORDS0, SCR_COORDS1,
+    SCR_APSP_D, SCR_APSP_P, SCR_ARENA, SCR_ALIGN,
+    SCR_MISC0, SCR_MISC1, SCR_MISC2, SCR_MISC3, SCR_MISC4, SCR_MISC5, SCR_MISC6, SCR_MISC7,
+    SCR_MISC8, SCR_MISC9, SCR_COUNT
+};
+
+// ---- kernel launchers (one per .cu) -------------------------------------------------------
+int launch_com(wisp_ctx* ctx, const float* d_coords, int64_t T, int A, const double* d_masses,
+               const int32_t* d_node_ptr, const int32_t* d_atom_idx, int N,
+               const int32_t* d_align_idx, int n_align, int atomic, double* d_nodes, int64_t ld,
+               int64_t row0, cudaStream_t st, float* d_align_out = nullptr);
+int launch_colsum_f32(wisp_ctx* ctx, const float* d_x, int64_t T, int64_t ld, int64_t ncols,
+                      double* d_colsum, cudaStream_t st);
+int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* d_nodes, int64_t ld,
+                            int N, int64_t T, double threshold, int max_iter, double* d_work,
+                            double* h_avg_nodes, double* log, int* n_iter_out, cudaStream_t st);
+int launch_colsum(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int64_t ncols,
+                  double* d_colsum, cudaStream_t st);
+int launch_center(wisp_ctx* ctx, double* d_x, int64_t T, int64_t ld, int64_t ncols,
+                  const double* d_mean, cudaStream_t st);
+int launch_gram(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_out, int stride,
+                double* d_out, cudaStream_t st);
+int launch_reduce_partials(wisp_ctx* ctx, const double* part, int n_seg, int64_t n_pad,
+                           double* out, int tile_r, int tile_c, cudaStream_t st);
+int wisp_pick_segments(int items_per_seg, int stages_total, int sm_count, int min_stages);
+int launch_contact_sum(wisp_ctx* ctx, const double* d_x, int64_t T, int N, int64_t ld,
+                       const double* d_mean, double* d_out, cudaStream_t st);
+int launch_epilogue(wisp_ctx* ctx, const double* d_gram, const double* d_dsum, int64_t T_total,
+                    int N, double cutoff, int which_map, double* d_var, double* d_ncov,
+                    double* d_corr, double* d_avgdist, int64_t* d_binary, double* d_w,
+                    cudaStream_t st);
+int launch_cov_finalize(wisp_ctx* ctx, const double* d_p, int64_t ldp, int n3, int64_t T,
+                        const double* d_avg, const double* d_delta, double* d_cov,
+                        cudaStream_t st);
+int launch_pearson_from_cov(wisp_ctx* ctx, const double* d_cov, int N, double* d_var,
+                            double* d_ncov, double* d_corr, cudaStream_t st);
+int launch_func_pearson(wisp_ctx* ctx, const double* d_corr, int N, const double* d_map,
+                        double* d_w, cudaStream_t st);
+int launch_apsp(wisp_ctx* ctx, const double* d_w, int N, int precision, double* d_dist,
+                int32_t* d_pred, cudaStream_t st);

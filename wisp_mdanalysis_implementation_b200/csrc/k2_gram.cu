@@ -1,0 +1,285 @@
+// K2 -- correlation contraction on the FP64 tensor pipe (DMMA m8n8k4), sm_100a.
+//
+// Replaces the reference's T rank-1 updates of a 3N x 3N matrix followed by N(N+1)/2
+// np.trace calls (trajectory_analysis_functions.py:163-170 +
+// adjacency_matrix_functions.py:34-46) by ONE dense contraction over the centred node
+// trajectory X [Tpad][ld] (row = frame, column = 3*node + component):
+//
+//   stride 3 (node Gram):   OUT[i][j] = sum_t sum_c X[t][3i+c] * X[t][3j+c]
+//   stride 1 (full cov.):   OUT[p][q] = sum_t       X[t][p]    * X[t][q]
+//
+// Only upper-triangular 128x128 output tiles are computed (OUT is symmetric).
+//
+// Structure per CTA (one 128x128 output tile x one frame segment):
+//   * warp 8 is the producer: per stage it issues one cp.async.bulk (TMA bulk copy, SASS
+//     UBLKCP) per frame row and operand into a padded shared-memory tile, completion
+//     tracked by an mbarrier (expect_tx);  4-stage ring, full/empty mbarriers;
+//   * warps 0-7 are consumers: each owns a 32x64 sub-tile = 4x8 DMMA tiles (64 FP64
+//     accumulators per lane), reads A/B fragments straight from the staged rows -- the
+//     (frame, 3*node+c) layout of the trajectory IS a valid k-major operand, no transpose --
+//     with row padding chosen so the 8-byte fragment loads are bank-conflict free
+//     (ld = 12 mod 16 doubles for stride 3, 4 mod 16 for stride 1);
+//   * frames are split into S segments so that (#tile pairs x S) fills the 148 SMs; the S
+//     partial tiles are summed in fixed order by a second kernel (deterministic).
+//
+// Algorithmic work: 2 * 128 * 128 * 24 flop per stage per CTA; executed MMA flop for the
+// whole launch = 2 * (#upper tiles * 128^2) * K,  K = STRIDE-independent 3*Tpad (stride 3)
+// or Tpad (stride 1).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kKPerStage = 24;
+constexpr int kConsumerWarps = 8;
+constexpr int kThreads = (kConsumerWarps + 1) * 32;
+
+template <int STRIDE>
+struct GramCfg {
+    static constexpr int kRowDoubles = kTile * STRIDE;                  // copied per frame/operand
+    static constexpr int kLd = kRowDoubles + (STRIDE == 3 ? 12 : 4);    // padded smem row
+    static constexpr int kFrames = kKPerStage / STRIDE;                 // frames per stage
+    static constexpr int kOperandDoubles = kFrames * kLd;
+    static constexpr int kStageBytes = 2 * kOperandDoubles * 8;
+    static constexpr uint32_t kTxBytes = 2u * kFrames * kRowDoubles * 8u;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStages * 8 + 128;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int STRIDE>
+__global__ void __launch_bounds__(kThreads, 1)
+gram_dmma_kernel(const double* __restrict__ x, int64_t ld, int n_tiles, int stages_total,
+                 int n_seg, double* __restrict__ out, int64_t out_ld) {
+    using Cfg = GramCfg<STRIDE>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stage_base = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * Cfg::kStageBytes);
+    uint64_t* empty = full + kStages;
+
+    // tile pair (bi <= bj) from the linear upper-triangular index
+    int bi = 0, rem = blockIdx.x;
+    while (rem >= n_tiles - bi) { rem -= n_tiles - bi; ++bi; }
+    const int bj = bi + rem;
+    const int seg = blockIdx.y;
+    const int g0 = (int)((int64_t)stages_total * seg / n_seg);
+    const int g1 = (int)((int64_t)stages_total * (seg + 1) / n_seg);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ---------------- producer warp: TMA bulk row copies ----------------
+        const double* srcA = x + (int64_t)STRIDE * kTile * bi;
+        const double* srcB = x + (int64_t)STRIDE * kTile * bj;
+        int it = 0;
+        for (int g = g0; g < g1; ++g, ++it) {
+            const int slot = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(&empty[slot], ph ^ 1);
+            if (lane == 0) mbar_expect_tx(&full[slot], Cfg::kTxBytes);
+            __syncwarp();
+            double* sA = stage_base + (size_t)slot * 2 * Cfg::kOperandDoubles;
+            double* sB = sA + Cfg::kOperandDoubles;
+            const int64_t f0 = (int64_t)g * Cfg::kFrames;
+            for (int r = lane; r < 2 * Cfg::kFrames; r += 32) {
+                const int op = r / Cfg::kFrames;
+                const int f = r - op * Cfg::kFrames;
+                const double* src = (op ? srcB : srcA) + (f0 + f) * ld;
+                double* dst = (op ? sB : sA) + f * Cfg::kLd;
+                bulk_g2s(dst, src, Cfg::kRowDoubles * 8, &full[slot]);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumer warps: DMMA ----------------
+    const int wm = warp >> 1;   // 0..3 -> 32 output rows each
+    const int wn = warp & 1;    // 0..1 -> 64 output cols each
+    const int r = lane >> 2;    // fragment row / col
+    const int kk = lane & 3;    // fragment k
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+
+    const int offA = kk * Cfg::kLd + STRIDE * (32 * wm + r);
+    const int offB = kk * Cfg::kLd + STRIDE * (64 * wn + r);
+
+    int it = 0;
+    for (int g = g0; g < g1; ++g, ++it) {
+        const int slot = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full[slot], ph);
+        const double* sA = stage_base + (size_t)slot * 2 * Cfg::kOperandDoubles;
+        const double* sB = sA + Cfg::kOperandDoubles;
+        const double* pa = sA + offA;
+        const double* pb = sB + offB;
+#pragma unroll
+        for (int ks = 0; ks < kKPerStage / 4; ++ks) {
+            // stride 3: k-step = 4 frames of one component; stride 1: 4 frames
+            const int fo = (STRIDE == 3) ? (ks / 3) * 4 : ks * 4;
+            const int co = (STRIDE == 3) ? (ks % 3) : 0;
+            double a[4], b[8];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) a[mb] = pa[fo * Cfg::kLd + mb * 8 * STRIDE + co];
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) b[nb] = pb[fo * Cfg::kLd + nb * 8 * STRIDE + co];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 8; ++nb)
+                    dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+    }
+
+    // ---------------- epilogue: accumulators -> partial output tile ----------------
+    double* o = out + (size_t)seg * out_ld * out_ld;
+    const int64_t row0 = (int64_t)kTile * bi + 32 * wm + r;
+    const int64_t col0 = (int64_t)kTile * bj + 64 * wn + 2 * kk;
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            double2 v = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+            *reinterpret_cast<double2*>(o + (row0 + 8 * mb) * out_ld + col0 + 8 * nb) = v;
+        }
+}
+
+// out[r][c] = sum_s part[s][r][c] for upper tiles (fixed order -> deterministic)
+__global__ void reduce_partials_kernel(const double* __restrict__ part, int n_seg, int64_t n_pad,
+                                       double* __restrict__ out, int tile_r, int tile_c) {
+    const int64_t total = n_pad * n_pad;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / n_pad, c = e - r * n_pad;
+        // keep every element that any upper tile (row tile tile_r, col tile tile_c) covers
+        if ((c / tile_c) * tile_c + tile_c - 1 < (r / tile_r) * tile_r) continue;
+        double s = 0.0;
+        for (int k = 0; k < n_seg; ++k) s += part[(size_t)k * total + e];
+        out[e] = s;
+    }
+}
+
+int pick_segments(int items_per_seg, int stages_total, int sm_count, int min_stages) {
+    int best = 1;
+    double best_eff = 0.0;
+    const int max_seg = 64;
+    for (int s = 1; s <= max_seg; ++s) {
+        if (s > 1 && stages_total / s < min_stages) break;
+        const int64_t items = (int64_t)items_per_seg * s;
+        const int64_t waves = (items + sm_count - 1) / sm_count;
+        const double eff = (double)items / (double)(waves * sm_count);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    }
+    return best;
+}
+
+}  // namespace
+
+int wisp_pick_segments(int items_per_seg, int stages_total, int sm_count, int min_stages) {
+    return pick_segments(items_per_seg, stages_total, sm_count, min_stages);
+}
+
+int launch_reduce_partials(wisp_ctx* ctx, const double* part, int n_seg, int64_t n_pad,
+                           double* out, int tile_r, int tile_c, cudaStream_t st) {
+    const int threads = 256;
+    int blocks = (int)std::min<int64_t>((n_pad * n_pad + threads - 1) / threads,
+                                        (int64_t)ctx->sm_count * 16);
+    reduce_partials_kernel<<<blocks, threads, 0, st>>>(part, n_seg, n_pad, out, tile_r, tile_c);
+    ctx->launches++;
+    WISP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_gram(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_out, int stride,
+                double* d_out, cudaStream_t st) {
+    WISP_CHECK(stride == 1 || stride == 3, "gram: stride must be 1 or 3 (got %d)", stride);
+    WISP_CHECK(T > 0 && n_out > 0, "gram: empty input (T=%lld, n=%d)", (long long)T, n_out);
+    const int n_tiles = (int)((n_out + kTile - 1) / kTile);
+    const int64_t n_pad = (int64_t)n_tiles * kTile;
+    WISP_CHECK((int64_t)stride * n_pad <= ld, "gram: ld=%lld too small for %d outputs x stride %d",
+               (long long)ld, n_out, stride);
+    const int64_t Tpad = round_up(T, kFramePad);
+    const int frames_per_stage = kKPerStage / stride;
+    const int stages_total = (int)(Tpad / frames_per_stage);
+    const int n_pairs = n_tiles * (n_tiles + 1) / 2;
+    const int n_seg = pick_segments(n_pairs, stages_total, ctx->sm_count, 8);
+
+    double* part = d_out;
+    if (n_seg > 1) {
+        void* p = nullptr;
+        WISP_TRY(wisp_scratch(ctx, SCR_GRAM_PART, (size_t)n_seg * n_pad * n_pad * 8, &p));
+        part = (double*)p;
+    }
+    dim3 grid(n_pairs, n_seg);
+    if (stride == 3) {
+        WISP_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<3>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       GramCfg<3>::kSmemBytes));
+        gram_dmma_kernel<3><<<grid, kThreads, GramCfg<3>::kSmemBytes, st>>>(
+            d_x, ld, n_tiles, stages_total, n_seg, part, n_pad);
+    } else {
+        WISP_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<1>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       GramCfg<1>::kSmemBytes));
+        gram_dmma_kernel<1><<<grid, kThreads, GramCfg<1>::kSmemBytes, st>>>(
+            d_x, ld, n_tiles, stages_total, n_seg, part, n_pad);
+    }
+    ctx->launches++;
+    WISP_CUDA(cudaGetLastError());
+    if (n_seg > 1) WISP_TRY(launch_reduce_partials(ctx, part, n_seg, n_pad, d_out, kTile, kTile, st));
+    return 0;
+}

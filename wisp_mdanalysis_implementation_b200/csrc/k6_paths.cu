@@ -1,0 +1,453 @@
+// K6 -- suboptimal source->sink path enumeration on the GPU + the get_paths contract.
+//
+// Replaces network_analysis_functions.py:12-214 (get_paths).  Verified behaviour
+// (SURVEY.md Appendix A): seed = first strict minimum over (source, sink) pairs of the
+// left-to-right float64 length of a shortest path; cutoff starts there and grows by repeated
+// "+= 0.1"; each pass collects, per pair, ALL simple paths with LR length <= cutoff (sink
+// only as last node; paths whose 2nd node is 0 are never produced when source != 0 -- the
+// reference's `node in [length, ...]` membership test), sorted by (length, nodes); a pass
+// list is de-duplicated with a path equal to its reverse; the loop stops after the first
+// pass with >= K entries; the union over passes plus the seed is de-duplicated, sorted, and
+// truncated to K only when the last pass did not count exactly K (K+1 results possible).
+//
+// The reference expands every partial path below the cutoff in Python lists with no
+// distance-to-sink bound.  Here each pass is two kernels over the APSP result of K5:
+//   expand_level_kernel  level-synchronous expansion of the first few hops (one thread per
+//                        partial path) until there are enough independent prefixes;
+//   dfs_kernel           one thread per prefix runs an explicit-stack DFS pruned by the
+//                        admissible bound  len + w(u,v) + dist(v, sink) <= cutoff (1 + 1e-9),
+//                        with the exact float64 LR length for the final `<= cutoff` test.
+// Paths are emitted through atomically reserved slots; the host sorts, so the result does
+// not depend on emission order.
+#include "common.cuh"
+#include <algorithm>
+#include <chrono>
+#include <set>
+
+namespace {
+
+constexpr int kMaxLen = 96;          // longest path (nodes) the enumerator supports
+constexpr int kTargetPrefixes = 16384;
+constexpr int kMaxExpandLevels = 8;
+
+struct EnumParams {
+    const int32_t* adj_ptr;
+    const int32_t* adj_idx;
+    const double* adj_w;
+    const double* dist;      // APSP distances [N][N] (row t = distances to sink t)
+    const int32_t* pairs;    // [P][2]
+    int N;
+    double cutoff;
+    double bound;
+    int quirk;
+    // outputs
+    int32_t* out_count;      // [0] n paths, [1] n node entries, [2] overflow flags
+    unsigned long long* expansions;
+    double* out_len;
+    int32_t* out_pair;
+    int32_t* out_off;        // node offset of path
+    int32_t* out_n;          // nodes in path
+    int32_t* out_nodes;
+    int cap_paths;
+    int cap_nodes;
+};
+
+__device__ __forceinline__ void emit_path(const EnumParams& P, int pair, const int32_t* nodes,
+                                          int depth, int last, double len) {
+    const int slot = atomicAdd(&P.out_count[0], 1);
+    const int off = atomicAdd(&P.out_count[1], depth + 1);
+    if (slot >= P.cap_paths || off + depth + 1 > P.cap_nodes) {
+        atomicOr(&P.out_count[2], 1);
+        return;
+    }
+    P.out_len[slot] = len;
+    P.out_pair[slot] = pair;
+    P.out_off[slot] = off;
+    P.out_n[slot] = depth + 1;
+    for (int k = 0; k < depth; ++k) P.out_nodes[off + k] = nodes[k];
+    P.out_nodes[off + depth] = last;
+}
+
+// frontier record layout: len[cap], meta[cap][2] = (pair, depth), nodes[cap][kMaxLen]
+__global__ void expand_level_kernel(EnumParams P, const double* __restrict__ fin_len,
+                                    const int32_t* __restrict__ fin_meta,
+                                    const int32_t* __restrict__ fin_nodes, int n_in,
+                                    double* __restrict__ fout_len, int32_t* __restrict__ fout_meta,
+                                    int32_t* __restrict__ fout_nodes, int32_t* fout_count,
+                                    int cap_out) {
+    const int rec = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rec >= n_in) return;
+    const int pair = fin_meta[2 * rec], depth = fin_meta[2 * rec + 1];
+    const int s = P.pairs[2 * pair], t = P.pairs[2 * pair + 1];
+    const int32_t* nodes = fin_nodes + (size_t)rec * kMaxLen;
+    const double len = fin_len[rec];
+    const int u = nodes[depth - 1];
+    const double* dt = P.dist + (size_t)t * P.N;
+    unsigned long long nexp = 0;
+    for (int e = P.adj_ptr[u]; e < P.adj_ptr[u + 1]; ++e) {
+        const int v = P.adj_idx[e];
+        bool on = false;
+        for (int k = 0; k < depth; ++k) on |= (nodes[k] == v);
+        if (on) continue;
+        if (P.quirk && depth == 1 && v == 0 && s != 0) continue;
+        const double nl = len + P.adj_w[e];
+        ++nexp;
+        if (!(nl + dt[v] <= P.bound)) continue;
+        if (v == t) {
+            if (nl <= P.cutoff) emit_path(P, pair, nodes, depth, v, nl);
+            continue;
+        }
+        if (nl > P.cutoff) continue;
+        if (depth + 1 >= kMaxLen) { atomicOr(&P.out_count[2], 2); continue; }
+        const int slot = atomicAdd(fout_count, 1);
+        if (slot >= cap_out) { atomicOr(&P.out_count[2], 4); continue; }
+        fout_len[slot] = nl;
+        fout_meta[2 * slot] = pair;
+        fout_meta[2 * slot + 1] = depth + 1;
+        int32_t* dst = fout_nodes + (size_t)slot * kMaxLen;
+        for (int k = 0; k < depth; ++k) dst[k] = nodes[k];
+        dst[depth] = v;
+    }
+    atomicAdd(P.expansions, nexp);
+}
+
+__global__ void dfs_kernel(EnumParams P, const double* __restrict__ f_len,
+                           const int32_t* __restrict__ f_meta, const int32_t* __restrict__ f_nodes,
+                           int n_in) {
+    const int rec = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rec >= n_in) return;
+    const int pair = f_meta[2 * rec], d0 = f_meta[2 * rec + 1];
+    const int s = P.pairs[2 * pair], t = P.pairs[2 * pair + 1];
+    const double* dt = P.dist + (size_t)t * P.N;
+    int32_t nodes[kMaxLen];
+    int32_t cur[kMaxLen];
+    double lens[kMaxLen];
+    for (int k = 0; k < d0; ++k) nodes[k] = f_nodes[(size_t)rec * kMaxLen + k];
+    lens[d0 - 1] = f_len[rec];
+    cur[d0 - 1] = P.adj_ptr[nodes[d0 - 1]];
+    int depth = d0;
+    unsigned long long nexp = 0;
+    while (depth >= d0) {
+        const int u = nodes[depth - 1];
+        const int e = cur[depth - 1];
+        if (e >= P.adj_ptr[u + 1]) { --depth; continue; }
+        cur[depth - 1] = e + 1;
+        const int v = P.adj_idx[e];
+        bool on = false;
+        for (int k = 0; k < depth; ++k) on |= (nodes[k] == v);
+        if (on) continue;
+        if (P.quirk && depth == 1 && v == 0 && s != 0) continue;
+        const double nl = lens[depth - 1] + P.adj_w[e];
+        ++nexp;
+        if (!(nl + dt[v] <= P.bound)) continue;
+        if (v == t) {
+            if (nl <= P.cutoff) emit_path(P, pair, nodes, depth, v, nl);
+            continue;
+        }
+        if (nl > P.cutoff) continue;
+        if (depth + 1 >= kMaxLen) { atomicOr(&P.out_count[2], 2); continue; }
+        nodes[depth] = v;
+        lens[depth] = nl;
+        cur[depth] = P.adj_ptr[v];
+        ++depth;
+    }
+    atomicAdd(P.expansions, nexp);
+}
+
+struct HostPath {
+    double len;
+    std::vector<int32_t> nodes;
+};
+
+inline bool path_less(const HostPath& a, const HostPath& b) {
+    // Python list comparison of [len, n0, n1, ...]
+    if (a.len != b.len) return a.len < b.len;
+    return a.nodes < b.nodes;
+}
+
+// remove_redundant_paths (:157-174): same number of nodes and same node sequence after
+// orienting each so that first >= last; first occurrence wins.
+void dedupe(std::vector<HostPath>& v) {
+    if (v.size() == 1) return;
+    std::set<std::vector<int32_t>> seen;
+    std::vector<HostPath> out;
+    out.reserve(v.size());
+    for (auto& p : v) {
+        std::vector<int32_t> key = p.nodes;
+        if (key.front() < key.back()) std::reverse(key.begin(), key.end());
+        if (seen.insert(key).second) out.push_back(std::move(p));
+    }
+    v.swap(out);
+}
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(
+               std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+extern "C" int wisp_get_paths(wisp_ctx* ctx, const double* w, int N, const int32_t* sources,
+                              int n_sources, const int32_t* sinks, int n_sinks,
+                              int number_of_paths, int flags) {
+    WISP_CHECK(ctx && w && N > 1, "get_paths: bad arguments");
+    WISP_CHECK(n_sources > 0 && n_sinks > 0, "get_paths: empty source or sink list");
+    WISP_CHECK(number_of_paths >= 1, "get_paths: number_of_paths must be >= 1");
+    const int quirk = (flags & 1) ? 1 : 0;
+    const int precision = (flags & 2) ? 32 : 64;
+    cudaStream_t st = ctx->stream;
+    for (int i = 0; i < n_sources; ++i) WISP_CHECK(sources[i] >= 0 && sources[i] < N, "get_paths: source %d out of range", sources[i]);
+    for (int i = 0; i < n_sinks; ++i) WISP_CHECK(sinks[i] >= 0 && sinks[i] < N, "get_paths: sink %d out of range", sinks[i]);
+
+    // ---- graph: non-zero entry <=> edge (networkx 1.x Graph(data=W), :20) ----
+    std::vector<int32_t> adj_ptr(N + 1, 0), adj_idx;
+    std::vector<double> adj_w;
+    for (int u = 0; u < N; ++u) {
+        for (int v = 0; v < N; ++v) {
+            const double x = w[(size_t)u * N + v];
+            WISP_CHECK(x == x, "get_paths: NaN weight at (%d,%d)", u, v);
+            if (x != 0.0 && u != v) {
+                WISP_CHECK(x > -1e-12, "get_paths: negative weight %g at (%d,%d)", x, u, v);
+                adj_idx.push_back(v);
+                adj_w.push_back(x);
+            }
+        }
+        adj_ptr[u + 1] = (int32_t)adj_idx.size();
+    }
+    const size_t E = adj_idx.size();
+    // upper bound on the length of any finite simple path: every node contributes at most
+    // its heaviest finite edge.  Past it, no new path can ever appear.
+    double max_simple_len = 0.0;
+    for (int u = 0; u < N; ++u) {
+        double m = 0.0;
+        for (int e = adj_ptr[u]; e < adj_ptr[u + 1]; ++e)
+            if (adj_w[e] < 1e300 && adj_w[e] > m) m = adj_w[e];
+        max_simple_len += m;
+    }
+
+    // ---- APSP on the device (K5) ----
+    double t0 = now_ms();
+    void *d_w, *d_dist, *d_pred;
+    WISP_TRY(wisp_scratch(ctx, SCR_MISC2, (size_t)N * N * 8, &d_w));
+    WISP_TRY(wisp_scratch(ctx, SCR_MISC3, (size_t)N * N * 8, &d_dist));
+    WISP_TRY(wisp_scratch(ctx, SCR_MISC4, (size_t)N * N * 4, &d_pred));
+    WISP_CUDA(cudaMemcpyAsync(d_w, w, (size_t)N * N * 8, cudaMemcpyHostToDevice, st));
+    WISP_TRY(launch_apsp(ctx, (const double*)d_w, N, precision, (double*)d_dist, (int32_t*)d_pred, st));
+    WISP_CUDA(cudaStreamSynchronize(st));
+    const double apsp_ms = now_ms() - t0;
+
+    // ---- pairs in the reference's loop order (:27-29), seed path (:25-36) ----
+    std::vector<int32_t> pairs;
+    for (int a = 0; a < n_sources; ++a)
+        for (int b = 0; b < n_sinks; ++b)
+            if (sources[a] != sinks[b]) { pairs.push_back(sources[a]); pairs.push_back(sinks[b]); }
+    const int n_pairs = (int)pairs.size() / 2;
+    WISP_CHECK(n_pairs > 0, "get_paths: no (source, sink) pair with source != sink");
+
+    double shortest_length = 99999999.999;
+    std::vector<int32_t> shortest_path;
+    std::vector<int32_t> pred_row(N);
+    std::vector<double> dist_row(N);
+    int last_row = -1;
+    for (int p = 0; p < n_pairs; ++p) {
+        const int s = pairs[2 * p], t = pairs[2 * p + 1];
+        if (s != last_row) {
+            WISP_CUDA(cudaMemcpy(pred_row.data(), (int32_t*)d_pred + (size_t)s * N, (size_t)N * 4, cudaMemcpyDeviceToHost));
+            WISP_CUDA(cudaMemcpy(dist_row.data(), (double*)d_dist + (size_t)s * N, (size_t)N * 8, cudaMemcpyDeviceToHost));
+            last_row = s;
+        }
+        WISP_CHECK(dist_row[t] < 1e300 && pred_row[t] >= 0, "get_paths: no path between node %d and node %d", s, t);
+        std::vector<int32_t> sp;
+        sp.push_back(t);
+        while (sp.back() != s) {
+            const int pr = pred_row[sp.back()];
+            WISP_CHECK(pr >= 0 && (int)sp.size() <= N, "get_paths: broken predecessor chain %d -> %d", s, t);
+            sp.push_back(pr);
+        }
+        std::reverse(sp.begin(), sp.end());
+        double length = 0.0;
+        for (size_t k = 0; k + 1 < sp.size(); ++k) length += w[(size_t)sp[k] * N + sp[k + 1]];
+        if (length < shortest_length) { shortest_length = length; shortest_path = sp; }
+    }
+
+    std::vector<HostPath> paths;
+    paths.push_back(HostPath{shortest_length, shortest_path});
+    int64_t num_paths = 1;
+    double cutoff = shortest_length;
+
+    // ---- device buffers for the enumeration ----
+    void *d_adj_ptr, *d_adj_idx, *d_adj_w, *d_pairs, *d_cnt;
+    WISP_TRY(wisp_scratch(ctx, SCR_MISC6, E * 8 + 16, &d_adj_w));
+    WISP_TRY(wisp_scratch(ctx, SCR_MISC7, (size_t)n_pairs * 8 + 256, &d_pairs));
+    d_cnt = (char*)d_pairs + round_up((size_t)n_pairs * 8, 64);     // 4 x int32 + 1 x u64 + frontier counts
+    WISP_TRY(wisp_scratch(ctx, SCR_MISC5, round_up((size_t)(N + 1) * 4, 16) + E * 4 + 64, &d_adj_ptr));
+    d_adj_idx = (char*)d_adj_ptr + round_up((size_t)(N + 1) * 4, 16);
+    WISP_CUDA(cudaMemcpyAsync(d_adj_ptr, adj_ptr.data(), (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (E) {
+        WISP_CUDA(cudaMemcpyAsync(d_adj_idx, adj_idx.data(), E * 4, cudaMemcpyHostToDevice, st));
+        WISP_CUDA(cudaMemcpyAsync(d_adj_w, adj_w.data(), E * 8, cudaMemcpyHostToDevice, st));
+    }
+    WISP_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
+
+    int cap_paths = std::max(4096, 8 * number_of_paths * std::max(1, n_pairs));
+    int cap_front = std::max(4 * kTargetPrefixes, 4 * n_pairs);
+    double enum_ms = 0.0, host_ms = 0.0;
+    unsigned long long expansions_total = 0;
+    int passes = 0;
+
+    while (num_paths < number_of_paths) {                                    // :56
+        std::vector<HostPath> temp_paths;
+        for (;;) {   // retry loop on capacity overflow
+            double te = now_ms();
+            const int cap_nodes = cap_paths * 24;
+            void *d_out, *d_front;
+            const size_t out_bytes = (size_t)cap_paths * (8 + 4 + 4 + 4) + (size_t)cap_nodes * 4 + 256;
+            WISP_TRY(wisp_scratch(ctx, SCR_MISC8, out_bytes, &d_out));
+            const size_t front_rec = 8 + 8 + (size_t)kMaxLen * 4;
+            WISP_TRY(wisp_scratch(ctx, SCR_MISC9, 2 * (size_t)cap_front * front_rec + 256, &d_front));
+            EnumParams P;
+            P.adj_ptr = (const int32_t*)d_adj_ptr; P.adj_idx = (const int32_t*)d_adj_idx;
+            P.adj_w = (const double*)d_adj_w; P.dist = (const double*)d_dist;
+            P.pairs = (const int32_t*)d_pairs; P.N = N; P.cutoff = cutoff;
+            P.bound = cutoff + 1e-9 * std::max(1.0, std::fabs(cutoff));
+            P.quirk = quirk;
+            int32_t* cnt = (int32_t*)d_cnt;                  // [0..2] out counters, [4],[5] frontier counts
+            P.out_count = cnt;
+            P.expansions = (unsigned long long*)(cnt + 8);
+            P.out_len = (double*)d_out;
+            P.out_pair = (int32_t*)(P.out_len + cap_paths);
+            P.out_off = P.out_pair + cap_paths;
+            P.out_n = P.out_off + cap_paths;
+            P.out_nodes = P.out_n + cap_paths;
+            P.cap_paths = cap_paths; P.cap_nodes = cap_nodes;
+            WISP_CUDA(cudaMemsetAsync(d_cnt, 0, 64, st));
+            // frontier double buffer
+            char* fb = (char*)d_front;
+            double* f_len[2]; int32_t* f_meta[2]; int32_t* f_nodes[2];
+            for (int b = 0; b < 2; ++b) {
+                f_len[b] = (double*)fb; fb += (size_t)cap_front * 8;
+                f_meta[b] = (int32_t*)fb; fb += (size_t)cap_front * 8;
+                f_nodes[b] = (int32_t*)fb; fb += (size_t)cap_front * kMaxLen * 4;
+            }
+            // seed frontier: one record [s] per pair
+            {
+                std::vector<double> hl(n_pairs, 0.0);
+                std::vector<int32_t> hm(2 * n_pairs), hn((size_t)n_pairs * kMaxLen, 0);
+                for (int p = 0; p < n_pairs; ++p) { hm[2 * p] = p; hm[2 * p + 1] = 1; hn[(size_t)p * kMaxLen] = pairs[2 * p]; }
+                WISP_CUDA(cudaMemcpyAsync(f_len[0], hl.data(), (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
+                WISP_CUDA(cudaMemcpyAsync(f_meta[0], hm.data(), (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
+                WISP_CUDA(cudaMemcpyAsync(f_nodes[0], hn.data(), (size_t)n_pairs * kMaxLen * 4, cudaMemcpyHostToDevice, st));
+                WISP_CUDA(cudaStreamSynchronize(st));
+            }
+            int n_front = n_pairs, cur = 0;
+            bool overflow = false;
+            for (int level = 0; level < kMaxExpandLevels && n_front > 0 && n_front < kTargetPrefixes; ++level) {
+                WISP_CUDA(cudaMemsetAsync(cnt + 4, 0, 4, st));
+                expand_level_kernel<<<(n_front + 127) / 128, 128, 0, st>>>(
+                    P, f_len[cur], f_meta[cur], f_nodes[cur], n_front, f_len[cur ^ 1], f_meta[cur ^ 1],
+                    f_nodes[cur ^ 1], cnt + 4, cap_front);
+                ctx->launches++;
+                int32_t hc[8];
+                WISP_CUDA(cudaMemcpyAsync(hc, cnt, 32, cudaMemcpyDeviceToHost, st));
+                WISP_CUDA(cudaStreamSynchronize(st));
+                if (hc[2] & 4) { overflow = true; cap_front *= 4; break; }
+                if (hc[2] & 1) { overflow = true; cap_paths *= 4; break; }
+                n_front = hc[4];
+                cur ^= 1;
+            }
+            if (!overflow && n_front > 0) {
+                dfs_kernel<<<(n_front + 63) / 64, 64, 0, st>>>(P, f_len[cur], f_meta[cur], f_nodes[cur], n_front);
+                ctx->launches++;
+            }
+            int32_t hc[8];
+            unsigned long long hexp = 0;
+            if (!overflow) {
+                WISP_CUDA(cudaMemcpyAsync(hc, cnt, 32, cudaMemcpyDeviceToHost, st));
+                WISP_CUDA(cudaMemcpyAsync(&hexp, cnt + 8, 8, cudaMemcpyDeviceToHost, st));
+                WISP_CUDA(cudaStreamSynchronize(st));
+                WISP_CUDA(cudaGetLastError());
+                WISP_CHECK(!(hc[2] & 2), "get_paths: a path exceeded the supported length of %d nodes", kMaxLen);
+                if (hc[2] & 1) { overflow = true; cap_paths = std::max(cap_paths * 4, hc[0] + 1024); }
+            }
+            if (overflow) continue;
+            expansions_total += hexp;
+            const int np = hc[0], nn = hc[1];
+            std::vector<double> hl(np);
+            std::vector<int32_t> hp(np), ho(np), hn(np), hnodes(nn);
+            if (np) {
+                WISP_CUDA(cudaMemcpy(hl.data(), P.out_len, (size_t)np * 8, cudaMemcpyDeviceToHost));
+                WISP_CUDA(cudaMemcpy(hp.data(), P.out_pair, (size_t)np * 4, cudaMemcpyDeviceToHost));
+                WISP_CUDA(cudaMemcpy(ho.data(), P.out_off, (size_t)np * 4, cudaMemcpyDeviceToHost));
+                WISP_CUDA(cudaMemcpy(hn.data(), P.out_n, (size_t)np * 4, cudaMemcpyDeviceToHost));
+                WISP_CUDA(cudaMemcpy(hnodes.data(), P.out_nodes, (size_t)nn * 4, cudaMemcpyDeviceToHost));
+            }
+            enum_ms += now_ms() - te;
+            double th = now_ms();
+            // per pair: sort by (length, nodes) (:145), concatenate in pair order
+            std::vector<std::vector<HostPath>> per_pair(n_pairs);
+            for (int k = 0; k < np; ++k) {
+                HostPath hpth;
+                hpth.len = hl[k];
+                hpth.nodes.assign(hnodes.begin() + ho[k], hnodes.begin() + ho[k] + hn[k]);
+                per_pair[hp[k]].push_back(std::move(hpth));
+            }
+            for (int p = 0; p < n_pairs; ++p) {
+                std::sort(per_pair[p].begin(), per_pair[p].end(), path_less);
+                for (auto& q : per_pair[p]) temp_paths.push_back(std::move(q));
+            }
+            host_ms += now_ms() - th;
+            break;
+        }
+        double th = now_ms();
+        if (temp_paths.size() != 1) dedupe(temp_paths);                      // :157
+        num_paths = (int64_t)temp_paths.size();                              // :179
+        for (auto& q : temp_paths) paths.push_back(q);
+        cutoff += 0.1;                                                       // :187
+        ++passes;
+        host_ms += now_ms() - th;
+        WISP_CHECK(passes < 100000, "get_paths: fewer than %d paths exist between the selections", number_of_paths);
+        // the reference never terminates when fewer than K simple paths exist (App. A.6):
+        // detect exhaustion (cutoff beyond any simple path) and fail loudly instead.
+        WISP_CHECK(cutoff <= max_simple_len + 0.2 || num_paths >= number_of_paths,
+                   "get_paths: only %lld simple paths exist, %d requested", (long long)num_paths, number_of_paths);
+    }
+    double th = now_ms();
+    if (paths.size() != 1) dedupe(paths);                                    // :189
+    std::sort(paths.begin(), paths.end(), path_less);                        // :209
+    if (num_paths != number_of_paths && (int64_t)paths.size() > number_of_paths)  // :211
+        paths.resize(number_of_paths);
+    host_ms += now_ms() - th;
+
+    ctx->path_len.clear(); ctx->path_off.clear(); ctx->path_nodes.clear();
+    ctx->path_off.push_back(0);
+    for (auto& p : paths) {
+        ctx->path_len.push_back(p.len);
+        for (int32_t n : p.nodes) ctx->path_nodes.push_back(n);
+        ctx->path_off.push_back((int64_t)ctx->path_nodes.size());
+    }
+    ctx->path_stats[0] = passes; ctx->path_stats[1] = (double)expansions_total;
+    ctx->path_stats[2] = cutoff - 0.1; ctx->path_stats[3] = apsp_ms;
+    ctx->path_stats[4] = enum_ms; ctx->path_stats[5] = host_ms;
+    return 0;
+}
+
+extern "C" int wisp_paths_size(wisp_ctx* ctx, int64_t* n_paths, int64_t* n_node_entries) {
+    WISP_CHECK(ctx, "paths_size: null context");
+    if (n_paths) *n_paths = (int64_t)ctx->path_len.size();
+    if (n_node_entries) *n_node_entries = (int64_t)ctx->path_nodes.size();
+    return 0;
+}
+
+extern "C" int wisp_paths_fetch(wisp_ctx* ctx, double* lengths, int64_t* offsets, int32_t* nodes) {
+    WISP_CHECK(ctx, "paths_fetch: null context");
+    if (lengths) memcpy(lengths, ctx->path_len.data(), ctx->path_len.size() * 8);
+    if (offsets) memcpy(offsets, ctx->path_off.data(), ctx->path_off.size() * 8);
+    if (nodes) memcpy(nodes, ctx->path_nodes.data(), ctx->path_nodes.size() * 4);
+    return 0;
+}
+
+extern "C" int wisp_paths_stats(wisp_ctx* ctx, double* out6) {
+    WISP_CHECK(ctx && out6, "paths_stats: null argument");
+    memcpy(out6, ctx->path_stats, sizeof(ctx->path_stats));
+    return 0;
+}
