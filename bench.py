@@ -1,0 +1,447 @@
+#!/usr/bin/env python
+"""bench.py -- WISP hot path on B200: corr+contact throughput in N^2*T/s (BASELINE.json).
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (port)
+    torchrun ... bench.py --gpus N ...                       # one rank per GPU, NCCL
+
+Workload (configs[1] of BASELINE.json): 2,000 nodes x 16 atoms, 50,000 frames, residue-COM
+nodes, binary contact map at 15 A; synthetic trajectory (synth.py model, generated on the
+device).  A "step" = one pass coordinates -> cost matrix: K1 node COM, mean + centring,
+K2 DMMA Gram, K3 pair distances, (all-reduce), K4 epilogue.  Frames are sharded over ranks
+(strong scaling: the 50,000 frames are split).  ``value`` has the coordinates resident in
+HBM; ``e2e`` starts from pinned host coordinates and ends with the result matrices on the
+host.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "corr+contact node-pair-frames per second (N^2*T/s)"
+UNIT = "pair-frames/s"
+
+
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "source_hbm": "fallback (B200_PROFILING.md)"}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            peaks["hbm_gbs"] = float(json.load(open(p))["hbm_gbs"])
+            peaks["source_hbm"] = "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    # FP64 / FP32 / MUFU pipe peaks are not in MEASURED_PEAKS.json; measured on this pool's
+    # B200 with tools/peaks.cu (register-resident loops) and tools/dgemm_peak.py (cuBLAS)
+    q = os.path.join(ROOT, "profiles", "peaks_r1.json")
+    peaks.update({"fp64_dmma_tflops": 37.08, "fp32_fma_tflops": 72.23, "mufu_sqrt_tops": 4.637,
+                  "cublas_dgemm_tflops": 35.47, "source_pipes": "builtin (profiles/peaks_r1.json)"})
+    if os.path.exists(q):
+        try:
+            peaks.update(json.load(open(q)))
+            peaks["source_pipes"] = "profiles/peaks_r1.json (tools/peaks.cu on this pool's B200)"
+        except Exception:
+            pass
+    return peaks
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "power_w_max": float(max(power)) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arms (the oracle is the thing being TIMED here, never part of the product path)
+# ---------------------------------------------------------------------------------------
+def cpu_sample(system, frames, cutoff, literal=True, fixed_stages=True):
+    """Time the oracle (port of the reference's CPU path) on `frames` frames of the workload.
+    Returns (per-frame-stage seconds, T-independent seconds, detail dict).  The T-independent
+    N^2 stages (Pearson trace loop, -log) can be skipped with fixed_stages=False."""
+    import oracle
+    coords = system.frames(0, frames)
+    t0 = time.perf_counter()
+    nodes, _ = oracle.com_nodes(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx)
+    t_com = time.perf_counter() - t0
+    avg = nodes.sum(axis=0) / frames
+    t0 = time.perf_counter()
+    cov = oracle.cartesian_covariance(nodes, avg) if literal else oracle.cartesian_covariance_fast(nodes, avg)
+    t_cov = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    if literal:
+        binary, avgdist = oracle.calc_contact_map(nodes, cutoff)
+    else:
+        binary, avgdist = oracle.calc_contact_map_fast(nodes, cutoff)
+    t_contact = time.perf_counter() - t0
+    t_pearson = t_func = 0.0
+    if fixed_stages:
+        t0 = time.perf_counter()
+        if literal:
+            _, _, corr = oracle.pearson_correlation_analysis(cov)
+        else:
+            _, _, corr = oracle.pearson_correlation_fast(cov)
+        t_pearson = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        oracle.func_pearson_correlation(corr, binary)
+        t_func = time.perf_counter() - t0
+    detail = dict(com_s=t_com, covariance_s=t_cov, pearson_s=t_pearson, contact_s=t_contact,
+                  functionalize_s=t_func)
+    return t_com + t_cov + t_contact, t_pearson + t_func, detail
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"]
+        return max(n) if n else 1
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU path (oracle port, literal loop structure, numpy BLAS
+    with every host thread it can use) on bounded samples of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from wisp_mdanalysis_implementation_b200 import synth
+    system = synth.SynthSystem(args.nodes, max(args.sample_frames, 8), args.atoms_per_node, seed=1002)
+    N, Ts, T = args.nodes, args.sample_frames, args.frames
+    times = []
+    detail = {}
+    fixed = None
+    for i in range(args.warmup + args.steps):
+        # the N^2-only stages (Pearson trace loop, -log) run once per job, not once per frame:
+        # time them once and amortise them over the full T like the real job would
+        per_frame, fx, d = cpu_sample(system, Ts, args.cutoff, literal=True, fixed_stages=fixed is None)
+        if fixed is None:
+            fixed, detail = fx, d
+        else:
+            detail.update({k: v for k, v in d.items() if k in ("com_s", "covariance_s", "contact_s")})
+        t = per_frame + fixed * (Ts / T)
+        if i >= args.warmup:
+            times.append(t)
+    ms = 1e3 * float(np.mean(times))
+    value = N * N * Ts / (ms * 1e-3)
+    cores = blas_threads()
+    sample = ("%d of %d frames, literal loop structure (per-frame rank-1 np.dot, per-pair np.trace, "
+              "per-frame N x N distances); N^2-only stages amortised over T" % (Ts, T))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": sample, "detail_s": detail},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": "configs[1]: %d nodes x %d atoms, %d frames, residue-COM nodes, binary contact "
+                        "map at %.1f A" % (args.nodes, args.atoms_per_node, args.frames, args.cutoff),
+            "nodes": args.nodes, "frames": args.frames, "atoms": args.nodes * args.atoms_per_node,
+            "paths": args.paths, "sharding": "frames over ranks",
+            "l2": "inputs larger than L2 (coordinate block per rank >= 2.4 GB vs 126 MB)"}
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nodes", type=int, default=2000)
+    ap.add_argument("--frames", type=int, default=50000)
+    ap.add_argument("--atoms-per-node", type=int, default=16)
+    ap.add_argument("--cutoff", type=float, default=15.0)
+    ap.add_argument("--paths", type=int, default=500)
+    ap.add_argument("--sample-frames", type=int, default=16, help="frames per CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-paths", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from wisp_mdanalysis_implementation_b200 import _lib, synth
+    from wisp_mdanalysis_implementation_b200.pipeline import FramePipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    ctx = _lib.default_context(local_rank)
+
+    N, T, apn = args.nodes, args.frames, args.atoms_per_node
+    A = N * apn
+    t_begin = T * rank // world
+    t_end = T * (rank + 1) // world
+    T_local = t_end - t_begin
+    system = synth.SynthSystem(N, T, apn, seed=1002)
+
+    # ---- synthetic coordinates generated on the device (no 19 GB host generation) ----
+    d_coords = torch.empty((T_local, A, 3), dtype=torch.float32, device=dev)
+    d_base = torch.as_tensor(system.atom_base, device=dev)
+    d_noa = torch.as_tensor(system.node_of_atom, device=dev)
+    d_modes = torch.as_tensor(np.ascontiguousarray(system.modes), device=dev)
+    d_coeff = torch.as_tensor(np.ascontiguousarray(system.coeff), device=dev)
+    cur = torch.cuda.current_stream(dev).cuda_stream
+    ctx.dev_synth_coords(d_coords.data_ptr(), t_begin, T_local, A, d_base.data_ptr(), d_noa.data_ptr(),
+                         d_modes.data_ptr(), synth.N_MODES, d_coeff.data_ptr(), system.noise_sigma,
+                         system.seed, stream=cur)
+    torch.cuda.synchronize()
+
+    pipe = FramePipeline(ctx, N, A, system.masses, system.node_ptr, system.atom_idx, system.align_idx,
+                         frames_local=T_local, frames_total=T, cutoff=args.cutoff, which_map=1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident steps: `value` ----
+    launches0 = ctx.kernel_launches()
+    for _ in range(args.warmup):
+        pipe.run_device(d_coords)
+    barrier()
+    launches_per_step = (ctx.kernel_launches() - launches0) // max(1, args.warmup)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0 = ctx.kernel_launches()
+    e0.record()
+    for _ in range(args.steps):
+        pipe.run_device(d_coords)
+    e1.record()
+    barrier()
+    gpu_launches = ctx.kernel_launches() - l0
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    value = float(N) * N * T / (ms_step * 1e-3)
+
+    # ---- per-kernel timing inside the same process (CUDA events on the launching stream) ----
+    def time_stage(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    reps = max(2, args.steps)
+    # order matters: K1 rewrites X (un-centred); mean_and_center centres it in place again
+    k1_ms = time_stage(lambda: pipe.com(d_coords), reps)
+    pipe.mean_and_center()
+    k2_ms = time_stage(pipe.gram, reps)
+    k3_ms = time_stage(pipe.contact, reps)
+    k4_ms = time_stage(pipe.reduce_and_epilogue, reps)
+    clocks = sampler.stop() if rank == 0 else None
+    work = pipe.work()
+    peaks = load_peaks()
+    k2_tflops = work["k2_flop_executed"] / (k2_ms * 1e-3) / 1e12
+    k3_rate = work["k3_pairframes_executed"] / (k3_ms * 1e-3)
+    k1_gbs = work["k1_bytes"] / (k1_ms * 1e-3) / 1e9
+    kernels = {
+        "k1_com": {"ms": k1_ms, "bound": "hbm", "achieved_gbs": k1_gbs, "peak_gbs": peaks["hbm_gbs"],
+                   "frac": k1_gbs / peaks["hbm_gbs"]},
+        "k2_gram_dmma": {"ms": k2_ms, "bound": "tensor(fp64)", "achieved_tflops": k2_tflops,
+                         "peak_tflops": peaks["fp64_dmma_tflops"],
+                         "frac": k2_tflops / peaks["fp64_dmma_tflops"],
+                         "frac_of_cublas_dgemm": k2_tflops / peaks["cublas_dgemm_tflops"]},
+        "k3_contact": {"ms": k3_ms, "bound": "mufu/fp32", "achieved_tpairframes": k3_rate / 1e12,
+                       "mufu_peak_tops": peaks["mufu_sqrt_tops"],
+                       "frac_mufu": k3_rate / 1e12 / peaks["mufu_sqrt_tops"],
+                       "fp32_flop_frac": 8 * k3_rate / 1e12 / peaks["fp32_fma_tflops"]},
+        "k4_epilogue_allreduce": {"ms": k4_ms},
+    }
+    dominant = "k2_gram_dmma" if k2_ms >= k3_ms else "k3_contact"
+    if dominant == "k2_gram_dmma":
+        roofline = {"kernel": "gram_dmma_kernel<3>", "bound": "tensor", "achieved": k2_tflops,
+                    "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
+                    "frac": k2_tflops / peaks["fp64_dmma_tflops"], "traffic": None,
+                    "peak_source": "FP64 DMMA pipe peak measured with tools/peaks.cu on this pool "
+                                   "(MEASURED_PEAKS.json has no FP64 figure); cuBLAS DGEMM 8192^3 = %.2f"
+                                   % peaks["cublas_dgemm_tflops"]}
+    else:
+        roofline = {"kernel": "contact_sum_kernel", "bound": "fp32/mufu pipe", "achieved": k3_rate / 1e12,
+                    "peak": peaks["mufu_sqrt_tops"], "unit": "Tsqrt/s", "frac": k3_rate / 1e12 / peaks["mufu_sqrt_tops"],
+                    "traffic": None,
+                    "peak_source": "MUFU.SQRT issue peak measured with tools/peaks.cu (1 sqrt per pair-frame)"}
+
+    # ---- e2e: pinned host coordinates -> results on the host ----
+    e2e = None
+    if not args.no_e2e:
+        h_coords = torch.empty((T_local, A, 3), dtype=torch.float32, pin_memory=True)
+        h_coords.copy_(d_coords)
+        torch.cuda.synchronize()
+        for _ in range(max(1, args.warmup - 1)):
+            pipe.run_host(h_coords)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(args.steps):
+            res = pipe.run_host(h_coords)
+        b.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        ms_e2e = max_over_ranks(max(a.elapsed_time(b) / args.steps, 0.0))
+        e2e = {"value": float(N) * N * T / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+               "wall_ms_per_step": wall_ms, "h2d_bytes_per_step": pipe.h2d_bytes() * world,
+               "d2h_bytes_per_step": pipe.d2h_bytes(),
+               "api": "FramePipeline.run_host (C-ABI wisp_dev_* calls; pinned host coords in, "
+                      "corr/avgdist/binary/w on the host out)"}
+        del h_coords
+
+    # ---- APSP + 500 suboptimal paths on the resulting cost matrix (rank 0) ----
+    extra = {}
+    if rank == 0 and not args.no_paths:
+        W = pipe.d_w.cpu().numpy()
+        hop_w = (W != 0).astype(np.float64)
+        t0 = time.perf_counter()
+        hops, _ = ctx.apsp(hop_w, precision=32, want_pred=False)
+        t_hops = time.perf_counter() - t0
+        cand = np.argwhere((hops >= 5) & (hops <= 8))
+        cand = cand[cand[:, 0] < cand[:, 1]]
+        s, t = (int(cand[0][0]), int(cand[0][1])) if len(cand) else (0, N - 1)
+        for prec in (64, 32):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d_W = torch.as_tensor(W, device=dev)
+            d_dist = torch.empty((N, N), dtype=torch.float64, device=dev)
+            d_pred = torch.empty((N, N), dtype=torch.int32, device=dev)
+            ctx.dev_apsp(d_W.data_ptr(), N, prec, d_dist.data_ptr(), d_pred.data_ptr(), stream=cur)
+            torch.cuda.synchronize()
+            ev0.record()
+            ctx.dev_apsp(d_W.data_ptr(), N, prec, d_dist.data_ptr(), d_pred.data_ptr(), stream=cur)
+            ev1.record()
+            torch.cuda.synchronize()
+            extra["apsp_fp%d_ms" % prec] = ev0.elapsed_time(ev1)
+            extra["apsp_fp%d_trelax_per_s" % prec] = float(N) ** 3 / (ev0.elapsed_time(ev1) * 1e-3) / 1e12
+        t0 = time.perf_counter()
+        paths = ctx.get_paths(W, [s], [t], args.paths)
+        extra["get_paths_wall_ms"] = (time.perf_counter() - t0) * 1e3
+        extra["get_paths"] = dict(source=s, sink=t, returned=len(paths), shortest=paths[0][0],
+                                  longest=paths[-1][0], **ctx.paths_stats())
+        extra["hops_apsp_wall_ms"] = t_hops * 1e3
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle timed on the box's host cores ----
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        Ts = args.sample_frames
+        per_frame, fixed, detail = cpu_sample(system, Ts, args.cutoff, literal=True)
+        t_lit = per_frame + fixed * (Ts / T)
+        per_frame_v, fixed_v, detail_v = cpu_sample(system, 4 * Ts, args.cutoff, literal=False)
+        t_vec = per_frame_v + fixed_v * (4 * Ts / T)
+        cpu_baseline = {"value": float(N) * N * Ts / t_lit, "unit": UNIT, "cores": blas_threads(),
+                        "kind": "port",
+                        "sample": "%d of %d frames through the oracle with the reference's loop structure; "
+                                  "N^2-only stages amortised over T" % (Ts, T),
+                        "detail_s": detail,
+                        "vectorised": {"value": float(N) * N * 4 * Ts / t_vec,
+                                       "sample": "%d frames, one GEMM + blocked distances (numpy, all BLAS threads)" % (4 * Ts),
+                                       "detail_s": detail_v}}
+        if "get_paths" in extra:
+            # the reference's get_paths on the same cost matrix, capped (it is exponential)
+            import oracle
+            t0 = time.perf_counter()
+            try:
+                ref_paths = oracle.get_paths_pruned(W, [s], [t], min(args.paths, 100))
+                extra["cpu_get_paths_pruned_100_s"] = time.perf_counter() - t0
+            except Exception as exc:   # pragma: no cover
+                extra["cpu_get_paths_pruned_100_s"] = "failed: %s" % exc
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
+                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "extra": extra}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

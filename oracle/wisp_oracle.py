@@ -267,10 +267,12 @@ def calc_contact_map(trajectory_data, distance_cutoff=9999.0, mda_float32=False)
     return binary, avg
 
 
-def calc_contact_map_fast(trajectory_data, distance_cutoff=9999.0, block=64):
+def calc_contact_map_fast(trajectory_data, distance_cutoff=9999.0, block=None):
     """Frame-blocked vectorised form (same per-pair summation order over frames)."""
     X = np.asarray(trajectory_data, dtype=np.float64)
     T, N, _ = X.shape
+    if block is None:
+        block = max(1, min(64, int(3e7 // (N * N))))
     avg = np.zeros((N, N), dtype=np.float64)
     for t0 in range(0, T, block):
         x = X[t0:t0 + block]

@@ -246,7 +246,8 @@ def test_properties_large(ctx):
     h = t // 2
     o1 = ctx.pipeline(coords[:h], system.masses, system.node_ptr, system.atom_idx, system.align_idx, cutoff=12.0)
     o2 = ctx.pipeline(coords[h:], system.masses, system.node_ptr, system.atom_idx, system.align_idx, cutoff=12.0)
-    np.testing.assert_allclose(0.5 * (o1["avgdist"] + o2["avgdist"]), d, rtol=1e-9)
+    # (distances are FP32 per frame, FP64 accumulated: 1e-6 is the stated tolerance)
+    np.testing.assert_allclose(0.5 * (o1["avgdist"] + o2["avgdist"]), d, rtol=1e-6)
     # APSP on the resulting cost matrix: triangle inequality + symmetric
     W = out["w"]
     dist, pred = ctx.apsp(W)

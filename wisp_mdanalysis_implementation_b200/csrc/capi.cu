@@ -71,9 +71,8 @@ int wisp_scratch(wisp_ctx* ctx, int slot, size_t bytes, void** out) {
     DevBuf& b = ctx->scratch[slot];
     if (b.bytes < bytes) {
         if (b.p) {
-            // earlier work on either stream may still use the old buffer
-            WISP_CUDA(cudaStreamSynchronize(ctx->stream));
-            WISP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+            // earlier work on any stream (ours or the caller's) may still use the old buffer
+            WISP_CUDA(cudaDeviceSynchronize());
             WISP_CUDA(cudaFree(b.p));
             b.p = nullptr;
             b.bytes = 0;

@@ -76,8 +76,11 @@ com_kernel(const float* __restrict__ coords, int64_t T, int A, const double* __r
         const int group = tid / kLanesPerNode;
         const int gl = tid % kLanesPerNode;
         double* out = nodes + (row0 + f) * ld;
-        for (int n = group; n < N; n += kComThreads / kLanesPerNode) {
-            const int e0 = __ldg(node_ptr + n), e1 = __ldg(node_ptr + n + 1);
+        // trip count is uniform across the block: the shuffles below need every lane present
+        for (int n0 = 0; n0 < N; n0 += kComThreads / kLanesPerNode) {
+            const int n = n0 + group;
+            const bool valid = n < N;
+            const int e0 = valid ? __ldg(node_ptr + n) : 0, e1 = valid ? __ldg(node_ptr + n + 1) : 0;
             double ax = 0, ay = 0, az = 0, am = 0;
             for (int e = e0 + gl; e < e1; e += kLanesPerNode) {
                 const int idx = __ldg(atom_idx + e);
@@ -100,9 +103,9 @@ com_kernel(const float* __restrict__ coords, int64_t T, int A, const double* __r
                 az += __shfl_xor_sync(0xffffffffu, az, o);
                 am += __shfl_xor_sync(0xffffffffu, am, o);
             }
-            if (gl == 0) out[3 * (int64_t)n + 0] = ax / am;
-            if (gl == 1) out[3 * (int64_t)n + 1] = ay / am;
-            if (gl == 2) out[3 * (int64_t)n + 2] = az / am;
+            if (valid && gl == 0) out[3 * (int64_t)n + 0] = ax / am;
+            if (valid && gl == 1) out[3 * (int64_t)n + 1] = ay / am;
+            if (valid && gl == 2) out[3 * (int64_t)n + 2] = az / am;
         }
         __syncthreads();   // shift[] / red[] reuse
     }

@@ -1,0 +1,159 @@
+"""Frame-sharded device pipeline: coordinates -> cost matrix on 1..8 B200s.
+
+One process per GPU.  Frames are the data-parallel axis: every rank runs
+K1 (translate + node COM) on its own frame block, the ranks agree on the global mean with a
+tiny all-reduce of the column sums, each rank centres its block and runs K2 (DMMA Gram) and
+K3 (pair distances) on it, and the partial ``[G || D]`` sums -- ONE contiguous buffer -- are
+combined by a single NCCL all-reduce before the fused epilogue K4.  torch is used only for
+device memory, streams and ``torch.distributed``; every kernel is this repository's own,
+called through the C ABI with raw pointers.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class FramePipeline:
+    def __init__(self, ctx, n_nodes, n_atoms, masses, node_ptr, atom_idx, align_idx,
+                 frames_local, frames_total=None, cutoff=15.0, which_map=1, atomic=False,
+                 group=None):
+        self.ctx = ctx
+        self.dev = torch.device("cuda", ctx.device)
+        self.N, self.A = int(n_nodes), int(n_atoms)
+        self.T = int(frames_local)
+        self.T_total = int(frames_total if frames_total is not None else frames_local)
+        self.cutoff, self.which_map, self.atomic = float(cutoff), int(which_map), bool(atomic)
+        self.group = group
+        self.distributed = group is not None or (torch.distributed.is_available()
+                                                 and torch.distributed.is_initialized()
+                                                 and torch.distributed.get_world_size() > 1)
+        self.ld = _lib.node_ld(self.N)
+        self.tpad = _lib.frames_pad(self.T)
+        self.npad = _lib.gram_ld(self.N)
+        dev = self.dev
+        f64, i32 = torch.float64, torch.int32
+        self.d_masses = torch.as_tensor(np.asarray(masses, dtype=np.float64), device=dev)
+        self.d_node_ptr = torch.as_tensor(np.asarray(node_ptr, dtype=np.int32), device=dev)
+        self.d_atom_idx = torch.as_tensor(np.asarray(atom_idx, dtype=np.int32), device=dev)
+        self.d_align_idx = torch.as_tensor(np.asarray(align_idx, dtype=np.int32), device=dev)
+        self.n_align = int(self.d_align_idx.numel())
+        self.d_x = torch.zeros((self.tpad, self.ld), dtype=f64, device=dev)
+        self.d_colsum = torch.zeros(self.ld, dtype=f64, device=dev)
+        self.d_mean = torch.zeros(self.ld, dtype=f64, device=dev)
+        self.d_sums = torch.zeros((2, self.npad, self.npad), dtype=f64, device=dev)   # [G || D]
+        n = self.N
+        self.d_corr = torch.empty((n, n), dtype=f64, device=dev)
+        self.d_avgdist = torch.empty((n, n), dtype=f64, device=dev)
+        self.d_binary = torch.empty((n, n), dtype=torch.int64, device=dev)
+        self.d_w = torch.empty((n, n), dtype=f64, device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.chunk_frames = max(1, min(self.T, (128 << 20) // (12 * self.A)))
+        self._stage = None
+        self.timings = {}
+
+    # -- stages (all on torch's current stream) ------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def com(self, d_coords, frames=None, row0=0):
+        t = self.T if frames is None else frames
+        self.ctx.dev_com(d_coords.data_ptr(), t, self.A, self.d_masses.data_ptr(),
+                         self.d_node_ptr.data_ptr(), self.d_atom_idx.data_ptr(), self.N,
+                         self.d_align_idx.data_ptr(), self.n_align,
+                         self.d_x.data_ptr() + row0 * self.ld * 8, None, atomic=self.atomic,
+                         stream=self._stream())
+
+    def mean_and_center(self):
+        s = self._stream()
+        self.ctx.dev_colsum(self.d_x.data_ptr(), self.T, self.N, self.d_colsum.data_ptr(), stream=s)
+        if self.distributed:
+            torch.distributed.all_reduce(self.d_colsum, group=self.group)
+        torch.div(self.d_colsum, float(self.T_total), out=self.d_mean)
+        self.ctx.dev_center(self.d_x.data_ptr(), self.T, self.N, self.d_mean.data_ptr(), stream=s)
+
+    def gram(self):
+        self.ctx.dev_gram(self.d_x.data_ptr(), self.T, self.ld, self.N, 3,
+                          self.d_sums[0].data_ptr(), stream=self._stream())
+
+    def contact(self):
+        self.ctx.dev_contact_sum(self.d_x.data_ptr(), self.T, self.N, self.d_mean.data_ptr(),
+                                 self.d_sums[1].data_ptr(), stream=self._stream())
+
+    def reduce_and_epilogue(self):
+        if self.distributed:
+            torch.distributed.all_reduce(self.d_sums, group=self.group)    # the ONE big collective
+        self.ctx.dev_epilogue(self.d_sums[0].data_ptr(), self.d_sums[1].data_ptr(), self.T_total,
+                              self.N, self.cutoff, self.which_map, d_corr=self.d_corr.data_ptr(),
+                              d_avgdist=self.d_avgdist.data_ptr(),
+                              d_binary=self.d_binary.data_ptr(), d_w=self.d_w.data_ptr(),
+                              stream=self._stream())
+
+    # -- whole steps ------------------------------------------------------------------
+    def run_device(self, d_coords):
+        """One pass with the coordinate block already resident in HBM."""
+        self.com(d_coords)
+        self.mean_and_center()
+        self.gram()
+        self.contact()
+        self.reduce_and_epilogue()
+
+    def run_host(self, h_coords, fetch=True):
+        """One pass from PINNED host coordinates (T_local, A, 3) float32: chunked H2D on a
+        copy stream double-buffered against K1, then the device stages, then the results are
+        read back to the host."""
+        main = torch.cuda.current_stream(self.dev)
+        if self._stage is None:
+            self._stage = [torch.empty((self.chunk_frames, self.A, 3), dtype=torch.float32,
+                                       device=self.dev) for _ in range(2)]
+            self._h_out = [torch.empty((self.N, self.N), dtype=torch.float64).pin_memory()
+                           for _ in range(3)] + [torch.empty((self.N, self.N), dtype=torch.int64).pin_memory()]
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
+        it = 0
+        for t0 in range(0, self.T, self.chunk_frames):
+            b = it & 1
+            nt = min(self.chunk_frames, self.T - t0)
+            with torch.cuda.stream(self.copy_stream):
+                if it >= 2:
+                    self.copy_stream.wait_event(freed[b])
+                self._stage[b][:nt].copy_(h_coords[t0:t0 + nt], non_blocking=True)
+                copied[b].record(self.copy_stream)
+            main.wait_event(copied[b])
+            self.com(self._stage[b], frames=nt, row0=t0)
+            freed[b].record(main)
+            it += 1
+        self.mean_and_center()
+        self.gram()
+        self.contact()
+        self.reduce_and_epilogue()
+        if fetch:
+            self._h_out[0].copy_(self.d_corr, non_blocking=True)
+            self._h_out[1].copy_(self.d_avgdist, non_blocking=True)
+            self._h_out[2].copy_(self.d_w, non_blocking=True)
+            self._h_out[3].copy_(self.d_binary, non_blocking=True)
+            main.synchronize()
+            return dict(corr=self._h_out[0].numpy(), avgdist=self._h_out[1].numpy(),
+                        w=self._h_out[2].numpy(), binary=self._h_out[3].numpy())
+        return None
+
+    def h2d_bytes(self):
+        return self.T * self.A * 12
+
+    def d2h_bytes(self):
+        return 4 * self.N * self.N * 8
+
+    # -- algorithmic work of one pass on this rank -----------------
+    def work(self):
+        n_tiles = self.npad // 128
+        pairs = n_tiles * (n_tiles + 1) // 2
+        return dict(
+            k1_bytes=self.T * (12 * self.A + 24 * self.N),
+            k2_flop_executed=2.0 * pairs * 128 * 128 * 3 * self.tpad,
+            k2_flop_full=6.0 * self.N * self.N * self.T,
+            k3_pairframes_full=float(self.N) * self.N * self.T,
+            k3_pairframes_executed=sum((self.npad // 128 - bi // 2) for bi in range(self.npad // 64))
+            * 64.0 * 128.0 * self.T,
+        )
