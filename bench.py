@@ -255,7 +255,7 @@ def main():
     d_noa = torch.as_tensor(system.node_of_atom, device=dev)
     d_modes = torch.as_tensor(np.ascontiguousarray(system.modes), device=dev)
     d_coeff = torch.as_tensor(np.ascontiguousarray(system.coeff), device=dev)
-    cur = torch.cuda.current_stream(dev).cuda_stream
+    cur = torch.cuda.current_stream(dev).cuda_stream or 1   # 0x1 == cudaStreamLegacy
     ctx.dev_synth_coords(d_coords.data_ptr(), t_begin, T_local, A, d_base.data_ptr(), d_noa.data_ptr(),
                          d_modes.data_ptr(), synth.N_MODES, d_coeff.data_ptr(), system.noise_sigma,
                          system.seed, stream=cur)

@@ -127,9 +127,11 @@ int wisp_dev_com(wisp_ctx* ctx, const float* d_coords, int64_t T, int A, const d
                  const int32_t* d_node_ptr, const int32_t* d_atom_idx, int N,
                  const int32_t* d_align_idx, int n_align, int atomic, double* d_nodes,
                  double* d_colsum, void* stream);
-/* X <- X - mean (in place), mean [ld]; pad columns / rows are left at zero. */
+/* X <- X - mean (in place), mean [ld]; pad columns / rows are left at zero.  When d_p32 is
+ * not NULL it also receives the FP32 tile-referenced copy K3 reads:
+ * float [T][wisp_gram_ld(N)/128][3][128], value = float(x - mean of the tile's middle node). */
 int wisp_dev_center(wisp_ctx* ctx, double* d_nodes, int64_t T, int N, const double* d_mean,
-                    void* stream);
+                    float* d_p32, void* stream);
 /* column sums of the (possibly centred) trajectory: d_colsum [ld] */
 int wisp_dev_colsum(wisp_ctx* ctx, const double* d_nodes, int64_t T, int N, double* d_colsum,
                     void* stream);
@@ -138,9 +140,9 @@ int wisp_dev_colsum(wisp_ctx* ctx, const double* d_nodes, int64_t T, int N, doub
  * [n_out_pad][n_out_pad] with n_out_pad = wisp_gram_ld(n_out); overwritten. */
 int wisp_dev_gram(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_out,
                   int stride, double* d_out, void* stream);
-/* K3: D[i][j] = sum_t |x_i(t) - x_j(t)| for i<=j tiles; d_x is the CENTRED trajectory and
- * d_mean [ld] the mean that was subtracted.  d_out [Npad][Npad] overwritten. */
-int wisp_dev_contact_sum(wisp_ctx* ctx, const double* d_x, int64_t T, int N,
+/* K3: D[i][j] = sum_t |x_i(t) - x_j(t)| for i<=j tiles; d_p32 is the FP32 copy written by
+ * wisp_dev_center and d_mean [ld] the mean used there.  d_out [Npad][Npad] overwritten. */
+int wisp_dev_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N,
                          const double* d_mean, double* d_out, void* stream);
 /* K4: fused epilogue on (all-reduced) sums.  d_gram / d_dsum are [Npad][Npad] upper-tile
  * sums over T_total frames.  Outputs (each may be NULL) are dense [N][N]:

@@ -39,7 +39,8 @@ elif step in ("cov", "contact", "gram3", "dev"):
             mean[:3 * n] = torch.from_numpy(avg.reshape(-1)).cuda()
             d = torch.zeros(npad, npad, dtype=torch.float64, device="cuda")
             torch.cuda.synchronize()
-            ctx.dev_contact_sum(x.data_ptr(), t, n, mean.data_ptr(), d.data_ptr())
+            p32 = torch.zeros(t, npad // 128, 3, 128, dtype=torch.float32, device="cuda")
+            ctx.dev_contact_sum(p32.data_ptr(), t, n, mean.data_ptr(), d.data_ptr())
             ctx.sync()
             print("contact done", flush=True)
 elif step == "pipeline":

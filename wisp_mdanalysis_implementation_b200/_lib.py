@@ -45,7 +45,7 @@ SIGNATURES = {
     "wisp_paths_fetch": (_int, [_c_ctx, _P, _P, _P]),
     "wisp_paths_stats": (_int, [_c_ctx, _P]),
     "wisp_dev_com": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P, _int, _P, _int, _int, _P, _P, _P]),
-    "wisp_dev_center": (_int, [_c_ctx, _P, _i64, _int, _P, _P]),
+    "wisp_dev_center": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P]),
     "wisp_dev_colsum": (_int, [_c_ctx, _P, _i64, _int, _P, _P]),
     "wisp_dev_gram": (_int, [_c_ctx, _P, _i64, _i64, _int, _int, _P, _P]),
     "wisp_dev_contact_sum": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P]),
@@ -271,8 +271,9 @@ class Context:
                                            n_align, int(bool(atomic)), _ptr(d_nodes), _ptr(d_colsum),
                                            _ptr(stream)))
 
-    def dev_center(self, d_nodes, T, N, d_mean, stream=None):
-        self._check(self._lib.wisp_dev_center(self._ctx, _ptr(d_nodes), T, N, _ptr(d_mean), _ptr(stream)))
+    def dev_center(self, d_nodes, T, N, d_mean, d_p32=None, stream=None):
+        self._check(self._lib.wisp_dev_center(self._ctx, _ptr(d_nodes), T, N, _ptr(d_mean),
+                                              _ptr(d_p32), _ptr(stream)))
 
     def dev_colsum(self, d_nodes, T, N, d_colsum, stream=None):
         self._check(self._lib.wisp_dev_colsum(self._ctx, _ptr(d_nodes), T, N, _ptr(d_colsum), _ptr(stream)))
@@ -281,8 +282,8 @@ class Context:
         self._check(self._lib.wisp_dev_gram(self._ctx, _ptr(d_x), T, ld, n_out, stride, _ptr(d_out),
                                             _ptr(stream)))
 
-    def dev_contact_sum(self, d_x, T, N, d_mean, d_out, stream=None):
-        self._check(self._lib.wisp_dev_contact_sum(self._ctx, _ptr(d_x), T, N, _ptr(d_mean),
+    def dev_contact_sum(self, d_p32, T, N, d_mean, d_out, stream=None):
+        self._check(self._lib.wisp_dev_contact_sum(self._ctx, _ptr(d_p32), T, N, _ptr(d_mean),
                                                    _ptr(d_out), _ptr(stream)))
 
     def dev_epilogue(self, d_gram, d_dsum, T_total, N, cutoff, which_map, d_var=None, d_ncov=None,

@@ -381,8 +381,10 @@ extern "C" int wisp_contact_map(wisp_ctx* ctx, const double* nodes, int64_t T, i
     WISP_CUDA(cudaMemsetAsync(d_mean, 0, (size_t)ld * 8, st));
     WISP_TRY(launch_colsum(ctx, d_x, T, ld, 3 * (int64_t)N, d_sum, st));
     WISP_TRY(dev_div(ctx, d_sum, (double)T, 3 * (int64_t)N, d_mean, st));
-    WISP_TRY(launch_center(ctx, d_x, T, ld, 3 * (int64_t)N, d_mean, st));
-    WISP_TRY(launch_contact_sum(ctx, d_x, T, N, ld, d_mean, d_dsum, st));
+    void* pp = nullptr;
+    WISP_TRY(wisp_scratch(ctx, SCR_P32, (size_t)T * n_pad * 12, &pp));
+    WISP_TRY(launch_center(ctx, d_x, T, ld, 3 * (int64_t)N, d_mean, st, (float*)pp, N));
+    WISP_TRY(launch_contact_sum(ctx, (const float*)pp, T, N, d_mean, d_dsum, st));
     WISP_TRY(launch_epilogue(ctx, nullptr, d_dsum, T, N, cutoff, 0, nullptr, nullptr, nullptr,
                              d_avgdist, d_binary, nullptr, st));
     if (out_avgdist) WISP_CUDA(cudaMemcpyAsync(out_avgdist, d_avgdist, nn * 8, cudaMemcpyDeviceToHost, st));
@@ -454,9 +456,11 @@ extern "C" int wisp_pipeline(wisp_ctx* ctx, const float* coords, int64_t T, int 
     if (out_nodes)   // un-centred node trajectory, as traj_alignment_and_averaging returns it
         WISP_CUDA(cudaMemcpy2DAsync(out_nodes, (size_t)3 * N * 8, d_x, (size_t)ld * 8, (size_t)3 * N * 8,
                                     (size_t)T, cudaMemcpyDeviceToHost, st));
-    WISP_TRY(launch_center(ctx, d_x, T, ld, 3 * (int64_t)N, d_mean, st));
+    void* pp = nullptr;
+    WISP_TRY(wisp_scratch(ctx, SCR_P32, (size_t)T * n_pad * 12, &pp));
+    WISP_TRY(launch_center(ctx, d_x, T, ld, 3 * (int64_t)N, d_mean, st, (float*)pp, N));
     WISP_TRY(launch_gram(ctx, d_x, T, ld, N, 3, d_gram, st));
-    WISP_TRY(launch_contact_sum(ctx, d_x, T, N, ld, d_mean, d_dsum, st));
+    WISP_TRY(launch_contact_sum(ctx, (const float*)pp, T, N, d_mean, d_dsum, st));
     WISP_TRY(launch_epilogue(ctx, d_gram, d_dsum, T, N, cutoff, which_map, nullptr, nullptr, d_corr,
                              d_avgdist, d_binary, d_w, st));
     if (out_corr) WISP_CUDA(cudaMemcpyAsync(out_corr, d_corr, nn * 8, cudaMemcpyDeviceToHost, st));
@@ -505,9 +509,10 @@ extern "C" int wisp_dev_com(wisp_ctx* ctx, const float* d_coords, int64_t T, int
 }
 
 extern "C" int wisp_dev_center(wisp_ctx* ctx, double* d_nodes, int64_t T, int N, const double* d_mean,
-                               void* stream) {
+                               float* d_p32, void* stream) {
     WISP_CHECK(ctx && d_nodes && d_mean, "dev_center: null argument");
-    return launch_center(ctx, d_nodes, T, wisp_node_ld(N), 3 * (int64_t)N, d_mean, wisp_stream(ctx, stream));
+    return launch_center(ctx, d_nodes, T, wisp_node_ld(N), 3 * (int64_t)N, d_mean, wisp_stream(ctx, stream),
+                         d_p32, N);
 }
 
 extern "C" int wisp_dev_colsum(wisp_ctx* ctx, const double* d_nodes, int64_t T, int N, double* d_colsum,
@@ -522,10 +527,10 @@ extern "C" int wisp_dev_gram(wisp_ctx* ctx, const double* d_x, int64_t T, int64_
     return launch_gram(ctx, d_x, T, ld, n_out, stride, d_out, wisp_stream(ctx, stream));
 }
 
-extern "C" int wisp_dev_contact_sum(wisp_ctx* ctx, const double* d_x, int64_t T, int N,
+extern "C" int wisp_dev_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N,
                                     const double* d_mean, double* d_out, void* stream) {
-    WISP_CHECK(ctx && d_x && d_mean && d_out, "dev_contact_sum: null argument");
-    return launch_contact_sum(ctx, d_x, T, N, wisp_node_ld(N), d_mean, d_out, wisp_stream(ctx, stream));
+    WISP_CHECK(ctx && d_p32 && d_mean && d_out, "dev_contact_sum: null argument");
+    return launch_contact_sum(ctx, d_p32, T, N, d_mean, d_out, wisp_stream(ctx, stream));
 }
 
 extern "C" int wisp_dev_epilogue(wisp_ctx* ctx, const double* d_gram, const double* d_dsum,

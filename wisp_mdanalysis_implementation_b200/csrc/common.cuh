@@ -76,7 +76,7 @@ static inline cudaStream_t wisp_stream(wisp_ctx* ctx, void* s) {
 
 enum ScratchSlot {
     SCR_GRAM_PART = 0, SCR_CONTACT_PART, SCR_COLSUM_PART, SCR_X, SCR_COORDS0, SCR_COORDS1,
-    SCR_APSP_D, SCR_APSP_P, SCR_ARENA, SCR_ALIGN,
+    SCR_APSP_D, SCR_APSP_P, SCR_ARENA, SCR_ALIGN, SCR_P32,
     SCR_MISC0, SCR_MISC1, SCR_MISC2, SCR_MISC3, SCR_MISC4, SCR_MISC5, SCR_MISC6, SCR_MISC7,
     SCR_MISC8, SCR_MISC9, SCR_COUNT
 };
@@ -93,15 +93,16 @@ int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* 
                             double* h_avg_nodes, double* log, int* n_iter_out, cudaStream_t st);
 int launch_colsum(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int64_t ncols,
                   double* d_colsum, cudaStream_t st);
+// d_p32 != nullptr: also write the FP32 tile-referenced copy [T][n_tiles][3][128] for K3
 int launch_center(wisp_ctx* ctx, double* d_x, int64_t T, int64_t ld, int64_t ncols,
-                  const double* d_mean, cudaStream_t st);
+                  const double* d_mean, cudaStream_t st, float* d_p32 = nullptr, int N = 0);
 int launch_gram(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_out, int stride,
                 double* d_out, cudaStream_t st);
 int launch_reduce_partials(wisp_ctx* ctx, const double* part, int n_seg, int64_t n_pad,
                            double* out, int tile_r, int tile_c, cudaStream_t st);
 int wisp_pick_segments(int items_per_seg, int stages_total, int sm_count, int min_stages);
-int launch_contact_sum(wisp_ctx* ctx, const double* d_x, int64_t T, int N, int64_t ld,
-                       const double* d_mean, double* d_out, cudaStream_t st);
+int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, const double* d_mean,
+                       double* d_out, cudaStream_t st);
 int launch_epilogue(wisp_ctx* ctx, const double* d_gram, const double* d_dsum, int64_t T_total,
                     int N, double cutoff, int which_map, double* d_var, double* d_ncov,
                     double* d_corr, double* d_avgdist, int64_t* d_binary, double* d_w,

@@ -103,9 +103,9 @@ com_kernel(const float* __restrict__ coords, int64_t T, int A, const double* __r
                 az += __shfl_xor_sync(0xffffffffu, az, o);
                 am += __shfl_xor_sync(0xffffffffu, am, o);
             }
-            if (valid && gl == 0) out[3 * (int64_t)n + 0] = ax / am;
-            if (valid && gl == 1) out[3 * (int64_t)n + 1] = ay / am;
-            if (valid && gl == 2) out[3 * (int64_t)n + 2] = az / am;
+            // one division per warp instruction: lanes 0..2 of the group pick x, y, z
+            const double num = (gl == 0) ? ax : ((gl == 1) ? ay : az);
+            if (valid && gl < 3) out[3 * (int64_t)n + gl] = num / am;
         }
         __syncthreads();   // shift[] / red[] reuse
     }
@@ -150,6 +150,33 @@ __global__ void center_kernel(double* __restrict__ x, int64_t T, int64_t ld, int
     if (col >= ncols) return;
     const double m = mean[col];
     for (int64_t t = blockIdx.y; t < T; t += gridDim.y) x[t * ld + col] -= m;
+}
+
+// Centring fused with the FP32 tile-referenced copy K3 consumes:
+//   X[t][col] -= mean[col]                                   (in place, float64)
+//   P[t][tile][c][n] = float( x - ref_tile,c )               (x = un-centred value)
+// One CTA of 384 threads per (tile, frame): coalesced 3 KB read, transpose through shared
+// memory, coalesced 1.5 KB write.
+__global__ void __launch_bounds__(384)
+center_convert_kernel(double* __restrict__ x, int64_t T, int64_t ld, int N,
+                      const double* __restrict__ mean, float* __restrict__ p32, int n_tiles) {
+    __shared__ float s[3][kTile + 1];
+    const int tile = blockIdx.x;
+    const int k = threadIdx.x;
+    const int64_t col = (int64_t)3 * kTile * tile + k;
+    const int c = k % 3, n = k / 3;
+    int nref = kTile * tile + kTile / 2;
+    if (nref > N - 1) nref = N - 1;
+    const double m = mean[col];
+    const double ref = mean[3 * nref + c];
+    for (int64_t t = blockIdx.y; t < T; t += gridDim.y) {
+        const double v = x[t * ld + col];
+        x[t * ld + col] = v - m;
+        s[c][n] = (float)(v - ref);
+        __syncthreads();
+        p32[(t * n_tiles + tile) * (int64_t)(3 * kTile) + k] = s[k / kTile][k % kTile];
+        __syncthreads();
+    }
 }
 
 }  // namespace
@@ -198,7 +225,15 @@ int launch_colsum_f32(wisp_ctx* ctx, const float* d_x, int64_t T, int64_t ld, in
 }
 
 int launch_center(wisp_ctx* ctx, double* d_x, int64_t T, int64_t ld, int64_t ncols,
-                  const double* d_mean, cudaStream_t st) {
+                  const double* d_mean, cudaStream_t st, float* d_p32, int N) {
+    if (d_p32) {
+        const int n_tiles = (int)(round_up(N, kTile) / kTile);
+        const int gy = (int)std::min<int64_t>(T, std::max<int64_t>(1, (int64_t)ctx->sm_count * 8 / n_tiles));
+        center_convert_kernel<<<dim3(n_tiles, gy), 384, 0, st>>>(d_x, T, ld, N, d_mean, d_p32, n_tiles);
+        ctx->launches++;
+        WISP_CUDA(cudaGetLastError());
+        return 0;
+    }
     const int gx = (int)((ncols + 255) / 256);
     const int gy = (int)std::min<int64_t>(T, std::max<int64_t>(1, (int64_t)ctx->sm_count * 16 / gx));
     center_kernel<<<dim3(gx, gy), 256, 0, st>>>(d_x, T, ld, ncols, d_mean);

@@ -4,27 +4,27 @@
 // N^2 numpy add per frame (trajectory_analysis_functions.py:207-215):
 //     D[i][j] = sum_t | x_i(t) - x_j(t) |          (divided by T and thresholded in K4)
 //
-// One CTA = one 64(i) x 128(j) pair tile x one frame segment, upper-triangular tiles only.
-// 512 threads, each owns 4 x 4 pairs.  The centred FP64 trajectory is staged 8 frames at a
-// time into shared memory as FP32 structure-of-arrays [frame][xyz][node], re-referenced to a
-// point inside the i-tile (x + mean - ref: one FP64 add per staged element, not per pair) so
-// FP32 differences keep ~1e-7 relative accuracy at any box size.  Inner loop per pair-frame:
-// 3 FSUB + FMUL + 2 FFMA + MUFU.SQRT + FADD; FP32 partial sums are promoted to the FP64
-// per-pair totals (registers) every 16 frames.  The kernel is co-limited by the MUFU pipe
-// (1 sqrt per pair-frame, 16 lanes/clk/SM) and FP32 issue (8 slots per pair-frame).
+// Input: the FP32 tile-referenced structure-of-arrays copy P of the node trajectory that the
+// centring pass writes (k1_com.cu: center_convert_kernel):
+//     P[t][tile][c][n] = float( x_{128*tile+n, c}(t) - ref_{tile, c} ),  ref_tile = mean
+//     position of the node in the middle of the tile.
+// FP32 differences of tile-referenced coordinates keep ~1e-7 relative accuracy at any box
+// size (the reference stack itself casts ABSOLUTE coordinates to float32 inside
+// distance_array); the reference offset between two tiles is added once per staged j value.
+//
+// One CTA = one 128 x 128 pair tile (upper triangle only) x one frame segment; 512 threads,
+// each owns 8 x 4 pairs.  Frames are staged 8 at a time (float4 loads, double-buffered).
+// Per pair-frame: 3 FADD + FMUL + 2 FFMA + MUFU.SQRT + FADD -- the kernel is co-limited by
+// the MUFU pipe (16 lanes/clk/SM) and FP32 issue.  FP32 partial sums are promoted every 64
+// frames into FP64 per-pair totals kept in shared memory (128 KB), written once at the end.
 #include "common.cuh"
 
 namespace {
 
-constexpr int kTI = 64;
-constexpr int kTJ = 128;
-constexpr int kFC = 8;            // frames per staged chunk
+constexpr int kFC = 8;             // frames per staged chunk
 constexpr int kThreadsC = 512;
-constexpr int kColsI = 3 * kTI;   // 192
-constexpr int kColsJ = 3 * kTJ;   // 384
-constexpr int kCols = kColsI + kColsJ;                 // 576 doubles per frame
-constexpr int kPerThread = kFC * kCols / kThreadsC;    // 9 staged elements per thread
-static_assert(kFC * kCols % kThreadsC == 0, "staging must divide evenly");
+constexpr int kFlushChunks = 8;    // promote FP32 -> FP64 every 64 frames
+constexpr int kTileFloats = 3 * kTile;   // 384 floats per tile-frame
 
 __device__ __forceinline__ float fast_sqrt(float x) {
     float r;
@@ -33,74 +33,84 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 }
 
 struct ContactSmem {
-    float si[2][kFC][3][kTI];
-    float sj[2][kFC][3][kTJ];
-    double offs[kCols];
+    double tot[32 * kThreadsC];            // [pair][thread] -> conflict-free flush
+    float si[2][kFC][3][kTile];
+    float sj[2][kFC][3][kTile];
 };
 
 __global__ void __launch_bounds__(kThreadsC, 1)
-contact_sum_kernel(const double* __restrict__ x, int64_t ld, int64_t T, int N,
-                   const double* __restrict__ mean, int n_ti, int n_tj, int n_seg,
-                   double* __restrict__ out, int64_t out_ld) {
-    __shared__ ContactSmem sm;
+contact_sum_kernel(const float* __restrict__ p32, int64_t T, int N, const double* __restrict__ mean,
+                   int n_tiles, int n_seg, double* __restrict__ out, int64_t out_ld) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ContactSmem& sm = *reinterpret_cast<ContactSmem*>(smem_raw);
 
-    // decode (bi, bj): bj >= bi/2
     int bi = 0, rem = blockIdx.x;
-    while (rem >= n_tj - bi / 2) { rem -= n_tj - bi / 2; ++bi; }
-    const int bj = bi / 2 + rem;
+    while (rem >= n_tiles - bi) { rem -= n_tiles - bi; ++bi; }
+    const int bj = bi + rem;
     const int seg = blockIdx.y;
     const int64_t f_begin = T * seg / n_seg;
     const int64_t f_end = T * (seg + 1) / n_seg;
 
     const int tid = threadIdx.x;
-    const int ti = tid & 15;     // i group: nodes 4ti..4ti+3
-    const int tj = tid >> 4;     // j group: nodes 4tj..4tj+3
+    const int ti = tid & 15;     // i nodes: 4ti..4ti+3 and 64+4ti..64+4ti+3
+    const int tj = tid >> 4;     // j nodes: 4tj..4tj+3
 
-    // reference point: mean position of a node in the middle of the i-tile
-    int nref = kTI * bi + kTI / 2;
-    if (nref > N - 1) nref = N - 1;
-    for (int c = tid; c < kCols; c += kThreadsC) {
-        const int64_t gcol = (c < kColsI) ? (int64_t)kColsI * bi + c : (int64_t)kColsJ * bj + (c - kColsI);
-        sm.offs[c] = mean[gcol] - mean[3 * nref + (c % 3)];
-    }
-    __syncthreads();
-
-    auto load_chunk = [&](int64_t f0, double (&v)[kPerThread]) {
+    // reference offset between the two tiles: x_i - x_j = a_i - (b_j + (ref_J - ref_I))
+    int ri = kTile * bi + kTile / 2, rj = kTile * bj + kTile / 2;
+    if (ri > N - 1) ri = N - 1;
+    if (rj > N - 1) rj = N - 1;
+    float roff[3];
 #pragma unroll
-        for (int q = 0; q < kPerThread; ++q) {
-            const int e = tid + kThreadsC * q;
-            const int fr = e / kCols;
-            const int c = e - fr * kCols;
-            const int64_t f = f0 + fr;
-            const int64_t gcol = (c < kColsI) ? (int64_t)kColsI * bi + c
-                                              : (int64_t)kColsJ * bj + (c - kColsI);
-            v[q] = (f < f_end) ? __ldg(x + f * ld + gcol) : 0.0;
+    for (int c = 0; c < 3; ++c) roff[c] = (float)(mean[3 * rj + c] - mean[3 * ri + c]);
+
+    // staging: 8 frames x (i tile + j tile) x 96 float4 = 1536 float4 per chunk, 3 per thread
+    auto load_chunk = [&](int64_t f0, float4 (&v)[3]) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int e = tid + kThreadsC * q;        // 0..1535
+            const int fl = e / 192;
+            const int r = e - fl * 192;
+            const int sel = r / 96;                   // 0 = i tile, 1 = j tile
+            const int w = r - sel * 96;               // float4 index inside the tile-frame
+            const int64_t f = f0 + fl;
+            if (f < f_end) {
+                const float4* src = reinterpret_cast<const float4*>(
+                    p32 + (f * n_tiles + (sel ? bj : bi)) * kTileFloats) + w;
+                v[q] = __ldg(src);
+            } else {
+                v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
     };
-    auto store_chunk = [&](int buf, const double (&v)[kPerThread]) {
+    auto store_chunk = [&](int buf, const float4 (&v)[3]) {
 #pragma unroll
-        for (int q = 0; q < kPerThread; ++q) {
+        for (int q = 0; q < 3; ++q) {
             const int e = tid + kThreadsC * q;
-            const int fr = e / kCols;
-            const int c = e - fr * kCols;
-            const float val = (float)(v[q] + sm.offs[c]);
-            if (c < kColsI) {
-                sm.si[buf][fr][c % 3][c / 3] = val;
+            const int fl = e / 192;
+            const int r = e - fl * 192;
+            const int sel = r / 96;
+            const int w = r - sel * 96;
+            const int c = w / 32;
+            float4 x = v[q];
+            if (sel) {
+                const float o = roff[c];
+                x.x += o; x.y += o; x.z += o; x.w += o;
+                *reinterpret_cast<float4*>(&sm.sj[buf][fl][0][0] + 4 * w) = x;
             } else {
-                const int cc = c - kColsI;
-                sm.sj[buf][fr][cc % 3][cc / 3] = val;
+                *reinterpret_cast<float4*>(&sm.si[buf][fl][0][0] + 4 * w) = x;
             }
         }
     };
 
-    double tot[4][4];
-    float acc[4][4];
+    float acc[8][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) { tot[a][b] = 0.0; acc[a][b] = 0.f; }
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll
+    for (int p = 0; p < 32; ++p) sm.tot[p * kThreadsC + tid] = 0.0;
 
-    double stage[kPerThread];
+    float4 stage[3];
     load_chunk(f_begin, stage);
     store_chunk(0, stage);
     __syncthreads();
@@ -110,52 +120,49 @@ contact_sum_kernel(const double* __restrict__ x, int64_t ld, int64_t T, int N,
     for (int64_t f0 = f_begin; f0 < f_end; f0 += kFC, ++chunk_idx) {
         const bool has_next = (f0 + kFC) < f_end;
         if (has_next) load_chunk(f0 + kFC, stage);
-
         const int nf = (int)((f_end - f0) < kFC ? (f_end - f0) : kFC);
-        if (nf == kFC) {
-#pragma unroll
-            for (int fl = 0; fl < kFC; ++fl) {
-                const float4 ax = *reinterpret_cast<const float4*>(&sm.si[buf][fl][0][4 * ti]);
-                const float4 ay = *reinterpret_cast<const float4*>(&sm.si[buf][fl][1][4 * ti]);
-                const float4 az = *reinterpret_cast<const float4*>(&sm.si[buf][fl][2][4 * ti]);
-                const float4 bx = *reinterpret_cast<const float4*>(&sm.sj[buf][fl][0][4 * tj]);
-                const float4 by = *reinterpret_cast<const float4*>(&sm.sj[buf][fl][1][4 * tj]);
-                const float4 bz = *reinterpret_cast<const float4*>(&sm.sj[buf][fl][2][4 * tj]);
-                const float axs[4] = {ax.x, ax.y, ax.z, ax.w}, ays[4] = {ay.x, ay.y, ay.z, ay.w},
-                            azs[4] = {az.x, az.y, az.z, az.w};
-                const float bxs[4] = {bx.x, bx.y, bx.z, bx.w}, bys[4] = {by.x, by.y, by.z, by.w},
-                            bzs[4] = {bz.x, bz.y, bz.z, bz.w};
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const float dx = axs[a] - bxs[b];
-                        const float dy = ays[a] - bys[b];
-                        const float dz = azs[a] - bzs[b];
-                        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                        acc[a][b] += fast_sqrt(d2);
-                    }
+#pragma unroll 2
+        for (int fl = 0; fl < nf; ++fl) {
+            float ax[8], ay[8], az[8], bx[4], by[4], bz[4];
+            {
+                const float4 t0 = *reinterpret_cast<const float4*>(&sm.si[buf][fl][0][4 * ti]);
+                const float4 t1 = *reinterpret_cast<const float4*>(&sm.si[buf][fl][0][64 + 4 * ti]);
+                ax[0] = t0.x; ax[1] = t0.y; ax[2] = t0.z; ax[3] = t0.w;
+                ax[4] = t1.x; ax[5] = t1.y; ax[6] = t1.z; ax[7] = t1.w;
+                const float4 u0 = *reinterpret_cast<const float4*>(&sm.si[buf][fl][1][4 * ti]);
+                const float4 u1 = *reinterpret_cast<const float4*>(&sm.si[buf][fl][1][64 + 4 * ti]);
+                ay[0] = u0.x; ay[1] = u0.y; ay[2] = u0.z; ay[3] = u0.w;
+                ay[4] = u1.x; ay[5] = u1.y; ay[6] = u1.z; ay[7] = u1.w;
+                const float4 v0 = *reinterpret_cast<const float4*>(&sm.si[buf][fl][2][4 * ti]);
+                const float4 v1 = *reinterpret_cast<const float4*>(&sm.si[buf][fl][2][64 + 4 * ti]);
+                az[0] = v0.x; az[1] = v0.y; az[2] = v0.z; az[3] = v0.w;
+                az[4] = v1.x; az[5] = v1.y; az[6] = v1.z; az[7] = v1.w;
+                const float4 w0 = *reinterpret_cast<const float4*>(&sm.sj[buf][fl][0][4 * tj]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&sm.sj[buf][fl][1][4 * tj]);
+                const float4 w2 = *reinterpret_cast<const float4*>(&sm.sj[buf][fl][2][4 * tj]);
+                bx[0] = w0.x; bx[1] = w0.y; bx[2] = w0.z; bx[3] = w0.w;
+                by[0] = w1.x; by[1] = w1.y; by[2] = w1.z; by[3] = w1.w;
+                bz[0] = w2.x; bz[1] = w2.y; bz[2] = w2.z; bz[3] = w2.w;
             }
-        } else {
-            for (int fl = 0; fl < nf; ++fl) {
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 8; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const float dx = sm.si[buf][fl][0][4 * ti + a] - sm.sj[buf][fl][0][4 * tj + b];
-                        const float dy = sm.si[buf][fl][1][4 * ti + a] - sm.sj[buf][fl][1][4 * tj + b];
-                        const float dz = sm.si[buf][fl][2][4 * ti + a] - sm.sj[buf][fl][2][4 * tj + b];
-                        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                        acc[a][b] += fast_sqrt(d2);
-                    }
-            }
+                for (int b = 0; b < 4; ++b) {
+                    const float dx = ax[a] - bx[b];
+                    const float dy = ay[a] - by[b];
+                    const float dz = az[a] - bz[b];
+                    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    acc[a][b] += fast_sqrt(d2);
+                }
         }
-        // promote FP32 partial sums to FP64 every 16 frames (and at the end)
-        if ((chunk_idx & 1) || !has_next) {
+        if ((chunk_idx % kFlushChunks) == kFlushChunks - 1 || !has_next) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 8; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) { tot[a][b] += (double)acc[a][b]; acc[a][b] = 0.f; }
+                for (int b = 0; b < 4; ++b) {
+                    sm.tot[(a * 4 + b) * kThreadsC + tid] += (double)acc[a][b];
+                    acc[a][b] = 0.f;
+                }
         }
         if (has_next) store_chunk(buf ^ 1, stage);
         __syncthreads();
@@ -163,26 +170,26 @@ contact_sum_kernel(const double* __restrict__ x, int64_t ld, int64_t T, int N,
     }
 
     double* o = out + (size_t)seg * out_ld * out_ld;
-    const int64_t row0 = (int64_t)kTI * bi + 4 * ti;
-    const int64_t col0 = (int64_t)kTJ * bj + 4 * tj;
+    const int64_t col0 = (int64_t)kTile * bj + 4 * tj;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        double* p = o + (row0 + a) * out_ld + col0;
-        *reinterpret_cast<double2*>(p) = make_double2(tot[a][0], tot[a][1]);
-        *reinterpret_cast<double2*>(p + 2) = make_double2(tot[a][2], tot[a][3]);
+    for (int a = 0; a < 8; ++a) {
+        const int64_t row = (int64_t)kTile * bi + ((a < 4) ? (4 * ti + a) : (64 + 4 * ti + (a - 4)));
+        double* p = o + row * out_ld + col0;
+        *reinterpret_cast<double2*>(p) =
+            make_double2(sm.tot[(a * 4 + 0) * kThreadsC + tid], sm.tot[(a * 4 + 1) * kThreadsC + tid]);
+        *reinterpret_cast<double2*>(p + 2) =
+            make_double2(sm.tot[(a * 4 + 2) * kThreadsC + tid], sm.tot[(a * 4 + 3) * kThreadsC + tid]);
     }
 }
 
 }  // namespace
 
-int launch_contact_sum(wisp_ctx* ctx, const double* d_x, int64_t T, int N, int64_t ld,
-                       const double* d_mean, double* d_out, cudaStream_t st) {
+int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, const double* d_mean,
+                       double* d_out, cudaStream_t st) {
     WISP_CHECK(T > 0 && N > 0, "contact: empty input (T=%lld, N=%d)", (long long)T, N);
     const int64_t n_pad = round_up(N, kTile);
-    WISP_CHECK(3 * n_pad <= ld, "contact: ld=%lld too small for N=%d", (long long)ld, N);
-    const int n_ti = (int)(n_pad / kTI), n_tj = (int)(n_pad / kTJ);
-    int n_items = 0;
-    for (int bi = 0; bi < n_ti; ++bi) n_items += n_tj - bi / 2;
+    const int n_tiles = (int)(n_pad / kTile);
+    const int n_items = n_tiles * (n_tiles + 1) / 2;
     const int chunks_total = (int)((T + kFC - 1) / kFC);
     const int n_seg = wisp_pick_segments(n_items, chunks_total, ctx->sm_count, 16);
     double* part = d_out;
@@ -191,11 +198,12 @@ int launch_contact_sum(wisp_ctx* ctx, const double* d_x, int64_t T, int N, int64
         WISP_TRY(wisp_scratch(ctx, SCR_CONTACT_PART, (size_t)n_seg * n_pad * n_pad * 8, &p));
         part = (double*)p;
     }
+    const int smem = (int)sizeof(ContactSmem);
+    WISP_CUDA(cudaFuncSetAttribute(contact_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dim3 grid(n_items, n_seg);
-    contact_sum_kernel<<<grid, kThreadsC, 0, st>>>(d_x, ld, T, N, d_mean, n_ti, n_tj, n_seg, part,
-                                                   n_pad);
+    contact_sum_kernel<<<grid, kThreadsC, smem, st>>>(d_p32, T, N, d_mean, n_tiles, n_seg, part, n_pad);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
-    if (n_seg > 1) WISP_TRY(launch_reduce_partials(ctx, part, n_seg, n_pad, d_out, kTI, kTJ, st));
+    if (n_seg > 1) WISP_TRY(launch_reduce_partials(ctx, part, n_seg, n_pad, d_out, kTile, kTile, st));
     return 0;
 }

@@ -40,6 +40,8 @@ struct EnumParams {
     double cutoff;
     double bound;
     int quirk;
+    int count_only;          // 1: count paths, do not store them
+    int cap;                 // count-only early exit: stop once more than cap paths were seen
     // outputs
     int32_t* out_count;      // [0] n paths, [1] n node entries, [2] overflow flags
     unsigned long long* expansions;
@@ -55,6 +57,7 @@ struct EnumParams {
 __device__ __forceinline__ void emit_path(const EnumParams& P, int pair, const int32_t* nodes,
                                           int depth, int last, double len) {
     const int slot = atomicAdd(&P.out_count[0], 1);
+    if (P.count_only) return;
     const int off = atomicAdd(&P.out_count[1], depth + 1);
     if (slot >= P.cap_paths || off + depth + 1 > P.cap_nodes) {
         atomicOr(&P.out_count[2], 1);
@@ -127,7 +130,10 @@ __global__ void dfs_kernel(EnumParams P, const double* __restrict__ f_len,
     cur[d0 - 1] = P.adj_ptr[nodes[d0 - 1]];
     int depth = d0;
     unsigned long long nexp = 0;
+    unsigned it = 0;
     while (depth >= d0) {
+        if (P.count_only && (++it & 63u) == 0 &&
+            *reinterpret_cast<volatile int32_t*>(P.out_count) > P.cap) break;
         const int u = nodes[depth - 1];
         const int e = cur[depth - 1];
         if (e >= P.adj_ptr[u + 1]) { --depth; continue; }
@@ -295,8 +301,11 @@ extern "C" int wisp_get_paths(wisp_ctx* ctx, const double* w, int N, const int32
     unsigned long long expansions_total = 0;
     int passes = 0;
 
-    while (num_paths < number_of_paths) {                                    // :56
-        std::vector<HostPath> temp_paths;
+    // One enumeration pass on the device.  count_only: only the number of paths <= cutoff is
+    // returned (early exit once it exceeds `cap`); otherwise the paths come back per pair,
+    // each pair's list sorted by (length, nodes) (:145) and concatenated in pair order.
+    auto run_pass = [&](double pass_cutoff, bool count_only, int cap, int64_t* count_out,
+                        std::vector<HostPath>* out_paths) -> int {
         for (;;) {   // retry loop on capacity overflow
             double te = now_ms();
             const int cap_nodes = cap_paths * 24;
@@ -308,10 +317,12 @@ extern "C" int wisp_get_paths(wisp_ctx* ctx, const double* w, int N, const int32
             EnumParams P;
             P.adj_ptr = (const int32_t*)d_adj_ptr; P.adj_idx = (const int32_t*)d_adj_idx;
             P.adj_w = (const double*)d_adj_w; P.dist = (const double*)d_dist;
-            P.pairs = (const int32_t*)d_pairs; P.N = N; P.cutoff = cutoff;
-            P.bound = cutoff + 1e-9 * std::max(1.0, std::fabs(cutoff));
+            P.pairs = (const int32_t*)d_pairs; P.N = N; P.cutoff = pass_cutoff;
+            P.bound = pass_cutoff + 1e-9 * std::max(1.0, std::fabs(pass_cutoff));
             P.quirk = quirk;
-            int32_t* cnt = (int32_t*)d_cnt;                  // [0..2] out counters, [4],[5] frontier counts
+            P.count_only = count_only ? 1 : 0;
+            P.cap = cap;
+            int32_t* cnt = (int32_t*)d_cnt;                  // [0..2] out counters, [4] frontier count
             P.out_count = cnt;
             P.expansions = (unsigned long long*)(cnt + 8);
             P.out_len = (double*)d_out;
@@ -321,7 +332,6 @@ extern "C" int wisp_get_paths(wisp_ctx* ctx, const double* w, int N, const int32
             P.out_nodes = P.out_n + cap_paths;
             P.cap_paths = cap_paths; P.cap_nodes = cap_nodes;
             WISP_CUDA(cudaMemsetAsync(d_cnt, 0, 64, st));
-            // frontier double buffer
             char* fb = (char*)d_front;
             double* f_len[2]; int32_t* f_meta[2]; int32_t* f_nodes[2];
             for (int b = 0; b < 2; ++b) {
@@ -329,8 +339,7 @@ extern "C" int wisp_get_paths(wisp_ctx* ctx, const double* w, int N, const int32
                 f_meta[b] = (int32_t*)fb; fb += (size_t)cap_front * 8;
                 f_nodes[b] = (int32_t*)fb; fb += (size_t)cap_front * kMaxLen * 4;
             }
-            // seed frontier: one record [s] per pair
-            {
+            {   // seed frontier: one record [s] per pair
                 std::vector<double> hl(n_pairs, 0.0);
                 std::vector<int32_t> hm(2 * n_pairs), hn((size_t)n_pairs * kMaxLen, 0);
                 for (int p = 0; p < n_pairs; ++p) { hm[2 * p] = p; hm[2 * p + 1] = 1; hn[(size_t)p * kMaxLen] = pairs[2 * p]; }
@@ -341,25 +350,25 @@ extern "C" int wisp_get_paths(wisp_ctx* ctx, const double* w, int N, const int32
             }
             int n_front = n_pairs, cur = 0;
             bool overflow = false;
+            int32_t hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (int level = 0; level < kMaxExpandLevels && n_front > 0 && n_front < kTargetPrefixes; ++level) {
                 WISP_CUDA(cudaMemsetAsync(cnt + 4, 0, 4, st));
                 expand_level_kernel<<<(n_front + 127) / 128, 128, 0, st>>>(
                     P, f_len[cur], f_meta[cur], f_nodes[cur], n_front, f_len[cur ^ 1], f_meta[cur ^ 1],
                     f_nodes[cur ^ 1], cnt + 4, cap_front);
                 ctx->launches++;
-                int32_t hc[8];
                 WISP_CUDA(cudaMemcpyAsync(hc, cnt, 32, cudaMemcpyDeviceToHost, st));
                 WISP_CUDA(cudaStreamSynchronize(st));
                 if (hc[2] & 4) { overflow = true; cap_front *= 4; break; }
                 if (hc[2] & 1) { overflow = true; cap_paths *= 4; break; }
                 n_front = hc[4];
                 cur ^= 1;
+                if (count_only && hc[0] > cap) { n_front = 0; break; }
             }
             if (!overflow && n_front > 0) {
                 dfs_kernel<<<(n_front + 63) / 64, 64, 0, st>>>(P, f_len[cur], f_meta[cur], f_nodes[cur], n_front);
                 ctx->launches++;
             }
-            int32_t hc[8];
             unsigned long long hexp = 0;
             if (!overflow) {
                 WISP_CUDA(cudaMemcpyAsync(hc, cnt, 32, cudaMemcpyDeviceToHost, st));
@@ -371,43 +380,96 @@ extern "C" int wisp_get_paths(wisp_ctx* ctx, const double* w, int N, const int32
             }
             if (overflow) continue;
             expansions_total += hexp;
-            const int np = hc[0], nn = hc[1];
-            std::vector<double> hl(np);
-            std::vector<int32_t> hp(np), ho(np), hn(np), hnodes(nn);
-            if (np) {
-                WISP_CUDA(cudaMemcpy(hl.data(), P.out_len, (size_t)np * 8, cudaMemcpyDeviceToHost));
-                WISP_CUDA(cudaMemcpy(hp.data(), P.out_pair, (size_t)np * 4, cudaMemcpyDeviceToHost));
-                WISP_CUDA(cudaMemcpy(ho.data(), P.out_off, (size_t)np * 4, cudaMemcpyDeviceToHost));
-                WISP_CUDA(cudaMemcpy(hn.data(), P.out_n, (size_t)np * 4, cudaMemcpyDeviceToHost));
-                WISP_CUDA(cudaMemcpy(hnodes.data(), P.out_nodes, (size_t)nn * 4, cudaMemcpyDeviceToHost));
+            *count_out = hc[0];
+            if (!count_only && out_paths) {
+                const int np = hc[0], nn = hc[1];
+                std::vector<double> hl(np);
+                std::vector<int32_t> hp(np), ho(np), hn(np), hnodes(nn);
+                if (np) {
+                    WISP_CUDA(cudaMemcpy(hl.data(), P.out_len, (size_t)np * 8, cudaMemcpyDeviceToHost));
+                    WISP_CUDA(cudaMemcpy(hp.data(), P.out_pair, (size_t)np * 4, cudaMemcpyDeviceToHost));
+                    WISP_CUDA(cudaMemcpy(ho.data(), P.out_off, (size_t)np * 4, cudaMemcpyDeviceToHost));
+                    WISP_CUDA(cudaMemcpy(hn.data(), P.out_n, (size_t)np * 4, cudaMemcpyDeviceToHost));
+                    WISP_CUDA(cudaMemcpy(hnodes.data(), P.out_nodes, (size_t)nn * 4, cudaMemcpyDeviceToHost));
+                }
+                enum_ms += now_ms() - te;
+                double th = now_ms();
+                std::vector<std::vector<HostPath>> per_pair(n_pairs);
+                for (int k = 0; k < np; ++k) {
+                    HostPath hpth;
+                    hpth.len = hl[k];
+                    hpth.nodes.assign(hnodes.begin() + ho[k], hnodes.begin() + ho[k] + hn[k]);
+                    per_pair[hp[k]].push_back(std::move(hpth));
+                }
+                for (int p = 0; p < n_pairs; ++p) {
+                    std::sort(per_pair[p].begin(), per_pair[p].end(), path_less);
+                    for (auto& q : per_pair[p]) out_paths->push_back(std::move(q));
+                }
+                host_ms += now_ms() - th;
+            } else {
+                enum_ms += now_ms() - te;
             }
-            enum_ms += now_ms() - te;
-            double th = now_ms();
-            // per pair: sort by (length, nodes) (:145), concatenate in pair order
-            std::vector<std::vector<HostPath>> per_pair(n_pairs);
-            for (int k = 0; k < np; ++k) {
-                HostPath hpth;
-                hpth.len = hl[k];
-                hpth.nodes.assign(hnodes.begin() + ho[k], hnodes.begin() + ho[k] + hn[k]);
-                per_pair[hp[k]].push_back(std::move(hpth));
+            return 0;
+        }
+    };
+
+    // A path and its reverse can both be enumerated only when (s,t) and (t,s) are both pairs;
+    // otherwise no two enumerated paths are "redundant" and pass counts need no dedupe.
+    bool has_reverse = false;
+    for (int p = 0; p < n_pairs && !has_reverse; ++p)
+        for (int q = 0; q < n_pairs; ++q)
+            if (pairs[2 * p] == pairs[2 * q + 1] && pairs[2 * p + 1] == pairs[2 * q]) { has_reverse = true; break; }
+
+    const int64_t K = number_of_paths;
+    const int cap_count = (int)std::min<int64_t>(4 * K + 64, 1 << 30);
+    double prev_cutoff = -1.0;     // largest cutoff known to hold fewer than K paths
+    while (num_paths < number_of_paths) {                                    // :56
+        std::vector<HostPath> temp_paths;
+        if (has_reverse) {
+            // literal: full pass, per-pass dedupe decides the count (:157-179)
+            int64_t n = 0;
+            WISP_TRY(run_pass(cutoff, false, 0, &n, &temp_paths));
+            if (temp_paths.size() != 1) dedupe(temp_paths);
+            num_paths = (int64_t)temp_paths.size();
+        } else {
+            // Every pass's list is a subset of the next one's, and only the K smallest of
+            // the last one survive the final sort + truncate.  So: count first (early exit
+            // beyond 4K); fetch paths only from the last pass, and when that pass holds far
+            // more than K, only those below a length tau (found by bisection on the count)
+            // that still contains at least K of them.
+            int64_t n = 0;
+            WISP_TRY(run_pass(cutoff, true, cap_count, &n, nullptr));
+            if (n < K) {
+                num_paths = n;
+                prev_cutoff = cutoff;
+            } else if (n <= cap_count) {
+                WISP_TRY(run_pass(cutoff, false, 0, &n, &temp_paths));
+                num_paths = (int64_t)temp_paths.size();
+            } else {
+                double lo = prev_cutoff, hi = cutoff, tau = cutoff;
+                bool found = false;
+                for (int itb = 0; itb < 60; ++itb) {
+                    const double mid = 0.5 * (lo + hi);
+                    if (!(mid > lo && mid < hi)) break;
+                    int64_t c = 0;
+                    WISP_TRY(run_pass(mid, true, cap_count, &c, nullptr));
+                    if (c < K) lo = mid;
+                    else if (c > cap_count) hi = mid;
+                    else { tau = mid; found = true; break; }
+                }
+                if (!found) tau = hi;      // massive ties: take everything up to hi
+                int64_t c = 0;
+                WISP_TRY(run_pass(tau, false, 0, &c, &temp_paths));
+                num_paths = n;             // > 4K: certainly != K, the final list is truncated
             }
-            for (int p = 0; p < n_pairs; ++p) {
-                std::sort(per_pair[p].begin(), per_pair[p].end(), path_less);
-                for (auto& q : per_pair[p]) temp_paths.push_back(std::move(q));
-            }
-            host_ms += now_ms() - th;
-            break;
         }
         double th = now_ms();
-        if (temp_paths.size() != 1) dedupe(temp_paths);                      // :157
-        num_paths = (int64_t)temp_paths.size();                              // :179
         for (auto& q : temp_paths) paths.push_back(q);
         cutoff += 0.1;                                                       // :187
         ++passes;
         host_ms += now_ms() - th;
-        WISP_CHECK(passes < 100000, "get_paths: fewer than %d paths exist between the selections", number_of_paths);
         // the reference never terminates when fewer than K simple paths exist (App. A.6):
-        // detect exhaustion (cutoff beyond any simple path) and fail loudly instead.
+        // past the longest possible simple path nothing new can appear -- fail loudly instead.
         WISP_CHECK(cutoff <= max_simple_len + 0.2 || num_paths >= number_of_paths,
                    "get_paths: only %lld simple paths exist, %d requested", (long long)num_paths, number_of_paths);
     }

@@ -41,6 +41,7 @@ class FramePipeline:
         self.d_align_idx = torch.as_tensor(np.asarray(align_idx, dtype=np.int32), device=dev)
         self.n_align = int(self.d_align_idx.numel())
         self.d_x = torch.zeros((self.tpad, self.ld), dtype=f64, device=dev)
+        self.d_p32 = torch.zeros((self.T, self.npad // 128, 3, 128), dtype=torch.float32, device=dev)
         self.d_colsum = torch.zeros(self.ld, dtype=f64, device=dev)
         self.d_mean = torch.zeros(self.ld, dtype=f64, device=dev)
         self.d_sums = torch.zeros((2, self.npad, self.npad), dtype=f64, device=dev)   # [G || D]
@@ -56,7 +57,9 @@ class FramePipeline:
 
     # -- stages (all on torch's current stream) ------------------------------------------
     def _stream(self):
-        return torch.cuda.current_stream(self.dev).cuda_stream
+        # 0 is torch's legacy default stream; the C ABI reads NULL as "the context's own
+        # stream", so name the legacy stream explicitly (cudaStreamLegacy == 0x1)
+        return torch.cuda.current_stream(self.dev).cuda_stream or 1
 
     def com(self, d_coords, frames=None, row0=0):
         t = self.T if frames is None else frames
@@ -72,14 +75,15 @@ class FramePipeline:
         if self.distributed:
             torch.distributed.all_reduce(self.d_colsum, group=self.group)
         torch.div(self.d_colsum, float(self.T_total), out=self.d_mean)
-        self.ctx.dev_center(self.d_x.data_ptr(), self.T, self.N, self.d_mean.data_ptr(), stream=s)
+        self.ctx.dev_center(self.d_x.data_ptr(), self.T, self.N, self.d_mean.data_ptr(),
+                            d_p32=self.d_p32.data_ptr(), stream=s)
 
     def gram(self):
         self.ctx.dev_gram(self.d_x.data_ptr(), self.T, self.ld, self.N, 3,
                           self.d_sums[0].data_ptr(), stream=self._stream())
 
     def contact(self):
-        self.ctx.dev_contact_sum(self.d_x.data_ptr(), self.T, self.N, self.d_mean.data_ptr(),
+        self.ctx.dev_contact_sum(self.d_p32.data_ptr(), self.T, self.N, self.d_mean.data_ptr(),
                                  self.d_sums[1].data_ptr(), stream=self._stream())
 
     def reduce_and_epilogue(self):
@@ -154,6 +158,5 @@ class FramePipeline:
             k2_flop_executed=2.0 * pairs * 128 * 128 * 3 * self.tpad,
             k2_flop_full=6.0 * self.N * self.N * self.T,
             k3_pairframes_full=float(self.N) * self.N * self.T,
-            k3_pairframes_executed=sum((self.npad // 128 - bi // 2) for bi in range(self.npad // 64))
-            * 64.0 * 128.0 * self.T,
+            k3_pairframes_executed=pairs * 128.0 * 128.0 * self.T,
         )
