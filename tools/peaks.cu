@@ -56,6 +56,48 @@ __global__ void mufu_peak(float* out, int iters) {
     for (int i = 0; i < 8; ++i) s += c[i];
     if (s == 123.456f) out[0] = s;
 }
+__global__ void ffma2_peak(float* out, int iters) {
+    unsigned long long c[16];
+    for (int i = 0; i < 16; ++i) c[i] = (unsigned long long)i * 0x3f8000003f800000ull;
+    float af = 1.0f + threadIdx.x * 1e-7f, bf = 1e-7f;
+    unsigned long long a, b;
+    asm("mov.b64 %0, {%1,%1};" : "=l"(a) : "f"(af));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(b) : "f"(bf));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(c[i]) : "l"(a), "l"(b));
+    }
+    unsigned long long s = 0;
+    for (int i = 0; i < 16; ++i) s ^= c[i];
+    if (s == 123456ull) out[0] = 1.f;
+}
+// 1 MUFU.SQRT + 3.5 packed FP32 instructions per element: the K3 inner-loop mix
+__global__ void k3mix_peak(float* out, int iters) {
+    unsigned long long c[8], d[8];
+    float x = 1.0f + threadIdx.x;
+    for (int i = 0; i < 8; ++i) { asm("mov.b64 %0, {%1,%1};" : "=l"(c[i]) : "f"(x + i)); d[i] = c[i]; }
+    unsigned long long a;
+    asm("mov.b64 %0, {%1,%1};" : "=l"(a) : "f"(0.999f));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            unsigned long long t;
+            asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(c[i]), "l"(a));
+            asm volatile("mul.rn.f32x2 %0, %0, %0;" : "+l"(t));
+            asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(t) : "l"(a));
+            asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(t) : "l"(c[i]));
+            float lo, hi;
+            asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(t));
+            asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(lo));
+            asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(hi));
+            asm("mov.b64 %0, {%1,%2};" : "=l"(t) : "f"(lo), "f"(hi));
+            asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(d[i]) : "l"(t));
+        }
+    }
+    unsigned long long s = 0;
+    for (int i = 0; i < 8; ++i) s ^= d[i];
+    if (s == 123456ull) out[0] = 1.f;
+}
 // FADD + FMNMX mix (min-plus relaxation without predecessors)
 __global__ void minplus_peak(float* out, int iters) {
     float c[16];
@@ -102,11 +144,16 @@ int main() {
     const double ffma_tf = lanes * it * 16 * 2.0 / (t * 1e-3) / 1e12;
     t = best_ms([&] { mufu_peak<<<blocks, threads>>>((float*)buf, it); });
     const double mufu_tops = lanes * it * 8.0 / (t * 1e-3) / 1e12;
+    t = best_ms([&] { ffma2_peak<<<blocks, threads>>>((float*)buf, it); });
+    const double ffma2_tf = lanes * it * 16 * 4.0 / (t * 1e-3) / 1e12;
+    t = best_ms([&] { k3mix_peak<<<blocks, threads>>>((float*)buf, it); });
+    const double k3mix_tpf = lanes * it * 16.0 / (t * 1e-3) / 1e12;
     t = best_ms([&] { minplus_peak<<<blocks, threads>>>((float*)buf, it); });
     const double minplus_trelax = lanes * it * 16.0 / (t * 1e-3) / 1e12;
     CK(cudaDeviceSynchronize());
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"fp64_dmma_tflops\": %.2f, \"fp64_fma_tflops\": %.2f, "
-           "\"fp32_fma_tflops\": %.2f, \"mufu_sqrt_tops\": %.3f, \"fp32_minplus_trelax\": %.3f}\n",
-           p.name, sms, dmma_tf, dfma_tf, ffma_tf, mufu_tops, minplus_trelax);
+           "\"fp32_fma_tflops\": %.2f, \"mufu_sqrt_tops\": %.3f, \"fp32_minplus_trelax\": %.3f, \"fp32_ffma2_tflops\": %.2f, "
+           "\"k3_mix_tpairframes\": %.3f}\n",
+           p.name, sms, dmma_tf, dfma_tf, ffma_tf, mufu_tops, minplus_trelax, ffma2_tf, k3mix_tpf);
     return 0;
 }

@@ -14,15 +14,15 @@
 //
 // One CTA = one 128 x 128 pair tile (upper triangle only) x one frame segment; 512 threads,
 // each owns 8 x 4 pairs.  Frames are staged 8 at a time (float4 loads, double-buffered).
-// Per pair-frame: 3 FADD + FMUL + 2 FFMA + MUFU.SQRT + FADD -- the kernel is co-limited by
-// the MUFU pipe (16 lanes/clk/SM) and FP32 issue.  FP32 partial sums are promoted every 64
+// Per pair-frame: 3 sub + mul + 2 fma + MUFU.SQRT + add, the FP32 part issued as packed
+// FADD2/FMUL2/FFMA2 over two pairs -- the kernel is bound by the MUFU pipe (16 lanes/clk/SM).  FP32 partial sums are promoted every 64
 // frames into FP64 per-pair totals kept in shared memory (128 KB), written once at the end.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
 constexpr int kFC = 8;             // frames per staged chunk
-constexpr int kThreadsC = 512;
 constexpr int kFlushChunks = 8;    // promote FP32 -> FP64 every 64 frames
 constexpr int kTileFloats = 3 * kTile;   // 384 floats per tile-frame
 
@@ -32,13 +32,47 @@ __device__ __forceinline__ float fast_sqrt(float x) {
     return r;
 }
 
+// Blackwell packed FP32x2 arithmetic (SASS FADD2 / FMUL2 / FFMA2): two pairs per issue
+// slot, which takes the FP32 issue pressure off the MUFU-bound loop (4.5 instead of 8 issue
+// slots per pair-frame).  A scalar `a` is broadcast to both halves by ptxas (R.F32 operand).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 struct ContactSmem {
-    double tot[32 * kThreadsC];            // [pair][thread] -> conflict-free flush
+    double tot[kTile * kTile];             // [pair][thread] -> conflict-free flush
     float si[2][kFC][3][kTile];
     float sj[2][kFC][3][kTile];
 };
 
-__global__ void __launch_bounds__(kThreadsC, 1)
+template <int JH>   // packed j pairs per thread: 2 -> 512 threads x (8x4 pairs), 4 -> 256 x (8x8)
+__global__ void __launch_bounds__(1024 / JH, 1)
 contact_sum_kernel(const float* __restrict__ p32, int64_t T, int N, const double* __restrict__ mean,
                    int n_tiles, int n_seg, double* __restrict__ out, int64_t out_ld) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -51,9 +85,11 @@ contact_sum_kernel(const float* __restrict__ p32, int64_t T, int N, const double
     const int64_t f_begin = T * seg / n_seg;
     const int64_t f_end = T * (seg + 1) / n_seg;
 
+    constexpr int kThreadsC = 1024 / JH;
+    constexpr int kPerThread = 1536 / kThreadsC;      // staged float4 per thread per chunk
     const int tid = threadIdx.x;
     const int ti = tid & 15;     // i nodes: 4ti..4ti+3 and 64+4ti..64+4ti+3
-    const int tj = tid >> 4;     // j nodes: 4tj..4tj+3
+    const int tj = tid >> 4;     // j nodes: 4tj..4tj+3 (and 64+4tj.. when JH == 4)
 
     // reference offset between the two tiles: x_i - x_j = a_i - (b_j + (ref_J - ref_I))
     int ri = kTile * bi + kTile / 2, rj = kTile * bj + kTile / 2;
@@ -64,9 +100,9 @@ contact_sum_kernel(const float* __restrict__ p32, int64_t T, int N, const double
     for (int c = 0; c < 3; ++c) roff[c] = (float)(mean[3 * rj + c] - mean[3 * ri + c]);
 
     // staging: 8 frames x (i tile + j tile) x 96 float4 = 1536 float4 per chunk, 3 per thread
-    auto load_chunk = [&](int64_t f0, float4 (&v)[3]) {
+    auto load_chunk = [&](int64_t f0, float4 (&v)[kPerThread]) {
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < kPerThread; ++q) {
             const int e = tid + kThreadsC * q;        // 0..1535
             const int fl = e / 192;
             const int r = e - fl * 192;
@@ -82,9 +118,9 @@ contact_sum_kernel(const float* __restrict__ p32, int64_t T, int N, const double
             }
         }
     };
-    auto store_chunk = [&](int buf, const float4 (&v)[3]) {
+    auto store_chunk = [&](int buf, const float4 (&v)[kPerThread]) {
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < kPerThread; ++q) {
             const int e = tid + kThreadsC * q;
             const int fl = e / 192;
             const int r = e - fl * 192;
@@ -102,15 +138,15 @@ contact_sum_kernel(const float* __restrict__ p32, int64_t T, int N, const double
         }
     };
 
-    float acc[8][4];
+    f32x2 acc[8][JH];       // packed FP32 partial sums: pairs (a, 2h) and (a, 2h+1)
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+        for (int h = 0; h < JH; ++h) acc[a][h] = pack2(0.f, 0.f);
 #pragma unroll
-    for (int p = 0; p < 32; ++p) sm.tot[p * kThreadsC + tid] = 0.0;
+    for (int p = 0; p < 16 * JH; ++p) sm.tot[p * kThreadsC + tid] = 0.0;
 
-    float4 stage[3];
+    float4 stage[kPerThread];
     load_chunk(f_begin, stage);
     store_chunk(0, stage);
     __syncthreads();
@@ -123,7 +159,8 @@ contact_sum_kernel(const float* __restrict__ p32, int64_t T, int N, const double
         const int nf = (int)((f_end - f0) < kFC ? (f_end - f0) : kFC);
 #pragma unroll 2
         for (int fl = 0; fl < nf; ++fl) {
-            float ax[8], ay[8], az[8], bx[4], by[4], bz[4];
+            float ax[8], ay[8], az[8];
+            f32x2 bx[JH], by[JH], bz[JH];
             {
                 const float4 t0 = *reinterpret_cast<const float4*>(&sm.si[buf][fl][0][4 * ti]);
                 const float4 t1 = *reinterpret_cast<const float4*>(&sm.si[buf][fl][0][64 + 4 * ti]);
@@ -140,28 +177,43 @@ contact_sum_kernel(const float* __restrict__ p32, int64_t T, int N, const double
                 const float4 w0 = *reinterpret_cast<const float4*>(&sm.sj[buf][fl][0][4 * tj]);
                 const float4 w1 = *reinterpret_cast<const float4*>(&sm.sj[buf][fl][1][4 * tj]);
                 const float4 w2 = *reinterpret_cast<const float4*>(&sm.sj[buf][fl][2][4 * tj]);
-                bx[0] = w0.x; bx[1] = w0.y; bx[2] = w0.z; bx[3] = w0.w;
-                by[0] = w1.x; by[1] = w1.y; by[2] = w1.z; by[3] = w1.w;
-                bz[0] = w2.x; bz[1] = w2.y; bz[2] = w2.z; bz[3] = w2.w;
+                bx[0] = pack2(w0.x, w0.y); bx[1] = pack2(w0.z, w0.w);
+                by[0] = pack2(w1.x, w1.y); by[1] = pack2(w1.z, w1.w);
+                bz[0] = pack2(w2.x, w2.y); bz[1] = pack2(w2.z, w2.w);
+                if (JH == 4) {
+                    const float4 x0 = *reinterpret_cast<const float4*>(&sm.sj[buf][fl][0][64 + 4 * tj]);
+                    const float4 x1 = *reinterpret_cast<const float4*>(&sm.sj[buf][fl][1][64 + 4 * tj]);
+                    const float4 x2 = *reinterpret_cast<const float4*>(&sm.sj[buf][fl][2][64 + 4 * tj]);
+                    bx[JH - 2] = pack2(x0.x, x0.y); bx[JH - 1] = pack2(x0.z, x0.w);
+                    by[JH - 2] = pack2(x1.x, x1.y); by[JH - 1] = pack2(x1.z, x1.w);
+                    bz[JH - 2] = pack2(x2.x, x2.y); bz[JH - 1] = pack2(x2.z, x2.w);
+                }
             }
 #pragma unroll
-            for (int a = 0; a < 8; ++a)
+            for (int a = 0; a < 8; ++a) {
+                const f32x2 axx = pack2(ax[a], ax[a]), ayy = pack2(ay[a], ay[a]), azz = pack2(az[a], az[a]);
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const float dx = ax[a] - bx[b];
-                    const float dy = ay[a] - by[b];
-                    const float dz = az[a] - bz[b];
-                    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                    acc[a][b] += fast_sqrt(d2);
+                for (int h = 0; h < JH; ++h) {
+                    const f32x2 dx = sub2(axx, bx[h]);
+                    const f32x2 dy = sub2(ayy, by[h]);
+                    const f32x2 dz = sub2(azz, bz[h]);
+                    const f32x2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                    float lo, hi;
+                    unpack2(d2, lo, hi);
+                    acc[a][h] = add2(acc[a][h], pack2(fast_sqrt(lo), fast_sqrt(hi)));
                 }
+            }
         }
         if ((chunk_idx % kFlushChunks) == kFlushChunks - 1 || !has_next) {
 #pragma unroll
             for (int a = 0; a < 8; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    sm.tot[(a * 4 + b) * kThreadsC + tid] += (double)acc[a][b];
-                    acc[a][b] = 0.f;
+                for (int h = 0; h < JH; ++h) {
+                    float lo, hi;
+                    unpack2(acc[a][h], lo, hi);
+                    sm.tot[(a * 2 * JH + 2 * h) * kThreadsC + tid] += (double)lo;
+                    sm.tot[(a * 2 * JH + 2 * h + 1) * kThreadsC + tid] += (double)hi;
+                    acc[a][h] = pack2(0.f, 0.f);
                 }
         }
         if (has_next) store_chunk(buf ^ 1, stage);
@@ -170,15 +222,19 @@ contact_sum_kernel(const float* __restrict__ p32, int64_t T, int N, const double
     }
 
     double* o = out + (size_t)seg * out_ld * out_ld;
-    const int64_t col0 = (int64_t)kTile * bj + 4 * tj;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
         const int64_t row = (int64_t)kTile * bi + ((a < 4) ? (4 * ti + a) : (64 + 4 * ti + (a - 4)));
-        double* p = o + row * out_ld + col0;
-        *reinterpret_cast<double2*>(p) =
-            make_double2(sm.tot[(a * 4 + 0) * kThreadsC + tid], sm.tot[(a * 4 + 1) * kThreadsC + tid]);
-        *reinterpret_cast<double2*>(p + 2) =
-            make_double2(sm.tot[(a * 4 + 2) * kThreadsC + tid], sm.tot[(a * 4 + 3) * kThreadsC + tid]);
+#pragma unroll
+        for (int g = 0; g < JH / 2; ++g) {       // groups of 4 consecutive j nodes
+            const int64_t col0 = (int64_t)kTile * bj + 64 * g + 4 * tj;
+            double* p = o + row * out_ld + col0;
+            const int pb = a * 2 * JH + 4 * g;
+            *reinterpret_cast<double2*>(p) =
+                make_double2(sm.tot[(pb + 0) * kThreadsC + tid], sm.tot[(pb + 1) * kThreadsC + tid]);
+            *reinterpret_cast<double2*>(p + 2) =
+                make_double2(sm.tot[(pb + 2) * kThreadsC + tid], sm.tot[(pb + 3) * kThreadsC + tid]);
+        }
     }
 }
 
@@ -199,9 +255,15 @@ int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, cons
         part = (double*)p;
     }
     const int smem = (int)sizeof(ContactSmem);
-    WISP_CUDA(cudaFuncSetAttribute(contact_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dim3 grid(n_items, n_seg);
-    contact_sum_kernel<<<grid, kThreadsC, smem, st>>>(d_p32, T, N, d_mean, n_tiles, n_seg, part, n_pad);
+    static const int variant = getenv("WISP_K3_VARIANT") ? atoi(getenv("WISP_K3_VARIANT")) : 4;
+    if (variant == 2) {
+        WISP_CUDA(cudaFuncSetAttribute(contact_sum_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        contact_sum_kernel<2><<<grid, 512, smem, st>>>(d_p32, T, N, d_mean, n_tiles, n_seg, part, n_pad);
+    } else {
+        WISP_CUDA(cudaFuncSetAttribute(contact_sum_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        contact_sum_kernel<4><<<grid, 256, smem, st>>>(d_p32, T, N, d_mean, n_tiles, n_seg, part, n_pad);
+    }
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
     if (n_seg > 1) WISP_TRY(launch_reduce_partials(ctx, part, n_seg, n_pad, d_out, kTile, kTile, st));
