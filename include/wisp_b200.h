@@ -120,13 +120,21 @@ int wisp_paths_stats(wisp_ctx* ctx, double* out6);
 
 /* ---- device-buffer entry points (bench, multi-GPU orchestration) --------------------- */
 
-/* K1 on device buffers.  d_nodes: double [wisp_frames_pad(T)][ld] (zeroed by the caller or
- * by this call when zero_pad != 0); d_colsum [ld] receives sum over frames of every column
- * (overwritten). */
-int wisp_dev_com(wisp_ctx* ctx, const float* d_coords, int64_t T, int A, const double* d_masses,
-                 const int32_t* d_node_ptr, const int32_t* d_atom_idx, int N,
-                 const int32_t* d_align_idx, int n_align, int atomic, double* d_nodes,
-                 double* d_colsum, void* stream);
+/* Node map ("plan") for K1: uploads masses / CSR node map / alignment landmarks once and
+ * decides between the TMA-streamed kernel (every node a contiguous ascending atom run) and
+ * the general CSR gather kernel.  All arrays are HOST pointers. */
+typedef struct wisp_com_plan wisp_com_plan;
+int  wisp_com_plan_create(wisp_ctx* ctx, int A, const double* masses, const int32_t* node_ptr,
+                          const int32_t* atom_idx, int N, const int32_t* align_idx, int n_align,
+                          int atomic, wisp_com_plan** out);
+void wisp_com_plan_destroy(wisp_ctx* ctx, wisp_com_plan* plan);
+int  wisp_com_plan_info(const wisp_com_plan* plan, int* streaming, int* n_pieces);
+
+/* K1 on device buffers.  d_coords float32 [T][A][3]; d_nodes: double [wisp_frames_pad(T)][ld]
+ * (pad rows / columns zeroed by the caller); d_colsum [ld] (may be NULL) receives the sum over
+ * frames of every column. */
+int wisp_dev_com(wisp_ctx* ctx, wisp_com_plan* plan, const float* d_coords, int64_t T, int N,
+                 double* d_nodes, double* d_colsum, void* stream);
 /* X <- X - mean (in place), mean [ld]; pad columns / rows are left at zero.  When d_p32 is
  * not NULL it also receives the FP32 tile-referenced copy K3 reads:
  * float [T][wisp_gram_ld(N)/128][3][128], value = float(x - mean of the tile's middle node). */

@@ -253,3 +253,52 @@ def test_properties_large(ctx):
     dist, pred = ctx.apsp(W)
     assert np.allclose(dist, dist.T, rtol=1e-12)
     assert np.all(dist[i, j] <= dist[i, k] + dist[k, j] + 1e-9)
+
+
+def test_com_general_node_maps(ctx):
+    """K1 on node maps the streaming kernel cannot take: ATOMIC nodes, nodes made of
+    non-contiguous atoms spanning two residues (make_node_selections.py:210), overlapping
+    nodes, descending order -- the CSR gather kernel must match the oracle too."""
+    system, coords = synth.synth(40, 90, 6, seed=21)
+    A = system.n_atoms
+    rng = np.random.default_rng(4)
+    # (a) ATOMIC: one atom per node
+    atoms = np.sort(rng.choice(A, size=70, replace=False)).astype(np.int32)
+    ptr = np.arange(71, dtype=np.int32)
+    nodes, avg = ctx.com_nodes(coords, system.masses, ptr, atoms, system.align_idx, atomic=True)
+    want, _ = oracle.com_nodes(coords, system.masses, ptr, atoms, system.align_idx, "ATOMIC")
+    np.testing.assert_allclose(nodes, want, rtol=0, atol=1e-12)
+    # (b) ragged, non-contiguous, overlapping, unordered nodes
+    idx, ptr = [], [0]
+    for n in range(55):
+        size = int(rng.integers(1, 23))
+        start = int(rng.integers(0, A - 30))
+        members = np.unique(np.concatenate([np.arange(start, start + size // 2 + 1),
+                                            rng.choice(A, size=size // 2 + 1)]))
+        rng.shuffle(members)
+        idx.extend(members.tolist())
+        ptr.append(len(idx))
+    ptr = np.array(ptr, dtype=np.int32)
+    idx = np.array(idx, dtype=np.int32)
+    nodes, avg = ctx.com_nodes(coords, system.masses, ptr, idx, system.align_idx)
+    want, _ = oracle.com_nodes(coords, system.masses, ptr, idx, system.align_idx)
+    np.testing.assert_allclose(nodes, want, rtol=0, atol=1e-11)
+    # (c) contiguous residues with unused atoms in between and a large gap (streaming pieces)
+    ptr2 = [0]
+    idx2 = []
+    for start, size in [(0, 5), (5, 7), (20, 3), (23, 9), (150, 12), (162, 6), (200, 1), (201, 30)]:
+        idx2.extend(range(start, start + size))
+        ptr2.append(len(idx2))
+    nodes, avg = ctx.com_nodes(coords, system.masses, np.array(ptr2, np.int32), np.array(idx2, np.int32),
+                               system.align_idx[::3])
+    want, _ = oracle.com_nodes(coords, system.masses, np.array(ptr2), np.array(idx2), system.align_idx[::3])
+    np.testing.assert_allclose(nodes, want, rtol=0, atol=1e-12)
+
+
+def test_com_streaming_many_pieces(ctx):
+    """A frame larger than one 2048-atom piece, odd atom count (unaligned frame starts)."""
+    system, coords = synth.synth(333, 37, 13, seed=8)     # 4329 atoms: 3 pieces, A % 4 == 1
+    nodes, avg = ctx.com_nodes(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx)
+    want, _ = oracle.com_nodes(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx)
+    np.testing.assert_allclose(nodes, want, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(avg, want.sum(axis=0) / want.shape[0], rtol=0, atol=1e-11)

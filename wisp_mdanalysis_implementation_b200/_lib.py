@@ -44,7 +44,10 @@ SIGNATURES = {
     "wisp_paths_size": (_int, [_c_ctx, C.POINTER(_i64), C.POINTER(_i64)]),
     "wisp_paths_fetch": (_int, [_c_ctx, _P, _P, _P]),
     "wisp_paths_stats": (_int, [_c_ctx, _P]),
-    "wisp_dev_com": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P, _int, _P, _int, _int, _P, _P, _P]),
+    "wisp_com_plan_create": (_int, [_c_ctx, _int, _P, _P, _P, _int, _P, _int, _int, C.POINTER(_P)]),
+    "wisp_com_plan_destroy": (None, [_c_ctx, _P]),
+    "wisp_com_plan_info": (_int, [_P, C.POINTER(_int), C.POINTER(_int)]),
+    "wisp_dev_com": (_int, [_c_ctx, _P, _P, _i64, _int, _P, _P, _P]),
     "wisp_dev_center": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P]),
     "wisp_dev_colsum": (_int, [_c_ctx, _P, _i64, _int, _P, _P]),
     "wisp_dev_gram": (_int, [_c_ctx, _P, _i64, _i64, _int, _int, _P, _P]),
@@ -264,12 +267,29 @@ class Context:
                     apsp_ms=float(s[3]), enumerate_ms=float(s[4]), host_ms=float(s[5]))
 
     # ---- device-buffer API (pointers are ints, e.g. torch.Tensor.data_ptr()) -----------
-    def dev_com(self, d_coords, T, A, d_masses, d_node_ptr, d_atom_idx, N, d_align_idx, n_align,
-                d_nodes, d_colsum=None, atomic=False, stream=None):
-        self._check(self._lib.wisp_dev_com(self._ctx, _ptr(d_coords), T, A, _ptr(d_masses),
-                                           _ptr(d_node_ptr), _ptr(d_atom_idx), N, _ptr(d_align_idx),
-                                           n_align, int(bool(atomic)), _ptr(d_nodes), _ptr(d_colsum),
-                                           _ptr(stream)))
+    def com_plan(self, n_atoms, masses, node_ptr, atom_idx, align_idx, atomic=False):
+        """Upload the node map once; returns an opaque plan handle for dev_com."""
+        masses = _arr(masses, np.float64, "masses", (n_atoms,))
+        node_ptr = _arr(node_ptr, np.int32, "node_ptr")
+        atom_idx = _arr(atom_idx, np.int32, "atom_idx")
+        align_idx = _arr(align_idx, np.int32, "align_idx")
+        plan = _P()
+        self._check(self._lib.wisp_com_plan_create(
+            self._ctx, int(n_atoms), _ptr(masses), _ptr(node_ptr), _ptr(atom_idx), len(node_ptr) - 1,
+            _ptr(align_idx), len(align_idx), int(bool(atomic)), C.byref(plan)))
+        return plan
+
+    def com_plan_info(self, plan):
+        s, p = _int(0), _int(0)
+        self._check(self._lib.wisp_com_plan_info(plan, C.byref(s), C.byref(p)))
+        return dict(streaming=bool(s.value), pieces=p.value)
+
+    def com_plan_destroy(self, plan):
+        self._lib.wisp_com_plan_destroy(self._ctx, plan)
+
+    def dev_com(self, plan, d_coords, T, N, d_nodes, d_colsum=None, stream=None):
+        self._check(self._lib.wisp_dev_com(self._ctx, plan, _ptr(d_coords), T, N, _ptr(d_nodes),
+                                           _ptr(d_colsum), _ptr(stream)))
 
     def dev_center(self, d_nodes, T, N, d_mean, d_p32=None, stream=None):
         self._check(self._lib.wisp_dev_center(self._ctx, _ptr(d_nodes), T, N, _ptr(d_mean),

@@ -149,47 +149,34 @@ int upload_nodes(wisp_ctx* ctx, const double* nodes, int64_t T, int N, double** 
     return 0;
 }
 
-struct NodeMapDev {
-    double* masses;
-    int32_t *node_ptr, *atom_idx, *align_idx;
-};
-
 // K1 over a host coordinate block: chunked H2D on the copy stream, double-buffered against
-// the COM kernel on the compute stream.
+// the COM kernels on the compute stream.
 int com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
                   const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
-                  int n_align, int atomic, double** d_x_out, int64_t* ld_out, Arena* arena,
+                  int n_align, int atomic, double** d_x_out, int64_t* ld_out,
                   float* d_align_out = nullptr) {
     const int64_t ld = wisp_node_ld(N), Tpad = wisp_frames_pad(T);
+    wisp_com_plan* plan = nullptr;
+    WISP_TRY(com_plan_create(ctx, A, masses, node_ptr, atom_idx, N, align_idx, n_align, atomic, &plan));
     void* px = nullptr;
-    WISP_TRY(wisp_scratch(ctx, SCR_X, (size_t)Tpad * ld * 8, &px));
+    int rc = wisp_scratch(ctx, SCR_X, (size_t)Tpad * ld * 8, &px);
+    if (rc) { com_plan_destroy(ctx, plan); return rc; }
     double* d_x = (double*)px;
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
-    WISP_CUDA(cudaMemsetAsync(d_x, 0, (size_t)Tpad * ld * 8, st));
-    const int n_entries = node_ptr[N];
-    NodeMapDev m;
-    m.masses = arena->take<double>(A);
-    m.node_ptr = arena->take<int32_t>(N + 1);
-    m.atom_idx = arena->take<int32_t>(n_entries);
-    m.align_idx = arena->take<int32_t>(n_align);
-    WISP_CUDA(cudaMemcpyAsync(m.masses, masses, (size_t)A * 8, cudaMemcpyHostToDevice, st));
-    WISP_CUDA(cudaMemcpyAsync(m.node_ptr, node_ptr, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, st));
-    WISP_CUDA(cudaMemcpyAsync(m.atom_idx, atom_idx, (size_t)n_entries * 4, cudaMemcpyHostToDevice, st));
-    WISP_CUDA(cudaMemcpyAsync(m.align_idx, align_idx, (size_t)n_align * 4, cudaMemcpyHostToDevice, st));
-
+    cudaMemsetAsync(d_x, 0, (size_t)Tpad * ld * 8, st);
     const size_t frame_bytes = (size_t)A * 12;
     int64_t chunk = std::max<int64_t>(1, ((size_t)128 << 20) / frame_bytes);
     chunk = std::min(chunk, T);
-    void* bufs[2];
-    WISP_TRY(wisp_scratch(ctx, SCR_COORDS0, (size_t)chunk * frame_bytes, &bufs[0]));
-    WISP_TRY(wisp_scratch(ctx, SCR_COORDS1, (size_t)chunk * frame_bytes, &bufs[1]));
+    void* bufs[2] = {nullptr, nullptr};
+    rc = wisp_scratch(ctx, SCR_COORDS0, (size_t)chunk * frame_bytes + 64, &bufs[0]);
+    if (!rc) rc = wisp_scratch(ctx, SCR_COORDS1, (size_t)chunk * frame_bytes + 64, &bufs[1]);
+    if (rc) { com_plan_destroy(ctx, plan); return rc; }
     cudaEvent_t copied[2], freed[2];
     for (int b = 0; b < 2; ++b) {
-        WISP_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
-        WISP_CUDA(cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming));
+        cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming);
     }
     int it = 0;
-    int rc = 0;
     for (int64_t t0 = 0; t0 < T && rc == 0; t0 += chunk, ++it) {
         const int b = it & 1;
         const int64_t nt = std::min(chunk, T - t0);
@@ -197,12 +184,12 @@ int com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const do
         cudaMemcpyAsync(bufs[b], coords + (size_t)t0 * A * 3, (size_t)nt * frame_bytes, cudaMemcpyHostToDevice, cs);
         cudaEventRecord(copied[b], cs);
         cudaStreamWaitEvent(st, copied[b], 0);
-        rc = launch_com(ctx, (const float*)bufs[b], nt, A, m.masses, m.node_ptr, m.atom_idx, N,
-                        m.align_idx, n_align, atomic, d_x, ld, t0, st, d_align_out);
+        rc = launch_com_plan(ctx, plan, (const float*)bufs[b], nt, d_x, ld, t0, st, d_align_out);
         cudaEventRecord(freed[b], st);
     }
     cudaError_t e = cudaStreamSynchronize(st);
     for (int b = 0; b < 2; ++b) { cudaEventDestroy(copied[b]); cudaEventDestroy(freed[b]); }
+    com_plan_destroy(ctx, plan);
     if (rc) return rc;
     WISP_CUDA(e);
     *d_x_out = d_x;
@@ -244,7 +231,7 @@ extern "C" int wisp_com_nodes(wisp_ctx* ctx, const float* coords, int64_t T, int
     double* d_x;
     int64_t ld;
     WISP_TRY(com_from_host(ctx, coords, T, A, masses, node_ptr, atom_idx, N, align_idx, n_align,
-                           atomic, &d_x, &ld, &ar));
+                           atomic, &d_x, &ld));
     cudaStream_t st = ctx->stream;
     if (out_avg) {
         double* d_sum = ar.take<double>(ld);
@@ -285,7 +272,7 @@ extern "C" int wisp_traj_alignment_and_averaging(wisp_ctx* ctx, const float* coo
     double* d_x;
     int64_t ld;
     WISP_TRY(com_from_host(ctx, coords, T, A, masses, node_ptr, atom_idx, N, align_idx, n_align,
-                           atomic, &d_x, &ld, &ar, d_align));
+                           atomic, &d_x, &ld, d_align));
     double* d_work = ar.take<double>((size_t)(2 * round_up(na3, 32) + round_up(nn3, 32)));
     std::vector<double> avg(nn3);
     int n_iter = 0;
@@ -440,7 +427,7 @@ extern "C" int wisp_pipeline(wisp_ctx* ctx, const float* coords, int64_t T, int 
     double* d_x;
     int64_t ldx;
     WISP_TRY(com_from_host(ctx, coords, T, A, masses, node_ptr, atom_idx, N, align_idx, n_align,
-                           atomic, &d_x, &ldx, &ar));
+                           atomic, &d_x, &ldx));
     double* d_sum = ar.take<double>(ld);
     double* d_mean = ar.take<double>(ld);
     double* d_gram = ar.take<double>((size_t)n_pad * n_pad);
@@ -495,15 +482,25 @@ extern "C" int wisp_apsp(wisp_ctx* ctx, const double* w, int N, int precision, d
 // ---------------------------------------------------------------------------------------
 // device-buffer entry points
 // ---------------------------------------------------------------------------------------
-extern "C" int wisp_dev_com(wisp_ctx* ctx, const float* d_coords, int64_t T, int A,
-                            const double* d_masses, const int32_t* d_node_ptr,
-                            const int32_t* d_atom_idx, int N, const int32_t* d_align_idx,
-                            int n_align, int atomic, double* d_nodes, double* d_colsum, void* stream) {
-    WISP_CHECK(ctx && d_coords && d_nodes, "dev_com: null argument");
+extern "C" int wisp_com_plan_create(wisp_ctx* ctx, int A, const double* masses, const int32_t* node_ptr,
+                                    const int32_t* atom_idx, int N, const int32_t* align_idx,
+                                    int n_align, int atomic, wisp_com_plan** out) {
+    return com_plan_create(ctx, A, masses, node_ptr, atom_idx, N, align_idx, n_align, atomic, out);
+}
+
+extern "C" void wisp_com_plan_destroy(wisp_ctx* ctx, wisp_com_plan* plan) { com_plan_destroy(ctx, plan); }
+
+extern "C" int wisp_com_plan_info(const wisp_com_plan* plan, int* streaming, int* n_pieces) {
+    WISP_CHECK(plan, "com_plan_info: null plan");
+    return com_plan_info(plan, streaming, n_pieces);
+}
+
+extern "C" int wisp_dev_com(wisp_ctx* ctx, wisp_com_plan* plan, const float* d_coords, int64_t T, int N,
+                            double* d_nodes, double* d_colsum, void* stream) {
+    WISP_CHECK(ctx && plan && d_coords && d_nodes, "dev_com: null argument");
     cudaStream_t st = wisp_stream(ctx, stream);
     const int64_t ld = wisp_node_ld(N);
-    WISP_TRY(launch_com(ctx, d_coords, T, A, d_masses, d_node_ptr, d_atom_idx, N, d_align_idx, n_align,
-                        atomic, d_nodes, ld, 0, st));
+    WISP_TRY(launch_com_plan(ctx, plan, d_coords, T, d_nodes, ld, 0, st));
     if (d_colsum) WISP_TRY(launch_colsum(ctx, d_nodes, T, ld, 3 * (int64_t)N, d_colsum, st));
     return 0;
 }

@@ -86,6 +86,14 @@ int launch_com(wisp_ctx* ctx, const float* d_coords, int64_t T, int A, const dou
                const int32_t* d_node_ptr, const int32_t* d_atom_idx, int N,
                const int32_t* d_align_idx, int n_align, int atomic, double* d_nodes, int64_t ld,
                int64_t row0, cudaStream_t st, float* d_align_out = nullptr);
+struct wisp_com_plan;
+int com_plan_create(wisp_ctx* ctx, int A, const double* masses, const int32_t* node_ptr,
+                    const int32_t* atom_idx, int N, const int32_t* align_idx, int n_align, int atomic,
+                    wisp_com_plan** out);
+void com_plan_destroy(wisp_ctx* ctx, wisp_com_plan* pl);
+int com_plan_info(const wisp_com_plan* pl, int* streaming, int* n_pieces);
+int launch_com_plan(wisp_ctx* ctx, wisp_com_plan* pl, const float* d_coords, int64_t T, double* d_nodes,
+                    int64_t ld, int64_t row0, cudaStream_t st, float* d_align_out = nullptr);
 int launch_colsum_f32(wisp_ctx* ctx, const float* d_x, int64_t T, int64_t ld, int64_t ncols,
                       double* d_colsum, cudaStream_t st);
 int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* d_nodes, int64_t ld,

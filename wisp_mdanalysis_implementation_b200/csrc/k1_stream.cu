@@ -1,0 +1,324 @@
+// K1 (streaming form) -- per-frame translate + per-node centre of mass with TMA-staged
+// coordinate streams, plus the plan object that owns the device-side node map.
+//
+// Same arithmetic as com_kernel (k1_com.cu, the general CSR gather), restructured for HBM
+// bandwidth when every node is a contiguous, ascending run of atoms (residue COM nodes,
+// make_node_selections.py:39-58):
+//   align_shift_kernel  one warp per frame gathers the alignment landmarks (a few percent of
+//                       the frame) and writes shift[f] = -COM_align(f)           (:71);
+//   com_stream_kernel   persistent CTAs; the frame is cut into "pieces" (<= 2048 atoms of
+//                       consecutive nodes); each CTA owns one piece index and walks the
+//                       frames with a 4-stage ring of cp.async.bulk (TMA) copies completed
+//                       on mbarriers, so a whole piece (24 KB) is in flight per stage with
+//                       no registers held; 8 lanes per node read x,y,z from shared memory
+//                       (12-byte lane stride: conflict-free), apply the float32 translate
+//                       rounding, accumulate m*x in FP64, shuffle-reduce, and lanes 0..2
+//                       store the COM                                            (:76).
+// HBM traffic: 12*A (bulk copies) + 24*N (stores) per frame, plus the 32-byte sectors of
+// the landmark gather (~17 % of a frame when there is one landmark per 16-atom node).
+#include "common.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int kPieceAtomsMax = 2048;
+constexpr int kStStages = 4;
+constexpr int kStThreads = 256;
+constexpr int kStageBytes = kPieceAtomsMax * 12 + 32;     // + slack for the 16-byte alignment shift
+
+struct Piece {
+    int32_t atom0, n_atoms, node0, n_nodes;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- shift[f] = -(sum_a m_a x_a / sum_a m_a) over the alignment landmarks; one warp per frame ----
+__global__ void __launch_bounds__(256)
+align_shift_kernel(const float* __restrict__ coords, int64_t T, int A,
+                   const int32_t* __restrict__ align_idx, const double* __restrict__ align_mass,
+                   int n_align, double inv_total_is_unused, double* __restrict__ shift,
+                   float* __restrict__ align_out, int64_t row0) {
+    const int lane = threadIdx.x & 31;
+    const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= T) return;
+    const float* fr = coords + f * (int64_t)A * 3;
+    double sx = 0, sy = 0, sz = 0, sm = 0;
+#pragma unroll 4
+    for (int a = lane; a < n_align; a += 32) {
+        const float* p = fr + 3 * (int64_t)__ldg(align_idx + a);
+        const double m = __ldg(align_mass + a);
+        sx += m * (double)__ldg(p + 0);
+        sy += m * (double)__ldg(p + 1);
+        sz += m * (double)__ldg(p + 2);
+        sm += m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+        sm += __shfl_xor_sync(0xffffffffu, sm, o);
+    }
+    const double hx = -(sx / sm), hy = -(sy / sm), hz = -(sz / sm);
+    if (lane == 0) { shift[3 * f + 0] = hx; shift[3 * f + 1] = hy; shift[3 * f + 2] = hz; }
+    if (align_out) {   // all_pos_Align.append(u_alignment.positions)  (:72)
+        float* ao = align_out + (row0 + f) * (int64_t)n_align * 3;
+        for (int a = lane; a < n_align; a += 32) {
+            const float* p = fr + 3 * (int64_t)__ldg(align_idx + a);
+            ao[3 * a + 0] = __double2float_rn((double)__ldg(p + 0) + hx);
+            ao[3 * a + 1] = __double2float_rn((double)__ldg(p + 1) + hy);
+            ao[3 * a + 2] = __double2float_rn((double)__ldg(p + 2) + hz);
+        }
+    }
+}
+
+// ---- streaming node COM ----
+__global__ void __launch_bounds__(kStThreads, 2)
+com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piece* __restrict__ pieces,
+                  int P, const double* __restrict__ shift, const int32_t* __restrict__ node_ptr,
+                  const int32_t* __restrict__ atom_first, const double* __restrict__ ent_mass,
+                  const double* __restrict__ node_mass, double* __restrict__ nodes, int64_t ld,
+                  int64_t row0, int64_t total_bytes) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full[kStStages];
+    const int tid = threadIdx.x;
+    const int p = blockIdx.x % P;
+    const int64_t f_start = blockIdx.x / P;
+    const int64_t f_stride = gridDim.x / P;
+    const Piece pc = pieces[p];
+    const int64_t n_items = (f_start < T) ? (T - f_start + f_stride - 1) / f_stride : 0;
+    const uint32_t piece_bytes = (uint32_t)pc.n_atoms * 12u;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // stage item k into slot k % kStStages: TMA bulk copy from the 16-byte-aligned address at or
+    // below the piece start; the last bytes of the whole buffer are copied by hand so the bulk
+    // copy never reads past the allocation.
+    auto stage_in = [&](int64_t k) {
+        const int64_t f = f_start + k * f_stride;
+        const int64_t src = (f * (int64_t)A + pc.atom0) * 12;
+        const int64_t src_al = src & ~(int64_t)15;
+        const uint32_t delta = (uint32_t)(src - src_al);
+        const uint32_t bytes = (delta + piece_bytes + 15u) & ~15u;
+        unsigned char* dst = smem_raw + (size_t)(k % kStStages) * kStageBytes;
+        if (src_al + bytes <= total_bytes) {
+            if (tid == 0) {
+                mbar_expect_tx(&full[k % kStStages], bytes);
+                bulk_g2s(dst, reinterpret_cast<const unsigned char*>(coords) + src_al, bytes,
+                         &full[k % kStStages]);
+            }
+        } else {
+            const float* s = coords + (f * (int64_t)A + pc.atom0) * 3;
+            float* d = reinterpret_cast<float*>(dst + delta);
+            for (int i = tid; i < pc.n_atoms * 3; i += kStThreads) d[i] = __ldg(s + i);
+            if (tid == 0) mbar_expect_tx(&full[k % kStStages], 0);   // completes the phase
+        }
+    };
+
+    for (int64_t k = 0; k < kStStages && k < n_items; ++k) stage_in(k);
+
+    const int group = tid >> 3, gl = tid & 7;
+    for (int64_t k = 0; k < n_items; ++k) {
+        const int slot = (int)(k % kStStages);
+        const uint32_t ph = (uint32_t)((k / kStStages) & 1);
+        mbar_wait(&full[slot], ph);
+        __syncthreads();     // manual-copy path: make the plain stores visible to every warp
+        const int64_t f = f_start + k * f_stride;
+        const int64_t src = (f * (int64_t)A + pc.atom0) * 12;
+        const float* base = reinterpret_cast<const float*>(smem_raw + (size_t)slot * kStageBytes + (src & 15));
+        const double hx = __ldg(shift + 3 * f + 0), hy = __ldg(shift + 3 * f + 1), hz = __ldg(shift + 3 * f + 2);
+        double* out = nodes + (row0 + f) * ld;
+        for (int n0 = 0; n0 < pc.n_nodes; n0 += kStThreads / 8) {   // uniform trip count
+            const int nl = n0 + group;
+            const bool valid = nl < pc.n_nodes;
+            const int n = pc.node0 + (valid ? nl : 0);
+            const int e0 = __ldg(node_ptr + n);
+            const int cnt = valid ? (__ldg(node_ptr + n + 1) - e0) : 0;
+            const float* q = base + 3 * (int64_t)(__ldg(atom_first + n) - pc.atom0);
+            double ax = 0, ay = 0, az = 0;
+            for (int a = gl; a < cnt; a += 8) {
+                // translate(): float32 position += float64 vector, rounded back to float32
+                const double px = (double)__double2float_rn((double)q[3 * a + 0] + hx);
+                const double py = (double)__double2float_rn((double)q[3 * a + 1] + hy);
+                const double pz = (double)__double2float_rn((double)q[3 * a + 2] + hz);
+                const double m = __ldg(ent_mass + e0 + a);
+                ax += m * px; ay += m * py; az += m * pz;
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                ax += __shfl_xor_sync(0xffffffffu, ax, o);
+                ay += __shfl_xor_sync(0xffffffffu, ay, o);
+                az += __shfl_xor_sync(0xffffffffu, az, o);
+            }
+            const double num = (gl == 0) ? ax : ((gl == 1) ? ay : az);
+            if (valid && gl < 3) out[3 * (int64_t)n + gl] = num / __ldg(node_mass + n);
+        }
+        __syncthreads();     // everyone is done with this slot
+        if (k + kStStages < n_items) stage_in(k + kStStages);
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------
+struct wisp_com_plan {
+    int A = 0, N = 0, n_align = 0, atomic = 0, n_entries = 0;
+    bool streaming = false;
+    int P = 0;
+    // device arrays
+    double* d_masses = nullptr;
+    int32_t *d_node_ptr = nullptr, *d_atom_idx = nullptr, *d_align_idx = nullptr;
+    double *d_align_mass = nullptr, *d_ent_mass = nullptr, *d_node_mass = nullptr;
+    int32_t* d_atom_first = nullptr;
+    Piece* d_pieces = nullptr;
+    double* d_shift = nullptr;
+    int64_t shift_frames = 0;
+};
+
+namespace {
+template <typename T>
+int upload(const std::vector<T>& h, T** d) {
+    WISP_CUDA(cudaMalloc((void**)d, std::max<size_t>(h.size(), 1) * sizeof(T)));
+    if (!h.empty()) WISP_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+}  // namespace
+
+int com_plan_create(wisp_ctx* ctx, int A, const double* masses, const int32_t* node_ptr,
+                    const int32_t* atom_idx, int N, const int32_t* align_idx, int n_align, int atomic,
+                    wisp_com_plan** out) {
+    WISP_CHECK(ctx && masses && node_ptr && atom_idx && align_idx && out, "com_plan: null argument");
+    WISP_CHECK(A > 0 && N > 0 && n_align > 0, "com_plan: empty input (A=%d N=%d nAlign=%d)", A, N, n_align);
+    WISP_CHECK(node_ptr[0] == 0, "com_plan: node_ptr[0] must be 0");
+    for (int n = 0; n < N; ++n) WISP_CHECK(node_ptr[n + 1] > node_ptr[n], "com_plan: node %d has no atoms", n);
+    const int E = node_ptr[N];
+    for (int e = 0; e < E; ++e) WISP_CHECK(atom_idx[e] >= 0 && atom_idx[e] < A, "com_plan: atom index %d out of range", atom_idx[e]);
+    for (int e = 0; e < n_align; ++e) WISP_CHECK(align_idx[e] >= 0 && align_idx[e] < A, "com_plan: alignment atom index %d out of range", align_idx[e]);
+    WISP_CUDA(cudaSetDevice(ctx->device));
+    wisp_com_plan* pl = new wisp_com_plan();
+    pl->A = A; pl->N = N; pl->n_align = n_align; pl->atomic = atomic; pl->n_entries = E;
+    std::vector<double> h_masses(masses, masses + A), h_align_mass(n_align), h_ent_mass(E), h_node_mass(N);
+    std::vector<int32_t> h_np(node_ptr, node_ptr + N + 1), h_ai(atom_idx, atom_idx + E),
+        h_al(align_idx, align_idx + n_align), h_first(N);
+    for (int a = 0; a < n_align; ++a) h_align_mass[a] = masses[align_idx[a]];
+    bool contiguous = !atomic;
+    for (int n = 0; n < N; ++n) {
+        double m = 0.0;
+        for (int e = node_ptr[n]; e < node_ptr[n + 1]; ++e) {
+            h_ent_mass[e] = masses[atom_idx[e]];
+            m += masses[atom_idx[e]];
+            if (e > node_ptr[n] && atom_idx[e] != atom_idx[e - 1] + 1) contiguous = false;
+        }
+        h_node_mass[n] = m;
+        h_first[n] = atom_idx[node_ptr[n]];
+        if (node_ptr[n + 1] - node_ptr[n] > kPieceAtomsMax) contiguous = false;
+        if (n > 0 && h_first[n] < h_first[n - 1] + (node_ptr[n] - node_ptr[n - 1])) contiguous = false;
+    }
+    // pieces: runs of consecutive nodes whose atoms span <= kPieceAtomsMax atoms; a gap of
+    // more than 64 unused atoms starts a new piece
+    std::vector<Piece> h_pieces;
+    if (contiguous) {
+        int n = 0;
+        while (n < N) {
+            Piece pc;
+            pc.node0 = n;
+            pc.atom0 = h_first[n];
+            int end = h_first[n] + (node_ptr[n + 1] - node_ptr[n]);
+            int m = n + 1;
+            while (m < N) {
+                const int s = h_first[m], e = s + (node_ptr[m + 1] - node_ptr[m]);
+                if (s - end > 64 || e - pc.atom0 > kPieceAtomsMax) break;
+                end = e;
+                ++m;
+            }
+            pc.n_nodes = m - n;
+            pc.n_atoms = end - pc.atom0;
+            h_pieces.push_back(pc);
+            n = m;
+        }
+    }
+    pl->streaming = contiguous && !h_pieces.empty() && getenv("WISP_K1_GATHER") == nullptr;
+    pl->P = (int)h_pieces.size();
+    int rc = upload(h_masses, &pl->d_masses) || upload(h_np, &pl->d_node_ptr) || upload(h_ai, &pl->d_atom_idx) ||
+             upload(h_al, &pl->d_align_idx) || upload(h_align_mass, &pl->d_align_mass) ||
+             upload(h_ent_mass, &pl->d_ent_mass) || upload(h_node_mass, &pl->d_node_mass) ||
+             upload(h_first, &pl->d_atom_first) || upload(h_pieces, &pl->d_pieces);
+    if (rc) { com_plan_destroy(ctx, pl); return 1; }
+    *out = pl;
+    return 0;
+}
+
+void com_plan_destroy(wisp_ctx* ctx, wisp_com_plan* pl) {
+    if (!pl) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(pl->d_masses); cudaFree(pl->d_node_ptr); cudaFree(pl->d_atom_idx); cudaFree(pl->d_align_idx);
+    cudaFree(pl->d_align_mass); cudaFree(pl->d_ent_mass); cudaFree(pl->d_node_mass);
+    cudaFree(pl->d_atom_first); cudaFree(pl->d_pieces); cudaFree(pl->d_shift);
+    delete pl;
+}
+
+int com_plan_info(const wisp_com_plan* pl, int* streaming, int* n_pieces) {
+    if (streaming) *streaming = pl->streaming ? 1 : 0;
+    if (n_pieces) *n_pieces = pl->P;
+    return 0;
+}
+
+int launch_com_plan(wisp_ctx* ctx, wisp_com_plan* pl, const float* d_coords, int64_t T, double* d_nodes,
+                    int64_t ld, int64_t row0, cudaStream_t st, float* d_align_out) {
+    WISP_CHECK(pl && d_coords && d_nodes && T > 0, "com: bad argument");
+    if (!pl->streaming)
+        return launch_com(ctx, d_coords, T, pl->A, pl->d_masses, pl->d_node_ptr, pl->d_atom_idx, pl->N,
+                          pl->d_align_idx, pl->n_align, pl->atomic, d_nodes, ld, row0, st, d_align_out);
+    if (pl->shift_frames < T) {
+        if (pl->d_shift) { WISP_CUDA(cudaDeviceSynchronize()); WISP_CUDA(cudaFree(pl->d_shift)); pl->d_shift = nullptr; }
+        WISP_CUDA(cudaMalloc((void**)&pl->d_shift, (size_t)T * 3 * 8));
+        pl->shift_frames = T;
+    }
+    align_shift_kernel<<<(unsigned)((T + 7) / 8), 256, 0, st>>>(d_coords, T, pl->A, pl->d_align_idx,
+                                                               pl->d_align_mass, pl->n_align, 0.0,
+                                                               pl->d_shift, d_align_out, row0);
+    ctx->launches++;
+    WISP_CUDA(cudaGetLastError());
+    const int smem = kStStages * kStageBytes;
+    WISP_CUDA(cudaFuncSetAttribute(com_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int P = pl->P;
+    int per_piece = std::max(1, (2 * ctx->sm_count) / P);
+    per_piece = (int)std::min<int64_t>(per_piece, T);
+    com_stream_kernel<<<P * per_piece, kStThreads, smem, st>>>(
+        d_coords, T, pl->A, pl->d_pieces, P, pl->d_shift, pl->d_node_ptr, pl->d_atom_first,
+        pl->d_ent_mass, pl->d_node_mass, d_nodes, ld, row0, (int64_t)T * pl->A * 12);
+    ctx->launches++;
+    WISP_CUDA(cudaGetLastError());
+    return 0;
+}

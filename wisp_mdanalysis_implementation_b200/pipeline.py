@@ -35,11 +35,8 @@ class FramePipeline:
         self.npad = _lib.gram_ld(self.N)
         dev = self.dev
         f64, i32 = torch.float64, torch.int32
-        self.d_masses = torch.as_tensor(np.asarray(masses, dtype=np.float64), device=dev)
-        self.d_node_ptr = torch.as_tensor(np.asarray(node_ptr, dtype=np.int32), device=dev)
-        self.d_atom_idx = torch.as_tensor(np.asarray(atom_idx, dtype=np.int32), device=dev)
-        self.d_align_idx = torch.as_tensor(np.asarray(align_idx, dtype=np.int32), device=dev)
-        self.n_align = int(self.d_align_idx.numel())
+        self.plan = ctx.com_plan(self.A, masses, node_ptr, atom_idx, align_idx, atomic=self.atomic)
+        self.plan_info = ctx.com_plan_info(self.plan)
         self.d_x = torch.zeros((self.tpad, self.ld), dtype=f64, device=dev)
         self.d_p32 = torch.zeros((self.T, self.npad // 128, 3, 128), dtype=torch.float32, device=dev)
         self.d_colsum = torch.zeros(self.ld, dtype=f64, device=dev)
@@ -63,11 +60,8 @@ class FramePipeline:
 
     def com(self, d_coords, frames=None, row0=0):
         t = self.T if frames is None else frames
-        self.ctx.dev_com(d_coords.data_ptr(), t, self.A, self.d_masses.data_ptr(),
-                         self.d_node_ptr.data_ptr(), self.d_atom_idx.data_ptr(), self.N,
-                         self.d_align_idx.data_ptr(), self.n_align,
-                         self.d_x.data_ptr() + row0 * self.ld * 8, None, atomic=self.atomic,
-                         stream=self._stream())
+        self.ctx.dev_com(self.plan, d_coords.data_ptr(), t, self.N,
+                         self.d_x.data_ptr() + row0 * self.ld * 8, None, stream=self._stream())
 
     def mean_and_center(self):
         s = self._stream()
