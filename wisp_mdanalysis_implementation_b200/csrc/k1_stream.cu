@@ -6,14 +6,15 @@
 // make_node_selections.py:39-58):
 //   align_shift_kernel  one warp per frame gathers the alignment landmarks (a few percent of
 //                       the frame) and writes shift[f] = -COM_align(f)           (:71);
-//   com_stream_kernel   persistent CTAs; the frame is cut into "pieces" (<= 2048 atoms of
-//                       consecutive nodes); each CTA owns one piece index and walks the
-//                       frames with a 4-stage ring of cp.async.bulk (TMA) copies completed
+//   com_stream_kernel   persistent CTAs; the frame is cut into "pieces" (<= 80 consecutive nodes,
+//                       <= 2048 atoms); each CTA owns one piece index and walks the
+//                       frames with a 3-stage ring of cp.async.bulk (TMA) copies completed
 //                       on mbarriers, so a whole piece (24 KB) is in flight per stage with
-//                       no registers held; 8 lanes per node read x,y,z from shared memory
-//                       (12-byte lane stride: conflict-free), apply the float32 translate
-//                       rounding, accumulate m*x in FP64, shuffle-reduce, and lanes 0..2
-//                       store the COM                                            (:76).
+//                       no registers held; one lane per (node, component) -- 10 nodes per
+//                       warp, no cross-lane reduction -- walks the node's atoms in shared
+//                       memory, applies the float32 translate rounding (Veltkamp split on
+//                       the FP64 pipe), accumulates m*x in FP64 and stores the COM (sum times
+//                       the precomputed 1/M_node), consecutive lanes -> consecutive doubles (:76).
 // HBM traffic: 12*A (bulk copies) + 24*N (stores) per frame, plus the 32-byte sectors of
 // the landmark gather (~17 % of a frame when there is one landmark per 16-atom node).
 #include "common.cuh"
@@ -22,8 +23,10 @@
 namespace {
 
 constexpr int kPieceAtomsMax = 2048;
-constexpr int kStStages = 4;
+constexpr int kStStages = 3;
 constexpr int kStThreads = 256;
+constexpr int kNodesPerWarp = 10;                              // 30 lanes = 10 nodes x (x,y,z)
+constexpr int kPieceNodesMax = (kStThreads / 32) * kNodesPerWarp;   // one pass per piece
 constexpr int kStageBytes = kPieceAtomsMax * 12 + 32;     // + slack for the 16-byte alignment shift
 
 struct Piece {
@@ -97,14 +100,25 @@ align_shift_kernel(const float* __restrict__ coords, int64_t T, int A,
 }
 
 // ---- streaming node COM ----
+// round a double to float precision (round-to-nearest-even) without leaving the FP64 pipe:
+// Veltkamp split with C = 2^29 + 1 -- bit-identical to (double)(float)t for |t| in float's
+// normal range (checked against numpy on random values, exact ties and near-ties); the
+// intrinsics keep the compiler from contracting the sequence into FMAs.  This replaces two
+// F2F conversions per coordinate on the quarter-rate XU pipe.
+__device__ __forceinline__ double round_to_f32(double t) {
+    const double g = __dmul_rn(t, 536870913.0);
+    const double d = __dsub_rn(g, t);
+    return __dsub_rn(g, d);
+}
+
 __global__ void __launch_bounds__(kStThreads, 2)
 com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piece* __restrict__ pieces,
-                  int P, const double* __restrict__ shift, const int32_t* __restrict__ node_ptr,
-                  const int32_t* __restrict__ atom_first, const double* __restrict__ ent_mass,
-                  const double* __restrict__ node_mass, double* __restrict__ nodes, int64_t ld,
-                  int64_t row0, int64_t total_bytes) {
+                  int P, const double* __restrict__ shift, const int4* __restrict__ node_info,
+                  const double* __restrict__ ent_mass, const double* __restrict__ inv_node_mass,
+                  double* __restrict__ nodes, int64_t ld, int64_t row0, int64_t total_bytes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full[kStStages];
+    double* smass = reinterpret_cast<double*>(smem_raw + (size_t)kStStages * kStageBytes);
     const int tid = threadIdx.x;
     const int p = blockIdx.x % P;
     const int64_t f_start = blockIdx.x / P;
@@ -116,6 +130,34 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
     if (tid == 0) {
         for (int s = 0; s < kStStages; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // this CTA always works on the same piece: its per-atom masses live in shared memory and
+    // its per-lane node descriptor in registers for the whole kernel
+    const int4 first_info = __ldg(node_info + pc.node0);
+    for (int i = tid; i < pc.n_atoms; i += kStThreads) smass[i] = 0.0;
+    __syncthreads();
+    for (int nl = tid; nl < pc.n_nodes; nl += kStThreads) {
+        const int4 info = __ldg(node_info + pc.node0 + nl);
+        for (int a = 0; a < info.y; ++a) smass[info.z + a] = __ldg(ent_mass + info.x + a);
+    }
+    (void)first_info;
+
+    // lane = (node j of this warp's 10, component c): no cross-lane reduction at all
+    const int lane = tid & 31, warp = tid >> 5;
+    const int j = lane / 3, comp = lane - 3 * j;
+    const int nl = warp * kNodesPerWarp + j;
+    const bool valid = lane < 3 * kNodesPerWarp && nl < pc.n_nodes;
+    int cnt = 0, qoff = 0, moff = 0, rot = 0;
+    double inv_m = 0.0;
+    int64_t out_col = 0;
+    if (valid) {
+        const int4 info = __ldg(node_info + pc.node0 + nl);
+        cnt = info.y;
+        qoff = 3 * info.z + comp;          // float index of this node's first atom, this component
+        moff = info.z;
+        rot = j % cnt;                     // staggered start: equally sized nodes hit different banks
+        inv_m = __ldg(inv_node_mass + pc.node0 + nl);
+        out_col = 3 * (int64_t)(pc.node0 + nl) + comp;
     }
     __syncthreads();
 
@@ -145,7 +187,7 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
 
     for (int64_t k = 0; k < kStStages && k < n_items; ++k) stage_in(k);
 
-    const int group = tid >> 3, gl = tid & 7;
+    const double* mb = smass + moff;
     for (int64_t k = 0; k < n_items; ++k) {
         const int slot = (int)(k % kStStages);
         const uint32_t ph = (uint32_t)((k / kStStages) & 1);
@@ -153,34 +195,18 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
         __syncthreads();     // manual-copy path: make the plain stores visible to every warp
         const int64_t f = f_start + k * f_stride;
         const int64_t src = (f * (int64_t)A + pc.atom0) * 12;
-        const float* base = reinterpret_cast<const float*>(smem_raw + (size_t)slot * kStageBytes + (src & 15));
-        const double hx = __ldg(shift + 3 * f + 0), hy = __ldg(shift + 3 * f + 1), hz = __ldg(shift + 3 * f + 2);
-        double* out = nodes + (row0 + f) * ld;
-        for (int n0 = 0; n0 < pc.n_nodes; n0 += kStThreads / 8) {   // uniform trip count
-            const int nl = n0 + group;
-            const bool valid = nl < pc.n_nodes;
-            const int n = pc.node0 + (valid ? nl : 0);
-            const int e0 = __ldg(node_ptr + n);
-            const int cnt = valid ? (__ldg(node_ptr + n + 1) - e0) : 0;
-            const float* q = base + 3 * (int64_t)(__ldg(atom_first + n) - pc.atom0);
-            double ax = 0, ay = 0, az = 0;
-            for (int a = gl; a < cnt; a += 8) {
-                // translate(): float32 position += float64 vector, rounded back to float32
-                const double px = (double)__double2float_rn((double)q[3 * a + 0] + hx);
-                const double py = (double)__double2float_rn((double)q[3 * a + 1] + hy);
-                const double pz = (double)__double2float_rn((double)q[3 * a + 2] + hz);
-                const double m = __ldg(ent_mass + e0 + a);
-                ax += m * px; ay += m * py; az += m * pz;
-            }
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-                ax += __shfl_xor_sync(0xffffffffu, ax, o);
-                ay += __shfl_xor_sync(0xffffffffu, ay, o);
-                az += __shfl_xor_sync(0xffffffffu, az, o);
-            }
-            const double num = (gl == 0) ? ax : ((gl == 1) ? ay : az);
-            if (valid && gl < 3) out[3 * (int64_t)n + gl] = num / __ldg(node_mass + n);
+        const float* qb = reinterpret_cast<const float*>(smem_raw + (size_t)slot * kStageBytes + (src & 15)) + qoff;
+        const double h = valid ? __ldg(shift + 3 * f + comp) : 0.0;
+        double acc = 0.0;
+        int a = rot;
+#pragma unroll 4
+        for (int it = 0; it < cnt; ++it) {
+            // translate(): float32 position += float64 vector, rounded back to float32
+            const double v = round_to_f32((double)qb[3 * a] + h);
+            acc = fma(mb[a], v, acc);
+            a = (a + 1 == cnt) ? 0 : a + 1;
         }
+        if (valid) nodes[(row0 + f) * ld + out_col] = acc * inv_m;
         __syncthreads();     // everyone is done with this slot
         if (k + kStStages < n_items) stage_in(k + kStStages);
     }
@@ -198,8 +224,8 @@ struct wisp_com_plan {
     // device arrays
     double* d_masses = nullptr;
     int32_t *d_node_ptr = nullptr, *d_atom_idx = nullptr, *d_align_idx = nullptr;
-    double *d_align_mass = nullptr, *d_ent_mass = nullptr, *d_node_mass = nullptr;
-    int32_t* d_atom_first = nullptr;
+    double *d_align_mass = nullptr, *d_ent_mass = nullptr, *d_inv_node_mass = nullptr;
+    int4* d_node_info = nullptr;
     Piece* d_pieces = nullptr;
     double* d_shift = nullptr;
     int64_t shift_frames = 0;
@@ -257,7 +283,7 @@ int com_plan_create(wisp_ctx* ctx, int A, const double* masses, const int32_t* n
             int m = n + 1;
             while (m < N) {
                 const int s = h_first[m], e = s + (node_ptr[m + 1] - node_ptr[m]);
-                if (s - end > 64 || e - pc.atom0 > kPieceAtomsMax) break;
+                if (s - end > 64 || e - pc.atom0 > kPieceAtomsMax || m - n >= kPieceNodesMax) break;
                 end = e;
                 ++m;
             }
@@ -269,10 +295,15 @@ int com_plan_create(wisp_ctx* ctx, int A, const double* masses, const int32_t* n
     }
     pl->streaming = contiguous && !h_pieces.empty() && getenv("WISP_K1_GATHER") == nullptr;
     pl->P = (int)h_pieces.size();
+    std::vector<int4> h_info(N);
+    std::vector<double> h_inv(N);
+    for (int n = 0; n < N; ++n) { h_info[n] = make_int4(node_ptr[n], node_ptr[n + 1] - node_ptr[n], 0, 0); h_inv[n] = 1.0 / h_node_mass[n]; }
+    for (const Piece& pc : h_pieces)
+        for (int n = pc.node0; n < pc.node0 + pc.n_nodes; ++n) h_info[n].z = h_first[n] - pc.atom0;
     int rc = upload(h_masses, &pl->d_masses) || upload(h_np, &pl->d_node_ptr) || upload(h_ai, &pl->d_atom_idx) ||
              upload(h_al, &pl->d_align_idx) || upload(h_align_mass, &pl->d_align_mass) ||
-             upload(h_ent_mass, &pl->d_ent_mass) || upload(h_node_mass, &pl->d_node_mass) ||
-             upload(h_first, &pl->d_atom_first) || upload(h_pieces, &pl->d_pieces);
+             upload(h_ent_mass, &pl->d_ent_mass) || upload(h_inv, &pl->d_inv_node_mass) ||
+             upload(h_info, &pl->d_node_info) || upload(h_pieces, &pl->d_pieces);
     if (rc) { com_plan_destroy(ctx, pl); return 1; }
     *out = pl;
     return 0;
@@ -283,8 +314,8 @@ void com_plan_destroy(wisp_ctx* ctx, wisp_com_plan* pl) {
     if (ctx) cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     cudaFree(pl->d_masses); cudaFree(pl->d_node_ptr); cudaFree(pl->d_atom_idx); cudaFree(pl->d_align_idx);
-    cudaFree(pl->d_align_mass); cudaFree(pl->d_ent_mass); cudaFree(pl->d_node_mass);
-    cudaFree(pl->d_atom_first); cudaFree(pl->d_pieces); cudaFree(pl->d_shift);
+    cudaFree(pl->d_align_mass); cudaFree(pl->d_ent_mass); cudaFree(pl->d_inv_node_mass);
+    cudaFree(pl->d_node_info); cudaFree(pl->d_pieces); cudaFree(pl->d_shift);
     delete pl;
 }
 
@@ -310,14 +341,14 @@ int launch_com_plan(wisp_ctx* ctx, wisp_com_plan* pl, const float* d_coords, int
                                                                pl->d_shift, d_align_out, row0);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
-    const int smem = kStStages * kStageBytes;
+    const int smem = kStStages * kStageBytes + kPieceAtomsMax * 8;
     WISP_CUDA(cudaFuncSetAttribute(com_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int P = pl->P;
     int per_piece = std::max(1, (2 * ctx->sm_count) / P);
     per_piece = (int)std::min<int64_t>(per_piece, T);
     com_stream_kernel<<<P * per_piece, kStThreads, smem, st>>>(
-        d_coords, T, pl->A, pl->d_pieces, P, pl->d_shift, pl->d_node_ptr, pl->d_atom_first,
-        pl->d_ent_mass, pl->d_node_mass, d_nodes, ld, row0, (int64_t)T * pl->A * 12);
+        d_coords, T, pl->A, pl->d_pieces, P, pl->d_shift, pl->d_node_info, pl->d_ent_mass,
+        pl->d_inv_node_mass, d_nodes, ld, row0, (int64_t)T * pl->A * 12);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
     return 0;
