@@ -302,3 +302,69 @@ def test_com_streaming_many_pieces(ctx):
     want, _ = oracle.com_nodes(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx)
     np.testing.assert_allclose(nodes, want, rtol=0, atol=1e-11)
     np.testing.assert_allclose(avg, want.sum(axis=0) / want.shape[0], rtol=0, atol=1e-11)
+
+
+def test_driver_end_to_end(ctx, tmp_path):
+    """`python wisp_w_mdanalysis.py <config>` with every stage pointed at the B200 modules
+    (config keys *_functions_file), on a stand-in universe; compared with the oracle."""
+    import importlib
+    import sys
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       "wisp_mdanalysis_implementation_b200")
+    n, t, apn = 48, 160, 5
+    system, coords = synth.synth(n, t, apn, seed=31)
+    np.save(tmp_path / "traj.npy", coords)
+    cfg = tmp_path / "run.config"
+    out = tmp_path / "out"
+    cfg.write_text("""
+output_directory = %r
+node_selection_file = 'make_node_selections.py'
+trajectory_functions_file = 'trajectory_analysis_functions.py'
+adjacency_matrix_functions_file = 'adjacency_matrix_functions.py'
+func_adjacency_matrix_functions_file = 'functionalize_adj_matrix_functions.py'
+network_functions_file = 'network_analysis_functions.py'
+visualization_functions_file = None
+trajectory_analysis_boolean = True
+weight_by_contact_map_boolean = True
+summary_boolean = True
+pdb = 'synthetic'
+visualization_frame_pdb = 'synthetic'
+universe_factory = 'wisp_mdanalysis_implementation_b200.mda_standin:synthetic_universe'
+synthetic = dict(n_nodes=%d, n_frames=%d, atoms_per_node=%d, seed=31)
+substrate_node_definition = 'COM'
+substrate_selection_string = 'protein'
+alignment_selection = 'protein and name CA'
+traj_list = [%r]
+contact_map_distance_cutoff = 12.0
+which_contact_map = 'binary contact map'
+adjacency_matrix_style = 'pearson correlation'
+source_selection_string_list = ['ALA_3']
+sink_selection_string_list = ['ALA_40']
+number_of_paths = 12
+""" % (str(out), n, t, apn, str(tmp_path / "traj.npy")))
+    sys.path.insert(0, pkg)
+    try:
+        for m in ("IO", "wisp_w_mdanalysis", "trajectory_analysis_functions", "adjacency_matrix_functions",
+                  "functionalize_adj_matrix_functions", "network_analysis_functions", "make_node_selections"):
+            sys.modules.pop(m, None)
+        driver = importlib.import_module("wisp_w_mdanalysis")
+        paths = driver.main(str(cfg), argv=["wisp_w_mdanalysis.py", str(cfg)])
+    finally:
+        sys.path.remove(pkg)
+    # oracle on the same inputs
+    nodes, avg = oracle.traj_alignment_and_averaging(coords.copy(), system.masses, system.node_ptr,
+                                                     system.atom_idx, system.align_idx)
+    _, _, corr = oracle.pearson_correlation_analysis(oracle.cartesian_covariance(nodes, avg))
+    binary, _ = oracle.calc_contact_map(nodes, 12.0)
+    W = oracle.func_pearson_correlation(corr, binary)
+    want = oracle.get_paths_pruned(W, [2], [39], 12)
+    assert [p[1:] for p in paths] == [[int(x) for x in p[1:]] for p in want]
+    np.testing.assert_allclose([p[0] for p in paths], [p[0] for p in want], rtol=1e-9)
+    for name in ("average_node_positions.dat", "cartesian_covariance.dat", "binary_contact_map.dat",
+                 "avg_distance_contact_map.dat", "node_correlation.dat", "func_pearson_correlation.dat",
+                 "simply_formatted_paths.txt", "node_selections.txt", "summary.txt"):
+        assert (out / name).exists(), name
+    got_corr = np.loadtxt(out / "node_correlation.dat")
+    assert_corr_close(got_corr, corr)
+    lines = (out / "simply_formatted_paths.txt").read_text().splitlines()
+    assert lines[0].startswith("# Pathway_Length") and len(lines) == len(paths) + 1

@@ -299,3 +299,14 @@ class Universe:
         if pos[0] != len(tokens):
             raise ValueError("could not parse selection %r" % sel)
         return mask
+
+
+def synthetic_universe(parameters):
+    """``universe_factory`` hook of the driver (IO.py extension key): builds the stand-in
+    universe of a ``synth.SynthSystem`` described by ``parameters['synthetic']`` =
+    dict(n_nodes, n_frames, atoms_per_node, seed)."""
+    from . import synth
+    spec = parameters['synthetic']
+    system = synth.SynthSystem(spec['n_nodes'], spec['n_frames'], spec.get('atoms_per_node', 16),
+                               spec.get('seed', 1001))
+    return Universe.from_synth(system)

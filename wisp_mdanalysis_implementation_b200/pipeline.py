@@ -13,7 +13,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, sharding
 
 
 class FramePipeline:
@@ -27,9 +27,6 @@ class FramePipeline:
         self.T_total = int(frames_total if frames_total is not None else frames_local)
         self.cutoff, self.which_map, self.atomic = float(cutoff), int(which_map), bool(atomic)
         self.group = group
-        self.distributed = group is not None or (torch.distributed.is_available()
-                                                 and torch.distributed.is_initialized()
-                                                 and torch.distributed.get_world_size() > 1)
         self.ld = _lib.node_ld(self.N)
         self.tpad = _lib.frames_pad(self.T)
         self.npad = _lib.gram_ld(self.N)
@@ -66,9 +63,7 @@ class FramePipeline:
     def mean_and_center(self):
         s = self._stream()
         self.ctx.dev_colsum(self.d_x.data_ptr(), self.T, self.N, self.d_colsum.data_ptr(), stream=s)
-        if self.distributed:
-            torch.distributed.all_reduce(self.d_colsum, group=self.group)
-        torch.div(self.d_colsum, float(self.T_total), out=self.d_mean)
+        sharding.global_mean(self.d_colsum, self.d_mean, self.T_total, group=self.group)
         self.ctx.dev_center(self.d_x.data_ptr(), self.T, self.N, self.d_mean.data_ptr(),
                             d_p32=self.d_p32.data_ptr(), stream=s)
 
@@ -81,8 +76,7 @@ class FramePipeline:
                                  self.d_sums[1].data_ptr(), stream=self._stream())
 
     def reduce_and_epilogue(self):
-        if self.distributed:
-            torch.distributed.all_reduce(self.d_sums, group=self.group)    # the ONE big collective
+        sharding.reduce_sums(self.d_sums, group=self.group)    # the ONE big collective
         self.ctx.dev_epilogue(self.d_sums[0].data_ptr(), self.d_sums[1].data_ptr(), self.T_total,
                               self.N, self.cutoff, self.which_map, d_corr=self.d_corr.data_ptr(),
                               d_avgdist=self.d_avgdist.data_ptr(),
