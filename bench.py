@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-paths", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--apsp-nodes", type=int, default=10000, help="configs[2] APSP size (0 = skip)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -385,19 +386,42 @@ def main():
         cand = np.argwhere((hops >= 5) & (hops <= 8))
         cand = cand[cand[:, 0] < cand[:, 1]]
         s, t = (int(cand[0][0]), int(cand[0][1])) if len(cand) else (0, N - 1)
-        for prec in (64, 32):
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            d_W = torch.as_tensor(W, device=dev)
-            d_dist = torch.empty((N, N), dtype=torch.float64, device=dev)
-            d_pred = torch.empty((N, N), dtype=torch.int32, device=dev)
-            ctx.dev_apsp(d_W.data_ptr(), N, prec, d_dist.data_ptr(), d_pred.data_ptr(), stream=cur)
+        def time_apsp(d_W, n, prec, with_pred):
+            d_dist = torch.empty((n, n), dtype=torch.float64, device=dev)
+            d_pred = torch.empty((n, n), dtype=torch.int32, device=dev) if with_pred else None
+            pp = d_pred.data_ptr() if with_pred else None
+            ctx.dev_apsp(d_W.data_ptr(), n, prec, d_dist.data_ptr(), pp, stream=cur)
             torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-            ctx.dev_apsp(d_W.data_ptr(), N, prec, d_dist.data_ptr(), d_pred.data_ptr(), stream=cur)
+            ctx.dev_apsp(d_W.data_ptr(), n, prec, d_dist.data_ptr(), pp, stream=cur)
             ev1.record()
             torch.cuda.synchronize()
-            extra["apsp_fp%d_ms" % prec] = ev0.elapsed_time(ev1)
-            extra["apsp_fp%d_trelax_per_s" % prec] = float(N) ** 3 / (ev0.elapsed_time(ev1) * 1e-3) / 1e12
+            return ev0.elapsed_time(ev1)
+
+        d_W = torch.as_tensor(W, device=dev)
+        peaks_ = load_peaks()
+        for prec, with_pred, tag in ((64, True, "fp64"), (32, True, "fp32"), (32, False, "fp32_dist_only")):
+            ms = time_apsp(d_W, N, prec, with_pred)
+            extra["apsp_%s_ms" % tag] = ms
+            extra["apsp_%s_trelax_per_s" % tag] = float(N) ** 3 / (ms * 1e-3) / 1e12
+        # configs[2]: 10,000-node single-GPU blocked Floyd-Warshall (dense random symmetric costs)
+        if args.apsp_nodes > 0:
+            n3 = args.apsp_nodes
+            g = torch.Generator(device=dev)
+            g.manual_seed(1003)
+            Wb = torch.rand((n3, n3), dtype=torch.float64, device=dev, generator=g) * 2.0 + 0.05
+            Wb = torch.triu(Wb, 1)
+            Wb = Wb + Wb.T
+            big = {}
+            for prec, with_pred, tag in ((32, False, "fp32_dist_only"), (32, True, "fp32"), (64, True, "fp64")):
+                ms = time_apsp(Wb, n3, prec, with_pred)
+                rate = float(n3) ** 3 / (ms * 1e-3) / 1e12
+                big[tag] = {"ms": ms, "trelax_per_s": rate,
+                            "frac_of_fp32_pipe_peak": 2.0 * rate / peaks_["fp32_fma_tflops"],
+                            "frac_of_fadd_fmnmx_peak": rate / peaks_.get("fp32_minplus_trelax", 12.1)}
+            extra["apsp_%d_nodes" % n3] = big
+            del Wb
         t0 = time.perf_counter()
         paths = ctx.get_paths(W, [s], [t], args.paths)
         extra["get_paths_wall_ms"] = (time.perf_counter() - t0) * 1e3

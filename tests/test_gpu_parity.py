@@ -368,3 +368,26 @@ number_of_paths = 12
     assert_corr_close(got_corr, corr)
     lines = (out / "simply_formatted_paths.txt").read_text().splitlines()
     assert lines[0].startswith("# Pathway_Length") and len(lines) == len(paths) + 1
+
+
+def test_frame_pipeline_matches_c_abi_pipeline(ctx):
+    """pipeline.FramePipeline (device API + torch plumbing, what bench.py and the multi-GPU
+    path run) against the single-call C-ABI wisp_pipeline and a host round trip."""
+    import torch
+    from wisp_mdanalysis_implementation_b200.pipeline import FramePipeline
+    system, coords = synth.synth(300, 700, 5, seed=12)
+    ref = ctx.pipeline(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx,
+                       cutoff=13.0, which_map=1)
+    pipe = FramePipeline(ctx, 300, system.n_atoms, system.masses, system.node_ptr, system.atom_idx,
+                         system.align_idx, frames_local=700, cutoff=13.0, which_map=1)
+    assert pipe.plan_info["streaming"]
+    d_coords = torch.from_numpy(coords).cuda()
+    pipe.run_device(d_coords)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(pipe.d_corr.cpu().numpy(), ref["corr"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(pipe.d_avgdist.cpu().numpy(), ref["avgdist"], rtol=1e-12)
+    assert np.array_equal(pipe.d_binary.cpu().numpy(), ref["binary"])
+    h = torch.from_numpy(coords).pin_memory()
+    out = pipe.run_host(h)
+    np.testing.assert_allclose(out["corr"], ref["corr"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(out["w"], ref["w"], rtol=1e-12, atol=1e-300)

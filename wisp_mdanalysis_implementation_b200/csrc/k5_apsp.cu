@@ -20,6 +20,8 @@
 // the FP32-pipe mode the north star asks to be measured.
 #include "common.cuh"
 #include <limits>
+#include <cstdlib>
+#include <algorithm>
 
 namespace {
 
@@ -272,6 +274,299 @@ int run_apsp(wisp_ctx* ctx, const double* d_w, int N, double* d_dist, int32_t* d
     return 0;
 }
 
+
+// =======================================================================================
+// FP32 throughput mode: distance-only Floyd-Warshall with 128-wide rounds.
+//   * phase 3 is a 128x128 register-tiled min-plus product, 8x8 outputs per thread, two
+//     k-steps per inner iteration: candidates from packed FADD2 (two outputs per issue slot),
+//     folded with the 3-input minimum FMNMX3  d = min(d, c1+r1, c2+r2)  -> one instruction per
+//     relaxation instead of four (add, compare, 2 selects) in the predecessor-tracking form;
+//   * predecessors are recovered afterwards from the distances:
+//     pred[i][j] = argmin_u ( dist[i][u] + w[u][j] ) over the in-neighbours u of j
+//     (N^2 * degree work on the CSR graph, first minimum wins).
+// =======================================================================================
+constexpr int kT = 128;            // tile edge / round width
+constexpr int kH = 64;             // k-depth staged per pass in phase 3
+
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t fw_add2(float c, f32x2_t r) {
+    f32x2_t cc, o;
+    asm("mov.b64 %0, {%1,%1};" : "=l"(cc) : "f"(c));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(o) : "l"(cc), "l"(r));
+    return o;
+}
+__device__ __forceinline__ float fw_min3(float a, float b, float c) {
+    float o;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(o) : "f"(a), "f"(b), "f"(c));
+    return o;
+}
+__device__ __forceinline__ f32x2_t fw_pack(float lo, float hi) {
+    f32x2_t o;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(o) : "f"(lo), "f"(hi));
+    return o;
+}
+__device__ __forceinline__ void fw_unpack(f32x2_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+__global__ void fw32_init_kernel(const double* __restrict__ w, int N, int64_t n_pad, float* __restrict__ dist) {
+    const int64_t total = n_pad * n_pad;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / n_pad, c = e - r * n_pad;
+        float d = __int_as_float(0x7f800000);
+        if (r == c) d = 0.f;
+        else if (r < N && c < N) { const double v = w[r * N + c]; if (v != 0.0) d = (float)v; }
+        dist[e] = d;
+    }
+}
+
+// phase 1: pivot tile, 1024 threads, 16 elements each, in-place (row k / column k are fixed
+// points of iteration k because d[k][k] == 0 and weights are non-negative)
+__global__ void __launch_bounds__(1024)
+fw32_phase1_kernel(float* __restrict__ dist, int64_t ld, int kb) {
+    extern __shared__ __align__(16) unsigned char fw_smem[];
+    float* d = reinterpret_cast<float*>(fw_smem);     // [128][129]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // ty 0..31 -> rows 4ty..4ty+3
+    const int64_t base = (int64_t)kb * kT * ld + (int64_t)kb * kT;
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) d[(4 * ty + a) * (kT + 1) + tx + 32 * b] = dist[base + (4 * ty + a) * ld + tx + 32 * b];
+    __syncthreads();
+    for (int k = 0; k < kT; ++k) {
+        float rk[4], ck[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) rk[b] = d[k * (kT + 1) + tx + 32 * b];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) ck[a] = d[(4 * ty + a) * (kT + 1) + k];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const float cand = ck[a] + rk[b];
+                float* p = &d[(4 * ty + a) * (kT + 1) + tx + 32 * b];
+                if (cand < *p) *p = cand;
+            }
+        __syncthreads();
+    }
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) dist[base + (4 * ty + a) * ld + tx + 32 * b] = d[(4 * ty + a) * (kT + 1) + tx + 32 * b];
+}
+
+// phase 2: pivot row tiles (blockIdx.y == 0) and pivot column tiles (blockIdx.y == 1)
+__global__ void __launch_bounds__(1024)
+fw32_phase2_kernel(float* __restrict__ dist, int64_t ld, int kb) {
+    const int other = blockIdx.x;
+    if (other == kb) return;
+    const bool is_row = blockIdx.y == 0;
+    extern __shared__ __align__(16) unsigned char fw_smem[];
+    float* pv = reinterpret_cast<float*>(fw_smem);     // pivot [128][129]
+    float* ow = pv + kT * (kT + 1);                    // own   [128][129]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t pbase = (int64_t)kb * kT * ld + (int64_t)kb * kT;
+    const int64_t obase = is_row ? (int64_t)kb * kT * ld + (int64_t)other * kT
+                                 : (int64_t)other * kT * ld + (int64_t)kb * kT;
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) {
+            const int i = 4 * ty + a, j = tx + 32 * b;
+            pv[i * (kT + 1) + j] = dist[pbase + i * ld + j];
+            ow[i * (kT + 1) + j] = dist[obase + i * ld + j];
+        }
+    __syncthreads();
+    for (int k = 0; k < kT; ++k) {
+        float rk[4], ck[4];
+        if (is_row) {      // own = (kb, other): d[i][j] <- pivot[i][k] + own[k][j]
+#pragma unroll
+            for (int b = 0; b < 4; ++b) rk[b] = ow[k * (kT + 1) + tx + 32 * b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) ck[a] = pv[(4 * ty + a) * (kT + 1) + k];
+        } else {           // own = (other, kb): d[i][j] <- own[i][k] + pivot[k][j]
+#pragma unroll
+            for (int b = 0; b < 4; ++b) rk[b] = pv[k * (kT + 1) + tx + 32 * b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) ck[a] = ow[(4 * ty + a) * (kT + 1) + k];
+        }
+        __syncthreads();   // own row k / column k may be rewritten below by their owners
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const float cand = ck[a] + rk[b];
+                float* p = &ow[(4 * ty + a) * (kT + 1) + tx + 32 * b];
+                if (cand < *p) *p = cand;
+            }
+        __syncthreads();
+    }
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) {
+            const int i = 4 * ty + a, j = tx + 32 * b;
+            dist[obase + i * ld + j] = ow[i * (kT + 1) + j];
+        }
+}
+
+// phase 3: all tiles outside the pivot row / column
+__global__ void __launch_bounds__(256, 2)
+fw32_phase3_kernel(float* __restrict__ dist, int64_t ld, int kb) {
+    const int bj = blockIdx.x, bi = blockIdx.y;
+    if (bi == kb || bj == kb) return;
+    extern __shared__ __align__(16) unsigned char fw_smem[];
+    float (*ct)[kT + 4] = reinterpret_cast<float (*)[kT + 4]>(fw_smem);                          // column panel, transposed: ct[k][i]
+    float (*rt)[kT] = reinterpret_cast<float (*)[kT]>(fw_smem + sizeof(float) * kH * (kT + 4));  // row panel: rt[k][j]
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;            // cols {4tx.., 64+4tx..}, rows {4ty.., 64+4ty..}
+    const int64_t obase = (int64_t)bi * kT * ld + (int64_t)bj * kT;
+    float d[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int row = (a < 4) ? 4 * ty + a : 64 + 4 * ty + (a - 4);
+        const float4 v0 = *reinterpret_cast<const float4*>(dist + obase + row * ld + 4 * tx);
+        const float4 v1 = *reinterpret_cast<const float4*>(dist + obase + row * ld + 64 + 4 * tx);
+        d[a][0] = v0.x; d[a][1] = v0.y; d[a][2] = v0.z; d[a][3] = v0.w;
+        d[a][4] = v1.x; d[a][5] = v1.y; d[a][6] = v1.z; d[a][7] = v1.w;
+    }
+    for (int h = 0; h < kT / kH; ++h) {
+        const int64_t cbase = (int64_t)bi * kT * ld + (int64_t)kb * kT + h * kH;     // (bi, kb) cols h*64..
+        const int64_t rbase = ((int64_t)kb * kT + h * kH) * ld + (int64_t)bj * kT;   // (kb, bj) rows h*64..
+        __syncthreads();
+        for (int e = tid; e < kT * kH; e += 256) {
+            const int i = e >> 6, k = e & 63;            // column panel: 128 rows x 64 k (k contiguous)
+            ct[k][i] = dist[cbase + i * ld + k];
+            const int kk = e >> 7, j = e & 127;          // row panel: 64 k x 128 cols
+            rt[kk][j] = dist[rbase + kk * ld + j];
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int k = 0; k < kH; k += 2) {
+            const float4 c1a = *reinterpret_cast<const float4*>(&ct[k][4 * ty]);
+            const float4 c1b = *reinterpret_cast<const float4*>(&ct[k][64 + 4 * ty]);
+            const float4 c2a = *reinterpret_cast<const float4*>(&ct[k + 1][4 * ty]);
+            const float4 c2b = *reinterpret_cast<const float4*>(&ct[k + 1][64 + 4 * ty]);
+            const float4 r1a = *reinterpret_cast<const float4*>(&rt[k][4 * tx]);
+            const float4 r1b = *reinterpret_cast<const float4*>(&rt[k][64 + 4 * tx]);
+            const float4 r2a = *reinterpret_cast<const float4*>(&rt[k + 1][4 * tx]);
+            const float4 r2b = *reinterpret_cast<const float4*>(&rt[k + 1][64 + 4 * tx]);
+            const float c1[8] = {c1a.x, c1a.y, c1a.z, c1a.w, c1b.x, c1b.y, c1b.z, c1b.w};
+            const float c2[8] = {c2a.x, c2a.y, c2a.z, c2a.w, c2b.x, c2b.y, c2b.z, c2b.w};
+            const f32x2_t r1[4] = {fw_pack(r1a.x, r1a.y), fw_pack(r1a.z, r1a.w), fw_pack(r1b.x, r1b.y), fw_pack(r1b.z, r1b.w)};
+            const f32x2_t r2[4] = {fw_pack(r2a.x, r2a.y), fw_pack(r2a.z, r2a.w), fw_pack(r2b.x, r2b.y), fw_pack(r2b.z, r2b.w)};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int bp = 0; bp < 4; ++bp) {
+                    float l1, h1, l2, h2;
+                    fw_unpack(fw_add2(c1[a], r1[bp]), l1, h1);
+                    fw_unpack(fw_add2(c2[a], r2[bp]), l2, h2);
+                    d[a][2 * bp] = fw_min3(d[a][2 * bp], l1, l2);
+                    d[a][2 * bp + 1] = fw_min3(d[a][2 * bp + 1], h1, h2);
+                }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int row = (a < 4) ? 4 * ty + a : 64 + 4 * ty + (a - 4);
+        *reinterpret_cast<float4*>(dist + obase + row * ld + 4 * tx) = make_float4(d[a][0], d[a][1], d[a][2], d[a][3]);
+        *reinterpret_cast<float4*>(dist + obase + row * ld + 64 + 4 * tx) = make_float4(d[a][4], d[a][5], d[a][6], d[a][7]);
+    }
+}
+
+// ---- CSR of in-edges from the dense cost matrix, and the argmin predecessor pass ----
+__global__ void csr_count_kernel(const double* __restrict__ w, int N, int32_t* __restrict__ count) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    int c = 0;
+    for (int u = 0; u < N; ++u) c += (u != j && w[(int64_t)u * N + j] != 0.0) ? 1 : 0;
+    count[j] = c;
+}
+__global__ void csr_fill_kernel(const double* __restrict__ w, int N, const int32_t* __restrict__ ptr,
+                                int32_t* __restrict__ idx, float* __restrict__ val) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    int e = ptr[j];
+    for (int u = 0; u < N; ++u) {
+        const double v = w[(int64_t)u * N + j];
+        if (u != j && v != 0.0) { idx[e] = u; val[e] = (float)v; ++e; }
+    }
+}
+__global__ void fw32_final_kernel(const float* __restrict__ dist, int N, int64_t n_pad,
+                                  const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                  const float* __restrict__ val, double* __restrict__ out_dist,
+                                  int32_t* __restrict__ out_pred) {
+    const int64_t total = (int64_t)N * N;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / N), j = (int)(e - (int64_t)i * N);
+        const float dij = dist[(int64_t)i * n_pad + j];
+        if (out_dist) out_dist[e] = (double)dij;
+        if (out_pred) {
+            int p = -1;
+            if (i != j && dij < __int_as_float(0x7f800000)) {
+                float best = __int_as_float(0x7f800000);
+                const float* di = dist + (int64_t)i * n_pad;
+                for (int q = ptr[j]; q < ptr[j + 1]; ++q) {
+                    const int u = idx[q];
+                    const float c = di[u] + val[q];
+                    if (c < best) { best = c; p = u; }
+                }
+            }
+            out_pred[e] = p;
+        }
+    }
+}
+
+int run_apsp_f32_fast(wisp_ctx* ctx, const double* d_w, int N, double* d_dist, int32_t* d_pred,
+                      cudaStream_t st) {
+    const int64_t n_pad = round_up(N, kT);
+    const int nb = (int)(n_pad / kT);
+    void* pd = nullptr;
+    WISP_TRY(wisp_scratch(ctx, SCR_APSP_D, (size_t)n_pad * n_pad * sizeof(float), &pd));
+    float* dist = (float*)pd;
+    const int g = (int)std::min<int64_t>((n_pad * n_pad + 255) / 256, (int64_t)ctx->sm_count * 16);
+    fw32_init_kernel<<<g, 256, 0, st>>>(d_w, N, n_pad, dist);
+    ctx->launches++;
+    const int smem1 = kT * (kT + 1) * 4, smem2 = 2 * kT * (kT + 1) * 4;
+    const int smem3 = (int)sizeof(float) * kH * (2 * kT + 4);
+    WISP_CUDA(cudaFuncSetAttribute(fw32_phase3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    WISP_CUDA(cudaFuncSetAttribute(fw32_phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    WISP_CUDA(cudaFuncSetAttribute(fw32_phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    for (int kb = 0; kb < nb; ++kb) {
+        fw32_phase1_kernel<<<1, 1024, smem1, st>>>(dist, n_pad, kb);
+        ctx->launches++;
+        if (nb > 1) {
+            fw32_phase2_kernel<<<dim3(nb, 2), 1024, smem2, st>>>(dist, n_pad, kb);
+            fw32_phase3_kernel<<<dim3(nb, nb), 256, smem3, st>>>(dist, n_pad, kb);
+            ctx->launches += 2;
+        }
+    }
+    WISP_CUDA(cudaGetLastError());
+    // predecessors from the distances (CSR of in-edges built from the dense matrix)
+    int32_t *ptr = nullptr, *idx = nullptr;
+    float* val = nullptr;
+    if (d_pred) {
+        void* pp = nullptr;
+        WISP_TRY(wisp_scratch(ctx, SCR_APSP_P, (size_t)(N + 1) * 4 + 256, &pp));
+        ptr = (int32_t*)pp;
+        csr_count_kernel<<<(N + 127) / 128, 128, 0, st>>>(d_w, N, ptr + 1);
+        ctx->launches++;
+        std::vector<int32_t> h(N + 1, 0);
+        WISP_CUDA(cudaMemcpyAsync(h.data() + 1, ptr + 1, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+        WISP_CUDA(cudaStreamSynchronize(st));
+        for (int j = 0; j < N; ++j) h[j + 1] += h[j];
+        const size_t E = (size_t)h[N];
+        void* pe = nullptr;
+        WISP_TRY(wisp_scratch(ctx, SCR_MISC0, E * 8 + 256, &pe));
+        idx = (int32_t*)pe;
+        val = (float*)((char*)pe + round_up((int64_t)E * 4, 16));
+        WISP_CUDA(cudaMemcpyAsync(ptr, h.data(), (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, st));
+        csr_fill_kernel<<<(N + 127) / 128, 128, 0, st>>>(d_w, N, ptr, idx, val);
+        ctx->launches++;
+        WISP_CUDA(cudaStreamSynchronize(st));   // h (host vector) must outlive the H2D copy
+    }
+    const int g2 = (int)std::min<int64_t>(((int64_t)N * N + 255) / 256, (int64_t)ctx->sm_count * 16);
+    fw32_final_kernel<<<g2, 256, 0, st>>>(dist, N, n_pad, ptr, idx, val, d_dist, d_pred);
+    ctx->launches++;
+    WISP_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 int launch_apsp(wisp_ctx* ctx, const double* d_w, int N, int precision, double* d_dist,
@@ -279,5 +574,6 @@ int launch_apsp(wisp_ctx* ctx, const double* d_w, int N, int precision, double* 
     WISP_CHECK(N > 0, "apsp: empty graph");
     WISP_CHECK(precision == 64 || precision == 32, "apsp: precision must be 64 or 32 (got %d)", precision);
     if (precision == 64) return run_apsp<double>(ctx, d_w, N, d_dist, d_pred, st);
-    return run_apsp<float>(ctx, d_w, N, d_dist, d_pred, st);
+    if (getenv("WISP_FW32_TRACKED")) return run_apsp<float>(ctx, d_w, N, d_dist, d_pred, st);
+    return run_apsp_f32_fast(ctx, d_w, N, d_dist, d_pred, st);
 }
