@@ -220,6 +220,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-paths", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--stress-pairs", type=int, default=200)
+    ap.add_argument("--stress-paths", type=int, default=1000)
     ap.add_argument("--apsp-nodes", type=int, default=10000, help="configs[2] APSP size (0 = skip)")
     args = ap.parse_args()
 
@@ -428,6 +430,25 @@ def main():
         extra["get_paths"] = dict(source=s, sink=t, returned=len(paths), shortest=paths[0][0],
                                   longest=paths[-1][0], **ctx.paths_stats())
         extra["hops_apsp_wall_ms"] = t_hops * 1e3
+        # configs[4]: 200 (source, sink) pairs x 1,000 suboptimal paths each, one APSP
+        if args.stress_pairs > 0:
+            rng = np.random.default_rng(1005)
+            cand5 = np.argwhere((hops >= 4) & (hops <= 10))
+            cand5 = cand5[cand5[:, 0] < cand5[:, 1]]
+            sel = cand5[rng.choice(len(cand5), size=min(args.stress_pairs, len(cand5)), replace=False)]
+            t0 = time.perf_counter()
+            ctx.paths_prepare(W)
+            t_prep = time.perf_counter() - t0
+            n_ret, exp_tot = 0, 0
+            t0 = time.perf_counter()
+            for (a, b) in sel:
+                n_ret += len(ctx.paths_query([int(a)], [int(b)], args.stress_paths))
+                exp_tot += ctx.paths_stats()["expansions"]
+            t_q = time.perf_counter() - t0
+            extra["stress_c5"] = {"pairs": int(len(sel)), "paths_each": args.stress_paths,
+                                  "prepare_ms": t_prep * 1e3, "queries_wall_ms": t_q * 1e3,
+                                  "paths_returned": int(n_ret), "expansions": int(exp_tot),
+                                  "expansions_per_s": exp_tot / max(t_q, 1e-9)}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle timed on the box's host cores ----
     cpu_baseline = None

@@ -111,6 +111,11 @@ int wisp_apsp(wisp_ctx* ctx, const double* w, int N, int precision, double* out_
  * context; fetch them with wisp_paths_size / wisp_paths_fetch. */
 int wisp_get_paths(wisp_ctx* ctx, const double* w, int N, const int32_t* sources, int n_sources,
                    const int32_t* sinks, int n_sinks, int number_of_paths, int flags);
+/* The same in two steps, for many queries on one graph (configs[4]: 200 pairs x 1,000 paths):
+ * prepare = upload + APSP + adjacency, query = seed + cutoff passes for one source/sink set. */
+int wisp_paths_prepare(wisp_ctx* ctx, const double* w, int N, int flags);
+int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sources, const int32_t* sinks,
+                     int n_sinks, int number_of_paths, int flags);
 int wisp_paths_size(wisp_ctx* ctx, int64_t* n_paths, int64_t* n_node_entries);
 int wisp_paths_fetch(wisp_ctx* ctx, double* lengths, int64_t* offsets /* n_paths+1 */,
                      int32_t* nodes);

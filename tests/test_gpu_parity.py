@@ -391,3 +391,31 @@ def test_frame_pipeline_matches_c_abi_pipeline(ctx):
     out = pipe.run_host(h)
     np.testing.assert_allclose(out["corr"], ref["corr"], rtol=0, atol=1e-13)
     np.testing.assert_allclose(out["w"], ref["w"], rtol=1e-12, atol=1e-300)
+
+
+def test_paths_prepare_query_stress(ctx):
+    """configs[4] in miniature: one APSP, many independent (source, sink) queries."""
+    W = synth.random_cost_matrix(60, seed=77, density=0.12, lo=0.05, hi=0.9)
+    ctx.paths_prepare(W)
+    rng = np.random.default_rng(5)
+    for _ in range(12):
+        s, t = (int(x) for x in rng.choice(60, size=2, replace=False))
+        K = int(rng.integers(3, 60))
+        want = oracle.get_paths_pruned(W, [s], [t], K)
+        got = ctx.paths_query([s], [t], K)
+        assert [p[1:] for p in got] == [[int(x) for x in p[1:]] for p in want]
+        assert [p[0] for p in got] == [float(p[0]) for p in want]
+
+
+def test_apsp_fp32_dense_predecessors(ctx):
+    """Dense graph: the FP32 mode recovers predecessors with the tiled argmin product."""
+    W = synth.random_cost_matrix(150, seed=3, density=0.95)
+    D, _ = oracle.apsp_dijkstra(W)
+    dist, pred = ctx.apsp(W, precision=32)
+    np.testing.assert_allclose(dist, D, rtol=2e-6)
+    ii, jj = np.nonzero(pred >= 0)
+    pp = pred[ii, jj]
+    assert np.all(W[pp, jj] != 0)
+    np.testing.assert_allclose(dist[ii, pp] + W[pp, jj], dist[ii, jj], rtol=2e-5, atol=1e-12)
+    off = ~np.eye(150, dtype=bool)
+    assert np.all(pred[off] >= 0) and np.all(np.diagonal(pred) == -1)

@@ -41,6 +41,8 @@ SIGNATURES = {
                              _P, _P, _P, _P, _P, _P]),
     "wisp_apsp": (_int, [_c_ctx, _P, _int, _int, _P, _P]),
     "wisp_get_paths": (_int, [_c_ctx, _P, _int, _P, _int, _P, _int, _int, _int]),
+    "wisp_paths_prepare": (_int, [_c_ctx, _P, _int, _int]),
+    "wisp_paths_query": (_int, [_c_ctx, _P, _int, _P, _int, _int, _int]),
     "wisp_paths_size": (_int, [_c_ctx, C.POINTER(_i64), C.POINTER(_i64)]),
     "wisp_paths_fetch": (_int, [_c_ctx, _P, _P, _P]),
     "wisp_paths_stats": (_int, [_c_ctx, _P]),
@@ -251,6 +253,21 @@ class Context:
         flags = (1 if node0_quirk else 0) | (2 if apsp_fp32 else 0)
         self._check(self._lib.wisp_get_paths(self._ctx, _ptr(w), N, _ptr(so), len(so), _ptr(si),
                                              len(si), int(number_of_paths), flags))
+        return self._fetch_paths()
+
+    def paths_prepare(self, w, apsp_fp32=False):
+        """Upload a cost matrix and run the APSP once; follow with any number of paths_query."""
+        w = _arr(w, np.float64, "adjacency_matrix")
+        self._check(self._lib.wisp_paths_prepare(self._ctx, _ptr(w), w.shape[0], 2 if apsp_fp32 else 0))
+
+    def paths_query(self, sources, sinks, number_of_paths, node0_quirk=True):
+        so = _arr(sources, np.int32, "sources")
+        si = _arr(sinks, np.int32, "sinks")
+        self._check(self._lib.wisp_paths_query(self._ctx, _ptr(so), len(so), _ptr(si), len(si),
+                                               int(number_of_paths), 1 if node0_quirk else 0))
+        return self._fetch_paths()
+
+    def _fetch_paths(self):
         n_paths, n_nodes = _i64(), _i64()
         self._check(self._lib.wisp_paths_size(self._ctx, C.byref(n_paths), C.byref(n_nodes)))
         lengths = np.empty(n_paths.value, dtype=np.float64)

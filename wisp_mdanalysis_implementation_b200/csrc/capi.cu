@@ -50,6 +50,7 @@ extern "C" void wisp_ctx_destroy(wisp_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    if (ctx->pg && ctx->pg_free) ctx->pg_free(ctx->pg);
     for (auto& b : ctx->scratch)
         if (b.p) cudaFree(b.p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -54,6 +54,8 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
+struct PathGraphState;
+
 struct wisp_ctx {
     int device = 0;
     int sm_count = 148;
@@ -67,6 +69,8 @@ struct wisp_ctx {
     std::vector<int64_t> path_off;
     std::vector<int32_t> path_nodes;
     double path_stats[6] = {0, 0, 0, 0, 0, 0};
+    PathGraphState* pg = nullptr;            // graph + APSP state of wisp_paths_prepare
+    void (*pg_free)(PathGraphState*) = nullptr;
 };
 
 int wisp_scratch(wisp_ctx* ctx, int slot, size_t bytes, void** out);   // grow-only device buffer

@@ -512,6 +512,58 @@ __global__ void fw32_final_kernel(const float* __restrict__ dist, int N, int64_t
     }
 }
 
+// dense graphs: pred[i][j] = argmin_u (dist[i][u] + w[u][j]) as a tiled min-plus product with
+// argmin (64x64 outputs per CTA, 4x4 per thread); used when the CSR form would be ~N^3 anyway
+__global__ void __launch_bounds__(256)
+fw32_pred_dense_kernel(const float* __restrict__ dist, int64_t n_pad, const double* __restrict__ w, int N,
+                       int32_t* __restrict__ out_pred) {
+    __shared__ float dt[64][64 + 4];    // dt[u][i]
+    __shared__ float wt[64][64];        // wt[u][j]
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    const float INF = __int_as_float(0x7f800000);
+    float best[4][4];
+    int arg[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { best[a][b] = INF; arg[a][b] = -1; }
+    for (int u0 = 0; u0 < N; u0 += 64) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+            const int r = e >> 6, c = e & 63;
+            // D tile: row i0+r, col u0+c  -> dt[c][r]
+            dt[c][r] = dist[(int64_t)(i0 + r) * n_pad + u0 + c];     // padded: always in range
+            // W tile: row u0+r, col j0+c  -> wt[r][c]
+            const int u = u0 + r, j = j0 + c;
+            float v = INF;
+            if (u < N && j < N && u != j) { const double x = w[(int64_t)u * N + j]; if (x != 0.0) v = (float)x; }
+            wt[r][c] = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < 64; ++k) {
+            const float4 cv = *reinterpret_cast<const float4*>(&dt[k][4 * ty]);
+            const float4 rv = *reinterpret_cast<const float4*>(&wt[k][4 * tx]);
+            const float c4[4] = {cv.x, cv.y, cv.z, cv.w}, r4[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const float cand = c4[a] + r4[b];
+                    if (cand < best[a][b]) { best[a][b] = cand; arg[a][b] = u0 + k; }
+                }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = i0 + 4 * ty + a, j = j0 + 4 * tx + b;
+            if (i < N && j < N) out_pred[(int64_t)i * N + j] = (i == j) ? -1 : arg[a][b];
+        }
+}
+
 int run_apsp_f32_fast(wisp_ctx* ctx, const double* d_w, int N, double* d_dist, int32_t* d_pred,
                       cudaStream_t st) {
     const int64_t n_pad = round_up(N, kT);
@@ -551,6 +603,16 @@ int run_apsp_f32_fast(wisp_ctx* ctx, const double* d_w, int N, double* d_dist, i
         WISP_CUDA(cudaStreamSynchronize(st));
         for (int j = 0; j < N; ++j) h[j + 1] += h[j];
         const size_t E = (size_t)h[N];
+        if (E > (size_t)N * N / 8) {
+            // dense graph: tiled argmin product instead of the CSR scan
+            fw32_pred_dense_kernel<<<dim3((N + 63) / 64, (N + 63) / 64), 256, 0, st>>>(dist, n_pad, d_w, N, d_pred);
+            ctx->launches++;
+            const int gd = (int)std::min<int64_t>(((int64_t)N * N + 255) / 256, (int64_t)ctx->sm_count * 16);
+            fw32_final_kernel<<<gd, 256, 0, st>>>(dist, N, n_pad, nullptr, nullptr, nullptr, d_dist, nullptr);
+            ctx->launches++;
+            WISP_CUDA(cudaGetLastError());
+            return 0;
+        }
         void* pe = nullptr;
         WISP_TRY(wisp_scratch(ctx, SCR_MISC0, E * 8 + 256, &pe));
         idx = (int32_t*)pe;

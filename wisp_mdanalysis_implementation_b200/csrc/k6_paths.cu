@@ -193,21 +193,38 @@ double now_ms() {
 
 }  // namespace
 
-extern "C" int wisp_get_paths(wisp_ctx* ctx, const double* w, int N, const int32_t* sources,
-                              int n_sources, const int32_t* sinks, int n_sinks,
-                              int number_of_paths, int flags) {
-    WISP_CHECK(ctx && w && N > 1, "get_paths: bad arguments");
-    WISP_CHECK(n_sources > 0 && n_sinks > 0, "get_paths: empty source or sink list");
-    WISP_CHECK(number_of_paths >= 1, "get_paths: number_of_paths must be >= 1");
-    const int quirk = (flags & 1) ? 1 : 0;
+// graph + APSP state kept between wisp_paths_prepare and any number of wisp_paths_query calls
+struct PathGraphState {
+    int N = 0, precision = 64;
+    std::vector<double> w;                       // host copy (LR path lengths are summed from it)
+    std::vector<int32_t> adj_ptr, adj_idx;
+    std::vector<double> adj_w;
+    double max_simple_len = 0.0, apsp_ms = 0.0;
+    void *d_w = nullptr, *d_dist = nullptr, *d_pred = nullptr, *d_adj_ptr = nullptr, *d_adj_idx = nullptr,
+         *d_adj_w = nullptr;
+};
+static void free_path_graph(PathGraphState* g) { delete g; }
+
+extern "C" int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sources,
+                                const int32_t* sinks, int n_sinks, int number_of_paths, int flags);
+
+extern "C" int wisp_paths_prepare(wisp_ctx* ctx, const double* w, int N, int flags) {
+    WISP_CHECK(ctx && w && N > 1, "paths_prepare: bad arguments");
+    WISP_CUDA(cudaSetDevice(ctx->device));
     const int precision = (flags & 2) ? 32 : 64;
     cudaStream_t st = ctx->stream;
-    for (int i = 0; i < n_sources; ++i) WISP_CHECK(sources[i] >= 0 && sources[i] < N, "get_paths: source %d out of range", sources[i]);
-    for (int i = 0; i < n_sinks; ++i) WISP_CHECK(sinks[i] >= 0 && sinks[i] < N, "get_paths: sink %d out of range", sinks[i]);
-
+    if (ctx->pg) { free_path_graph(ctx->pg); ctx->pg = nullptr; }
+    PathGraphState* g = new PathGraphState();
+    ctx->pg = g;
+    ctx->pg_free = free_path_graph;
+    g->N = N;
+    g->precision = precision;
+    g->w.assign(w, w + (size_t)N * N);
     // ---- graph: non-zero entry <=> edge (networkx 1.x Graph(data=W), :20) ----
-    std::vector<int32_t> adj_ptr(N + 1, 0), adj_idx;
-    std::vector<double> adj_w;
+    std::vector<int32_t>& adj_ptr = g->adj_ptr;
+    std::vector<int32_t>& adj_idx = g->adj_idx;
+    std::vector<double>& adj_w = g->adj_w;
+    adj_ptr.assign(N + 1, 0);
     for (int u = 0; u < N; ++u) {
         for (int v = 0; v < N; ++v) {
             const double x = w[(size_t)u * N + v];
@@ -223,24 +240,56 @@ extern "C" int wisp_get_paths(wisp_ctx* ctx, const double* w, int N, const int32
     const size_t E = adj_idx.size();
     // upper bound on the length of any finite simple path: every node contributes at most
     // its heaviest finite edge.  Past it, no new path can ever appear.
-    double max_simple_len = 0.0;
     for (int u = 0; u < N; ++u) {
         double m = 0.0;
         for (int e = adj_ptr[u]; e < adj_ptr[u + 1]; ++e)
             if (adj_w[e] < 1e300 && adj_w[e] > m) m = adj_w[e];
-        max_simple_len += m;
+        g->max_simple_len += m;
     }
-
     // ---- APSP on the device (K5) ----
     double t0 = now_ms();
-    void *d_w, *d_dist, *d_pred;
-    WISP_TRY(wisp_scratch(ctx, SCR_MISC2, (size_t)N * N * 8, &d_w));
-    WISP_TRY(wisp_scratch(ctx, SCR_MISC3, (size_t)N * N * 8, &d_dist));
-    WISP_TRY(wisp_scratch(ctx, SCR_MISC4, (size_t)N * N * 4, &d_pred));
-    WISP_CUDA(cudaMemcpyAsync(d_w, w, (size_t)N * N * 8, cudaMemcpyHostToDevice, st));
-    WISP_TRY(launch_apsp(ctx, (const double*)d_w, N, precision, (double*)d_dist, (int32_t*)d_pred, st));
+    WISP_TRY(wisp_scratch(ctx, SCR_MISC2, (size_t)N * N * 8, &g->d_w));
+    WISP_TRY(wisp_scratch(ctx, SCR_MISC3, (size_t)N * N * 8, &g->d_dist));
+    WISP_TRY(wisp_scratch(ctx, SCR_MISC4, (size_t)N * N * 4, &g->d_pred));
+    WISP_CUDA(cudaMemcpyAsync(g->d_w, w, (size_t)N * N * 8, cudaMemcpyHostToDevice, st));
+    WISP_TRY(launch_apsp(ctx, (const double*)g->d_w, N, precision, (double*)g->d_dist, (int32_t*)g->d_pred, st));
+    WISP_TRY(wisp_scratch(ctx, SCR_MISC5, round_up((size_t)(N + 1) * 4, 16) + E * 4 + 64, &g->d_adj_ptr));
+    g->d_adj_idx = (char*)g->d_adj_ptr + round_up((size_t)(N + 1) * 4, 16);
+    WISP_TRY(wisp_scratch(ctx, SCR_MISC6, E * 8 + 16, &g->d_adj_w));
+    WISP_CUDA(cudaMemcpyAsync(g->d_adj_ptr, adj_ptr.data(), (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (E) {
+        WISP_CUDA(cudaMemcpyAsync(g->d_adj_idx, adj_idx.data(), E * 4, cudaMemcpyHostToDevice, st));
+        WISP_CUDA(cudaMemcpyAsync(g->d_adj_w, adj_w.data(), E * 8, cudaMemcpyHostToDevice, st));
+    }
     WISP_CUDA(cudaStreamSynchronize(st));
-    const double apsp_ms = now_ms() - t0;
+    g->apsp_ms = now_ms() - t0;
+    return 0;
+}
+
+extern "C" int wisp_get_paths(wisp_ctx* ctx, const double* w, int N, const int32_t* sources,
+                              int n_sources, const int32_t* sinks, int n_sinks,
+                              int number_of_paths, int flags) {
+    WISP_TRY(wisp_paths_prepare(ctx, w, N, flags));
+    return wisp_paths_query(ctx, sources, n_sources, sinks, n_sinks, number_of_paths, flags);
+}
+
+extern "C" int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sources,
+                                const int32_t* sinks, int n_sinks, int number_of_paths, int flags) {
+    WISP_CHECK(ctx && ctx->pg, "paths_query: call wisp_paths_prepare first");
+    WISP_CHECK(sources && sinks && n_sources > 0 && n_sinks > 0, "get_paths: empty source or sink list");
+    WISP_CHECK(number_of_paths >= 1, "get_paths: number_of_paths must be >= 1");
+    WISP_CUDA(cudaSetDevice(ctx->device));
+    PathGraphState* g = ctx->pg;
+    const int N = g->N;
+    const double* w = g->w.data();
+    const int quirk = (flags & 1) ? 1 : 0;
+    cudaStream_t st = ctx->stream;
+    for (int i = 0; i < n_sources; ++i) WISP_CHECK(sources[i] >= 0 && sources[i] < N, "get_paths: source %d out of range", sources[i]);
+    for (int i = 0; i < n_sinks; ++i) WISP_CHECK(sinks[i] >= 0 && sinks[i] < N, "get_paths: sink %d out of range", sinks[i]);
+    void *d_dist = g->d_dist, *d_pred = g->d_pred, *d_adj_ptr = g->d_adj_ptr, *d_adj_idx = g->d_adj_idx,
+         *d_adj_w = g->d_adj_w;
+    const double max_simple_len = g->max_simple_len;
+    const double apsp_ms = g->apsp_ms;
 
     // ---- pairs in the reference's loop order (:27-29), seed path (:25-36) ----
     std::vector<int32_t> pairs;
@@ -282,17 +331,9 @@ extern "C" int wisp_get_paths(wisp_ctx* ctx, const double* w, int N, const int32
     double cutoff = shortest_length;
 
     // ---- device buffers for the enumeration ----
-    void *d_adj_ptr, *d_adj_idx, *d_adj_w, *d_pairs, *d_cnt;
-    WISP_TRY(wisp_scratch(ctx, SCR_MISC6, E * 8 + 16, &d_adj_w));
+    void *d_pairs, *d_cnt;
     WISP_TRY(wisp_scratch(ctx, SCR_MISC7, (size_t)n_pairs * 8 + 256, &d_pairs));
-    d_cnt = (char*)d_pairs + round_up((size_t)n_pairs * 8, 64);     // 4 x int32 + 1 x u64 + frontier counts
-    WISP_TRY(wisp_scratch(ctx, SCR_MISC5, round_up((size_t)(N + 1) * 4, 16) + E * 4 + 64, &d_adj_ptr));
-    d_adj_idx = (char*)d_adj_ptr + round_up((size_t)(N + 1) * 4, 16);
-    WISP_CUDA(cudaMemcpyAsync(d_adj_ptr, adj_ptr.data(), (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, st));
-    if (E) {
-        WISP_CUDA(cudaMemcpyAsync(d_adj_idx, adj_idx.data(), E * 4, cudaMemcpyHostToDevice, st));
-        WISP_CUDA(cudaMemcpyAsync(d_adj_w, adj_w.data(), E * 8, cudaMemcpyHostToDevice, st));
-    }
+    d_cnt = (char*)d_pairs + round_up((size_t)n_pairs * 8, 64);     // counters + frontier counts
     WISP_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
 
     int cap_paths = std::max(4096, 8 * number_of_paths * std::max(1, n_pairs));
