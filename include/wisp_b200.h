@@ -123,6 +123,14 @@ int wisp_paths_fetch(wisp_ctx* ctx, double* lengths, int64_t* offsets /* n_paths
  * [3] apsp ms, [4] enumeration ms, [5] host finalize ms */
 int wisp_paths_stats(wisp_ctx* ctx, double* out6);
 
+/* ---- stage-boundary text files (host only) ---------------------------- */
+/* Byte-identical to np.savetxt(path, a, fmt='%.18e' / '%i', header=...), formatted on all
+ * host threads.  header may be NULL. */
+int wisp_savetxt_f64(const char* path, const double* a, int64_t rows, int64_t cols, const char* header);
+int wisp_savetxt_i64(const char* path, const int64_t* a, int64_t rows, int64_t cols, const char* header);
+/* np.loadtxt for the same files: out == NULL returns only the shape. */
+int wisp_loadtxt_f64(const char* path, double* out, int64_t capacity, int64_t* rows, int64_t* cols);
+
 /* ---- device-buffer entry points (bench, multi-GPU orchestration) --------------------- */
 
 /* Node map ("plan") for K1: uploads masses / CSR node map / alignment landmarks once and

@@ -1,0 +1,51 @@
+"""Host text I/O: byte-identical to np.savetxt, round-trips np.loadtxt.
+CPU only -- these routines need no GPU."""
+import numpy as np
+
+from wisp_mdanalysis_implementation_b200 import _lib
+
+
+def test_savetxt_matches_numpy_bytes(tmp_path):
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(137, 53)) * 10.0 ** rng.integers(-12, 12, size=(137, 53))
+    a[0, 0] = 0.0
+    a[1, 1] = -0.0
+    a[2, 2] = np.inf
+    a[3, 3] = -np.inf
+    a[4, 4] = np.nan
+    np.savetxt(tmp_path / "np.dat", a)
+    _lib.savetxt(str(tmp_path / "c.dat"), a)
+    assert (tmp_path / "np.dat").read_bytes() == (tmp_path / "c.dat").read_bytes()
+    b = (rng.random((60, 60)) < 0.3).astype(np.int64)
+    np.savetxt(tmp_path / "npi.dat", b, fmt='%i')
+    _lib.savetxt(str(tmp_path / "ci.dat"), b, fmt='%i')
+    assert (tmp_path / "npi.dat").read_bytes() == (tmp_path / "ci.dat").read_bytes()
+    v = rng.normal(size=17)
+    np.savetxt(tmp_path / "npv.dat", v, header='Shape: nNodes x 3 (%d x 3)' % 17)
+    _lib.savetxt(str(tmp_path / "cv.dat"), v, header='Shape: nNodes x 3 (%d x 3)' % 17)
+    assert (tmp_path / "npv.dat").read_bytes() == (tmp_path / "cv.dat").read_bytes()
+
+
+def test_loadtxt_round_trip(tmp_path):
+    rng = np.random.default_rng(1)
+    a = rng.normal(size=(301, 77))
+    np.savetxt(tmp_path / "a.dat", a, header="a header line")
+    got = _lib.loadtxt(str(tmp_path / "a.dat"))
+    assert np.array_equal(got, a)            # %.18e round-trips float64 exactly
+    assert np.array_equal(got, np.loadtxt(tmp_path / "a.dat"))
+    v = rng.normal(size=40)
+    np.savetxt(tmp_path / "v.dat", v)
+    assert np.array_equal(_lib.loadtxt(str(tmp_path / "v.dat")), v)
+
+
+def test_large_matrix_speed(tmp_path):
+    a = np.random.default_rng(2).normal(size=(1500, 1500))
+    import time
+    t0 = time.perf_counter()
+    _lib.savetxt(str(tmp_path / "big.dat"), a)
+    t_c = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    b = _lib.loadtxt(str(tmp_path / "big.dat"))
+    t_l = time.perf_counter() - t0
+    assert np.array_equal(a, b)
+    assert t_c < 10 and t_l < 10

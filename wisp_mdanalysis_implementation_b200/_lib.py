@@ -46,6 +46,9 @@ SIGNATURES = {
     "wisp_paths_size": (_int, [_c_ctx, C.POINTER(_i64), C.POINTER(_i64)]),
     "wisp_paths_fetch": (_int, [_c_ctx, _P, _P, _P]),
     "wisp_paths_stats": (_int, [_c_ctx, _P]),
+    "wisp_savetxt_f64": (_int, [C.c_char_p, _P, _i64, _i64, C.c_char_p]),
+    "wisp_savetxt_i64": (_int, [C.c_char_p, _P, _i64, _i64, C.c_char_p]),
+    "wisp_loadtxt_f64": (_int, [C.c_char_p, _P, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "wisp_com_plan_create": (_int, [_c_ctx, _int, _P, _P, _P, _int, _P, _int, _int, C.POINTER(_P)]),
     "wisp_com_plan_destroy": (None, [_c_ctx, _P]),
     "wisp_com_plan_info": (_int, [_P, C.POINTER(_int), C.POINTER(_int)]),
@@ -340,6 +343,33 @@ class Context:
                                                     _ptr(d_atom_base), _ptr(d_node_of_atom),
                                                     _ptr(d_modes), n_modes, _ptr(d_coeff),
                                                     float(noise_sigma), int(seed), _ptr(stream)))
+
+
+def savetxt(path, array, fmt='%.18e', header=''):
+    """np.savetxt-compatible writer for the two formats the reference uses."""
+    a = np.asarray(array)
+    shape = a.shape if a.ndim == 2 else (a.size, 1)
+    hdr = header.encode() if header else None
+    if fmt == '%.18e':
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        rc = lib().wisp_savetxt_f64(os.fsencode(path), _ptr(a), shape[0], shape[1], hdr)
+    elif fmt in ('%i', '%d'):
+        a = np.ascontiguousarray(a, dtype=np.int64)
+        rc = lib().wisp_savetxt_i64(os.fsencode(path), _ptr(a), shape[0], shape[1], hdr)
+    else:
+        raise ValueError("savetxt: unsupported format %r" % fmt)
+    if rc != 0:
+        raise WispError(lib().wisp_last_error().decode())
+
+
+def loadtxt(path):
+    rows, cols = _i64(), _i64()
+    if lib().wisp_loadtxt_f64(os.fsencode(path), None, 0, C.byref(rows), C.byref(cols)) != 0:
+        raise WispError(lib().wisp_last_error().decode())
+    out = np.empty((rows.value, cols.value), dtype=np.float64)
+    if lib().wisp_loadtxt_f64(os.fsencode(path), _ptr(out), out.size, C.byref(rows), C.byref(cols)) != 0:
+        raise WispError(lib().wisp_last_error().decode())
+    return out[:, 0].copy() if cols.value == 1 else out
 
 
 def node_ld(n_nodes):

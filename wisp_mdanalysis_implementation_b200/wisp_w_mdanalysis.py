@@ -19,6 +19,7 @@ for _p in (_HERE, os.path.dirname(_HERE)):
         sys.path.insert(0, _p)
 
 from IO import config_parser, summary  # noqa: E402
+from wisp_mdanalysis_implementation_b200 import textio  # noqa: E402
 
 
 def _stage(parameters, key, name):
@@ -107,19 +108,19 @@ def main(config_file, argv=None):
     else:
         n = len(selection_list)
         print('Loading in the user specified cartesian covariance data file. Note: no node trajectory has been created.')
-        Node_cart_covariance = np.loadtxt(parameters['user_input_cartesian_covariance_matrix'])
+        Node_cart_covariance = textio.loadtxt(parameters['user_input_cartesian_covariance_matrix'])
         if Node_cart_covariance.shape[0] % 3 != 0 or Node_cart_covariance.shape[0] != Node_cart_covariance.shape[1]:
             print('User has read in a cartesian covariance matrix that does not have the correct shape '
                   '(expected: %d x %d, got: %d x %d).' % (3 * n, 3 * n, Node_cart_covariance.shape[0], Node_cart_covariance.shape[1]))
             sys.exit()
         avg_Node_positions = None
         if parameters['user_input_average_node_positions']:
-            avg_Node_positions = np.loadtxt(parameters['user_input_average_node_positions'])
+            avg_Node_positions = textio.loadtxt(parameters['user_input_average_node_positions'])
             if avg_Node_positions.shape != (n, 3):
                 print('User has read in an average node positions file that does not have the correct shape.')
                 sys.exit()
         if parameters['user_input_contact_map']:
-            contact_map = np.loadtxt(parameters['user_input_contact_map'])
+            contact_map = textio.loadtxt(parameters['user_input_contact_map'])
             if contact_map.shape != (n, n):
                 print('User has read in a contact map that does not have the correct shape.')
                 sys.exit()
@@ -129,7 +130,7 @@ def main(config_file, argv=None):
         print('Beginning the calculation of the adjacency matrix (' + parameters['adjacency_matrix_style'] + ').')
         adjacency_matrix = adjacency_matrix_analysis(Node_cart_covariance, avg_Node_positions, out)   # B3
     else:
-        adjacency_matrix = np.loadtxt(parameters['user_input_adjacency_matrix'])
+        adjacency_matrix = textio.loadtxt(parameters['user_input_adjacency_matrix'])
         if adjacency_matrix.shape != (len(selection_list), len(selection_list)):
             print('User has read in an adjacency matrix that does not have the correct shape.')
             sys.exit()
