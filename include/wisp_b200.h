@@ -89,6 +89,15 @@ int wisp_contact_map(wisp_ctx* ctx, const double* nodes, int64_t T, int N, doubl
 int wisp_func_pearson(wisp_ctx* ctx, const double* corr, int N, const double* contact_map,
                       double* out_w);
 
+/* 8f row 4: linear_mutual_information_analysis(cov, ...) -- adjacency_matrix_functions.py:62-103.
+ * cov [3N][3N] -> out_mi [N][N] (+inf on the diagonal). */
+int wisp_lmi_from_covariance(wisp_ctx* ctx, const double* cov, int N, double* out_mi);
+/* generalized_correlation_coefficient_calc(MI, ..., contact_map, Lambda) --
+ * functionalize_adj_matrix_functions.py:27-46.  contact_map may be NULL; the damping is applied
+ * only when both contact_map and has_lambda are given.  out_rmi / out_func [N][N] (either may be NULL). */
+int wisp_func_generalized_correlation(wisp_ctx* ctx, const double* mi, int N, const double* contact_map,
+                                      double lambda, int has_lambda, double* out_rmi, double* out_func);
+
 /* Fused a1..a5: coordinates -> node COMs -> centred Gram + mean distances -> correlation,
  * contact maps, cost matrix, with the node trajectory never leaving the device.
  * which_map: 0 none, 1 binary, 2 average-distance (wisp_w_mdanalysis.py:98-101,141-144).

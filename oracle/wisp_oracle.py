@@ -30,6 +30,7 @@ __all__ = [
     "graph_edges", "dijkstra", "dijkstra_path", "apsp_floyd_warshall", "apsp_dijkstra",
     "get_paths", "get_paths_pruned", "enumerate_paths_literal", "enumerate_paths_pruned",
     "lr_length", "dedupe_paths",
+    "linear_mutual_information_analysis", "generalized_correlation_coefficient_calc",
 ]
 
 
@@ -602,3 +603,35 @@ def get_paths_pruned(adjacency_matrix, sources, sinks, number_of_paths, node0_qu
     if num_paths != number_of_paths:
         paths = paths[:number_of_paths]
     return paths
+
+
+# ----------------------------------------------------------------------------------------
+# linear mutual information adjacency and its functionalisation
+# ----------------------------------------------------------------------------------------
+def linear_mutual_information_analysis(cartesian_covariance_matrix):
+    """adjacency_matrix_functions.py:62-103 literal: MI_ij = 0.5 ln(det C_ii det C_jj /
+    det C_(ij)) with C_(ij) the 6x6 covariance of the two nodes; +inf on the diagonal."""
+    C = np.asarray(cartesian_covariance_matrix, dtype=np.float64)
+    nNodes = C.shape[0] // 3
+    MI = np.zeros((nNodes, nNodes), dtype=np.float64)
+    for i in range(nNodes - 1):
+        iIndex = i * 3
+        iIndex3 = iIndex + 3
+        for j in range(i + 1, nNodes):
+            jIndex = j * 3
+            jIndex3 = jIndex + 3
+            temp = np.linalg.det(C[iIndex:iIndex3, iIndex:iIndex3]) * np.linalg.det(C[jIndex:jIndex3, jIndex:jIndex3])
+            idx = np.append(np.arange(iIndex, iIndex3, 1), np.arange(jIndex, jIndex3, 1))
+            MI[i, j] = MI[j, i] = 0.5 * np.log(temp / np.linalg.det(C[np.ix_(idx, idx)]))   # :87
+    MI += np.diagflat(np.full(nNodes, np.inf))                                               # :89
+    return MI
+
+
+def generalized_correlation_coefficient_calc(adjacency_matrix, contact_map=None, Lambda=None):
+    """functionalize_adj_matrix_functions.py:27-46: r_MI = sqrt(1 - exp(-2 MI / 3)),
+    optionally damped by exp(-d_ij / Lambda); returns (r_MI, -log r_MI)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rMI = np.sqrt(1.0 - np.exp(-2.0 * np.asarray(adjacency_matrix, dtype=np.float64) / 3))   # :34
+        if contact_map is not None and Lambda is not None:
+            rMI = rMI * np.exp(-np.asarray(contact_map, dtype=np.float64) / Lambda)               # :38-40
+        return rMI, -np.log(rMI)                                                                  # :42

@@ -205,6 +205,14 @@ def golden_trajectory(tag, n_nodes, n_frames, apn, seed, cutoff, rigid_motion):
     w_plain = quiet(fun_mod.func_pearson_correlation, corr, out)
     w_binary = quiet(fun_mod.func_pearson_correlation, corr, out, contact_map=binary)
     w_avg = quiet(fun_mod.func_pearson_correlation, corr, out, contact_map=avgdist)
+    # linear mutual information style
+    mi = quiet(adj_mod.linear_mutual_information_analysis, cov, avg, out)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        func_mi = quiet(fun_mod.generalized_correlation_coefficient_calc, mi, out)
+        rmi = np.loadtxt(out + "gen_corr_coefficients.dat")
+        func_mi_damped = quiet(fun_mod.generalized_correlation_coefficient_calc, mi, out,
+                               contact_map=avgdist, Lambda=5.0)
+        rmi_damped = np.loadtxt(out + "gen_corr_coefficients.dat")
     node_ptr = np.array([0] + list(np.cumsum([len(s.indices) for s in selection_list])), dtype=np.int32)
     atom_idx = np.concatenate([s.indices for s in selection_list]).astype(np.int32)
     align_idx = u.select_atoms("protein and name CA").indices.astype(np.int32)
@@ -213,7 +221,8 @@ def golden_trajectory(tag, n_nodes, n_frames, apn, seed, cutoff, rigid_motion):
         coords=coords_in, masses=system.masses, node_ptr=node_ptr, atom_idx=atom_idx,
         align_idx=align_idx, com_only=com_only, com_avg=com_avg, node_traj=node_traj, avg=avg, cov=cov, binary=binary,
         avgdist=avgdist, corr=corr, var=var, ncov=ncov, w_plain=w_plain, w_binary=w_binary,
-        w_avg=w_avg, cutoff=np.float64(cutoff), sources=np.array(src), sinks=np.array(snk))
+        w_avg=w_avg, mi=mi, func_mi=func_mi, rmi=rmi, func_mi_damped=func_mi_damped,
+        rmi_damped=rmi_damped, cutoff=np.float64(cutoff), sources=np.array(src), sinks=np.array(snk))
     print(tag, "nodes", n_nodes, "frames", n_frames, "contacts", int(binary.sum()) // 2)
 
 

@@ -419,3 +419,20 @@ def test_apsp_fp32_dense_predecessors(ctx):
     np.testing.assert_allclose(dist[ii, pp] + W[pp, jj], dist[ii, jj], rtol=2e-5, atol=1e-12)
     off = ~np.eye(150, dtype=bool)
     assert np.all(pred[off] >= 0) and np.all(np.diagonal(pred) == -1)
+
+
+@pytest.mark.parametrize("tag", ["traj_small", "traj_aligned"])
+def test_golden_lmi(ctx, golden_dir, tag):
+    """SURVEY 8f row 4 against the reference's own LMI output."""
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    mi = ctx.lmi_from_covariance(g["cov"])
+    assert np.all(np.isinf(np.diagonal(mi))) and np.array_equal(mi, mi.T)
+    off = ~np.eye(mi.shape[0], dtype=bool)
+    np.testing.assert_allclose(mi[off], g["mi"][off], rtol=1e-9, atol=1e-12)
+    rmi, func = ctx.func_generalized_correlation(g["mi"])
+    np.testing.assert_allclose(rmi, g["rmi"], rtol=1e-12)
+    np.testing.assert_allclose(func[off], g["func_mi"][off], rtol=1e-11, atol=1e-15)
+    assert np.all(np.diagonal(func) == 0.0)
+    rmi_d, func_d = ctx.func_generalized_correlation(g["mi"], g["avgdist"], 5.0)
+    np.testing.assert_allclose(rmi_d, g["rmi_damped"], rtol=1e-12)
+    np.testing.assert_allclose(func_d[off], g["func_mi_damped"][off], rtol=1e-11, atol=1e-15)

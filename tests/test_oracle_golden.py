@@ -84,3 +84,15 @@ def test_com_extraction_golden(golden_dir):
         np.testing.assert_allclose(nodes, g["com_only"], rtol=0, atol=1e-13)
         np.testing.assert_allclose(nodes.sum(axis=0) / nodes.shape[0], g["com_avg"], rtol=0,
                                    atol=1e-13)
+
+
+@pytest.mark.parametrize("tag", ["traj_small", "traj_aligned"])
+def test_lmi_golden(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    mi = oracle.linear_mutual_information_analysis(g["cov"])
+    assert np.array_equal(mi, g["mi"])
+    rmi, func = oracle.generalized_correlation_coefficient_calc(g["mi"])
+    assert np.array_equal(rmi, g["rmi"]) and np.array_equal(func, g["func_mi"])
+    rmi_d, func_d = oracle.generalized_correlation_coefficient_calc(g["mi"], g["avgdist"], 5.0)
+    np.testing.assert_allclose(rmi_d, g["rmi_damped"], rtol=1e-15)
+    np.testing.assert_allclose(func_d, g["func_mi_damped"], rtol=1e-13)

@@ -37,6 +37,8 @@ SIGNATURES = {
     "wisp_pearson_from_covariance": (_int, [_c_ctx, _P, _int, _P, _P, _P]),
     "wisp_contact_map": (_int, [_c_ctx, _P, _i64, _int, _dbl, _P, _P]),
     "wisp_func_pearson": (_int, [_c_ctx, _P, _int, _P, _P]),
+    "wisp_lmi_from_covariance": (_int, [_c_ctx, _P, _int, _P]),
+    "wisp_func_generalized_correlation": (_int, [_c_ctx, _P, _int, _P, _dbl, _int, _P, _P]),
     "wisp_pipeline": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P, _int, _P, _int, _int, _dbl, _int,
                              _P, _P, _P, _P, _P, _P]),
     "wisp_apsp": (_int, [_c_ctx, _P, _int, _int, _P, _P]),
@@ -217,6 +219,27 @@ class Context:
         w = np.empty((N, N), dtype=np.float64)
         self._check(self._lib.wisp_func_pearson(self._ctx, _ptr(corr), N, _ptr(cm), _ptr(w)))
         return w
+
+    def lmi_from_covariance(self, cov):
+        cov = _arr(cov, np.float64, "cartesian_covariance_matrix")
+        n3 = cov.shape[0]
+        if cov.ndim != 2 or cov.shape[1] != n3 or n3 % 3:
+            raise ValueError("covariance must be (3N, 3N), got %s" % (cov.shape,))
+        N = n3 // 3
+        mi = np.empty((N, N))
+        self._check(self._lib.wisp_lmi_from_covariance(self._ctx, _ptr(cov), N, _ptr(mi)))
+        return mi
+
+    def func_generalized_correlation(self, mi, contact_map=None, Lambda=None):
+        mi = _arr(mi, np.float64, "adjacency_matrix")
+        N = mi.shape[0]
+        cm = None if contact_map is None else _arr(contact_map, np.float64, "contact_map", (N, N))
+        rmi = np.empty((N, N))
+        func = np.empty((N, N))
+        self._check(self._lib.wisp_func_generalized_correlation(
+            self._ctx, _ptr(mi), N, _ptr(cm), float(Lambda) if Lambda is not None else 0.0,
+            int(Lambda is not None), _ptr(rmi), _ptr(func)))
+        return rmi, func
 
     def pipeline(self, coords, masses, node_ptr, atom_idx, align_idx, cutoff=9999.0,
                  which_map=0, atomic=False, want_nodes=False):

@@ -1,6 +1,6 @@
 """Drop-in replacement for the Pearson part of the reference's
-``adjacency_matrix_functions.py`` (config key ``adjacency_matrix_functions_file``).  The LMI
-and hENM styles are out of scope of the accelerated path."""
+``adjacency_matrix_functions.py`` (config key ``adjacency_matrix_functions_file``).  The hENM
+style is out of scope (it does not run in the reference either)."""
 from wisp_mdanalysis_implementation_b200 import _lib, textio
 
 
@@ -24,5 +24,16 @@ def pearson_correlation_analysis(cartesian_covariance_matrix, average_node_posit
     return node_correlation
 
 
-def linear_mutual_information_analysis(*args, **kwargs):
-    raise NotImplementedError("LMI adjacency is outside the B200 hot path (SURVEY.md 8f row 4)")
+def linear_mutual_information_analysis(cartesian_covariance_matrix, average_node_positions=None,
+                                       output_directory=None, distance_cutoff=9999., threshold=1e-4,
+                                       max_iterations=100, guess=None, alpha=0.1):
+    """adjacency_matrix_functions.py:62-103: linear mutual information from
+    the 3x3 / 6x6 covariance determinants of every node pair, +inf on the diagonal."""
+    if output_directory is None and isinstance(average_node_positions, str):
+        output_directory, average_node_positions = average_node_positions, None
+    ctx = _lib.default_context()
+    MI = ctx.lmi_from_covariance(cartesian_covariance_matrix)
+    print('LMI has been calculated from the cartesian covariance.')
+    if output_directory is not None:
+        textio.savetxt(output_directory + 'linear_mutual_information.dat', MI)
+    return MI
