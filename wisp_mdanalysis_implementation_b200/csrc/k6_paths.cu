@@ -14,8 +14,8 @@
 // distance-to-sink bound.  Here each pass is two kernels over the APSP result of K5:
 //   expand_level_kernel  level-synchronous expansion of the first few hops (one thread per
 //                        partial path) until there are enough independent prefixes;
-//   dfs_kernel           one thread per prefix runs an explicit-stack DFS pruned by the
-//                        admissible bound  len + w(u,v) + dist(v, sink) <= cutoff (1 + 1e-9),
+//   dfs_warp_kernel      one WARP per prefix runs an explicit-stack DFS (32 edges examined per
+//                        step, ballot-compacted pushes) pruned by the admissible bound  len + w(u,v) + dist(v, sink) <= cutoff (1 + 1e-9),
 //                        with the exact float64 LR length for the final `<= cutoff` test.
 // Paths are emitted through atomically reserved slots; the host sorts, so the result does
 // not depend on emission order.
@@ -27,7 +27,7 @@
 namespace {
 
 constexpr int kMaxLen = 96;          // longest path (nodes) the enumerator supports
-constexpr int kTargetPrefixes = 16384;
+constexpr int kTargetPrefixes = 4096;
 constexpr int kMaxExpandLevels = 8;
 
 struct EnumParams {
@@ -114,50 +114,121 @@ __global__ void expand_level_kernel(EnumParams P, const double* __restrict__ fin
     atomicAdd(P.expansions, nexp);
 }
 
-__global__ void dfs_kernel(EnumParams P, const double* __restrict__ f_len,
-                           const int32_t* __restrict__ f_meta, const int32_t* __restrict__ f_nodes,
-                           int n_in) {
-    const int rec = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per prefix: depth-first search with an explicit stack of pending children in global
+// memory (16 bytes per entry, coalesced pushes).  Popping an entry makes it the path tip at
+// its depth (the prefix below it is still valid: deeper entries are popped first); its
+// adjacency list is then examined 32 edges at a time -- coalesced loads of (neighbour, weight),
+// a gather of dist(v, sink), the on-path test against the warp's path in shared memory, the
+// admissible bound -- survivors are pushed with one ballot-compacted store, sink hits are
+// emitted with warp-aggregated slot reservation.
+struct StackEntry {
+    int32_t node, depth;
+    double len;
+};
+
+constexpr int kDfsWarps = 4;      // warps per block
+
+__global__ void __launch_bounds__(kDfsWarps * 32)
+dfs_warp_kernel(EnumParams P, const double* __restrict__ f_len, const int32_t* __restrict__ f_meta,
+                const int32_t* __restrict__ f_nodes, int n_in, StackEntry* __restrict__ stacks,
+                int cap_stack) {
+    __shared__ int32_t spath[kDfsWarps][kMaxLen];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int rec = blockIdx.x * kDfsWarps + wib;
     if (rec >= n_in) return;
+    const unsigned FULL = 0xffffffffu;
     const int pair = f_meta[2 * rec], d0 = f_meta[2 * rec + 1];
     const int s = P.pairs[2 * pair], t = P.pairs[2 * pair + 1];
     const double* dt = P.dist + (size_t)t * P.N;
-    int32_t nodes[kMaxLen];
-    int32_t cur[kMaxLen];
-    double lens[kMaxLen];
-    for (int k = 0; k < d0; ++k) nodes[k] = f_nodes[(size_t)rec * kMaxLen + k];
-    lens[d0 - 1] = f_len[rec];
-    cur[d0 - 1] = P.adj_ptr[nodes[d0 - 1]];
-    int depth = d0;
+    int32_t* path = spath[wib];
+    for (int k = lane; k < d0; k += 32) path[k] = f_nodes[(size_t)rec * kMaxLen + k];
+    StackEntry* stack = stacks + (size_t)rec * cap_stack;
+    int sp = 0;
+    if (lane == 0) { stack[0].node = f_nodes[(size_t)rec * kMaxLen + d0 - 1]; stack[0].depth = d0 - 1; stack[0].len = f_len[rec]; }
+    sp = 1;
+    __syncwarp();
     unsigned long long nexp = 0;
     unsigned it = 0;
-    while (depth >= d0) {
-        if (P.count_only && (++it & 63u) == 0 &&
-            *reinterpret_cast<volatile int32_t*>(P.out_count) > P.cap) break;
-        const int u = nodes[depth - 1];
-        const int e = cur[depth - 1];
-        if (e >= P.adj_ptr[u + 1]) { --depth; continue; }
-        cur[depth - 1] = e + 1;
-        const int v = P.adj_idx[e];
-        bool on = false;
-        for (int k = 0; k < depth; ++k) on |= (nodes[k] == v);
-        if (on) continue;
-        if (P.quirk && depth == 1 && v == 0 && s != 0) continue;
-        const double nl = lens[depth - 1] + P.adj_w[e];
-        ++nexp;
-        if (!(nl + dt[v] <= P.bound)) continue;
-        if (v == t) {
-            if (nl <= P.cutoff) emit_path(P, pair, nodes, depth, v, nl);
-            continue;
+    while (sp > 0) {
+        if (P.count_only && (++it & 15u) == 0) {
+            int c = 0;
+            if (lane == 0) c = *reinterpret_cast<volatile int32_t*>(P.out_count);
+            c = __shfl_sync(FULL, c, 0);
+            if (c > P.cap) break;
         }
-        if (nl > P.cutoff) continue;
-        if (depth + 1 >= kMaxLen) { atomicOr(&P.out_count[2], 2); continue; }
-        nodes[depth] = v;
-        lens[depth] = nl;
-        cur[depth] = P.adj_ptr[v];
-        ++depth;
+        --sp;
+        const StackEntry top = stack[sp];          // same address for all lanes: broadcast
+        const int u = top.node, depth = top.depth + 1;   // path has `depth` nodes once u is placed
+        if (lane == 0) path[depth - 1] = u;
+        __syncwarp();
+        const int e_end = P.adj_ptr[u + 1];
+        for (int e0 = P.adj_ptr[u]; e0 < e_end; e0 += 32) {
+            const int e = e0 + lane;
+            bool ok = e < e_end;
+            int v = -1;
+            double nl = 0.0;
+            if (ok) {
+                v = P.adj_idx[e];
+                nl = top.len + P.adj_w[e];
+            }
+            if (ok) {
+                for (int k = 0; k < depth; ++k) ok &= (path[k] != v);
+            }
+            if (ok && P.quirk && depth == 1 && v == 0 && s != 0) ok = false;
+            nexp += ok ? 1 : 0;
+            if (ok) ok = (nl + dt[v] <= P.bound);
+            const bool hit = ok && v == t && nl <= P.cutoff;
+            const bool cont = ok && v != t && nl <= P.cutoff;
+            // ---- sink hits ----
+            const unsigned hmask = __ballot_sync(FULL, hit);
+            if (hmask) {
+                const int nh = __popc(hmask);
+                int slot0 = 0, off0 = 0;
+                if (lane == 0) {
+                    slot0 = atomicAdd(&P.out_count[0], nh);
+                    if (!P.count_only) off0 = atomicAdd(&P.out_count[1], nh * (depth + 1));
+                }
+                slot0 = __shfl_sync(FULL, slot0, 0);
+                off0 = __shfl_sync(FULL, off0, 0);
+                if (hit && !P.count_only) {
+                    const int r = __popc(hmask & ((1u << lane) - 1));
+                    const int slot = slot0 + r, off = off0 + r * (depth + 1);
+                    if (slot >= P.cap_paths || off + depth + 1 > P.cap_nodes) {
+                        atomicOr(&P.out_count[2], 1);
+                    } else {
+                        P.out_len[slot] = nl;
+                        P.out_pair[slot] = pair;
+                        P.out_off[slot] = off;
+                        P.out_n[slot] = depth + 1;
+                        for (int k = 0; k < depth; ++k) P.out_nodes[off + k] = path[k];
+                        P.out_nodes[off + depth] = v;
+                    }
+                }
+            }
+            // ---- push survivors ----
+            const unsigned cmask = __ballot_sync(FULL, cont);
+            if (cmask) {
+                const int nc = __popc(cmask);
+                if (depth + 1 >= kMaxLen) { if (lane == 0) atomicOr(&P.out_count[2], 2); }
+                else if (sp + nc > cap_stack) { if (lane == 0) atomicOr(&P.out_count[2], 8); }
+                else {
+                    if (cont) {
+                        const int r = __popc(cmask & ((1u << lane) - 1));
+                        StackEntry en;
+                        en.node = v; en.depth = depth; en.len = nl;
+                        stack[sp + r] = en;
+                    }
+                    sp += nc;
+                }
+            }
+        }
+        __syncwarp();
     }
-    atomicAdd(P.expansions, nexp);
+    if (lane == 0) atomicAdd(P.expansions, nexp);
+    // lanes other than 0 counted their own edges too
+    nexp = (lane == 0) ? 0 : nexp;
+    for (int o = 16; o > 0; o >>= 1) nexp += __shfl_xor_sync(FULL, nexp, o);
+    if (lane == 0) atomicAdd(P.expansions, nexp);
 }
 
 struct HostPath {
@@ -337,7 +408,8 @@ extern "C" int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sou
     WISP_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
 
     int cap_paths = std::max(4096, 8 * number_of_paths * std::max(1, n_pairs));
-    int cap_front = std::max(4 * kTargetPrefixes, 4 * n_pairs);
+    int cap_front = std::max(16 * kTargetPrefixes, 4 * n_pairs);
+    int cap_stack = 1024;
     double enum_ms = 0.0, host_ms = 0.0;
     unsigned long long expansions_total = 0;
     int passes = 0;
@@ -407,7 +479,10 @@ extern "C" int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sou
                 if (count_only && hc[0] > cap) { n_front = 0; break; }
             }
             if (!overflow && n_front > 0) {
-                dfs_kernel<<<(n_front + 63) / 64, 64, 0, st>>>(P, f_len[cur], f_meta[cur], f_nodes[cur], n_front);
+                void* d_stack = nullptr;
+                WISP_TRY(wisp_scratch(ctx, SCR_MISC0, (size_t)n_front * cap_stack * sizeof(StackEntry) + 256, &d_stack));
+                dfs_warp_kernel<<<(n_front + kDfsWarps - 1) / kDfsWarps, kDfsWarps * 32, 0, st>>>(
+                    P, f_len[cur], f_meta[cur], f_nodes[cur], n_front, (StackEntry*)d_stack, cap_stack);
                 ctx->launches++;
             }
             unsigned long long hexp = 0;
@@ -418,6 +493,7 @@ extern "C" int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sou
                 WISP_CUDA(cudaGetLastError());
                 WISP_CHECK(!(hc[2] & 2), "get_paths: a path exceeded the supported length of %d nodes", kMaxLen);
                 if (hc[2] & 1) { overflow = true; cap_paths = std::max(cap_paths * 4, hc[0] + 1024); }
+                if (hc[2] & 8) { overflow = true; cap_stack *= 4; }
             }
             if (overflow) continue;
             expansions_total += hexp;
