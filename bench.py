@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-paths", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-mode", default="streamed", choices=["streamed", "two-pass"])
     ap.add_argument("--stress-pairs", type=int, default=200)
     ap.add_argument("--stress-paths", type=int, default=1000)
     ap.add_argument("--apsp-nodes", type=int, default=10000, help="configs[2] APSP size (0 = skip)")
@@ -358,14 +359,15 @@ def main():
         h_coords = torch.empty((T_local, A, 3), dtype=torch.float32, pin_memory=True)
         h_coords.copy_(d_coords)
         torch.cuda.synchronize()
+        run_e2e = pipe.run_host_streamed if args.e2e_mode == "streamed" else pipe.run_host
         for _ in range(max(1, args.warmup - 1)):
-            pipe.run_host(h_coords)
+            run_e2e(h_coords)
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         a.record()
         for _ in range(args.steps):
-            res = pipe.run_host(h_coords)
+            res = run_e2e(h_coords)
         b.record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
@@ -373,8 +375,8 @@ def main():
         e2e = {"value": float(N) * N * T / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                "wall_ms_per_step": wall_ms, "h2d_bytes_per_step": pipe.h2d_bytes() * world,
                "d2h_bytes_per_step": pipe.d2h_bytes(),
-               "api": "FramePipeline.run_host (C-ABI wisp_dev_* calls; pinned host coords in, "
-                      "corr/avgdist/binary/w on the host out)"}
+               "api": "FramePipeline.%s (C-ABI wisp_dev_* calls; pinned host coords in, "
+                      "corr/avgdist/binary/w on the host out)" % run_e2e.__name__}
         del h_coords
 
     # ---- APSP + 500 suboptimal paths on the resulting cost matrix (rank 0) ----

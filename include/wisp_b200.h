@@ -176,11 +176,16 @@ int wisp_dev_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N,
                          const double* d_mean, double* d_out, void* stream);
 /* K4: fused epilogue on (all-reduced) sums.  d_gram / d_dsum are [Npad][Npad] upper-tile
  * sums over T_total frames.  Outputs (each may be NULL) are dense [N][N]:
- * corr, ncov (=G/T), avgdist, binary (int64), w (= -log|corr| (.) map). d_var [N]. */
+ * corr, ncov (=G/T), avgdist, binary (int64), w (= -log|corr| (.) map). d_var [N].
+ * d_offset_sum (may be NULL): column sums [3N] of a trajectory centred with a provisional
+ * reference instead of its mean; G is then re-centred exactly, G_ij -= (s_i . s_j)/T. */
 int wisp_dev_epilogue(wisp_ctx* ctx, const double* d_gram, const double* d_dsum,
                       int64_t T_total, int N, double cutoff, int which_map, double* d_var,
                       double* d_ncov, double* d_corr, double* d_avgdist, int64_t* d_binary,
-                      double* d_w, void* stream);
+                      double* d_w, const double* d_offset_sum, void* stream);
+/* out = sum over n_parts partial [Npad][Npad] matrices (upper 128-tiles, fixed order). */
+int wisp_dev_reduce_partials(wisp_ctx* ctx, const double* d_parts, int n_parts, int N,
+                             double* d_out, void* stream);
 /* K5 on device: d_w [N][N] cost matrix -> d_dist (float64 [N][N]) and d_pred (int32). */
 int wisp_dev_apsp(wisp_ctx* ctx, const double* d_w, int N, int precision, double* d_dist,
                   int32_t* d_pred, void* stream);

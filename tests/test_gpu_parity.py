@@ -391,6 +391,13 @@ def test_frame_pipeline_matches_c_abi_pipeline(ctx):
     out = pipe.run_host(h)
     np.testing.assert_allclose(out["corr"], ref["corr"], rtol=0, atol=1e-13)
     np.testing.assert_allclose(out["w"], ref["w"], rtol=1e-12, atol=1e-300)
+    # streamed mode: blocks centred with a provisional reference + parallel-axis correction
+    out = pipe.run_host_streamed(h, n_blocks=5)
+    assert_corr_close(out["corr"], ref["corr"], rel=1e-9, floor=1e-3)
+    assert np.all(np.diagonal(out["corr"]) == 1.0)
+    np.testing.assert_allclose(out["avgdist"], ref["avgdist"], rtol=1e-6)
+    assert np.array_equal(out["binary"], ref["binary"])
+    np.testing.assert_allclose(pipe.d_mean.cpu().numpy()[:900], ref["avg"].reshape(-1), rtol=0, atol=1e-11)
 
 
 def test_paths_prepare_query_stress(ctx):

@@ -59,7 +59,8 @@ SIGNATURES = {
     "wisp_dev_colsum": (_int, [_c_ctx, _P, _i64, _int, _P, _P]),
     "wisp_dev_gram": (_int, [_c_ctx, _P, _i64, _i64, _int, _int, _P, _P]),
     "wisp_dev_contact_sum": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P]),
-    "wisp_dev_epilogue": (_int, [_c_ctx, _P, _P, _i64, _int, _dbl, _int, _P, _P, _P, _P, _P, _P, _P]),
+    "wisp_dev_epilogue": (_int, [_c_ctx, _P, _P, _i64, _int, _dbl, _int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "wisp_dev_reduce_partials": (_int, [_c_ctx, _P, _int, _int, _P, _P]),
     "wisp_dev_apsp": (_int, [_c_ctx, _P, _int, _int, _P, _P, _P]),
     "wisp_dev_synth_coords": (_int, [_c_ctx, _P, _i64, _i64, _int, _P, _P, _P, _int, _P, _dbl,
                                      C.c_uint64, _P]),
@@ -350,11 +351,17 @@ class Context:
                                                    _ptr(d_out), _ptr(stream)))
 
     def dev_epilogue(self, d_gram, d_dsum, T_total, N, cutoff, which_map, d_var=None, d_ncov=None,
-                     d_corr=None, d_avgdist=None, d_binary=None, d_w=None, stream=None):
+                     d_corr=None, d_avgdist=None, d_binary=None, d_w=None, d_offset_sum=None,
+                     stream=None):
         self._check(self._lib.wisp_dev_epilogue(self._ctx, _ptr(d_gram), _ptr(d_dsum), T_total, N,
                                                 float(cutoff), int(which_map), _ptr(d_var),
                                                 _ptr(d_ncov), _ptr(d_corr), _ptr(d_avgdist),
-                                                _ptr(d_binary), _ptr(d_w), _ptr(stream)))
+                                                _ptr(d_binary), _ptr(d_w), _ptr(d_offset_sum),
+                                                _ptr(stream)))
+
+    def dev_reduce_partials(self, d_parts, n_parts, N, d_out, stream=None):
+        self._check(self._lib.wisp_dev_reduce_partials(self._ctx, _ptr(d_parts), n_parts, N,
+                                                       _ptr(d_out), _ptr(stream)))
 
     def dev_apsp(self, d_w, N, precision, d_dist, d_pred, stream=None):
         self._check(self._lib.wisp_dev_apsp(self._ctx, _ptr(d_w), N, int(precision), _ptr(d_dist),

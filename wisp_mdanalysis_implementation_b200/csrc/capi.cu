@@ -534,10 +534,17 @@ extern "C" int wisp_dev_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T
 extern "C" int wisp_dev_epilogue(wisp_ctx* ctx, const double* d_gram, const double* d_dsum,
                                  int64_t T_total, int N, double cutoff, int which_map, double* d_var,
                                  double* d_ncov, double* d_corr, double* d_avgdist, int64_t* d_binary,
-                                 double* d_w, void* stream) {
+                                 double* d_w, const double* d_offset_sum, void* stream) {
     WISP_CHECK(ctx, "dev_epilogue: null context");
     return launch_epilogue(ctx, d_gram, d_dsum, T_total, N, cutoff, which_map, d_var, d_ncov, d_corr,
-                           d_avgdist, d_binary, d_w, wisp_stream(ctx, stream));
+                           d_avgdist, d_binary, d_w, wisp_stream(ctx, stream), d_offset_sum);
+}
+
+extern "C" int wisp_dev_reduce_partials(wisp_ctx* ctx, const double* d_parts, int n_parts, int N,
+                                        double* d_out, void* stream) {
+    WISP_CHECK(ctx && d_parts && d_out && n_parts > 0, "dev_reduce_partials: bad argument");
+    return launch_reduce_partials(ctx, d_parts, n_parts, round_up(N, kTile), d_out, kTile, kTile,
+                                  wisp_stream(ctx, stream));
 }
 
 extern "C" int wisp_dev_apsp(wisp_ctx* ctx, const double* d_w, int N, int precision, double* d_dist,

@@ -118,7 +118,7 @@ int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, cons
 int launch_epilogue(wisp_ctx* ctx, const double* d_gram, const double* d_dsum, int64_t T_total,
                     int N, double cutoff, int which_map, double* d_var, double* d_ncov,
                     double* d_corr, double* d_avgdist, int64_t* d_binary, double* d_w,
-                    cudaStream_t st);
+                    cudaStream_t st, const double* d_offs = nullptr);
 int launch_cov_finalize(wisp_ctx* ctx, const double* d_p, int64_t ldp, int n3, int64_t T,
                         const double* d_avg, const double* d_delta, double* d_cov,
                         cudaStream_t st);

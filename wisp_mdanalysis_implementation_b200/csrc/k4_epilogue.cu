@@ -17,7 +17,21 @@
 
 namespace {
 
+// offs (may be NULL): column sums s = sum_t (x - r) of a trajectory that was centred with a
+// provisional reference r instead of its mean; the Gram sums are then re-centred exactly with
+// the parallel-axis term  G_ij -= (s_i . s_j) / T.
+__device__ __forceinline__ double gram_entry(const double* __restrict__ gram, const double* __restrict__ offs,
+                                             int64_t n_pad, int i, int j, double Td) {
+    double g = gram[(int64_t)i * n_pad + j];
+    if (offs) {
+        const double dot = (offs[3 * i] * offs[3 * j] + offs[3 * i + 1] * offs[3 * j + 1]) + offs[3 * i + 2] * offs[3 * j + 2];
+        g -= dot / Td;
+    }
+    return g / Td;
+}
+
 __global__ void epilogue_kernel(const double* __restrict__ gram, const double* __restrict__ dsum,
+                                const double* __restrict__ offs,
                                 int64_t n_pad, int64_t T, int N, double cutoff, int which_map,
                                 double* __restrict__ var, double* __restrict__ ncov,
                                 double* __restrict__ corr, double* __restrict__ avgdist,
@@ -30,9 +44,9 @@ __global__ void epilogue_kernel(const double* __restrict__ gram, const double* _
         const int i = r < c ? r : c, j = r < c ? c : r;
         double cij = 0.0;
         if (gram) {
-            const double g = gram[(int64_t)i * n_pad + j] / Td;
-            const double vi = gram[(int64_t)i * n_pad + i] / Td;
-            const double vj = gram[(int64_t)j * n_pad + j] / Td;
+            const double g = gram_entry(gram, offs, n_pad, i, j, Td);
+            const double vi = gram_entry(gram, offs, n_pad, i, i, Td);
+            const double vj = gram_entry(gram, offs, n_pad, j, j, Td);
             cij = g / sqrt(vi * vj);
             if (ncov) ncov[e] = g;
             if (corr) corr[e] = cij;
@@ -109,12 +123,12 @@ inline int grid_for(wisp_ctx* ctx, int64_t total) {
 int launch_epilogue(wisp_ctx* ctx, const double* d_gram, const double* d_dsum, int64_t T_total,
                     int N, double cutoff, int which_map, double* d_var, double* d_ncov,
                     double* d_corr, double* d_avgdist, int64_t* d_binary, double* d_w,
-                    cudaStream_t st) {
+                    cudaStream_t st, const double* d_offs) {
     WISP_CHECK(N > 0 && T_total > 0, "epilogue: empty input");
     WISP_CHECK(which_map == 0 || d_dsum, "epilogue: contact-map weighting needs distance sums");
     const int64_t n_pad = round_up(N, kTile);
     epilogue_kernel<<<grid_for(ctx, (int64_t)N * N), 256, 0, st>>>(
-        d_gram, d_dsum, n_pad, T_total, N, cutoff, which_map, d_var, d_ncov, d_corr, d_avgdist,
+        d_gram, d_dsum, d_offs, n_pad, T_total, N, cutoff, which_map, d_var, d_ncov, d_corr, d_avgdist,
         d_binary, d_w);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());

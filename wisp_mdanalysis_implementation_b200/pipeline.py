@@ -38,7 +38,15 @@ class FramePipeline:
         self.d_p32 = torch.zeros((self.T, self.npad // 128, 3, 128), dtype=torch.float32, device=dev)
         self.d_colsum = torch.zeros(self.ld, dtype=f64, device=dev)
         self.d_mean = torch.zeros(self.ld, dtype=f64, device=dev)
-        self.d_sums = torch.zeros((2, self.npad, self.npad), dtype=f64, device=dev)   # [G || D]
+        # ONE contiguous buffer [G || D || s]: Gram sums, distance sums, and (streamed mode) the
+        # column sums of the provisionally centred trajectory -> one all-reduce
+        nn = self.npad * self.npad
+        self.d_flat = torch.zeros(2 * nn + self.ld, dtype=f64, device=dev)
+        self.d_sums = self.d_flat[:2 * nn].view(2, self.npad, self.npad)
+        self.d_offs = self.d_flat[2 * nn:]
+        self.d_ref = torch.zeros(self.ld, dtype=f64, device=dev)
+        self.d_parts = None
+        self.k23_stream = torch.cuda.Stream(device=dev)
         n = self.N
         self.d_corr = torch.empty((n, n), dtype=f64, device=dev)
         self.d_avgdist = torch.empty((n, n), dtype=f64, device=dev)
@@ -121,6 +129,84 @@ class FramePipeline:
         self.gram()
         self.contact()
         self.reduce_and_epilogue()
+        if fetch:
+            self._h_out[0].copy_(self.d_corr, non_blocking=True)
+            self._h_out[1].copy_(self.d_avgdist, non_blocking=True)
+            self._h_out[2].copy_(self.d_w, non_blocking=True)
+            self._h_out[3].copy_(self.d_binary, non_blocking=True)
+            main.synchronize()
+            return dict(corr=self._h_out[0].numpy(), avgdist=self._h_out[1].numpy(),
+                        w=self._h_out[2].numpy(), binary=self._h_out[3].numpy())
+        return None
+
+    def run_host_streamed(self, h_coords, n_blocks=8, fetch=True):
+        """Like run_host, but the frames are processed in blocks so that K2 / K3 of block b run
+        (on a second stream) while block b+1 is still crossing PCIe.  No pass over the data
+        waits for the global mean: every block is centred with a provisional reference r (the
+        mean of the first block, broadcast from rank 0), and the exact parallel-axis term
+        (s_i . s_j)/T with s = sum_t (x - r) is removed in the epilogue -- so the ranks exchange
+        a SINGLE all-reduce of [G || D || s]."""
+        main = torch.cuda.current_stream(self.dev)
+        side = self.k23_stream
+        if self._stage is None:
+            self._stage = [torch.empty((self.chunk_frames, self.A, 3), dtype=torch.float32,
+                                       device=self.dev) for _ in range(2)]
+            self._h_out = [torch.empty((self.N, self.N), dtype=torch.float64).pin_memory()
+                           for _ in range(3)] + [torch.empty((self.N, self.N), dtype=torch.int64).pin_memory()]
+        block = -(-self.T // n_blocks)
+        block = max(24, -(-block // 24) * 24)
+        starts = list(range(0, self.T, block))
+        if self.d_parts is None or self.d_parts.shape[1] != len(starts):
+            self.d_parts = torch.zeros((2, len(starts), self.npad, self.npad), dtype=torch.float64,
+                                       device=self.dev)
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
+        tile_floats = (self.npad // 128) * 384
+        it = 0
+        for b, f0 in enumerate(starts):
+            f1 = min(self.T, f0 + block)
+            for t0 in range(f0, f1, self.chunk_frames):
+                k = it & 1
+                nt = min(self.chunk_frames, f1 - t0)
+                with torch.cuda.stream(self.copy_stream):
+                    if it >= 2:
+                        self.copy_stream.wait_event(freed[k])
+                    self._stage[k][:nt].copy_(h_coords[t0:t0 + nt], non_blocking=True)
+                    copied[k].record(self.copy_stream)
+                main.wait_event(copied[k])
+                self.com(self._stage[k], frames=nt, row0=t0)
+                freed[k].record(main)
+                it += 1
+            if b == 0:
+                s = self._stream()
+                self.ctx.dev_colsum(self.d_x.data_ptr(), f1 - f0, self.N, self.d_colsum.data_ptr(), stream=s)
+                torch.div(self.d_colsum, float(f1 - f0), out=self.d_ref)
+                if sharding.is_distributed(self.group):
+                    torch.distributed.broadcast(self.d_ref, src=0, group=self.group)
+            done_k1 = torch.cuda.Event()
+            done_k1.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(done_k1)
+                ss = side.cuda_stream or 1
+                nb = f1 - f0
+                self.ctx.dev_center(self.d_x.data_ptr() + f0 * self.ld * 8, nb, self.N, self.d_ref.data_ptr(),
+                                    d_p32=self.d_p32.data_ptr() + f0 * tile_floats * 4, stream=ss)
+                self.ctx.dev_gram(self.d_x.data_ptr() + f0 * self.ld * 8, nb, self.ld, self.N, 3,
+                                  self.d_parts[0, b].data_ptr(), stream=ss)
+                self.ctx.dev_contact_sum(self.d_p32.data_ptr() + f0 * tile_floats * 4, nb, self.N,
+                                         self.d_ref.data_ptr(), self.d_parts[1, b].data_ptr(), stream=ss)
+        main.wait_stream(side)
+        s = self._stream()
+        self.ctx.dev_colsum(self.d_x.data_ptr(), self.T, self.N, self.d_offs.data_ptr(), stream=s)
+        for k in (0, 1):
+            self.ctx.dev_reduce_partials(self.d_parts[k].data_ptr(), len(starts), self.N,
+                                         self.d_sums[k].data_ptr(), stream=s)
+        sharding.reduce_sums(self.d_flat, group=self.group)          # the ONE collective
+        self.ctx.dev_epilogue(self.d_sums[0].data_ptr(), self.d_sums[1].data_ptr(), self.T_total,
+                              self.N, self.cutoff, self.which_map, d_corr=self.d_corr.data_ptr(),
+                              d_avgdist=self.d_avgdist.data_ptr(), d_binary=self.d_binary.data_ptr(),
+                              d_w=self.d_w.data_ptr(), d_offset_sum=self.d_offs.data_ptr(), stream=s)
+        torch.add(self.d_ref, self.d_offs, alpha=1.0 / self.T_total, out=self.d_mean)
         if fetch:
             self._h_out[0].copy_(self.d_corr, non_blocking=True)
             self._h_out[1].copy_(self.d_avgdist, non_blocking=True)
