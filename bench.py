@@ -353,6 +353,16 @@ def main():
                     "traffic": None,
                     "peak_source": "MUFU.SQRT issue peak measured with tools/peaks.cu (1 sqrt per pair-frame)"}
 
+    roofline_tensor = {"kernel": "gram_dmma_kernel<3>", "bound": "tensor", "achieved": k2_tflops,
+                       "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
+                       "frac": k2_tflops / peaks["fp64_dmma_tflops"], "traffic": None}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+        roofline["traffic"] = ncu.get(roofline["kernel"].split("<")[0])
+        roofline_tensor["traffic"] = ncu.get("gram_dmma_kernel")
+    except Exception:
+        pass
+
     # ---- e2e: pinned host coordinates -> results on the host ----
     e2e = None
     if not args.no_e2e:
@@ -484,7 +494,7 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
-                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "extra": extra}
+                "roofline": roofline, "roofline_tensor": roofline_tensor, "kernels": kernels, "cpu_baseline": cpu_baseline, "extra": extra}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
