@@ -443,3 +443,61 @@ def test_golden_lmi(ctx, golden_dir, tag):
     rmi_d, func_d = ctx.func_generalized_correlation(g["mi"], g["avgdist"], 5.0)
     np.testing.assert_allclose(rmi_d, g["rmi_damped"], rtol=1e-12)
     np.testing.assert_allclose(func_d[off], g["func_mi_damped"][off], rtol=1e-11, atol=1e-15)
+
+
+def test_tiny_and_ragged_inputs(ctx):
+    """Smallest legal sizes and sizes that straddle every tile boundary."""
+    from wisp_mdanalysis_implementation_b200 import _lib
+    for n, t, apn in [(1, 1, 1), (2, 3, 1), (3, 2, 2), (127, 23, 1), (129, 25, 2)]:
+        system, coords = synth.synth(n, t, apn, seed=100 + n)
+        out = ctx.pipeline(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx,
+                           cutoff=8.0, which_map=2, want_nodes=True)
+        nodes, _ = oracle.com_nodes(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx)
+        np.testing.assert_allclose(out["nodes"], nodes, rtol=0, atol=1e-11)
+        binary, avgdist = oracle.calc_contact_map_fast(nodes, 8.0)
+        np.testing.assert_allclose(out["avgdist"], avgdist, rtol=1e-6, atol=1e-9)
+        if t > 2:
+            avg = nodes.sum(axis=0) / t
+            _, _, corr = oracle.pearson_correlation_fast(oracle.cartesian_covariance_fast(nodes, avg))
+            ok = np.isfinite(corr)
+            assert_corr_close(out["corr"][ok], corr[ok], rel=1e-6, floor=1e-3)
+    # error paths fail loudly with a message (no silent fallback)
+    system, coords = synth.synth(4, 5, 2, seed=1)
+    with pytest.raises((_lib.WispError, ValueError)):
+        ctx.pipeline(coords, system.masses[:-1], system.node_ptr, system.atom_idx, system.align_idx)
+    with pytest.raises(_lib.WispError):
+        bad_ptr = system.node_ptr.copy(); bad_ptr[2] = bad_ptr[1]          # empty node
+        ctx.com_nodes(coords, system.masses, bad_ptr, system.atom_idx, system.align_idx)
+    with pytest.raises(_lib.WispError):
+        bad_idx = system.atom_idx.copy(); bad_idx[0] = 999                 # atom out of range
+        ctx.com_nodes(coords, system.masses, system.node_ptr, bad_idx, system.align_idx)
+    with pytest.raises(_lib.WispError):
+        W = synth.random_cost_matrix(6, seed=1); W[1, 2] = np.nan
+        ctx.get_paths(W, [0], [5], 2)
+    with pytest.raises(_lib.WispError):
+        ctx.get_paths(synth.random_cost_matrix(6, seed=1), [0], [9], 2)    # sink out of range
+
+
+def test_apsp_fp32_multi_tile_vs_fp64(ctx):
+    """FP32 throughput mode (128-wide rounds, FADD2 + FMNMX3) against the FP64 parity mode on a
+    graph spanning many tiles."""
+    W = synth.random_cost_matrix(1100, seed=9, density=0.02)
+    d64, p64 = ctx.apsp(W, precision=64)
+    d32, p32 = ctx.apsp(W, precision=32)
+    np.testing.assert_allclose(d32, d64, rtol=3e-6)
+    rng = np.random.default_rng(0)
+    i, j, k = rng.integers(0, 1100, size=(3, 5000))
+    assert np.all(d64[i, j] <= d64[i, k] + d64[k, j] + 1e-9)
+    # walking FP32 predecessors reproduces the FP32 distance
+    for s, t in zip(i[:50], j[:50]):
+        if s == t:
+            continue
+        node, length, hops = t, 0.0, 0
+        while node != s:
+            prev = p32[s, node]
+            assert prev >= 0
+            length += W[prev, node]
+            node = prev
+            hops += 1
+            assert hops < 1100
+        assert abs(length - d64[s, t]) <= 1e-4 * max(1.0, d64[s, t])
