@@ -189,6 +189,18 @@ int wisp_dev_reduce_partials(wisp_ctx* ctx, const double* d_parts, int n_parts, 
 /* K5 on device: d_w [N][N] cost matrix -> d_dist (float64 [N][N]) and d_pred (int32). */
 int wisp_dev_apsp(wisp_ctx* ctx, const double* d_w, int N, int precision, double* d_dist,
                   int32_t* d_pred, void* stream);
+/* Row-block sharded FP32 Floyd-Warshall (BASELINE configs[3]): each rank owns whole 128-row tile
+ * rows of the distance matrix, float [rows_pad][wisp_gram_ld(N)].  Per round kb the owner of the
+ * pivot rows copies them into a [128][wisp_gram_ld(N)] panel, finishes it with
+ * wisp_dev_fw32_pivot_panel, the caller broadcasts the panel (NCCL), and every rank applies
+ * wisp_dev_fw32_update_rows to its own rows (skip_local_tile = local tile-row index of the pivot
+ * rows on the owner, -1 elsewhere; the owner copies the panel back into its rows). */
+int wisp_dev_fw32_init_rows(wisp_ctx* ctx, const double* d_w_rows, int N, int64_t row0, int64_t rows_pad,
+                            float* d_dist_local, void* stream);
+int wisp_dev_fw32_pivot_panel(wisp_ctx* ctx, float* d_panel, int N, int kb, void* stream);
+int wisp_dev_fw32_update_rows(wisp_ctx* ctx, float* d_dist_local, int64_t rows_pad, const float* d_panel,
+                              int N, int kb, int skip_local_tile, void* stream);
+
 /* synthetic coordinates generated on the device (bench-scale inputs; synth.py model):
  * atom_base [A][3] f64, node_of_atom [A], modes [N][M][3] f64, coeff [T][M] f64. */
 int wisp_dev_synth_coords(wisp_ctx* ctx, float* d_coords, int64_t t0, int64_t T, int A,

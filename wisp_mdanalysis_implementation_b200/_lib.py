@@ -62,6 +62,9 @@ SIGNATURES = {
     "wisp_dev_epilogue": (_int, [_c_ctx, _P, _P, _i64, _int, _dbl, _int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "wisp_dev_reduce_partials": (_int, [_c_ctx, _P, _int, _int, _P, _P]),
     "wisp_dev_apsp": (_int, [_c_ctx, _P, _int, _int, _P, _P, _P]),
+    "wisp_dev_fw32_init_rows": (_int, [_c_ctx, _P, _int, _i64, _i64, _P, _P]),
+    "wisp_dev_fw32_pivot_panel": (_int, [_c_ctx, _P, _int, _int, _P]),
+    "wisp_dev_fw32_update_rows": (_int, [_c_ctx, _P, _i64, _P, _int, _int, _int, _P]),
     "wisp_dev_synth_coords": (_int, [_c_ctx, _P, _i64, _i64, _int, _P, _P, _P, _int, _P, _dbl,
                                      C.c_uint64, _P]),
 }
@@ -366,6 +369,17 @@ class Context:
     def dev_apsp(self, d_w, N, precision, d_dist, d_pred, stream=None):
         self._check(self._lib.wisp_dev_apsp(self._ctx, _ptr(d_w), N, int(precision), _ptr(d_dist),
                                             _ptr(d_pred), _ptr(stream)))
+
+    def dev_fw32_init_rows(self, d_w_rows, N, row0, rows_pad, d_dist_local, stream=None):
+        self._check(self._lib.wisp_dev_fw32_init_rows(self._ctx, _ptr(d_w_rows), N, row0, rows_pad,
+                                                      _ptr(d_dist_local), _ptr(stream)))
+
+    def dev_fw32_pivot_panel(self, d_panel, N, kb, stream=None):
+        self._check(self._lib.wisp_dev_fw32_pivot_panel(self._ctx, _ptr(d_panel), N, kb, _ptr(stream)))
+
+    def dev_fw32_update_rows(self, d_dist_local, rows_pad, d_panel, N, kb, skip_local_tile, stream=None):
+        self._check(self._lib.wisp_dev_fw32_update_rows(self._ctx, _ptr(d_dist_local), rows_pad,
+                                                        _ptr(d_panel), N, kb, skip_local_tile, _ptr(stream)))
 
     def dev_synth_coords(self, d_coords, t0, T, A, d_atom_base, d_node_of_atom, d_modes, n_modes,
                          d_coeff, noise_sigma, seed, stream=None):

@@ -325,10 +325,11 @@ __global__ void fw32_init_kernel(const double* __restrict__ w, int N, int64_t n_
 // points of iteration k because d[k][k] == 0 and weights are non-negative)
 __global__ void __launch_bounds__(1024)
 fw32_phase1_kernel(float* __restrict__ dist, int64_t ld, int kb) {
+    // `dist` is the pivot ROW PANEL (128 rows x ld): the pivot tile sits at column block kb
     extern __shared__ __align__(16) unsigned char fw_smem[];
     float* d = reinterpret_cast<float*>(fw_smem);     // [128][129]
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // ty 0..31 -> rows 4ty..4ty+3
-    const int64_t base = (int64_t)kb * kT * ld + (int64_t)kb * kT;
+    const int64_t base = (int64_t)kb * kT;
     for (int a = 0; a < 4; ++a)
         for (int b = 0; b < 4; ++b) d[(4 * ty + a) * (kT + 1) + tx + 32 * b] = dist[base + (4 * ty + a) * ld + tx + 32 * b];
     __syncthreads();
@@ -352,24 +353,28 @@ fw32_phase1_kernel(float* __restrict__ dist, int64_t ld, int kb) {
         for (int b = 0; b < 4; ++b) dist[base + (4 * ty + a) * ld + tx + 32 * b] = d[(4 * ty + a) * (kT + 1) + tx + 32 * b];
 }
 
-// phase 2: pivot row tiles (blockIdx.y == 0) and pivot column tiles (blockIdx.y == 1)
+// phase 2: pivot row tiles (blockIdx.y == 0, inside the row panel) and pivot column tiles
+// (blockIdx.y == 1, tile (bi, kb) of the LOCAL row block; local tile-row `skip` holds the pivot
+// rows themselves and is left alone)
 __global__ void __launch_bounds__(1024)
-fw32_phase2_kernel(float* __restrict__ dist, int64_t ld, int kb) {
+fw32_phase2_kernel(float* __restrict__ local, int64_t ld, float* __restrict__ panel, int64_t ldp,
+                   int kb, int n_col_tiles, int n_local_tiles, int skip) {
     const int other = blockIdx.x;
-    if (other == kb) return;
     const bool is_row = blockIdx.y == 0;
+    if (is_row) { if (other >= n_col_tiles || other == kb) return; }
+    else        { if (other >= n_local_tiles || other == skip) return; }
     extern __shared__ __align__(16) unsigned char fw_smem[];
     float* pv = reinterpret_cast<float*>(fw_smem);     // pivot [128][129]
     float* ow = pv + kT * (kT + 1);                    // own   [128][129]
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int64_t pbase = (int64_t)kb * kT * ld + (int64_t)kb * kT;
-    const int64_t obase = is_row ? (int64_t)kb * kT * ld + (int64_t)other * kT
-                                 : (int64_t)other * kT * ld + (int64_t)kb * kT;
+    const float* pbase = panel + (int64_t)kb * kT;
+    float* obase = is_row ? panel + (int64_t)other * kT : local + (int64_t)other * kT * ld + (int64_t)kb * kT;
+    const int64_t ldo = is_row ? ldp : ld;
     for (int a = 0; a < 4; ++a)
         for (int b = 0; b < 4; ++b) {
             const int i = 4 * ty + a, j = tx + 32 * b;
-            pv[i * (kT + 1) + j] = dist[pbase + i * ld + j];
-            ow[i * (kT + 1) + j] = dist[obase + i * ld + j];
+            pv[i * (kT + 1) + j] = pbase[i * ldp + j];
+            ow[i * (kT + 1) + j] = obase[i * ldo + j];
         }
     __syncthreads();
     for (int k = 0; k < kT; ++k) {
@@ -399,15 +404,18 @@ fw32_phase2_kernel(float* __restrict__ dist, int64_t ld, int kb) {
     for (int a = 0; a < 4; ++a)
         for (int b = 0; b < 4; ++b) {
             const int i = 4 * ty + a, j = tx + 32 * b;
-            dist[obase + i * ld + j] = ow[i * (kT + 1) + j];
+            obase[i * ldo + j] = ow[i * (kT + 1) + j];
         }
 }
 
 // phase 3: all tiles outside the pivot row / column
 __global__ void __launch_bounds__(256, 2)
-fw32_phase3_kernel(float* __restrict__ dist, int64_t ld, int kb) {
+fw32_phase3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict__ panel, int64_t ldp,
+                   int kb, int skip) {
+    // dist = LOCAL row block; tile (bi, bj) <- min-plus of local column tile (bi, kb) and the
+    // pivot row panel's tile (., bj); local tile-row `skip` (the pivot rows) is left alone
     const int bj = blockIdx.x, bi = blockIdx.y;
-    if (bi == kb || bj == kb) return;
+    if (bi == skip || bj == kb) return;
     extern __shared__ __align__(16) unsigned char fw_smem[];
     float (*ct)[kT + 4] = reinterpret_cast<float (*)[kT + 4]>(fw_smem);                          // column panel, transposed: ct[k][i]
     float (*rt)[kT] = reinterpret_cast<float (*)[kT]>(fw_smem + sizeof(float) * kH * (kT + 4));  // row panel: rt[k][j]
@@ -425,13 +433,13 @@ fw32_phase3_kernel(float* __restrict__ dist, int64_t ld, int kb) {
     }
     for (int h = 0; h < kT / kH; ++h) {
         const int64_t cbase = (int64_t)bi * kT * ld + (int64_t)kb * kT + h * kH;     // (bi, kb) cols h*64..
-        const int64_t rbase = ((int64_t)kb * kT + h * kH) * ld + (int64_t)bj * kT;   // (kb, bj) rows h*64..
+        const int64_t rbase = ((int64_t)h * kH) * ldp + (int64_t)bj * kT;            // panel rows h*64.., cols of bj
         __syncthreads();
         for (int e = tid; e < kT * kH; e += 256) {
             const int i = e >> 6, k = e & 63;            // column panel: 128 rows x 64 k (k contiguous)
             ct[k][i] = dist[cbase + i * ld + k];
             const int kk = e >> 7, j = e & 127;          // row panel: 64 k x 128 cols
-            rt[kk][j] = dist[rbase + kk * ld + j];
+            rt[kk][j] = panel[rbase + kk * ldp + j];
         }
         __syncthreads();
 #pragma unroll 2
@@ -580,11 +588,12 @@ int run_apsp_f32_fast(wisp_ctx* ctx, const double* d_w, int N, double* d_dist, i
     WISP_CUDA(cudaFuncSetAttribute(fw32_phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     WISP_CUDA(cudaFuncSetAttribute(fw32_phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
     for (int kb = 0; kb < nb; ++kb) {
-        fw32_phase1_kernel<<<1, 1024, smem1, st>>>(dist, n_pad, kb);
+        float* panel = dist + (int64_t)kb * kT * n_pad;     // single GPU: the panel is the pivot rows in place
+        fw32_phase1_kernel<<<1, 1024, smem1, st>>>(panel, n_pad, kb);
         ctx->launches++;
         if (nb > 1) {
-            fw32_phase2_kernel<<<dim3(nb, 2), 1024, smem2, st>>>(dist, n_pad, kb);
-            fw32_phase3_kernel<<<dim3(nb, nb), 256, smem3, st>>>(dist, n_pad, kb);
+            fw32_phase2_kernel<<<dim3(nb, 2), 1024, smem2, st>>>(dist, n_pad, panel, n_pad, kb, nb, nb, kb);
+            fw32_phase3_kernel<<<dim3(nb, nb), 256, smem3, st>>>(dist, n_pad, panel, n_pad, kb, kb);
             ctx->launches += 2;
         }
     }
@@ -629,6 +638,28 @@ int run_apsp_f32_fast(wisp_ctx* ctx, const double* d_w, int N, double* d_dist, i
     return 0;
 }
 
+int fw32_set_attrs() {
+    const int smem1 = kT * (kT + 1) * 4, smem2 = 2 * kT * (kT + 1) * 4;
+    const int smem3 = (int)sizeof(float) * kH * (2 * kT + 4);
+    WISP_CUDA(cudaFuncSetAttribute(fw32_phase3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    WISP_CUDA(cudaFuncSetAttribute(fw32_phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    WISP_CUDA(cudaFuncSetAttribute(fw32_phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    return 0;
+}
+
+__global__ void fw32_init_rows_kernel(const double* __restrict__ w_rows, int N, int64_t n_pad, int64_t row0,
+                                      int64_t rows_pad, float* __restrict__ dist) {
+    const int64_t total = rows_pad * n_pad;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t rl = e / n_pad, c = e - rl * n_pad, r = row0 + rl;
+        float d = __int_as_float(0x7f800000);
+        if (r == c) d = 0.f;
+        else if (r < N && c < N) { const double v = w_rows[rl * N + c]; if (v != 0.0) d = (float)v; }
+        dist[e] = d;
+    }
+}
+
 }  // namespace
 
 int launch_apsp(wisp_ctx* ctx, const double* d_w, int N, int precision, double* d_dist,
@@ -638,4 +669,61 @@ int launch_apsp(wisp_ctx* ctx, const double* d_w, int N, int precision, double* 
     if (precision == 64) return run_apsp<double>(ctx, d_w, N, d_dist, d_pred, st);
     if (getenv("WISP_FW32_TRACKED")) return run_apsp<float>(ctx, d_w, N, d_dist, d_pred, st);
     return run_apsp_f32_fast(ctx, d_w, N, d_dist, d_pred, st);
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Row-block sharded FP32 Floyd-Warshall (BASELINE configs[3]): every rank owns a
+// block of 128-row tile rows.  Round kb: the owner of pivot rows kb finishes the pivot ROW
+// PANEL (phase 1 + row half of phase 2) in a separate buffer and broadcasts it (NCCL, done by
+// the caller); every rank then updates its own pivot-column tiles and its remainder tiles
+// from that panel.  The single-GPU path above is the same kernels with the panel aliased to
+// the pivot rows in place.
+// ---------------------------------------------------------------------------------------
+extern "C" int wisp_dev_fw32_init_rows(wisp_ctx* ctx, const double* d_w_rows, int N, int64_t row0,
+                                       int64_t rows_pad, float* d_dist_local, void* stream) {
+    WISP_CHECK(ctx && d_w_rows && d_dist_local && rows_pad % kT == 0, "fw32_init_rows: bad argument");
+    cudaStream_t st = wisp_stream(ctx, stream);
+    const int64_t n_pad = round_up(N, kT);
+    const int g = (int)std::min<int64_t>((rows_pad * n_pad + 255) / 256, (int64_t)ctx->sm_count * 16);
+    fw32_init_rows_kernel<<<g, 256, 0, st>>>(d_w_rows, N, n_pad, row0, rows_pad, d_dist_local);
+    ctx->launches++;
+    WISP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// phase 1 + pivot-row tiles on a [128][n_pad] panel (owner only)
+extern "C" int wisp_dev_fw32_pivot_panel(wisp_ctx* ctx, float* d_panel, int N, int kb, void* stream) {
+    WISP_CHECK(ctx && d_panel, "fw32_pivot_panel: bad argument");
+    cudaStream_t st = wisp_stream(ctx, stream);
+    const int64_t n_pad = round_up(N, kT);
+    const int nb = (int)(n_pad / kT);
+    WISP_TRY(fw32_set_attrs());
+    const int smem1 = kT * (kT + 1) * 4, smem2 = 2 * kT * (kT + 1) * 4;
+    fw32_phase1_kernel<<<1, 1024, smem1, st>>>(d_panel, n_pad, kb);
+    fw32_phase2_kernel<<<dim3(nb, 1), 1024, smem2, st>>>(d_panel, n_pad, d_panel, n_pad, kb, nb, 0, -1);
+    ctx->launches += 2;
+    WISP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// pivot-column tiles + remainder tiles of a local row block from a received panel;
+// skip_local_tile = local tile-row index holding the pivot rows (-1 if they live elsewhere)
+extern "C" int wisp_dev_fw32_update_rows(wisp_ctx* ctx, float* d_dist_local, int64_t rows_pad,
+                                         const float* d_panel, int N, int kb, int skip_local_tile,
+                                         void* stream) {
+    WISP_CHECK(ctx && d_dist_local && d_panel && rows_pad % kT == 0, "fw32_update_rows: bad argument");
+    cudaStream_t st = wisp_stream(ctx, stream);
+    const int64_t n_pad = round_up(N, kT);
+    const int nb = (int)(n_pad / kT), nl = (int)(rows_pad / kT);
+    WISP_TRY(fw32_set_attrs());
+    const int smem2 = 2 * kT * (kT + 1) * 4;
+    const int smem3 = (int)sizeof(float) * kH * (2 * kT + 4);
+    // column tiles: launch only the y == 1 half (grid.y index 1)
+    fw32_phase2_kernel<<<dim3(nl, 2), 1024, smem2, st>>>(d_dist_local, n_pad, const_cast<float*>(d_panel), n_pad,
+                                                        kb, 0, nl, skip_local_tile);
+    fw32_phase3_kernel<<<dim3(nb, nl), 256, smem3, st>>>(d_dist_local, n_pad, d_panel, n_pad, kb, skip_local_tile);
+    ctx->launches += 2;
+    WISP_CUDA(cudaGetLastError());
+    return 0;
 }
