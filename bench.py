@@ -230,10 +230,16 @@ def main():
         run_reference_arm(args)
         return
 
+    # stdout must carry exactly ONE JSON line: libraries (NCCL's version banner, ...) that
+    # write to fd 1 are pointed at stderr for the whole run; the line goes to the saved fd.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from wisp_mdanalysis_implementation_b200 import _lib, synth
-    from wisp_mdanalysis_implementation_b200.pipeline import FramePipeline
+    from wisp_mdanalysis_implementation_b200.pipeline import FramePipeline, bind_to_gpu_numa_node
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -241,6 +247,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -384,7 +391,7 @@ def main():
         ms_e2e = max_over_ranks(max(a.elapsed_time(b) / args.steps, 0.0))
         e2e = {"value": float(N) * N * T / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                "wall_ms_per_step": wall_ms, "h2d_bytes_per_step": pipe.h2d_bytes() * world,
-               "d2h_bytes_per_step": pipe.d2h_bytes(),
+               "d2h_bytes_per_step": pipe.d2h_bytes(), "numa_node_rank0": numa_node,
                "api": "FramePipeline.%s (C-ABI wisp_dev_* calls; pinned host coords in, "
                       "corr/avgdist/binary/w on the host out)" % run_e2e.__name__}
         del h_coords
@@ -495,7 +502,8 @@ def main():
                 "config": workload_config(args), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
                 "roofline": roofline, "roofline_tensor": roofline_tensor, "kernels": kernels, "cpu_baseline": cpu_baseline, "extra": extra}
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -16,6 +16,37 @@ import torch
 from . import _lib, sharding
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that pinned host
+    buffers allocated afterwards are node-local and every rank's H2D stream crosses only its own
+    PCIe root (matters at 8 ranks: 8 x 50 GB/s of host reads).  Best effort; returns the node or
+    None."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # 00000000:1b:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 class FramePipeline:
     def __init__(self, ctx, n_nodes, n_atoms, masses, node_ptr, atom_idx, align_idx,
                  frames_local, frames_total=None, cutoff=15.0, which_map=1, atomic=False,
