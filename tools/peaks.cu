@@ -112,6 +112,34 @@ __global__ void minplus_peak(float* out, int iters) {
     if (s == 123.456f) out[0] = s;
 }
 
+// pure 2-input FMNMX stream: the ALU-pipe rate that bounds min-plus relaxations
+__global__ void fmnmx_peak(float* out, int iters) {
+    float c[16];
+    for (int i = 0; i < 16; ++i) c[i] = 1e9f + i;
+    float a = threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) asm volatile("min.f32 %0, %0, %1;" : "+f"(c[i]) : "f"(a));
+        a += 1e-3f;
+    }
+    float s = 0;
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 123.456f) out[0] = s;
+}
+__global__ void fmnmx3_peak(float* out, int iters) {
+    float c[16];
+    for (int i = 0; i < 16; ++i) c[i] = 1e9f + i;
+    float a = threadIdx.x, b = threadIdx.x + 0.5f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(c[i]) : "f"(a), "f"(b));
+        a += 1e-3f;
+    }
+    float s = 0;
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 123.456f) out[0] = s;
+}
+
 template <typename F>
 double best_ms(F launch) {
     cudaEvent_t e0, e1;
@@ -148,12 +176,16 @@ int main() {
     const double ffma2_tf = lanes * it * 16 * 4.0 / (t * 1e-3) / 1e12;
     t = best_ms([&] { k3mix_peak<<<blocks, threads>>>((float*)buf, it); });
     const double k3mix_tpf = lanes * it * 16.0 / (t * 1e-3) / 1e12;
+    t = best_ms([&] { fmnmx_peak<<<blocks, threads>>>((float*)buf, it); });
+    const double fmnmx_tops = lanes * it * 16.0 / (t * 1e-3) / 1e12;
+    t = best_ms([&] { fmnmx3_peak<<<blocks, threads>>>((float*)buf, it); });
+    const double fmnmx3_tops = lanes * it * 16.0 / (t * 1e-3) / 1e12;
     t = best_ms([&] { minplus_peak<<<blocks, threads>>>((float*)buf, it); });
     const double minplus_trelax = lanes * it * 16.0 / (t * 1e-3) / 1e12;
     CK(cudaDeviceSynchronize());
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"fp64_dmma_tflops\": %.2f, \"fp64_fma_tflops\": %.2f, "
            "\"fp32_fma_tflops\": %.2f, \"mufu_sqrt_tops\": %.3f, \"fp32_minplus_trelax\": %.3f, \"fp32_ffma2_tflops\": %.2f, "
-           "\"k3_mix_tpairframes\": %.3f}\n",
-           p.name, sms, dmma_tf, dfma_tf, ffma_tf, mufu_tops, minplus_trelax, ffma2_tf, k3mix_tpf);
+           "\"k3_mix_tpairframes\": %.3f, \"fmnmx_tops\": %.3f, \"fmnmx3_tops\": %.3f}\n",
+           p.name, sms, dmma_tf, dfma_tf, ffma_tf, mufu_tops, minplus_trelax, ffma2_tf, k3mix_tpf, fmnmx_tops, fmnmx3_tops);
     return 0;
 }

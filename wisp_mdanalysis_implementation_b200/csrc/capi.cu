@@ -120,10 +120,6 @@ int arena_open(wisp_ctx* ctx, size_t bytes, Arena* a) {
     return 0;
 }
 
-__global__ void scale_kernel(const double* __restrict__ in, double s, int64_t n, double* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = in[i] * s;
-}
 __global__ void div_kernel(const double* __restrict__ in, double d, int64_t n, double* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] / d;

@@ -63,7 +63,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __global__ void __launch_bounds__(256)
 align_shift_kernel(const float* __restrict__ coords, int64_t T, int A,
                    const int32_t* __restrict__ align_idx, const double* __restrict__ align_mass,
-                   int n_align, double inv_total_is_unused, double* __restrict__ shift,
+                   int n_align, double* __restrict__ shift,
                    float* __restrict__ align_out, int64_t row0) {
     const int lane = threadIdx.x & 31;
     const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -133,14 +133,12 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
     }
     // this CTA always works on the same piece: its per-atom masses live in shared memory and
     // its per-lane node descriptor in registers for the whole kernel
-    const int4 first_info = __ldg(node_info + pc.node0);
     for (int i = tid; i < pc.n_atoms; i += kStThreads) smass[i] = 0.0;
     __syncthreads();
     for (int nl = tid; nl < pc.n_nodes; nl += kStThreads) {
         const int4 info = __ldg(node_info + pc.node0 + nl);
         for (int a = 0; a < info.y; ++a) smass[info.z + a] = __ldg(ent_mass + info.x + a);
     }
-    (void)first_info;
 
     // lane = (node j of this warp's 10, component c): no cross-lane reduction at all
     const int lane = tid & 31, warp = tid >> 5;
@@ -337,8 +335,8 @@ int launch_com_plan(wisp_ctx* ctx, wisp_com_plan* pl, const float* d_coords, int
         pl->shift_frames = T;
     }
     align_shift_kernel<<<(unsigned)((T + 7) / 8), 256, 0, st>>>(d_coords, T, pl->A, pl->d_align_idx,
-                                                               pl->d_align_mass, pl->n_align, 0.0,
-                                                               pl->d_shift, d_align_out, row0);
+                                                               pl->d_align_mass, pl->n_align, pl->d_shift,
+                                                               d_align_out, row0);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
     const int smem = kStStages * kStageBytes + kPieceAtomsMax * 8;
