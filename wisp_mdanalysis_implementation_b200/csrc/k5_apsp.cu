@@ -408,7 +408,19 @@ fw32_phase2_kernel(float* __restrict__ local, int64_t ld, float* __restrict__ pa
         }
 }
 
-// phase 3: all tiles outside the pivot row / column
+// phase 3: all tiles outside the pivot row / column.  The 128-deep k range is streamed in four
+// 32-deep chunks through a 3-stage cp.async ring (column panel kept i-major: no transpose),
+// so the panel loads of chunk s+2 overlap the min-plus arithmetic of chunk s.
+constexpr int kC = 32;                 // k-depth per stage
+constexpr int kColLd = kC + 4;         // padded row of the column-panel stage (floats)
+constexpr int kP3Stages = 3;
+constexpr int kP3StageFloats = kT * kColLd + kC * kT;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+
 __global__ void __launch_bounds__(256, 2)
 fw32_phase3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict__ panel, int64_t ldp,
                    int kb, int skip) {
@@ -417,11 +429,29 @@ fw32_phase3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict
     const int bj = blockIdx.x, bi = blockIdx.y;
     if (bi == skip || bj == kb) return;
     extern __shared__ __align__(16) unsigned char fw_smem[];
-    float (*ct)[kT + 4] = reinterpret_cast<float (*)[kT + 4]>(fw_smem);                          // column panel, transposed: ct[k][i]
-    float (*rt)[kT] = reinterpret_cast<float (*)[kT]>(fw_smem + sizeof(float) * kH * (kT + 4));  // row panel: rt[k][j]
+    float* stages = reinterpret_cast<float*>(fw_smem);
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;            // cols {4tx.., 64+4tx..}, rows {4ty.., 64+4ty..}
     const int64_t obase = (int64_t)bi * kT * ld + (int64_t)bj * kT;
+    const float* cg = dist + (int64_t)bi * kT * ld + (int64_t)kb * kT;    // column tile (bi, kb): [i][k]
+    const float* rg = panel + (int64_t)bj * kT;                            // row tile (kb, bj):   [k][j]
+
+    auto issue = [&](int chunk) {
+        float* cs = stages + (size_t)(chunk % kP3Stages) * kP3StageFloats;     // [128][kColLd]
+        float* rs = cs + kT * kColLd;                                            // [kC][128]
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = tid + 256 * q;              // 1024 16-byte granules per panel
+            const int i = e >> 3, g = e & 7;          // column panel: row i, granule g (4 floats of k)
+            cp_async16(cs + i * kColLd + 4 * g, cg + i * ld + chunk * kC + 4 * g);
+            const int k = e >> 5, h = e & 31;         // row panel: row k, granule h (4 floats of j)
+            cp_async16(rs + k * kT + 4 * h, rg + (int64_t)(chunk * kC + k) * ldp + 4 * h);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    issue(0);
+    issue(1);
     float d[8][8];
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
@@ -431,29 +461,27 @@ fw32_phase3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict
         d[a][0] = v0.x; d[a][1] = v0.y; d[a][2] = v0.z; d[a][3] = v0.w;
         d[a][4] = v1.x; d[a][5] = v1.y; d[a][6] = v1.z; d[a][7] = v1.w;
     }
-    for (int h = 0; h < kT / kH; ++h) {
-        const int64_t cbase = (int64_t)bi * kT * ld + (int64_t)kb * kT + h * kH;     // (bi, kb) cols h*64..
-        const int64_t rbase = ((int64_t)h * kH) * ldp + (int64_t)bj * kT;            // panel rows h*64.., cols of bj
-        __syncthreads();
-        for (int e = tid; e < kT * kH; e += 256) {
-            const int i = e >> 6, k = e & 63;            // column panel: 128 rows x 64 k (k contiguous)
-            ct[k][i] = dist[cbase + i * ld + k];
-            const int kk = e >> 7, j = e & 127;          // row panel: 64 k x 128 cols
-            rt[kk][j] = panel[rbase + kk * ldp + j];
-        }
-        __syncthreads();
+    constexpr int kChunks = kT / kC;
+    for (int chunk = 0; chunk < kChunks; ++chunk) {
+        if (chunk + 1 < kChunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                               // chunk landed for everyone; chunk-1 fully consumed
+        if (chunk + 2 < kChunks) issue(chunk + 2);
+        const float* cs = stages + (size_t)(chunk % kP3Stages) * kP3StageFloats;
+        const float* rs = cs + kT * kColLd;
 #pragma unroll 2
-        for (int k = 0; k < kH; k += 2) {
-            const float4 c1a = *reinterpret_cast<const float4*>(&ct[k][4 * ty]);
-            const float4 c1b = *reinterpret_cast<const float4*>(&ct[k][64 + 4 * ty]);
-            const float4 c2a = *reinterpret_cast<const float4*>(&ct[k + 1][4 * ty]);
-            const float4 c2b = *reinterpret_cast<const float4*>(&ct[k + 1][64 + 4 * ty]);
-            const float4 r1a = *reinterpret_cast<const float4*>(&rt[k][4 * tx]);
-            const float4 r1b = *reinterpret_cast<const float4*>(&rt[k][64 + 4 * tx]);
-            const float4 r2a = *reinterpret_cast<const float4*>(&rt[k + 1][4 * tx]);
-            const float4 r2b = *reinterpret_cast<const float4*>(&rt[k + 1][64 + 4 * tx]);
-            const float c1[8] = {c1a.x, c1a.y, c1a.z, c1a.w, c1b.x, c1b.y, c1b.z, c1b.w};
-            const float c2[8] = {c2a.x, c2a.y, c2a.z, c2a.w, c2b.x, c2b.y, c2b.z, c2b.w};
+        for (int k = 0; k < kC; k += 2) {
+            float c1[8], c2[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const int row = (a < 4) ? 4 * ty + a : 64 + 4 * ty + (a - 4);
+                const float2 cc = *reinterpret_cast<const float2*>(cs + row * kColLd + k);
+                c1[a] = cc.x; c2[a] = cc.y;
+            }
+            const float4 r1a = *reinterpret_cast<const float4*>(rs + k * kT + 4 * tx);
+            const float4 r1b = *reinterpret_cast<const float4*>(rs + k * kT + 64 + 4 * tx);
+            const float4 r2a = *reinterpret_cast<const float4*>(rs + (k + 1) * kT + 4 * tx);
+            const float4 r2b = *reinterpret_cast<const float4*>(rs + (k + 1) * kT + 64 + 4 * tx);
             const f32x2_t r1[4] = {fw_pack(r1a.x, r1a.y), fw_pack(r1a.z, r1a.w), fw_pack(r1b.x, r1b.y), fw_pack(r1b.z, r1b.w)};
             const f32x2_t r2[4] = {fw_pack(r2a.x, r2a.y), fw_pack(r2a.z, r2a.w), fw_pack(r2b.x, r2b.y), fw_pack(r2b.z, r2b.w)};
 #pragma unroll
@@ -583,7 +611,7 @@ int run_apsp_f32_fast(wisp_ctx* ctx, const double* d_w, int N, double* d_dist, i
     fw32_init_kernel<<<g, 256, 0, st>>>(d_w, N, n_pad, dist);
     ctx->launches++;
     const int smem1 = kT * (kT + 1) * 4, smem2 = 2 * kT * (kT + 1) * 4;
-    const int smem3 = (int)sizeof(float) * kH * (2 * kT + 4);
+    const int smem3 = (int)sizeof(float) * kP3Stages * kP3StageFloats;
     WISP_CUDA(cudaFuncSetAttribute(fw32_phase3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     WISP_CUDA(cudaFuncSetAttribute(fw32_phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     WISP_CUDA(cudaFuncSetAttribute(fw32_phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
@@ -640,7 +668,7 @@ int run_apsp_f32_fast(wisp_ctx* ctx, const double* d_w, int N, double* d_dist, i
 
 int fw32_set_attrs() {
     const int smem1 = kT * (kT + 1) * 4, smem2 = 2 * kT * (kT + 1) * 4;
-    const int smem3 = (int)sizeof(float) * kH * (2 * kT + 4);
+    const int smem3 = (int)sizeof(float) * kP3Stages * kP3StageFloats;
     WISP_CUDA(cudaFuncSetAttribute(fw32_phase3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     WISP_CUDA(cudaFuncSetAttribute(fw32_phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     WISP_CUDA(cudaFuncSetAttribute(fw32_phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
@@ -718,7 +746,7 @@ extern "C" int wisp_dev_fw32_update_rows(wisp_ctx* ctx, float* d_dist_local, int
     const int nb = (int)(n_pad / kT), nl = (int)(rows_pad / kT);
     WISP_TRY(fw32_set_attrs());
     const int smem2 = 2 * kT * (kT + 1) * 4;
-    const int smem3 = (int)sizeof(float) * kH * (2 * kT + 4);
+    const int smem3 = (int)sizeof(float) * kP3Stages * kP3StageFloats;
     // column tiles: launch only the y == 1 half (grid.y index 1)
     fw32_phase2_kernel<<<dim3(nl, 2), 1024, smem2, st>>>(d_dist_local, n_pad, const_cast<float*>(d_panel), n_pad,
                                                         kb, 0, nl, skip_local_tile);
