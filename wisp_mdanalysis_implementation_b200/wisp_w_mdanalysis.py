@@ -1,17 +1,14 @@
-"""Driver: ``python wisp_w_mdanalysis.py <config>`` -- the reference's command line
-(wisp_w_mdanalysis.py:5,54) restated for Python 3 with the repairs of SURVEY.md Appendix B
-(B1 output file names, B2 stray mkdir, B3 adjacency call arity, B4 undeclared keys).
+"""``python wisp_w_mdanalysis.py <config>`` -- the reference's command line and stage order
+(wisp_w_mdanalysis.py:5,54,60-208), for Python 3, with the defects of SURVEY.md Appendix B
+repaired (B1 output names, B2 stray mkdir, B3 adjacency call arity, B4 undeclared keys).
 
-Stage implementations are looked up BY NAME from the module files named in the config
-(wisp_w_mdanalysis.config:7-12, wisp_w_mdanalysis.py:233-267), exactly like the reference,
-so a config can point any stage at the reference's own module or at the B200 module of the
-same name in this directory.  Boundary code: nothing is computed here.
+Like the reference, stage implementations are looked up BY NAME from the module files the
+config names (wisp_w_mdanalysis.config:7-12), so any stage can point at the reference's own
+module or at the B200 module of the same name in this directory.  Nothing is computed here.
 """
 import importlib
 import os
 import sys
-
-import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 for _p in (_HERE, os.path.dirname(_HERE)):
@@ -21,156 +18,158 @@ for _p in (_HERE, os.path.dirname(_HERE)):
 from IO import config_parser, summary  # noqa: E402
 from wisp_mdanalysis_implementation_b200 import textio  # noqa: E402
 
+STYLES = {   # adjacency_matrix_style -> (adjacency function, functionalisation function)
+    'PEARSON': ('pearson_correlation_analysis', 'func_pearson_correlation'),
+    'PEARSON CORRELATION': ('pearson_correlation_analysis', 'func_pearson_correlation'),
+    'LMI': ('linear_mutual_information_analysis', 'generalized_correlation_coefficient_calc'),
+    'LINEAR MUTUAL INFORMATION': ('linear_mutual_information_analysis', 'generalized_correlation_coefficient_calc'),
+}
 
-def _stage(parameters, key, name):
-    module = importlib.import_module(parameters[key].split('.')[0], package=None)
-    return getattr(module, name)
+
+def _fail(message):
+    """The reference's error convention: print, then sys.exit()."""
+    print(message)
+    sys.exit()
 
 
-def _universe(parameters):
-    if parameters['universe_factory']:
-        mod, fn = parameters['universe_factory'].split(':')
-        return getattr(importlib.import_module(mod), fn)(parameters)
-    import MDAnalysis
-    return MDAnalysis.Universe(parameters['pdb'])
+class WispRun:
+    def __init__(self, config_file, argv=None):
+        self.argv = list(argv) if argv is not None else list(sys.argv)
+        self.p = {}
+        config_parser(config_file, self.p)
+        out = self.p['output_directory']
+        self.out = out if out.endswith(os.sep) else out + os.sep
+        self.p['output_directory'] = self.out
+        if os.path.exists(self.out):
+            _fail('The output directory, %s already exists. Please select a different directory name '
+                  'for output.' % self.out)
+        os.mkdir(self.out)
+        self._bind_stages()
+
+    # -- stage lookup (wisp_w_mdanalysis.py:233-267) ---------------------------------------
+    def _load(self, key, name):
+        module = importlib.import_module(self.p[key].split('.')[0], package=None)
+        return getattr(module, name)
+
+    def _bind_stages(self):
+        p = self.p
+        self.make_selections = self._load('node_selection_file', 'make_selections')
+        if p['trajectory_analysis_boolean']:
+            self.align = self._load('trajectory_functions_file', 'traj_alignment_and_averaging')
+            self.covariance = self._load('trajectory_functions_file', 'cartesian_covariance')
+            self.contact = self._load('trajectory_functions_file', 'calc_contact_map')
+        style = p['adjacency_matrix_style'].upper()
+        if style not in STYLES:
+            _fail("adjacency_matrix_style %r is not available on the accelerated path; use one of %s"
+                  % (p['adjacency_matrix_style'], sorted(STYLES)))
+        adj_name, func_name = STYLES[style]
+        self.adjacency = self._load('adjacency_matrix_functions_file', adj_name)
+        self.functionalize = self._load('func_adjacency_matrix_functions_file', func_name)
+        self.get_paths = self._load('network_functions_file', 'get_paths')
+        vis = p['visualization_functions_file']
+        self.vis_state = None if vis in (None, 'None', 'none') else self._load('visualization_functions_file', 'create_vis_state')
+
+    def _universe(self):
+        factory = self.p['universe_factory']
+        if factory:
+            module, function = factory.split(':')
+            return getattr(importlib.import_module(module), function)(self.p)
+        import MDAnalysis
+        return MDAnalysis.Universe(self.p['pdb'])
+
+    # -- stages -----------------------------------------------------------------------------
+    def select_nodes(self):
+        p = self.p
+        self.universe = self._universe()
+        self.nodes, self.sources, self.sinks = self.make_selections(
+            self.universe, self.out + 'node_selections.txt', p['substrate_node_definition'],
+            p['substrate_selection_string'], p['source_selection_string_list'],
+            p['sink_selection_string_list'],
+            nonstandard_substrates_selection=p['nonstandard_substrates_selection'],
+            homemade_selections=p['homemade_selections'])
+        print('Number of nodes: %d\nsource node indices: %s\nsink node indices: %s'
+              % (len(self.nodes), self.sources, self.sinks))
+
+    def analyze_trajectory(self):
+        """Stage 4 with a trajectory (reference :80-104)."""
+        p = self.p
+        trajectory, self.avg = self.align(self.universe, p['alignment_selection'], self.nodes,
+                                          p['substrate_node_definition'], p['traj_list'], self.out,
+                                          step=p['trajectory_step'], convergence_threshold=1E-5)
+        self.cov = self.covariance(trajectory, self.avg, self.out)
+        binary, mean_distance = self.contact(trajectory, self.out,
+                                             distance_cutoff=p['contact_map_distance_cutoff'])
+        which = p['which_contact_map'].upper()
+        if which == 'AVERAGE CONTACT MAP':
+            self.contact_map = mean_distance
+        elif which == 'BINARY CONTACT MAP':
+            self.contact_map = binary
+        else:
+            _fail("which_contact_map must be 'AVERAGE CONTACT MAP' or 'BINARY CONTACT MAP'.")
+
+    def load_matrices(self):
+        """Stage 4 from user-supplied text matrices (reference :106-123)."""
+        p, n = self.p, len(self.nodes)
+        self.cov = textio.loadtxt(p['user_input_cartesian_covariance_matrix'])
+        if self.cov.ndim != 2 or self.cov.shape[0] % 3 or self.cov.shape[0] != self.cov.shape[1]:
+            _fail('The supplied cartesian covariance matrix has shape %s, expected (%d, %d).'
+                  % (self.cov.shape, 3 * n, 3 * n))
+        self.avg = self.contact_map = None
+        if p['user_input_average_node_positions']:
+            self.avg = textio.loadtxt(p['user_input_average_node_positions'])
+            if self.avg.shape != (n, 3):
+                _fail('The supplied average node positions have shape %s, expected (%d, 3).' % (self.avg.shape, n))
+        if p['user_input_contact_map']:
+            self.contact_map = textio.loadtxt(p['user_input_contact_map'])
+            if self.contact_map.shape != (n, n):
+                _fail('The supplied contact map has shape %s, expected (%d, %d).' % (self.contact_map.shape, n, n))
+
+    def build_cost_matrix(self):
+        p, n = self.p, len(self.nodes)
+        if p['adjacency_matrix_analysis_boolean']:
+            adjacency = self.adjacency(self.cov, self.avg, self.out)          # B3: three arguments
+        else:
+            adjacency = textio.loadtxt(p['user_input_adjacency_matrix'])
+            if adjacency.shape != (n, n):
+                _fail('The supplied adjacency matrix has shape %s, expected (%d, %d).' % (adjacency.shape, n, n))
+        if p['weight_by_contact_map_boolean']:
+            self.cost = self.functionalize(adjacency, self.out, contact_map=self.contact_map, Lambda=p['Lambda'])
+        else:
+            self.cost = self.functionalize(adjacency, self.out)
+
+    def find_paths(self):
+        self.paths = self.get_paths(self.cost, self.sources, self.sinks, self.p['number_of_paths'])
+        with open(self.out + 'simply_formatted_paths.txt', 'w') as handle:   # reference :157-165
+            handle.write('# Pathway_Length Node_Indices (zero indexed)\n')
+            for path in self.paths:
+                handle.write('%f ' % path[0] + ''.join('%d ' % node for node in path[1:]) + '\n')
+
+    def write_extras(self):
+        p = self.p
+        if self.vis_state is not None:      # VMD state: outside the accelerated path, optional
+            self.universe.load_new(p['visualization_frame_pdb'])
+            keys = ('node_sphere_radius', 'node_sphere_rgb', 'shortest_path_radius', 'shortest_path_rgb',
+                    'longest_path_radius', 'longest_path_rgb', 'node_sphere_color_index',
+                    'VMD_color_index_range', 'VMD_resolution', 'VMD_spline_smoothness')
+            self.vis_state(p['visualization_frame_pdb'], self.nodes, self.paths,
+                           self.out + 'pathways_vis_state.vmd', **{k: p[k] for k in keys})
+        if p['summary_boolean']:
+            summary(self.out + 'summary.txt', self.argv, p)
+
+    def run(self):
+        self.select_nodes()
+        if self.p['trajectory_analysis_boolean']:
+            self.analyze_trajectory()
+        else:
+            self.load_matrices()
+        self.build_cost_matrix()
+        self.find_paths()
+        self.write_extras()
+        return self.paths
 
 
 def main(config_file, argv=None):
-    parameters = {}
-    config_parser(config_file, parameters)                                          # :213-214
-    if parameters['output_directory'][-1] != os.sep:
-        parameters['output_directory'] += os.sep
-    if os.path.exists(parameters['output_directory']):                              # :222-224
-        print('The output directory, ', parameters['output_directory'],
-              'already exists. Please select a different directory name for output.')
-        sys.exit()
-    os.mkdir(parameters['output_directory'])
-    out = parameters['output_directory']
-
-    # ---- 2) stage functions by name (:233-267) ----
-    make_selections = _stage(parameters, 'node_selection_file', 'make_selections')
-    if parameters['trajectory_analysis_boolean']:
-        traj_alignment_and_averaging = _stage(parameters, 'trajectory_functions_file', 'traj_alignment_and_averaging')
-        cartesian_covariance = _stage(parameters, 'trajectory_functions_file', 'cartesian_covariance')
-        calc_contact_map = _stage(parameters, 'trajectory_functions_file', 'calc_contact_map')
-    style = parameters['adjacency_matrix_style'].upper()
-    if style in ('PEARSON', 'PEARSON CORRELATION'):
-        adjacency_matrix_analysis = _stage(parameters, 'adjacency_matrix_functions_file', 'pearson_correlation_analysis')
-        functionalize_adjacency_matrix = _stage(parameters, 'func_adjacency_matrix_functions_file', 'func_pearson_correlation')
-    elif style in ('LMI', 'LINEAR MUTUAL INFORMATION'):
-        adjacency_matrix_analysis = _stage(parameters, 'adjacency_matrix_functions_file', 'linear_mutual_information_analysis')
-        functionalize_adjacency_matrix = _stage(parameters, 'func_adjacency_matrix_functions_file', 'generalized_correlation_coefficient_calc')
-    else:
-        print("The user has not read in an accepted style of adjacency matrix. Accelerated here: "
-              "'PEARSON' / 'PEARSON CORRELATION'.")
-        sys.exit()
-    get_paths = _stage(parameters, 'network_functions_file', 'get_paths')
-    create_vis_state = None
-    if parameters['visualization_functions_file'] not in (None, 'None', 'none'):
-        create_vis_state = _stage(parameters, 'visualization_functions_file', 'create_vis_state')
-
-    # B1: the three names the reference left commented out (:65-67)
-    simply_formatted_paths_file_name = out + 'simply_formatted_paths.txt'
-    pathways_vis_state_file_name = out + 'pathways_vis_state.vmd'
-    summary_file_name = out + 'summary.txt'
-
-    # ---- 3) universe and node selections (:72-75) ----
-    u = _universe(parameters)
-    selection_list, source_indices, sink_indices = make_selections(
-        u, out + 'node_selections.txt', parameters['substrate_node_definition'],
-        parameters['substrate_selection_string'], parameters['source_selection_string_list'],
-        parameters['sink_selection_string_list'],
-        nonstandard_substrates_selection=parameters['nonstandard_substrates_selection'],
-        homemade_selections=parameters['homemade_selections'])
-    print('Number of nodes:', len(selection_list), '\nsource node indices:', source_indices,
-          '\nsink node indices:', sink_indices, '\nNode selections written out to', out + 'node_selections.txt')
-
-    contact_map = None
-    # ---- 4) trajectory analysis (:80-123) ----
-    if parameters['trajectory_analysis_boolean']:
-        print('Beginning trajectory analysis.')
-        Node_trajectory, avg_Node_positions = traj_alignment_and_averaging(
-            u, parameters['alignment_selection'], selection_list, parameters['substrate_node_definition'],
-            parameters['traj_list'], out, step=parameters['trajectory_step'], convergence_threshold=1E-5)
-        Node_cart_covariance = cartesian_covariance(Node_trajectory, avg_Node_positions, out)
-        print('Beginning node pair distance calculation.')
-        binary_contact_map, avg_node_node_distances = calc_contact_map(
-            Node_trajectory, out, distance_cutoff=parameters['contact_map_distance_cutoff'])
-        if parameters['which_contact_map'].upper() == 'AVERAGE CONTACT MAP':
-            contact_map = avg_node_node_distances
-        elif parameters['which_contact_map'].upper() == 'BINARY CONTACT MAP':
-            contact_map = binary_contact_map
-        else:
-            print("User has not defined which contact map should be used in subsequent weighting of the "
-                  "adjacency matrix. Acceptable values for the 'which_contact_map' parameter are "
-                  "'AVERAGE CONTACT MAP' or 'BINARY CONTACT MAP'.")
-            sys.exit()
-    else:
-        n = len(selection_list)
-        print('Loading in the user specified cartesian covariance data file. Note: no node trajectory has been created.')
-        Node_cart_covariance = textio.loadtxt(parameters['user_input_cartesian_covariance_matrix'])
-        if Node_cart_covariance.shape[0] % 3 != 0 or Node_cart_covariance.shape[0] != Node_cart_covariance.shape[1]:
-            print('User has read in a cartesian covariance matrix that does not have the correct shape '
-                  '(expected: %d x %d, got: %d x %d).' % (3 * n, 3 * n, Node_cart_covariance.shape[0], Node_cart_covariance.shape[1]))
-            sys.exit()
-        avg_Node_positions = None
-        if parameters['user_input_average_node_positions']:
-            avg_Node_positions = textio.loadtxt(parameters['user_input_average_node_positions'])
-            if avg_Node_positions.shape != (n, 3):
-                print('User has read in an average node positions file that does not have the correct shape.')
-                sys.exit()
-        if parameters['user_input_contact_map']:
-            contact_map = textio.loadtxt(parameters['user_input_contact_map'])
-            if contact_map.shape != (n, n):
-                print('User has read in a contact map that does not have the correct shape.')
-                sys.exit()
-
-    # ---- 5) adjacency matrix (:128-136) ----
-    if parameters['adjacency_matrix_analysis_boolean']:
-        print('Beginning the calculation of the adjacency matrix (' + parameters['adjacency_matrix_style'] + ').')
-        adjacency_matrix = adjacency_matrix_analysis(Node_cart_covariance, avg_Node_positions, out)   # B3
-    else:
-        adjacency_matrix = textio.loadtxt(parameters['user_input_adjacency_matrix'])
-        if adjacency_matrix.shape != (len(selection_list), len(selection_list)):
-            print('User has read in an adjacency matrix that does not have the correct shape.')
-            sys.exit()
-
-    # ---- 6) cost matrix (:141-144) ----
-    if parameters['weight_by_contact_map_boolean']:
-        functionalized_adjacency_matrix = functionalize_adjacency_matrix(
-            adjacency_matrix, out, contact_map=contact_map, Lambda=parameters['Lambda'])
-    else:
-        functionalized_adjacency_matrix = functionalize_adjacency_matrix(adjacency_matrix, out)
-    print('Finished functionalizing and weighting the adjacency matrix.')
-
-    # ---- 7) paths (:154-165; B2: the stray os.mkdir at :152 is dropped) ----
-    paths = get_paths(functionalized_adjacency_matrix, source_indices, sink_indices, parameters['number_of_paths'])
-    print('Finished calculating the pathways that connect the source and sink selections.')
-    with open(simply_formatted_paths_file_name, 'w') as W:
-        W.write('# Pathway_Length Node_Indices (zero indexed)\n')
-        for path in paths:
-            path_string = '%f ' % (path[0])
-            for node in path[1:]:
-                path_string += '%d ' % (node)
-            path_string += '\n'
-            W.write(path_string)
-
-    # ---- 9) VMD state (out of the accelerated path; optional) ----
-    if create_vis_state is not None:
-        u.load_new(parameters['visualization_frame_pdb'])
-        create_vis_state(parameters['visualization_frame_pdb'], selection_list, paths, pathways_vis_state_file_name,
-                         node_sphere_radius=parameters['node_sphere_radius'], node_sphere_rgb=parameters['node_sphere_rgb'],
-                         shortest_path_radius=parameters['shortest_path_radius'], shortest_path_rgb=parameters['shortest_path_rgb'],
-                         longest_path_radius=parameters['longest_path_radius'], longest_path_rgb=parameters['longest_path_rgb'],
-                         node_sphere_color_index=parameters['node_sphere_color_index'],
-                         VMD_color_index_range=parameters['VMD_color_index_range'], VMD_resolution=parameters['VMD_resolution'],
-                         VMD_spline_smoothness=parameters['VMD_spline_smoothness'])
-        print('Finished creating the vis state file.')
-
-    # ---- 11) summary (:207-208) ----
-    if parameters['summary_boolean']:
-        summary(summary_file_name, argv if argv is not None else sys.argv, parameters)
-    return paths
+    return WispRun(config_file, argv).run()
 
 
 if __name__ == '__main__':
