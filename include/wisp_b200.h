@@ -98,15 +98,17 @@ int wisp_lmi_from_covariance(wisp_ctx* ctx, const double* cov, int N, double* ou
 int wisp_func_generalized_correlation(wisp_ctx* ctx, const double* mi, int N, const double* contact_map,
                                       double lambda, int has_lambda, double* out_rmi, double* out_func);
 
-/* Fused a1..a5: coordinates -> node COMs -> centred Gram + mean distances -> correlation,
- * contact maps, cost matrix, with the node trajectory never leaving the device.
+/* Fused a1..a5: coordinates -> node COMs -> (iterative alignment, max_align_iterations > 0) ->
+ * centred Gram + mean distances -> correlation, contact maps, cost matrix, with the node
+ * trajectory never leaving the device and the 3N x 3N covariance never materialised.
  * which_map: 0 none, 1 binary, 2 average-distance (wisp_w_mdanalysis.py:98-101,141-144).
  * Any output pointer may be NULL.  out_nodes [T][N][3] is optional (large). */
 int wisp_pipeline(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
                   const int32_t* node_ptr, const int32_t* atom_idx, int N,
-                  const int32_t* align_idx, int n_align, int atomic, double cutoff,
-                  int which_map, double* out_avg, double* out_corr, double* out_avgdist,
-                  int64_t* out_binary, double* out_w, double* out_nodes);
+                  const int32_t* align_idx, int n_align, int atomic, double align_threshold,
+                  int max_align_iterations, double cutoff, int which_map, double* out_avg,
+                  double* out_corr, double* out_avgdist, int64_t* out_binary, double* out_w,
+                  double* out_nodes);
 
 /* a6 (north-star APSP; the reference calls Dijkstra, network_analysis_functions.py:30,71-72).
  * w [N][N] cost matrix (non-zero = edge).  precision 64 or 32 (distances are returned as

@@ -368,6 +368,17 @@ number_of_paths = 12
     assert_corr_close(got_corr, corr)
     lines = (out / "simply_formatted_paths.txt").read_text().splitlines()
     assert lines[0].startswith("# Pathway_Length") and len(lines) == len(paths) + 1
+    # the fused device pass (config key fused_pipeline_boolean) gives the same paths
+    cfg2 = tmp_path / "run_fused.config"
+    cfg2.write_text(cfg.read_text().replace(str(out), str(tmp_path / "out_fused")) + "\nfused_pipeline_boolean = True\n")
+    sys.path.insert(0, pkg)
+    try:
+        paths2 = driver.main(str(cfg2), argv=["wisp_w_mdanalysis.py", str(cfg2)])
+    finally:
+        sys.path.remove(pkg)
+    assert [p[1:] for p in paths2] == [p[1:] for p in paths]
+    np.testing.assert_allclose([p[0] for p in paths2], [p[0] for p in paths], rtol=1e-9)
+    assert_corr_close(np.loadtxt(tmp_path / "out_fused" / "node_correlation.dat"), corr)
 
 
 def test_frame_pipeline_matches_c_abi_pipeline(ctx):

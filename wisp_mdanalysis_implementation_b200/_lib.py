@@ -40,7 +40,7 @@ SIGNATURES = {
     "wisp_lmi_from_covariance": (_int, [_c_ctx, _P, _int, _P]),
     "wisp_func_generalized_correlation": (_int, [_c_ctx, _P, _int, _P, _dbl, _int, _P, _P]),
     "wisp_pipeline": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P, _int, _P, _int, _int, _dbl, _int,
-                             _P, _P, _P, _P, _P, _P]),
+                             _dbl, _int, _P, _P, _P, _P, _P, _P]),
     "wisp_apsp": (_int, [_c_ctx, _P, _int, _int, _P, _P]),
     "wisp_get_paths": (_int, [_c_ctx, _P, _int, _P, _int, _P, _int, _int, _int]),
     "wisp_paths_prepare": (_int, [_c_ctx, _P, _int, _int]),
@@ -246,8 +246,10 @@ class Context:
         return rmi, func
 
     def pipeline(self, coords, masses, node_ptr, atom_idx, align_idx, cutoff=9999.0,
-                 which_map=0, atomic=False, want_nodes=False):
-        """coords -> dict(avg, corr, avgdist, binary, w[, nodes]) in one fused device pass."""
+                 which_map=0, atomic=False, want_nodes=False, convergence_threshold=1e-5,
+                 maximum_num_iterations=0):
+        """coords -> dict(avg, corr, avgdist, binary, w[, nodes]) in one fused device pass
+        (K1, optional K7 alignment, K2, K3, K4)."""
         coords = _arr(coords, np.float32, "coords")
         T, A, _ = coords.shape
         masses = _arr(masses, np.float64, "masses", (A,))
@@ -260,7 +262,8 @@ class Context:
         nodes = np.empty((T, N, 3)) if want_nodes else None
         self._check(self._lib.wisp_pipeline(
             self._ctx, _ptr(coords), T, A, _ptr(masses), _ptr(node_ptr), _ptr(atom_idx), N,
-            _ptr(align_idx), len(align_idx), int(bool(atomic)), float(cutoff), int(which_map),
+            _ptr(align_idx), len(align_idx), int(bool(atomic)), float(convergence_threshold),
+            int(maximum_num_iterations), float(cutoff), int(which_map),
             _ptr(out["avg"]), _ptr(out["corr"]), _ptr(out["avgdist"]), _ptr(out["binary"]),
             _ptr(out["w"]), _ptr(nodes)))
         if want_nodes:

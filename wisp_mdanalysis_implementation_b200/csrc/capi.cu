@@ -401,10 +401,12 @@ extern "C" int wisp_func_pearson(wisp_ctx* ctx, const double* corr, int N, const
 extern "C" int wisp_pipeline(wisp_ctx* ctx, const float* coords, int64_t T, int A,
                              const double* masses, const int32_t* node_ptr,
                              const int32_t* atom_idx, int N, const int32_t* align_idx, int n_align,
-                             int atomic, double cutoff, int which_map, double* out_avg,
+                             int atomic, double align_threshold, int max_align_iterations,
+                             double cutoff, int which_map, double* out_avg,
                              double* out_corr, double* out_avgdist, int64_t* out_binary,
                              double* out_w, double* out_nodes) {
     WISP_CHECK(ctx && coords && masses, "pipeline: null argument");
+    WISP_CHECK(max_align_iterations >= 0, "pipeline: negative alignment iteration limit");
     WISP_CHECK(T > 0 && A > 0 && N > 0 && n_align > 0, "pipeline: empty input");
     WISP_CHECK(which_map >= 0 && which_map <= 2, "pipeline: which_map must be 0, 1 or 2");
     WISP_TRY(validate_node_map(A, node_ptr, atom_idx, N, align_idx, n_align));
@@ -423,8 +425,22 @@ extern "C" int wisp_pipeline(wisp_ctx* ctx, const float* coords, int64_t T, int 
     WISP_TRY(arena_open(ctx, plan.bytes + 8192, &ar));
     double* d_x;
     int64_t ldx;
+    float* d_align = nullptr;
+    const int64_t na3 = 3 * (int64_t)n_align, nn3 = 3 * (int64_t)N;
+    if (max_align_iterations > 0) {
+        void* pa = nullptr;
+        WISP_TRY(wisp_scratch(ctx, SCR_ALIGN, (size_t)T * na3 * 4, &pa));
+        d_align = (float*)pa;
+    }
     WISP_TRY(com_from_host(ctx, coords, T, A, masses, node_ptr, atom_idx, N, align_idx, n_align,
-                           atomic, &d_x, &ldx));
+                           atomic, &d_x, &ldx, d_align));
+    if (max_align_iterations > 0) {   // K7: iterative alignment on the device-resident trajectory
+        void* pw = nullptr;
+        WISP_TRY(wisp_scratch(ctx, SCR_MISC1, (size_t)(2 * round_up(na3, 32) + round_up(nn3, 32)) * 8, &pw));
+        int n_iter = 0;
+        WISP_TRY(run_iterative_alignment(ctx, d_align, n_align, d_x, ld, N, T, align_threshold,
+                                         max_align_iterations, (double*)pw, nullptr, nullptr, &n_iter, st));
+    }
     double* d_sum = ar.take<double>(ld);
     double* d_mean = ar.take<double>(ld);
     double* d_gram = ar.take<double>((size_t)n_pad * n_pad);

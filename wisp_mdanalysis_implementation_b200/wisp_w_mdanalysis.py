@@ -107,6 +107,39 @@ class WispRun:
         else:
             _fail("which_contact_map must be 'AVERAGE CONTACT MAP' or 'BINARY CONTACT MAP'.")
 
+    def analyze_trajectory_fused(self):
+        """Extension (config key ``fused_pipeline_boolean``): stages 4a-6 in ONE device pass --
+        K1, K7, K2, K3, K4 -- the node trajectory never leaves the GPU and the 3N x 3N
+        covariance is never materialised.  Writes the N x N stage files only."""
+        import numpy as np
+        from wisp_mdanalysis_implementation_b200 import _adapt, _lib
+        p = self.p
+        ctx = _lib.default_context()
+        align_idx = np.asarray(self.universe.select_atoms(p['alignment_selection']).indices, dtype=np.int32)
+        node_ptr, atom_idx = _adapt.selection_to_csr(self.nodes)
+        blocks = []
+        for traj in p['traj_list']:
+            self.universe.load_new(traj)
+            if len(self.universe.trajectory) % p['trajectory_step'] != 0:
+                _fail('User defined step size is not a factor of the number of frames in %s.' % traj)
+            blocks.append(_adapt.universe_coordinates(self.universe, p['trajectory_step']))
+        coords = blocks[0] if len(blocks) == 1 else np.concatenate(blocks)
+        which = {'AVERAGE CONTACT MAP': 2, 'BINARY CONTACT MAP': 1}.get(p['which_contact_map'].upper())
+        if which is None:
+            _fail("which_contact_map must be 'AVERAGE CONTACT MAP' or 'BINARY CONTACT MAP'.")
+        out = ctx.pipeline(coords, _adapt.universe_masses(self.universe), node_ptr, atom_idx, align_idx,
+                           cutoff=p['contact_map_distance_cutoff'],
+                           which_map=which if p['weight_by_contact_map_boolean'] else 0,
+                           atomic=p['substrate_node_definition'].upper() == 'ATOMIC',
+                           convergence_threshold=1E-5, maximum_num_iterations=100)
+        textio.savetxt(self.out + 'average_node_positions.dat', out['avg'],
+                       header='Shape: nNodes x 3 (%d x 3)' % len(self.nodes))
+        textio.savetxt(self.out + 'binary_contact_map.dat', out['binary'], fmt='%i')
+        textio.savetxt(self.out + 'avg_distance_contact_map.dat', out['avgdist'])
+        textio.savetxt(self.out + 'node_correlation.dat', out['corr'])
+        textio.savetxt(self.out + 'func_pearson_correlation.dat', out['w'])
+        self.cost = out['w']
+
     def load_matrices(self):
         """Stage 4 from user-supplied text matrices (reference :106-123)."""
         p, n = self.p, len(self.nodes)
@@ -158,11 +191,16 @@ class WispRun:
 
     def run(self):
         self.select_nodes()
-        if self.p['trajectory_analysis_boolean']:
-            self.analyze_trajectory()
+        fused = (self.p['fused_pipeline_boolean'] and self.p['trajectory_analysis_boolean']
+                 and self.p['adjacency_matrix_style'].upper() in ('PEARSON', 'PEARSON CORRELATION'))
+        if fused:
+            self.analyze_trajectory_fused()
         else:
-            self.load_matrices()
-        self.build_cost_matrix()
+            if self.p['trajectory_analysis_boolean']:
+                self.analyze_trajectory()
+            else:
+                self.load_matrices()
+            self.build_cost_matrix()
         self.find_paths()
         self.write_extras()
         return self.paths
