@@ -487,6 +487,21 @@ def main():
                                        "sample": "%d frames, one GEMM + blocked distances (numpy, all BLAS threads)" % (4 * Ts),
                                        "detail_s": detail_v}}
         if "get_paths" in extra:
+            # CPU shortest-path baselines on the same cost matrix: (L) the three pure-Python
+            # Dijkstra calls the reference makes per (pair, pass) (network_analysis_functions.py:
+            # 30,71-72), (V) scipy's C Dijkstra from every source = a CPU APSP
+            import oracle
+            import scipy.sparse
+            import scipy.sparse.csgraph
+            t0 = time.perf_counter()
+            adj = oracle.graph_edges(W)
+            oracle.dijkstra_path(W, s, t, adj)
+            oracle.dijkstra(W, s, adj)
+            oracle.dijkstra(W, t, adj)
+            extra["cpu_three_dijkstra_python_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            scipy.sparse.csgraph.dijkstra(scipy.sparse.csr_matrix(W), directed=False, return_predecessors=True)
+            extra["cpu_apsp_scipy_dijkstra_s"] = time.perf_counter() - t0
             # the reference's get_paths on the same cost matrix through the pruned-equivalent
             # oracle, in a child process under a wall-clock cap (it is exponential; the literal
             # frontier loop would not finish at all -- BASELINE.md section 3)

@@ -536,3 +536,13 @@ def test_sharded_apsp_protocol(ctx, world):
     got = torch.cat([sh.local_rows() for sh in ranks]).cpu().numpy().astype(np.float64)
     assert got.shape == (n, n)
     assert np.array_equal(got, want)
+
+
+def test_get_paths_fp32_apsp_bounds(ctx):
+    """FP32 APSP is only used for pruning bounds: the enumerated set stays exact."""
+    W = synth.random_cost_matrix(80, seed=123, density=0.1, lo=0.05, hi=0.9)
+    for s, t, K in [(3, 70, 25), (10, 11, 40)]:
+        want = oracle.get_paths_pruned(W, [s], [t], K)
+        got = ctx.get_paths(W, [s], [t], K, apsp_fp32=True)
+        assert [p[1:] for p in got] == [[int(x) for x in p[1:]] for p in want]
+        assert [p[0] for p in got] == [float(p[0]) for p in want]

@@ -431,7 +431,9 @@ extern "C" int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sou
             P.adj_ptr = (const int32_t*)d_adj_ptr; P.adj_idx = (const int32_t*)d_adj_idx;
             P.adj_w = (const double*)d_adj_w; P.dist = (const double*)d_dist;
             P.pairs = (const int32_t*)d_pairs; P.N = N; P.cutoff = pass_cutoff;
-            P.bound = pass_cutoff + 1e-9 * std::max(1.0, std::fabs(pass_cutoff));
+            // admissible bound: APSP distances are only bounds (summation order / FP32 mode), so
+            // leave slack; the exact float64 left-to-right length decides membership
+            P.bound = pass_cutoff + (g->precision == 32 ? 2e-5 : 1e-9) * std::max(1.0, std::fabs(pass_cutoff));
             P.quirk = quirk;
             P.count_only = count_only ? 1 : 0;
             P.cap = cap;
