@@ -333,6 +333,13 @@ fw32_phase1_kernel(float* __restrict__ dist, int64_t ld, int kb) {
     for (int a = 0; a < 4; ++a)
         for (int b = 0; b < 4; ++b) d[(4 * ty + a) * (kT + 1) + tx + 32 * b] = dist[base + (4 * ty + a) * ld + tx + 32 * b];
     __syncthreads();
+    // own 16 elements live in registers; shared memory is only the exchange medium for row k /
+    // column k, written when an element improves (row k / column k are fixed points of step k)
+    float own[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) own[a][b] = d[(4 * ty + a) * (kT + 1) + tx + 32 * b];
     for (int k = 0; k < kT; ++k) {
         float rk[4], ck[4];
 #pragma unroll
@@ -344,13 +351,12 @@ fw32_phase1_kernel(float* __restrict__ dist, int64_t ld, int kb) {
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const float cand = ck[a] + rk[b];
-                float* p = &d[(4 * ty + a) * (kT + 1) + tx + 32 * b];
-                if (cand < *p) *p = cand;
+                if (cand < own[a][b]) { own[a][b] = cand; d[(4 * ty + a) * (kT + 1) + tx + 32 * b] = cand; }
             }
         __syncthreads();
     }
     for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b) dist[base + (4 * ty + a) * ld + tx + 32 * b] = d[(4 * ty + a) * (kT + 1) + tx + 32 * b];
+        for (int b = 0; b < 4; ++b) dist[base + (4 * ty + a) * ld + tx + 32 * b] = own[a][b];
 }
 
 // phase 2: pivot row tiles (blockIdx.y == 0, inside the row panel) and pivot column tiles
@@ -377,6 +383,11 @@ fw32_phase2_kernel(float* __restrict__ local, int64_t ld, float* __restrict__ pa
             ow[i * (kT + 1) + j] = obase[i * ldo + j];
         }
     __syncthreads();
+    float own[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) own[a][b] = ow[(4 * ty + a) * (kT + 1) + tx + 32 * b];
     for (int k = 0; k < kT; ++k) {
         float rk[4], ck[4];
         if (is_row) {      // own = (kb, other): d[i][j] <- pivot[i][k] + own[k][j]
@@ -390,21 +401,21 @@ fw32_phase2_kernel(float* __restrict__ local, int64_t ld, float* __restrict__ pa
 #pragma unroll
             for (int a = 0; a < 4; ++a) ck[a] = ow[(4 * ty + a) * (kT + 1) + k];
         }
-        __syncthreads();   // own row k / column k may be rewritten below by their owners
+        // (row k / column k of the own tile are fixed points of step k: pivot[k][k] == 0, so no
+        //  barrier is needed between these reads and the writes below)
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const float cand = ck[a] + rk[b];
-                float* p = &ow[(4 * ty + a) * (kT + 1) + tx + 32 * b];
-                if (cand < *p) *p = cand;
+                if (cand < own[a][b]) { own[a][b] = cand; ow[(4 * ty + a) * (kT + 1) + tx + 32 * b] = cand; }
             }
         __syncthreads();
     }
     for (int a = 0; a < 4; ++a)
         for (int b = 0; b < 4; ++b) {
             const int i = 4 * ty + a, j = tx + 32 * b;
-            obase[i * ldo + j] = ow[i * (kT + 1) + j];
+            obase[i * ldo + j] = own[a][b];
         }
 }
 
