@@ -377,6 +377,19 @@ def main():
         h_coords = torch.empty((T_local, A, 3), dtype=torch.float32, pin_memory=True)
         h_coords.copy_(d_coords)
         torch.cuda.synchronize()
+        # raw pinned H2D bandwidth of this box: the e2e pass can not beat h2d_bytes / this
+        nprobe = min(T_local, max(1, (2 << 30) // (A * 12)))
+        probe = torch.empty((nprobe, A, 3), dtype=torch.float32, device=dev)
+        probe.copy_(h_coords[:nprobe], non_blocking=True)
+        torch.cuda.synchronize()
+        pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pa.record()
+        for _ in range(3):
+            probe.copy_(h_coords[:nprobe], non_blocking=True)
+        pb.record()
+        torch.cuda.synchronize()
+        h2d_gbs = 3 * nprobe * A * 12 / (pa.elapsed_time(pb) * 1e-3) / 1e9
+        del probe
         run_e2e = pipe.run_host_streamed if args.e2e_mode == "streamed" else pipe.run_host
         for _ in range(max(1, args.warmup - 1)):
             run_e2e(h_coords)
@@ -393,6 +406,8 @@ def main():
         e2e = {"value": float(N) * N * T / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                "wall_ms_per_step": wall_ms, "h2d_bytes_per_step": pipe.h2d_bytes() * world,
                "d2h_bytes_per_step": pipe.d2h_bytes(), "numa_node_rank0": numa_node,
+               "pcie_h2d_gbs_measured": h2d_gbs,
+               "frac_of_pcie_bound": (pipe.h2d_bytes() / (h2d_gbs * 1e9)) / (ms_e2e * 1e-3),
                "api": "FramePipeline.%s (C-ABI wisp_dev_* calls; pinned host coords in, "
                       "corr/avgdist/binary/w on the host out)" % run_e2e.__name__}
         del h_coords
