@@ -40,6 +40,10 @@ int64_t     wisp_frames_pad(int64_t n_frames);/* rows of the device node traject
 int64_t     wisp_gram_ld(int n_cols);         /* leading dimension of Gram / sum buffers  */
 /* number of launches of this library's kernels since the context was created */
 int64_t     wisp_kernel_launches(wisp_ctx* ctx);
+/* K2 engine for the node Gram: 0 = auto (INT8 tensor cores from 4096 frames up, guarded by an
+ * on-device accuracy bound with DMMA fallback), 1 = always the FP64 DMMA kernel, 2 = INT8
+ * whenever the bound holds.  Initial value: $WISP_K2_MODE = auto | dmma | i8. */
+int         wisp_set_gram_mode(wisp_ctx* ctx, int mode);
 
 /* ---- host-buffer entry points (what the reference-facing Python modules call) ------- */
 
@@ -172,6 +176,10 @@ int wisp_dev_colsum(wisp_ctx* ctx, const double* d_nodes, int64_t T, int N, doub
  * [n_out_pad][n_out_pad] with n_out_pad = wisp_gram_ld(n_out); overwritten. */
 int wisp_dev_gram(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_out,
                   int stride, double* d_out, void* stream);
+/* K2 on the INT8 tensor cores (tcgen05, exact byte-plane slicing, FP64-grade result; see
+ * csrc/k2_gram_i8.cu): same node Gram as wisp_dev_gram(stride 3).  Same output layout. */
+int wisp_dev_gram_i8(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int N,
+                     double* d_out, void* stream);
 /* K3: D[i][j] = sum_t |x_i(t) - x_j(t)| for i<=j tiles; d_p32 is the FP32 copy written by
  * wisp_dev_center and d_mean [ld] the mean used there.  d_out [Npad][Npad] overwritten. */
 int wisp_dev_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N,

@@ -30,6 +30,7 @@ SIGNATURES = {
     "wisp_frames_pad": (_i64, [_i64]),
     "wisp_gram_ld": (_i64, [_int]),
     "wisp_kernel_launches": (_i64, [_c_ctx]),
+    "wisp_set_gram_mode": (_int, [_c_ctx, _int]),
     "wisp_com_nodes": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P, _int, _P, _int, _int, _P, _P]),
     "wisp_traj_alignment_and_averaging": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P, _int, _P, _int,
                                                  _int, _dbl, _int, _P, _P, _P, C.POINTER(_int)]),
@@ -58,6 +59,7 @@ SIGNATURES = {
     "wisp_dev_center": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P]),
     "wisp_dev_colsum": (_int, [_c_ctx, _P, _i64, _int, _P, _P]),
     "wisp_dev_gram": (_int, [_c_ctx, _P, _i64, _i64, _int, _int, _P, _P]),
+    "wisp_dev_gram_i8": (_int, [_c_ctx, _P, _i64, _i64, _int, _P, _P]),
     "wisp_dev_contact_sum": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P]),
     "wisp_dev_epilogue": (_int, [_c_ctx, _P, _P, _i64, _int, _dbl, _int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "wisp_dev_reduce_partials": (_int, [_c_ctx, _P, _int, _int, _P, _P]),
@@ -144,6 +146,10 @@ class Context:
 
     def kernel_launches(self):
         return int(self._lib.wisp_kernel_launches(self._ctx))
+
+    def set_gram_mode(self, mode):
+        """K2 engine: 'auto' | 'dmma' | 'i8' (see include/wisp_b200.h)."""
+        self._check(self._lib.wisp_set_gram_mode(self._ctx, {"auto": 0, "dmma": 1, "i8": 2}[mode]))
 
     def sync(self):
         self._check(self._lib.wisp_sync(self._ctx))
@@ -351,6 +357,9 @@ class Context:
     def dev_gram(self, d_x, T, ld, n_out, stride, d_out, stream=None):
         self._check(self._lib.wisp_dev_gram(self._ctx, _ptr(d_x), T, ld, n_out, stride, _ptr(d_out),
                                             _ptr(stream)))
+
+    def dev_gram_i8(self, d_x, T, ld, N, d_out, stream=None):
+        self._check(self._lib.wisp_dev_gram_i8(self._ctx, _ptr(d_x), T, ld, N, _ptr(d_out), _ptr(stream)))
 
     def dev_contact_sum(self, d_p32, T, N, d_mean, d_out, stream=None):
         self._check(self._lib.wisp_dev_contact_sum(self._ctx, _ptr(d_p32), T, N, _ptr(d_mean),

@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 // ---------------------------------------------------------------------------------------
 // errors / context / scratch
@@ -62,6 +64,20 @@ extern "C" int wisp_sync(wisp_ctx* ctx) {
     WISP_CHECK(ctx, "sync: null context");
     WISP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     WISP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int wisp_gram_mode(wisp_ctx* ctx) {
+    if (ctx->gram_mode < 0) {
+        const char* e = getenv("WISP_K2_MODE");
+        ctx->gram_mode = !e ? WISP_GRAM_AUTO : !strcmp(e, "dmma") ? WISP_GRAM_DMMA : !strcmp(e, "i8") ? WISP_GRAM_I8 : WISP_GRAM_AUTO;
+    }
+    return ctx->gram_mode;
+}
+
+extern "C" int wisp_set_gram_mode(wisp_ctx* ctx, int mode) {
+    WISP_CHECK(ctx && mode >= 0 && mode <= 2, "set_gram_mode: mode must be 0 (auto), 1 (dmma) or 2 (i8)");
+    ctx->gram_mode = mode;
     return 0;
 }
 
@@ -535,6 +551,12 @@ extern "C" int wisp_dev_gram(wisp_ctx* ctx, const double* d_x, int64_t T, int64_
                              int stride, double* d_out, void* stream) {
     WISP_CHECK(ctx && d_x && d_out, "dev_gram: null argument");
     return launch_gram(ctx, d_x, T, ld, n_out, stride, d_out, wisp_stream(ctx, stream));
+}
+
+extern "C" int wisp_dev_gram_i8(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int N,
+                                double* d_out, void* stream) {
+    WISP_CHECK(ctx && d_x && d_out, "dev_gram_i8: null argument");
+    return launch_gram_i8(ctx, d_x, T, ld, N, d_out, wisp_stream(ctx, stream), nullptr);
 }
 
 extern "C" int wisp_dev_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N,

@@ -62,8 +62,9 @@ struct wisp_ctx {
     cudaStream_t stream = nullptr;   // compute
     cudaStream_t copy_stream = nullptr;
     int64_t launches = 0;
+    int gram_mode = -1;              // WISP_GRAM_*; -1 = read $WISP_K2_MODE on first use
     // grow-only scratch buffers, keyed by slot
-    DevBuf scratch[24];
+    DevBuf scratch[32];
     // get_paths results
     std::vector<double> path_len;
     std::vector<int64_t> path_off;
@@ -82,7 +83,7 @@ enum ScratchSlot {
     SCR_GRAM_PART = 0, SCR_CONTACT_PART, SCR_COLSUM_PART, SCR_X, SCR_COORDS0, SCR_COORDS1,
     SCR_APSP_D, SCR_APSP_P, SCR_ARENA, SCR_ALIGN, SCR_P32,
     SCR_MISC0, SCR_MISC1, SCR_MISC2, SCR_MISC3, SCR_MISC4, SCR_MISC5, SCR_MISC6, SCR_MISC7,
-    SCR_MISC8, SCR_MISC9, SCR_COUNT
+    SCR_MISC8, SCR_MISC9, SCR_I8_PLANES, SCR_I8_SMALL, SCR_I8_PART, SCR_COUNT
 };
 
 // ---- kernel launchers (one per .cu) -------------------------------------------------------
@@ -110,8 +111,18 @@ int launch_center(wisp_ctx* ctx, double* d_x, int64_t T, int64_t ld, int64_t nco
                   const double* d_mean, cudaStream_t st, float* d_p32 = nullptr, int N = 0);
 int launch_gram(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_out, int stride,
                 double* d_out, cudaStream_t st);
+int launch_gram_dmma(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_out, int stride,
+                     double* d_out, cudaStream_t st, const int* gate, int gate_want);
+// *gate_out (device int, valid until the next call): 0 = the INT8 result stands, 1 = accuracy
+// bound not met for this data and nothing was written.  gate_out == NULL: no bound check.
+int launch_gram_i8(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int N, double* d_out,
+                   cudaStream_t st, const int** gate_out);
+enum { WISP_GRAM_AUTO = 0, WISP_GRAM_DMMA = 1, WISP_GRAM_I8 = 2 };
+constexpr int64_t kGramI8AutoRows = 12288;      // auto mode: INT8 path from 4096 frames up
+int wisp_gram_mode(wisp_ctx* ctx);
 int launch_reduce_partials(wisp_ctx* ctx, const double* part, int n_seg, int64_t n_pad,
-                           double* out, int tile_r, int tile_c, cudaStream_t st);
+                           double* out, int tile_r, int tile_c, cudaStream_t st,
+                           const int* gate = nullptr, int gate_want = 0);
 int wisp_pick_segments(int items_per_seg, int stages_total, int sm_count, int min_stages);
 int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, const double* d_mean,
                        double* d_out, cudaStream_t st);

@@ -89,8 +89,10 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 template <int STRIDE>
 __global__ void __launch_bounds__(kThreads, 1)
 gram_dmma_kernel(const double* __restrict__ x, int64_t ld, int n_tiles, int stages_total,
-                 int n_seg, double* __restrict__ out, int64_t out_ld) {
+                 int n_seg, double* __restrict__ out, int64_t out_ld, const int* __restrict__ gate,
+                 int gate_want) {
     using Cfg = GramCfg<STRIDE>;
+    if (gate && *gate != gate_want) return;      // the INT8 path already produced this Gram
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_base = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * Cfg::kStageBytes);
@@ -200,7 +202,9 @@ gram_dmma_kernel(const double* __restrict__ x, int64_t ld, int n_tiles, int stag
 
 // out[r][c] = sum_s part[s][r][c] for upper tiles (fixed order -> deterministic)
 __global__ void reduce_partials_kernel(const double* __restrict__ part, int n_seg, int64_t n_pad,
-                                       double* __restrict__ out, int tile_r, int tile_c) {
+                                       double* __restrict__ out, int tile_r, int tile_c,
+                                       const int* __restrict__ gate, int gate_want) {
+    if (gate && *gate != gate_want) return;
     const int64_t total = n_pad * n_pad;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (int64_t)gridDim.x * blockDim.x) {
@@ -234,18 +238,19 @@ int wisp_pick_segments(int items_per_seg, int stages_total, int sm_count, int mi
 }
 
 int launch_reduce_partials(wisp_ctx* ctx, const double* part, int n_seg, int64_t n_pad,
-                           double* out, int tile_r, int tile_c, cudaStream_t st) {
+                           double* out, int tile_r, int tile_c, cudaStream_t st, const int* gate,
+                           int gate_want) {
     const int threads = 256;
     int blocks = (int)std::min<int64_t>((n_pad * n_pad + threads - 1) / threads,
                                         (int64_t)ctx->sm_count * 16);
-    reduce_partials_kernel<<<blocks, threads, 0, st>>>(part, n_seg, n_pad, out, tile_r, tile_c);
+    reduce_partials_kernel<<<blocks, threads, 0, st>>>(part, n_seg, n_pad, out, tile_r, tile_c, gate, gate_want);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_gram(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_out, int stride,
-                double* d_out, cudaStream_t st) {
+int launch_gram_dmma(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_out, int stride,
+                     double* d_out, cudaStream_t st, const int* gate, int gate_want) {
     WISP_CHECK(stride == 1 || stride == 3, "gram: stride must be 1 or 3 (got %d)", stride);
     WISP_CHECK(T > 0 && n_out > 0, "gram: empty input (T=%lld, n=%d)", (long long)T, n_out);
     const int n_tiles = (int)((n_out + kTile - 1) / kTile);
@@ -270,16 +275,33 @@ int launch_gram(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_o
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        GramCfg<3>::kSmemBytes));
         gram_dmma_kernel<3><<<grid, kThreads, GramCfg<3>::kSmemBytes, st>>>(
-            d_x, ld, n_tiles, stages_total, n_seg, part, n_pad);
+            d_x, ld, n_tiles, stages_total, n_seg, part, n_pad, gate, gate_want);
     } else {
         WISP_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<1>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        GramCfg<1>::kSmemBytes));
         gram_dmma_kernel<1><<<grid, kThreads, GramCfg<1>::kSmemBytes, st>>>(
-            d_x, ld, n_tiles, stages_total, n_seg, part, n_pad);
+            d_x, ld, n_tiles, stages_total, n_seg, part, n_pad, gate, gate_want);
     }
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
-    if (n_seg > 1) WISP_TRY(launch_reduce_partials(ctx, part, n_seg, n_pad, d_out, kTile, kTile, st));
+    if (n_seg > 1)
+        WISP_TRY(launch_reduce_partials(ctx, part, n_seg, n_pad, d_out, kTile, kTile, st, gate, gate_want));
     return 0;
+}
+
+// K2 dispatcher.  Node Gram (stride 3): long trajectories go to the INT8 tensor-core kernel
+// (k2_gram_i8.cu); it leaves a device-side gate saying whether its accuracy bound held for this
+// data, and the DMMA kernel below is launched behind the same gate, so the fallback costs one
+// empty launch and no host synchronisation.  Short trajectories, the full 3N x 3N covariance
+// (stride 1) and WISP_K2_MODE=dmma use the FP64 tensor pipe directly.
+int launch_gram(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_out, int stride,
+                double* d_out, cudaStream_t st) {
+    const int mode = wisp_gram_mode(ctx);
+    const bool use_i8 = stride == 3 && mode != WISP_GRAM_DMMA && T > 0 && n_out > 0 &&
+                        (mode == WISP_GRAM_I8 || 3 * T >= kGramI8AutoRows);
+    if (!use_i8) return launch_gram_dmma(ctx, d_x, T, ld, n_out, stride, d_out, st, nullptr, 0);
+    const int* gate = nullptr;
+    WISP_TRY(launch_gram_i8(ctx, d_x, T, ld, n_out, d_out, st, &gate));
+    return launch_gram_dmma(ctx, d_x, T, ld, n_out, stride, d_out, st, gate, 1);
 }
