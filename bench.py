@@ -37,7 +37,9 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            peaks["hbm_gbs"] = float(json.load(open(p))["hbm_gbs"])
+            mp = json.load(open(p))
+            peaks["hbm_gbs"] = float(mp["hbm_gbs"])
+            peaks["bf16_tflops"] = float(mp.get("bf16_tflops", 1633.1))
             peaks["source_hbm"] = "MEASURED_PEAKS.json"
         except Exception:
             pass
@@ -325,29 +327,48 @@ def main():
     # order matters: K1 rewrites X (un-centred); mean_and_center centres it in place again
     k1_ms = time_stage(lambda: pipe.com(d_coords), reps)
     pipe.mean_and_center()
-    k2_ms = time_stage(pipe.gram, reps)
+    k2_ms = time_stage(pipe.gram, reps)                       # K2 as the step runs it (auto engine)
+    g_auto = pipe.d_sums[0].clone()
+    ctx.set_gram_mode("dmma")
+    k2_dmma_ms = time_stage(pipe.gram, reps)                  # FP64 DMMA engine, for comparison
+    k2_engine = "fp64 dmma" if torch.equal(g_auto, pipe.d_sums[0]) else "int8 tcgen05"
+    k2_i8_vs_dmma = float(((g_auto - pipe.d_sums[0]).abs().triu() /
+                           torch.sqrt(torch.outer(pipe.d_sums[0].diagonal(), pipe.d_sums[0].diagonal())).clamp_min(1e-300)).max())
+    ctx.set_gram_mode("auto")
+    pipe.gram()
+    del g_auto
     k3_ms = time_stage(pipe.contact, reps)
     k4_ms = time_stage(pipe.reduce_and_epilogue, reps)
     clocks = sampler.stop() if rank == 0 else None
     work = pipe.work()
     peaks = load_peaks()
     k2_tflops = work["k2_flop_executed"] / (k2_ms * 1e-3) / 1e12
+    k2_dmma_tflops = work["k2_flop_executed"] / (k2_dmma_ms * 1e-3) / 1e12
+    # INT8 engine: 10 digit-pair MMAs per FP64 product
+    k2_int8_tops = 10.0 * k2_tflops if k2_engine == "int8 tcgen05" else 0.0
+    int8_peak = 2.0 * peaks.get("bf16_tflops", 1633.1)        # dense INT8 = 2 x dense bf16 (MEASURED_PEAKS.json)
     k3_rate = work["k3_pairframes_executed"] / (k3_ms * 1e-3)
     k1_gbs = work["k1_bytes"] / (k1_ms * 1e-3) / 1e9
     kernels = {
         "k1_com": {"ms": k1_ms, "bound": "hbm", "achieved_gbs": k1_gbs, "peak_gbs": peaks["hbm_gbs"],
                    "frac": k1_gbs / peaks["hbm_gbs"]},
-        "k2_gram_dmma": {"ms": k2_ms, "bound": "tensor(fp64)", "achieved_tflops": k2_tflops,
+        "k2_gram": {"ms": k2_ms, "engine": k2_engine, "fp64_equivalent_tflops": k2_tflops,
+                    "int8_tops_executed": k2_int8_tops, "int8_peak_tops": int8_peak,
+                    "frac_int8": k2_int8_tops / int8_peak,
+                    "max_abs_dev_vs_dmma_rel_sqrt_GiiGjj": k2_i8_vs_dmma,
+                    "note": "ms covers the whole K2 stage: node statistics, digit planes, tcgen05 Gram, "
+                            "partial reduce, plus the gated (empty) DMMA launch"},
+        "k2_gram_dmma": {"ms": k2_dmma_ms, "bound": "tensor(fp64)", "achieved_tflops": k2_dmma_tflops,
                          "peak_tflops": peaks["fp64_dmma_tflops"],
-                         "frac": k2_tflops / peaks["fp64_dmma_tflops"],
-                         "frac_of_cublas_dgemm": k2_tflops / peaks["cublas_dgemm_tflops"]},
+                         "frac": k2_dmma_tflops / peaks["fp64_dmma_tflops"],
+                         "frac_of_cublas_dgemm": k2_dmma_tflops / peaks["cublas_dgemm_tflops"]},
         "k3_contact": {"ms": k3_ms, "bound": "mufu/fp32", "achieved_tpairframes": k3_rate / 1e12,
                        "mufu_peak_tops": peaks["mufu_sqrt_tops"],
                        "frac_mufu": k3_rate / 1e12 / peaks["mufu_sqrt_tops"],
                        "fp32_flop_frac": 8 * k3_rate / 1e12 / peaks["fp32_fma_tflops"]},
         "k4_epilogue_allreduce": {"ms": k4_ms},
     }
-    dominant = "k2_gram_dmma" if k2_ms >= k3_ms else "k3_contact"
+    dominant = "k2_gram_dmma" if (k2_ms >= k3_ms and k2_engine == "fp64 dmma") else "k3_contact"
     if dominant == "k2_gram_dmma":
         roofline = {"kernel": "gram_dmma_kernel<3>", "bound": "tensor", "achieved": k2_tflops,
                     "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
@@ -361,13 +382,19 @@ def main():
                     "traffic": None,
                     "peak_source": "MUFU.SQRT issue peak measured with tools/peaks.cu (1 sqrt per pair-frame)"}
 
-    roofline_tensor = {"kernel": "gram_dmma_kernel<3>", "bound": "tensor", "achieved": k2_tflops,
-                       "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
-                       "frac": k2_tflops / peaks["fp64_dmma_tflops"], "traffic": None}
+    if k2_engine == "int8 tcgen05":
+        roofline_tensor = {"kernel": "gram_i8_kernel", "bound": "tensor", "achieved": k2_int8_tops, "peak": int8_peak,
+                           "unit": "TOP/s", "frac": k2_int8_tops / int8_peak, "traffic": None,
+                           "peak_source": "2 x MEASURED_PEAKS.json dense bf16 (INT8 is twice bf16 on tcgen05); "
+                                          "achieved counts the whole K2 stage time, not the MMA kernel alone"}
+    else:
+        roofline_tensor = {"kernel": "gram_dmma_kernel<3>", "bound": "tensor", "achieved": k2_tflops,
+                           "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
+                           "frac": k2_tflops / peaks["fp64_dmma_tflops"], "traffic": None}
     try:
         ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
         roofline["traffic"] = ncu.get(roofline["kernel"].split("<")[0])
-        roofline_tensor["traffic"] = ncu.get("gram_dmma_kernel")
+        roofline_tensor["traffic"] = ncu.get(roofline_tensor["kernel"].split("<")[0])
     except Exception:
         pass
 
@@ -541,6 +568,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "dtype_note": "results float64; K2 products as exact INT8 digit planes on tcgen05 with FP64 combine "
+                              "(accuracy-gated, DMMA FP64 fallback), K3 per-frame distances FP32 with FP64 sums",
                 "config": workload_config(args), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
                 "roofline": roofline, "roofline_tensor": roofline_tensor, "kernels": kernels, "cpu_baseline": cpu_baseline, "extra": extra}

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 

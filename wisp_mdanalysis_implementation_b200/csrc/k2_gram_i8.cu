@@ -264,36 +264,40 @@ __global__ void node_scale_kernel(const unsigned long long* __restrict__ absmax_
 }
 // X (float64 [T][ld]) -> four planes of BALANCED base-256 digits [4][rows_total][n_pad] (int8),
 // row = 3*frame + c, node contiguous:  rint(x * scale) = d0 2^24 + d1 2^16 + d2 2^8 + d3, d in [-128, 127]
-__global__ void slice_planes_kernel(const double* __restrict__ x, int64_t T, int64_t ld, int n_pad,
-                                    const double* __restrict__ scale, int rows_total,
-                                    unsigned char* __restrict__ planes, const int* __restrict__ unsafe) {
-    __shared__ uint32_t v_s[3][kTile];
+constexpr int kSliceFrames = 4;     // frames per block (threadIdx.z)
+
+// block (32, 3, kSliceFrames): lane = 4 consecutive nodes, y = component, z = frame.  The three
+// component warps of a frame read the same 3 KB of the row (stride-3 picks, served by L1); every
+// warp writes one full 128-byte row per plane.  No shared memory, no barriers.
+__global__ void __launch_bounds__(96 * kSliceFrames)
+slice_planes_kernel(const double* __restrict__ x, int64_t T, int64_t ld, int n_pad,
+                    const double* __restrict__ scale, int rows_total,
+                    unsigned char* __restrict__ planes, const int* __restrict__ unsafe) {
     if (*unsafe) return;
     const int tile = blockIdx.x;
-    const int k = threadIdx.x;                      // 0..383: column inside the tile-frame
-    const int c = k % 3, n = k / 3;
-    const double sc = scale[tile * kTile + n];
-    for (int64_t t = blockIdx.y; t < T; t += gridDim.y) {
-        const double xv = x[t * ld + (int64_t)3 * kTile * tile + k];
-        int32_t v = __double2int_rn(xv * sc);
-        const int32_t d3 = (int32_t)(int8_t)(v & 255); v = (v - d3) >> 8;
-        const int32_t d2 = (int32_t)(int8_t)(v & 255); v = (v - d2) >> 8;
-        const int32_t d1 = (int32_t)(int8_t)(v & 255); v = (v - d1) >> 8;      // v is now d0
-        v_s[c][n] = ((uint32_t)v & 255u) | (((uint32_t)d1 & 255u) << 8) | (((uint32_t)d2 & 255u) << 16) | (((uint32_t)d3 & 255u) << 24);
-        __syncthreads();
-        if (k < 3 * (kTile / 4)) {                  // 96 threads: 4 nodes of one component, all planes
-            const int cc = k / (kTile / 4), n4 = (k % (kTile / 4)) * 4;
-            const uint32_t a = v_s[cc][n4], b = v_s[cc][n4 + 1], d = v_s[cc][n4 + 2], f = v_s[cc][n4 + 3];
-            const int64_t row = 3 * t + cc;
+    const int w = threadIdx.x, c = threadIdx.y;
+    const int n0 = tile * kTile + 4 * w;
+    double sc[4];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const int sh = 8 * p;
-                const uint32_t packed = ((a >> sh) & 255u) | (((b >> sh) & 255u) << 8) |
-                                        (((d >> sh) & 255u) << 16) | (((f >> sh) & 255u) << 24);
-                *reinterpret_cast<uint32_t*>(planes + ((int64_t)p * rows_total + row) * n_pad + tile * kTile + n4) = packed;
-            }
+    for (int j = 0; j < 4; ++j) sc[j] = scale[n0 + j];
+    const double* xcol = x + 3 * (int64_t)n0 + c;
+    for (int64_t t = (int64_t)blockIdx.y * kSliceFrames + threadIdx.z; t < T; t += (int64_t)gridDim.y * kSliceFrames) {
+        uint32_t word[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int32_t v = __double2int_rn(xcol[t * ld + 3 * j] * sc[j]);
+            const int32_t d3 = (int32_t)(int8_t)(v & 255); v = (v - d3) >> 8;
+            const int32_t d2 = (int32_t)(int8_t)(v & 255); v = (v - d2) >> 8;
+            const int32_t d1 = (int32_t)(int8_t)(v & 255); v = (v - d1) >> 8;      // v is now d0
+            word[0] |= ((uint32_t)v & 255u) << (8 * j);
+            word[1] |= ((uint32_t)d1 & 255u) << (8 * j);
+            word[2] |= ((uint32_t)d2 & 255u) << (8 * j);
+            word[3] |= ((uint32_t)d3 & 255u) << (8 * j);
         }
-        __syncthreads();
+        const int64_t row = 3 * t + c;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+            *reinterpret_cast<uint32_t*>(planes + ((int64_t)p * rows_total + row) * n_pad + n0) = word[p];
     }
 }
 
@@ -342,8 +346,9 @@ int launch_gram_i8(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int 
     const double rho2_min = force_safe ? 0.0 : 1.3 / std::sqrt(3.0 * (double)T);
     node_scale_kernel<<<(n_pad + 127) / 128, 128, 0, st>>>(d_absmax, d_sumsq, gy, n_pad, 3.0 * (double)T, rho2_min,
                                                            d_scale, d_unit, d_diag, d_unsafe);
-    const int gy2 = (int)std::min<int64_t>(T, std::max<int64_t>(1, (int64_t)ctx->sm_count * 8 / n_tiles));
-    slice_planes_kernel<<<dim3(n_tiles, gy2), 384, 0, st>>>(d_x, T, ld, n_pad, d_scale, rows_total, planes, d_unsafe);
+    const int gy2 = (int)std::min<int64_t>((T + kSliceFrames - 1) / kSliceFrames,
+                                           std::max<int64_t>(1, (int64_t)ctx->sm_count * 16 / n_tiles));
+    slice_planes_kernel<<<dim3(n_tiles, gy2), dim3(32, 3, kSliceFrames), 0, st>>>(d_x, T, ld, n_pad, d_scale, rows_total, planes, d_unsafe);
     ctx->launches += 3;
     WISP_CUDA(cudaGetLastError());
 
