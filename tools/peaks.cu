@@ -71,31 +71,37 @@ __global__ void ffma2_peak(float* out, int iters) {
     for (int i = 0; i < 16; ++i) s ^= c[i];
     if (s == 123456ull) out[0] = 1.f;
 }
-// 1 MUFU.SQRT + 3.5 packed FP32 instructions per element: the K3 inner-loop mix
+// the K3 inner-loop mix, register-resident: per PACKED pair 3 sub2 + mul2 + 2 fma2 + add2 and
+// 2 MUFU.SQRT (= 3.5 FP32-pipe instructions + 1 MUFU per pair-frame).  The running sum feeds
+// the next iteration's subtraction so nothing is loop-invariant.
 __global__ void k3mix_peak(float* out, int iters) {
-    unsigned long long c[8], d[8];
+    unsigned long long acc[8];
     float x = 1.0f + threadIdx.x;
-    for (int i = 0; i < 8; ++i) { asm("mov.b64 %0, {%1,%1};" : "=l"(c[i]) : "f"(x + i)); d[i] = c[i]; }
-    unsigned long long a;
+    for (int i = 0; i < 8; ++i) asm("mov.b64 %0, {%1,%1};" : "=l"(acc[i]) : "f"(x + i));
+    unsigned long long a, b, c;
     asm("mov.b64 %0, {%1,%1};" : "=l"(a) : "f"(0.999f));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(b) : "f"(1.5f));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(c) : "f"(-0.25f));
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            unsigned long long t;
-            asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(c[i]), "l"(a));
-            asm volatile("mul.rn.f32x2 %0, %0, %0;" : "+l"(t));
-            asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(t) : "l"(a));
-            asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(t) : "l"(c[i]));
+            unsigned long long dx, dy, dz, t;
+            asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(acc[i]), "l"(a));
+            asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(acc[i]), "l"(b));
+            asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(acc[i]), "l"(c));
+            asm volatile("mul.rn.f32x2 %0, %1, %1;" : "=l"(t) : "l"(dx));
+            asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(t) : "l"(dy));
+            asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(t) : "l"(dz));
             float lo, hi;
             asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(t));
             asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(lo));
             asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(hi));
             asm("mov.b64 %0, {%1,%2};" : "=l"(t) : "f"(lo), "f"(hi));
-            asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(d[i]) : "l"(t));
+            asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(acc[i]) : "l"(t));
         }
     }
     unsigned long long s = 0;
-    for (int i = 0; i < 8; ++i) s ^= d[i];
+    for (int i = 0; i < 8; ++i) s ^= acc[i];
     if (s == 123456ull) out[0] = 1.f;
 }
 // FADD + FMNMX mix (min-plus relaxation without predecessors)
@@ -176,6 +182,11 @@ int main() {
     const double ffma2_tf = lanes * it * 16 * 4.0 / (t * 1e-3) / 1e12;
     t = best_ms([&] { k3mix_peak<<<blocks, threads>>>((float*)buf, it); });
     const double k3mix_tpf = lanes * it * 16.0 / (t * 1e-3) / 1e12;
+    // the same mix at the occupancy K3 really runs at (2 warps per scheduler) and at 4
+    t = best_ms([&] { k3mix_peak<<<sms, 256>>>((float*)buf, it); });
+    const double k3mix_occ2 = (double)sms * 256 * it * 16.0 / (t * 1e-3) / 1e12;
+    t = best_ms([&] { k3mix_peak<<<sms, 512>>>((float*)buf, it); });
+    const double k3mix_occ4 = (double)sms * 512 * it * 16.0 / (t * 1e-3) / 1e12;
     t = best_ms([&] { fmnmx_peak<<<blocks, threads>>>((float*)buf, it); });
     const double fmnmx_tops = lanes * it * 16.0 / (t * 1e-3) / 1e12;
     t = best_ms([&] { fmnmx3_peak<<<blocks, threads>>>((float*)buf, it); });
@@ -185,7 +196,7 @@ int main() {
     CK(cudaDeviceSynchronize());
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"fp64_dmma_tflops\": %.2f, \"fp64_fma_tflops\": %.2f, "
            "\"fp32_fma_tflops\": %.2f, \"mufu_sqrt_tops\": %.3f, \"fp32_minplus_trelax\": %.3f, \"fp32_ffma2_tflops\": %.2f, "
-           "\"k3_mix_tpairframes\": %.3f, \"fmnmx_tops\": %.3f, \"fmnmx3_tops\": %.3f}\n",
-           p.name, sms, dmma_tf, dfma_tf, ffma_tf, mufu_tops, minplus_trelax, ffma2_tf, k3mix_tpf, fmnmx_tops, fmnmx3_tops);
+           "\"k3_mix_tpairframes\": %.3f, \"k3_mix_2warps_per_sched\": %.3f, \"k3_mix_4warps_per_sched\": %.3f, \"fmnmx_tops\": %.3f, \"fmnmx3_tops\": %.3f}\n",
+           p.name, sms, dmma_tf, dfma_tf, ffma_tf, mufu_tops, minplus_trelax, ffma2_tf, k3mix_tpf, k3mix_occ2, k3mix_occ4, fmnmx_tops, fmnmx3_tops);
     return 0;
 }

@@ -13,17 +13,22 @@
 // distance_array); the reference offset between two tiles is added once per staged j value.
 //
 // One CTA = one 128 x 128 pair tile (upper triangle only) x one frame segment; 512 threads,
-// each owns 8 x 4 pairs.  Frames are staged 8 at a time (float4 loads, double-buffered).
-// Per pair-frame: 3 sub + mul + 2 fma + MUFU.SQRT + add, the FP32 part issued as packed
-// FADD2/FMUL2/FFMA2 over two pairs -- the kernel is bound by the MUFU pipe (16 lanes/clk/SM).  FP32 partial sums are promoted every 64
-// frames into FP64 per-pair totals kept in shared memory (128 KB), written once at the end.
+// each owns 8 x 4 pairs (measured variants: 31.1 ms at C2 against 31.5 ms for 256 threads x
+// 8 x 8 and 32.7 ms with the frame loop unrolled twice).  Frames are staged 8 at a time (float4
+// loads, double-buffered).  Per pair-frame: 3 sub + mul + 2 fma + MUFU.SQRT + add, the FP32
+// part issued as packed FADD2/FMUL2/FFMA2 over two pairs.  The MUFU pipe (16 lanes/clk/SM) is
+// the bound: the same instruction mix held in registers (tools/peaks.cu, k3mix) reaches 92-95 %
+// of the MUFU issue peak with the FP32 pipe at 83 %; this kernel, which also has to feed the
+// operands from shared memory through the same MIO queue the MUFU instructions use, reaches
+// 77 %.  FP32 partial sums are promoted every 128 frames into FP64 per-pair totals kept in
+// shared memory (128 KB), written once at the end.
 #include "common.cuh"
 #include <cstdlib>
 
 namespace {
 
 constexpr int kFC = 8;             // frames per staged chunk
-constexpr int kFlushChunks = 8;    // promote FP32 -> FP64 every 64 frames
+constexpr int kFlushChunks = 16;   // promote FP32 -> FP64 every 128 frames
 constexpr int kTileFloats = 3 * kTile;   // 384 floats per tile-frame
 
 __device__ __forceinline__ float fast_sqrt(float x) {
@@ -71,7 +76,7 @@ struct ContactSmem {
     float sj[2][kFC][3][kTile];
 };
 
-template <int JH>   // packed j pairs per thread: 2 -> 512 threads x (8x4 pairs), 4 -> 256 x (8x8)
+template <int JH, int UNROLL>   // packed j pairs per thread: 2 -> 512 threads x (8x4 pairs), 4 -> 256 x (8x8)
 __global__ void __launch_bounds__(1024 / JH, 1)
 contact_sum_kernel(const float* __restrict__ p32, int64_t T, int N, const double* __restrict__ mean,
                    int n_tiles, int n_seg, double* __restrict__ out, int64_t out_ld) {
@@ -157,7 +162,7 @@ contact_sum_kernel(const float* __restrict__ p32, int64_t T, int N, const double
         const bool has_next = (f0 + kFC) < f_end;
         if (has_next) load_chunk(f0 + kFC, stage);
         const int nf = (int)((f_end - f0) < kFC ? (f_end - f0) : kFC);
-#pragma unroll 2
+#pragma unroll UNROLL
         for (int fl = 0; fl < nf; ++fl) {
             float ax[8], ay[8], az[8];
             f32x2 bx[JH], by[JH], bz[JH];
@@ -256,14 +261,20 @@ int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, cons
     }
     const int smem = (int)sizeof(ContactSmem);
     dim3 grid(n_items, n_seg);
-    static const int variant = getenv("WISP_K3_VARIANT") ? atoi(getenv("WISP_K3_VARIANT")) : 4;
-    if (variant == 2) {
-        WISP_CUDA(cudaFuncSetAttribute(contact_sum_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        contact_sum_kernel<2><<<grid, 512, smem, st>>>(d_p32, T, N, d_mean, n_tiles, n_seg, part, n_pad);
-    } else {
-        WISP_CUDA(cudaFuncSetAttribute(contact_sum_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        contact_sum_kernel<4><<<grid, 256, smem, st>>>(d_p32, T, N, d_mean, n_tiles, n_seg, part, n_pad);
+    static const int variant = getenv("WISP_K3_VARIANT") ? atoi(getenv("WISP_K3_VARIANT")) : 21;
+#define WISP_K3_LAUNCH(JH_, UN_)                                                                          \
+    do {                                                                                                  \
+        WISP_CUDA(cudaFuncSetAttribute(contact_sum_kernel<JH_, UN_>,                                      \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));               \
+        contact_sum_kernel<JH_, UN_><<<grid, 1024 / JH_, smem, st>>>(d_p32, T, N, d_mean, n_tiles, n_seg, \
+                                                                     part, n_pad);                        \
+    } while (0)
+    switch (variant) {
+        case 41: WISP_K3_LAUNCH(4, 1); break;      // 256 threads x (8 x 8 pairs), 246 registers
+        case 42: WISP_K3_LAUNCH(4, 2); break;      // the same, frame loop unrolled twice (253 registers)
+        default: WISP_K3_LAUNCH(2, 1); break;      // 512 threads x (8 x 4 pairs), 124 registers: 4 warps per scheduler
     }
+#undef WISP_K3_LAUNCH
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
     if (n_seg > 1) WISP_TRY(launch_reduce_partials(ctx, part, n_seg, n_pad, d_out, kTile, kTile, st));
