@@ -6,15 +6,17 @@
 // make_node_selections.py:39-58):
 //   align_shift_kernel  one warp per frame gathers the alignment landmarks (a few percent of
 //                       the frame) and writes shift[f] = -COM_align(f)           (:71);
-//   com_stream_kernel   persistent CTAs; the frame is cut into "pieces" (<= 80 consecutive nodes,
+//   com_stream_kernel   persistent CTAs; the frame is cut into "pieces" (<= 128 consecutive nodes,
 //                       <= 2048 atoms); each CTA owns one piece index and walks the
 //                       frames with a 3-stage ring of cp.async.bulk (TMA) copies completed
 //                       on mbarriers, so a whole piece (24 KB) is in flight per stage with
-//                       no registers held; one lane per (node, component) -- 10 nodes per
-//                       warp, no cross-lane reduction -- walks the node's atoms in shared
-//                       memory, applies the float32 translate rounding (Veltkamp split on
-//                       the FP64 pipe), accumulates m*x in FP64 and stores the COM (sum times
-//                       the precomputed 1/M_node), consecutive lanes -> consecutive doubles (:76).
+//                       no registers held; one lane PAIR per node -- each lane walks every
+//                       second atom of the node in shared memory for all three components
+//                       (three independent FP64 chains, 27 instructions per atom instead of
+//                       the 72 of a lane-per-component layout), applies the float32 translate
+//                       rounding (Veltkamp split on the FP64 pipe), accumulates m*x in FP64;
+//                       one shuffle step joins the pair and the COM (sum times the
+//                       precomputed 1/M_node) is stored (:76).
 // HBM traffic: 12*A (bulk copies) + 24*N (stores) per frame, plus the 32-byte sectors of
 // the landmark gather (~17 % of a frame when there is one landmark per 16-atom node).
 #include "common.cuh"
@@ -25,8 +27,7 @@ namespace {
 constexpr int kPieceAtomsMax = 2048;
 constexpr int kStStages = 3;
 constexpr int kStThreads = 256;
-constexpr int kNodesPerWarp = 10;                              // 30 lanes = 10 nodes x (x,y,z)
-constexpr int kPieceNodesMax = (kStThreads / 32) * kNodesPerWarp;   // one pass per piece
+constexpr int kPieceNodesMax = kStThreads / 2;             // one lane pair per node, one pass per piece
 constexpr int kStageBytes = kPieceAtomsMax * 12 + 32;     // + slack for the 16-byte alignment shift
 
 struct Piece {
@@ -111,6 +112,17 @@ __device__ __forceinline__ double round_to_f32(double t) {
     return __dsub_rn(g, d);
 }
 
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
 __global__ void __launch_bounds__(kStThreads, 2)
 com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piece* __restrict__ pieces,
                   int P, const double* __restrict__ shift, const int4* __restrict__ node_info,
@@ -140,23 +152,28 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
         for (int a = 0; a < info.y; ++a) smass[info.z + a] = __ldg(ent_mass + info.x + a);
     }
 
-    // lane = (node j of this warp's 10, component c): no cross-lane reduction at all
-    const int lane = tid & 31, warp = tid >> 5;
-    const int j = lane / 3, comp = lane - 3 * j;
-    const int nl = warp * kNodesPerWarp + j;
-    const bool valid = lane < 3 * kNodesPerWarp && nl < pc.n_nodes;
-    int cnt = 0, qoff = 0, moff = 0, rot = 0;
+    // lane pair = one node: lane h of the pair takes the atoms a = h (mod 2), all three components
+    // (three independent FP64 chains), the pair is combined with one shuffle step.  Atom order is
+    // rotated per node so that the 32 lanes of a warp read 32 different banks when nodes are
+    // equally sized (16 atoms: float address 48 j + 6 u + 3 h, u rotated by j / 2).
+    const int nl = tid >> 1, h = tid & 1;
+    const bool valid = nl < pc.n_nodes;
+    int cnt_h = 0, rot = 0;
+    uint32_t q_rel = 0, m_addr = 0;
     double inv_m = 0.0;
     int64_t out_col = 0;
     if (valid) {
         const int4 info = __ldg(node_info + pc.node0 + nl);
-        cnt = info.y;
-        qoff = 3 * info.z + comp;          // float index of this node's first atom, this component
-        moff = info.z;
-        rot = j % cnt;                     // staggered start: equally sized nodes hit different banks
+        cnt_h = (info.y + 1 - h) >> 1;                       // atoms h, h+2, ... of this node
+        q_rel = 12u * (uint32_t)(info.z + h);                // byte offset of atom h inside the piece
+        m_addr = smem_u32(smass) + 8u * (uint32_t)(info.z + h);
+        rot = cnt_h > 0 ? (nl >> 1) % cnt_h : 0;
         inv_m = __ldg(inv_node_mass + pc.node0 + nl);
-        out_col = 3 * (int64_t)(pc.node0 + nl) + comp;
+        out_col = 3 * (int64_t)(pc.node0 + nl);
     }
+    int cnt_max = cnt_h;                                     // warp-uniform trip count
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt_max = max(cnt_max, __shfl_xor_sync(0xffffffffu, cnt_max, o));
     __syncthreads();
 
     // stage item k into slot k % kStStages: TMA bulk copy from the 16-byte-aligned address at or
@@ -185,7 +202,7 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
 
     for (int64_t k = 0; k < kStStages && k < n_items; ++k) stage_in(k);
 
-    const double* mb = smass + moff;
+    const uint32_t smem_base = smem_u32(smem_raw);
     for (int64_t k = 0; k < n_items; ++k) {
         const int slot = (int)(k % kStStages);
         const uint32_t ph = (uint32_t)((k / kStStages) & 1);
@@ -193,18 +210,33 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
         __syncthreads();     // manual-copy path: make the plain stores visible to every warp
         const int64_t f = f_start + k * f_stride;
         const int64_t src = (f * (int64_t)A + pc.atom0) * 12;
-        const float* qb = reinterpret_cast<const float*>(smem_raw + (size_t)slot * kStageBytes + (src & 15)) + qoff;
-        const double h = valid ? __ldg(shift + 3 * f + comp) : 0.0;
-        double acc = 0.0;
-        int a = rot;
-#pragma unroll 4
-        for (int it = 0; it < cnt; ++it) {
-            // translate(): float32 position += float64 vector, rounded back to float32
-            const double v = round_to_f32((double)qb[3 * a] + h);
-            acc = fma(mb[a], v, acc);
-            a = (a + 1 == cnt) ? 0 : a + 1;
+        const uint32_t q_addr = smem_base + (uint32_t)slot * kStageBytes + (uint32_t)(src & 15) + q_rel;
+        const double hx = __ldg(shift + 3 * f), hy = __ldg(shift + 3 * f + 1), hz = __ldg(shift + 3 * f + 2);
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        int u = rot;
+#pragma unroll 2
+        for (int it = 0; it < cnt_max; ++it) {
+            if (it < cnt_h) {
+                // translate(): float32 position += float64 vector, rounded back to float32
+                const uint32_t qa = q_addr + 24u * (uint32_t)u;
+                const double m = lds_f64(m_addr + 16u * (uint32_t)u);
+                const double vx = round_to_f32((double)lds_f32(qa) + hx);
+                const double vy = round_to_f32((double)lds_f32(qa + 4) + hy);
+                const double vz = round_to_f32((double)lds_f32(qa + 8) + hz);
+                ax = fma(m, vx, ax);
+                ay = fma(m, vy, ay);
+                az = fma(m, vz, az);
+                u = (u + 1 == cnt_h) ? 0 : u + 1;
+            }
         }
-        if (valid) nodes[(row0 + f) * ld + out_col] = acc * inv_m;
+        ax += __shfl_xor_sync(0xffffffffu, ax, 1);
+        ay += __shfl_xor_sync(0xffffffffu, ay, 1);
+        az += __shfl_xor_sync(0xffffffffu, az, 1);
+        if (valid) {
+            double* o = nodes + (row0 + f) * ld + out_col;
+            if (h == 0) { o[0] = ax * inv_m; o[1] = ay * inv_m; }
+            else o[2] = az * inv_m;
+        }
         __syncthreads();     // everyone is done with this slot
         if (k + kStStages < n_items) stage_in(k + kStStages);
     }
