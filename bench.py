@@ -483,7 +483,10 @@ def main():
                 rate = float(n3) ** 3 / (ms * 1e-3) / 1e12
                 big[tag] = {"ms": ms, "trelax_per_s": rate,
                             "frac_of_fp32_pipe_peak": 2.0 * rate / peaks_["fp32_fma_tflops"],
-                            "frac_of_fadd_fmnmx_peak": rate / peaks_.get("fp32_minplus_trelax", 12.1)}
+                            # pipe bound of a relaxation: adds on the FP32 pipe (FADD2) vs mins on the ALU pipe
+                            "frac_of_add_min_pipe_bound": rate / min(peaks_.get("fp32_ffma2_tflops", 72.1) / 2.0,
+                                                                     peaks_.get("fmnmx_tops", 36.6)),
+                            "vs_scalar_fadd_fmnmx_loop": rate / peaks_.get("fp32_minplus_trelax", 12.1)}
             extra["apsp_%d_nodes" % n3] = big
             del Wb
         t0 = time.perf_counter()
