@@ -515,6 +515,25 @@ def main():
                                   "paths_returned": int(n_ret), "expansions": int(exp_tot),
                                   "expansions_per_s": exp_tot / max(t_q, 1e-9)}
 
+    # ---- configs[4] over all ranks: pairs dealt round-robin, one APSP per rank, gather on rank 0 ----
+    if world > 1 and not args.no_paths and args.stress_pairs > 0:
+        from wisp_mdanalysis_implementation_b200 import paths_sharded
+        W = pipe.d_w.cpu().numpy()              # identical on every rank after the all-reduce + K4
+        hops, _ = ctx.apsp((W != 0).astype(np.float64), precision=32, want_pred=False)
+        rng = np.random.default_rng(1005)
+        cand5 = np.argwhere((hops >= 4) & (hops <= 10))
+        cand5 = cand5[cand5[:, 0] < cand5[:, 1]]
+        sel = cand5[rng.choice(len(cand5), size=min(args.stress_pairs, len(cand5)), replace=False)]
+        barrier()
+        t0 = time.perf_counter()
+        res = paths_sharded.query_pairs(ctx, W, sel, args.stress_paths)
+        barrier()
+        t_all = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        if rank == 0:
+            extra["stress_c5_sharded"] = {"ranks": world, "pairs": int(len(sel)), "paths_each": args.stress_paths,
+                                          "wall_ms_incl_apsp_and_gather": t_all,
+                                          "paths_returned": int(sum(len(r) for r in res))}
+
     # ---- CPU baseline (rank 0, N = 1 only): the oracle timed on the box's host cores ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

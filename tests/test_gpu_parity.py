@@ -425,6 +425,19 @@ def test_paths_prepare_query_stress(ctx):
         assert [p[0] for p in got] == [float(p[0]) for p in want]
 
 
+def test_pair_sharded_queries(ctx):
+    """paths_sharded.query_pairs (SURVEY 8(e), configs[4]) on one rank equals per-pair get_paths
+    and the oracle; the multi-rank gather is covered on gloo in test_sharding_gloo.py."""
+    from wisp_mdanalysis_implementation_b200 import paths_sharded
+    W = synth.random_cost_matrix(50, seed=12, density=0.15, lo=0.05, hi=0.9)
+    pairs = [(3, 41), (0, 17), (29, 5), (11, 48)]
+    got = paths_sharded.query_pairs(ctx, W, pairs, 7)
+    for (s, t), paths in zip(pairs, got):
+        assert paths == ctx.get_paths(W, [s], [t], 7)
+        want = oracle.get_paths_pruned(W, [s], [t], 7)
+        assert [p[1:] for p in paths] == [[int(x) for x in p[1:]] for p in want]
+
+
 def test_apsp_fp32_dense_predecessors(ctx):
     """Dense graph: the FP32 mode recovers predecessors with the tiled argmin product."""
     W = synth.random_cost_matrix(150, seed=3, density=0.95)

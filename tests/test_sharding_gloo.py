@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from wisp_mdanalysis_implementation_b200 import sharding
+from wisp_mdanalysis_implementation_b200 import paths_sharded, sharding
 
 
 def _local_pass(nodes, lo, hi, group=None):
@@ -62,3 +62,39 @@ def test_two_rank_reduction_matches_single_rank(tmp_path):
         mean = np.load(tmp_path / ("mean_%d.npy" % r))
         np.testing.assert_allclose(mean, want_mean, rtol=1e-13)
         np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-9)
+
+
+def _fake_query(s, t):
+    """Stand-in for wisp_paths_query: a result that depends on the pair only."""
+    return [[0.25 * (s + t) + k, s] + list(range(s + 1, s + 1 + k)) + [t] for k in range(1 + (s + t) % 3)]
+
+
+def _pairs_worker(rank, world, port, pairs, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    got = paths_sharded.query_pairs(None, None, pairs, 3, query=_fake_query)
+    if rank == 0:
+        import pickle
+        with open(os.path.join(out_dir, "pairs.pkl"), "wb") as f:
+            pickle.dump(got, f)
+    else:
+        assert got is None
+    dist.destroy_process_group()
+
+
+def test_pair_sharding_covers_every_pair_once():
+    for n, world in ((0, 2), (1, 4), (7, 2), (200, 8)):
+        seen = sorted(i for r in range(world) for i in paths_sharded.pair_shard(n, r, world))
+        assert seen == list(range(n))
+
+
+def test_two_rank_pair_queries_gather_in_order(tmp_path):
+    import pickle
+    pairs = [(3, 11), (0, 5), (7, 2), (4, 4 + 9), (1, 30), (6, 8), (2, 19)]
+    want = [_fake_query(s, t) for s, t in pairs]
+    assert paths_sharded.query_pairs(None, None, pairs, 3, query=_fake_query) == want   # no process group
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_pairs_worker, args=(2, port, pairs, str(tmp_path)), nprocs=2, join=True)
+    with open(tmp_path / "pairs.pkl", "rb") as f:
+        assert pickle.load(f) == want

@@ -91,7 +91,7 @@ contact_sum_kernel(const float* __restrict__ p32, int64_t T, int N, const double
     const int64_t f_end = T * (seg + 1) / n_seg;
 
     constexpr int kThreadsC = 1024 / JH;
-    constexpr int kPerThread = 1536 / kThreadsC;      // staged float4 per thread per chunk
+    constexpr int kPerThread = kFC * 192 / kThreadsC; // staged float4 per thread per chunk
     const int tid = threadIdx.x;
     const int ti = tid & 15;     // i nodes: 4ti..4ti+3 and 64+4ti..64+4ti+3
     const int tj = tid >> 4;     // j nodes: 4tj..4tj+3 (and 64+4tj.. when JH == 4)
@@ -104,7 +104,7 @@ contact_sum_kernel(const float* __restrict__ p32, int64_t T, int N, const double
 #pragma unroll
     for (int c = 0; c < 3; ++c) roff[c] = (float)(mean[3 * rj + c] - mean[3 * ri + c]);
 
-    // staging: 8 frames x (i tile + j tile) x 96 float4 = 1536 float4 per chunk, 3 per thread
+    // staging: kFC frames x (i tile + j tile) x 96 float4 per chunk
     auto load_chunk = [&](int64_t f0, float4 (&v)[kPerThread]) {
 #pragma unroll
         for (int q = 0; q < kPerThread; ++q) {
