@@ -411,6 +411,40 @@ def test_frame_pipeline_matches_c_abi_pipeline(ctx):
     np.testing.assert_allclose(pipe.d_mean.cpu().numpy()[:900], ref["avg"].reshape(-1), rtol=0, atol=1e-11)
 
 
+def test_frame_pipeline_int8_engine_vs_oracle(ctx):
+    """Trajectories of 4096+ frames per rank take the INT8 tensor-core K2 inside FramePipeline
+    (device-resident, host-fed and streamed modes); all three against the oracle."""
+    import torch
+    from wisp_mdanalysis_implementation_b200.pipeline import FramePipeline
+    n, t, apn = 140, 4500, 3
+    system, coords = synth.synth(n, t, apn, seed=31)
+    nodes, _ = oracle.com_nodes(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx)
+    _, _, corr = oracle.pearson_correlation_fast(oracle.cartesian_covariance_fast(nodes, nodes.sum(axis=0) / t))
+    binary, avgdist = oracle.calc_contact_map_fast(nodes, 13.0)
+    pipe = FramePipeline(ctx, n, system.n_atoms, system.masses, system.node_ptr, system.atom_idx,
+                         system.align_idx, frames_local=t, cutoff=13.0, which_map=1)
+    pipe.run_device(torch.from_numpy(coords).cuda())
+    torch.cuda.synchronize()
+    got_int8 = pipe.d_corr.cpu().numpy()
+    ctx.set_gram_mode("dmma")
+    try:
+        pipe.gram()
+        pipe.reduce_and_epilogue()
+        torch.cuda.synchronize()
+        got_dmma = pipe.d_corr.cpu().numpy()
+    finally:
+        ctx.set_gram_mode("auto")
+    assert not np.array_equal(got_int8, got_dmma)              # the INT8 engine really ran
+    assert np.abs(got_int8 - got_dmma).max() < 1e-9
+    h = torch.from_numpy(coords).pin_memory()
+    for out in (dict(corr=got_int8, avgdist=pipe.d_avgdist.cpu().numpy(), binary=pipe.d_binary.cpu().numpy()),
+                pipe.run_host(h), pipe.run_host_streamed(h, n_blocks=1)):
+        assert_corr_close(out["corr"], corr)
+        assert np.all(np.diagonal(out["corr"]) == 1.0) and np.array_equal(out["corr"], out["corr"].T)
+        np.testing.assert_allclose(out["avgdist"], avgdist, rtol=1e-6, atol=1e-9)
+        assert_binary_equal_outside_ties(out["binary"], avgdist, 13.0, binary)
+
+
 def test_paths_prepare_query_stress(ctx):
     """configs[4] in miniature: one APSP, many independent (source, sink) queries."""
     W = synth.random_cost_matrix(60, seed=77, density=0.12, lo=0.05, hi=0.9)
