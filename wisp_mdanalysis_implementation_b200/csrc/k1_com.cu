@@ -159,7 +159,8 @@ __global__ void center_kernel(double* __restrict__ x, int64_t T, int64_t ld, int
 // memory, coalesced 1.5 KB write.
 __global__ void __launch_bounds__(384)
 center_convert_kernel(double* __restrict__ x, int64_t T, int64_t ld, int N,
-                      const double* __restrict__ mean, float* __restrict__ p32, int n_tiles) {
+                      const double* __restrict__ mean, float* __restrict__ p32, int n_tiles,
+                      double* __restrict__ stat) {
     __shared__ float s[3][kTile + 1];
     const int tile = blockIdx.x;
     const int k = threadIdx.x;
@@ -169,13 +170,22 @@ center_convert_kernel(double* __restrict__ x, int64_t T, int64_t ld, int N,
     if (nref > N - 1) nref = N - 1;
     const double m = mean[col];
     const double ref = mean[3 * nref + c];
+    double amax = 0.0, ssq = 0.0;      // per column, over this block's frames: what the INT8 K2 scales by
     for (int64_t t = blockIdx.y; t < T; t += gridDim.y) {
         const double v = x[t * ld + col];
-        x[t * ld + col] = v - m;
+        const double xc = v - m;
+        x[t * ld + col] = xc;
+        amax = fmax(amax, fabs(xc));
+        ssq = fma(xc, xc, ssq);
         s[c][n] = (float)(v - ref);
         __syncthreads();
         p32[(t * n_tiles + tile) * (int64_t)(3 * kTile) + k] = s[k / kTile][k % kTile];
         __syncthreads();
+    }
+    if (stat) {                        // [gridDim.y][2][3 * 128 * n_tiles]
+        const int64_t w = (int64_t)3 * kTile * n_tiles;
+        stat[((int64_t)blockIdx.y * 2 + 0) * w + col] = amax;
+        stat[((int64_t)blockIdx.y * 2 + 1) * w + col] = ssq;
     }
 }
 
@@ -187,6 +197,7 @@ int launch_com(wisp_ctx* ctx, const float* d_coords, int64_t T, int A, const dou
                int64_t row0, cudaStream_t st, float* d_align_out) {
     WISP_CHECK(T > 0 && A > 0 && N > 0 && n_align > 0, "com: empty input (T=%lld A=%d N=%d nAlign=%d)",
                (long long)T, A, N, n_align);
+    ctx->i8_stats_x = nullptr;        // the node trajectory is being rewritten
     const int blocks = (int)std::min<int64_t>(T, (int64_t)ctx->sm_count * 8);
     com_kernel<<<blocks, kComThreads, 0, st>>>(d_coords, T, A, d_masses, d_node_ptr, d_atom_idx, N,
                                               d_align_idx, n_align, atomic, d_nodes, ld, row0, d_align_out);
@@ -229,9 +240,18 @@ int launch_center(wisp_ctx* ctx, double* d_x, int64_t T, int64_t ld, int64_t nco
     if (d_p32) {
         const int n_tiles = (int)(round_up(N, kTile) / kTile);
         const int gy = (int)std::min<int64_t>(T, std::max<int64_t>(1, (int64_t)ctx->sm_count * 8 / n_tiles));
-        center_convert_kernel<<<dim3(n_tiles, gy), 384, 0, st>>>(d_x, T, ld, N, d_mean, d_p32, n_tiles);
+        // per-column statistics of the centred block ride along: the INT8 K2 engine takes them from
+        // here instead of reading X once more, if the next wisp_dev_gram is on this very block
+        void* p_stat = nullptr;
+        WISP_TRY(wisp_scratch(ctx, SCR_I8_STATS, (size_t)gy * 2 * 3 * kTile * n_tiles * 8, &p_stat));
+        center_convert_kernel<<<dim3(n_tiles, gy), 384, 0, st>>>(d_x, T, ld, N, d_mean, d_p32, n_tiles,
+                                                                 (double*)p_stat);
         ctx->launches++;
         WISP_CUDA(cudaGetLastError());
+        ctx->i8_stats_x = d_x;
+        ctx->i8_stats_T = T;
+        ctx->i8_stats_parts = gy;
+        ctx->i8_stats_stream = st;
         return 0;
     }
     const int gx = (int)((ncols + 255) / 256);

@@ -364,6 +364,7 @@ int com_plan_info(const wisp_com_plan* pl, int* streaming, int* n_pieces) {
 int launch_com_plan(wisp_ctx* ctx, wisp_com_plan* pl, const float* d_coords, int64_t T, double* d_nodes,
                     int64_t ld, int64_t row0, cudaStream_t st, float* d_align_out) {
     WISP_CHECK(pl && d_coords && d_nodes && T > 0, "com: bad argument");
+    ctx->i8_stats_x = nullptr;        // the node trajectory is being rewritten
     if (!pl->streaming)
         return launch_com(ctx, d_coords, T, pl->A, pl->d_masses, pl->d_node_ptr, pl->d_atom_idx, pl->N,
                           pl->d_align_idx, pl->n_align, pl->atomic, d_nodes, ld, row0, st, d_align_out);

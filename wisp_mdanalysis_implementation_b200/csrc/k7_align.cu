@@ -149,6 +149,7 @@ int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* 
                             int N, int64_t T, double threshold, int max_iter, double* d_work,
                             double* h_avg_nodes, double* log, int* n_iter_out, cudaStream_t st) {
     const int64_t na3 = 3 * (int64_t)n_align, nn3 = 3 * (int64_t)N;
+    ctx->i8_stats_x = nullptr;               // the node trajectory is rotated in place
     double* d_avgA = d_work;                 // [na3]
     double* d_sumA = d_avgA + round_up(na3, 32);
     double* d_sumN = d_sumA + round_up(na3, 32);   // [nn3]
