@@ -304,6 +304,28 @@ def test_com_streaming_many_pieces(ctx):
     np.testing.assert_allclose(avg, want.sum(axis=0) / want.shape[0], rtol=0, atol=1e-11)
 
 
+@pytest.mark.parametrize("n,t,apn", [(333, 37, 13), (150, 700, 16), (40, 3, 5)])
+def test_com_fused_column_sums(ctx, n, t, apn):
+    """wisp_dev_com with d_colsum: the column sums come out of the streaming COM kernel itself
+    (per frame-class partials, fixed-order finish) and equal the sums of the rows it wrote."""
+    import torch
+    from wisp_mdanalysis_implementation_b200.pipeline import FramePipeline
+    system, coords = synth.synth(n, t, apn, seed=5 + n)
+    pipe = FramePipeline(ctx, n, system.n_atoms, system.masses, system.node_ptr, system.atom_idx,
+                         system.align_idx, frames_local=t)
+    assert pipe.plan_info["streaming"]
+    pipe.d_colsum.fill_(float("nan"))
+    pipe.d_colsum[3 * n:] = 0.0
+    pipe.com(torch.from_numpy(coords).cuda(), colsum=True)
+    torch.cuda.synchronize()
+    x = pipe.d_x.cpu().numpy()[:t, :3 * n]
+    want, _ = oracle.com_nodes(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx)
+    np.testing.assert_allclose(x, want.reshape(t, 3 * n), rtol=0, atol=1e-11)
+    got = pipe.d_colsum.cpu().numpy()
+    np.testing.assert_allclose(got[:3 * n], x.sum(axis=0), rtol=1e-13, atol=1e-10)
+    assert np.all(got[3 * n:] == 0.0)
+
+
 def test_driver_end_to_end(ctx, tmp_path):
     """`python wisp_w_mdanalysis.py <config>` with every stage pointed at the B200 modules
     (config keys *_functions_file), on a stand-in universe; compared with the oracle."""

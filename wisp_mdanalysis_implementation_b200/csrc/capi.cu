@@ -530,9 +530,7 @@ extern "C" int wisp_dev_com(wisp_ctx* ctx, wisp_com_plan* plan, const float* d_c
     WISP_CHECK(ctx && plan && d_coords && d_nodes, "dev_com: null argument");
     cudaStream_t st = wisp_stream(ctx, stream);
     const int64_t ld = wisp_node_ld(N);
-    WISP_TRY(launch_com_plan(ctx, plan, d_coords, T, d_nodes, ld, 0, st));
-    if (d_colsum) WISP_TRY(launch_colsum(ctx, d_nodes, T, ld, 3 * (int64_t)N, d_colsum, st));
-    return 0;
+    return launch_com_plan(ctx, plan, d_coords, T, d_nodes, ld, 0, st, nullptr, d_colsum);
 }
 
 extern "C" int wisp_dev_center(wisp_ctx* ctx, double* d_nodes, int64_t T, int N, const double* d_mean,

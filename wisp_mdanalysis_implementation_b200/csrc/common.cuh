@@ -103,8 +103,14 @@ int com_plan_create(wisp_ctx* ctx, int A, const double* masses, const int32_t* n
                     wisp_com_plan** out);
 void com_plan_destroy(wisp_ctx* ctx, wisp_com_plan* pl);
 int com_plan_info(const wisp_com_plan* pl, int* streaming, int* n_pieces);
+// d_colsum != nullptr: also the column sums of the T rows just written (fused into the streaming
+// kernel; the gather fallback runs the separate column-sum pass)
 int launch_com_plan(wisp_ctx* ctx, wisp_com_plan* pl, const float* d_coords, int64_t T, double* d_nodes,
-                    int64_t ld, int64_t row0, cudaStream_t st, float* d_align_out = nullptr);
+                    int64_t ld, int64_t row0, cudaStream_t st, float* d_align_out = nullptr,
+                    double* d_colsum = nullptr);
+// out[col] = sum over n_rows rows of part[row * row_stride + col], fixed order
+int launch_colsum_finish(wisp_ctx* ctx, const double* d_part, int n_rows, int64_t row_stride, int64_t ncols,
+                         double* d_colsum, cudaStream_t st);
 int launch_colsum_f32(wisp_ctx* ctx, const float* d_x, int64_t T, int64_t ld, int64_t ncols,
                       double* d_colsum, cudaStream_t st);
 int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* d_nodes, int64_t ld,

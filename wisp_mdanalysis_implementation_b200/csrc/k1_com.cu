@@ -135,12 +135,12 @@ __global__ void colsum_part_kernel(const TIn* __restrict__ x, int64_t T, int64_t
     }
 }
 
-__global__ void colsum_final_kernel(const double* __restrict__ part, int n_seg, int64_t ncols,
-                                    double* __restrict__ out) {
+__global__ void colsum_final_kernel(const double* __restrict__ part, int n_seg, int64_t row_stride,
+                                    int64_t ncols, double* __restrict__ out) {
     const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= ncols) return;
     double s = 0.0;
-    for (int k = 0; k < n_seg; ++k) s += part[(int64_t)k * ncols + col];
+    for (int k = 0; k < n_seg; ++k) s += part[(int64_t)k * row_stride + col];
     out[col] = s;
 }
 
@@ -218,8 +218,16 @@ static int launch_colsum_t(wisp_ctx* ctx, const TIn* d_x, int64_t T, int64_t ld,
         d_x, T, ld, ncols, n_seg, (double*)p);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
-    colsum_final_kernel<<<(int)((ncols + 255) / 256), 256, 0, st>>>((const double*)p, n_seg, ncols,
+    colsum_final_kernel<<<(int)((ncols + 255) / 256), 256, 0, st>>>((const double*)p, n_seg, ncols, ncols,
                                                                     d_colsum);
+    ctx->launches++;
+    WISP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_colsum_finish(wisp_ctx* ctx, const double* d_part, int n_rows, int64_t row_stride, int64_t ncols,
+                         double* d_colsum, cudaStream_t st) {
+    colsum_final_kernel<<<(int)((ncols + 255) / 256), 256, 0, st>>>(d_part, n_rows, row_stride, ncols, d_colsum);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
     return 0;

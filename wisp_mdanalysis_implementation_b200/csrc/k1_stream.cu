@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(kStThreads, 2)
 com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piece* __restrict__ pieces,
                   int P, const double* __restrict__ shift, const int4* __restrict__ node_info,
                   const double* __restrict__ ent_mass, const double* __restrict__ inv_node_mass,
-                  double* __restrict__ nodes, int64_t ld, int64_t row0, int64_t total_bytes) {
+                  double* __restrict__ nodes, int64_t ld, int64_t row0, int64_t total_bytes,
+                  double* __restrict__ colpart) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full[kStStages];
     double* smass = reinterpret_cast<double*>(smem_raw + (size_t)kStStages * kStageBytes);
@@ -209,6 +210,7 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
     for (int64_t k = 0; k < kStStages && k < n_items; ++k) stage_in(k);
 
     const uint32_t smem_base = smem_u32(smem_raw);
+    double cs0 = 0.0, cs1 = 0.0;      // column sums of what this lane stores, over this CTA's frames
     for (int64_t k = 0; k < n_items; ++k) {
         const int slot = (int)(k % kStStages);
         const uint32_t ph = (uint32_t)((k / kStStages) & 1);
@@ -240,11 +242,23 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
         az += __shfl_xor_sync(0xffffffffu, az, 1);
         if (valid) {
             double* o = nodes + (row0 + f) * ld + out_col;
-            if (h == 0) { o[0] = ax * inv_m; o[1] = ay * inv_m; }
-            else o[2] = az * inv_m;
+            if (h == 0) {
+                const double vx = ax * inv_m, vy = ay * inv_m;
+                o[0] = vx; o[1] = vy;
+                cs0 += vx; cs1 += vy;
+            } else {
+                const double vz = az * inv_m;
+                o[2] = vz;
+                cs0 += vz;
+            }
         }
         __syncthreads();     // everyone is done with this slot
         if (k + kStStages < n_items) stage_in(k + kStStages);
+    }
+    if (colpart && valid) {           // row = this CTA's frame class; summed over rows in fixed order later
+        double* o = colpart + f_start * ld + out_col;
+        if (h == 0) { o[0] = cs0; o[1] = cs1; }
+        else o[2] = cs0;
     }
 }
 
@@ -362,12 +376,15 @@ int com_plan_info(const wisp_com_plan* pl, int* streaming, int* n_pieces) {
 }
 
 int launch_com_plan(wisp_ctx* ctx, wisp_com_plan* pl, const float* d_coords, int64_t T, double* d_nodes,
-                    int64_t ld, int64_t row0, cudaStream_t st, float* d_align_out) {
+                    int64_t ld, int64_t row0, cudaStream_t st, float* d_align_out, double* d_colsum) {
     WISP_CHECK(pl && d_coords && d_nodes && T > 0, "com: bad argument");
     ctx->i8_stats_x = nullptr;        // the node trajectory is being rewritten
-    if (!pl->streaming)
-        return launch_com(ctx, d_coords, T, pl->A, pl->d_masses, pl->d_node_ptr, pl->d_atom_idx, pl->N,
-                          pl->d_align_idx, pl->n_align, pl->atomic, d_nodes, ld, row0, st, d_align_out);
+    if (!pl->streaming) {
+        WISP_TRY(launch_com(ctx, d_coords, T, pl->A, pl->d_masses, pl->d_node_ptr, pl->d_atom_idx, pl->N,
+                            pl->d_align_idx, pl->n_align, pl->atomic, d_nodes, ld, row0, st, d_align_out));
+        if (d_colsum) WISP_TRY(launch_colsum(ctx, d_nodes + row0 * ld, T, ld, 3 * (int64_t)pl->N, d_colsum, st));
+        return 0;
+    }
     if (pl->shift_frames < T) {
         if (pl->d_shift) { WISP_CUDA(cudaDeviceSynchronize()); WISP_CUDA(cudaFree(pl->d_shift)); pl->d_shift = nullptr; }
         WISP_CUDA(cudaMalloc((void**)&pl->d_shift, (size_t)T * 3 * 8));
@@ -383,10 +400,17 @@ int launch_com_plan(wisp_ctx* ctx, wisp_com_plan* pl, const float* d_coords, int
     const int P = pl->P;
     int per_piece = std::max(1, (2 * ctx->sm_count) / P);
     per_piece = (int)std::min<int64_t>(per_piece, T);
+    double* d_colpart = nullptr;      // [per_piece][ld] column sums per frame class, fused into the COM pass
+    if (d_colsum) {
+        void* p = nullptr;
+        WISP_TRY(wisp_scratch(ctx, SCR_COLSUM_PART, (size_t)per_piece * ld * 8, &p));
+        d_colpart = (double*)p;
+    }
     com_stream_kernel<<<P * per_piece, kStThreads, smem, st>>>(
         d_coords, T, pl->A, pl->d_pieces, P, pl->d_shift, pl->d_node_info, pl->d_ent_mass,
-        pl->d_inv_node_mass, d_nodes, ld, row0, (int64_t)T * pl->A * 12);
+        pl->d_inv_node_mass, d_nodes, ld, row0, (int64_t)T * pl->A * 12, d_colpart);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
+    if (d_colsum) WISP_TRY(launch_colsum_finish(ctx, d_colpart, per_piece, ld, 3 * (int64_t)pl->N, d_colsum, st));
     return 0;
 }

@@ -94,14 +94,18 @@ class FramePipeline:
         # stream", so name the legacy stream explicitly (cudaStreamLegacy == 0x1)
         return torch.cuda.current_stream(self.dev).cuda_stream or 1
 
-    def com(self, d_coords, frames=None, row0=0):
+    def com(self, d_coords, frames=None, row0=0, colsum=False):
+        """K1 on a coordinate block; colsum=True also leaves the column sums of the rows just
+        written in d_colsum (fused into the streaming kernel)."""
         t = self.T if frames is None else frames
         self.ctx.dev_com(self.plan, d_coords.data_ptr(), t, self.N,
-                         self.d_x.data_ptr() + row0 * self.ld * 8, None, stream=self._stream())
+                         self.d_x.data_ptr() + row0 * self.ld * 8,
+                         self.d_colsum.data_ptr() if colsum else None, stream=self._stream())
 
-    def mean_and_center(self):
+    def mean_and_center(self, have_colsum=False):
         s = self._stream()
-        self.ctx.dev_colsum(self.d_x.data_ptr(), self.T, self.N, self.d_colsum.data_ptr(), stream=s)
+        if not have_colsum:
+            self.ctx.dev_colsum(self.d_x.data_ptr(), self.T, self.N, self.d_colsum.data_ptr(), stream=s)
         sharding.global_mean(self.d_colsum, self.d_mean, self.T_total, group=self.group)
         self.ctx.dev_center(self.d_x.data_ptr(), self.T, self.N, self.d_mean.data_ptr(),
                             d_p32=self.d_p32.data_ptr(), stream=s)
@@ -125,8 +129,8 @@ class FramePipeline:
     # -- whole steps ------------------------------------------------------------------
     def run_device(self, d_coords):
         """One pass with the coordinate block already resident in HBM."""
-        self.com(d_coords)
-        self.mean_and_center()
+        self.com(d_coords, colsum=True)
+        self.mean_and_center(have_colsum=True)
         self.gram()
         self.contact()
         self.reduce_and_epilogue()
