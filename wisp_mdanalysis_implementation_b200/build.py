@@ -19,6 +19,8 @@ SOURCES = ["capi.cu", "k1_com.cu", "k1_stream.cu", "k2_gram.cu", "k2_gram_i8.cu"
            "k5_apsp.cu", "k6_paths.cu", "k7_align.cu", "k8_lmi.cu", "textio.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+# tuning experiments: WISP_NVCC_DEFS="-DWISP_WS_FC=16 -DWISP_WS_STAGES=2" python -m ...build --force
+NVCC_FLAGS += os.environ.get("WISP_NVCC_DEFS", "").split()
 
 
 def _nvcc():

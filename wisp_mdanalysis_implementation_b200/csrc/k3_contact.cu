@@ -134,7 +134,7 @@ contact_sum_kernel(const float* __restrict__ p32, int64_t T, int N, const double
             const int c = w / 32;
             float4 x = v[q];
             if (sel) {
-                const float o = roff[c];
+                const float o = c == 0 ? roff[0] : (c == 1 ? roff[1] : roff[2]);
                 x.x += o; x.y += o; x.z += o; x.w += o;
                 *reinterpret_cast<float4*>(&sm.sj[buf][fl][0][0] + 4 * w) = x;
             } else {
@@ -243,6 +243,220 @@ contact_sum_kernel(const float* __restrict__ p32, int64_t T, int N, const double
     }
 }
 
+// ---- warp-specialised form --------------------------------------------------------------
+// Same arithmetic, other plumbing: the 16 compute warps execute nothing but the pair loop (the
+// loop needs 7 issue cycles of packed FP32 per MUFU cycle of 8, so every staging instruction a
+// compute warp issues is lost MUFU time).  Warp 16 is the producer: one lane issues the TMA bulk
+// copies of the next 16 frames (one 1.5 KB row per frame and tile, cp.async.bulk + mbarrier
+// complete_tx) into a 2-stage ring, the warp then adds the tile-pair reference offset to the j
+// rows in place and releases the stage (full barrier); compute warps hand stages back through
+// an empty barrier.  No __syncthreads in the frame loop.
+#ifndef WISP_WS_FC
+#define WISP_WS_FC 16
+#endif
+#ifndef WISP_WS_STAGES
+#define WISP_WS_STAGES 2
+#endif
+constexpr int kWsFC = WISP_WS_FC;                 // frames per stage
+constexpr int kWsStages = WISP_WS_STAGES;
+constexpr int kWsComputeThreads = 512;
+constexpr int kWsThreads = kWsComputeThreads + 32;
+
+struct ContactWsSmem {
+    double tot[kTile * kTile];
+    float ring[kWsStages][2][kWsFC][3][kTile];                // [stage][0 = i rows, 1 = j rows]
+    unsigned long long landed[kWsStages], full[kWsStages], empty[kWsStages];
+};
+
+__device__ __forceinline__ uint32_t ws_smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void ws_mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ws_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ws_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ws_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ws_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(ws_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void ws_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(ws_smem_u32(dst)), "l"(src), "r"(bytes), "r"(ws_smem_u32(bar)) : "memory");
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(kWsThreads, 1)
+contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const double* __restrict__ mean,
+                      int n_tiles, int n_seg, double* __restrict__ out, int64_t out_ld) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ContactWsSmem& sm = *reinterpret_cast<ContactWsSmem*>(smem_raw);
+
+    int bi = 0, rem = blockIdx.x;
+    while (rem >= n_tiles - bi) { rem -= n_tiles - bi; ++bi; }
+    const int bj = bi + rem;
+    const int seg = blockIdx.y;
+    const int64_t f_begin = T * seg / n_seg;
+    const int64_t f_end = T * (seg + 1) / n_seg;
+    const int n_chunks = (int)((f_end - f_begin + kWsFC - 1) / kWsFC);
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < kWsStages; ++s) {
+            ws_mbar_init(&sm.landed[s], 1);
+            ws_mbar_init(&sm.full[s], 1);
+            ws_mbar_init(&sm.empty[s], kWsComputeThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < kWsComputeThreads) {
+#pragma unroll
+        for (int p = 0; p < 32; ++p) sm.tot[p * kWsComputeThreads + tid] = 0.0;
+    }
+    __syncthreads();
+
+    if (tid >= kWsComputeThreads) {
+        // ---------------- producer warp ----------------
+        const int lane = tid & 31;
+        int ri = kTile * bi + kTile / 2, rj = kTile * bj + kTile / 2;
+        if (ri > N - 1) ri = N - 1;
+        if (rj > N - 1) rj = N - 1;
+        float roff[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) roff[c] = (float)(mean[3 * rj + c] - mean[3 * ri + c]);
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            const int slot = ch % kWsStages;
+            const uint32_t ph = (uint32_t)((ch / kWsStages) & 1);
+            const int64_t f0 = f_begin + (int64_t)ch * kWsFC;
+            const int nf = (int)((f_end - f0) < kWsFC ? (f_end - f0) : kWsFC);
+            ws_mbar_wait(&sm.empty[slot], ph ^ 1);
+            if (lane == 0) {
+                ws_mbar_expect_tx(&sm.landed[slot], (uint32_t)nf * 2u * kTileFloats * 4u);
+                for (int fl = 0; fl < nf; ++fl) {
+                    const float* row = p32 + (f0 + fl) * (int64_t)n_tiles * kTileFloats;
+                    ws_bulk_g2s(&sm.ring[slot][0][fl][0][0], row + (int64_t)bi * kTileFloats, kTileFloats * 4, &sm.landed[slot]);
+                    ws_bulk_g2s(&sm.ring[slot][1][fl][0][0], row + (int64_t)bj * kTileFloats, kTileFloats * 4, &sm.landed[slot]);
+                }
+            }
+            ws_mbar_wait(&sm.landed[slot], ph);
+            if (bi != bj) {          // x_i - x_j = a_i - (b_j + (ref_J - ref_I)): shift the j rows once
+                float4* q = reinterpret_cast<float4*>(&sm.ring[slot][1][0][0][0]);
+                for (int fl = 0; fl < nf; ++fl)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {              // 32 float4 per component row
+                        float4 v = q[fl * 96 + c * 32 + lane];
+                        v.x += roff[c]; v.y += roff[c]; v.z += roff[c]; v.w += roff[c];
+                        q[fl * 96 + c * 32 + lane] = v;
+                    }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // before the next TMA write here
+            }
+            __syncwarp();
+            if (lane == 0) ws_mbar_arrive(&sm.full[slot]);
+        }
+        return;
+    }
+
+    // ---------------- compute warps ----------------
+    constexpr int JH = 2;
+    const int ti = tid & 15;     // i nodes: 4ti..4ti+3 and 64+4ti..64+4ti+3
+    const int tj = tid >> 4;     // j nodes: 4tj..4tj+3
+    f32x2 acc[8][JH];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int h = 0; h < JH; ++h) acc[a][h] = pack2(0.f, 0.f);
+
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int slot = ch % kWsStages;
+        const uint32_t ph = (uint32_t)((ch / kWsStages) & 1);
+        const int64_t f0 = f_begin + (int64_t)ch * kWsFC;
+        const int nf = (int)((f_end - f0) < kWsFC ? (f_end - f0) : kWsFC);
+        ws_mbar_wait(&sm.full[slot], ph);
+        const float* si = &sm.ring[slot][0][0][0][0];
+        const float* sj = &sm.ring[slot][1][0][0][0];
+#pragma unroll UNROLL
+        for (int fl = 0; fl < nf; ++fl) {
+            float ax[8], ay[8], az[8];
+            f32x2 bx[JH], by[JH], bz[JH];
+            {
+                const float* fi = si + fl * kTileFloats;
+                const float* fj = sj + fl * kTileFloats;
+                const float4 t0 = *reinterpret_cast<const float4*>(fi + 4 * ti);
+                const float4 t1 = *reinterpret_cast<const float4*>(fi + 64 + 4 * ti);
+                ax[0] = t0.x; ax[1] = t0.y; ax[2] = t0.z; ax[3] = t0.w;
+                ax[4] = t1.x; ax[5] = t1.y; ax[6] = t1.z; ax[7] = t1.w;
+                const float4 u0 = *reinterpret_cast<const float4*>(fi + kTile + 4 * ti);
+                const float4 u1 = *reinterpret_cast<const float4*>(fi + kTile + 64 + 4 * ti);
+                ay[0] = u0.x; ay[1] = u0.y; ay[2] = u0.z; ay[3] = u0.w;
+                ay[4] = u1.x; ay[5] = u1.y; ay[6] = u1.z; ay[7] = u1.w;
+                const float4 v0 = *reinterpret_cast<const float4*>(fi + 2 * kTile + 4 * ti);
+                const float4 v1 = *reinterpret_cast<const float4*>(fi + 2 * kTile + 64 + 4 * ti);
+                az[0] = v0.x; az[1] = v0.y; az[2] = v0.z; az[3] = v0.w;
+                az[4] = v1.x; az[5] = v1.y; az[6] = v1.z; az[7] = v1.w;
+                const float4 w0 = *reinterpret_cast<const float4*>(fj + 4 * tj);
+                const float4 w1 = *reinterpret_cast<const float4*>(fj + kTile + 4 * tj);
+                const float4 w2 = *reinterpret_cast<const float4*>(fj + 2 * kTile + 4 * tj);
+                bx[0] = pack2(w0.x, w0.y); bx[1] = pack2(w0.z, w0.w);
+                by[0] = pack2(w1.x, w1.y); by[1] = pack2(w1.z, w1.w);
+                bz[0] = pack2(w2.x, w2.y); bz[1] = pack2(w2.z, w2.w);
+            }
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const f32x2 axx = pack2(ax[a], ax[a]), ayy = pack2(ay[a], ay[a]), azz = pack2(az[a], az[a]);
+#pragma unroll
+                for (int h = 0; h < JH; ++h) {
+                    const f32x2 dx = sub2(axx, bx[h]);
+                    const f32x2 dy = sub2(ayy, by[h]);
+                    const f32x2 dz = sub2(azz, bz[h]);
+                    const f32x2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                    float lo, hi;
+                    unpack2(d2, lo, hi);
+                    acc[a][h] = add2(acc[a][h], pack2(fast_sqrt(lo), fast_sqrt(hi)));
+                }
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) ws_mbar_arrive(&sm.empty[slot]);        // this warp is done with the stage
+        if ((ch % (128 / kWsFC)) == (128 / kWsFC) - 1 || ch == n_chunks - 1) {      // every 128 frames
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int h = 0; h < JH; ++h) {
+                    float lo, hi;
+                    unpack2(acc[a][h], lo, hi);
+                    sm.tot[(a * 2 * JH + 2 * h) * kWsComputeThreads + tid] += (double)lo;
+                    sm.tot[(a * 2 * JH + 2 * h + 1) * kWsComputeThreads + tid] += (double)hi;
+                    acc[a][h] = pack2(0.f, 0.f);
+                }
+        }
+    }
+
+    double* o = out + (size_t)seg * out_ld * out_ld;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int64_t row = (int64_t)kTile * bi + ((a < 4) ? (4 * ti + a) : (64 + 4 * ti + (a - 4)));
+        const int64_t col0 = (int64_t)kTile * bj + 4 * tj;
+        double* p = o + row * out_ld + col0;
+        const int pb = a * 2 * JH;
+        *reinterpret_cast<double2*>(p) =
+            make_double2(sm.tot[(pb + 0) * kWsComputeThreads + tid], sm.tot[(pb + 1) * kWsComputeThreads + tid]);
+        *reinterpret_cast<double2*>(p + 2) =
+            make_double2(sm.tot[(pb + 2) * kWsComputeThreads + tid], sm.tot[(pb + 3) * kWsComputeThreads + tid]);
+    }
+}
+
 }  // namespace
 
 int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, const double* d_mean,
@@ -261,7 +475,7 @@ int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, cons
     }
     const int smem = (int)sizeof(ContactSmem);
     dim3 grid(n_items, n_seg);
-    static const int variant = getenv("WISP_K3_VARIANT") ? atoi(getenv("WISP_K3_VARIANT")) : 21;
+    static const int variant = getenv("WISP_K3_VARIANT") ? atoi(getenv("WISP_K3_VARIANT")) : 58;
 #define WISP_K3_LAUNCH(JH_, UN_)                                                                          \
     do {                                                                                                  \
         WISP_CUDA(cudaFuncSetAttribute(contact_sum_kernel<JH_, UN_>,                                      \
@@ -269,10 +483,26 @@ int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, cons
         contact_sum_kernel<JH_, UN_><<<grid, 1024 / JH_, smem, st>>>(d_p32, T, N, d_mean, n_tiles, n_seg, \
                                                                      part, n_pad);                        \
     } while (0)
+    if (variant >= 50 && variant < 60) {
+        const int smem_ws = (int)sizeof(ContactWsSmem);
+#define WISP_K3_WS(UN_)                                                                                         \
+    do {                                                                                                        \
+        WISP_CUDA(cudaFuncSetAttribute(contact_sum_ws_kernel<UN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       smem_ws));                                                               \
+        contact_sum_ws_kernel<UN_><<<grid, kWsThreads, smem_ws, st>>>(d_p32, T, N, d_mean, n_tiles, n_seg, part, \
+                                                                      n_pad);                                   \
+    } while (0)
+        if (variant == 51) WISP_K3_WS(1);
+        else if (variant == 54) WISP_K3_WS(4);
+        else if (variant == 58) WISP_K3_WS(8);
+        else if (variant == 56) WISP_K3_WS(16);
+        else WISP_K3_WS(2);
+#undef WISP_K3_WS
+    } else
     switch (variant) {
         case 41: WISP_K3_LAUNCH(4, 1); break;      // 256 threads x (8 x 8 pairs), 246 registers
         case 42: WISP_K3_LAUNCH(4, 2); break;      // the same, frame loop unrolled twice (253 registers)
-        default: WISP_K3_LAUNCH(2, 1); break;      // 512 threads x (8 x 4 pairs), 124 registers: 4 warps per scheduler
+        default: WISP_K3_LAUNCH(2, 1); break;      // 21: 512 threads x (8 x 4 pairs), 124 registers: 4 warps per scheduler
     }
 #undef WISP_K3_LAUNCH
     ctx->launches++;
