@@ -26,7 +26,8 @@ namespace {
 
 constexpr int kPieceAtomsMax = 2048;
 constexpr int kStStages = 3;
-constexpr int kStThreads = 256;
+constexpr int kStThreads = 256;                            // compute threads (one lane pair per node)
+constexpr int kStLaunchThreads = kStThreads + 32;          // + the producer warp
 constexpr int kPieceNodesMax = kStThreads / 2;             // one lane pair per node, one pass per piece
 constexpr int kStageBytes = kPieceAtomsMax * 12 + 32;     // + slack for the 16-byte alignment shift
 
@@ -42,6 +43,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -129,14 +133,14 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
     return v;
 }
 
-__global__ void __launch_bounds__(kStThreads, 2)
+__global__ void __launch_bounds__(kStLaunchThreads, 2)
 com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piece* __restrict__ pieces,
                   int P, const double* __restrict__ shift, const int4* __restrict__ node_info,
                   const double* __restrict__ ent_mass, const double* __restrict__ inv_node_mass,
                   double* __restrict__ nodes, int64_t ld, int64_t row0, int64_t total_bytes,
                   double* __restrict__ colpart) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t full[kStStages];
+    __shared__ uint64_t full[kStStages], empty[kStStages];
     double* smass = reinterpret_cast<double*>(smem_raw + (size_t)kStStages * kStageBytes);
     const int tid = threadIdx.x;
     const int p = blockIdx.x % P;
@@ -147,14 +151,14 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
     const uint32_t piece_bytes = (uint32_t)pc.n_atoms * 12u;
 
     if (tid == 0) {
-        for (int s = 0; s < kStStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kStStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kStThreads / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // this CTA always works on the same piece: its per-atom masses live in shared memory and
     // its per-lane node descriptor in registers for the whole kernel
-    for (int i = tid; i < pc.n_atoms; i += kStThreads) smass[i] = 0.0;
+    for (int i = tid; i < pc.n_atoms; i += kStLaunchThreads) smass[i] = 0.0;
     __syncthreads();
-    for (int nl = tid; nl < pc.n_nodes; nl += kStThreads) {
+    for (int nl = tid; nl < pc.n_nodes; nl += kStLaunchThreads) {
         const int4 info = __ldg(node_info + pc.node0 + nl);
         for (int a = 0; a < info.y; ++a) smass[info.z + a] = __ldg(ent_mass + info.x + a);
     }
@@ -164,7 +168,7 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
     // rotated per node so that the 32 lanes of a warp read 32 different banks when nodes are
     // equally sized (16 atoms: float address 48 j + 6 u + 3 h, u rotated by j / 2).
     const int nl = tid >> 1, h = tid & 1;
-    const bool valid = nl < pc.n_nodes;
+    const bool valid = tid < kStThreads && nl < pc.n_nodes;
     int cnt_h = 0, rot = 0;
     uint32_t q_rel = 0, m_addr = 0;
     double inv_m = 0.0;
@@ -183,39 +187,45 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
     for (int o = 16; o > 0; o >>= 1) cnt_max = max(cnt_max, __shfl_xor_sync(0xffffffffu, cnt_max, o));
     __syncthreads();
 
-    // stage item k into slot k % kStStages: TMA bulk copy from the 16-byte-aligned address at or
-    // below the piece start; the last bytes of the whole buffer are copied by hand so the bulk
-    // copy never reads past the allocation.
-    auto stage_in = [&](int64_t k) {
-        const int64_t f = f_start + k * f_stride;
-        const int64_t src = (f * (int64_t)A + pc.atom0) * 12;
-        const int64_t src_al = src & ~(int64_t)15;
-        const uint32_t delta = (uint32_t)(src - src_al);
-        const uint32_t bytes = (delta + piece_bytes + 15u) & ~15u;
-        unsigned char* dst = smem_raw + (size_t)(k % kStStages) * kStageBytes;
-        if (src_al + bytes <= total_bytes) {
-            if (tid == 0) {
-                mbar_expect_tx(&full[k % kStStages], bytes);
-                bulk_g2s(dst, reinterpret_cast<const unsigned char*>(coords) + src_al, bytes,
-                         &full[k % kStStages]);
+    if (tid >= kStThreads) {
+        // ---------------- producer warp: stage item k into slot k % kStStages ----------------
+        // TMA bulk copy from the 16-byte-aligned address at or below the piece start; the last bytes
+        // of the whole buffer are copied by hand so the bulk copy never reads past the allocation.
+        const int lane = tid & 31;
+        for (int64_t k = 0; k < n_items; ++k) {
+            const int slot = (int)(k % kStStages);
+            const uint32_t ph = (uint32_t)((k / kStStages) & 1);
+            mbar_wait(&empty[slot], ph ^ 1);
+            const int64_t f = f_start + k * f_stride;
+            const int64_t src = (f * (int64_t)A + pc.atom0) * 12;
+            const int64_t src_al = src & ~(int64_t)15;
+            const uint32_t delta = (uint32_t)(src - src_al);
+            const uint32_t bytes = (delta + piece_bytes + 15u) & ~15u;
+            unsigned char* dst = smem_raw + (size_t)slot * kStageBytes;
+            if (src_al + bytes <= total_bytes) {
+                if (lane == 0) {
+                    mbar_expect_tx(&full[slot], bytes);
+                    bulk_g2s(dst, reinterpret_cast<const unsigned char*>(coords) + src_al, bytes, &full[slot]);
+                }
+            } else {
+                const float* sp = coords + (f * (int64_t)A + pc.atom0) * 3;
+                float* d = reinterpret_cast<float*>(dst + delta);
+                for (int i = lane; i < pc.n_atoms * 3; i += 32) d[i] = __ldg(sp + i);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_expect_tx(&full[slot], 0);   // plain arrival completes the phase
             }
-        } else {
-            const float* s = coords + (f * (int64_t)A + pc.atom0) * 3;
-            float* d = reinterpret_cast<float*>(dst + delta);
-            for (int i = tid; i < pc.n_atoms * 3; i += kStThreads) d[i] = __ldg(s + i);
-            if (tid == 0) mbar_expect_tx(&full[k % kStStages], 0);   // completes the phase
         }
-    };
+        return;
+    }
 
-    for (int64_t k = 0; k < kStStages && k < n_items; ++k) stage_in(k);
-
+    // ---------------- compute warps ----------------
     const uint32_t smem_base = smem_u32(smem_raw);
     double cs0 = 0.0, cs1 = 0.0;      // column sums of what this lane stores, over this CTA's frames
     for (int64_t k = 0; k < n_items; ++k) {
         const int slot = (int)(k % kStStages);
         const uint32_t ph = (uint32_t)((k / kStStages) & 1);
         mbar_wait(&full[slot], ph);
-        __syncthreads();     // manual-copy path: make the plain stores visible to every warp
         const int64_t f = f_start + k * f_stride;
         const int64_t src = (f * (int64_t)A + pc.atom0) * 12;
         const uint32_t q_addr = smem_base + (uint32_t)slot * kStageBytes + (uint32_t)(src & 15) + q_rel;
@@ -237,6 +247,8 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
                 u = (u + 1 == cnt_h) ? 0 : u + 1;
             }
         }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[slot]);      // this warp has read the stage
         ax += __shfl_xor_sync(0xffffffffu, ax, 1);
         ay += __shfl_xor_sync(0xffffffffu, ay, 1);
         az += __shfl_xor_sync(0xffffffffu, az, 1);
@@ -252,8 +264,6 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
                 cs0 += vz;
             }
         }
-        __syncthreads();     // everyone is done with this slot
-        if (k + kStStages < n_items) stage_in(k + kStStages);
     }
     if (colpart && valid) {           // row = this CTA's frame class; summed over rows in fixed order later
         double* o = colpart + f_start * ld + out_col;
@@ -406,7 +416,7 @@ int launch_com_plan(wisp_ctx* ctx, wisp_com_plan* pl, const float* d_coords, int
         WISP_TRY(wisp_scratch(ctx, SCR_COLSUM_PART, (size_t)per_piece * ld * 8, &p));
         d_colpart = (double*)p;
     }
-    com_stream_kernel<<<P * per_piece, kStThreads, smem, st>>>(
+    com_stream_kernel<<<P * per_piece, kStLaunchThreads, smem, st>>>(
         d_coords, T, pl->A, pl->d_pieces, P, pl->d_shift, pl->d_node_info, pl->d_ent_mass,
         pl->d_inv_node_mass, d_nodes, ld, row0, (int64_t)T * pl->A * 12, d_colpart);
     ctx->launches++;
