@@ -155,13 +155,17 @@ __global__ void center_kernel(double* __restrict__ x, int64_t T, int64_t ld, int
 // Centring fused with the FP32 tile-referenced copy K3 consumes:
 //   X[t][col] -= mean[col]                                   (in place, float64)
 //   P[t][tile][c][n] = float( x - ref_tile,c )               (x = un-centred value)
-// One CTA of 384 threads per (tile, frame): coalesced 3 KB read, transpose through shared
-// memory, coalesced 1.5 KB write.
+// One CTA of 384 threads per tile, kCcFrames frames per step: thread = column, so the 3 KB rows
+// of X are read and written coalesced; the (node, component) -> (component, node) transpose of P
+// goes through shared memory, 1.5 KB coalesced writes.  Each thread also keeps max|x| and sum x^2
+// of its centred column: the statistics the INT8 K2 engine scales by.
+constexpr int kCcFrames = 4;
+
 __global__ void __launch_bounds__(384)
 center_convert_kernel(double* __restrict__ x, int64_t T, int64_t ld, int N,
                       const double* __restrict__ mean, float* __restrict__ p32, int n_tiles,
                       double* __restrict__ stat) {
-    __shared__ float s[3][kTile + 1];
+    __shared__ float s[kCcFrames][3][kTile + 1];
     const int tile = blockIdx.x;
     const int k = threadIdx.x;
     const int64_t col = (int64_t)3 * kTile * tile + k;
@@ -170,16 +174,24 @@ center_convert_kernel(double* __restrict__ x, int64_t T, int64_t ld, int N,
     if (nref > N - 1) nref = N - 1;
     const double m = mean[col];
     const double ref = mean[3 * nref + c];
-    double amax = 0.0, ssq = 0.0;      // per column, over this block's frames: what the INT8 K2 scales by
-    for (int64_t t = blockIdx.y; t < T; t += gridDim.y) {
-        const double v = x[t * ld + col];
-        const double xc = v - m;
-        x[t * ld + col] = xc;
-        amax = fmax(amax, fabs(xc));
-        ssq = fma(xc, xc, ssq);
-        s[c][n] = (float)(v - ref);
+    double amax = 0.0, ssq = 0.0;
+    for (int64_t t0 = (int64_t)blockIdx.y * kCcFrames; t0 < T; t0 += (int64_t)gridDim.y * kCcFrames) {
+        double v[kCcFrames];
+#pragma unroll
+        for (int f = 0; f < kCcFrames; ++f) v[f] = (t0 + f < T) ? x[(t0 + f) * ld + col] : m;
+#pragma unroll
+        for (int f = 0; f < kCcFrames; ++f) {
+            const double xc = v[f] - m;
+            if (t0 + f < T) x[(t0 + f) * ld + col] = xc;
+            amax = fmax(amax, fabs(xc));
+            ssq = fma(xc, xc, ssq);
+            s[f][c][n] = (float)(v[f] - ref);
+        }
         __syncthreads();
-        p32[(t * n_tiles + tile) * (int64_t)(3 * kTile) + k] = s[k / kTile][k % kTile];
+#pragma unroll
+        for (int f = 0; f < kCcFrames; ++f)
+            if (t0 + f < T)
+                p32[((t0 + f) * n_tiles + tile) * (int64_t)(3 * kTile) + k] = s[f][k / kTile][k % kTile];
         __syncthreads();
     }
     if (stat) {                        // [gridDim.y][2][3 * 128 * n_tiles]
@@ -247,18 +259,20 @@ int launch_center(wisp_ctx* ctx, double* d_x, int64_t T, int64_t ld, int64_t nco
                   const double* d_mean, cudaStream_t st, float* d_p32, int N) {
     if (d_p32) {
         const int n_tiles = (int)(round_up(N, kTile) / kTile);
-        const int gy = (int)std::min<int64_t>(T, std::max<int64_t>(1, (int64_t)ctx->sm_count * 8 / n_tiles));
+        const int gy = (int)std::min<int64_t>((T + kCcFrames - 1) / kCcFrames,
+                                              std::max<int64_t>(1, (int64_t)ctx->sm_count * 8 / n_tiles));
+        const int parts = gy;
         // per-column statistics of the centred block ride along: the INT8 K2 engine takes them from
         // here instead of reading X once more, if the next wisp_dev_gram is on this very block
         void* p_stat = nullptr;
-        WISP_TRY(wisp_scratch(ctx, SCR_I8_STATS, (size_t)gy * 2 * 3 * kTile * n_tiles * 8, &p_stat));
+        WISP_TRY(wisp_scratch(ctx, SCR_I8_STATS, (size_t)parts * 2 * 3 * kTile * n_tiles * 8, &p_stat));
         center_convert_kernel<<<dim3(n_tiles, gy), 384, 0, st>>>(d_x, T, ld, N, d_mean, d_p32, n_tiles,
                                                                  (double*)p_stat);
         ctx->launches++;
         WISP_CUDA(cudaGetLastError());
         ctx->i8_stats_x = d_x;
         ctx->i8_stats_T = T;
-        ctx->i8_stats_parts = gy;
+        ctx->i8_stats_parts = parts;
         ctx->i8_stats_stream = st;
         return 0;
     }
