@@ -12,16 +12,15 @@
 // size (the reference stack itself casts ABSOLUTE coordinates to float32 inside
 // distance_array); the reference offset between two tiles is added once per staged j value.
 //
-// One CTA = one 128 x 128 pair tile (upper triangle only) x one frame segment; 512 threads,
-// each owns 8 x 4 pairs (measured variants: 31.1 ms at C2 against 31.5 ms for 256 threads x
-// 8 x 8 and 32.7 ms with the frame loop unrolled twice).  Frames are staged 8 at a time (float4
-// loads, double-buffered).  Per pair-frame: 3 sub + mul + 2 fma + MUFU.SQRT + add, the FP32
-// part issued as packed FADD2/FMUL2/FFMA2 over two pairs.  The MUFU pipe (16 lanes/clk/SM) is
-// the bound: the same instruction mix held in registers (tools/peaks.cu, k3mix) reaches 92-95 %
-// of the MUFU issue peak with the FP32 pipe at 83 %; this kernel, which also has to feed the
-// operands from shared memory through the same MIO queue the MUFU instructions use, reaches
-// 77 %.  FP32 partial sums are promoted every 128 frames into FP64 per-pair totals kept in
-// shared memory (128 KB), written once at the end.
+// One CTA = one 128 x 128 pair tile (upper triangle only) x one frame segment.  Per pair-frame:
+// 3 sub + mul + 2 fma + MUFU.SQRT + add, the FP32 part issued as packed FADD2/FMUL2/FFMA2 over
+// two pairs.  The MUFU pipe (16 lanes/clk/SM) is the bound, and the FP32 pipe is nearly
+// saturated with it (7 of every 8 cycles), so the production kernel is the warp-specialised
+// contact_sum_ws_kernel further down: compute warps run only the pair loop, a producer warp feeds
+// them by TMA.  contact_sum_kernel (in-warp staging, block barriers) is kept as the measured
+// baseline: 31.1 ms at C2 (512 threads x 8 x 4 pairs) / 31.5 ms (256 x 8 x 8) against 27.9 ms.
+// FP32 partial sums are promoted every 128 frames into FP64 per-pair totals kept in shared
+// memory (128 KB), written once at the end.
 #include "common.cuh"
 #include <cstdlib>
 
@@ -492,17 +491,13 @@ int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, cons
         contact_sum_ws_kernel<UN_><<<grid, kWsThreads, smem_ws, st>>>(d_p32, T, N, d_mean, n_tiles, n_seg, part, \
                                                                       n_pad);                                   \
     } while (0)
-        if (variant == 51) WISP_K3_WS(1);
-        else if (variant == 54) WISP_K3_WS(4);
-        else if (variant == 58) WISP_K3_WS(8);
-        else if (variant == 56) WISP_K3_WS(16);
-        else WISP_K3_WS(2);
+        if (variant == 51) WISP_K3_WS(1);      // frame loop not unrolled: 30.1 ms at C2 with 8-frame stages
+        else WISP_K3_WS(8);                    // 58 (default)
 #undef WISP_K3_WS
     } else
     switch (variant) {
         case 41: WISP_K3_LAUNCH(4, 1); break;      // 256 threads x (8 x 8 pairs), 246 registers
-        case 42: WISP_K3_LAUNCH(4, 2); break;      // the same, frame loop unrolled twice (253 registers)
-        default: WISP_K3_LAUNCH(2, 1); break;      // 21: 512 threads x (8 x 4 pairs), 124 registers: 4 warps per scheduler
+        default: WISP_K3_LAUNCH(2, 1); break;      // 21: 512 threads x (8 x 4 pairs), 126 registers: 4 warps per scheduler
     }
 #undef WISP_K3_LAUNCH
     ctx->launches++;
