@@ -377,10 +377,11 @@ def main():
                                    "(MEASURED_PEAKS.json has no FP64 figure); cuBLAS DGEMM 8192^3 = %.2f"
                                    % peaks["cublas_dgemm_tflops"]}
     else:
-        roofline = {"kernel": "contact_sum_kernel", "bound": "fp32/mufu pipe", "achieved": k3_rate / 1e12,
+        roofline = {"kernel": "contact_sum_ws_kernel", "bound": "fp32/mufu pipe", "achieved": k3_rate / 1e12,
                     "peak": peaks["mufu_sqrt_tops"], "unit": "Tsqrt/s", "frac": k3_rate / 1e12 / peaks["mufu_sqrt_tops"],
                     "traffic": None,
-                    "peak_source": "MUFU.SQRT issue peak measured with tools/peaks.cu (1 sqrt per pair-frame)"}
+                    "peak_source": "MUFU.SQRT issue peak measured with tools/peaks.cu (1 sqrt per pair-frame); the same "
+                                   "instruction mix held in registers tops out at %.2f T pair-frames/s" % peaks.get("k3_mix_tpairframes", 4.42)}
 
     if k2_engine == "int8 tcgen05":
         roofline_tensor = {"kernel": "gram_i8_kernel", "bound": "tensor", "achieved": k2_int8_tops, "peak": int8_peak,

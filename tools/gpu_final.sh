@@ -21,7 +21,7 @@ launches)
 full)
   CMD2="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-paths"
   timeout 300 $CMD2 > gpurun_out/plain2.log 2>&1 && \
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gram_i8|gram_dmma|contact_sum|com_stream|align_shift|center_convert|epilogue_kernel|slice_planes|node_stats' -s 9 -c 9 -o gpurun_out/prof_final -f $CMD2 > gpurun_out/ncu_full.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gram_i8|gram_dmma|contact_sum|com_stream|align_shift|center_convert|epilogue_kernel|slice_planes' -s 8 -c 8 -o gpurun_out/prof_final -f $CMD2 > gpurun_out/ncu_full.log 2>&1
   echo "ncu full rc=$?"
   ;;
 *) echo "usage: $0 bench|launches|full"; exit 2;;
