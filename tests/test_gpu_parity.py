@@ -698,3 +698,39 @@ def test_pipeline_int8_gram_vs_oracle(ctx):
     _, _, corr = oracle.pearson_correlation_fast(oracle.cartesian_covariance_fast(nodes, nodes.sum(axis=0) / t))
     assert_corr_close(out["corr"], corr)
     assert np.all(np.diagonal(out["corr"]) == 1.0) and np.array_equal(out["corr"], out["corr"].T)
+
+
+def test_known_answers_through_the_c_abi(ctx):
+    """Closed-form cases (tests/known_answers.py): perfectly correlated / mirrored /
+    orthogonal nodes, a rigid translation, an exact 3-4-5 contact geometry with the cutoff on a
+    distance, and a hand-enumerated graph with the node-0 rule and the K+1 return."""
+    from known_answers import (LADDER_PATHS_1_TO_5, correlated_trajectory, ladder_graph,
+                               lattice_contact_case, rigid_translation_trajectory)
+    nodes, want = correlated_trajectory()
+    avg = nodes.sum(axis=0) / nodes.shape[0]
+    _, _, corr = ctx.pearson_from_covariance(ctx.cartesian_covariance(nodes, avg))
+    np.testing.assert_allclose(corr, want, rtol=0, atol=1e-15)
+    assert np.all(np.diagonal(corr) == 1.0)
+    w = ctx.func_pearson(np.where(np.abs(want) == 1.0, want, 0.0), None)
+    assert np.all(w[:3, :3] == 0.0) and np.all(np.isinf(w[3, :3])) and w[3, 3] == 0.0
+
+    nodes, base = rigid_translation_trajectory()
+    avg = nodes.sum(axis=0) / nodes.shape[0]
+    _, _, corr = ctx.pearson_from_covariance(ctx.cartesian_covariance(nodes, avg))
+    np.testing.assert_allclose(corr, np.ones_like(corr), rtol=0, atol=1e-11)
+    binary, avgdist = ctx.contact_map(nodes, 7.5)
+    dist = np.sqrt(((base[:, None, :] - base[None, :, :]) ** 2).sum(-1))
+    np.testing.assert_allclose(avgdist, dist, rtol=1e-6, atol=1e-9)
+    assert_binary_equal_outside_ties(binary, dist, 7.5, ((dist < 7.5) & ~np.eye(len(base), dtype=bool)).astype(np.int64))
+
+    nodes, cutoff, binary_want, d = lattice_contact_case()
+    binary, avgdist = ctx.contact_map(nodes, cutoff)
+    np.testing.assert_allclose(avgdist, d, rtol=1e-6, atol=1e-9)
+    assert_binary_equal_outside_ties(binary, d, cutoff, binary_want)     # |p0 - p2| == cutoff is the tie
+    assert binary[0, 1] == 1 and binary[1, 2] == 1 and binary[0, 3] == 0 and np.all(np.diagonal(binary) == 0)
+
+    W = ladder_graph()
+    assert ctx.get_paths(W, [1], [5], 2) == LADDER_PATHS_1_TO_5[:3]       # K + 1: the seed rides along
+    assert ctx.get_paths(W, [1], [5], 3) == LADDER_PATHS_1_TO_5[:4]
+    assert ctx.get_paths(W, [0], [5], 1)[0] == [0.125, 0, 5]
+    assert ctx.get_paths(W, [1], [5], 4, node0_quirk=False) == LADDER_PATHS_1_TO_5[:4]
