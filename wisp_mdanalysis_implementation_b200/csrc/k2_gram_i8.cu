@@ -17,8 +17,8 @@
 // bound on the device and raises a flag that turns every kernel of this path into a no-op and lets
 // the DMMA kernel (k2_gram.cu), launched behind the same flag, produce the Gram instead.  The
 // diagonal G_ii is summed in plain FP64 (the dropped d2*d2 term is NOT zero-mean there).
-// K is cut into segments of <= 32768 rows so the int32 accumulators cannot overflow
-// (4 pairs x 128 x 128 x 32768 = 2^31 is not reached because |d0| <= 127); per-segment partial
+// K is cut into segments of <= 16384 rows so the int32 accumulators cannot overflow
+// (4 pairs x 128 x 128 x 16384 = 2^30); per-segment partial
 // tiles are reduced in FP64 in fixed order, like the DMMA kernel's: results are deterministic.
 //
 // Operand layout: digit planes are stored [plane][k = 3*frame + c][node] -- node-contiguous rows --
@@ -42,7 +42,7 @@ constexpr int kI8Stages = 6;
 constexpr int kI8Rows = 32;                       // k-rows per stage = K of one tcgen05.mma (i8)
 constexpr int kPlaneBytes = kI8Rows * 128;        // 4 KB: one plane tile of one operand
 constexpr int kI8StageBytes = 8 * kPlaneBytes;    // A planes 0..3, B planes 0..3
-constexpr int kSegRows = 32768;                   // K rows per CTA: 4 pairs x 128^2 x 32768 = 2^31 is never reached (|d0| <= 127)
+constexpr int kSegRows = 16384;                   // K rows per CTA: 4 digit pairs x 128^2 x 16384 = 2^30, half the int32 range
 constexpr int kI8Threads = 6 * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
