@@ -257,6 +257,12 @@ def golden_paths():
     for k in (2, 3, 4):
         paths = quiet(net.get_paths, W, [1], [2], k)
         cases.append((W.copy(), [1], [2], k, paths))
+    # the hand-enumerated ladder graph of tests/known_answers.py: the reference's own code confirms
+    # the answers derived on paper (node-0 rule, K+1 returns)
+    sys.path.insert(0, os.path.dirname(HERE))
+    from known_answers import ladder_graph
+    for so, si, k in (([1], [5], 2), ([1], [5], 3), ([0], [5], 1), ([5], [1], 2)):
+        cases.append((ladder_graph(), so, si, k, quiet(net.get_paths, ladder_graph(), so, si, k)))
     blob = {}
     for i, (W, so, si, k, paths) in enumerate(cases):
         blob["W%d" % i] = W

@@ -59,3 +59,22 @@ def test_ladder_graph_paths_by_hand():
     assert rev[0] == [0.125, 0, 5]
     # without the quirk the plain K shortest simple paths come back
     assert oracle.get_paths_pruned(W, [1], [5], 4, node0_quirk=False) == every[:4]
+
+
+def test_reference_code_confirms_the_hand_enumeration(golden_dir):
+    """tests/golden/get_paths.npz cases 11-14 are the ladder graph run through the reference's
+    own get_paths (make_golden.py): its output is the list derived on paper."""
+    import os
+    g = np.load(os.path.join(golden_dir, "get_paths.npz"))
+
+    def case(i):
+        off, nodes = g["offsets%d" % i], g["nodes%d" % i]
+        return [[float(g["lengths%d" % i][k])] + [int(x) for x in nodes[off[k]:off[k + 1]]]
+                for k in range(len(off) - 1)]
+    assert np.array_equal(g["W11"], ladder_graph())
+    assert case(11) == LADDER_PATHS_1_TO_5[:3]          # K = 2 -> 3 results
+    assert case(12) == LADDER_PATHS_1_TO_5[:4]          # K = 3 -> 4 results
+    assert case(13) == [[0.125, 0, 5]]
+    # 5 -> 1: same paths, stored in the orientation they were enumerated in
+    assert [p[0] for p in case(14)] == [0.25, 0.5, 0.625]
+    assert case(14)[0][1:] in ([5, 0, 1], [1, 0, 5])
