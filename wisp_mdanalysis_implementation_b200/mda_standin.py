@@ -237,6 +237,8 @@ class Universe:
             return tokens[pos[0]] if pos[0] < len(tokens) else None
 
         def take():
+            if pos[0] >= len(tokens):
+                raise ValueError("selection %r ends unexpectedly" % sel)
             tok = tokens[pos[0]]
             pos[0] += 1
             return tok
