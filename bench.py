@@ -392,10 +392,15 @@ def main():
         roofline_tensor = {"kernel": "gram_dmma_kernel<3>", "bound": "tensor", "achieved": k2_tflops,
                            "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
                            "frac": k2_tflops / peaks["fp64_dmma_tflops"], "traffic": None}
+    # the HBM-bound stage of the path (K1 = landmark gather + streaming COM), in the contract's own terms
+    roofline_hbm = {"kernel": "align_shift_kernel + com_stream_kernel", "bound": "hbm", "achieved": k1_gbs,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": k1_gbs / peaks["hbm_gbs"], "traffic": None,
+                    "peak_source": peaks["source_hbm"]}
     try:
         ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
         roofline["traffic"] = ncu.get(roofline["kernel"].split("<")[0])
         roofline_tensor["traffic"] = ncu.get(roofline_tensor["kernel"].split("<")[0])
+        roofline_hbm["traffic"] = ncu.get("com_stream_kernel", 0.0) + ncu.get("align_shift_kernel", 0.0)
     except Exception:
         pass
 
@@ -595,7 +600,7 @@ def main():
                               "(accuracy-gated, DMMA FP64 fallback), K3 per-frame distances FP32 with FP64 sums",
                 "config": workload_config(args), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
-                "roofline": roofline, "roofline_tensor": roofline_tensor, "kernels": kernels, "cpu_baseline": cpu_baseline, "extra": extra}
+                "roofline": roofline, "roofline_tensor": roofline_tensor, "roofline_hbm": roofline_hbm, "kernels": kernels, "cpu_baseline": cpu_baseline, "extra": extra}
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
     if world > 1:
