@@ -361,7 +361,10 @@ def main():
         "k2_gram_dmma": {"ms": k2_dmma_ms, "bound": "tensor(fp64)", "achieved_tflops": k2_dmma_tflops,
                          "peak_tflops": peaks["fp64_dmma_tflops"],
                          "frac": k2_dmma_tflops / peaks["fp64_dmma_tflops"],
-                         "frac_of_cublas_dgemm": k2_dmma_tflops / peaks["cublas_dgemm_tflops"]},
+                         "frac_of_cublas_dgemm": k2_dmma_tflops / peaks["cublas_dgemm_tflops"],
+                         # the same pass with K2 pinned to the FP64 engine (WISP_K2_MODE=dmma)
+                         "pass_ms_with_this_engine": ms_step - k2_ms + k2_dmma_ms,
+                         "value_with_this_engine": float(N) * N * T / ((ms_step - k2_ms + k2_dmma_ms) * 1e-3)},
         "k3_contact": {"ms": k3_ms, "bound": "mufu/fp32", "achieved_tpairframes": k3_rate / 1e12,
                        "mufu_peak_tops": peaks["mufu_sqrt_tops"],
                        "frac_mufu": k3_rate / 1e12 / peaks["mufu_sqrt_tops"],
