@@ -467,6 +467,34 @@ def test_frame_pipeline_int8_engine_vs_oracle(ctx):
         assert_binary_equal_outside_ties(out["binary"], avgdist, 13.0, binary)
 
 
+def test_streamed_blocks_on_the_int8_engine(ctx):
+    """run_host_streamed with two 4100-frame blocks: each block is centred with the provisional
+    reference, goes through the INT8 K2 engine on the side stream, and the parallel-axis term is
+    removed in the epilogue -- against the oracle on the whole trajectory."""
+    import torch
+    from wisp_mdanalysis_implementation_b200.pipeline import FramePipeline
+    n, t, apn = 130, 8200, 3
+    system, coords = synth.synth(n, t, apn, seed=44)
+    nodes, _ = oracle.com_nodes(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx)
+    _, _, corr = oracle.pearson_correlation_fast(oracle.cartesian_covariance_fast(nodes, nodes.sum(axis=0) / t))
+    binary, avgdist = oracle.calc_contact_map_fast(nodes, 13.0)
+    pipe = FramePipeline(ctx, n, system.n_atoms, system.masses, system.node_ptr, system.atom_idx,
+                         system.align_idx, frames_local=t, cutoff=13.0, which_map=1)
+    # the returned arrays are views of the pipeline's pinned output buffers: copy before the next run
+    out = {k: v.copy() for k, v in pipe.run_host_streamed(torch.from_numpy(coords).pin_memory(), n_blocks=2).items()}
+    assert_corr_close(out["corr"], corr)
+    assert np.all(np.diagonal(out["corr"]) == 1.0)
+    np.testing.assert_allclose(out["avgdist"], avgdist, rtol=1e-6, atol=1e-9)
+    assert_binary_equal_outside_ties(out["binary"], avgdist, 13.0, binary)
+    ctx.set_gram_mode("dmma")
+    try:
+        out_f64 = pipe.run_host_streamed(torch.from_numpy(coords).pin_memory(), n_blocks=2)
+    finally:
+        ctx.set_gram_mode("auto")
+    assert not np.array_equal(out["corr"], out_f64["corr"])          # the INT8 engine really ran
+    assert np.abs(out["corr"] - out_f64["corr"]).max() < 1e-9
+
+
 def test_paths_prepare_query_stress(ctx):
     """configs[4] in miniature: one APSP, many independent (source, sink) queries."""
     W = synth.random_cost_matrix(60, seed=77, density=0.12, lo=0.05, hi=0.9)

@@ -180,7 +180,10 @@ class FramePipeline:
         waits for the global mean: every block is centred with a provisional reference r (the
         mean of the first block, broadcast from rank 0), and the exact parallel-axis term
         (s_i . s_j)/T with s = sum_t (x - r) is removed in the epilogue -- so the ranks exchange
-        a SINGLE all-reduce of [G || D || s]."""
+        a SINGLE all-reduce of [G || D || s].
+
+        Like run_host, returns numpy views of the pipeline's pinned output buffers: they are
+        overwritten by the next run_host / run_host_streamed call -- copy what must outlive it."""
         main = torch.cuda.current_stream(self.dev)
         side = self.k23_stream
         if self._stage is None:
