@@ -98,3 +98,59 @@ def test_two_rank_pair_queries_gather_in_order(tmp_path):
     mp.spawn(_pairs_worker, args=(2, port, pairs, str(tmp_path)), nprocs=2, join=True)
     with open(tmp_path / "pairs.pkl", "rb") as f:
         assert pickle.load(f) == want
+
+
+def _streamed_pass(nodes, lo, hi, rank, n_blocks=2):
+    """numpy stand-in for FramePipeline.run_host_streamed: blocks centred with a provisional
+    reference (mean of rank 0's first block, broadcast), ONE all-reduce of [G || D || s], exact
+    parallel-axis correction afterwards (what K4 does with d_offset_sum)."""
+    T, N, _ = nodes.shape
+    x = nodes[lo:hi].reshape(hi - lo, 3 * N)
+    bounds = np.linspace(0, hi - lo, n_blocks + 1).astype(int)
+    ref = torch.from_numpy(x[bounds[0]:bounds[1]].mean(axis=0).copy())
+    if sharding.is_distributed():
+        dist.broadcast(ref, src=0)
+    ref = ref.numpy()
+    g = np.zeros((N, N))
+    d = np.zeros((N, N))
+    for b in range(n_blocks):
+        xb = x[bounds[b]:bounds[b + 1]] - ref
+        g += np.einsum("tic,tjc->ij", xb.reshape(-1, N, 3), xb.reshape(-1, N, 3))
+        pos = x[bounds[b]:bounds[b + 1]].reshape(-1, N, 3)        # distances do not care about the reference
+        d += np.sqrt(((pos[:, :, None, :] - pos[:, None, :, :]) ** 2).sum(-1)).sum(axis=0)
+    s = (x - ref).sum(axis=0)
+    flat = torch.from_numpy(np.concatenate([g.ravel(), d.ravel(), s]))
+    sharding.reduce_sums(flat)
+    flat = flat.numpy()
+    g, d, s = flat[:N * N].reshape(N, N), flat[N * N:2 * N * N].reshape(N, N), flat[2 * N * N:].reshape(N, 3)
+    return g - (s @ s.T) / T, d, ref + s.reshape(-1) / T
+
+
+def _streamed_worker(rank, world, port, nodes, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = sharding.frame_range(nodes.shape[0], rank, world)
+    g, d, mean = _streamed_pass(nodes, lo, hi, rank)
+    np.savez(os.path.join(out_dir, "streamed_%d.npz" % rank), g=g, d=d, mean=mean)
+    dist.destroy_process_group()
+
+
+def test_two_rank_streamed_protocol_matches_centred_gram(tmp_path):
+    """The host-fed mode's single-collective protocol: provisional reference + parallel-axis
+    correction gives the mean-centred Gram, the distance sums and the mean of one rank."""
+    rng = np.random.default_rng(3)
+    nodes = rng.normal(size=(53, 7, 3)) + rng.normal(scale=20, size=(1, 7, 3))
+    T, N, _ = nodes.shape
+    xc = nodes - nodes.mean(axis=0)
+    want_g = np.einsum("tic,tjc->ij", xc, xc)
+    want_d = np.sqrt(((nodes[:, :, None, :] - nodes[:, None, :, :]) ** 2).sum(-1)).sum(axis=0)
+    g1, d1, m1 = _streamed_pass(nodes, 0, T, 0)                       # no process group
+    np.testing.assert_allclose(g1, want_g, rtol=1e-10, atol=1e-9)
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_streamed_worker, args=(2, port, nodes, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        got = np.load(tmp_path / ("streamed_%d.npz" % r))
+        np.testing.assert_allclose(got["g"], want_g, rtol=1e-10, atol=1e-9)
+        np.testing.assert_allclose(got["d"], want_d, rtol=1e-12)
+        np.testing.assert_allclose(got["mean"], nodes.mean(axis=0).reshape(-1), rtol=1e-13)
