@@ -96,3 +96,36 @@ def test_lmi_golden(golden_dir, tag):
     rmi_d, func_d = oracle.generalized_correlation_coefficient_calc(g["mi"], g["avgdist"], 5.0)
     np.testing.assert_allclose(rmi_d, g["rmi_damped"], rtol=1e-15)
     np.testing.assert_allclose(func_d, g["func_mi_damped"], rtol=1e-13)
+
+
+def test_pruned_enumerator_equals_literal_on_random_graphs():
+    """The GPU parity tests use oracle.get_paths_pruned at sizes where the literal transliteration
+    of the reference loop is too slow; here the two are held together on many small random graphs
+    (single and multiple sources / sinks, node 0 in every role, sparse and dense)."""
+    from wisp_mdanalysis_implementation_b200 import synth
+    rng = np.random.default_rng(20260101)
+    checked = k_plus_1 = 0
+    for trial in range(60):
+        n = int(rng.integers(6, 12))
+        W = synth.random_cost_matrix(n, seed=int(rng.integers(1 << 30)), density=float(rng.uniform(0.3, 0.8)),
+                                     lo=0.05, hi=0.7)
+        ns, nt = (1, 1) if trial % 3 else (2, 2)
+        so = [int(x) for x in rng.choice(n, size=ns, replace=False)]
+        si = [int(x) for x in rng.choice(n, size=nt, replace=False)]
+        if all(s == t for s in so for t in si):
+            continue
+        K = int(rng.integers(2, 9))
+        D, _ = oracle.apsp_dijkstra(W)
+        if not any(np.isfinite(D[s, t]) for s in so for t in si if s != t):
+            continue
+        try:
+            lit = oracle.get_paths(W, so, si, K, max_passes=80)
+        except RuntimeError:                     # fewer than K simple paths: the reference never returns
+            continue
+        pru = oracle.get_paths_pruned(W, so, si, K)
+        assert len(pru) == len(lit), (trial, len(pru), len(lit))
+        for a, b in zip(pru, lit):
+            assert [int(x) for x in a[1:]] == [int(x) for x in b[1:]] and float(a[0]) == float(b[0]), (trial, a, b)
+        checked += 1
+        k_plus_1 += len(lit) == K + 1
+    assert checked >= 30
