@@ -7,6 +7,8 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cerrno>
+#include <charconv>
+#include <cmath>
 #include <cstdlib>
 #include <thread>
 
@@ -65,7 +67,15 @@ extern "C" int wisp_savetxt_f64(const char* path, const double* a, int64_t rows,
                                 const char* header) {
     WISP_CHECK(path && a && rows >= 0 && cols >= 1, "savetxt_f64: bad argument");
     return save_matrix(path, a, rows, cols, header,
-                       [](char* buf, double v) { return snprintf(buf, 64, "%.18e", v); }, 26);
+                       [](char* buf, double v) {
+                           // std::to_chars(scientific, 18) is specified to print what printf("%.18e") prints,
+                           // correctly rounded (Ryu-printf in libstdc++), at ~10x the speed of glibc's printf
+                           if (std::isfinite(v)) {
+                               auto r = std::to_chars(buf, buf + 64, v, std::chars_format::scientific, 18);
+                               if (r.ec == std::errc()) return (int)(r.ptr - buf);
+                           }
+                           return snprintf(buf, 64, "%.18e", v);
+                       }, 26);
 }
 
 extern "C" int wisp_savetxt_i64(const char* path, const int64_t* a, int64_t rows, int64_t cols,
