@@ -26,6 +26,21 @@ def test_savetxt_matches_numpy_bytes(tmp_path):
     assert (tmp_path / "npv.dat").read_bytes() == (tmp_path / "cv.dat").read_bytes()
 
 
+def test_savetxt_extreme_values_match_numpy_bytes(tmp_path):
+    """Every decade of the double range, denormals, the largest double, halfway decimal cases."""
+    rng = np.random.default_rng(7)
+    wide = rng.normal(size=6000) * 10.0 ** rng.integers(-300, 300, size=6000)
+    special = np.array([0.0, -0.0, 5e-324, -5e-324, 4.35e-320, 2.2250738585072014e-308, 2.225073858507201e-308,
+                        1.7976931348623157e308, -1.7976931348623157e308, 1.0, -1.0, 0.1, 1 / 3, 0.5, 2.5, 1e22,
+                        9.999999999999999e22, 1e23, 123456789.123456789, 1.0000000000000002, 0.9999999999999999])
+    a = np.concatenate([wide, special])
+    a = np.concatenate([a, np.zeros((-len(a)) % 3)]).reshape(-1, 3)
+    np.savetxt(tmp_path / "np.dat", a)
+    _lib.savetxt(str(tmp_path / "c.dat"), a)
+    assert (tmp_path / "np.dat").read_bytes() == (tmp_path / "c.dat").read_bytes()
+    assert np.array_equal(_lib.loadtxt(str(tmp_path / "c.dat")), a)
+
+
 def test_loadtxt_round_trip(tmp_path):
     rng = np.random.default_rng(1)
     a = rng.normal(size=(301, 77))
