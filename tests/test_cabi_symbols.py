@@ -63,3 +63,42 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_stage_functions_fail_loudly_without_gpu(tmp_path):
+    """Every reference-facing stage function raises instead of computing anything on the CPU when
+    there is no B200: nothing in the product path can quietly fall back."""
+    import sys
+    import numpy as np
+    import torch
+    from wisp_mdanalysis_implementation_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    _lib._default_ctx.clear()
+    pkg = os.path.join(ROOT, "wisp_mdanalysis_implementation_b200")
+    sys.path.insert(0, pkg)
+    try:
+        import adjacency_matrix_functions as amf
+        import functionalize_adj_matrix_functions as faf
+        import network_analysis_functions as naf
+        import trajectory_analysis_functions as taf
+    finally:
+        sys.path.remove(pkg)
+    out = str(tmp_path) + os.sep
+    rng = np.random.default_rng(0)
+    nodes = rng.normal(size=(8, 4, 3))
+    w = np.abs(rng.normal(size=(5, 5)))
+    w = w + w.T
+    np.fill_diagonal(w, 0.0)
+    calls = [
+        lambda: taf.cartesian_covariance(nodes, nodes.mean(axis=0), out),
+        lambda: taf.calc_contact_map(nodes, out, 9.0),
+        lambda: amf.pearson_correlation_analysis(np.eye(12), out),
+        lambda: amf.linear_mutual_information_analysis(np.eye(12), out),
+        lambda: faf.func_pearson_correlation(np.full((4, 4), 0.5), out),
+        lambda: naf.get_paths(w, [0], [4], 2),
+    ]
+    for call in calls:
+        with pytest.raises(_lib.WispError):
+            call()
+    assert not any(f.endswith(".dat") for f in os.listdir(tmp_path))      # and nothing was written
