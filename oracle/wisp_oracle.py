@@ -22,7 +22,7 @@ import heapq
 import numpy as np
 
 __all__ = [
-    "center_of_mass", "com_nodes", "rotation_matrix", "iterative_alignment",
+    "center_of_mass", "com_nodes", "com_nodes_fast", "rotation_matrix", "iterative_alignment",
     "traj_alignment_and_averaging",
     "cartesian_covariance", "cartesian_covariance_fast",
     "pearson_correlation_analysis", "pearson_correlation_fast", "node_gram_truth",
@@ -75,6 +75,51 @@ def com_nodes(coords, masses, node_ptr, atom_idx, align_idx, node_definition="CO
             else:
                 all_pos_Nodes[ts, i] = center_of_mass(pos[idx], masses[idx])   # :76
     return all_pos_Nodes, all_pos_Align
+
+
+def com_nodes_fast(coords, masses, node_ptr, atom_idx, align_idx, node_definition="COM", block=64):
+    """Frame-blocked vectorised form of :func:`com_nodes` (trajectory_analysis_functions.py:70-79)
+    for the large parity cases: the same float64 operations in the same order per node
+    (sequential sum over the node's atoms, then one division), so the result is bit-identical
+    (tests/test_oracle_golden.py::test_com_nodes_fast_is_bit_identical)."""
+    coords = np.asarray(coords, dtype=np.float32)
+    masses = np.asarray(masses, dtype=np.float64)
+    node_ptr = np.asarray(node_ptr, dtype=np.int64)
+    atom_idx = np.asarray(atom_idx, dtype=np.int64)
+    align_idx = np.asarray(align_idx, dtype=np.int64)
+    T = coords.shape[0]
+    N = len(node_ptr) - 1
+    out = np.empty((T, N, 3), dtype=np.float64)
+    out_align = np.empty((T, len(align_idx), 3), dtype=np.float32)
+    atomic = node_definition.upper() == "ATOMIC"
+    m_al = masses[align_idx]
+    m_nodes = masses[atom_idx]
+    sizes = np.diff(node_ptr)
+    kmax = int(sizes.max())
+    for t0 in range(0, T, block):
+        pos = coords[t0:t0 + block].astype(np.float64)                          # (b, A, 3)
+        pa = pos[:, align_idx, :] * m_al[None, :, None]
+        s = np.zeros((pos.shape[0], 3))
+        for k in range(pa.shape[1]):                                             # np.sum(axis=0): row by row
+            s += pa[:, k, :]
+        shift = -(s / m_al.sum())                                               # :71
+        pos = (pos + shift[:, None, :]).astype(np.float32)                      # translate, float32 store
+        out_align[t0:t0 + block] = pos[:, align_idx, :]                         # :72
+        if atomic:
+            out[t0:t0 + block] = pos[:, atom_idx[node_ptr[:-1]], :]            # :78
+            continue
+        acc = np.zeros((pos.shape[0], N, 3))
+        msum = np.zeros(N)
+        for k in range(kmax):                                                    # k-th atom of every node
+            live = sizes > k
+            idx = atom_idx[node_ptr[:-1][live] + k]
+            mk = m_nodes[node_ptr[:-1][live] + k]
+            acc[:, live, :] += pos[:, idx, :].astype(np.float64) * mk[None, :, None]
+            msum[live] += mk
+        # m.sum() of the literal form is numpy's pairwise sum; recompute it exactly per node
+        msum = np.array([masses[atom_idx[node_ptr[i]:node_ptr[i + 1]]].sum() for i in range(N)])
+        out[t0:t0 + block] = acc / msum[None, :, None]                          # :76
+    return out, out_align
 
 
 # ----------------------------------------------------------------------------------------

@@ -762,3 +762,138 @@ def test_known_answers_through_the_c_abi(ctx):
     assert ctx.get_paths(W, [1], [5], 3) == LADDER_PATHS_1_TO_5[:4]
     assert ctx.get_paths(W, [0], [5], 1)[0] == [0.125, 0, 5]
     assert ctx.get_paths(W, [1], [5], 4, node0_quirk=False) == LADDER_PATHS_1_TO_5[:4]
+
+
+# ---------------------------------------------------------------------------------------
+# parity at the sizes bench.py publishes numbers for (VERDICT r1 "What's weak" 1-3)
+# ---------------------------------------------------------------------------------------
+def _oracle_on_node_subset(system, coords, sel, cutoff):
+    """Oracle correlation / mean distances for the nodes `sel` only: every entry (i, j) of
+    both matrices depends on nodes i and j alone, so the oracle run on a node subset IS the
+    corresponding sub-block of the full result."""
+    ptr = np.concatenate([[0], np.cumsum(np.diff(system.node_ptr)[sel])]).astype(np.int64)
+    idx = np.concatenate([system.atom_idx[system.node_ptr[i]:system.node_ptr[i + 1]] for i in sel])
+    nodes, _ = oracle.com_nodes_fast(coords, system.masses, ptr, idx, system.align_idx)
+    avg = nodes.sum(axis=0) / nodes.shape[0]
+    _, _, corr = oracle.pearson_correlation_fast(oracle.cartesian_covariance_fast(nodes, avg))
+    binary, avgdist = oracle.calc_contact_map_fast(nodes, cutoff)
+    return nodes, corr, binary, avgdist
+
+
+def _check_subset(out, sel, corr, binary, avgdist, cutoff):
+    ix = np.ix_(sel, sel)
+    assert_corr_close(out["corr"][ix], corr)
+    np.testing.assert_allclose(out["avgdist"][ix], avgdist, rtol=1e-6, atol=1e-9)
+    assert_binary_equal_outside_ties(out["binary"][ix], avgdist, cutoff, binary)
+
+
+def test_published_config_c2_vs_oracle(ctx):
+    """configs[1] geometry -- 2,000 nodes x 16 atoms, 16 node tiles with a partial last tile --
+    at 8,200 frames: the tcgen05 INT8 K2 engine, the K3 frame segments and the tile-referenced
+    FP32 copy all run exactly as in the bench.  wisp_pipeline, FramePipeline.run_device and
+    run_host_streamed against the oracle on 288 nodes drawn from every tile (82,944 of the
+    4,000,000 matrix entries; each entry depends on its two nodes only)."""
+    import torch
+    from wisp_mdanalysis_implementation_b200.pipeline import FramePipeline
+    n, t, apn, cutoff = 2000, 8200, 16, 15.0
+    system = synth.SynthSystem(n, t, apn, seed=1002)
+    coords = system.coords()
+    rng = np.random.default_rng(5)
+    sel = np.unique(np.concatenate([rng.choice(n, size=250, replace=False),
+                                    [0, 1, 127, 128, 129, 1919, 1920, 1921, 1998, 1999]]))
+    _, corr, binary, avgdist = _oracle_on_node_subset(system, coords, sel, cutoff)
+    out = ctx.pipeline(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx,
+                       cutoff=cutoff, which_map=1)
+    _check_subset(out, sel, corr, binary, avgdist, cutoff)
+    assert np.all(np.diagonal(out["corr"]) == 1.0) and np.array_equal(out["corr"], out["corr"].T)
+    pipe = FramePipeline(ctx, n, system.n_atoms, system.masses, system.node_ptr, system.atom_idx,
+                         system.align_idx, frames_local=t, cutoff=cutoff, which_map=1)
+    h = torch.from_numpy(coords).pin_memory()
+    d_coords = h.cuda()
+    pipe.run_device(d_coords)
+    torch.cuda.synchronize()
+    dev = dict(corr=pipe.d_corr.cpu().numpy(), avgdist=pipe.d_avgdist.cpu().numpy(),
+               binary=pipe.d_binary.cpu().numpy())
+    _check_subset(dev, sel, corr, binary, avgdist, cutoff)
+    # the INT8 engine really ran: the FP64 DMMA engine gives different bits, same numbers
+    ctx.set_gram_mode("dmma")
+    try:
+        pipe.gram()
+        pipe.reduce_and_epilogue()
+        torch.cuda.synchronize()
+        f64 = pipe.d_corr.cpu().numpy()
+    finally:
+        ctx.set_gram_mode("auto")
+    assert not np.array_equal(f64, dev["corr"]) and np.abs(f64 - dev["corr"]).max() < 1e-9
+    del d_coords
+    _check_subset(pipe.run_host_streamed(h, n_blocks=2), sel, corr, binary, avgdist, cutoff)
+
+
+@pytest.mark.parametrize("kind", ["bimodal", "heavy_tailed", "drift"])
+def test_gram_int8_gate_on_md_like_columns(ctx, kind):
+    """The INT8 engine's accuracy gate on what real MD columns look like:
+    side chains flipping between two rotamers (bimodal), heavy-tailed excursions (Student t,
+    3 degrees of freedom) and slow drift.  Whatever the dispatcher decides, the result must meet
+    the bar |dG| <= 1e-9 sqrt(G_ii G_jj); when the gate keeps the tensor-core path the bits differ
+    from DMMA, when it trips they are DMMA's."""
+    import torch
+    from wisp_mdanalysis_implementation_b200 import _lib
+    n, t = 260, 6000
+    rng = np.random.default_rng({"bimodal": 1, "heavy_tailed": 2, "drift": 3}[kind])
+    if kind == "bimodal":
+        state = np.cumsum(rng.random((t, 3 * n)) < 0.002, axis=0) % 2          # rare flips
+        xh = (2.0 * state - 1.0) * rng.uniform(0.5, 3.0, size=3 * n) + rng.normal(scale=0.3, size=(t, 3 * n))
+        xh[:, ::7] = rng.normal(scale=0.4, size=(t, len(range(0, 3 * n, 7))))  # and some quiet columns
+    elif kind == "heavy_tailed":
+        xh = rng.standard_t(3, size=(t, 3 * n)) * rng.uniform(0.2, 2.0, size=3 * n)
+    else:
+        xh = np.cumsum(rng.normal(scale=0.05, size=(t, 3 * n)), axis=0) + rng.normal(scale=0.3, size=(t, 3 * n))
+    xh -= xh.mean(axis=0)
+    ld, tp = _lib.node_ld(n), _lib.frames_pad(t)
+    x = torch.zeros(tp, ld, dtype=torch.float64, device="cuda")
+    x[:t, :3 * n] = torch.from_numpy(xh).cuda()
+    nodes = xh.reshape(t, n, 3)
+    truth = np.triu(np.einsum("tic,tjc->ij", nodes, nodes))
+    dg = np.sqrt(np.outer(np.diag(truth), np.diag(truth)))
+    g_dmma = _gram(ctx, "dmma", x, t, ld, n)
+    g_auto = _gram(ctx, "auto", x, t, ld, n)
+    assert (np.abs(g_dmma - truth) / dg).max() < 1e-12
+    assert (np.abs(g_auto - truth) / dg).max() < 1e-9, kind
+    # the un-gated tensor-core kernel on the same data: how far the bound is from being needed
+    g_forced = _gram(ctx, "i8", x, t, ld, n, forced=True)
+    err_forced = (np.abs(g_forced - truth) / dg).max()
+    took_i8 = not np.array_equal(g_auto, g_dmma)
+    if not took_i8:
+        assert np.array_equal(g_auto, g_dmma)
+    else:
+        assert np.array_equal(g_auto, g_forced)
+    print("%s: engine=%s, forced-int8 error %.2e" % (kind, "int8" if took_i8 else "dmma (gate)", err_forced))
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-12), (32, 2e-6)])
+def test_apsp_c3_size_vs_scipy_dijkstra(ctx, precision, tol):
+    """configs[2] size: 10,000 nodes, sparse contact-map-like graph (mean degree 10), against
+    scipy's C Dijkstra from 300 sources (rows of the all-pairs result)."""
+    import scipy.sparse
+    import scipy.sparse.csgraph
+    n = 10000
+    W = synth.random_cost_matrix(n, seed=1003, density=10.0 / n, lo=0.05, hi=3.0)
+    rng = np.random.default_rng(0)
+    src = np.sort(rng.choice(n, size=300, replace=False))
+    want, want_pred = scipy.sparse.csgraph.dijkstra(scipy.sparse.csr_matrix(W), directed=True, indices=src,
+                                                    return_predecessors=True)
+    dist, pred = ctx.apsp(W, precision=precision)
+    assert np.all(np.isfinite(dist))
+    np.testing.assert_allclose(dist[src], want, rtol=tol, atol=1e-300)
+    assert np.all(np.diagonal(dist) == 0) and np.all(np.diagonal(pred) == -1)
+    # predecessors: every pred is a real edge on a shortest path; in FP64 (unique shortest paths
+    # on random real weights) they are the same tree scipy found
+    jj = np.arange(n)
+    for r, s in enumerate(src[:40]):
+        p = pred[s]
+        ok = jj != s
+        assert np.all(p[ok] >= 0)
+        assert np.all(W[p[ok], jj[ok]] != 0)
+        np.testing.assert_allclose(dist[s, p[ok]] + W[p[ok], jj[ok]], dist[s, ok], rtol=10 * tol, atol=1e-12)
+        if precision == 64:
+            assert np.array_equal(p[ok], want_pred[r][ok])

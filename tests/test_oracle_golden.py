@@ -129,3 +129,28 @@ def test_pruned_enumerator_equals_literal_on_random_graphs():
         checked += 1
         k_plus_1 += len(lit) == K + 1
     assert checked >= 30
+
+
+def test_com_nodes_fast_is_bit_identical(golden_dir):
+    """The vectorised COM form used by the large GPU parity cases equals the literal per-frame /
+    per-node loop bit for bit: on the golden coordinates (which pin the literal form to the
+    reference's own output) and on ragged / ATOMIC node maps."""
+    g = np.load(os.path.join(golden_dir, "traj_small.npz"))
+    a, al = oracle.com_nodes(g["coords"], g["masses"], g["node_ptr"], g["atom_idx"], g["align_idx"])
+    b, bl = oracle.com_nodes_fast(g["coords"], g["masses"], g["node_ptr"], g["atom_idx"], g["align_idx"], block=7)
+    assert np.array_equal(a, b) and np.array_equal(al, bl)
+    rng = np.random.default_rng(0)
+    coords = (rng.normal(size=(23, 90, 3)) * 20).astype(np.float32)
+    masses = rng.uniform(1, 32, size=90)
+    ptr, idx = [0], []
+    for _ in range(17):
+        k = int(rng.integers(1, 19))
+        idx += list(rng.choice(90, size=k, replace=False))
+        ptr.append(len(idx))
+    align = rng.choice(90, size=31, replace=False)
+    a, al = oracle.com_nodes(coords, masses, np.array(ptr), np.array(idx), align)
+    b, bl = oracle.com_nodes_fast(coords, masses, np.array(ptr), np.array(idx), align)
+    assert np.array_equal(a, b) and np.array_equal(al, bl)
+    a, _ = oracle.com_nodes(coords, masses, np.arange(18), np.array(idx[:17]), align, "ATOMIC")
+    b, _ = oracle.com_nodes_fast(coords, masses, np.arange(18), np.array(idx[:17]), align, "ATOMIC")
+    assert np.array_equal(a, b)
