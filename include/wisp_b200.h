@@ -210,6 +210,13 @@ int wisp_dev_fw32_init_rows(wisp_ctx* ctx, const double* d_w_rows, int N, int64_
 int wisp_dev_fw32_pivot_panel(wisp_ctx* ctx, float* d_panel, int N, int kb, void* stream);
 int wisp_dev_fw32_update_rows(wisp_ctx* ctx, float* d_dist_local, int64_t rows_pad, const float* d_panel,
                               int N, int kb, int skip_local_tile, void* stream);
+/* The same update split for look-ahead: part 1 = only local tile-row next_local_tile (the NEXT
+ * pivot rows, on their owner), part 2 = everything part 1 left out, part 0 = everything.  The owner
+ * of the next pivot rows runs part 1, builds and broadcasts the next panel on a second stream, and
+ * runs part 2 meanwhile. */
+int wisp_dev_fw32_update_rows_part(wisp_ctx* ctx, float* d_dist_local, int64_t rows_pad, const float* d_panel,
+                                   int N, int kb, int skip_local_tile, int next_local_tile, int part,
+                                   void* stream);
 
 /* synthetic coordinates generated on the device (bench-scale inputs; synth.py model):
  * atom_base [A][3] f64, node_of_atom [A], modes [N][M][3] f64, coeff [T][M] f64. */

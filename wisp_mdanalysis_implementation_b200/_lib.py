@@ -67,6 +67,7 @@ SIGNATURES = {
     "wisp_dev_fw32_init_rows": (_int, [_c_ctx, _P, _int, _i64, _i64, _P, _P]),
     "wisp_dev_fw32_pivot_panel": (_int, [_c_ctx, _P, _int, _int, _P]),
     "wisp_dev_fw32_update_rows": (_int, [_c_ctx, _P, _i64, _P, _int, _int, _int, _P]),
+    "wisp_dev_fw32_update_rows_part": (_int, [_c_ctx, _P, _i64, _P, _int, _int, _int, _int, _int, _P]),
     "wisp_dev_synth_coords": (_int, [_c_ctx, _P, _i64, _i64, _int, _P, _P, _P, _int, _P, _dbl,
                                      C.c_uint64, _P]),
 }
@@ -392,6 +393,12 @@ class Context:
     def dev_fw32_update_rows(self, d_dist_local, rows_pad, d_panel, N, kb, skip_local_tile, stream=None):
         self._check(self._lib.wisp_dev_fw32_update_rows(self._ctx, _ptr(d_dist_local), rows_pad,
                                                         _ptr(d_panel), N, kb, skip_local_tile, _ptr(stream)))
+
+    def dev_fw32_update_rows_part(self, d_dist_local, rows_pad, d_panel, N, kb, skip_local_tile,
+                                  next_local_tile, part, stream=None):
+        self._check(self._lib.wisp_dev_fw32_update_rows_part(self._ctx, _ptr(d_dist_local), rows_pad,
+                                                             _ptr(d_panel), N, kb, skip_local_tile,
+                                                             next_local_tile, part, _ptr(stream)))
 
     def dev_synth_coords(self, d_coords, t0, T, A, d_atom_base, d_node_of_atom, d_modes, n_modes,
                          d_coeff, noise_sigma, seed, stream=None):

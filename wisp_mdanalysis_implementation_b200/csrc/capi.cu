@@ -58,6 +58,8 @@ extern "C" void wisp_ctx_destroy(wisp_ctx* ctx) {
         if (b.p) cudaFree(b.p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    for (auto& e : ctx->aux_events) if (e) cudaEventDestroy(e);
     delete ctx;
 }
 

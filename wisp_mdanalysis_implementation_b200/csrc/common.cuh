@@ -61,6 +61,8 @@ struct wisp_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;   // compute
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;   // high-priority side stream (K5 look-ahead), created on first use
+    cudaEvent_t aux_events[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t launches = 0;
     int gram_mode = -1;              // WISP_GRAM_*; -1 = read $WISP_K2_MODE on first use
     // column statistics left by the last centring pass (launch_center) for the INT8 K2 engine:
@@ -70,7 +72,7 @@ struct wisp_ctx {
     int i8_stats_parts = 0;
     cudaStream_t i8_stats_stream = nullptr;
     // grow-only scratch buffers, keyed by slot
-    DevBuf scratch[32];
+    DevBuf scratch[40];
     // get_paths results
     std::vector<double> path_len;
     std::vector<int64_t> path_off;
@@ -89,7 +91,7 @@ enum ScratchSlot {
     SCR_GRAM_PART = 0, SCR_CONTACT_PART, SCR_COLSUM_PART, SCR_X, SCR_COORDS0, SCR_COORDS1,
     SCR_APSP_D, SCR_APSP_P, SCR_ARENA, SCR_ALIGN, SCR_P32,
     SCR_MISC0, SCR_MISC1, SCR_MISC2, SCR_MISC3, SCR_MISC4, SCR_MISC5, SCR_MISC6, SCR_MISC7,
-    SCR_MISC8, SCR_MISC9, SCR_I8_PLANES, SCR_I8_SMALL, SCR_I8_PART, SCR_I8_STATS, SCR_COUNT
+    SCR_MISC8, SCR_MISC9, SCR_I8_PLANES, SCR_I8_SMALL, SCR_I8_PART, SCR_I8_STATS, SCR_APSP_R, SCR_APSP_T, SCR_APSP_M, SCR_COUNT
 };
 
 // ---- kernel launchers (one per .cu) -------------------------------------------------------

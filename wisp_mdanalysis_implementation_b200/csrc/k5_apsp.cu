@@ -6,18 +6,33 @@
 // return.  Graph semantics follow networkx 1.x Graph(data=W): entry != 0 <=> edge; the
 // diagonal is never an edge.
 //
-// Classic 3-phase tiling with 64x64 tiles (round kb = pivot block):
-//   phase 1  pivot tile (kb,kb) in shared memory, 64 dependent k-steps;
-//   phase 2  pivot row tiles (kb,*) and pivot column tiles (*,kb): pivot tile + own tile in
-//            shared memory;
-//   phase 3  every other tile: min-plus product of its pivot-column tile (staged transposed
-//            so a thread's 4 rows are one vector load) and pivot-row tile (+ its predecessor
-//            tile), 4x4 outputs per thread held in registers, no synchronisation inside the
-//            k loop.  This phase is N^3 (1 - 2/nb) of the work.
-// Relaxation: cand = d_ik + d_kj; if (cand < d_ij) { d_ij = cand; pred_ij = pred_kj; }
-// (strict '<': the first k that reaches the minimum wins -> deterministic predecessors).
-// Templated on float / double: float64 is the parity mode (path lengths to 1e-9), float32 is
-// the FP32-pipe mode the north star asks to be measured.
+// Round kb of the blocked algorithm (tile edge B = 128 in FP32, 64 in FP64):
+//   P1   pivot tile (kb,kb): B dependent k-steps in one CTA, own elements in registers, one
+//        barrier per step;
+//   P2   pivot-row tiles (kb,*) and pivot-column tiles (*,kb).  WARP-AUTONOMOUS: a warp owns 8
+//        whole columns (rows) of its tile -- lane (q, v) holds B/4 consecutive elements of vector
+//        v in registers -- so the value of row k of its own tile is one register shuffle away and
+//        the pivot tile sits read-only in shared memory: no barrier in the k loop at all;
+//   P3   every other tile: min-plus product of its pivot-column tile and pivot-row tile,
+//        register-tiled, accumulated into fresh minima m and merged into the tile at the end.
+//        N^3 (1 - 2/nb) of the work.
+// LOOK-AHEAD.  Only the tiles of row kb+1 and column kb+1 are needed by the next round's P1/P2,
+// so P3 is split: a small "lead" launch for those tiles, then P1/P2 of round kb+1 run on a
+// second, high-priority stream WHILE the bulk of round kb's P3 is still running on the main
+// stream.  The serial pivot phases disappear from the critical path once N is more than a few
+// tiles (round 1 spent 62 % of an N = 2,000 run and 25 % of an N = 10,000 run in them).
+// PREDECESSORS WITHOUT A SINGLE EXTRA INSTRUCTION IN THE RELAXATION LOOP.  The min-plus loop is
+// dispatch bound -- tools/peaks_minplus.cu: FADD2+FMNMX3, scalar FADD+FMNMX and the DPX VIADDMNMX
+// all top out at 16-18 T relaxations/s because every half-rate or packed instruction holds the
+// dispatch port two cycles -- so carrying a predecessor select (round 1: x3.7 slower) is the
+// wrong trade.  Instead every kernel records, per element, the ROUND in which it last improved
+// (one compare when the tile is merged; uint16 matrix).  After the last round
+//   mid[i][j]  = argmin over the <= B vertices k of that round of dist[i][k] + dist[k][j]
+//                (N^2 * B work = B/N of the main loop; the improving k lies in that round, and
+//                final distances reproduce it up to rounding),
+//   pred[i][j] = follow mid along column j until the remaining hop is a direct edge
+// (the classic midpoint form of Floyd-Warshall path reconstruction).  On generic weights the
+// shortest path is unique and the result equals the Dijkstra predecessor tree.
 #include "common.cuh"
 #include <limits>
 #include <cstdlib>
@@ -25,268 +40,174 @@
 
 namespace {
 
-constexpr int kB = 64;            // tile edge
-constexpr int kFwThreads = 256;   // 16 x 16 threads, 4 x 4 elements each
+constexpr uint16_t kNoRound = 0xFFFFu;
 
-template <typename T>
-__device__ __forceinline__ T inf_v() { return std::numeric_limits<T>::infinity(); }
+template <typename T> __device__ __forceinline__ T inf_v();
 template <> __device__ __forceinline__ float inf_v<float>() { return __int_as_float(0x7f800000); }
 template <> __device__ __forceinline__ double inf_v<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
+__device__ __forceinline__ float fw_min(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double fw_min(double a, double b) { return fmin(a, b); }
 
 template <typename T>
-__global__ void fw_init_kernel(const double* __restrict__ w, int N, int64_t n_pad,
-                               T* __restrict__ dist, int32_t* __restrict__ pred) {
-    const int64_t total = n_pad * n_pad;
+__global__ void fw_init_kernel(const double* __restrict__ w, int N, int64_t n_pad, int64_t row0, int64_t rows,
+                               T* __restrict__ dist, uint16_t* __restrict__ rounds) {
+    // rows [row0, row0 + rows) of the padded matrix; w holds the same rows of the N x N cost matrix
+    const int64_t total = rows * n_pad;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = e / n_pad, c = e - r * n_pad;
+        const int64_t rl = e / n_pad, c = e - rl * n_pad, r = row0 + rl;
         T d = inf_v<T>();
-        int32_t p = -1;
-        if (r == c) {
-            d = (T)0;
-        } else if (r < N && c < N) {
-            const double v = w[r * N + c];
-            if (v != 0.0) { d = (T)v; p = (int32_t)r; }
-        }
+        if (r == c) d = (T)0;
+        else if (r < N && c < N) { const double v = w[rl * N + c]; if (v != 0.0) d = (T)v; }
         dist[e] = d;
-        pred[e] = p;
+        if (rounds) rounds[e] = kNoRound;
     }
 }
 
-template <typename T>
-__global__ void fw_final_kernel(const T* __restrict__ dist, const int32_t* __restrict__ pred,
-                                int N, int64_t n_pad, double* __restrict__ out_dist,
-                                int32_t* __restrict__ out_pred) {
-    const int64_t total = (int64_t)N * N;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = e / N, c = e - r * N;
-        if (out_dist) out_dist[e] = (double)dist[r * n_pad + c];
-        if (out_pred) out_pred[e] = pred[r * n_pad + c];
-    }
-}
-
-// ---- phase 1: pivot tile ----
-template <typename T>
-__global__ void __launch_bounds__(kFwThreads)
-fw_phase1_kernel(T* __restrict__ dist, int32_t* __restrict__ pred, int64_t ld, int kb) {
+// ---------------------------------------------------------------------------------------
+// P1: pivot tile.  (B/4)^2 threads, 4 x 4 elements each (rows 4ty+a, columns tx + (B/4) b), own
+// elements in registers; shared memory is only the exchange medium for row k / column k, written
+// when an element improves.  Row k and column k are fixed points of step k (d[k][k] == 0), so one
+// barrier per step is enough.  `panel` = the pivot ROW PANEL (B rows x ld): the pivot tile sits at
+// column block kb.
+// ---------------------------------------------------------------------------------------
+template <typename T, int B>
+__global__ void __launch_bounds__((B / 4) * (B / 4))
+fw_p1_kernel(T* __restrict__ panel, int64_t ld, int kb, uint16_t* __restrict__ rounds_panel) {
+    constexpr int TX = B / 4;
     extern __shared__ __align__(16) unsigned char fw_smem[];
-    T* d = reinterpret_cast<T*>(fw_smem);                       // [64][65]
-    int32_t* p = reinterpret_cast<int32_t*>(d + kB * (kB + 1)); // [64][65]
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int64_t base = (int64_t)kb * kB * ld + (int64_t)kb * kB;
+    T* d = reinterpret_cast<T*>(fw_smem);     // [B][B+1]
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int64_t base = (int64_t)kb * B;
+    T own[4][4], init[4][4];
+#pragma unroll
     for (int a = 0; a < 4; ++a)
+#pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const int i = 4 * ty + a, j = 4 * tx + b;
-            d[i * (kB + 1) + j] = dist[base + i * ld + j];
-            p[i * (kB + 1) + j] = pred[base + i * ld + j];
+            own[a][b] = init[a][b] = panel[base + (4 * ty + a) * ld + tx + TX * b];
+            d[(4 * ty + a) * (B + 1) + tx + TX * b] = own[a][b];
         }
     __syncthreads();
-    for (int k = 0; k < kB; ++k) {
-        T nd[4][4];
-        int32_t np[4][4];
-        bool up[4][4];
+    for (int k = 0; k < B; ++k) {
+        T rk[4], ck[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) rk[b] = d[k * (B + 1) + tx + TX * b];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) ck[a] = d[(4 * ty + a) * (B + 1) + k];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                const int i = 4 * ty + a, j = 4 * tx + b;
-                const T cand = d[i * (kB + 1) + k] + d[k * (kB + 1) + j];
-                up[a][b] = cand < d[i * (kB + 1) + j];
-                nd[a][b] = cand;
-                np[a][b] = p[k * (kB + 1) + j];
+                const T cand = ck[a] + rk[b];
+                if (cand < own[a][b]) { own[a][b] = cand; d[(4 * ty + a) * (B + 1) + tx + TX * b] = cand; }
             }
         __syncthreads();
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-                if (up[a][b]) {
-                    const int i = 4 * ty + a, j = 4 * tx + b;
-                    d[i * (kB + 1) + j] = nd[a][b];
-                    p[i * (kB + 1) + j] = np[a][b];
-                }
-        __syncthreads();
     }
+#pragma unroll
     for (int a = 0; a < 4; ++a)
+#pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const int i = 4 * ty + a, j = 4 * tx + b;
-            dist[base + i * ld + j] = d[i * (kB + 1) + j];
-            pred[base + i * ld + j] = p[i * (kB + 1) + j];
+            const int64_t o = base + (4 * ty + a) * ld + tx + TX * b;
+            if (own[a][b] < init[a][b]) {
+                panel[o] = own[a][b];
+                if (rounds_panel) rounds_panel[o] = (uint16_t)kb;
+            }
         }
 }
 
-// ---- phase 2: pivot row (blockIdx.y == 0) and pivot column (blockIdx.y == 1) tiles ----
-template <typename T>
-__global__ void __launch_bounds__(kFwThreads)
-fw_phase2_kernel(T* __restrict__ dist, int32_t* __restrict__ pred, int64_t ld, int kb) {
-    const int other = blockIdx.x;
-    if (other == kb) return;
+// ---------------------------------------------------------------------------------------
+// P2: warp-autonomous pivot-row / pivot-column tiles.
+//   row tile (kb, other):  own[i][j] <- min(own[i][j], piv[i][k] + own[k][j]),  vector = column j
+//   col tile (other, kb):  own[i][j] <- min(own[i][j], own[i][k] + piv[k][j]),  vector = row i
+// In both cases, with s the position along the vector:  o_v[s] <- min(o_v[s], M[k][s] + o_v[k]),
+// M[k][s] = piv[s][k] (row tiles: pivot transposed) or piv[k][s] (column tiles).  Lane (q, v) of a
+// warp holds o_v[q*E .. q*E+E), E = B/4, so o_v[k] lives in lane (k / E, v), register k % E: one
+// shuffle.  CTA = 4 warps = 32 vectors; B/32 CTAs per tile; grid (tiles * B/32, 2): y = 0 row
+// tiles (inside the row panel), y = 1 column tiles (tile-rows of the LOCAL row block, `skip` = the
+// local tile-row that holds the pivot rows themselves).
+// ---------------------------------------------------------------------------------------
+template <typename T, int B>
+__global__ void __launch_bounds__(128)
+fw_p2_kernel(T* __restrict__ local, int64_t ld, T* __restrict__ panel, int64_t ldp, int kb,
+             int n_col_tiles, int n_local_tiles, int skip, int skip2, uint16_t* __restrict__ rounds_local,
+             uint16_t* __restrict__ rounds_panel, int only_tile) {
+    constexpr int E = B / 4;                       // elements per lane
+    constexpr int PAD = 16 / sizeof(T);            // keeps rows 16-byte aligned
+    constexpr int LDM = B + PAD;
+    constexpr int SUB = B / 32;                    // CTAs per tile
     const bool is_row = blockIdx.y == 0;
+    const int other = only_tile >= 0 ? only_tile : blockIdx.x / SUB;
+    const int sub = blockIdx.x % SUB;
+    if (only_tile >= 0 && (int)(blockIdx.x / SUB) != 0) return;
+    if (is_row) { if (other >= n_col_tiles || other == kb) return; }
+    else        { if (other >= n_local_tiles || other == skip || other == skip2) return; }
     extern __shared__ __align__(16) unsigned char fw_smem[];
-    T* pv = reinterpret_cast<T*>(fw_smem);          // pivot dist   [64][65]
-    T* ow = pv + kB * (kB + 1);                      // own dist     [64][65]
-    int32_t* pp = reinterpret_cast<int32_t*>(ow + kB * (kB + 1));   // pivot pred
-    int32_t* op = pp + kB * (kB + 1);                                // own pred
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int64_t pbase = (int64_t)kb * kB * ld + (int64_t)kb * kB;
-    const int64_t obase = is_row ? (int64_t)kb * kB * ld + (int64_t)other * kB
-                                 : (int64_t)other * kB * ld + (int64_t)kb * kB;
-    for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b) {
-            const int i = 4 * ty + a, j = 4 * tx + b;
-            pv[i * (kB + 1) + j] = dist[pbase + i * ld + j];
-            pp[i * (kB + 1) + j] = pred[pbase + i * ld + j];
-            ow[i * (kB + 1) + j] = dist[obase + i * ld + j];
-            op[i * (kB + 1) + j] = pred[obase + i * ld + j];
-        }
+    T* M = reinterpret_cast<T*>(fw_smem);          // [B][LDM]
+    const T* piv = panel + (int64_t)kb * B;
+    for (int e = threadIdx.x; e < B * B; e += 128) {
+        const int r = e / B, c = e % B;
+        const T v = piv[(int64_t)r * ldp + c];
+        if (is_row) M[c * LDM + r] = v; else M[r * LDM + c] = v;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane >> 3, vv = lane & 7;
+    const int v = sub * 32 + warp * 8 + vv;        // vector index inside the tile
+    T* own = is_row ? panel + (int64_t)other * B : local + (int64_t)other * B * ld + (int64_t)kb * B;
+    uint16_t* rnd = is_row ? (rounds_panel ? rounds_panel + (int64_t)other * B : nullptr)
+                           : (rounds_local ? rounds_local + (int64_t)other * B * ld + (int64_t)kb * B : nullptr);
+    const int64_t ldo = is_row ? ldp : ld;
+    // element s of vector v: row tile -> own[s][v]; column tile -> own[v][s]
+    const int64_t e0 = is_row ? (int64_t)(q * E) * ldo + v : (int64_t)v * ldo + q * E;
+    const int64_t es = is_row ? ldo : 1;
+    T o[E], init[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) o[r] = init[r] = own[e0 + r * es];
     __syncthreads();
-    for (int k = 0; k < kB; ++k) {
-        T nd[4][4];
-        int32_t np[4][4];
-        bool up[4][4];
+    for (int kq = 0; kq < 4; ++kq) {
+        const int src = kq * 8 + vv;
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int r = 0; r < E; ++r) {
+            const T xk = __shfl_sync(0xffffffffu, o[r], src);      // o_v[k], k = kq*E + r
+            const T* mrow = M + (kq * E + r) * LDM + q * E;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int i = 4 * ty + a, j = 4 * tx + b;
-                T cand;
-                int32_t cp;
-                if (is_row) {   // own = (kb, other): d[i][j] <- pivot[i][k] + own[k][j]
-                    cand = pv[i * (kB + 1) + k] + ow[k * (kB + 1) + j];
-                    cp = op[k * (kB + 1) + j];
-                } else {        // own = (other, kb): d[i][j] <- own[i][k] + pivot[k][j]
-                    cand = ow[i * (kB + 1) + k] + pv[k * (kB + 1) + j];
-                    cp = pp[k * (kB + 1) + j];
-                }
-                up[a][b] = cand < ow[i * (kB + 1) + j];
-                nd[a][b] = cand;
-                np[a][b] = cp;
-            }
-        __syncthreads();
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-                if (up[a][b]) {
-                    const int i = 4 * ty + a, j = 4 * tx + b;
-                    ow[i * (kB + 1) + j] = nd[a][b];
-                    op[i * (kB + 1) + j] = np[a][b];
-                }
-        __syncthreads();
+            for (int r2 = 0; r2 < E; ++r2) o[r2] = fw_min(o[r2], mrow[r2] + xk);
+        }
     }
-    for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b) {
-            const int i = 4 * ty + a, j = 4 * tx + b;
-            dist[obase + i * ld + j] = ow[i * (kB + 1) + j];
-            pred[obase + i * ld + j] = op[i * (kB + 1) + j];
+#pragma unroll
+    for (int r = 0; r < E; ++r)
+        if (o[r] < init[r]) {
+            own[e0 + r * es] = o[r];
+            if (rnd) rnd[e0 + r * es] = (uint16_t)kb;
         }
 }
 
-// ---- phase 3: remaining tiles (register-tiled min-plus product) ----
-template <typename T>
-__global__ void __launch_bounds__(kFwThreads)
-fw_phase3_kernel(T* __restrict__ dist, int32_t* __restrict__ pred, int64_t ld, int kb) {
-    const int bj = blockIdx.x, bi = blockIdx.y;
-    if (bi == kb || bj == kb) return;
-    extern __shared__ __align__(16) unsigned char fw_smem[];
-    T* ct = reinterpret_cast<T*>(fw_smem);          // column tile transposed: ct[k][i]
-    T* rt = ct + kB * kB;                            // row tile: rt[k][j]
-    int32_t* rp = reinterpret_cast<int32_t*>(rt + kB * kB);   // row tile preds: rp[k][j]
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int64_t cbase = (int64_t)bi * kB * ld + (int64_t)kb * kB;   // (bi, kb)
-    const int64_t rbase = (int64_t)kb * kB * ld + (int64_t)bj * kB;   // (kb, bj)
-    const int64_t obase = (int64_t)bi * kB * ld + (int64_t)bj * kB;
-    for (int e = threadIdx.x; e < kB * kB; e += kFwThreads) {
-        const int r = e >> 6, c = e & 63;
-        ct[c * kB + r] = dist[cbase + r * ld + c];
-        rt[r * kB + c] = dist[rbase + r * ld + c];
-        rp[r * kB + c] = pred[rbase + r * ld + c];
+// ---------------------------------------------------------------------------------------
+// P3 tile selection shared by both precisions.  part 0: every tile outside the pivot row / column;
+// part 1 ("lead"): only the tiles of column `next_col` and of local tile-row `next_row`;
+// part 2 ("rest"): every tile outside those (and outside the pivot row / column).
+// Lead grids are 1-D: [0, nl) = (bi, next_col), [nl, nl + nb) = (next_row, bj).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool fw_p3_tile(int part, int nb, int nl, int kb, int skip, int next_col, int next_row,
+                                           int& bi, int& bj) {
+    if (part == 1) {
+        const int x = blockIdx.x;
+        if (x < nl) { if (next_col < 0) return false; bi = x; bj = next_col; }
+        else { if (next_row < 0) return false; bi = next_row; bj = x - nl; if (bj == next_col) return false; }
+    } else {
+        bj = blockIdx.x; bi = blockIdx.y;
+        if (part == 2 && (bj == next_col || bi == next_row)) return false;
     }
-    T d[4][4];
-    int32_t p[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            d[a][b] = dist[obase + (4 * ty + a) * ld + 4 * tx + b];
-            p[a][b] = pred[obase + (4 * ty + a) * ld + 4 * tx + b];
-        }
-    __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < kB; ++k) {
-        T cv[4], rv[4];
-        int32_t pv[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) cv[a] = ct[k * kB + 4 * ty + a];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) { rv[b] = rt[k * kB + 4 * tx + b]; pv[b] = rp[k * kB + 4 * tx + b]; }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const T cand = cv[a] + rv[b];
-                if (cand < d[a][b]) { d[a][b] = cand; p[a][b] = pv[b]; }
-            }
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            dist[obase + (4 * ty + a) * ld + 4 * tx + b] = d[a][b];
-            pred[obase + (4 * ty + a) * ld + 4 * tx + b] = p[a][b];
-        }
+    return !(bi == skip || bj == kb || bi >= nl || bj >= nb);
 }
 
-template <typename T>
-int run_apsp(wisp_ctx* ctx, const double* d_w, int N, double* d_dist, int32_t* d_pred,
-             cudaStream_t st) {
-    const int64_t n_pad = round_up(N, kB);
-    const int nb = (int)(n_pad / kB);
-    void *pd = nullptr, *pp = nullptr;
-    WISP_TRY(wisp_scratch(ctx, SCR_APSP_D, (size_t)n_pad * n_pad * sizeof(T), &pd));
-    WISP_TRY(wisp_scratch(ctx, SCR_APSP_P, (size_t)n_pad * n_pad * sizeof(int32_t), &pp));
-    T* dist = (T*)pd;
-    int32_t* pred = (int32_t*)pp;
-    const int g = (int)std::min<int64_t>((n_pad * n_pad + 255) / 256, (int64_t)ctx->sm_count * 16);
-    fw_init_kernel<T><<<g, 256, 0, st>>>(d_w, N, n_pad, dist, pred);
-    ctx->launches++;
-    const int smem1 = kB * (kB + 1) * (sizeof(T) + 4);
-    const int smem2 = 2 * kB * (kB + 1) * (sizeof(T) + 4);
-    const int smem3 = kB * kB * (2 * sizeof(T) + 4);
-    WISP_CUDA(cudaFuncSetAttribute(fw_phase1_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    WISP_CUDA(cudaFuncSetAttribute(fw_phase2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-    WISP_CUDA(cudaFuncSetAttribute(fw_phase3_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-    for (int kb = 0; kb < nb; ++kb) {
-        fw_phase1_kernel<T><<<1, kFwThreads, smem1, st>>>(dist, pred, n_pad, kb);
-        if (nb > 1) {
-            fw_phase2_kernel<T><<<dim3(nb, 2), kFwThreads, smem2, st>>>(dist, pred, n_pad, kb);
-            fw_phase3_kernel<T><<<dim3(nb, nb), kFwThreads, smem3, st>>>(dist, pred, n_pad, kb);
-            ctx->launches += 2;
-        }
-        ctx->launches++;
-    }
-    WISP_CUDA(cudaGetLastError());
-    const int g2 = (int)std::min<int64_t>(((int64_t)N * N + 255) / 256, (int64_t)ctx->sm_count * 16);
-    fw_final_kernel<T><<<g2, 256, 0, st>>>(dist, pred, N, n_pad, d_dist, d_pred);
-    ctx->launches++;
-    WISP_CUDA(cudaGetLastError());
-    return 0;
-}
-
-
-// =======================================================================================
-// FP32 throughput mode: distance-only Floyd-Warshall with 128-wide rounds.
-//   * phase 3 is a 128x128 register-tiled min-plus product, 8x8 outputs per thread, two
-//     k-steps per inner iteration: candidates from packed FADD2 (two outputs per issue slot),
-//     folded with the 3-input minimum FMNMX3  d = min(d, c1+r1, c2+r2)  -> one instruction per
-//     relaxation instead of four (add, compare, 2 selects) in the predecessor-tracking form;
-//   * predecessors are recovered afterwards from the distances:
-//     pred[i][j] = argmin_u ( dist[i][u] + w[u][j] ) over the in-neighbours u of j
-//     (N^2 * degree work on the CSR graph, first minimum wins).
-// =======================================================================================
-constexpr int kT = 128;            // tile edge / round width
-constexpr int kH = 64;             // k-depth staged per pass in phase 3
+// ---- FP32 P3: 128 x 128 tile, 8 x 8 outputs per thread, 32-deep k chunks through a 3-stage cp.async
+// ring; candidates from packed FADD2, folded with the 3-input minimum FMNMX3 (m = min(m, c1+r1, c2+r2)):
+// one dispatch cycle pair per relaxation, which is the machine's limit for a 32-bit min-plus.
+constexpr int kT = 128;
+constexpr int kC = 32;                 // k-depth per stage
+constexpr int kColLd = kC + 4;         // padded row of the column-panel stage (floats)
+constexpr int kP3Stages = 3;
+constexpr int kP3StageFloats = kT * kColLd + kC * kT;
 
 typedef unsigned long long f32x2_t;
 __device__ __forceinline__ f32x2_t fw_add2(float c, f32x2_t r) {
@@ -308,137 +229,19 @@ __device__ __forceinline__ f32x2_t fw_pack(float lo, float hi) {
 __device__ __forceinline__ void fw_unpack(f32x2_t v, float& lo, float& hi) {
     asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
-
-__global__ void fw32_init_kernel(const double* __restrict__ w, int N, int64_t n_pad, float* __restrict__ dist) {
-    const int64_t total = n_pad * n_pad;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = e / n_pad, c = e - r * n_pad;
-        float d = __int_as_float(0x7f800000);
-        if (r == c) d = 0.f;
-        else if (r < N && c < N) { const double v = w[r * N + c]; if (v != 0.0) d = (float)v; }
-        dist[e] = d;
-    }
-}
-
-// phase 1: pivot tile, 1024 threads, 16 elements each, in-place (row k / column k are fixed
-// points of iteration k because d[k][k] == 0 and weights are non-negative)
-__global__ void __launch_bounds__(1024)
-fw32_phase1_kernel(float* __restrict__ dist, int64_t ld, int kb) {
-    // `dist` is the pivot ROW PANEL (128 rows x ld): the pivot tile sits at column block kb
-    extern __shared__ __align__(16) unsigned char fw_smem[];
-    float* d = reinterpret_cast<float*>(fw_smem);     // [128][129]
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // ty 0..31 -> rows 4ty..4ty+3
-    const int64_t base = (int64_t)kb * kT;
-    for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b) d[(4 * ty + a) * (kT + 1) + tx + 32 * b] = dist[base + (4 * ty + a) * ld + tx + 32 * b];
-    __syncthreads();
-    // own 16 elements live in registers; shared memory is only the exchange medium for row k /
-    // column k, written when an element improves (row k / column k are fixed points of step k)
-    float own[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) own[a][b] = d[(4 * ty + a) * (kT + 1) + tx + 32 * b];
-    for (int k = 0; k < kT; ++k) {
-        float rk[4], ck[4];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) rk[b] = d[k * (kT + 1) + tx + 32 * b];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) ck[a] = d[(4 * ty + a) * (kT + 1) + k];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const float cand = ck[a] + rk[b];
-                if (cand < own[a][b]) { own[a][b] = cand; d[(4 * ty + a) * (kT + 1) + tx + 32 * b] = cand; }
-            }
-        __syncthreads();
-    }
-    for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b) dist[base + (4 * ty + a) * ld + tx + 32 * b] = own[a][b];
-}
-
-// phase 2: pivot row tiles (blockIdx.y == 0, inside the row panel) and pivot column tiles
-// (blockIdx.y == 1, tile (bi, kb) of the LOCAL row block; local tile-row `skip` holds the pivot
-// rows themselves and is left alone)
-__global__ void __launch_bounds__(1024)
-fw32_phase2_kernel(float* __restrict__ local, int64_t ld, float* __restrict__ panel, int64_t ldp,
-                   int kb, int n_col_tiles, int n_local_tiles, int skip) {
-    const int other = blockIdx.x;
-    const bool is_row = blockIdx.y == 0;
-    if (is_row) { if (other >= n_col_tiles || other == kb) return; }
-    else        { if (other >= n_local_tiles || other == skip) return; }
-    extern __shared__ __align__(16) unsigned char fw_smem[];
-    float* pv = reinterpret_cast<float*>(fw_smem);     // pivot [128][129]
-    float* ow = pv + kT * (kT + 1);                    // own   [128][129]
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const float* pbase = panel + (int64_t)kb * kT;
-    float* obase = is_row ? panel + (int64_t)other * kT : local + (int64_t)other * kT * ld + (int64_t)kb * kT;
-    const int64_t ldo = is_row ? ldp : ld;
-    for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b) {
-            const int i = 4 * ty + a, j = tx + 32 * b;
-            pv[i * (kT + 1) + j] = pbase[i * ldp + j];
-            ow[i * (kT + 1) + j] = obase[i * ldo + j];
-        }
-    __syncthreads();
-    float own[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) own[a][b] = ow[(4 * ty + a) * (kT + 1) + tx + 32 * b];
-    for (int k = 0; k < kT; ++k) {
-        float rk[4], ck[4];
-        if (is_row) {      // own = (kb, other): d[i][j] <- pivot[i][k] + own[k][j]
-#pragma unroll
-            for (int b = 0; b < 4; ++b) rk[b] = ow[k * (kT + 1) + tx + 32 * b];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) ck[a] = pv[(4 * ty + a) * (kT + 1) + k];
-        } else {           // own = (other, kb): d[i][j] <- own[i][k] + pivot[k][j]
-#pragma unroll
-            for (int b = 0; b < 4; ++b) rk[b] = pv[k * (kT + 1) + tx + 32 * b];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) ck[a] = ow[(4 * ty + a) * (kT + 1) + k];
-        }
-        // (row k / column k of the own tile are fixed points of step k: pivot[k][k] == 0, so no
-        //  barrier is needed between these reads and the writes below)
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const float cand = ck[a] + rk[b];
-                if (cand < own[a][b]) { own[a][b] = cand; ow[(4 * ty + a) * (kT + 1) + tx + 32 * b] = cand; }
-            }
-        __syncthreads();
-    }
-    for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b) {
-            const int i = 4 * ty + a, j = tx + 32 * b;
-            obase[i * ldo + j] = own[a][b];
-        }
-}
-
-// phase 3: all tiles outside the pivot row / column.  The 128-deep k range is streamed in four
-// 32-deep chunks through a 3-stage cp.async ring (column panel kept i-major: no transpose),
-// so the panel loads of chunk s+2 overlap the min-plus arithmetic of chunk s.
-constexpr int kC = 32;                 // k-depth per stage
-constexpr int kColLd = kC + 4;         // padded row of the column-panel stage (floats)
-constexpr int kP3Stages = 3;
-constexpr int kP3StageFloats = kT * kColLd + kC * kT;
-
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
 
 __global__ void __launch_bounds__(256, 2)
-fw32_phase3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict__ panel, int64_t ldp,
-                   int kb, int skip) {
+fw32_p3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict__ panel, int64_t ldp,
+               int kb, int skip, int nb, int nl, int part, int next_col, int next_row,
+               uint16_t* __restrict__ rounds) {
     // dist = LOCAL row block; tile (bi, bj) <- min-plus of local column tile (bi, kb) and the
     // pivot row panel's tile (., bj); local tile-row `skip` (the pivot rows) is left alone
-    const int bj = blockIdx.x, bi = blockIdx.y;
-    if (bi == skip || bj == kb) return;
+    int bi, bj;
+    if (!fw_p3_tile(part, nb, nl, kb, skip, next_col, next_row, bi, bj)) return;
     extern __shared__ __align__(16) unsigned char fw_smem[];
     float* stages = reinterpret_cast<float*>(fw_smem);
     const int tid = threadIdx.x;
@@ -463,15 +266,11 @@ fw32_phase3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict
 
     issue(0);
     issue(1);
-    float d[8][8];
+    float m[8][8];
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        const int row = (a < 4) ? 4 * ty + a : 64 + 4 * ty + (a - 4);
-        const float4 v0 = *reinterpret_cast<const float4*>(dist + obase + row * ld + 4 * tx);
-        const float4 v1 = *reinterpret_cast<const float4*>(dist + obase + row * ld + 64 + 4 * tx);
-        d[a][0] = v0.x; d[a][1] = v0.y; d[a][2] = v0.z; d[a][3] = v0.w;
-        d[a][4] = v1.x; d[a][5] = v1.y; d[a][6] = v1.z; d[a][7] = v1.w;
-    }
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) m[a][b] = __int_as_float(0x7f800000);
     constexpr int kChunks = kT / kC;
     for (int chunk = 0; chunk < kChunks; ++chunk) {
         if (chunk + 1 < kChunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -502,201 +301,316 @@ fw32_phase3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict
                     float l1, h1, l2, h2;
                     fw_unpack(fw_add2(c1[a], r1[bp]), l1, h1);
                     fw_unpack(fw_add2(c2[a], r2[bp]), l2, h2);
-                    d[a][2 * bp] = fw_min3(d[a][2 * bp], l1, l2);
-                    d[a][2 * bp + 1] = fw_min3(d[a][2 * bp + 1], h1, h2);
+                    m[a][2 * bp] = fw_min3(m[a][2 * bp], l1, l2);
+                    m[a][2 * bp + 1] = fw_min3(m[a][2 * bp + 1], h1, h2);
                 }
         }
     }
+    // merge: the tile is read only now (it was not needed during the loop), written only where it
+    // improved, and the round of the improvement is recorded
+    uint16_t* rt = rounds ? rounds + obase : nullptr;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
         const int row = (a < 4) ? 4 * ty + a : 64 + 4 * ty + (a - 4);
-        *reinterpret_cast<float4*>(dist + obase + row * ld + 4 * tx) = make_float4(d[a][0], d[a][1], d[a][2], d[a][3]);
-        *reinterpret_cast<float4*>(dist + obase + row * ld + 64 + 4 * tx) = make_float4(d[a][4], d[a][5], d[a][6], d[a][7]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float* p = dist + obase + row * ld + 64 * h + 4 * tx;
+            float4 d4 = *reinterpret_cast<const float4*>(p);
+            float* dv = reinterpret_cast<float*>(&d4);
+            bool any = false;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (m[a][4 * h + b] < dv[b]) {
+                    dv[b] = m[a][4 * h + b];
+                    any = true;
+                    if (rt) rt[row * ld + 64 * h + 4 * tx + b] = (uint16_t)kb;
+                }
+            if (any) *reinterpret_cast<float4*>(p) = d4;
+        }
     }
 }
 
-// ---- CSR of in-edges from the dense cost matrix, and the argmin predecessor pass ----
-__global__ void csr_count_kernel(const double* __restrict__ w, int N, int32_t* __restrict__ count) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
-    int c = 0;
-    for (int u = 0; u < N; ++u) c += (u != j && w[(int64_t)u * N + j] != 0.0) ? 1 : 0;
-    count[j] = c;
-}
-__global__ void csr_fill_kernel(const double* __restrict__ w, int N, const int32_t* __restrict__ ptr,
-                                int32_t* __restrict__ idx, float* __restrict__ val) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
-    int e = ptr[j];
-    for (int u = 0; u < N; ++u) {
-        const double v = w[(int64_t)u * N + j];
-        if (u != j && v != 0.0) { idx[e] = u; val[e] = (float)v; ++e; }
+// ---- FP64 P3: 64 x 64 tile, 4 x 4 outputs per thread, whole 64-deep round staged at once (column tile
+// transposed so a thread's 4 rows are one pair of vector loads); DADD + DSETP.MIN per relaxation.
+constexpr int kB64 = 64;
+
+__global__ void __launch_bounds__(256)
+fw64_p3_kernel(double* __restrict__ dist, int64_t ld, const double* __restrict__ panel, int64_t ldp,
+               int kb, int skip, int nb, int nl, int part, int next_col, int next_row,
+               uint16_t* __restrict__ rounds) {
+    int bi, bj;
+    if (!fw_p3_tile(part, nb, nl, kb, skip, next_col, next_row, bi, bj)) return;
+    extern __shared__ __align__(16) unsigned char fw_smem[];
+    double* ct = reinterpret_cast<double*>(fw_smem);    // column tile transposed: ct[k][i]
+    double* rt = ct + kB64 * kB64;                       // row tile: rt[k][j]
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const double* cg = dist + (int64_t)bi * kB64 * ld + (int64_t)kb * kB64;
+    const double* rg = panel + (int64_t)bj * kB64;
+    const int64_t obase = (int64_t)bi * kB64 * ld + (int64_t)bj * kB64;
+    for (int e = threadIdx.x; e < kB64 * kB64; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        ct[c * kB64 + r] = cg[(int64_t)r * ld + c];
+        rt[r * kB64 + c] = rg[(int64_t)r * ldp + c];
+    }
+    double m[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) m[a][b] = inf_v<double>();
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < kB64; ++k) {
+        const double2 ca = *reinterpret_cast<const double2*>(ct + k * kB64 + 4 * ty);
+        const double2 cb = *reinterpret_cast<const double2*>(ct + k * kB64 + 4 * ty + 2);
+        const double2 ra = *reinterpret_cast<const double2*>(rt + k * kB64 + 4 * tx);
+        const double2 rb = *reinterpret_cast<const double2*>(rt + k * kB64 + 4 * tx + 2);
+        const double cv[4] = {ca.x, ca.y, cb.x, cb.y}, rv[4] = {ra.x, ra.y, rb.x, rb.y};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) m[a][b] = fmin(m[a][b], cv[a] + rv[b]);
+    }
+    uint16_t* rr = rounds ? rounds + obase : nullptr;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        double* p = dist + obase + (int64_t)(4 * ty + a) * ld + 4 * tx;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (m[a][b] < p[b]) {
+                p[b] = m[a][b];
+                if (rr) rr[(int64_t)(4 * ty + a) * ld + 4 * tx + b] = (uint16_t)kb;
+            }
     }
 }
-__global__ void fw32_final_kernel(const float* __restrict__ dist, int N, int64_t n_pad,
-                                  const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                                  const float* __restrict__ val, double* __restrict__ out_dist,
-                                  int32_t* __restrict__ out_pred) {
-    const int64_t total = (int64_t)N * N;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (int64_t)gridDim.x * blockDim.x) {
-        const int i = (int)(e / N), j = (int)(e - (int64_t)i * N);
-        const float dij = dist[(int64_t)i * n_pad + j];
-        if (out_dist) out_dist[e] = (double)dij;
-        if (out_pred) {
-            int p = -1;
-            if (i != j && dij < __int_as_float(0x7f800000)) {
-                float best = __int_as_float(0x7f800000);
-                const float* di = dist + (int64_t)i * n_pad;
-                for (int q = ptr[j]; q < ptr[j + 1]; ++q) {
-                    const int u = idx[q];
-                    const float c = di[u] + val[q];
-                    if (c < best) { best = c; p = u; }
+
+// ---------------------------------------------------------------------------------------
+// predecessors from (dist, rounds)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void fw_transpose_kernel(const T* __restrict__ in, int64_t n_pad, T* __restrict__ out) {
+    __shared__ T tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) tile[r][threadIdx.x] = in[(int64_t)(by + r) * n_pad + bx + threadIdx.x];
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) out[(int64_t)(bx + r) * n_pad + by + threadIdx.x] = tile[threadIdx.x][r];
+}
+
+// midT[j][i] = the vertex k of round rounds[i][j] that minimises dist[i][k] + dist[k][j] (k != i, j;
+// first minimum wins), or -1 when (i, j) never improved (direct edge, or no path).  distT = dist
+// transposed, so both operands are contiguous row segments.  Eight lanes per element; one CTA
+// walks the elements of one j (row j of distT stays in L1).
+template <typename T, int B>
+__global__ void __launch_bounds__(256)
+fw_resolve_kernel(const T* __restrict__ dist, const T* __restrict__ distT, const uint16_t* __restrict__ rounds,
+                  int N, int64_t n_pad, int32_t* __restrict__ midT) {
+    constexpr int V = 16 / sizeof(T);                 // elements per 16-byte load
+    const int j = blockIdx.x;
+    const int g = threadIdx.x >> 3, l = threadIdx.x & 7;       // 32 groups of 8 lanes
+    const T* dj = distT + (int64_t)j * n_pad;
+    for (int i0 = blockIdx.y * 32; i0 < N; i0 += gridDim.y * 32) {
+        const int i = i0 + g;
+        int best_k = -1;
+        T best = inf_v<T>();
+        uint16_t r = kNoRound;
+        if (i < N && i != j) r = rounds[(int64_t)i * n_pad + j];
+        if (r != kNoRound) {
+            const T* di = dist + (int64_t)i * n_pad;
+            const int k0 = (int)r * B;
+            for (int kk = l * V; kk < B; kk += 8 * V) {
+                T a[V], b[V];
+                *reinterpret_cast<int4*>(a) = *reinterpret_cast<const int4*>(di + k0 + kk);
+                *reinterpret_cast<int4*>(b) = *reinterpret_cast<const int4*>(dj + k0 + kk);
+#pragma unroll
+                for (int u = 0; u < V; ++u) {
+                    const int k = k0 + kk + u;
+                    const T c = a[u] + b[u];
+                    if (c < best && k != i && k != j) { best = c; best_k = k; }
                 }
             }
-            out_pred[e] = p;
+        }
+        // argmin over the 8 lanes of the group (ties: smaller k); executed by every lane of the warp
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const T ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+            if (ok >= 0 && (best_k < 0 || ob < best || (ob == best && ok < best_k))) { best = ob; best_k = ok; }
+        }
+        if (l == 0 && i < N) midT[(int64_t)j * n_pad + i] = best_k;
+    }
+}
+
+// predT[j][i] = last vertex before j on the path i -> j: follow midT[j][.] (the path i -> j splits
+// at mid into i -> mid and mid -> j; the predecessor of j lies on the second part) until the
+// remaining hop is a direct edge.
+template <typename T>
+__global__ void fw_chase_kernel(const int32_t* __restrict__ midT, const T* __restrict__ distT, int N,
+                                int64_t n_pad, int32_t* __restrict__ predT) {
+    const int j = blockIdx.x;
+    const int32_t* mj = midT + (int64_t)j * n_pad;
+    const T* dj = distT + (int64_t)j * n_pad;          // dist[i][j] for all i
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        int p = -1;
+        if (i != j && dj[i] < inf_v<T>()) {
+            int cur = i;
+            for (int hop = 0; hop < N; ++hop) {
+                const int mm = mj[cur];
+                if (mm < 0) break;
+                cur = mm;
+            }
+            p = cur;
+        }
+        predT[(int64_t)j * n_pad + i] = p;
+    }
+}
+
+// out_dist[i][j] = (double) dist[i][j]; out_pred[i][j] = predT[j][i] (transposed through shared memory)
+template <typename T>
+__global__ void fw_final_kernel(const T* __restrict__ dist, const int32_t* __restrict__ predT, int N,
+                                int64_t n_pad, double* __restrict__ out_dist, int32_t* __restrict__ out_pred) {
+    __shared__ int32_t tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;      // output block: rows by.., cols bx..
+    if (out_pred) {
+        for (int r = threadIdx.y; r < 32; r += blockDim.y)       // read predT rows bx.., cols by..
+            tile[r][threadIdx.x] = predT[(int64_t)(bx + r) * n_pad + by + threadIdx.x];
+        __syncthreads();
+    }
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = by + r, j = bx + threadIdx.x;
+        if (i < N && j < N) {
+            if (out_dist) out_dist[(int64_t)i * N + j] = (double)dist[(int64_t)i * n_pad + j];
+            if (out_pred) out_pred[(int64_t)i * N + j] = tile[threadIdx.x][r];
         }
     }
 }
 
-// dense graphs: pred[i][j] = argmin_u (dist[i][u] + w[u][j]) as a tiled min-plus product with
-// argmin (64x64 outputs per CTA, 4x4 per thread); used when the CSR form would be ~N^3 anyway
-__global__ void __launch_bounds__(256)
-fw32_pred_dense_kernel(const float* __restrict__ dist, int64_t n_pad, const double* __restrict__ w, int N,
-                       int32_t* __restrict__ out_pred) {
-    __shared__ float dt[64][64 + 4];    // dt[u][i]
-    __shared__ float wt[64][64];        // wt[u][j]
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
-    const float INF = __int_as_float(0x7f800000);
-    float best[4][4];
-    int arg[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) { best[a][b] = INF; arg[a][b] = -1; }
-    for (int u0 = 0; u0 < N; u0 += 64) {
-        __syncthreads();
-        for (int e = threadIdx.x; e < 64 * 64; e += 256) {
-            const int r = e >> 6, c = e & 63;
-            // D tile: row i0+r, col u0+c  -> dt[c][r]
-            dt[c][r] = dist[(int64_t)(i0 + r) * n_pad + u0 + c];     // padded: always in range
-            // W tile: row u0+r, col j0+c  -> wt[r][c]
-            const int u = u0 + r, j = j0 + c;
-            float v = INF;
-            if (u < N && j < N && u != j) { const double x = w[(int64_t)u * N + j]; if (x != 0.0) v = (float)x; }
-            wt[r][c] = v;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int k = 0; k < 64; ++k) {
-            const float4 cv = *reinterpret_cast<const float4*>(&dt[k][4 * ty]);
-            const float4 rv = *reinterpret_cast<const float4*>(&wt[k][4 * tx]);
-            const float c4[4] = {cv.x, cv.y, cv.z, cv.w}, r4[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const float cand = c4[a] + r4[b];
-                    if (cand < best[a][b]) { best[a][b] = cand; arg[a][b] = u0 + k; }
-                }
-        }
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int i = i0 + 4 * ty + a, j = j0 + 4 * tx + b;
-            if (i < N && j < N) out_pred[(int64_t)i * N + j] = (i == j) ? -1 : arg[a][b];
-        }
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+template <typename T> struct FwCfg;
+template <> struct FwCfg<float> {
+    static constexpr int B = kT;
+    static int p3_smem() { return (int)sizeof(float) * kP3Stages * kP3StageFloats; }
+    static constexpr int p3_threads = 256;
+};
+template <> struct FwCfg<double> {
+    static constexpr int B = kB64;
+    static int p3_smem() { return 2 * kB64 * kB64 * (int)sizeof(double); }
+    static constexpr int p3_threads = 256;
+};
+
+template <typename T> int fw_p1_smem() { return FwCfg<T>::B * (FwCfg<T>::B + 1) * (int)sizeof(T); }
+template <typename T> int fw_p2_smem() { return FwCfg<T>::B * (FwCfg<T>::B + 16 / (int)sizeof(T)) * (int)sizeof(T); }
+
+template <typename T>
+int fw_set_attrs() {
+    constexpr int B = FwCfg<T>::B;
+    WISP_CUDA(cudaFuncSetAttribute(fw_p1_kernel<T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw_p1_smem<T>()));
+    WISP_CUDA(cudaFuncSetAttribute(fw_p2_kernel<T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw_p2_smem<T>()));
+    if (sizeof(T) == 4)
+        WISP_CUDA(cudaFuncSetAttribute(fw32_p3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwCfg<float>::p3_smem()));
+    else
+        WISP_CUDA(cudaFuncSetAttribute(fw64_p3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwCfg<double>::p3_smem()));
+    return 0;
 }
 
-int run_apsp_f32_fast(wisp_ctx* ctx, const double* d_w, int N, double* d_dist, int32_t* d_pred,
-                      cudaStream_t st) {
-    const int64_t n_pad = round_up(N, kT);
-    const int nb = (int)(n_pad / kT);
-    void* pd = nullptr;
-    WISP_TRY(wisp_scratch(ctx, SCR_APSP_D, (size_t)n_pad * n_pad * sizeof(float), &pd));
-    float* dist = (float*)pd;
+inline void launch_p3(float* dist, int64_t ld, const float* panel, int64_t ldp, int kb, int skip, int nb, int nl,
+                      int part, int next_col, int next_row, uint16_t* rounds, cudaStream_t st) {
+    const dim3 grid = part == 1 ? dim3(nl + nb) : dim3(nb, nl);
+    fw32_p3_kernel<<<grid, 256, FwCfg<float>::p3_smem(), st>>>(dist, ld, panel, ldp, kb, skip, nb, nl, part,
+                                                              next_col, next_row, rounds);
+}
+inline void launch_p3(double* dist, int64_t ld, const double* panel, int64_t ldp, int kb, int skip, int nb, int nl,
+                      int part, int next_col, int next_row, uint16_t* rounds, cudaStream_t st) {
+    const dim3 grid = part == 1 ? dim3(nl + nb) : dim3(nb, nl);
+    fw64_p3_kernel<<<grid, 256, FwCfg<double>::p3_smem(), st>>>(dist, ld, panel, ldp, kb, skip, nb, nl, part,
+                                                               next_col, next_row, rounds);
+}
+
+int fw_aux(wisp_ctx* ctx) {
+    if (!ctx->aux_stream) {
+        int lo = 0, hi = 0;
+        WISP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        WISP_CUDA(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi));
+        for (auto& e : ctx->aux_events) WISP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+template <typename T>
+int run_apsp(wisp_ctx* ctx, const double* d_w, int N, double* d_dist, int32_t* d_pred, cudaStream_t st) {
+    constexpr int B = FwCfg<T>::B;
+    const int64_t n_pad = round_up(N, 128);          // both tile sizes divide it; rows stay 16-byte aligned
+    const int nb = (int)(n_pad / B);
+    WISP_CHECK(nb < (int)kNoRound, "apsp: too many rounds (%d)", nb);
+    void *pd = nullptr, *pr = nullptr;
+    WISP_TRY(wisp_scratch(ctx, SCR_APSP_D, (size_t)n_pad * n_pad * sizeof(T), &pd));
+    T* dist = (T*)pd;
+    uint16_t* rounds = nullptr;
+    if (d_pred) {
+        WISP_TRY(wisp_scratch(ctx, SCR_APSP_R, (size_t)n_pad * n_pad * sizeof(uint16_t), &pr));
+        rounds = (uint16_t*)pr;
+    }
+    WISP_TRY(fw_set_attrs<T>());
+    WISP_TRY(fw_aux(ctx));
+    cudaStream_t side = ctx->aux_stream;
+    cudaEvent_t ev_lead = ctx->aux_events[0], ev_piv = ctx->aux_events[1];
     const int g = (int)std::min<int64_t>((n_pad * n_pad + 255) / 256, (int64_t)ctx->sm_count * 16);
-    fw32_init_kernel<<<g, 256, 0, st>>>(d_w, N, n_pad, dist);
+    fw_init_kernel<T><<<g, 256, 0, st>>>(d_w, N, n_pad, 0, n_pad, dist, rounds);
     ctx->launches++;
-    const int smem1 = kT * (kT + 1) * 4, smem2 = 2 * kT * (kT + 1) * 4;
-    const int smem3 = (int)sizeof(float) * kP3Stages * kP3StageFloats;
-    WISP_CUDA(cudaFuncSetAttribute(fw32_phase3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-    WISP_CUDA(cudaFuncSetAttribute(fw32_phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    WISP_CUDA(cudaFuncSetAttribute(fw32_phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-    for (int kb = 0; kb < nb; ++kb) {
-        float* panel = dist + (int64_t)kb * kT * n_pad;     // single GPU: the panel is the pivot rows in place
-        fw32_phase1_kernel<<<1, 1024, smem1, st>>>(panel, n_pad, kb);
+    const int smem1 = fw_p1_smem<T>(), smem2 = fw_p2_smem<T>();
+    constexpr int P1T = (B / 4) * (B / 4), SUB = B / 32;
+    auto pivot_phases = [&](int kb, cudaStream_t s) {
+        T* panel = dist + (int64_t)kb * B * n_pad;     // single GPU: the panel is the pivot rows in place
+        uint16_t* rpanel = rounds ? rounds + (int64_t)kb * B * n_pad : nullptr;
+        fw_p1_kernel<T, B><<<1, P1T, smem1, s>>>(panel, n_pad, kb, rpanel);
         ctx->launches++;
         if (nb > 1) {
-            fw32_phase2_kernel<<<dim3(nb, 2), 1024, smem2, st>>>(dist, n_pad, panel, n_pad, kb, nb, nb, kb);
-            fw32_phase3_kernel<<<dim3(nb, nb), 256, smem3, st>>>(dist, n_pad, panel, n_pad, kb, kb);
-            ctx->launches += 2;
+            fw_p2_kernel<T, B><<<dim3(nb * SUB, 2), 128, smem2, s>>>(dist, n_pad, panel, n_pad, kb, nb, nb, kb, -1,
+                                                                     rounds, rpanel, -1);
+            ctx->launches++;
         }
+    };
+    pivot_phases(0, st);
+    for (int kb = 0; kb < nb && nb > 1; ++kb) {
+        const T* panel = dist + (int64_t)kb * B * n_pad;
+        const bool more = kb + 1 < nb;
+        if (more) {
+            // lead: the tiles of row / column kb+1, then the next round's pivot phases on the side
+            // stream while the rest of this round runs here
+            launch_p3(dist, n_pad, panel, n_pad, kb, kb, nb, nb, 1, kb + 1, kb + 1, rounds, st);
+            ctx->launches++;
+            WISP_CUDA(cudaEventRecord(ev_lead, st));
+            WISP_CUDA(cudaStreamWaitEvent(side, ev_lead, 0));
+            pivot_phases(kb + 1, side);
+            WISP_CUDA(cudaEventRecord(ev_piv, side));
+        }
+        launch_p3(dist, n_pad, panel, n_pad, kb, kb, nb, nb, more ? 2 : 0, more ? kb + 1 : -1, more ? kb + 1 : -1,
+                  rounds, st);
+        ctx->launches++;
+        if (more) WISP_CUDA(cudaStreamWaitEvent(st, ev_piv, 0));
     }
     WISP_CUDA(cudaGetLastError());
-    // predecessors from the distances (CSR of in-edges built from the dense matrix)
-    int32_t *ptr = nullptr, *idx = nullptr;
-    float* val = nullptr;
+    // ---- predecessors: transpose, resolve the midpoints, chase, transpose back ----
+    const dim3 tb(32, 8), tg((unsigned)(n_pad / 32), (unsigned)(n_pad / 32));
+    int32_t* predT = nullptr;
     if (d_pred) {
-        void* pp = nullptr;
-        WISP_TRY(wisp_scratch(ctx, SCR_APSP_P, (size_t)(N + 1) * 4 + 256, &pp));
-        ptr = (int32_t*)pp;
-        csr_count_kernel<<<(N + 127) / 128, 128, 0, st>>>(d_w, N, ptr + 1);
-        ctx->launches++;
-        std::vector<int32_t> h(N + 1, 0);
-        WISP_CUDA(cudaMemcpyAsync(h.data() + 1, ptr + 1, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
-        WISP_CUDA(cudaStreamSynchronize(st));
-        for (int j = 0; j < N; ++j) h[j + 1] += h[j];
-        const size_t E = (size_t)h[N];
-        if (E > (size_t)N * N / 8) {
-            // dense graph: tiled argmin product instead of the CSR scan
-            fw32_pred_dense_kernel<<<dim3((N + 63) / 64, (N + 63) / 64), 256, 0, st>>>(dist, n_pad, d_w, N, d_pred);
-            ctx->launches++;
-            const int gd = (int)std::min<int64_t>(((int64_t)N * N + 255) / 256, (int64_t)ctx->sm_count * 16);
-            fw32_final_kernel<<<gd, 256, 0, st>>>(dist, N, n_pad, nullptr, nullptr, nullptr, d_dist, nullptr);
-            ctx->launches++;
-            WISP_CUDA(cudaGetLastError());
-            return 0;
-        }
-        void* pe = nullptr;
-        WISP_TRY(wisp_scratch(ctx, SCR_MISC0, E * 8 + 256, &pe));
-        idx = (int32_t*)pe;
-        val = (float*)((char*)pe + round_up((int64_t)E * 4, 16));
-        WISP_CUDA(cudaMemcpyAsync(ptr, h.data(), (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, st));
-        csr_fill_kernel<<<(N + 127) / 128, 128, 0, st>>>(d_w, N, ptr, idx, val);
-        ctx->launches++;
-        WISP_CUDA(cudaStreamSynchronize(st));   // h (host vector) must outlive the H2D copy
+        void *pt = nullptr, *pm = nullptr, *pp = nullptr;
+        WISP_TRY(wisp_scratch(ctx, SCR_APSP_T, (size_t)n_pad * n_pad * sizeof(T), &pt));
+        WISP_TRY(wisp_scratch(ctx, SCR_APSP_M, (size_t)n_pad * n_pad * sizeof(int32_t), &pm));
+        WISP_TRY(wisp_scratch(ctx, SCR_APSP_P, (size_t)n_pad * n_pad * sizeof(int32_t), &pp));
+        T* distT = (T*)pt;
+        int32_t* midT = (int32_t*)pm;
+        predT = (int32_t*)pp;
+        fw_transpose_kernel<T><<<tg, tb, 0, st>>>(dist, n_pad, distT);
+        const int gy = (int)std::max<int64_t>(1, std::min<int64_t>((N + 31) / 32, (int64_t)ctx->sm_count * 8 / std::max(1, N)));
+        fw_resolve_kernel<T, B><<<dim3(N, gy), 256, 0, st>>>(dist, distT, rounds, N, n_pad, midT);
+        fw_chase_kernel<T><<<N, 256, 0, st>>>(midT, distT, N, n_pad, predT);
+        ctx->launches += 3;
     }
-    const int g2 = (int)std::min<int64_t>(((int64_t)N * N + 255) / 256, (int64_t)ctx->sm_count * 16);
-    fw32_final_kernel<<<g2, 256, 0, st>>>(dist, N, n_pad, ptr, idx, val, d_dist, d_pred);
+    fw_final_kernel<T><<<tg, tb, 0, st>>>(dist, predT, N, n_pad, d_dist, d_pred);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
     return 0;
-}
-
-int fw32_set_attrs() {
-    const int smem1 = kT * (kT + 1) * 4, smem2 = 2 * kT * (kT + 1) * 4;
-    const int smem3 = (int)sizeof(float) * kP3Stages * kP3StageFloats;
-    WISP_CUDA(cudaFuncSetAttribute(fw32_phase3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-    WISP_CUDA(cudaFuncSetAttribute(fw32_phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    WISP_CUDA(cudaFuncSetAttribute(fw32_phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-    return 0;
-}
-
-__global__ void fw32_init_rows_kernel(const double* __restrict__ w_rows, int N, int64_t n_pad, int64_t row0,
-                                      int64_t rows_pad, float* __restrict__ dist) {
-    const int64_t total = rows_pad * n_pad;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t rl = e / n_pad, c = e - rl * n_pad, r = row0 + rl;
-        float d = __int_as_float(0x7f800000);
-        if (r == c) d = 0.f;
-        else if (r < N && c < N) { const double v = w_rows[rl * N + c]; if (v != 0.0) d = (float)v; }
-        dist[e] = d;
-    }
 }
 
 }  // namespace
@@ -706,18 +620,18 @@ int launch_apsp(wisp_ctx* ctx, const double* d_w, int N, int precision, double* 
     WISP_CHECK(N > 0, "apsp: empty graph");
     WISP_CHECK(precision == 64 || precision == 32, "apsp: precision must be 64 or 32 (got %d)", precision);
     if (precision == 64) return run_apsp<double>(ctx, d_w, N, d_dist, d_pred, st);
-    if (getenv("WISP_FW32_TRACKED")) return run_apsp<float>(ctx, d_w, N, d_dist, d_pred, st);
-    return run_apsp_f32_fast(ctx, d_w, N, d_dist, d_pred, st);
+    return run_apsp<float>(ctx, d_w, N, d_dist, d_pred, st);
 }
-
 
 // ---------------------------------------------------------------------------------------
 // Row-block sharded FP32 Floyd-Warshall (BASELINE configs[3]): every rank owns a
 // block of 128-row tile rows.  Round kb: the owner of pivot rows kb finishes the pivot ROW
-// PANEL (phase 1 + row half of phase 2) in a separate buffer and broadcasts it (NCCL, done by
-// the caller); every rank then updates its own pivot-column tiles and its remainder tiles
-// from that panel.  The single-GPU path above is the same kernels with the panel aliased to
-// the pivot rows in place.
+// PANEL (P1 + the row half of P2) in a separate buffer and broadcasts it (NCCL, done by the
+// caller); every rank then updates its own pivot-column tiles and its remainder tiles from that
+// panel.  The single-GPU path above is the same kernels with the panel aliased to the pivot rows
+// in place.  wisp_dev_fw32_update_rows_part splits the remainder update for look-ahead: the owner
+// of the NEXT pivot rows updates that tile-row first (part 1), builds and broadcasts the next
+// panel on a second stream, and runs the rest (part 2) meanwhile.
 // ---------------------------------------------------------------------------------------
 extern "C" int wisp_dev_fw32_init_rows(wisp_ctx* ctx, const double* d_w_rows, int N, int64_t row0,
                                        int64_t rows_pad, float* d_dist_local, void* stream) {
@@ -725,44 +639,63 @@ extern "C" int wisp_dev_fw32_init_rows(wisp_ctx* ctx, const double* d_w_rows, in
     cudaStream_t st = wisp_stream(ctx, stream);
     const int64_t n_pad = round_up(N, kT);
     const int g = (int)std::min<int64_t>((rows_pad * n_pad + 255) / 256, (int64_t)ctx->sm_count * 16);
-    fw32_init_rows_kernel<<<g, 256, 0, st>>>(d_w_rows, N, n_pad, row0, rows_pad, d_dist_local);
+    fw_init_kernel<float><<<g, 256, 0, st>>>(d_w_rows, N, n_pad, row0, rows_pad, d_dist_local, nullptr);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
     return 0;
 }
 
-// phase 1 + pivot-row tiles on a [128][n_pad] panel (owner only)
+// P1 + pivot-row tiles on a [128][n_pad] panel (owner only)
 extern "C" int wisp_dev_fw32_pivot_panel(wisp_ctx* ctx, float* d_panel, int N, int kb, void* stream) {
     WISP_CHECK(ctx && d_panel, "fw32_pivot_panel: bad argument");
     cudaStream_t st = wisp_stream(ctx, stream);
     const int64_t n_pad = round_up(N, kT);
     const int nb = (int)(n_pad / kT);
-    WISP_TRY(fw32_set_attrs());
-    const int smem1 = kT * (kT + 1) * 4, smem2 = 2 * kT * (kT + 1) * 4;
-    fw32_phase1_kernel<<<1, 1024, smem1, st>>>(d_panel, n_pad, kb);
-    fw32_phase2_kernel<<<dim3(nb, 1), 1024, smem2, st>>>(d_panel, n_pad, d_panel, n_pad, kb, nb, 0, -1);
+    WISP_TRY(fw_set_attrs<float>());
+    fw_p1_kernel<float, kT><<<1, 1024, fw_p1_smem<float>(), st>>>(d_panel, n_pad, kb, nullptr);
+    fw_p2_kernel<float, kT><<<dim3(nb * (kT / 32), 1), 128, fw_p2_smem<float>(), st>>>(
+        d_panel, n_pad, d_panel, n_pad, kb, nb, 0, -1, -1, nullptr, nullptr, -1);
     ctx->launches += 2;
     WISP_CUDA(cudaGetLastError());
     return 0;
 }
 
-// pivot-column tiles + remainder tiles of a local row block from a received panel;
-// skip_local_tile = local tile-row index holding the pivot rows (-1 if they live elsewhere)
-extern "C" int wisp_dev_fw32_update_rows(wisp_ctx* ctx, float* d_dist_local, int64_t rows_pad,
-                                         const float* d_panel, int N, int kb, int skip_local_tile,
-                                         void* stream) {
+// part 0: pivot-column tiles + every remainder tile of the local row block;
+// part 1: pivot-column tile and remainder tiles of local tile-row `next_local_tile` only;
+// part 2: everything part 1 left out.  skip_local_tile = local tile-row holding the pivot rows
+// of THIS round (-1 if they live elsewhere).
+extern "C" int wisp_dev_fw32_update_rows_part(wisp_ctx* ctx, float* d_dist_local, int64_t rows_pad,
+                                              const float* d_panel, int N, int kb, int skip_local_tile,
+                                              int next_local_tile, int part, void* stream) {
     WISP_CHECK(ctx && d_dist_local && d_panel && rows_pad % kT == 0, "fw32_update_rows: bad argument");
+    WISP_CHECK(part >= 0 && part <= 2, "fw32_update_rows: part must be 0, 1 or 2");
     cudaStream_t st = wisp_stream(ctx, stream);
     const int64_t n_pad = round_up(N, kT);
     const int nb = (int)(n_pad / kT), nl = (int)(rows_pad / kT);
-    WISP_TRY(fw32_set_attrs());
-    const int smem2 = 2 * kT * (kT + 1) * 4;
-    const int smem3 = (int)sizeof(float) * kP3Stages * kP3StageFloats;
-    // column tiles: launch only the y == 1 half (grid.y index 1)
-    fw32_phase2_kernel<<<dim3(nl, 2), 1024, smem2, st>>>(d_dist_local, n_pad, const_cast<float*>(d_panel), n_pad,
-                                                        kb, 0, nl, skip_local_tile);
-    fw32_phase3_kernel<<<dim3(nb, nl), 256, smem3, st>>>(d_dist_local, n_pad, d_panel, n_pad, kb, skip_local_tile);
-    ctx->launches += 2;
+    WISP_TRY(fw_set_attrs<float>());
+    float* panel = const_cast<float*>(d_panel);
+    if (part == 1) {
+        if (next_local_tile < 0 || next_local_tile >= nl) return 0;
+        // column tile (next, kb) first, then the tile-row
+        fw_p2_kernel<float, kT><<<dim3(kT / 32, 2), 128, fw_p2_smem<float>(), st>>>(
+            d_dist_local, n_pad, panel, n_pad, kb, 0, nl, skip_local_tile, -1, nullptr, nullptr, next_local_tile);
+        launch_p3(d_dist_local, n_pad, d_panel, n_pad, kb, skip_local_tile, nb, nl, 1, -1, next_local_tile, nullptr, st);
+        ctx->launches += 2;
+    } else {
+        // column tiles (in part 2 the tile of `next_local_tile` was already done by part 1)
+        fw_p2_kernel<float, kT><<<dim3(nl * (kT / 32), 2), 128, fw_p2_smem<float>(), st>>>(
+            d_dist_local, n_pad, panel, n_pad, kb, 0, nl, skip_local_tile, part == 2 ? next_local_tile : -1,
+            nullptr, nullptr, -1);
+        launch_p3(d_dist_local, n_pad, d_panel, n_pad, kb, skip_local_tile, nb, nl, part == 2 ? 2 : 0, -1,
+                  part == 2 ? next_local_tile : -1, nullptr, st);
+        ctx->launches += 2;
+    }
     WISP_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int wisp_dev_fw32_update_rows(wisp_ctx* ctx, float* d_dist_local, int64_t rows_pad,
+                                         const float* d_panel, int N, int kb, int skip_local_tile,
+                                         void* stream) {
+    return wisp_dev_fw32_update_rows_part(ctx, d_dist_local, rows_pad, d_panel, N, kb, skip_local_tile, -1, 0, stream);
 }
