@@ -7,11 +7,15 @@
 
 Workload (configs[1] of BASELINE.json): 2,000 nodes x 16 atoms, 50,000 frames, residue-COM
 nodes, binary contact map at 15 A; synthetic trajectory (synth.py model, generated on the
-device).  A "step" = one pass coordinates -> cost matrix: K1 node COM, mean + centring,
-K2 DMMA Gram, K3 pair distances, (all-reduce), K4 epilogue.  Frames are sharded over ranks
-(strong scaling: the 50,000 frames are split).  ``value`` has the coordinates resident in
-HBM; ``e2e`` starts from pinned host coordinates and ends with the result matrices on the
-host.  Prints ONE JSON line on rank 0.
+device).  A "step" = one pass coordinates -> cost matrix: K1 node COM (+ alignment landmarks),
+K7 iterative alignment (the reference always runs it, trajectory_analysis_functions.py:96),
+centring, K2 Gram (tcgen05 INT8 digit planes / FP64 DMMA), K3 pair distances, (all-reduce), K4
+epilogue.  Frames are sharded over ranks (strong scaling: the 50,000 frames are split).
+``value`` has the coordinates resident in HBM; ``e2e`` is the ONE call a drop-in user makes --
+wisp_pipeline through the C ABI on a context over all N GPUs, page-locked host coordinates in,
+result matrices in host buffers out.  After the timed loops the results are CHECKED: a 4,096-frame
+prefix goes through the same pipelines and is compared with the CPU oracle (``parity``).
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -54,6 +58,13 @@ def load_peaks():
             peaks["source_pipes"] = "profiles/peaks_r1.json (tools/peaks.cu on this pool's B200)"
         except Exception:
             pass
+    # dispatch ceiling of a 32-bit min-plus relaxation (tools/peaks_minplus.cu, round 2)
+    peaks["minplus_dispatch_ceiling_trelax"] = 17.9
+    try:
+        peaks["minplus_dispatch_ceiling_trelax"] = float(json.load(open(os.path.join(
+            ROOT, "profiles", "peaks_minplus_r2.json")))["minplus_dispatch_ceiling_trelax"])
+    except Exception:
+        pass
     return peaks
 
 
@@ -120,9 +131,11 @@ def cpu_sample(system, frames, cutoff, literal=True, fixed_stages=True):
     import oracle
     coords = system.frames(0, frames)
     t0 = time.perf_counter()
-    nodes, _ = oracle.com_nodes(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx)
+    nodes, align = oracle.com_nodes(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx)
     t_com = time.perf_counter() - t0
-    avg = nodes.sum(axis=0) / frames
+    t0 = time.perf_counter()
+    nodes, avg = oracle.iterative_alignment(align, nodes)           # K7's stage: always runs in the reference
+    t_align = time.perf_counter() - t0
     t0 = time.perf_counter()
     cov = oracle.cartesian_covariance(nodes, avg) if literal else oracle.cartesian_covariance_fast(nodes, avg)
     t_cov = time.perf_counter() - t0
@@ -143,9 +156,9 @@ def cpu_sample(system, frames, cutoff, literal=True, fixed_stages=True):
         t0 = time.perf_counter()
         oracle.func_pearson_correlation(corr, binary)
         t_func = time.perf_counter() - t0
-    detail = dict(com_s=t_com, covariance_s=t_cov, pearson_s=t_pearson, contact_s=t_contact,
+    detail = dict(com_s=t_com, alignment_s=t_align, covariance_s=t_cov, pearson_s=t_pearson, contact_s=t_contact,
                   functionalize_s=t_func)
-    return t_com + t_cov + t_contact, t_pearson + t_func, detail
+    return t_com + t_align + t_cov + t_contact, t_pearson + t_func, detail
 
 
 def blas_threads():
@@ -157,12 +170,20 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+REFERENCE_BLAS_THREADS = 16      # the same at every N (torchrun exports OMP_NUM_THREADS=1 otherwise)
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU path (oracle port, literal loop structure, numpy BLAS
-    with every host thread it can use) on bounded samples of the same workload."""
+    pinned to REFERENCE_BLAS_THREADS threads at every N) on bounded samples of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=min(REFERENCE_BLAS_THREADS, os.cpu_count() or 1))
+    except Exception:
+        pass
     from wisp_mdanalysis_implementation_b200 import synth
     system = synth.SynthSystem(args.nodes, max(args.sample_frames, 8), args.atoms_per_node, seed=1002)
     N, Ts, T = args.nodes, args.sample_frames, args.frames
@@ -176,15 +197,16 @@ def run_reference_arm(args):
         if fixed is None:
             fixed, detail = fx, d
         else:
-            detail.update({k: v for k, v in d.items() if k in ("com_s", "covariance_s", "contact_s")})
+            detail.update({k: v for k, v in d.items() if k in ("com_s", "alignment_s", "covariance_s", "contact_s")})
         t = per_frame + fixed * (Ts / T)
         if i >= args.warmup:
             times.append(t)
     ms = 1e3 * float(np.mean(times))
     value = N * N * Ts / (ms * 1e-3)
     cores = blas_threads()
-    sample = ("%d of %d frames, literal loop structure (per-frame rank-1 np.dot, per-pair np.trace, "
-              "per-frame N x N distances); N^2-only stages amortised over T" % (Ts, T))
+    sample = ("%d of %d frames, literal loop structure (per-frame COM calls, iterative alignment, per-frame rank-1 "
+              "np.dot, per-pair np.trace, per-frame N x N distances); N^2-only stages amortised over T; BLAS "
+              "threads pinned to %d at every N" % (Ts, T, cores))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -201,6 +223,8 @@ def workload_config(args):
                         "map at %.1f A" % (args.nodes, args.atoms_per_node, args.frames, args.cutoff),
             "nodes": args.nodes, "frames": args.frames, "atoms": args.nodes * args.atoms_per_node,
             "paths": args.paths, "sharding": "frames over ranks",
+            "alignment": "iterative alignment to the running average, threshold 1e-5, <= 100 iterations "
+                         "(the reference's defaults); the synthetic trajectory has no global tumbling",
             "l2": "inputs larger than L2 (coordinate block per rank >= 2.4 GB vs 126 MB)"}
 
 
@@ -223,7 +247,9 @@ def main():
     ap.add_argument("--no-paths", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-paths-cap", type=int, default=20, help="seconds allowed for the CPU get_paths comparison")
-    ap.add_argument("--e2e-mode", default="streamed", choices=["streamed", "two-pass"])
+    ap.add_argument("--align-iterations", type=int, default=100, help="K7 iteration limit (reference default 100; 0 = off)")
+    ap.add_argument("--parity-frames", type=int, default=4096, help="frames of the prefix the results are checked on (0 = skip)")
+    ap.add_argument("--parity-nodes", type=int, default=256, help="nodes of the oracle comparison")
     ap.add_argument("--stress-pairs", type=int, default=200)
     ap.add_argument("--stress-paths", type=int, default=1000)
     ap.add_argument("--apsp-nodes", type=int, default=10000, help="configs[2] APSP size (0 = skip)")
@@ -276,7 +302,8 @@ def main():
     torch.cuda.synchronize()
 
     pipe = FramePipeline(ctx, N, A, system.masses, system.node_ptr, system.atom_idx, system.align_idx,
-                         frames_local=T_local, frames_total=T, cutoff=args.cutoff, which_map=1)
+                         frames_local=T_local, frames_total=T, cutoff=args.cutoff, which_map=1,
+                         align_iterations=args.align_iterations)
 
     def barrier():
         if world > 1:
@@ -325,8 +352,29 @@ def main():
 
     reps = max(2, args.steps)
     # order matters: K1 rewrites X (un-centred); mean_and_center centres it in place again
-    k1_ms = time_stage(lambda: pipe.com(d_coords, colsum=True), reps)
-    pipe.mean_and_center(have_colsum=True)
+    aligned = args.align_iterations > 0
+    k1_ms = time_stage(lambda: pipe.com(d_coords, colsum=not aligned), reps)
+    k7 = None
+    if aligned:
+        torch.cuda.synchronize()
+        a7, b7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a7.record()
+        n_it = pipe.align()
+        b7.record()
+        torch.cuda.synchronize()
+        k7_ms = a7.elapsed_time(b7)
+        # per frame and iteration: landmarks read + written (float32), nodes read + written (float64),
+        # then both read again for the column sums; the first (float32-chained) sums read both once more
+        n_al = len(system.align_idx)
+        k7_bytes = T_local * ((n_it * 3 + 1) * (12.0 * n_al) + (n_it * 3 + 1) * (24.0 * N))
+        k7 = {"ms": k7_ms, "iterations": n_it, "ms_per_iteration": k7_ms / max(1, n_it), "bound": "hbm",
+              "achieved_gbs": k7_bytes / (k7_ms * 1e-3) / 1e9, "peak_gbs": load_peaks()["hbm_gbs"],
+              "frac": k7_bytes / (k7_ms * 1e-3) / 1e9 / load_peaks()["hbm_gbs"],
+              "residuals": [r[1] for r in pipe.alignment_log],
+              "note": "host loop: one all-reduce of 3(n_align+N) doubles and one D2H of the same per iteration"}
+        pipe.center_on_mean()
+    else:
+        pipe.mean_and_center(have_colsum=True)
     k2_ms = time_stage(pipe.gram, reps)                       # K2 as the step runs it (auto engine)
     g_auto = pipe.d_sums[0].clone()
     ctx.set_gram_mode("dmma")
@@ -346,7 +394,9 @@ def main():
     k2_dmma_tflops = work["k2_flop_executed"] / (k2_dmma_ms * 1e-3) / 1e12
     # INT8 engine: 10 digit-pair MMAs per FP64 product
     k2_int8_tops = 10.0 * k2_tflops if k2_engine == "int8 tcgen05" else 0.0
-    int8_peak = 2.0 * peaks.get("bf16_tflops", 1633.1)        # dense INT8 = 2 x dense bf16 (MEASURED_PEAKS.json)
+    # INT8 tcgen05 peak: the MMA kernel alone sustains 3,044 TOP/s with ncu reading the utcimma pipe at 72.9 %
+    # (profiles/ncu_final_r1.json) -> 4,175 TOP/s at 100 %; 2 x the measured dense bf16 (3,266) would flatter
+    int8_peak = peaks.get("int8_tcgen05_tops", 4175.0)
     k3_rate = work["k3_pairframes_executed"] / (k3_ms * 1e-3)
     k1_gbs = work["k1_bytes"] / (k1_ms * 1e-3) / 1e9
     kernels = {
@@ -371,6 +421,8 @@ def main():
                        "fp32_flop_frac": 8 * k3_rate / 1e12 / peaks["fp32_fma_tflops"]},
         "k4_epilogue_allreduce": {"ms": k4_ms},
     }
+    if k7:
+        kernels["k7_align"] = k7
     dominant = "k2_gram_dmma" if (k2_ms >= k3_ms and k2_engine == "fp64 dmma") else "k3_contact"
     if dominant == "k2_gram_dmma":
         roofline = {"kernel": "gram_dmma_kernel<3>", "bound": "tensor", "achieved": k2_tflops,
@@ -389,7 +441,8 @@ def main():
     if k2_engine == "int8 tcgen05":
         roofline_tensor = {"kernel": "gram_i8_kernel", "bound": "tensor", "achieved": k2_int8_tops, "peak": int8_peak,
                            "unit": "TOP/s", "frac": k2_int8_tops / int8_peak, "traffic": None,
-                           "peak_source": "2 x MEASURED_PEAKS.json dense bf16 (INT8 is twice bf16 on tcgen05); "
+                           "peak_source": "ncu-derived: gram_i8_kernel alone = 3,044 TOP/s at 72.9 % utcimma pipe "
+                                          "utilisation -> 4,175 TOP/s (2 x measured dense bf16 would be 3,266); "
                                           "achieved counts the whole K2 stage time, not the MMA kernel alone"}
     else:
         roofline_tensor = {"kernel": "gram_dmma_kernel<3>", "bound": "tensor", "achieved": k2_tflops,
@@ -404,49 +457,200 @@ def main():
         roofline["traffic"] = ncu.get(roofline["kernel"].split("<")[0])
         roofline_tensor["traffic"] = ncu.get(roofline_tensor["kernel"].split("<")[0])
         roofline_hbm["traffic"] = ncu.get("com_stream_kernel", 0.0) + ncu.get("align_shift_kernel", 0.0)
+        for rf in (roofline, roofline_tensor, roofline_hbm):
+            rf["traffic_source"] = ncu.get("_source", "profiles/ncu_traffic_r1.json (ncu --set full of the round-1 build; "
+                                                     "these kernels are unchanged since)")
     except Exception:
         pass
 
-    # ---- e2e: pinned host coordinates -> results on the host ----
+    # ---- e2e: the ONE call a drop-in user makes.  wisp_pipeline (C ABI) on a context over all N GPUs of the
+    # box, page-locked host coordinates in, result matrices in page-locked host buffers out.  Under torchrun the
+    # other ranks wait at a barrier while rank 0 makes the call: the library shards the frames over the N GPUs
+    # itself (one host thread, stream and PCIe link per GPU; partial sums combined over NVLink peer memory inside
+    # the epilogue kernel).  The per-rank NCCL path (FramePipeline.run_host) is timed beside it. ----
     e2e = None
     if not args.no_e2e:
-        h_coords = torch.empty((T_local, A, 3), dtype=torch.float32, pin_memory=True)
-        h_coords.copy_(d_coords)
+        def pinned(shape, dtype):
+            return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+        # (a) per-rank path: every rank feeds its own frames from its own pinned buffer, NCCL all-reduce
+        h_local = pinned((T_local, A, 3), torch.float32)
+        h_local.copy_(d_coords)
         torch.cuda.synchronize()
-        # raw pinned H2D bandwidth of this box: the e2e pass can not beat h2d_bytes / this
+        # barrier-aligned concurrent H2D probe: every rank copies 2 GiB x 3 at the same time
         nprobe = min(T_local, max(1, (2 << 30) // (A * 12)))
         probe = torch.empty((nprobe, A, 3), dtype=torch.float32, device=dev)
-        probe.copy_(h_coords[:nprobe], non_blocking=True)
-        torch.cuda.synchronize()
+        probe.copy_(h_local[:nprobe], non_blocking=True)
+        barrier()
         pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         pa.record()
         for _ in range(3):
-            probe.copy_(h_coords[:nprobe], non_blocking=True)
+            probe.copy_(h_local[:nprobe], non_blocking=True)
         pb.record()
         torch.cuda.synchronize()
-        h2d_gbs = 3 * nprobe * A * 12 / (pa.elapsed_time(pb) * 1e-3) / 1e9
+        probe_ms = pa.elapsed_time(pb)
+        h2d_gbs_rank = 3 * nprobe * A * 12 / (probe_ms * 1e-3) / 1e9
+        h2d_gbs_aggregate = world * 3 * nprobe * A * 12 / (max_over_ranks(probe_ms) * 1e-3) / 1e9
         del probe
-        run_e2e = pipe.run_host_streamed if args.e2e_mode == "streamed" else pipe.run_host
-        for _ in range(max(1, args.warmup - 1)):
-            run_e2e(h_coords)
+        for _ in range(2):
+            pipe.run_host(h_local)
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
         a.record()
         for _ in range(args.steps):
-            res = run_e2e(h_coords)
+            pipe.run_host(h_local)
         b.record()
         barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-        ms_e2e = max_over_ranks(max(a.elapsed_time(b) / args.steps, 0.0))
-        e2e = {"value": float(N) * N * T / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-               "wall_ms_per_step": wall_ms, "h2d_bytes_per_step": pipe.h2d_bytes() * world,
-               "d2h_bytes_per_step": pipe.d2h_bytes(), "numa_node_rank0": numa_node,
-               "pcie_h2d_gbs_measured": h2d_gbs,
-               "frac_of_pcie_bound": (pipe.h2d_bytes() / (h2d_gbs * 1e9)) / (ms_e2e * 1e-3),
-               "api": "FramePipeline.%s (C-ABI wisp_dev_* calls; pinned host coords in, "
-                      "corr/avgdist/binary/w on the host out)" % run_e2e.__name__}
-        del h_coords
+        ms_rank_path = max_over_ranks(a.elapsed_time(b) / args.steps)
+
+        # (b) the C-ABI call on rank 0 over all N GPUs
+        ms_call, wall_call, api_gpus = None, None, world
+        host_nodes = None
+        if world > 1:
+            # gather the whole trajectory into ONE page-locked buffer on rank 0 (setup, untimed); frame
+            # shard r is first-touched on the NUMA node of GPU r (pipeline.host_trajectory_numa_sharded)
+            if rank == 0:
+                affinity0 = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, range(os.cpu_count()))       # undo the per-rank binding for the threads of the call
+
+                def fill(r, view):
+                    dst = torch.from_numpy(view)
+                    if r == 0:
+                        dst.copy_(d_coords)
+                    else:
+                        tmp = torch.empty(view.shape, dtype=torch.float32, device=dev)
+                        dist.recv(tmp, src=r)
+                        dst.copy_(tmp)
+                        del tmp
+                from wisp_mdanalysis_implementation_b200.pipeline import host_trajectory_numa_sharded
+                h_np, host_nodes = host_trajectory_numa_sharded((T, A, 3), world, fill)
+            else:
+                dist.send(d_coords, dst=0)
+            torch.cuda.synchronize()
+        else:
+            h_np = h_local.numpy()
+        barrier()
+        if rank == 0:
+            mctx = _lib.Context(gpus=world) if world > 1 else ctx
+            outbuf = {"avg": pinned((N, 3), torch.float64).numpy(), "corr": pinned((N, N), torch.float64).numpy(),
+                      "avgdist": pinned((N, N), torch.float64).numpy(), "binary": pinned((N, N), torch.int64).numpy(),
+                      "w": pinned((N, N), torch.float64).numpy()}
+
+            def call():
+                return mctx.pipeline(h_np, system.masses, system.node_ptr, system.atom_idx, system.align_idx,
+                                     cutoff=args.cutoff, which_map=1, maximum_num_iterations=args.align_iterations,
+                                     out=outbuf)
+            for _ in range(2):
+                res_call = call()
+            torch.cuda.synchronize()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            ea.record()
+            for _ in range(args.steps):
+                res_call = call()          # blocking: returns when every GPU's slice is in the host buffers
+            eb.record()
+            torch.cuda.synchronize()
+            wall_call = (time.perf_counter() - t0) * 1e3 / args.steps
+            ms_call = ea.elapsed_time(eb) / args.steps
+            e2e_corr = res_call["corr"].copy()
+            e2e_avgdist = res_call["avgdist"].copy()
+            e2e_iters = len(res_call["alignment_log"])
+        barrier()
+        if rank == 0:
+            h2d_total = T * A * 12
+            e2e = {"value": float(N) * N * T / (ms_call * 1e-3), "unit": UNIT, "ms_per_step": ms_call,
+                   "wall_ms_per_step": wall_call, "h2d_bytes_per_step": h2d_total,
+                   "d2h_bytes_per_step": 4 * N * N * 8 + N * 24,
+                   "api": "wisp_pipeline (C ABI, include/wisp_b200.h) on wisp_ctx_create_multi(%d): page-locked host "
+                          "coordinates in; avg / corr / avgdist / binary / w in page-locked host buffers out; "
+                          "K7 alignment included (%d iterations)" % (api_gpus, e2e_iters),
+                   "gpus_in_call": api_gpus,
+                   "host_numa_node_per_shard": host_nodes,
+                   "pcie_h2d_gbs_per_rank_concurrent": h2d_gbs_rank,
+                   "pcie_h2d_gbs_aggregate_concurrent": h2d_gbs_aggregate,
+                   "frac_of_pcie_bound": (h2d_total / (h2d_gbs_aggregate * 1e9)) / (ms_call * 1e-3),
+                   "per_rank_nccl_path": {"ms_per_step": ms_rank_path, "value": float(N) * N * T / (ms_rank_path * 1e-3),
+                                          "api": "FramePipeline.run_host on every rank (wisp_dev_* C-ABI calls, "
+                                                 "K7 all-reduces, one NCCL all-reduce of [G || D])"}}
+            if world > 1:
+                mctx.close()
+                _lib.host_unregister(h_np)
+                os.sched_setaffinity(0, affinity0)
+        del h_local
+
+    # ---- parity: the SAME pipelines on a frame prefix, checked against the CPU oracle on a node subset (every
+    # matrix entry depends on its two nodes only), the multi-rank result against a single-GPU recomputation,
+    # and the e2e call's full-length result against the device-resident pass ----
+    parity = None
+    if args.parity_frames > 0:
+        Tp = int(min(args.parity_frames, T // world))
+        d_prefix = d_coords[:Tp].clone() if rank == 0 else torch.empty((Tp, A, 3), dtype=torch.float32, device=dev)
+        if world > 1:
+            dist.broadcast(d_prefix, src=0)
+        q0, q1 = Tp * rank // world, Tp * (rank + 1) // world
+        ctx.set_gram_mode("i8" if k2_engine == "int8 tcgen05" else "dmma")      # the engine the timed pass used
+        try:
+            pp = FramePipeline(ctx, N, A, system.masses, system.node_ptr, system.atom_idx, system.align_idx,
+                               frames_local=q1 - q0, frames_total=Tp, cutoff=args.cutoff, which_map=1,
+                               align_iterations=args.align_iterations)
+            pp.run_device(d_prefix[q0:q1].contiguous())
+            torch.cuda.synchronize()
+            if rank == 0:
+                import oracle
+                got = dict(corr=pp.d_corr.cpu().numpy(), avgdist=pp.d_avgdist.cpu().numpy(),
+                           binary=pp.d_binary.cpu().numpy())
+                parity = {"frames": Tp, "k2_engine_forced": "i8 (accuracy-gated)" if k2_engine == "int8 tcgen05" else "dmma",
+                          "alignment_iterations": len(pp.alignment_log)}
+                if world > 1:
+                    one = FramePipeline(ctx, N, A, system.masses, system.node_ptr, system.atom_idx, system.align_idx,
+                                        frames_local=Tp, frames_total=Tp, cutoff=args.cutoff, which_map=1,
+                                        align_iterations=args.align_iterations, group=False)
+                    one.run_device(d_prefix)
+                    torch.cuda.synchronize()
+                    c1, d1, b1 = one.d_corr.cpu().numpy(), one.d_avgdist.cpu().numpy(), one.d_binary.cpu().numpy()
+                    parity["multi_rank_vs_single_gpu"] = {
+                        "ranks": world,
+                        "max_rel_corr": float((np.abs(got["corr"] - c1) / np.maximum(np.abs(c1), 1e-3)).max()),
+                        "max_rel_dist": float((np.abs(got["avgdist"] - d1) / np.maximum(d1, 1e-9))[~np.eye(N, dtype=bool)].max()),
+                        "topology_mismatches": int((got["binary"] != b1).sum())}
+                    del one
+                # oracle on a node subset that touches every tile class
+                rng = np.random.default_rng(7)
+                sel = np.unique(np.concatenate([rng.choice(N, size=min(N, args.parity_nodes), replace=False),
+                                                [0, min(N - 1, 127), min(N - 1, 128), N - 1]]))
+                ptr = np.concatenate([[0], np.cumsum(np.diff(system.node_ptr)[sel])]).astype(np.int64)
+                idx = np.concatenate([system.atom_idx[system.node_ptr[i]:system.node_ptr[i + 1]] for i in sel])
+                h_prefix = d_prefix.cpu().numpy()
+                t0 = time.perf_counter()
+                nodes_o, align_o = oracle.com_nodes_fast(h_prefix, system.masses, ptr, idx, system.align_idx)
+                if args.align_iterations > 0:
+                    nodes_o, avg_o = oracle.iterative_alignment(align_o, nodes_o, maximum_num_iterations=args.align_iterations)
+                else:
+                    avg_o = nodes_o.sum(axis=0) / Tp
+                _, _, corr_o = oracle.pearson_correlation_fast(oracle.cartesian_covariance_fast(nodes_o, avg_o))
+                bin_o, dist_o = oracle.calc_contact_map_fast(nodes_o, args.cutoff)
+                ix = np.ix_(sel, sel)
+                off = ~np.eye(len(sel), dtype=bool)
+                rel_c = np.abs(got["corr"][ix] - corr_o) / np.maximum(np.abs(corr_o), 1e-3)
+                rel_d = (np.abs(got["avgdist"][ix] - dist_o) / np.maximum(dist_o, 1e-9))[off]
+                near = np.abs(dist_o - args.cutoff) <= 1e-6 * args.cutoff
+                mism = int(((got["binary"][ix] != bin_o) & ~near).sum())
+                parity.update({"nodes_checked": int(len(sel)), "entries_checked": int(len(sel)) ** 2,
+                               "max_rel_corr": float(rel_c.max()), "max_rel_dist": float(rel_d.max()),
+                               "topology_mismatches": mism, "oracle_s": time.perf_counter() - t0,
+                               "tolerance": "1e-6 relative (|C| floor 1e-3), topology exact outside |D - cutoff| <= 1e-6 cutoff",
+                               "pass": bool(rel_c.max() <= 1e-6 and rel_d.max() <= 1e-6 and mism == 0)})
+                if e2e is not None:
+                    # the e2e call worked on ALL frames: compare with the device-resident pass (same data, same stages)
+                    parity["e2e_call_vs_resident_pass"] = {
+                        "max_abs_corr": float(np.abs(e2e_corr - pipe.d_corr.cpu().numpy()).max()),
+                        "max_rel_dist": float((np.abs(e2e_avgdist - pipe.d_avgdist.cpu().numpy())
+                                               / np.maximum(e2e_avgdist, 1e-9))[~np.eye(N, dtype=bool)].max())}
+            del pp
+        finally:
+            ctx.set_gram_mode("auto")
+        del d_prefix
+        barrier()
 
     # ---- APSP + 500 suboptimal paths on the resulting cost matrix (rank 0) ----
     extra = {}
@@ -495,7 +699,9 @@ def main():
                             # pipe bound of a relaxation: adds on the FP32 pipe (FADD2) vs mins on the ALU pipe
                             "frac_of_add_min_pipe_bound": rate / min(peaks_.get("fp32_ffma2_tflops", 72.1) / 2.0,
                                                                      peaks_.get("fmnmx_tops", 36.6)),
-                            "vs_scalar_fadd_fmnmx_loop": rate / peaks_.get("fp32_minplus_trelax", 12.1)}
+                            # two dispatch cycles per relaxation whatever the instruction form (FADD2+FMNMX3,
+                            # FADD+FMNMX, DPX VIADDMNMX): 17.9 T/s = 49.6 % of the FP32 peak is the machine's limit
+                            "frac_of_dispatch_ceiling": rate / peaks_["minplus_dispatch_ceiling_trelax"]}
             extra["apsp_%d_nodes" % n3] = big
             del Wb
         t0 = time.perf_counter()
@@ -603,7 +809,7 @@ def main():
                               "(accuracy-gated, DMMA FP64 fallback), K3 per-frame distances FP32 with FP64 sums",
                 "config": workload_config(args), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
-                "roofline": roofline, "roofline_tensor": roofline_tensor, "roofline_hbm": roofline_hbm, "kernels": kernels, "cpu_baseline": cpu_baseline, "extra": extra}
+                "roofline": roofline, "roofline_tensor": roofline_tensor, "roofline_hbm": roofline_hbm, "kernels": kernels, "parity": parity, "cpu_baseline": cpu_baseline, "extra": extra}
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
     if world > 1:

@@ -20,6 +20,7 @@
 #ifndef WISP_B200_H
 #define WISP_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -30,6 +31,17 @@ typedef struct wisp_ctx wisp_ctx;
 
 /* ---- context ------------------------------------------------------------------------ */
 int         wisp_ctx_create(int device, wisp_ctx** out);
+/* One context over n_gpus GPUs of this box (devices[] or, when NULL, 0..n_gpus-1; n_gpus = 0: every
+ * visible GPU).  wisp_pipeline on such a context shards the frames over the GPUs (one host thread,
+ * stream and PCIe link per GPU) and combines the partial sums over NVLink peer memory inside its
+ * epilogue kernel -- the caller makes the same single call as on one GPU.  Every other entry point
+ * uses the first device. */
+int         wisp_ctx_create_multi(int n_gpus, const int* devices, wisp_ctx** out);
+int         wisp_ctx_gpus(wisp_ctx* ctx);
+/* Page-lock a caller-owned host range (e.g. the MemoryReader coordinate array) so that the chunked
+ * H2D copies of wisp_pipeline / wisp_com_nodes run asynchronously at full PCIe rate from every GPU. */
+int         wisp_host_register(void* ptr, size_t bytes);
+int         wisp_host_unregister(void* ptr);
 void        wisp_ctx_destroy(wisp_ctx* ctx);
 const char* wisp_last_error(void);
 int         wisp_abi_version(void);
@@ -114,6 +126,15 @@ int wisp_pipeline(wisp_ctx* ctx, const float* coords, int64_t T, int A, const do
                   double* out_corr, double* out_avgdist, int64_t* out_binary, double* out_w,
                   double* out_nodes);
 
+/* The same call, also returning the alignment log: out_log [3 * max_align_iterations] =
+ * (iteration, landmark RMSD, node RMSD) per iteration, *out_n_iter = iterations run (may be NULL). */
+int wisp_pipeline_log(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
+                      const int32_t* node_ptr, const int32_t* atom_idx, int N,
+                      const int32_t* align_idx, int n_align, int atomic, double align_threshold,
+                      int max_align_iterations, double cutoff, int which_map, double* out_avg,
+                      double* out_corr, double* out_avgdist, int64_t* out_binary, double* out_w,
+                      double* out_nodes, double* out_log, int* out_n_iter);
+
 /* a6 (north-star APSP; the reference calls Dijkstra, network_analysis_functions.py:30,71-72).
  * w [N][N] cost matrix (non-zero = edge).  precision 64 or 32 (distances are returned as
  * float64 either way).  out_dist [N][N], out_pred [N][N] (-1 = none); pred may be NULL. */
@@ -131,6 +152,13 @@ int wisp_get_paths(wisp_ctx* ctx, const double* w, int N, const int32_t* sources
 int wisp_paths_prepare(wisp_ctx* ctx, const double* w, int N, int flags);
 int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sources, const int32_t* sinks,
                      int n_sinks, int number_of_paths, int flags);
+/* Many independent queries on the prepared graph, answered together: query q =
+ * get_paths([pairs[q][0]], [pairs[q][1]], number_of_paths).  The results are concatenated in query
+ * order (wisp_paths_size / wisp_paths_fetch); wisp_paths_query_offsets gives the index of the first
+ * path of every query: offsets [n_queries + 1] (pass NULL to get only the count). */
+int wisp_paths_query_pairs(wisp_ctx* ctx, const int32_t* pairs /* [n_queries][2] */, int n_queries,
+                           int number_of_paths, int flags);
+int wisp_paths_query_offsets(wisp_ctx* ctx, int64_t* n_queries, int64_t* offsets);
 int wisp_paths_size(wisp_ctx* ctx, int64_t* n_paths, int64_t* n_node_entries);
 int wisp_paths_fetch(wisp_ctx* ctx, double* lengths, int64_t* offsets /* n_paths+1 */,
                      int32_t* nodes);
@@ -163,6 +191,19 @@ int  wisp_com_plan_info(const wisp_com_plan* plan, int* streaming, int* n_pieces
  * frames of every column. */
 int wisp_dev_com(wisp_ctx* ctx, wisp_com_plan* plan, const float* d_coords, int64_t T, int N,
                  double* d_nodes, double* d_colsum, void* stream);
+/* The same, also writing the translated alignment landmarks (trajectory_analysis_functions.py:72):
+ * d_align_out float32 [T][n_align][3] (may be NULL). */
+int wisp_dev_com_align(wisp_ctx* ctx, wisp_com_plan* plan, const float* d_coords, int64_t T, int N,
+                       double* d_nodes, double* d_colsum, float* d_align_out, void* stream);
+/* K7 building blocks for a frame-sharded alignment loop (trajectory_analysis_functions.py:86-126).
+ * wisp_dev_align_sums: d_sums [3 n_align + 3 N] = column sums of this rank's landmarks, then of its
+ * node rows; first != 0: the landmark sums are the reference's sequential float32 sums (:86).
+ * wisp_dev_align_rotate: rotate every frame of this rank onto d_avg_align [3 n_align] in place.
+ * The caller all-reduces the sums, divides by the total frame count and tests the RMSD (:118). */
+int wisp_dev_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_nodes,
+                        int64_t T, int N, int first, double* d_sums, void* stream);
+int wisp_dev_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align,
+                          double* d_nodes, int64_t T, int N, void* stream);
 /* X <- X - mean (in place), mean [ld]; pad columns / rows are left at zero.  When d_p32 is
  * not NULL it also receives the FP32 tile-referenced copy K3 reads:
  * float [T][wisp_gram_ld(N)/128][3][128], value = float(x - mean of the tile's middle node). */

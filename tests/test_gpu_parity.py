@@ -897,3 +897,144 @@ def test_apsp_c3_size_vs_scipy_dijkstra(ctx, precision, tol):
         np.testing.assert_allclose(dist[s, p[ok]] + W[p[ok], jj[ok]], dist[s, ok], rtol=10 * tol, atol=1e-12)
         if precision == 64:
             assert np.array_equal(p[ok], want_pred[r][ok])
+
+
+# ---------------------------------------------------------------------------------------
+# wisp_pipeline on a multi-GPU context (wisp_ctx_create_multi): frames sharded inside the one C
+# call, K7 alignment with per-iteration host reduction, partial sums combined inside the fused
+# peer-memory epilogue.  On a one-GPU box the shards share the device (same code path: host
+# threads, barriers, reductions, row-sliced epilogue reading every shard's partials).
+# ---------------------------------------------------------------------------------------
+def _multi_ctx(n_shards):
+    import torch
+    from wisp_mdanalysis_implementation_b200 import _lib
+    n_dev = torch.cuda.device_count()
+    return _lib.Context(gpus=[k % n_dev for k in range(n_shards)])
+
+
+@pytest.mark.parametrize("shards,n,t,apn", [(2, 150, 700, 5), (3, 257, 1001, 4), (8, 300, 999, 3)])
+def test_pipeline_multi_shard_with_alignment(ctx, shards, n, t, apn):
+    system, coords = synth.synth(n, t, apn, seed=50 + shards)
+    # a slow global tumble so that the alignment has something to do
+    ang = np.linspace(0.0, 0.6, t)
+    c, s = np.cos(ang), np.sin(ang)
+    rot = np.zeros((t, 3, 3)); rot[:, 0, 0] = c; rot[:, 0, 1] = -s; rot[:, 1, 0] = s; rot[:, 1, 1] = c; rot[:, 2, 2] = 1
+    centre = coords.mean(axis=1, keepdims=True)
+    coords = (np.einsum("tac,tdc->tad", coords - centre, rot) + centre).astype(np.float32)
+    cutoff = 13.0
+    mctx = _multi_ctx(shards)
+    assert mctx.n_gpus == shards
+    one = ctx.pipeline(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx, cutoff=cutoff,
+                       which_map=1, want_nodes=True, maximum_num_iterations=100)
+    got = mctx.pipeline(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx, cutoff=cutoff,
+                        which_map=1, want_nodes=True, maximum_num_iterations=100)
+    assert len(got["alignment_log"]) == len(one["alignment_log"]) >= 2
+    assert got["alignment_log"][-1][1] <= 1e-5
+    # sharded vs single GPU: same arithmetic up to the order of the frame sums
+    np.testing.assert_allclose(got["nodes"], one["nodes"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(got["avg"], one["avg"], rtol=0, atol=1e-7)
+    assert_corr_close(got["corr"], one["corr"], rel=1e-7)
+    np.testing.assert_allclose(got["avgdist"], one["avgdist"], rtol=1e-7)
+    assert np.all(np.diagonal(got["corr"]) == 1.0) and np.array_equal(got["corr"], got["corr"].T)
+    # and against the oracle's traj_alignment_and_averaging -> covariance -> Pearson / contact map
+    nodes, avg = oracle.traj_alignment_and_averaging(coords.copy(), system.masses, system.node_ptr,
+                                                     system.atom_idx, system.align_idx)
+    np.testing.assert_allclose(got["nodes"], nodes, rtol=0, atol=1e-6)
+    _, _, corr = oracle.pearson_correlation_fast(oracle.cartesian_covariance_fast(nodes, avg))
+    binary, avgdist = oracle.calc_contact_map_fast(nodes, cutoff)
+    assert_corr_close(got["corr"], corr)
+    np.testing.assert_allclose(got["avgdist"], avgdist, rtol=1e-6, atol=1e-9)
+    assert_binary_equal_outside_ties(got["binary"], avgdist, cutoff, binary)
+    w = oracle.func_pearson_correlation(corr, binary)
+    if np.array_equal(got["binary"], binary):
+        nz = w != 0
+        assert np.array_equal(got["w"] != 0, nz)
+        np.testing.assert_allclose(got["w"][nz], w[nz], rtol=0, atol=2e-6)
+    mctx.close()
+
+
+def test_pipeline_multi_shard_without_alignment_and_errors(ctx):
+    from wisp_mdanalysis_implementation_b200 import _lib
+    system, coords = synth.synth(130, 500, 4, seed=77)
+    mctx = _multi_ctx(4)
+    one = ctx.pipeline(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx, cutoff=12.0, which_map=2)
+    got = mctx.pipeline(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx, cutoff=12.0, which_map=2)
+    assert got["alignment_log"] == []
+    assert_corr_close(got["corr"], one["corr"], rel=1e-9)
+    np.testing.assert_allclose(got["avgdist"], one["avgdist"], rtol=1e-9)
+    np.testing.assert_allclose(got["w"], one["w"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(got["avg"], one["avg"], rtol=0, atol=1e-11)
+    # fewer frames than shards: the call still works (shards beyond the frame count stay idle)
+    tiny = mctx.pipeline(coords[:3], system.masses, system.node_ptr, system.atom_idx, system.align_idx, cutoff=12.0)
+    ref = ctx.pipeline(coords[:3], system.masses, system.node_ptr, system.atom_idx, system.align_idx, cutoff=12.0)
+    np.testing.assert_allclose(tiny["avgdist"], ref["avgdist"], rtol=1e-9)
+    # a failing shard fails the call loudly instead of hanging the others
+    with pytest.raises(_lib.WispError):
+        bad = system.atom_idx.copy(); bad[5] = 10 ** 6
+        mctx.pipeline(coords, system.masses, system.node_ptr, bad, system.align_idx)
+    # every other entry point of a multi context runs on its first device
+    W = synth.random_cost_matrix(40, seed=3, density=0.2)
+    assert mctx.get_paths(W, [1], [30], 5) == ctx.get_paths(W, [1], [30], 5)
+    mctx.close()
+
+
+def test_published_config_c2_multi_shard_with_alignment(ctx):
+    """configs[1] geometry through the ONE call a drop-in user makes -- wisp_pipeline on a multi-GPU
+    context, alignment included -- against the oracle (alignment on all landmarks, correlation /
+    contacts on 200 nodes drawn from every tile).  Two shards of 4,100 frames: each runs the INT8
+    tensor-core K2 engine on its own frames."""
+    n, t, apn, cutoff = 2000, 8200, 16, 15.0
+    system = synth.SynthSystem(n, t, apn, seed=1002)
+    coords = system.coords()
+    rng = np.random.default_rng(6)
+    sel = np.unique(np.concatenate([rng.choice(n, size=190, replace=False), [0, 127, 128, 1919, 1920, 1999]]))
+    ptr = np.concatenate([[0], np.cumsum(np.diff(system.node_ptr)[sel])]).astype(np.int64)
+    idx = np.concatenate([system.atom_idx[system.node_ptr[i]:system.node_ptr[i + 1]] for i in sel])
+    nodes, align = oracle.com_nodes_fast(coords, system.masses, ptr, idx, system.align_idx)
+    log = []
+    nodes, avg = oracle.iterative_alignment(align, nodes, log=log)
+    _, _, corr = oracle.pearson_correlation_fast(oracle.cartesian_covariance_fast(nodes, avg))
+    binary, avgdist = oracle.calc_contact_map_fast(nodes, cutoff)
+    mctx = _multi_ctx(2)
+    out = mctx.pipeline(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx,
+                        cutoff=cutoff, which_map=1, maximum_num_iterations=100)
+    assert len(out["alignment_log"]) == len(log)
+    np.testing.assert_allclose(out["avg"][sel], avg, rtol=0, atol=1e-6)
+    _check_subset(out, sel, corr, binary, avgdist, cutoff)
+    mctx.close()
+
+
+def test_paths_query_pairs_batched(ctx):
+    """wisp_paths_query_pairs: many independent get_paths([s], [t], K) queries served by the same kernel
+    passes (configs[4]) -- every query must equal its stand-alone answer and the oracle, including the
+    K + 1 returns and K = 1."""
+    W = synth.random_cost_matrix(70, seed=78, density=0.12, lo=0.05, hi=0.9)
+    ctx.paths_prepare(W)
+    rng = np.random.default_rng(9)
+    pairs = [tuple(int(x) for x in rng.choice(70, size=2, replace=False)) for _ in range(17)]
+    pairs += [pairs[0], (pairs[1][1], pairs[1][0])]           # a repeated and a reversed query
+    for K in (1, 7, 60):
+        got = ctx.paths_query_pairs(pairs, K)
+        assert len(got) == len(pairs)
+        for (s, t), paths in zip(pairs, got):
+            assert paths == ctx.paths_query([s], [t], K), (s, t, K)
+        for (s, t), paths in list(zip(pairs, got))[:5]:
+            want = oracle.get_paths_pruned(W, [s], [t], K)
+            assert [p[1:] for p in paths] == [[int(x) for x in p[1:]] for p in want]
+            assert [p[0] for p in paths] == [float(p[0]) for p in want]
+    qoff, lengths, noff, nodes = ctx.paths_query_pairs(pairs, 7, packed=True)
+    assert len(qoff) == len(pairs) + 1 and qoff[-1] == len(lengths) and noff[-1] == len(nodes)
+    from wisp_mdanalysis_implementation_b200 import _lib
+    with pytest.raises(_lib.WispError):
+        ctx.paths_query_pairs([(3, 3)], 5)
+
+
+def test_get_paths_duplicate_pairs(ctx):
+    """A repeated index in sources / sinks makes identical paths inside one pass; the reference removes
+    them per pass before comparing with K (remove_redundant_paths), so the ratchet must too."""
+    W = synth.random_cost_matrix(40, seed=31, density=0.2, lo=0.05, hi=0.9)
+    for so, si, K in [([3, 3], [30], 9), ([5], [22, 22], 14), ([3, 3], [30, 30], 6)]:
+        want = oracle.get_paths_pruned(W, so, si, K)
+        got = ctx.get_paths(W, so, si, K)
+        assert [p[1:] for p in got] == [[int(x) for x in p[1:]] for p in want], (so, si, K)
+        assert [p[0] for p in got] == [float(p[0]) for p in want]

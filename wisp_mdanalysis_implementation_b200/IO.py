@@ -4,7 +4,8 @@ Behaviour follows the reference's ``IO.py``: the config file is Python source ex
 the ``parameters`` dict (IO.py:54), sixteen keys are mandatory (IO.py:24,55-58), the rest have
 defaults (IO.py:32-51).  Keys the reference's driver reads without ever declaring
 (wisp_w_mdanalysis.py:114,128,141,142 -- SURVEY.md App. B4) get defaults here as well, and two
-extension keys exist: ``universe_factory`` and ``fused_pipeline_boolean``.
+extension keys exist: ``universe_factory``, ``fused_pipeline_boolean`` and ``gpus`` (GPUs of this
+box the fused pipeline shards the frames over; 0 = all of them).
 """
 import sys
 
@@ -31,7 +32,7 @@ DEFAULTS = dict(
     adjacency_matrix_analysis_boolean=True, weight_by_contact_map_boolean=False, Lambda=None,
     user_input_average_node_positions=None,
     # extensions of this implementation
-    universe_factory=None, fused_pipeline_boolean=False,
+    universe_factory=None, fused_pipeline_boolean=False, gpus=1,
 )
 
 

@@ -22,6 +22,10 @@ _int = C.c_int
 _dbl = C.c_double
 SIGNATURES = {
     "wisp_ctx_create": (_int, [_int, C.POINTER(_c_ctx)]),
+    "wisp_ctx_create_multi": (_int, [_int, _P, C.POINTER(_c_ctx)]),
+    "wisp_ctx_gpus": (_int, [_c_ctx]),
+    "wisp_host_register": (_int, [_P, C.c_size_t]),
+    "wisp_host_unregister": (_int, [_P]),
     "wisp_ctx_destroy": (None, [_c_ctx]),
     "wisp_last_error": (C.c_char_p, []),
     "wisp_abi_version": (_int, []),
@@ -42,10 +46,14 @@ SIGNATURES = {
     "wisp_func_generalized_correlation": (_int, [_c_ctx, _P, _int, _P, _dbl, _int, _P, _P]),
     "wisp_pipeline": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P, _int, _P, _int, _int, _dbl, _int,
                              _dbl, _int, _P, _P, _P, _P, _P, _P]),
+    "wisp_pipeline_log": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P, _int, _P, _int, _int, _dbl, _int,
+                                 _dbl, _int, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_int)]),
     "wisp_apsp": (_int, [_c_ctx, _P, _int, _int, _P, _P]),
     "wisp_get_paths": (_int, [_c_ctx, _P, _int, _P, _int, _P, _int, _int, _int]),
     "wisp_paths_prepare": (_int, [_c_ctx, _P, _int, _int]),
     "wisp_paths_query": (_int, [_c_ctx, _P, _int, _P, _int, _int, _int]),
+    "wisp_paths_query_pairs": (_int, [_c_ctx, _P, _int, _int, _int]),
+    "wisp_paths_query_offsets": (_int, [_c_ctx, C.POINTER(_i64), _P]),
     "wisp_paths_size": (_int, [_c_ctx, C.POINTER(_i64), C.POINTER(_i64)]),
     "wisp_paths_fetch": (_int, [_c_ctx, _P, _P, _P]),
     "wisp_paths_stats": (_int, [_c_ctx, _P]),
@@ -56,6 +64,9 @@ SIGNATURES = {
     "wisp_com_plan_destroy": (None, [_c_ctx, _P]),
     "wisp_com_plan_info": (_int, [_P, C.POINTER(_int), C.POINTER(_int)]),
     "wisp_dev_com": (_int, [_c_ctx, _P, _P, _i64, _int, _P, _P, _P]),
+    "wisp_dev_com_align": (_int, [_c_ctx, _P, _P, _i64, _int, _P, _P, _P, _P]),
+    "wisp_dev_align_sums": (_int, [_c_ctx, _P, _int, _P, _i64, _int, _int, _P, _P]),
+    "wisp_dev_align_rotate": (_int, [_c_ctx, _P, _int, _P, _P, _i64, _int, _P]),
     "wisp_dev_center": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P]),
     "wisp_dev_colsum": (_int, [_c_ctx, _P, _i64, _int, _P, _P]),
     "wisp_dev_gram": (_int, [_c_ctx, _P, _i64, _i64, _int, _int, _P, _P]),
@@ -116,15 +127,28 @@ def _arr(a, dtype, name, shape=None):
 
 
 class Context:
-    """One ``wisp_ctx`` (streams + scratch memory) on one B200."""
+    """One ``wisp_ctx`` (streams + scratch memory) on one B200 -- or, with ``gpus``, on several GPUs
+    of the box: ``gpus`` = a count (devices 0..gpus-1; 0 = every visible GPU) or an explicit device
+    list.  ``pipeline`` then shards the frames over them inside the one C call; every other method
+    runs on the first device."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, gpus=None):
         self._lib = lib()
         self._ctx = _c_ctx()
-        rc = self._lib.wisp_ctx_create(int(device), C.byref(self._ctx))
+        if gpus is None:
+            rc = self._lib.wisp_ctx_create(int(device), C.byref(self._ctx))
+            self.device = int(device)
+        else:
+            if isinstance(gpus, int):
+                n, devs = int(gpus), None
+            else:
+                devs = np.ascontiguousarray(list(gpus), dtype=np.int32)
+                n = len(devs)
+            rc = self._lib.wisp_ctx_create_multi(n, _ptr(devs), C.byref(self._ctx))
+            self.device = int(devs[0]) if devs is not None else 0
         if rc != 0:
             raise WispError(self._lib.wisp_last_error().decode())
-        self.device = int(device)
+        self.n_gpus = int(self._lib.wisp_ctx_gpus(self._ctx))
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -254,9 +278,10 @@ class Context:
 
     def pipeline(self, coords, masses, node_ptr, atom_idx, align_idx, cutoff=9999.0,
                  which_map=0, atomic=False, want_nodes=False, convergence_threshold=1e-5,
-                 maximum_num_iterations=0):
-        """coords -> dict(avg, corr, avgdist, binary, w[, nodes]) in one fused device pass
-        (K1, optional K7 alignment, K2, K3, K4)."""
+                 maximum_num_iterations=0, out=None):
+        """coords -> dict(avg, corr, avgdist, binary, w[, nodes], alignment_log) in one fused pass
+        (K1, optional K7 alignment, K2, K3, K4) on every GPU of this context.  ``out`` may supply
+        preallocated (e.g. page-locked) result arrays under the same keys."""
         coords = _arr(coords, np.float32, "coords")
         T, A, _ = coords.shape
         masses = _arr(masses, np.float64, "masses", (A,))
@@ -264,17 +289,29 @@ class Context:
         atom_idx = _arr(atom_idx, np.int32, "atom_idx")
         align_idx = _arr(align_idx, np.int32, "align_idx")
         N = len(node_ptr) - 1
-        out = dict(avg=np.empty((N, 3)), corr=np.empty((N, N)), avgdist=np.empty((N, N)),
-                   binary=np.empty((N, N), dtype=np.int64), w=np.empty((N, N)))
+        given = out or {}
+        out = {}
+        for key, shape, dt in (("avg", (N, 3), np.float64), ("corr", (N, N), np.float64),
+                               ("avgdist", (N, N), np.float64), ("binary", (N, N), np.int64),
+                               ("w", (N, N), np.float64)):
+            buf = given.get(key)
+            if buf is None:
+                buf = np.empty(shape, dtype=dt)
+            elif buf.shape != shape or buf.dtype != dt or not buf.flags.c_contiguous:
+                raise ValueError("pipeline: out[%r] must be a C-contiguous %s array of shape %s" % (key, dt.__name__, shape))
+            out[key] = buf
         nodes = np.empty((T, N, 3)) if want_nodes else None
-        self._check(self._lib.wisp_pipeline(
+        log = np.zeros((max(1, int(maximum_num_iterations)), 3), dtype=np.float64)
+        n_iter = _int(0)
+        self._check(self._lib.wisp_pipeline_log(
             self._ctx, _ptr(coords), T, A, _ptr(masses), _ptr(node_ptr), _ptr(atom_idx), N,
             _ptr(align_idx), len(align_idx), int(bool(atomic)), float(convergence_threshold),
             int(maximum_num_iterations), float(cutoff), int(which_map),
             _ptr(out["avg"]), _ptr(out["corr"]), _ptr(out["avgdist"]), _ptr(out["binary"]),
-            _ptr(out["w"]), _ptr(nodes)))
+            _ptr(out["w"]), _ptr(nodes), _ptr(log), C.byref(n_iter)))
         if want_nodes:
             out["nodes"] = nodes
+        out["alignment_log"] = [(int(r[0]), float(r[1]), float(r[2])) for r in log[:n_iter.value]]
         return out
 
     def apsp(self, w, precision=64, want_pred=True):
@@ -306,6 +343,26 @@ class Context:
         self._check(self._lib.wisp_paths_query(self._ctx, _ptr(so), len(so), _ptr(si), len(si),
                                                int(number_of_paths), 1 if node0_quirk else 0))
         return self._fetch_paths()
+
+    def paths_query_pairs(self, pairs, number_of_paths, node0_quirk=True, packed=False):
+        """``[get_paths(w, [s], [t], K) for (s, t) in pairs]`` on the prepared graph, all queries served
+        by the same kernel passes.  packed=True returns the raw arrays (query_offsets, lengths,
+        node_offsets, nodes) instead of Python lists."""
+        pr = _arr(pairs, np.int32, "pairs").reshape(-1, 2)
+        self._check(self._lib.wisp_paths_query_pairs(self._ctx, _ptr(pr), len(pr), int(number_of_paths),
+                                                     1 if node0_quirk else 0))
+        n_paths, n_nodes, nq = _i64(), _i64(), _i64()
+        self._check(self._lib.wisp_paths_size(self._ctx, C.byref(n_paths), C.byref(n_nodes)))
+        self._check(self._lib.wisp_paths_query_offsets(self._ctx, C.byref(nq), None))
+        qoff = np.empty(nq.value + 1, dtype=np.int64)
+        self._check(self._lib.wisp_paths_query_offsets(self._ctx, C.byref(nq), _ptr(qoff)))
+        lengths = np.empty(n_paths.value, dtype=np.float64)
+        offsets = np.empty(n_paths.value + 1, dtype=np.int64)
+        nodes = np.empty(n_nodes.value, dtype=np.int32)
+        self._check(self._lib.wisp_paths_fetch(self._ctx, _ptr(lengths), _ptr(offsets), _ptr(nodes)))
+        if packed:
+            return qoff, lengths, offsets, nodes
+        return unpack_paths(qoff, lengths, offsets, nodes)
 
     def _fetch_paths(self):
         n_paths, n_nodes = _i64(), _i64()
@@ -347,6 +404,18 @@ class Context:
     def dev_com(self, plan, d_coords, T, N, d_nodes, d_colsum=None, stream=None):
         self._check(self._lib.wisp_dev_com(self._ctx, plan, _ptr(d_coords), T, N, _ptr(d_nodes),
                                            _ptr(d_colsum), _ptr(stream)))
+
+    def dev_com_align(self, plan, d_coords, T, N, d_nodes, d_colsum=None, d_align_out=None, stream=None):
+        self._check(self._lib.wisp_dev_com_align(self._ctx, plan, _ptr(d_coords), T, N, _ptr(d_nodes),
+                                                 _ptr(d_colsum), _ptr(d_align_out), _ptr(stream)))
+
+    def dev_align_sums(self, d_align, n_align, d_nodes, T, N, first, d_sums, stream=None):
+        self._check(self._lib.wisp_dev_align_sums(self._ctx, _ptr(d_align), n_align, _ptr(d_nodes), T, N,
+                                                  int(bool(first)), _ptr(d_sums), _ptr(stream)))
+
+    def dev_align_rotate(self, d_align, n_align, d_avg_align, d_nodes, T, N, stream=None):
+        self._check(self._lib.wisp_dev_align_rotate(self._ctx, _ptr(d_align), n_align, _ptr(d_avg_align),
+                                                    _ptr(d_nodes), T, N, _ptr(stream)))
 
     def dev_center(self, d_nodes, T, N, d_mean, d_p32=None, stream=None):
         self._check(self._lib.wisp_dev_center(self._ctx, _ptr(d_nodes), T, N, _ptr(d_mean),
@@ -408,6 +477,15 @@ class Context:
                                                     float(noise_sigma), int(seed), _ptr(stream)))
 
 
+def unpack_paths(query_offsets, lengths, node_offsets, nodes):
+    """Packed path arrays -> list (per query) of lists of ``[length, n0, n1, ...]``."""
+    nl = nodes.tolist()
+    ll = lengths.tolist()
+    no = node_offsets.tolist()
+    return [[[ll[k]] + nl[no[k]:no[k + 1]] for k in range(int(query_offsets[q]), int(query_offsets[q + 1]))]
+            for q in range(len(query_offsets) - 1)]
+
+
 def savetxt(path, array, fmt='%.18e', header=''):
     """np.savetxt-compatible writer for the two formats the reference uses."""
     a = np.asarray(array)
@@ -447,11 +525,32 @@ def gram_ld(n_cols):
     return int(lib().wisp_gram_ld(int(n_cols)))
 
 
+def host_register(array):
+    """Page-lock a numpy array in place (cudaHostRegister, portable) so that the pipeline's H2D
+    copies run asynchronously at full PCIe rate from every GPU; pair with host_unregister."""
+    if lib().wisp_host_register(_ptr(array), array.nbytes) != 0:
+        raise WispError(lib().wisp_last_error().decode())
+
+
+def host_unregister(array):
+    if lib().wisp_host_unregister(_ptr(array)) != 0:
+        raise WispError(lib().wisp_last_error().decode())
+
+
 _default_ctx = {}
 
 
-def default_context(device=None):
-    """Process-wide context per device (device defaults to $LOCAL_RANK or 0)."""
+def default_context(device=None, gpus=None):
+    """Process-wide context: one per device (device defaults to $WISP_DEVICE, $LOCAL_RANK or 0), or
+    ONE over several GPUs when ``gpus`` (or $WISP_GPUS; 0 = every visible GPU) is given -- what the
+    config key ``gpus`` of wisp_w_mdanalysis.py selects."""
+    if gpus is None and device is None and os.environ.get("WISP_GPUS") is not None:
+        gpus = int(os.environ["WISP_GPUS"])
+    if gpus is not None and gpus != 1:
+        key = ("multi", gpus if isinstance(gpus, int) else tuple(gpus))
+        if key not in _default_ctx:
+            _default_ctx[key] = Context(gpus=gpus)
+        return _default_ctx[key]
     if device is None:
         device = int(os.environ.get("WISP_DEVICE", os.environ.get("LOCAL_RANK", "0")))
     if device not in _default_ctx:

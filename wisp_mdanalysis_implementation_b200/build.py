@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwisp_b200.so")
 SOURCES = ["capi.cu", "k1_com.cu", "k1_stream.cu", "k2_gram.cu", "k2_gram_i8.cu", "k3_contact.cu", "k4_epilogue.cu",
-           "k5_apsp.cu", "k6_paths.cu", "k7_align.cu", "k8_lmi.cu", "textio.cu"]
+           "k5_apsp.cu", "k6_paths.cu", "k7_align.cu", "k8_lmi.cu", "textio.cu", "pipeline.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 # tuning experiments: WISP_NVCC_DEFS="-DWISP_WS_FC=16 -DWISP_WS_STAGES=2" python -m ...build --force

@@ -51,6 +51,8 @@ extern "C" int wisp_ctx_create(int device, wisp_ctx** out) {
 
 extern "C" void wisp_ctx_destroy(wisp_ctx* ctx) {
     if (!ctx) return;
+    for (wisp_ctx* c : ctx->children) wisp_ctx_destroy(c);
+    ctx->children.clear();
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->pg && ctx->pg_free) ctx->pg_free(ctx->pg);
@@ -81,6 +83,7 @@ int wisp_gram_mode(wisp_ctx* ctx) {
 extern "C" int wisp_set_gram_mode(wisp_ctx* ctx, int mode) {
     WISP_CHECK(ctx && mode >= 0 && mode <= 2, "set_gram_mode: mode must be 0 (auto), 1 (dmma) or 2 (i8)");
     ctx->gram_mode = mode;
+    for (wisp_ctx* c : ctx->children) c->gram_mode = mode;
     return 0;
 }
 
@@ -171,6 +174,15 @@ int com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const do
                   const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
                   int n_align, int atomic, double** d_x_out, int64_t* ld_out,
                   float* d_align_out = nullptr) {
+    return wisp_com_from_host(ctx, coords, T, A, masses, node_ptr, atom_idx, N, align_idx, n_align, atomic,
+                              d_x_out, ld_out, d_align_out);
+}
+
+}  // namespace
+
+int wisp_com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
+                       const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
+                       int n_align, int atomic, double** d_x_out, int64_t* ld_out, float* d_align_out) {
     const int64_t ld = wisp_node_ld(N), Tpad = wisp_frames_pad(T);
     wisp_com_plan* plan = nullptr;
     WISP_TRY(com_plan_create(ctx, A, masses, node_ptr, atom_idx, N, align_idx, n_align, atomic, &plan));
@@ -179,39 +191,54 @@ int com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const do
     if (rc) { com_plan_destroy(ctx, plan); return rc; }
     double* d_x = (double*)px;
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
-    cudaMemsetAsync(d_x, 0, (size_t)Tpad * ld * 8, st);
     const size_t frame_bytes = (size_t)A * 12;
     int64_t chunk = std::max<int64_t>(1, ((size_t)128 << 20) / frame_bytes);
     chunk = std::min(chunk, T);
     void* bufs[2] = {nullptr, nullptr};
+    cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+    // every CUDA call is checked; the first failure is reported with its own message after the
+    // events and the plan have been released
+    cudaError_t err = cudaMemsetAsync(d_x, 0, (size_t)Tpad * ld * 8, st);
+    const char* what = "cudaMemsetAsync(node trajectory)";
     rc = wisp_scratch(ctx, SCR_COORDS0, (size_t)chunk * frame_bytes + 64, &bufs[0]);
     if (!rc) rc = wisp_scratch(ctx, SCR_COORDS1, (size_t)chunk * frame_bytes + 64, &bufs[1]);
-    if (rc) { com_plan_destroy(ctx, plan); return rc; }
-    cudaEvent_t copied[2], freed[2];
-    for (int b = 0; b < 2; ++b) {
-        cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming);
+    for (int b = 0; b < 2 && !rc && err == cudaSuccess; ++b) {
+        err = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming);
+        what = "cudaEventCreate";
     }
+    auto step = [&](cudaError_t e, const char* w) { if (err == cudaSuccess && e != cudaSuccess) { err = e; what = w; } };
     int it = 0;
-    for (int64_t t0 = 0; t0 < T && rc == 0; t0 += chunk, ++it) {
+    for (int64_t t0 = 0; t0 < T && rc == 0 && err == cudaSuccess; t0 += chunk, ++it) {
         const int b = it & 1;
         const int64_t nt = std::min(chunk, T - t0);
-        if (it >= 2) cudaStreamWaitEvent(cs, freed[b], 0);
-        cudaMemcpyAsync(bufs[b], coords + (size_t)t0 * A * 3, (size_t)nt * frame_bytes, cudaMemcpyHostToDevice, cs);
-        cudaEventRecord(copied[b], cs);
-        cudaStreamWaitEvent(st, copied[b], 0);
+        if (it >= 2) step(cudaStreamWaitEvent(cs, freed[b], 0), "cudaStreamWaitEvent(copy stream)");
+        step(cudaMemcpyAsync(bufs[b], coords + (size_t)t0 * A * 3, (size_t)nt * frame_bytes, cudaMemcpyHostToDevice, cs),
+             "cudaMemcpyAsync(coordinates H2D)");
+        step(cudaEventRecord(copied[b], cs), "cudaEventRecord(copied)");
+        step(cudaStreamWaitEvent(st, copied[b], 0), "cudaStreamWaitEvent(compute stream)");
+        if (err != cudaSuccess) break;
         rc = launch_com_plan(ctx, plan, (const float*)bufs[b], nt, d_x, ld, t0, st, d_align_out);
-        cudaEventRecord(freed[b], st);
+        step(cudaEventRecord(freed[b], st), "cudaEventRecord(freed)");
     }
-    cudaError_t e = cudaStreamSynchronize(st);
-    for (int b = 0; b < 2; ++b) { cudaEventDestroy(copied[b]); cudaEventDestroy(freed[b]); }
+    step(cudaStreamSynchronize(cs), "cudaStreamSynchronize(copy stream)");
+    step(cudaStreamSynchronize(st), "cudaStreamSynchronize(compute stream)");
+    for (int b = 0; b < 2; ++b) {
+        if (copied[b]) cudaEventDestroy(copied[b]);
+        if (freed[b]) cudaEventDestroy(freed[b]);
+    }
     com_plan_destroy(ctx, plan);
     if (rc) return rc;
-    WISP_CUDA(e);
+    if (err != cudaSuccess) {
+        wisp_set_error("com_from_host: %s failed: %s", what, cudaGetErrorString(err));
+        return 1;
+    }
     *d_x_out = d_x;
     *ld_out = ld;
     return 0;
 }
+
+namespace {
 
 int validate_node_map(int A, const int32_t* node_ptr, const int32_t* atom_idx, int N,
                       const int32_t* align_idx, int n_align) {
@@ -424,70 +451,26 @@ extern "C" int wisp_pipeline(wisp_ctx* ctx, const float* coords, int64_t T, int 
                              double cutoff, int which_map, double* out_avg,
                              double* out_corr, double* out_avgdist, int64_t* out_binary,
                              double* out_w, double* out_nodes) {
+    return wisp_pipeline_log(ctx, coords, T, A, masses, node_ptr, atom_idx, N, align_idx, n_align, atomic,
+                             align_threshold, max_align_iterations, cutoff, which_map, out_avg, out_corr,
+                             out_avgdist, out_binary, out_w, out_nodes, nullptr, nullptr);
+}
+
+extern "C" int wisp_pipeline_log(wisp_ctx* ctx, const float* coords, int64_t T, int A,
+                                 const double* masses, const int32_t* node_ptr,
+                                 const int32_t* atom_idx, int N, const int32_t* align_idx, int n_align,
+                                 int atomic, double align_threshold, int max_align_iterations,
+                                 double cutoff, int which_map, double* out_avg,
+                                 double* out_corr, double* out_avgdist, int64_t* out_binary,
+                                 double* out_w, double* out_nodes, double* out_log, int* out_n_iter) {
     WISP_CHECK(ctx && coords && masses, "pipeline: null argument");
     WISP_CHECK(max_align_iterations >= 0, "pipeline: negative alignment iteration limit");
     WISP_CHECK(T > 0 && A > 0 && N > 0 && n_align > 0, "pipeline: empty input");
     WISP_CHECK(which_map >= 0 && which_map <= 2, "pipeline: which_map must be 0, 1 or 2");
     WISP_TRY(validate_node_map(A, node_ptr, atom_idx, N, align_idx, n_align));
-    WISP_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    const int64_t ld = wisp_node_ld(N);
-    const int64_t n_pad = round_up(N, kTile);
-    const size_t nn = (size_t)N * N;
-    ArenaPlan plan;
-    plan.add((size_t)A * 8); plan.add((size_t)(N + 1) * 4); plan.add((size_t)node_ptr[N] * 4);
-    plan.add((size_t)n_align * 4);
-    plan.add((size_t)ld * 8); plan.add((size_t)ld * 8);
-    plan.add((size_t)n_pad * n_pad * 8); plan.add((size_t)n_pad * n_pad * 8);
-    plan.add(nn * 8); plan.add(nn * 8); plan.add(nn * 8); plan.add(nn * 8);
-    Arena ar;
-    WISP_TRY(arena_open(ctx, plan.bytes + 8192, &ar));
-    double* d_x;
-    int64_t ldx;
-    float* d_align = nullptr;
-    const int64_t na3 = 3 * (int64_t)n_align, nn3 = 3 * (int64_t)N;
-    if (max_align_iterations > 0) {
-        void* pa = nullptr;
-        WISP_TRY(wisp_scratch(ctx, SCR_ALIGN, (size_t)T * na3 * 4, &pa));
-        d_align = (float*)pa;
-    }
-    WISP_TRY(com_from_host(ctx, coords, T, A, masses, node_ptr, atom_idx, N, align_idx, n_align,
-                           atomic, &d_x, &ldx, d_align));
-    if (max_align_iterations > 0) {   // K7: iterative alignment on the device-resident trajectory
-        void* pw = nullptr;
-        WISP_TRY(wisp_scratch(ctx, SCR_MISC1, (size_t)(2 * round_up(na3, 32) + round_up(nn3, 32)) * 8, &pw));
-        int n_iter = 0;
-        WISP_TRY(run_iterative_alignment(ctx, d_align, n_align, d_x, ld, N, T, align_threshold,
-                                         max_align_iterations, (double*)pw, nullptr, nullptr, &n_iter, st));
-    }
-    double* d_sum = ar.take<double>(ld);
-    double* d_mean = ar.take<double>(ld);
-    double* d_gram = ar.take<double>((size_t)n_pad * n_pad);
-    double* d_dsum = ar.take<double>((size_t)n_pad * n_pad);
-    double* d_corr = ar.take<double>(nn);
-    double* d_avgdist = ar.take<double>(nn);
-    int64_t* d_binary = ar.take<int64_t>(nn);
-    double* d_w = ar.take<double>(nn);
-    WISP_CUDA(cudaMemsetAsync(d_mean, 0, (size_t)ld * 8, st));
-    WISP_TRY(launch_colsum(ctx, d_x, T, ld, 3 * (int64_t)N, d_sum, st));
-    WISP_TRY(dev_div(ctx, d_sum, (double)T, 3 * (int64_t)N, d_mean, st));
-    if (out_avg) WISP_CUDA(cudaMemcpyAsync(out_avg, d_mean, (size_t)3 * N * 8, cudaMemcpyDeviceToHost, st));
-    if (out_nodes)   // un-centred node trajectory, as traj_alignment_and_averaging returns it
-        WISP_CUDA(cudaMemcpy2DAsync(out_nodes, (size_t)3 * N * 8, d_x, (size_t)ld * 8, (size_t)3 * N * 8,
-                                    (size_t)T, cudaMemcpyDeviceToHost, st));
-    void* pp = nullptr;
-    WISP_TRY(wisp_scratch(ctx, SCR_P32, (size_t)T * n_pad * 12, &pp));
-    WISP_TRY(launch_center(ctx, d_x, T, ld, 3 * (int64_t)N, d_mean, st, (float*)pp, N));
-    WISP_TRY(launch_gram(ctx, d_x, T, ld, N, 3, d_gram, st));
-    WISP_TRY(launch_contact_sum(ctx, (const float*)pp, T, N, d_mean, d_dsum, st));
-    WISP_TRY(launch_epilogue(ctx, d_gram, d_dsum, T, N, cutoff, which_map, nullptr, nullptr, d_corr,
-                             d_avgdist, d_binary, d_w, st));
-    if (out_corr) WISP_CUDA(cudaMemcpyAsync(out_corr, d_corr, nn * 8, cudaMemcpyDeviceToHost, st));
-    if (out_avgdist) WISP_CUDA(cudaMemcpyAsync(out_avgdist, d_avgdist, nn * 8, cudaMemcpyDeviceToHost, st));
-    if (out_binary) WISP_CUDA(cudaMemcpyAsync(out_binary, d_binary, nn * 8, cudaMemcpyDeviceToHost, st));
-    if (out_w) WISP_CUDA(cudaMemcpyAsync(out_w, d_w, nn * 8, cudaMemcpyDeviceToHost, st));
-    WISP_CUDA(cudaStreamSynchronize(st));
-    return 0;
+    return wisp_pipeline_run(ctx, coords, T, A, masses, node_ptr, atom_idx, N, align_idx, n_align, atomic,
+                             align_threshold, max_align_iterations, cutoff, which_map, out_avg, out_corr,
+                             out_avgdist, out_binary, out_w, out_nodes, out_log, out_n_iter);
 }
 
 extern "C" int wisp_apsp(wisp_ctx* ctx, const double* w, int N, int precision, double* out_dist,
@@ -533,6 +516,27 @@ extern "C" int wisp_dev_com(wisp_ctx* ctx, wisp_com_plan* plan, const float* d_c
     cudaStream_t st = wisp_stream(ctx, stream);
     const int64_t ld = wisp_node_ld(N);
     return launch_com_plan(ctx, plan, d_coords, T, d_nodes, ld, 0, st, nullptr, d_colsum);
+}
+
+extern "C" int wisp_dev_com_align(wisp_ctx* ctx, wisp_com_plan* plan, const float* d_coords, int64_t T, int N,
+                                  double* d_nodes, double* d_colsum, float* d_align_out, void* stream) {
+    WISP_CHECK(ctx && plan && d_coords && d_nodes, "dev_com_align: null argument");
+    return launch_com_plan(ctx, plan, d_coords, T, d_nodes, wisp_node_ld(N), 0, wisp_stream(ctx, stream), d_align_out,
+                           d_colsum);
+}
+
+extern "C" int wisp_dev_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_nodes,
+                                   int64_t T, int N, int first, double* d_sums, void* stream) {
+    WISP_CHECK(ctx && d_align && d_nodes && d_sums && T > 0, "dev_align_sums: bad argument");
+    return launch_align_sums(ctx, d_align, n_align, d_nodes, wisp_node_ld(N), N, T, first != 0, d_sums,
+                             wisp_stream(ctx, stream));
+}
+
+extern "C" int wisp_dev_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align,
+                                     double* d_nodes, int64_t T, int N, void* stream) {
+    WISP_CHECK(ctx && d_align && d_avg_align && d_nodes && T > 0, "dev_align_rotate: bad argument");
+    return launch_align_rotate(ctx, d_align, n_align, d_avg_align, d_nodes, wisp_node_ld(N), N, T,
+                               wisp_stream(ctx, stream));
 }
 
 extern "C" int wisp_dev_center(wisp_ctx* ctx, double* d_nodes, int64_t T, int N, const double* d_mean,

@@ -7,6 +7,7 @@
 #include <string.h>
 #include <vector>
 #include <string>
+#include <functional>
 
 #include "../../include/wisp_b200.h"
 
@@ -64,6 +65,11 @@ struct wisp_ctx {
     cudaStream_t aux_stream = nullptr;   // high-priority side stream (K5 look-ahead), created on first use
     cudaEvent_t aux_events[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t launches = 0;
+    // multi-GPU (wisp_ctx_create_multi): this context is shard 0; one child context per further GPU
+    std::vector<wisp_ctx*> children;
+    std::vector<int> peer_devices;           // device id of every shard, in shard order
+    std::vector<int> peer_ok;                // [R][R] peer access enabled from shard p to shard q
+    int64_t launches_reported = 0;           // (children) launches already added to the root's counter
     int gram_mode = -1;              // WISP_GRAM_*; -1 = read $WISP_K2_MODE on first use
     // column statistics left by the last centring pass (launch_center) for the INT8 K2 engine:
     // valid for ONE following launch_gram on the same block and stream
@@ -72,11 +78,12 @@ struct wisp_ctx {
     int i8_stats_parts = 0;
     cudaStream_t i8_stats_stream = nullptr;
     // grow-only scratch buffers, keyed by slot
-    DevBuf scratch[40];
+    DevBuf scratch[64];
     // get_paths results
     std::vector<double> path_len;
     std::vector<int64_t> path_off;
     std::vector<int32_t> path_nodes;
+    std::vector<int64_t> path_query_off;    // wisp_paths_query_pairs: first path of every query (+ end)
     double path_stats[6] = {0, 0, 0, 0, 0, 0};
     PathGraphState* pg = nullptr;            // graph + APSP state of wisp_paths_prepare
     void (*pg_free)(PathGraphState*) = nullptr;
@@ -91,7 +98,8 @@ enum ScratchSlot {
     SCR_GRAM_PART = 0, SCR_CONTACT_PART, SCR_COLSUM_PART, SCR_X, SCR_COORDS0, SCR_COORDS1,
     SCR_APSP_D, SCR_APSP_P, SCR_ARENA, SCR_ALIGN, SCR_P32,
     SCR_MISC0, SCR_MISC1, SCR_MISC2, SCR_MISC3, SCR_MISC4, SCR_MISC5, SCR_MISC6, SCR_MISC7,
-    SCR_MISC8, SCR_MISC9, SCR_I8_PLANES, SCR_I8_SMALL, SCR_I8_PART, SCR_I8_STATS, SCR_APSP_R, SCR_APSP_T, SCR_APSP_M, SCR_COUNT
+    SCR_MISC8, SCR_MISC9, SCR_I8_PLANES, SCR_I8_SMALL, SCR_I8_PART, SCR_I8_STATS, SCR_APSP_R, SCR_APSP_T, SCR_APSP_M,
+    SCR_PIPE_G, SCR_PIPE_D, SCR_PIPE_OUT, SCR_PIPE_STAGE0, SCR_PIPE_STAGE_LAST = SCR_PIPE_STAGE0 + 15, SCR_COUNT
 };
 
 // ---- kernel launchers (one per .cu) -------------------------------------------------------
@@ -115,9 +123,16 @@ int launch_colsum_finish(wisp_ctx* ctx, const double* d_part, int n_rows, int64_
                          double* d_colsum, cudaStream_t st);
 int launch_colsum_f32(wisp_ctx* ctx, const float* d_x, int64_t T, int64_t ld, int64_t ncols,
                       double* d_colsum, cudaStream_t st);
+// sums a host vector over the frame shards (in shard order; float32-chained when f32_chain)
+typedef std::function<int(double* buf, size_t n, bool f32_chain)> AlignReduce;
 int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* d_nodes, int64_t ld,
                             int N, int64_t T, double threshold, int max_iter, double* d_work,
-                            double* h_avg_nodes, double* log, int* n_iter_out, cudaStream_t st);
+                            double* h_avg_nodes, double* log, int* n_iter_out, cudaStream_t st,
+                            int64_t T_total = 0, const AlignReduce& reduce = AlignReduce());
+int launch_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_nodes, int64_t ld,
+                      int N, int64_t T, bool first, double* d_sums, cudaStream_t st);
+int launch_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align, double* d_nodes,
+                        int64_t ld, int N, int64_t T, cudaStream_t st);
 int launch_colsum(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int64_t ncols,
                   double* d_colsum, cudaStream_t st);
 // d_p32 != nullptr: also write the FP32 tile-referenced copy [T][n_tiles][3][128] for K3
@@ -144,6 +159,26 @@ int launch_epilogue(wisp_ctx* ctx, const double* d_gram, const double* d_dsum, i
                     int N, double cutoff, int which_map, double* d_var, double* d_ncov,
                     double* d_corr, double* d_avgdist, int64_t* d_binary, double* d_w,
                     cudaStream_t st, const double* d_offs = nullptr);
+// cross-GPU reduction fused into the epilogue: entry (i, j) of the Gram / distance sums is the sum,
+// in shard order, of the R partial matrices addressed by `ps` (own HBM or peers' HBM over NVLink)
+constexpr int kMaxPeers = 8;
+struct PeerSums {
+    const double* gram[kMaxPeers];
+    const double* dsum[kMaxPeers];
+    int n;
+};
+// rows [row0, row1) of the dense outputs, each [row1 - row0][N]; d_diag [N] scratch
+int launch_epilogue_peers(wisp_ctx* ctx, const PeerSums& ps, int64_t T_total, int N, int row0, int row1,
+                          double cutoff, int which_map, double* d_diag, double* d_corr, double* d_avgdist,
+                          int64_t* d_binary, double* d_w, cudaStream_t st);
+int wisp_com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
+                       const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
+                       int n_align, int atomic, double** d_x_out, int64_t* ld_out, float* d_align_out);
+int wisp_pipeline_run(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
+                      const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
+                      int n_align, int atomic, double align_threshold, int max_align_iterations,
+                      double cutoff, int which_map, double* out_avg, double* out_corr, double* out_avgdist,
+                      int64_t* out_binary, double* out_w, double* out_nodes, double* out_log, int* out_n_iter);
 int launch_cov_finalize(wisp_ctx* ctx, const double* d_p, int64_t ldp, int n3, int64_t T,
                         const double* d_avg, const double* d_delta, double* d_cov,
                         cudaStream_t st);

@@ -69,6 +69,43 @@ __global__ void epilogue_kernel(const double* __restrict__ gram, const double* _
     }
 }
 
+// ---- cross-GPU reduction fused into the epilogue (pipeline.cu, stage S4) ----
+__device__ __forceinline__ double peer_sum(const double* const* part, int n, int64_t idx) {
+    double s = part[0][idx];
+    for (int q = 1; q < n; ++q) s += part[q][idx];       // fixed shard order: deterministic
+    return s;
+}
+
+__global__ void diag_peers_kernel(PeerSums ps, int64_t n_pad, int64_t T, int N, double* __restrict__ diag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) diag[i] = peer_sum(ps.gram, ps.n, (int64_t)i * n_pad + i) / (double)T;
+}
+
+__global__ void epilogue_peers_kernel(PeerSums ps, const double* __restrict__ diag, int64_t n_pad, int64_t T, int N,
+                                      int row0, int row1, double cutoff, int which_map,
+                                      double* __restrict__ corr, double* __restrict__ avgdist,
+                                      int64_t* __restrict__ binary, double* __restrict__ w) {
+    const int64_t total = (int64_t)(row1 - row0) * N;
+    const double Td = (double)T;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int r = row0 + (int)(e / N), c = (int)(e % N);
+        const int i = r < c ? r : c, j = r < c ? c : r;
+        const int64_t idx = (int64_t)i * n_pad + j;
+        const double g = peer_sum(ps.gram, ps.n, idx) / Td;
+        const double cij = g / sqrt(diag[i] * diag[j]);
+        const double d = peer_sum(ps.dsum, ps.n, idx) / Td;
+        const int64_t b = (r != c && d < cutoff) ? 1 : 0;
+        corr[e] = cij;
+        avgdist[e] = d;
+        binary[e] = b;
+        double v = -log(fabs(cij));
+        if (which_map == 1) v *= (double)b;
+        else if (which_map == 2) v *= d;
+        w[e] = v;
+    }
+}
+
 __global__ void cov_finalize_kernel(const double* __restrict__ p, int64_t ldp, int n3, int64_t T,
                                     const double* __restrict__ avg, const double* __restrict__ delta,
                                     double* __restrict__ cov) {
@@ -131,6 +168,19 @@ int launch_epilogue(wisp_ctx* ctx, const double* d_gram, const double* d_dsum, i
         d_gram, d_dsum, d_offs, n_pad, T_total, N, cutoff, which_map, d_var, d_ncov, d_corr, d_avgdist,
         d_binary, d_w);
     ctx->launches++;
+    WISP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_epilogue_peers(wisp_ctx* ctx, const PeerSums& ps, int64_t T_total, int N, int row0, int row1,
+                          double cutoff, int which_map, double* d_diag, double* d_corr, double* d_avgdist,
+                          int64_t* d_binary, double* d_w, cudaStream_t st) {
+    WISP_CHECK(N > 0 && T_total > 0 && ps.n >= 1 && ps.n <= kMaxPeers && row1 > row0, "epilogue_peers: bad argument");
+    const int64_t n_pad = round_up(N, kTile);
+    diag_peers_kernel<<<(N + 127) / 128, 128, 0, st>>>(ps, n_pad, T_total, N, d_diag);
+    epilogue_peers_kernel<<<grid_for(ctx, (int64_t)(row1 - row0) * N), 256, 0, st>>>(
+        ps, d_diag, n_pad, T_total, N, row0, row1, cutoff, which_map, d_corr, d_avgdist, d_binary, d_w);
+    ctx->launches += 2;
     WISP_CUDA(cudaGetLastError());
     return 0;
 }

@@ -144,10 +144,28 @@ fw_p2_kernel(T* __restrict__ local, int64_t ld, T* __restrict__ panel, int64_t l
     extern __shared__ __align__(16) unsigned char fw_smem[];
     T* M = reinterpret_cast<T*>(fw_smem);          // [B][LDM]
     const T* piv = panel + (int64_t)kb * B;
-    for (int e = threadIdx.x; e < B * B; e += 128) {
-        const int r = e / B, c = e % B;
-        const T v = piv[(int64_t)r * ldp + c];
-        if (is_row) M[c * LDM + r] = v; else M[r * LDM + c] = v;
+    {   // pivot tile -> shared memory with 16-byte loads, a batch of a thread's loads in flight at once
+        constexpr int V = 16 / sizeof(T), PER = B * B / V / 128, BATCH = 16;
+#pragma unroll 1
+        for (int u0 = 0; u0 < PER; u0 += BATCH) {
+            int4 buf[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const int e = (threadIdx.x + 128 * (u0 + u)) * V, r = e / B, c = e % B;
+                buf[u] = *reinterpret_cast<const int4*>(piv + (int64_t)r * ldp + c);
+            }
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const int e = (threadIdx.x + 128 * (u0 + u)) * V, r = e / B, c = e % B;
+                if (is_row) {
+                    const T* vals = reinterpret_cast<const T*>(&buf[u]);
+#pragma unroll
+                    for (int w = 0; w < V; ++w) M[(c + w) * LDM + r] = vals[w];
+                } else {
+                    *reinterpret_cast<int4*>(M + r * LDM + c) = buf[u];
+                }
+            }
+        }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = lane >> 3, vv = lane & 7;

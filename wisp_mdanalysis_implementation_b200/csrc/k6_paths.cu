@@ -36,14 +36,19 @@ struct EnumParams {
     const double* adj_w;
     const double* dist;      // APSP distances [N][N] (row t = distances to sink t)
     const int32_t* pairs;    // [P][2]
+    // A pass serves one or more QUERY GROUPS at once: the pairs of one get_paths call form one group
+    // (one cutoff, one shared count); the batched API (wisp_paths_query_pairs) puts every independent
+    // (source, sink) query in its own group, each at its own point of its own cutoff ratchet.
+    const int32_t* pair_group;   // [P] group of every pair
+    const double* g_cutoff;      // [G] LR-length cutoff of the pass
+    const double* g_bound;       // [G] admissible pruning bound (cutoff + slack)
+    const int32_t* g_count_only; // [G] 1: count paths, do not store them
+    const int32_t* g_cap;        // [G] count-only early exit: stop once more than cap paths were seen
+    int32_t* g_count;            // [G] paths found per group (both modes)
     int N;
-    double cutoff;
-    double bound;
     int quirk;
-    int count_only;          // 1: count paths, do not store them
-    int cap;                 // count-only early exit: stop once more than cap paths were seen
     // outputs
-    int32_t* out_count;      // [0] n paths, [1] n node entries, [2] overflow flags
+    int32_t* out_count;      // [0] stored paths, [1] n node entries, [2] overflow flags
     unsigned long long* expansions;
     double* out_len;
     int32_t* out_pair;
@@ -56,8 +61,10 @@ struct EnumParams {
 
 __device__ __forceinline__ void emit_path(const EnumParams& P, int pair, const int32_t* nodes,
                                           int depth, int last, double len) {
+    const int g = P.pair_group[pair];
+    atomicAdd(&P.g_count[g], 1);
+    if (P.g_count_only[g]) return;
     const int slot = atomicAdd(&P.out_count[0], 1);
-    if (P.count_only) return;
     const int off = atomicAdd(&P.out_count[1], depth + 1);
     if (slot >= P.cap_paths || off + depth + 1 > P.cap_nodes) {
         atomicOr(&P.out_count[2], 1);
@@ -82,6 +89,8 @@ __global__ void expand_level_kernel(EnumParams P, const double* __restrict__ fin
     if (rec >= n_in) return;
     const int pair = fin_meta[2 * rec], depth = fin_meta[2 * rec + 1];
     const int s = P.pairs[2 * pair], t = P.pairs[2 * pair + 1];
+    const int grp = P.pair_group[pair];
+    const double cutoff = P.g_cutoff[grp], bound = P.g_bound[grp];
     const int32_t* nodes = fin_nodes + (size_t)rec * kMaxLen;
     const double len = fin_len[rec];
     const int u = nodes[depth - 1];
@@ -95,12 +104,12 @@ __global__ void expand_level_kernel(EnumParams P, const double* __restrict__ fin
         if (P.quirk && depth == 1 && v == 0 && s != 0) continue;
         const double nl = len + P.adj_w[e];
         ++nexp;
-        if (!(nl + dt[v] <= P.bound)) continue;
+        if (!(nl + dt[v] <= bound)) continue;
         if (v == t) {
-            if (nl <= P.cutoff) emit_path(P, pair, nodes, depth, v, nl);
+            if (nl <= cutoff) emit_path(P, pair, nodes, depth, v, nl);
             continue;
         }
-        if (nl > P.cutoff) continue;
+        if (nl > cutoff) continue;
         if (depth + 1 >= kMaxLen) { atomicOr(&P.out_count[2], 2); continue; }
         const int slot = atomicAdd(fout_count, 1);
         if (slot >= cap_out) { atomicOr(&P.out_count[2], 4); continue; }
@@ -139,6 +148,9 @@ dfs_warp_kernel(EnumParams P, const double* __restrict__ f_len, const int32_t* _
     const unsigned FULL = 0xffffffffu;
     const int pair = f_meta[2 * rec], d0 = f_meta[2 * rec + 1];
     const int s = P.pairs[2 * pair], t = P.pairs[2 * pair + 1];
+    const int grp = P.pair_group[pair];
+    const double cutoff = P.g_cutoff[grp], bound = P.g_bound[grp];
+    const int count_only = P.g_count_only[grp], cap = P.g_cap[grp];
     const double* dt = P.dist + (size_t)t * P.N;
     int32_t* path = spath[wib];
     for (int k = lane; k < d0; k += 32) path[k] = f_nodes[(size_t)rec * kMaxLen + k];
@@ -150,11 +162,11 @@ dfs_warp_kernel(EnumParams P, const double* __restrict__ f_len, const int32_t* _
     unsigned long long nexp = 0;
     unsigned it = 0;
     while (sp > 0) {
-        if (P.count_only && (++it & 15u) == 0) {
+        if (count_only && (++it & 15u) == 0) {
             int c = 0;
-            if (lane == 0) c = *reinterpret_cast<volatile int32_t*>(P.out_count);
+            if (lane == 0) c = *reinterpret_cast<volatile int32_t*>(P.g_count + grp);
             c = __shfl_sync(FULL, c, 0);
-            if (c > P.cap) break;
+            if (c > cap) break;
         }
         --sp;
         const StackEntry top = stack[sp];          // same address for all lanes: broadcast
@@ -176,21 +188,24 @@ dfs_warp_kernel(EnumParams P, const double* __restrict__ f_len, const int32_t* _
             }
             if (ok && P.quirk && depth == 1 && v == 0 && s != 0) ok = false;
             nexp += ok ? 1 : 0;
-            if (ok) ok = (nl + dt[v] <= P.bound);
-            const bool hit = ok && v == t && nl <= P.cutoff;
-            const bool cont = ok && v != t && nl <= P.cutoff;
+            if (ok) ok = (nl + dt[v] <= bound);
+            const bool hit = ok && v == t && nl <= cutoff;
+            const bool cont = ok && v != t && nl <= cutoff;
             // ---- sink hits ----
             const unsigned hmask = __ballot_sync(FULL, hit);
             if (hmask) {
                 const int nh = __popc(hmask);
                 int slot0 = 0, off0 = 0;
                 if (lane == 0) {
-                    slot0 = atomicAdd(&P.out_count[0], nh);
-                    if (!P.count_only) off0 = atomicAdd(&P.out_count[1], nh * (depth + 1));
+                    atomicAdd(&P.g_count[grp], nh);
+                    if (!count_only) {
+                        slot0 = atomicAdd(&P.out_count[0], nh);
+                        off0 = atomicAdd(&P.out_count[1], nh * (depth + 1));
+                    }
                 }
                 slot0 = __shfl_sync(FULL, slot0, 0);
                 off0 = __shfl_sync(FULL, off0, 0);
-                if (hit && !P.count_only) {
+                if (hit && !count_only) {
                     const int r = __popc(hmask & ((1u << lane) - 1));
                     const int slot = slot0 + r, off = off0 + r * (depth + 1);
                     if (slot >= P.cap_paths || off + depth + 1 > P.cap_nodes) {
@@ -344,100 +359,76 @@ extern "C" int wisp_get_paths(wisp_ctx* ctx, const double* w, int N, const int32
     return wisp_paths_query(ctx, sources, n_sources, sinks, n_sinks, number_of_paths, flags);
 }
 
-extern "C" int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sources,
-                                const int32_t* sinks, int n_sinks, int number_of_paths, int flags) {
-    WISP_CHECK(ctx && ctx->pg, "paths_query: call wisp_paths_prepare first");
-    WISP_CHECK(sources && sinks && n_sources > 0 && n_sinks > 0, "get_paths: empty source or sink list");
-    WISP_CHECK(number_of_paths >= 1, "get_paths: number_of_paths must be >= 1");
-    WISP_CUDA(cudaSetDevice(ctx->device));
-    PathGraphState* g = ctx->pg;
-    const int N = g->N;
-    const double* w = g->w.data();
-    const int quirk = (flags & 1) ? 1 : 0;
-    cudaStream_t st = ctx->stream;
-    for (int i = 0; i < n_sources; ++i) WISP_CHECK(sources[i] >= 0 && sources[i] < N, "get_paths: source %d out of range", sources[i]);
-    for (int i = 0; i < n_sinks; ++i) WISP_CHECK(sinks[i] >= 0 && sinks[i] < N, "get_paths: sink %d out of range", sinks[i]);
-    void *d_dist = g->d_dist, *d_pred = g->d_pred, *d_adj_ptr = g->d_adj_ptr, *d_adj_idx = g->d_adj_idx,
-         *d_adj_w = g->d_adj_w;
-    const double max_simple_len = g->max_simple_len;
-    const double apsp_ms = g->apsp_ms;
+// ---------------------------------------------------------------------------------------
+// Enumeration engine: one PASS answers, for every query group, "all simple paths of the group's pairs
+// with LR length <= the group's cutoff" -- counted (with early exit beyond the group's cap) or stored.
+// All groups of a pass share the level expansion and ONE dfs launch, so a batch of independent
+// queries (configs[4]: 200 pairs) keeps the whole GPU busy instead of 2 % of it per query.
+// ---------------------------------------------------------------------------------------
+namespace {
 
-    // ---- pairs in the reference's loop order (:27-29), seed path (:25-36) ----
-    std::vector<int32_t> pairs;
-    for (int a = 0; a < n_sources; ++a)
-        for (int b = 0; b < n_sinks; ++b)
-            if (sources[a] != sinks[b]) { pairs.push_back(sources[a]); pairs.push_back(sinks[b]); }
-    const int n_pairs = (int)pairs.size() / 2;
-    WISP_CHECK(n_pairs > 0, "get_paths: no (source, sink) pair with source != sink");
+struct GroupRequest {
+    double cutoff = 0.0;
+    bool count_only = true;
+    int cap = 0;
+};
 
-    double shortest_length = 99999999.999;
-    std::vector<int32_t> shortest_path;
-    std::vector<int32_t> pred_row(N);
-    std::vector<double> dist_row(N);
-    int last_row = -1;
-    for (int p = 0; p < n_pairs; ++p) {
-        const int s = pairs[2 * p], t = pairs[2 * p + 1];
-        if (s != last_row) {
-            WISP_CUDA(cudaMemcpy(pred_row.data(), (int32_t*)d_pred + (size_t)s * N, (size_t)N * 4, cudaMemcpyDeviceToHost));
-            WISP_CUDA(cudaMemcpy(dist_row.data(), (double*)d_dist + (size_t)s * N, (size_t)N * 8, cudaMemcpyDeviceToHost));
-            last_row = s;
-        }
-        WISP_CHECK(dist_row[t] < 1e300 && pred_row[t] >= 0, "get_paths: no path between node %d and node %d", s, t);
-        std::vector<int32_t> sp;
-        sp.push_back(t);
-        while (sp.back() != s) {
-            const int pr = pred_row[sp.back()];
-            WISP_CHECK(pr >= 0 && (int)sp.size() <= N, "get_paths: broken predecessor chain %d -> %d", s, t);
-            sp.push_back(pr);
-        }
-        std::reverse(sp.begin(), sp.end());
-        double length = 0.0;
-        for (size_t k = 0; k + 1 < sp.size(); ++k) length += w[(size_t)sp[k] * N + sp[k + 1]];
-        if (length < shortest_length) { shortest_length = length; shortest_path = sp; }
-    }
-
-    std::vector<HostPath> paths;
-    paths.push_back(HostPath{shortest_length, shortest_path});
-    int64_t num_paths = 1;
-    double cutoff = shortest_length;
-
-    // ---- device buffers for the enumeration ----
-    void *d_pairs, *d_cnt;
-    WISP_TRY(wisp_scratch(ctx, SCR_MISC7, (size_t)n_pairs * 8 + 256, &d_pairs));
-    d_cnt = (char*)d_pairs + round_up((size_t)n_pairs * 8, 64);     // counters + frontier counts
-    WISP_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
-
-    int cap_paths = std::max(4096, 8 * number_of_paths * std::max(1, n_pairs));
-    int cap_front = std::max(16 * kTargetPrefixes, 4 * n_pairs);
-    int cap_stack = 1024;
+struct EnumEngine {
+    wisp_ctx* ctx;
+    PathGraphState* g;
+    int quirk;
+    int cap_paths = 4096, cap_front = 16 * kTargetPrefixes, cap_stack = 1024, target_prefixes = kTargetPrefixes;
     double enum_ms = 0.0, host_ms = 0.0;
     unsigned long long expansions_total = 0;
-    int passes = 0;
 
-    // One enumeration pass on the device.  count_only: only the number of paths <= cutoff is
-    // returned (early exit once it exceeds `cap`); otherwise the paths come back per pair,
-    // each pair's list sorted by (length, nodes) (:145) and concatenated in pair order.
-    auto run_pass = [&](double pass_cutoff, bool count_only, int cap, int64_t* count_out,
-                        std::vector<HostPath>* out_paths) -> int {
+    // pairs [P][2], pair_group [P], req [G].  counts [G] out; paths_per_pair [P] out (fetch groups only),
+    // every pair's list sorted by (length, nodes) (:145).
+    int pass(const std::vector<int32_t>& pairs, const std::vector<int32_t>& pair_group,
+             const std::vector<GroupRequest>& req, std::vector<int64_t>* counts,
+             std::vector<std::vector<HostPath>>* paths_per_pair) {
+        const int n_pairs = (int)pair_group.size(), n_groups = (int)req.size();
+        const int N = g->N;
+        cudaStream_t st = ctx->stream;
+        bool any_fetch = false;
+        for (const auto& r : req) any_fetch |= !r.count_only;
         for (;;) {   // retry loop on capacity overflow
             double te = now_ms();
             const int cap_nodes = cap_paths * 24;
-            void *d_out, *d_front;
+            void *d_out, *d_front, *d_small;
             const size_t out_bytes = (size_t)cap_paths * (8 + 4 + 4 + 4) + (size_t)cap_nodes * 4 + 256;
             WISP_TRY(wisp_scratch(ctx, SCR_MISC8, out_bytes, &d_out));
             const size_t front_rec = 8 + 8 + (size_t)kMaxLen * 4;
             WISP_TRY(wisp_scratch(ctx, SCR_MISC9, 2 * (size_t)cap_front * front_rec + 256, &d_front));
+            // small per-pass arrays in one block: pairs, pair_group, group params, counters
+            const size_t o_pairs = 0, o_pg = round_up((int64_t)n_pairs * 8, 64), o_cut = o_pg + round_up((int64_t)n_pairs * 4, 64),
+                         o_bnd = o_cut + round_up((int64_t)n_groups * 8, 64), o_co = o_bnd + round_up((int64_t)n_groups * 8, 64),
+                         o_cap = o_co + round_up((int64_t)n_groups * 4, 64), o_gc = o_cap + round_up((int64_t)n_groups * 4, 64),
+                         o_cnt = o_gc + round_up((int64_t)n_groups * 4, 64), small_bytes = o_cnt + 128;
+            WISP_TRY(wisp_scratch(ctx, SCR_MISC7, small_bytes, &d_small));
+            std::vector<char> h_small(small_bytes, 0);
+            memcpy(h_small.data() + o_pairs, pairs.data(), (size_t)n_pairs * 8);
+            memcpy(h_small.data() + o_pg, pair_group.data(), (size_t)n_pairs * 4);
+            for (int q = 0; q < n_groups; ++q) {
+                const double c = req[q].cutoff;
+                // admissible bound: APSP distances are only bounds (summation order / FP32 mode), so leave
+                // slack; the exact float64 left-to-right length decides membership
+                const double bnd = c + (g->precision == 32 ? 2e-5 : 1e-9) * std::max(1.0, std::fabs(c));
+                ((double*)(h_small.data() + o_cut))[q] = c;
+                ((double*)(h_small.data() + o_bnd))[q] = bnd;
+                ((int32_t*)(h_small.data() + o_co))[q] = req[q].count_only ? 1 : 0;
+                ((int32_t*)(h_small.data() + o_cap))[q] = req[q].cap;
+            }
+            WISP_CUDA(cudaMemcpyAsync(d_small, h_small.data(), small_bytes, cudaMemcpyHostToDevice, st));
+            char* ds = (char*)d_small;
             EnumParams P;
-            P.adj_ptr = (const int32_t*)d_adj_ptr; P.adj_idx = (const int32_t*)d_adj_idx;
-            P.adj_w = (const double*)d_adj_w; P.dist = (const double*)d_dist;
-            P.pairs = (const int32_t*)d_pairs; P.N = N; P.cutoff = pass_cutoff;
-            // admissible bound: APSP distances are only bounds (summation order / FP32 mode), so
-            // leave slack; the exact float64 left-to-right length decides membership
-            P.bound = pass_cutoff + (g->precision == 32 ? 2e-5 : 1e-9) * std::max(1.0, std::fabs(pass_cutoff));
-            P.quirk = quirk;
-            P.count_only = count_only ? 1 : 0;
-            P.cap = cap;
-            int32_t* cnt = (int32_t*)d_cnt;                  // [0..2] out counters, [4] frontier count
+            P.adj_ptr = (const int32_t*)g->d_adj_ptr; P.adj_idx = (const int32_t*)g->d_adj_idx;
+            P.adj_w = (const double*)g->d_adj_w; P.dist = (const double*)g->d_dist;
+            P.pairs = (const int32_t*)(ds + o_pairs); P.pair_group = (const int32_t*)(ds + o_pg);
+            P.g_cutoff = (const double*)(ds + o_cut); P.g_bound = (const double*)(ds + o_bnd);
+            P.g_count_only = (const int32_t*)(ds + o_co); P.g_cap = (const int32_t*)(ds + o_cap);
+            P.g_count = (int32_t*)(ds + o_gc);
+            P.N = N; P.quirk = quirk;
+            int32_t* cnt = (int32_t*)(ds + o_cnt);           // [0..2] out counters, [4] frontier count, [8..9] expansions
             P.out_count = cnt;
             P.expansions = (unsigned long long*)(cnt + 8);
             P.out_len = (double*)d_out;
@@ -446,27 +437,27 @@ extern "C" int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sou
             P.out_n = P.out_off + cap_paths;
             P.out_nodes = P.out_n + cap_paths;
             P.cap_paths = cap_paths; P.cap_nodes = cap_nodes;
-            WISP_CUDA(cudaMemsetAsync(d_cnt, 0, 64, st));
             char* fb = (char*)d_front;
             double* f_len[2]; int32_t* f_meta[2]; int32_t* f_nodes[2];
-            for (int b = 0; b < 2; ++b) {
-                f_len[b] = (double*)fb; fb += (size_t)cap_front * 8;
-                f_meta[b] = (int32_t*)fb; fb += (size_t)cap_front * 8;
-                f_nodes[b] = (int32_t*)fb; fb += (size_t)cap_front * kMaxLen * 4;
+            for (int bq = 0; bq < 2; ++bq) {
+                f_len[bq] = (double*)fb; fb += (size_t)cap_front * 8;
+                f_meta[bq] = (int32_t*)fb; fb += (size_t)cap_front * 8;
+                f_nodes[bq] = (int32_t*)fb; fb += (size_t)cap_front * kMaxLen * 4;
             }
+            if (n_pairs > cap_front) { cap_front = 2 * n_pairs; continue; }
             {   // seed frontier: one record [s] per pair
                 std::vector<double> hl(n_pairs, 0.0);
-                std::vector<int32_t> hm(2 * n_pairs), hn((size_t)n_pairs * kMaxLen, 0);
+                std::vector<int32_t> hm(2 * (size_t)n_pairs), hn((size_t)n_pairs * kMaxLen, 0);
                 for (int p = 0; p < n_pairs; ++p) { hm[2 * p] = p; hm[2 * p + 1] = 1; hn[(size_t)p * kMaxLen] = pairs[2 * p]; }
                 WISP_CUDA(cudaMemcpyAsync(f_len[0], hl.data(), (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
                 WISP_CUDA(cudaMemcpyAsync(f_meta[0], hm.data(), (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
                 WISP_CUDA(cudaMemcpyAsync(f_nodes[0], hn.data(), (size_t)n_pairs * kMaxLen * 4, cudaMemcpyHostToDevice, st));
-                WISP_CUDA(cudaStreamSynchronize(st));
+                WISP_CUDA(cudaStreamSynchronize(st));     // the host vectors above and h_small go out of use
             }
             int n_front = n_pairs, cur = 0;
             bool overflow = false;
             int32_t hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (int level = 0; level < kMaxExpandLevels && n_front > 0 && n_front < kTargetPrefixes; ++level) {
+            for (int level = 0; level < kMaxExpandLevels && n_front > 0 && n_front < target_prefixes; ++level) {
                 WISP_CUDA(cudaMemsetAsync(cnt + 4, 0, 4, st));
                 expand_level_kernel<<<(n_front + 127) / 128, 128, 0, st>>>(
                     P, f_len[cur], f_meta[cur], f_nodes[cur], n_front, f_len[cur ^ 1], f_meta[cur ^ 1],
@@ -478,7 +469,6 @@ extern "C" int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sou
                 if (hc[2] & 1) { overflow = true; cap_paths *= 4; break; }
                 n_front = hc[4];
                 cur ^= 1;
-                if (count_only && hc[0] > cap) { n_front = 0; break; }
             }
             if (!overflow && n_front > 0) {
                 void* d_stack = nullptr;
@@ -488,9 +478,11 @@ extern "C" int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sou
                 ctx->launches++;
             }
             unsigned long long hexp = 0;
+            std::vector<int32_t> hg(n_groups, 0);
             if (!overflow) {
                 WISP_CUDA(cudaMemcpyAsync(hc, cnt, 32, cudaMemcpyDeviceToHost, st));
                 WISP_CUDA(cudaMemcpyAsync(&hexp, cnt + 8, 8, cudaMemcpyDeviceToHost, st));
+                WISP_CUDA(cudaMemcpyAsync(hg.data(), P.g_count, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, st));
                 WISP_CUDA(cudaStreamSynchronize(st));
                 WISP_CUDA(cudaGetLastError());
                 WISP_CHECK(!(hc[2] & 2), "get_paths: a path exceeded the supported length of %d nodes", kMaxLen);
@@ -499,52 +491,159 @@ extern "C" int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sou
             }
             if (overflow) continue;
             expansions_total += hexp;
-            *count_out = hc[0];
-            if (!count_only && out_paths) {
+            counts->assign(hg.begin(), hg.end());
+            if (any_fetch && paths_per_pair) {
                 const int np = hc[0], nn = hc[1];
                 std::vector<double> hl(np);
                 std::vector<int32_t> hp(np), ho(np), hn(np), hnodes(nn);
                 if (np) {
-                    WISP_CUDA(cudaMemcpy(hl.data(), P.out_len, (size_t)np * 8, cudaMemcpyDeviceToHost));
-                    WISP_CUDA(cudaMemcpy(hp.data(), P.out_pair, (size_t)np * 4, cudaMemcpyDeviceToHost));
-                    WISP_CUDA(cudaMemcpy(ho.data(), P.out_off, (size_t)np * 4, cudaMemcpyDeviceToHost));
-                    WISP_CUDA(cudaMemcpy(hn.data(), P.out_n, (size_t)np * 4, cudaMemcpyDeviceToHost));
-                    WISP_CUDA(cudaMemcpy(hnodes.data(), P.out_nodes, (size_t)nn * 4, cudaMemcpyDeviceToHost));
+                    WISP_CUDA(cudaMemcpyAsync(hl.data(), P.out_len, (size_t)np * 8, cudaMemcpyDeviceToHost, st));
+                    WISP_CUDA(cudaMemcpyAsync(hp.data(), P.out_pair, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+                    WISP_CUDA(cudaMemcpyAsync(ho.data(), P.out_off, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+                    WISP_CUDA(cudaMemcpyAsync(hn.data(), P.out_n, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+                    WISP_CUDA(cudaMemcpyAsync(hnodes.data(), P.out_nodes, (size_t)nn * 4, cudaMemcpyDeviceToHost, st));
+                    WISP_CUDA(cudaStreamSynchronize(st));
                 }
                 enum_ms += now_ms() - te;
                 double th = now_ms();
-                std::vector<std::vector<HostPath>> per_pair(n_pairs);
+                paths_per_pair->assign(n_pairs, std::vector<HostPath>());
                 for (int k = 0; k < np; ++k) {
                     HostPath hpth;
                     hpth.len = hl[k];
                     hpth.nodes.assign(hnodes.begin() + ho[k], hnodes.begin() + ho[k] + hn[k]);
-                    per_pair[hp[k]].push_back(std::move(hpth));
+                    (*paths_per_pair)[hp[k]].push_back(std::move(hpth));
                 }
-                for (int p = 0; p < n_pairs; ++p) {
-                    std::sort(per_pair[p].begin(), per_pair[p].end(), path_less);
-                    for (auto& q : per_pair[p]) out_paths->push_back(std::move(q));
-                }
+                for (int p = 0; p < n_pairs; ++p) std::sort((*paths_per_pair)[p].begin(), (*paths_per_pair)[p].end(), path_less);
                 host_ms += now_ms() - th;
             } else {
                 enum_ms += now_ms() - te;
             }
             return 0;
         }
+    }
+};
+
+// seed of one (source, sink) pair: a shortest path from the APSP predecessors, LR length from the matrix (:30-33)
+int seed_path(const PathGraphState* g, const int32_t* pred_row, const double* dist_row, int s, int t,
+              std::vector<int32_t>* sp, double* length) {
+    const int N = g->N;
+    WISP_CHECK(dist_row[t] < 1e300 && pred_row[t] >= 0, "get_paths: no path between node %d and node %d", s, t);
+    sp->clear();
+    sp->push_back(t);
+    while (sp->back() != s) {
+        const int pr = pred_row[sp->back()];
+        WISP_CHECK(pr >= 0 && (int)sp->size() <= N, "get_paths: broken predecessor chain %d -> %d", s, t);
+        sp->push_back(pr);
+    }
+    std::reverse(sp->begin(), sp->end());
+    double len = 0.0;
+    for (size_t k = 0; k + 1 < sp->size(); ++k) len += g->w[(size_t)(*sp)[k] * N + (*sp)[k + 1]];
+    *length = len;
+    return 0;
+}
+
+// rows `rows` of (pred, dist) in ONE round trip: [n][N] each
+int fetch_rows(wisp_ctx* ctx, const PathGraphState* g, const std::vector<int>& rows, std::vector<int32_t>* pred,
+               std::vector<double>* dist) {
+    const int N = g->N;
+    cudaStream_t st = ctx->stream;
+    pred->resize(rows.size() * (size_t)N);
+    dist->resize(rows.size() * (size_t)N);
+    for (size_t k = 0; k < rows.size(); ++k) {
+        WISP_CUDA(cudaMemcpyAsync(pred->data() + k * N, (int32_t*)g->d_pred + (size_t)rows[k] * N, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+        WISP_CUDA(cudaMemcpyAsync(dist->data() + k * N, (double*)g->d_dist + (size_t)rows[k] * N, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+    }
+    WISP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+void store_result(wisp_ctx* ctx, std::vector<HostPath>& paths) {
+    for (auto& p : paths) {
+        ctx->path_len.push_back(p.len);
+        for (int32_t n : p.nodes) ctx->path_nodes.push_back(n);
+        ctx->path_off.push_back((int64_t)ctx->path_nodes.size());
+    }
+}
+
+}  // namespace
+
+extern "C" int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sources,
+                                const int32_t* sinks, int n_sinks, int number_of_paths, int flags) {
+    WISP_CHECK(ctx && ctx->pg, "paths_query: call wisp_paths_prepare first");
+    WISP_CHECK(sources && sinks && n_sources > 0 && n_sinks > 0, "get_paths: empty source or sink list");
+    WISP_CHECK(number_of_paths >= 1, "get_paths: number_of_paths must be >= 1");
+    WISP_CUDA(cudaSetDevice(ctx->device));
+    PathGraphState* g = ctx->pg;
+    const int N = g->N;
+    for (int i = 0; i < n_sources; ++i) WISP_CHECK(sources[i] >= 0 && sources[i] < N, "get_paths: source %d out of range", sources[i]);
+    for (int i = 0; i < n_sinks; ++i) WISP_CHECK(sinks[i] >= 0 && sinks[i] < N, "get_paths: sink %d out of range", sinks[i]);
+    const double max_simple_len = g->max_simple_len;
+
+    // ---- pairs in the reference's loop order (:27-29), seed path (:25-36) ----
+    std::vector<int32_t> pairs;
+    for (int a = 0; a < n_sources; ++a)
+        for (int b = 0; b < n_sinks; ++b)
+            if (sources[a] != sinks[b]) { pairs.push_back(sources[a]); pairs.push_back(sinks[b]); }
+    const int n_pairs = (int)pairs.size() / 2;
+    WISP_CHECK(n_pairs > 0, "get_paths: no (source, sink) pair with source != sink");
+
+    std::vector<int> rows;
+    std::vector<int> row_of(N, -1);
+    for (int p = 0; p < n_pairs; ++p)
+        if (row_of[pairs[2 * p]] < 0) { row_of[pairs[2 * p]] = (int)rows.size(); rows.push_back(pairs[2 * p]); }
+    std::vector<int32_t> pred_rows;
+    std::vector<double> dist_rows;
+    WISP_TRY(fetch_rows(ctx, g, rows, &pred_rows, &dist_rows));
+    double shortest_length = 99999999.999;
+    std::vector<int32_t> shortest_path;
+    for (int p = 0; p < n_pairs; ++p) {
+        const int s = pairs[2 * p], t = pairs[2 * p + 1];
+        std::vector<int32_t> sp;
+        double length = 0.0;
+        WISP_TRY(seed_path(g, pred_rows.data() + (size_t)row_of[s] * N, dist_rows.data() + (size_t)row_of[s] * N, s, t, &sp, &length));
+        if (length < shortest_length) { shortest_length = length; shortest_path = sp; }
+    }
+
+    std::vector<HostPath> paths;
+    paths.push_back(HostPath{shortest_length, shortest_path});
+    int64_t num_paths = 1;
+    double cutoff = shortest_length;
+
+    EnumEngine eng{ctx, g, (flags & 1) ? 1 : 0};
+    eng.cap_paths = std::max(4096, 8 * number_of_paths * std::max(1, n_pairs));
+    eng.cap_front = std::max(16 * kTargetPrefixes, 4 * n_pairs);
+    const std::vector<int32_t> pair_group(n_pairs, 0);
+    int passes = 0;
+    auto run_pass = [&](double pass_cutoff, bool count_only, int cap, int64_t* count_out,
+                        std::vector<HostPath>* out_paths) -> int {
+        std::vector<GroupRequest> req(1);
+        req[0].cutoff = pass_cutoff; req[0].count_only = count_only; req[0].cap = cap;
+        std::vector<int64_t> counts;
+        std::vector<std::vector<HostPath>> per_pair;
+        WISP_TRY(eng.pass(pairs, pair_group, req, &counts, count_only ? nullptr : &per_pair));
+        *count_out = counts[0];
+        if (!count_only && out_paths)
+            for (auto& lst : per_pair)
+                for (auto& q : lst) out_paths->push_back(std::move(q));
+        return 0;
     };
 
-    // A path and its reverse can both be enumerated only when (s,t) and (t,s) are both pairs;
-    // otherwise no two enumerated paths are "redundant" and pass counts need no dedupe.
-    bool has_reverse = false;
-    for (int p = 0; p < n_pairs && !has_reverse; ++p)
-        for (int q = 0; q < n_pairs; ++q)
-            if (pairs[2 * p] == pairs[2 * q + 1] && pairs[2 * p + 1] == pairs[2 * q]) { has_reverse = true; break; }
+    // A path and its reverse can both be enumerated only when (s,t) and (t,s) are both pairs, and the
+    // same path twice only when a pair occurs twice (a repeated index in sources or sinks); otherwise
+    // no two enumerated paths are "redundant" and pass counts need no dedupe.
+    bool needs_dedupe = false;
+    for (int p = 0; p < n_pairs && !needs_dedupe; ++p)
+        for (int q = 0; q < n_pairs; ++q) {
+            if (pairs[2 * p] == pairs[2 * q + 1] && pairs[2 * p + 1] == pairs[2 * q]) { needs_dedupe = true; break; }
+            if (q != p && pairs[2 * p] == pairs[2 * q] && pairs[2 * p + 1] == pairs[2 * q + 1]) { needs_dedupe = true; break; }
+        }
 
     const int64_t K = number_of_paths;
     const int cap_count = (int)std::min<int64_t>(4 * K + 64, 1 << 30);
     double prev_cutoff = -1.0;     // largest cutoff known to hold fewer than K paths
     while (num_paths < number_of_paths) {                                    // :56
         std::vector<HostPath> temp_paths;
-        if (has_reverse) {
+        if (needs_dedupe) {
             // literal: full pass, per-pass dedupe decides the count (:157-179)
             int64_t n = 0;
             WISP_TRY(run_pass(cutoff, false, 0, &n, &temp_paths));
@@ -586,7 +685,7 @@ extern "C" int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sou
         for (auto& q : temp_paths) paths.push_back(q);
         cutoff += 0.1;                                                       // :187
         ++passes;
-        host_ms += now_ms() - th;
+        eng.host_ms += now_ms() - th;
         // the reference never terminates when fewer than K simple paths exist (App. A.6):
         // past the longest possible simple path nothing new can appear -- fail loudly instead.
         WISP_CHECK(cutoff <= max_simple_len + 0.2 || num_paths >= number_of_paths,
@@ -597,18 +696,163 @@ extern "C" int wisp_paths_query(wisp_ctx* ctx, const int32_t* sources, int n_sou
     std::sort(paths.begin(), paths.end(), path_less);                        // :209
     if (num_paths != number_of_paths && (int64_t)paths.size() > number_of_paths)  // :211
         paths.resize(number_of_paths);
-    host_ms += now_ms() - th;
+    eng.host_ms += now_ms() - th;
 
-    ctx->path_len.clear(); ctx->path_off.clear(); ctx->path_nodes.clear();
+    ctx->path_len.clear(); ctx->path_off.clear(); ctx->path_nodes.clear(); ctx->path_query_off.clear();
     ctx->path_off.push_back(0);
-    for (auto& p : paths) {
-        ctx->path_len.push_back(p.len);
-        for (int32_t n : p.nodes) ctx->path_nodes.push_back(n);
-        ctx->path_off.push_back((int64_t)ctx->path_nodes.size());
+    store_result(ctx, paths);
+    ctx->path_stats[0] = passes; ctx->path_stats[1] = (double)eng.expansions_total;
+    ctx->path_stats[2] = cutoff - 0.1; ctx->path_stats[3] = g->apsp_ms;
+    ctx->path_stats[4] = eng.enum_ms; ctx->path_stats[5] = eng.host_ms;
+    return 0;
+}
+
+// Many INDEPENDENT queries on the prepared graph -- query q = get_paths([s_q], [t_q], K) -- answered
+// together (configs[4]: 200 pairs x 1,000 paths).  Every query runs the reference's own cutoff ratchet
+// (count passes until >= K, bisection when a pass overshoots, one fetch); the passes of all unfinished
+// queries are served by the same kernels.  Results: wisp_paths_size / wisp_paths_fetch give the
+// concatenation, wisp_paths_query_offsets the first path of every query.
+extern "C" int wisp_paths_query_pairs(wisp_ctx* ctx, const int32_t* pairs_in, int n_queries, int number_of_paths,
+                                      int flags) {
+    WISP_CHECK(ctx && ctx->pg, "paths_query_pairs: call wisp_paths_prepare first");
+    WISP_CHECK(pairs_in && n_queries > 0, "paths_query_pairs: empty pair list");
+    WISP_CHECK(number_of_paths >= 1, "get_paths: number_of_paths must be >= 1");
+    WISP_CUDA(cudaSetDevice(ctx->device));
+    PathGraphState* g = ctx->pg;
+    const int N = g->N;
+    const int64_t K = number_of_paths;
+    const int cap_count = (int)std::min<int64_t>(4 * K + 64, 1 << 30);
+    for (int q = 0; q < n_queries; ++q) {
+        const int s = pairs_in[2 * q], t = pairs_in[2 * q + 1];
+        WISP_CHECK(s >= 0 && s < N && t >= 0 && t < N, "get_paths: pair (%d, %d) out of range", s, t);
+        WISP_CHECK(s != t, "get_paths: no (source, sink) pair with source != sink");
     }
-    ctx->path_stats[0] = passes; ctx->path_stats[1] = (double)expansions_total;
-    ctx->path_stats[2] = cutoff - 0.1; ctx->path_stats[3] = apsp_ms;
-    ctx->path_stats[4] = enum_ms; ctx->path_stats[5] = host_ms;
+    // ---- seeds: the needed predecessor / distance rows in one round trip ----
+    std::vector<int> rows, row_of(N, -1);
+    for (int q = 0; q < n_queries; ++q)
+        if (row_of[pairs_in[2 * q]] < 0) { row_of[pairs_in[2 * q]] = (int)rows.size(); rows.push_back(pairs_in[2 * q]); }
+    std::vector<int32_t> pred_rows;
+    std::vector<double> dist_rows;
+    WISP_TRY(fetch_rows(ctx, g, rows, &pred_rows, &dist_rows));
+    enum Phase { COUNT, BISECT, FETCH, DONE };
+    struct Query {
+        Phase phase = COUNT;
+        std::vector<HostPath> paths;
+        int64_t num_paths = 1, n_over = 0;
+        double cutoff = 0.0, prev_cutoff = -1.0, lo = 0.0, hi = 0.0, req_cutoff = 0.0;
+        int bisect_it = 0, passes = 0;
+    };
+    std::vector<Query> Q(n_queries);
+    for (int q = 0; q < n_queries; ++q) {
+        const int s = pairs_in[2 * q], t = pairs_in[2 * q + 1];
+        std::vector<int32_t> sp;
+        double length = 0.0;
+        WISP_TRY(seed_path(g, pred_rows.data() + (size_t)row_of[s] * N, dist_rows.data() + (size_t)row_of[s] * N, s, t, &sp, &length));
+        Q[q].paths.push_back(HostPath{length, sp});
+        Q[q].cutoff = length;
+        Q[q].req_cutoff = length;
+        if (Q[q].num_paths >= K) Q[q].phase = DONE;         // K == 1: the seed alone (:56 is false at once)
+    }
+    EnumEngine eng{ctx, g, (flags & 1) ? 1 : 0};
+    eng.target_prefixes = std::min(65536, std::max(kTargetPrefixes, 512 * n_queries));
+    eng.cap_front = std::max(16 * eng.target_prefixes, 4 * n_queries);
+    eng.cap_paths = std::max(4096, (int)std::min<int64_t>((int64_t)8 * K * n_queries, 1 << 26));
+    int rounds = 0;
+    for (;;) {
+        // one request per unfinished query
+        std::vector<int32_t> pairs, pair_group;
+        std::vector<GroupRequest> req;
+        std::vector<int> who;
+        for (int q = 0; q < n_queries; ++q) {
+            if (Q[q].phase == DONE) continue;
+            GroupRequest r;
+            r.cutoff = Q[q].req_cutoff;
+            r.count_only = Q[q].phase != FETCH;
+            r.cap = cap_count;
+            pairs.push_back(pairs_in[2 * q]); pairs.push_back(pairs_in[2 * q + 1]);
+            pair_group.push_back((int32_t)req.size());
+            req.push_back(r);
+            who.push_back(q);
+        }
+        if (who.empty()) break;
+        std::vector<int64_t> counts;
+        std::vector<std::vector<HostPath>> per_pair;
+        WISP_TRY(eng.pass(pairs, pair_group, req, &counts, &per_pair));
+        ++rounds;
+        for (size_t k = 0; k < who.size(); ++k) {
+            Query& y = Q[who[k]];
+            const int64_t n = counts[k];
+            auto finish_pass = [&]() -> int {       // the tail of the reference's while body (:187) + the guard
+                y.cutoff += 0.1;
+                ++y.passes;
+                WISP_CHECK(y.cutoff <= g->max_simple_len + 0.2 || y.num_paths >= K,
+                           "get_paths: only %lld simple paths exist, %d requested", (long long)y.num_paths, number_of_paths);
+                if (y.num_paths >= K) y.phase = DONE;
+                else { y.phase = COUNT; y.req_cutoff = y.cutoff; }
+                return 0;
+            };
+            if (y.phase == COUNT) {
+                if (n < K) {
+                    y.num_paths = n;
+                    y.prev_cutoff = y.cutoff;
+                    WISP_TRY(finish_pass());
+                } else if (n <= cap_count) {
+                    y.phase = FETCH;
+                    y.req_cutoff = y.cutoff;
+                } else {
+                    y.n_over = n;
+                    y.lo = y.prev_cutoff; y.hi = y.cutoff; y.bisect_it = 0;
+                    const double mid = 0.5 * (y.lo + y.hi);
+                    if (mid > y.lo && mid < y.hi) { y.phase = BISECT; y.req_cutoff = mid; }
+                    else { y.phase = FETCH; y.req_cutoff = y.hi; }
+                }
+            } else if (y.phase == BISECT) {
+                const double mid = y.req_cutoff;
+                bool found = false;
+                if (n < K) y.lo = mid;
+                else if (n > cap_count) y.hi = mid;
+                else found = true;
+                ++y.bisect_it;
+                if (found) { y.phase = FETCH; y.req_cutoff = mid; }
+                else {
+                    const double m2 = 0.5 * (y.lo + y.hi);
+                    if (y.bisect_it < 60 && m2 > y.lo && m2 < y.hi) y.req_cutoff = m2;
+                    else { y.phase = FETCH; y.req_cutoff = y.hi; }      // massive ties: take everything up to hi
+                }
+            } else {   // FETCH
+                for (auto& hp : per_pair[k]) y.paths.push_back(std::move(hp));
+                y.num_paths = y.n_over > 0 ? y.n_over : (int64_t)per_pair[k].size();
+                y.n_over = 0;
+                WISP_TRY(finish_pass());
+            }
+        }
+    }
+    double th = now_ms();
+    ctx->path_len.clear(); ctx->path_off.clear(); ctx->path_nodes.clear(); ctx->path_query_off.clear();
+    ctx->path_off.push_back(0);
+    int passes = 0;
+    for (int q = 0; q < n_queries; ++q) {
+        Query& y = Q[q];
+        if (y.paths.size() != 1) dedupe(y.paths);                            // :189
+        std::sort(y.paths.begin(), y.paths.end(), path_less);                // :209
+        if (y.num_paths != K && (int64_t)y.paths.size() > K) y.paths.resize(K);   // :211
+        ctx->path_query_off.push_back((int64_t)ctx->path_len.size());
+        store_result(ctx, y.paths);
+        passes += y.passes;
+    }
+    ctx->path_query_off.push_back((int64_t)ctx->path_len.size());
+    eng.host_ms += now_ms() - th;
+    ctx->path_stats[0] = passes; ctx->path_stats[1] = (double)eng.expansions_total;
+    ctx->path_stats[2] = rounds; ctx->path_stats[3] = g->apsp_ms;
+    ctx->path_stats[4] = eng.enum_ms; ctx->path_stats[5] = eng.host_ms;
+    return 0;
+}
+
+extern "C" int wisp_paths_query_offsets(wisp_ctx* ctx, int64_t* n_queries, int64_t* offsets) {
+    WISP_CHECK(ctx, "paths_query_offsets: null context");
+    const int64_t nq = ctx->path_query_off.empty() ? 0 : (int64_t)ctx->path_query_off.size() - 1;
+    if (n_queries) *n_queries = nq;
+    if (offsets && nq > 0) memcpy(offsets, ctx->path_query_off.data(), (size_t)(nq + 1) * 8);
     return 0;
 }
 

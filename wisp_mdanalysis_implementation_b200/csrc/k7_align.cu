@@ -131,56 +131,83 @@ align_rotate_kernel(float* __restrict__ align, int n_align, const double* __rest
     }
 }
 
-// np.sum(float32 array, axis=0) / nSteps of the reference (:86): sequential float32 adds.
-__global__ void mean32_sequential_kernel(const float* __restrict__ a, int64_t T, int64_t ncols,
-                                         double* __restrict__ out) {
+// np.sum(float32 array, axis=0) of the reference (:86): sequential float32 adds down the frames.
+// The raw float32 sum is returned (as a double holding a float), so that frame-sharded callers can
+// chain the shards' sums in float32 before the single float32 division by nSteps.
+__global__ void sum32_sequential_kernel(const float* __restrict__ a, int64_t T, int64_t ncols,
+                                        double* __restrict__ out) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncols) return;
     float s = 0.f;
     for (int64_t t = 0; t < T; ++t) s = __fadd_rn(s, a[t * ncols + c]);
-    out[c] = (double)__fdiv_rn(s, (float)T);
+    out[c] = (double)s;
 }
 
 }  // namespace
 
-// d_align: float32 [T][n_align][3] (in/out); d_nodes: pitched float64 trajectory (in/out).
+// ---- building blocks (also the device-level C ABI: wisp_dev_align_sums / wisp_dev_align_iter) ----
+// d_sums [na3 + nn3]: first the landmark column sums, then the node column sums of this frame block.
+// first == true: landmark sums as the reference's sequential float32 sums (initial average, :86).
+int launch_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_nodes, int64_t ld,
+                      int N, int64_t T, bool first, double* d_sums, cudaStream_t st) {
+    const int64_t na3 = 3 * (int64_t)n_align, nn3 = 3 * (int64_t)N;
+    if (first) {
+        sum32_sequential_kernel<<<(int)((na3 + 127) / 128), 128, 0, st>>>(d_align, T, na3, d_sums);
+        ctx->launches++;
+        WISP_CUDA(cudaGetLastError());
+    } else {
+        WISP_TRY(launch_colsum_f32(ctx, d_align, T, na3, na3, d_sums, st));
+    }
+    WISP_TRY(launch_colsum(ctx, d_nodes, T, ld, nn3, d_sums + na3, st));
+    return 0;
+}
+
+// one alignment pass over this frame block: rotate every frame onto d_avg_align (in place)
+int launch_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align, double* d_nodes,
+                        int64_t ld, int N, int64_t T, cudaStream_t st) {
+    ctx->i8_stats_x = nullptr;               // the node trajectory is rotated in place
+    const int blocks = (int)std::min<int64_t>(T, (int64_t)ctx->sm_count * 8);
+    align_rotate_kernel<<<blocks, kAlThreads, 0, st>>>(d_align, n_align, d_avg_align, d_nodes, ld, N, T);
+    ctx->launches++;
+    WISP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// d_align: float32 [T][n_align][3] (in/out); d_nodes: pitched float64 trajectory (in/out), T = the
+// frames of THIS shard, T_total = all frames.  `reduce` (may be empty) sums a host vector over the
+// frame shards in shard order, float32-chained when its last argument is true; every shard then
+// takes the same decisions from the same numbers.  d_work: [2 * round_up(na3,32) + round_up(nn3,32)].
 // Returns iterations run; log gets (iteration, residual, node RMSD) triples.
 int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* d_nodes, int64_t ld,
                             int N, int64_t T, double threshold, int max_iter, double* d_work,
-                            double* h_avg_nodes, double* log, int* n_iter_out, cudaStream_t st) {
+                            double* h_avg_nodes, double* log, int* n_iter_out, cudaStream_t st,
+                            int64_t T_total, const AlignReduce& reduce) {
     const int64_t na3 = 3 * (int64_t)n_align, nn3 = 3 * (int64_t)N;
-    ctx->i8_stats_x = nullptr;               // the node trajectory is rotated in place
+    if (T_total <= 0) T_total = T;
     double* d_avgA = d_work;                 // [na3]
-    double* d_sumA = d_avgA + round_up(na3, 32);
-    double* d_sumN = d_sumA + round_up(na3, 32);   // [nn3]
-    std::vector<double> avgA(na3), avgN(nn3), newA(na3), newN(nn3);
-    mean32_sequential_kernel<<<(int)((na3 + 127) / 128), 128, 0, st>>>(d_align, T, na3, d_avgA);
-    ctx->launches++;
-    WISP_TRY(launch_colsum(ctx, d_nodes, T, ld, nn3, d_sumN, st));
-    WISP_CUDA(cudaMemcpyAsync(avgA.data(), d_avgA, na3 * 8, cudaMemcpyDeviceToHost, st));
-    WISP_CUDA(cudaMemcpyAsync(avgN.data(), d_sumN, nn3 * 8, cudaMemcpyDeviceToHost, st));
+    double* d_sums = d_avgA + round_up(na3, 32);   // [na3 + nn3]
+    std::vector<double> avgA(na3), avgN(nn3), sums(na3 + nn3);
+    WISP_TRY(launch_align_sums(ctx, d_align, n_align, d_nodes, ld, N, T, true, d_sums, st));
+    WISP_CUDA(cudaMemcpyAsync(sums.data(), d_sums, (na3 + nn3) * 8, cudaMemcpyDeviceToHost, st));
     WISP_CUDA(cudaStreamSynchronize(st));
-    for (auto& v : avgN) v /= (double)T;
+    if (reduce) { WISP_TRY(reduce(sums.data(), (size_t)na3, true)); WISP_TRY(reduce(sums.data() + na3, (size_t)nn3, false)); }
+    for (int64_t k = 0; k < na3; ++k) avgA[k] = (double)((float)sums[k] / (float)T_total);   // float32 mean (:86)
+    for (int64_t k = 0; k < nn3; ++k) avgN[k] = sums[na3 + k] / (double)T_total;
+    WISP_CUDA(cudaMemcpyAsync(d_avgA, avgA.data(), na3 * 8, cudaMemcpyHostToDevice, st));
     int iteration = 0;
     double residual = threshold + 9999.0;
-    const int blocks = (int)std::min<int64_t>(T, (int64_t)ctx->sm_count * 8);
     while (residual > threshold && iteration < max_iter) {
-        align_rotate_kernel<<<blocks, kAlThreads, 0, st>>>(d_align, n_align, d_avgA, d_nodes, ld, N, T);
-        ctx->launches++;
-        WISP_CUDA(cudaGetLastError());
-        WISP_TRY(launch_colsum_f32(ctx, d_align, T, na3, na3, d_sumA, st));
-        WISP_TRY(launch_colsum(ctx, d_nodes, T, ld, nn3, d_sumN, st));
-        WISP_CUDA(cudaMemcpyAsync(newA.data(), d_sumA, na3 * 8, cudaMemcpyDeviceToHost, st));
-        WISP_CUDA(cudaMemcpyAsync(newN.data(), d_sumN, nn3 * 8, cudaMemcpyDeviceToHost, st));
+        WISP_TRY(launch_align_rotate(ctx, d_align, n_align, d_avgA, d_nodes, ld, N, T, st));
+        WISP_TRY(launch_align_sums(ctx, d_align, n_align, d_nodes, ld, N, T, false, d_sums, st));
+        WISP_CUDA(cudaMemcpyAsync(sums.data(), d_sums, (na3 + nn3) * 8, cudaMemcpyDeviceToHost, st));
         WISP_CUDA(cudaStreamSynchronize(st));
+        if (reduce) WISP_TRY(reduce(sums.data(), (size_t)(na3 + nn3), false));
         double ra = 0.0, rn = 0.0;
-        for (int64_t k = 0; k < na3; ++k) { newA[k] /= (double)T; const double d = avgA[k] - newA[k]; ra += d * d; }
-        for (int64_t k = 0; k < nn3; ++k) { newN[k] /= (double)T; const double d = avgN[k] - newN[k]; rn += d * d; }
+        for (int64_t k = 0; k < na3; ++k) { const double v = sums[k] / (double)T_total; const double d = avgA[k] - v; ra += d * d; avgA[k] = v; }
+        for (int64_t k = 0; k < nn3; ++k) { const double v = sums[na3 + k] / (double)T_total; const double d = avgN[k] - v; rn += d * d; avgN[k] = v; }
         residual = std::sqrt(ra / n_align);
         const double analysis = std::sqrt(rn / N);
         ++iteration;
-        avgA = newA;
-        avgN = newN;
         WISP_CUDA(cudaMemcpyAsync(d_avgA, avgA.data(), na3 * 8, cudaMemcpyHostToDevice, st));
         if (log) { log[3 * (iteration - 1)] = iteration; log[3 * (iteration - 1) + 1] = residual; log[3 * (iteration - 1) + 2] = analysis; }
     }

@@ -1,0 +1,327 @@
+// pipeline.cu -- wisp_pipeline: coordinates -> cost matrix in ONE call, on 1..8 B200s of one box.
+//
+// Replaces the three stage calls of the driver (wisp_w_mdanalysis.py:86-97:
+// traj_alignment_and_averaging, cartesian_covariance + pearson_correlation_analysis,
+// calc_contact_map) and func_pearson_correlation (:141-144) without the node trajectory or the
+// 3N x 3N covariance ever leaving the device.
+//
+// A context made by wisp_ctx_create_multi owns one child context (device, streams, scratch) per GPU.
+// Frames are the data-parallel axis: shard r = frames [T r / R, T (r+1) / R), one host
+// thread per GPU, every shard streams ITS frames over ITS PCIe link:
+//   S1  chunked H2D double-buffered against K1 (translate + node COM, + the alignment landmarks);
+//   S2  K7 iterative alignment (trajectory_analysis_functions.py:86-126): every shard rotates its
+//       frames onto the current landmark average; the new [landmark || node] column sums are
+//       combined over the shards in shard order on the host (a few KB per iteration) and every
+//       shard takes the same convergence decision from the same numbers;
+//   S3  mean -> centring (+ FP32 tile copy) -> K2 Gram -> K3 distance sums: partial [G], [D] per GPU;
+//   S4  ONE fused kernel per GPU does the cross-GPU reduction AND the epilogue for its row slice of
+//       the outputs: it reads the R partial sums of each entry straight from the peers' HBM over
+//       NVLink (P2P loads, fixed shard order -> every GPU would compute identical bits), applies K4
+//       (Pearson, mean distance, strict-< map, -log|C|) and the slice goes to the caller's host
+//       buffers over that GPU's own PCIe link.  No all-reduce buffer, no all-gather, no NCCL.
+// With one GPU the same code runs inline (no threads, no peers).
+#include "common.cuh"
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+namespace {
+
+// Host barrier over the shard threads.  abort() releases everybody, now and at every later wait():
+// a shard that fails can never leave the others blocked inside a reduction.
+class HostBarrier {
+  public:
+    explicit HostBarrier(int n) : n_(n) {}
+    bool wait() {                        // false: somebody aborted
+        if (n_ <= 1) return !aborted_;
+        std::unique_lock<std::mutex> lk(m_);
+        if (aborted_) return false;
+        const uint64_t gen = gen_;
+        if (++count_ == n_) { count_ = 0; ++gen_; cv_.notify_all(); }
+        else cv_.wait(lk, [&] { return gen_ != gen || aborted_; });
+        return !aborted_;
+    }
+    void abort() {
+        std::lock_guard<std::mutex> lk(m_);
+        aborted_ = true;
+        cv_.notify_all();
+    }
+  private:
+    int n_, count_ = 0;
+    uint64_t gen_ = 0;
+    bool aborted_ = false;
+    std::mutex m_;
+    std::condition_variable cv_;
+};
+
+struct PipeArgs {
+    const float* coords; int64_t T; int A; const double* masses; const int32_t* node_ptr;
+    const int32_t* atom_idx; int N; const int32_t* align_idx; int n_align; int atomic;
+    double align_threshold; int max_align_iterations; double cutoff; int which_map;
+    double *out_avg, *out_corr, *out_avgdist; int64_t* out_binary; double *out_w, *out_nodes;
+    double* out_log; int* out_n_iter;
+};
+
+struct Shared {
+    int R = 1;
+    HostBarrier bar;
+    std::atomic<int> failed{0};
+    std::mutex err_m;
+    std::string err;
+    std::vector<std::vector<double>> slots;     // per-shard host vectors for the small reductions
+    std::vector<const double*> d_gram, d_dsum;  // per-shard partial sums (device pointers)
+    std::vector<int> can_p2p;                   // [R*R]
+    explicit Shared(int r) : R(r), bar(r), slots(r), d_gram(r, nullptr), d_dsum(r, nullptr) {}
+};
+
+// sum `buf` over the shards in shard order; every shard ends with the same numbers
+int reduce_host(Shared& S, int r, double* buf, size_t n, bool f32_chain) {
+    if (S.R == 1) return 0;
+    S.slots[r].assign(buf, buf + n);
+    WISP_CHECK(S.bar.wait(), "pipeline: another shard failed");
+    for (size_t k = 0; k < n; ++k) {
+        if (f32_chain) {
+            float s = (float)S.slots[0][k];
+            for (int q = 1; q < S.R; ++q) s += (float)S.slots[q][k];
+            buf[k] = (double)s;
+        } else {
+            double s = S.slots[0][k];
+            for (int q = 1; q < S.R; ++q) s += S.slots[q][k];
+            buf[k] = s;
+        }
+    }
+    WISP_CHECK(S.bar.wait(), "pipeline: another shard failed");
+    return 0;
+}
+
+int shard_body(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
+    const int R = S.R, N = a.N;
+    const int64_t t0 = a.T * r / R, t1 = a.T * (r + 1) / R, Tl = t1 - t0;
+    const int64_t ld = wisp_node_ld(N), n_pad = round_up(N, kTile);
+    const int64_t na3 = 3 * (int64_t)a.n_align, nn3 = 3 * (int64_t)N;
+    const size_t nn = (size_t)N * N;
+    WISP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // ---- S1: H2D || K1 ----
+    float* d_align = nullptr;
+    if (a.max_align_iterations > 0) {
+        void* pa = nullptr;
+        WISP_TRY(wisp_scratch(ctx, SCR_ALIGN, (size_t)Tl * na3 * 4, &pa));
+        d_align = (float*)pa;
+    }
+    double* d_x = nullptr;
+    int64_t ldx = 0;
+    WISP_TRY(wisp_com_from_host(ctx, a.coords + (size_t)t0 * a.A * 3, Tl, a.A, a.masses, a.node_ptr, a.atom_idx, N,
+                                a.align_idx, a.n_align, a.atomic, &d_x, &ldx, d_align));
+    // small device vectors + the partial sums live in this shard's arena
+    void* pw = nullptr;
+    const size_t work_d = (size_t)(2 * round_up(na3, 32) + round_up(nn3, 32)) + 2 * (size_t)ld;
+    WISP_TRY(wisp_scratch(ctx, SCR_MISC1, work_d * 8, &pw));
+    double* d_work = (double*)pw;
+    double* d_sum = d_work + (2 * round_up(na3, 32) + round_up(nn3, 32));
+    double* d_mean = d_sum + ld;
+    void *pg = nullptr, *pd = nullptr;
+    WISP_TRY(wisp_scratch(ctx, SCR_PIPE_G, (size_t)n_pad * n_pad * 8, &pg));
+    WISP_TRY(wisp_scratch(ctx, SCR_PIPE_D, (size_t)n_pad * n_pad * 8, &pd));
+    double* d_gram = (double*)pg;
+    double* d_dsum = (double*)pd;
+    S.d_gram[r] = d_gram;
+    S.d_dsum[r] = d_dsum;
+    // ---- S2: K7 ----
+    std::vector<double> mean(nn3);
+    bool have_mean = false;
+    if (a.max_align_iterations > 0) {
+        int n_iter = 0;
+        AlignReduce red = [&](double* buf, size_t n, bool f32) { return reduce_host(S, r, buf, n, f32); };
+        WISP_TRY(run_iterative_alignment(ctx, d_align, a.n_align, d_x, ld, N, Tl, a.align_threshold,
+                                         a.max_align_iterations, d_work, mean.data(), r == 0 ? a.out_log : nullptr,
+                                         &n_iter, st, a.T, R > 1 ? red : AlignReduce()));
+        if (r == 0 && a.out_n_iter) *a.out_n_iter = n_iter;
+        have_mean = true;       // the node average of the last iteration IS the frame mean (:112)
+    }
+    // ---- S3: mean, centring, K2, K3 ----
+    if (!have_mean) {
+        WISP_TRY(launch_colsum(ctx, d_x, Tl, ld, nn3, d_sum, st));
+        WISP_CUDA(cudaMemcpyAsync(mean.data(), d_sum, nn3 * 8, cudaMemcpyDeviceToHost, st));
+        WISP_CUDA(cudaStreamSynchronize(st));
+        WISP_TRY(reduce_host(S, r, mean.data(), (size_t)nn3, false));
+        for (auto& v : mean) v /= (double)a.T;
+    }
+    if (r == 0 && a.out_avg) memcpy(a.out_avg, mean.data(), nn3 * 8);
+    WISP_CUDA(cudaMemsetAsync(d_mean, 0, (size_t)ld * 8, st));
+    WISP_CUDA(cudaMemcpyAsync(d_mean, mean.data(), nn3 * 8, cudaMemcpyHostToDevice, st));
+    if (a.out_nodes)   // un-centred node trajectory, as traj_alignment_and_averaging returns it
+        WISP_CUDA(cudaMemcpy2DAsync(a.out_nodes + (size_t)t0 * nn3, (size_t)nn3 * 8, d_x, (size_t)ld * 8, (size_t)nn3 * 8,
+                                    (size_t)Tl, cudaMemcpyDeviceToHost, st));
+    void* pp = nullptr;
+    WISP_TRY(wisp_scratch(ctx, SCR_P32, (size_t)Tl * n_pad * 12, &pp));
+    WISP_TRY(launch_center(ctx, d_x, Tl, ld, nn3, d_mean, st, (float*)pp, N));
+    WISP_TRY(launch_gram(ctx, d_x, Tl, ld, N, 3, d_gram, st));
+    WISP_TRY(launch_contact_sum(ctx, (const float*)pp, Tl, N, d_mean, d_dsum, st));
+    WISP_CUDA(cudaStreamSynchronize(st));     // `mean` (host) was the source of an async copy; partials complete
+    return 0;
+}
+
+int shard_finish(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
+    const int R = S.R, N = a.N;
+    const int64_t n_pad = round_up(N, kTile);
+    WISP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // row slice of the outputs this GPU produces
+    const int row0 = (int)((int64_t)N * r / R), row1 = (int)((int64_t)N * (r + 1) / R), rows = row1 - row0;
+    if (rows <= 0) return 0;
+    PeerSums ps;
+    ps.n = R;
+    for (int q = 0; q < R; ++q) {
+        const double *g = S.d_gram[q], *d = S.d_dsum[q];
+        if (q != r && !S.can_p2p[r * R + q]) {
+            // no peer mapping between this pair: stage the partials through a peer copy
+            void *sg = nullptr, *sd = nullptr;
+            WISP_TRY(wisp_scratch(ctx, SCR_PIPE_STAGE0 + 2 * q, (size_t)n_pad * n_pad * 8, &sg));
+            WISP_TRY(wisp_scratch(ctx, SCR_PIPE_STAGE0 + 2 * q + 1, (size_t)n_pad * n_pad * 8, &sd));
+            WISP_CUDA(cudaMemcpyPeerAsync(sg, ctx->device, g, ctx->peer_devices[q], (size_t)n_pad * n_pad * 8, st));
+            WISP_CUDA(cudaMemcpyPeerAsync(sd, ctx->device, d, ctx->peer_devices[q], (size_t)n_pad * n_pad * 8, st));
+            g = (const double*)sg;
+            d = (const double*)sd;
+        }
+        ps.gram[q] = g;
+        ps.dsum[q] = d;
+    }
+    const size_t sl = (size_t)rows * N;
+    void* po = nullptr;
+    WISP_TRY(wisp_scratch(ctx, SCR_PIPE_OUT, sl * 8 * 4 + (size_t)N * 8 + 1024, &po));
+    double* d_corr = (double*)po;
+    double* d_avgdist = d_corr + sl;
+    double* d_w = d_avgdist + sl;
+    int64_t* d_binary = (int64_t*)(d_w + sl);
+    double* d_diag = (double*)(d_binary + sl);
+    WISP_TRY(launch_epilogue_peers(ctx, ps, a.T, N, row0, row1, a.cutoff, a.which_map, d_diag, d_corr, d_avgdist,
+                                   d_binary, d_w, st));
+    const size_t off = (size_t)row0 * N;
+    if (a.out_corr) WISP_CUDA(cudaMemcpyAsync(a.out_corr + off, d_corr, sl * 8, cudaMemcpyDeviceToHost, st));
+    if (a.out_avgdist) WISP_CUDA(cudaMemcpyAsync(a.out_avgdist + off, d_avgdist, sl * 8, cudaMemcpyDeviceToHost, st));
+    if (a.out_binary) WISP_CUDA(cudaMemcpyAsync(a.out_binary + off, d_binary, sl * 8, cudaMemcpyDeviceToHost, st));
+    if (a.out_w) WISP_CUDA(cudaMemcpyAsync(a.out_w + off, d_w, sl * 8, cudaMemcpyDeviceToHost, st));
+    WISP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+void shard_thread(Shared* S, int r, wisp_ctx* ctx, const PipeArgs* a) {
+    auto fail = [&]() {
+        {
+            std::lock_guard<std::mutex> lk(S->err_m);
+            if (!S->failed.exchange(1)) S->err = std::string("shard ") + std::to_string(r) + ": " + wisp_last_error();
+        }
+        S->bar.abort();                  // nobody stays blocked at a barrier or inside a reduction
+    };
+    if (shard_body(*S, r, ctx, *a)) { fail(); return; }
+    if (!S->bar.wait()) return;          // all partial sums complete
+    if (shard_finish(*S, r, ctx, *a)) { fail(); return; }
+    S->bar.wait();                       // nobody reuses its partials while a peer still reads them
+}
+
+}  // namespace
+
+int wisp_pipeline_run(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
+                      const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
+                      int n_align, int atomic, double align_threshold, int max_align_iterations,
+                      double cutoff, int which_map, double* out_avg, double* out_corr, double* out_avgdist,
+                      int64_t* out_binary, double* out_w, double* out_nodes, double* out_log, int* out_n_iter) {
+    PipeArgs a{coords, T, A, masses, node_ptr, atom_idx, N, align_idx, n_align, atomic, align_threshold,
+               max_align_iterations, cutoff, which_map, out_avg, out_corr, out_avgdist, out_binary, out_w,
+               out_nodes, out_log, out_n_iter};
+    std::vector<wisp_ctx*> ctxs;
+    ctxs.push_back(ctx);
+    for (wisp_ctx* c : ctx->children) ctxs.push_back(c);
+    int R = (int)std::min<int64_t>((int64_t)ctxs.size(), T);     // never an empty shard
+    R = std::min(R, N);
+    ctxs.resize(R);
+    Shared S(R);
+    S.can_p2p.assign((size_t)R * R, 1);
+    for (int p = 0; p < R; ++p)
+        for (int q = 0; q < R; ++q)
+            if (p != q) S.can_p2p[p * R + q] = ctx->peer_ok.empty() ? 0 : ctx->peer_ok[p * (int)(ctx->children.size() + 1) + q];
+    if (R == 1) {
+        // inline: a failure cannot leave anybody at a barrier
+        WISP_TRY(shard_body(S, 0, ctx, a));
+        return shard_finish(S, 0, ctx, a);
+    }
+    std::vector<std::thread> th;
+    for (int r = 0; r < R; ++r) th.emplace_back(shard_thread, &S, r, ctxs[r], &a);
+    for (auto& t : th) t.join();
+    WISP_CUDA(cudaSetDevice(ctx->device));
+    if (S.failed.load()) { wisp_set_error("pipeline: %s", S.err.c_str()); return 1; }
+    int64_t launches = 0;
+    for (wisp_ctx* c : ctx->children) { launches += c->launches - c->launches_reported; c->launches_reported = c->launches; }
+    ctx->launches += launches;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// multi-GPU context
+// ---------------------------------------------------------------------------------------
+extern "C" int wisp_ctx_create_multi(int n_gpus, const int* devices, wisp_ctx** out) {
+    WISP_CHECK(out, "ctx_create_multi: null output pointer");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        wisp_set_error("ctx_create_multi: no CUDA device available (%s) -- this library has no CPU fallback",
+                       cudaGetErrorString(e));
+        return 1;
+    }
+    if (n_gpus <= 0) n_gpus = n_dev;                       // 0 = every GPU of the box
+    WISP_CHECK(devices || n_gpus <= n_dev, "ctx_create_multi: %d GPUs requested, %d visible", n_gpus, n_dev);
+    WISP_CHECK(n_gpus <= kMaxPeers, "ctx_create_multi: at most %d GPUs", kMaxPeers);
+    std::vector<int> devs(n_gpus);
+    // A device may be listed more than once: the shards then share that GPU (separate streams and
+    // scratch, plain device pointers instead of peer mappings).  This is how the sharding protocol is
+    // exercised on a one-GPU box (tests); it is not a way to go faster.
+    for (int i = 0; i < n_gpus; ++i) {
+        devs[i] = devices ? devices[i] : i;
+        WISP_CHECK(devs[i] >= 0 && devs[i] < n_dev, "ctx_create_multi: device %d out of range (0..%d)", devs[i], n_dev - 1);
+    }
+    wisp_ctx* root = nullptr;
+    WISP_TRY(wisp_ctx_create(devs[0], &root));
+    for (int i = 1; i < n_gpus; ++i) {
+        wisp_ctx* c = nullptr;
+        if (wisp_ctx_create(devs[i], &c)) { wisp_ctx_destroy(root); return 1; }
+        root->children.push_back(c);
+    }
+    root->peer_devices = devs;
+    for (wisp_ctx* c : root->children) c->peer_devices = devs;
+    root->peer_ok.assign((size_t)n_gpus * n_gpus, 1);
+    for (int p = 0; p < n_gpus; ++p) {
+        cudaSetDevice(devs[p]);
+        for (int q = 0; q < n_gpus; ++q) {
+            if (devs[p] == devs[q]) continue;      // same device: plain pointers
+            int ok = 0;
+            cudaDeviceCanAccessPeer(&ok, devs[p], devs[q]);
+            if (ok) {
+                cudaError_t pe = cudaDeviceEnablePeerAccess(devs[q], 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+                (void)cudaGetLastError();
+            }
+            root->peer_ok[p * n_gpus + q] = ok;
+        }
+    }
+    cudaSetDevice(devs[0]);
+    *out = root;
+    return 0;
+}
+
+extern "C" int wisp_ctx_gpus(wisp_ctx* ctx) { return ctx ? 1 + (int)ctx->children.size() : 0; }
+
+extern "C" int wisp_host_register(void* ptr, size_t bytes) {
+    WISP_CHECK(ptr && bytes, "host_register: empty range");
+    WISP_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+
+extern "C" int wisp_host_unregister(void* ptr) {
+    WISP_CHECK(ptr, "host_unregister: null pointer");
+    WISP_CUDA(cudaHostUnregister(ptr));
+    return 0;
+}

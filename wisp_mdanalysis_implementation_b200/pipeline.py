@@ -16,12 +16,8 @@ import torch
 from . import _lib, sharding
 
 
-def bind_to_gpu_numa_node(device_index):
-    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that pinned host
-    buffers allocated afterwards are node-local and every rank's H2D stream crosses only its own
-    PCIe root (matters at 8 ranks: 8 x 50 GB/s of host reads).  Best effort; returns the node or
-    None."""
-    import os
+def gpu_numa_node(device_index):
+    """(NUMA node, set of its CPUs) of the PCIe root the GPU hangs off, or (None, None)."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -33,11 +29,26 @@ def bind_to_gpu_numa_node(device_index):
             bus = bus[4:]
         node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
         if node < 0:
-            return None
+            return None, None
         cpus = set()
         for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
+        return node, cpus
+    except Exception:
+        return None, None
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that pinned host
+    buffers allocated afterwards are node-local and every rank's H2D stream crosses only its own
+    PCIe root (matters at 8 ranks: 8 x 50 GB/s of host reads).  Best effort; returns the node or
+    None."""
+    import os
+    node, cpus = gpu_numa_node(device_index)
+    if node is None:
+        return None
+    try:
         allowed = cpus & os.sched_getaffinity(0)
         if allowed:
             os.sched_setaffinity(0, allowed)
@@ -47,10 +58,37 @@ def bind_to_gpu_numa_node(device_index):
     return None
 
 
+def host_trajectory_numa_sharded(shape, n_shards, fill):
+    """Page-locked float32 host array of `shape` = (frames, atoms, 3) whose frame shard r (the frames
+    wisp_pipeline on an n_shards-GPU context gives GPU r) is physically placed on the NUMA node of
+    GPU r: the pages are first touched -- by ``fill(r, view)`` writing the shard -- while the calling
+    thread is bound to that node's CPUs, then the whole range is page-locked in place
+    (wisp_host_register).  Returns (array, [node per shard]); call _lib.host_unregister when done."""
+    import os
+    arr = np.empty(shape, dtype=np.float32)
+    T = shape[0]
+    before = os.sched_getaffinity(0)
+    nodes = []
+    try:
+        for r in range(n_shards):
+            node, cpus = gpu_numa_node(r)
+            nodes.append(node)
+            if cpus:
+                try:
+                    os.sched_setaffinity(0, cpus)
+                except Exception:
+                    pass
+            fill(r, arr[T * r // n_shards:T * (r + 1) // n_shards])
+    finally:
+        os.sched_setaffinity(0, before)
+    _lib.host_register(arr)
+    return arr, nodes
+
+
 class FramePipeline:
     def __init__(self, ctx, n_nodes, n_atoms, masses, node_ptr, atom_idx, align_idx,
                  frames_local, frames_total=None, cutoff=15.0, which_map=1, atomic=False,
-                 group=None):
+                 group=None, align_iterations=0, align_threshold=1e-5):
         self.ctx = ctx
         self.dev = torch.device("cuda", ctx.device)
         self.N, self.A = int(n_nodes), int(n_atoms)
@@ -58,6 +96,10 @@ class FramePipeline:
         self.T_total = int(frames_total if frames_total is not None else frames_local)
         self.cutoff, self.which_map, self.atomic = float(cutoff), int(which_map), bool(atomic)
         self.group = group
+        # K7 (trajectory_analysis_functions.py:86-126): 0 = translation only (pre-aligned input)
+        self.align_iterations, self.align_threshold = int(align_iterations), float(align_threshold)
+        self.n_align = len(align_idx)
+        self.alignment_log = []
         self.ld = _lib.node_ld(self.N)
         self.tpad = _lib.frames_pad(self.T)
         self.npad = _lib.gram_ld(self.N)
@@ -76,6 +118,10 @@ class FramePipeline:
         self.d_sums = self.d_flat[:2 * nn].view(2, self.npad, self.npad)
         self.d_offs = self.d_flat[2 * nn:]
         self.d_ref = torch.zeros(self.ld, dtype=f64, device=dev)
+        if self.align_iterations > 0:
+            self.d_align = torch.empty((self.T, self.n_align, 3), dtype=torch.float32, device=dev)
+            self.d_align_sums = torch.zeros(3 * self.n_align + 3 * self.N, dtype=f64, device=dev)
+            self.d_avg_align = torch.zeros(3 * self.n_align, dtype=f64, device=dev)
         self.d_parts = None
         self.k23_stream = torch.cuda.Stream(device=dev)
         n = self.N
@@ -98,9 +144,62 @@ class FramePipeline:
         """K1 on a coordinate block; colsum=True also leaves the column sums of the rows just
         written in d_colsum (fused into the streaming kernel)."""
         t = self.T if frames is None else frames
-        self.ctx.dev_com(self.plan, d_coords.data_ptr(), t, self.N,
-                         self.d_x.data_ptr() + row0 * self.ld * 8,
-                         self.d_colsum.data_ptr() if colsum else None, stream=self._stream())
+        d_al = self.d_align.data_ptr() + row0 * self.n_align * 12 if self.align_iterations > 0 else None
+        self.ctx.dev_com_align(self.plan, d_coords.data_ptr(), t, self.N,
+                               self.d_x.data_ptr() + row0 * self.ld * 8,
+                               self.d_colsum.data_ptr() if colsum else None, d_al, stream=self._stream())
+
+    def align(self):
+        """K7, frame-sharded: every rank rotates its frames onto the current landmark average; the
+        new [landmark || node] column sums are all-reduced (3 (n_align + N) doubles per iteration)
+        and every rank takes the same convergence decision.  Leaves the frame mean of the aligned
+        node trajectory in d_mean (the node average of the last iteration IS that mean) and
+        returns the number of iterations."""
+        s = self._stream()
+        na3, nn3 = 3 * self.n_align, 3 * self.N
+        world = torch.distributed.get_world_size(self.group) if sharding.is_distributed(self.group) else 1
+        self.ctx.dev_align_sums(self.d_align.data_ptr(), self.n_align, self.d_x.data_ptr(), self.T, self.N, True,
+                                self.d_align_sums.data_ptr(), stream=s)
+        if world > 1:
+            # the initial landmark average is a float32 sum chained over the ranks in rank order
+            allsums = torch.empty((world, na3 + nn3), dtype=torch.float64, device=self.dev)
+            torch.distributed.all_gather_into_tensor(allsums, self.d_align_sums, group=self.group)
+            h = allsums.cpu().numpy()
+            sa = h[0, :na3].astype(np.float32)
+            for r in range(1, world):
+                sa = sa + h[r, :na3].astype(np.float32)
+            sn = h[0, na3:].copy()
+            for r in range(1, world):
+                sn += h[r, na3:]
+        else:
+            h = self.d_align_sums.cpu().numpy()
+            sa, sn = h[:na3].astype(np.float32), h[na3:].copy()
+        avg_a = (sa / np.float32(self.T_total)).astype(np.float64)
+        avg_n = sn / float(self.T_total)
+        self.alignment_log = []
+        residual, it = self.align_threshold + 9999.0, 0
+        while residual > self.align_threshold and it < self.align_iterations:
+            self.d_avg_align.copy_(torch.from_numpy(avg_a))
+            self.ctx.dev_align_rotate(self.d_align.data_ptr(), self.n_align, self.d_avg_align.data_ptr(),
+                                      self.d_x.data_ptr(), self.T, self.N, stream=s)
+            self.ctx.dev_align_sums(self.d_align.data_ptr(), self.n_align, self.d_x.data_ptr(), self.T, self.N,
+                                    False, self.d_align_sums.data_ptr(), stream=s)
+            sharding.reduce_sums(self.d_align_sums, group=self.group)
+            h = self.d_align_sums.cpu().numpy() / float(self.T_total)
+            new_a, new_n = h[:na3], h[na3:]
+            residual = float(np.sqrt(np.sum((avg_a - new_a) ** 2) / self.n_align))
+            node_rmsd = float(np.sqrt(np.sum((avg_n - new_n) ** 2) / self.N))
+            avg_a, avg_n = new_a.copy(), new_n.copy()
+            it += 1
+            self.alignment_log.append((it, residual, node_rmsd))
+        self.d_mean.zero_()
+        self.d_mean[:nn3].copy_(torch.from_numpy(avg_n))
+        return it
+
+    def center_on_mean(self):
+        """Centre with the mean already in d_mean (after align())."""
+        self.ctx.dev_center(self.d_x.data_ptr(), self.T, self.N, self.d_mean.data_ptr(),
+                            d_p32=self.d_p32.data_ptr(), stream=self._stream())
 
     def mean_and_center(self, have_colsum=False):
         s = self._stream()
@@ -129,8 +228,13 @@ class FramePipeline:
     # -- whole steps ------------------------------------------------------------------
     def run_device(self, d_coords):
         """One pass with the coordinate block already resident in HBM."""
-        self.com(d_coords, colsum=True)
-        self.mean_and_center(have_colsum=True)
+        if self.align_iterations > 0:
+            self.com(d_coords)
+            self.align()
+            self.center_on_mean()
+        else:
+            self.com(d_coords, colsum=True)
+            self.mean_and_center(have_colsum=True)
         self.gram()
         self.contact()
         self.reduce_and_epilogue()
@@ -160,7 +264,11 @@ class FramePipeline:
             self.com(self._stage[b], frames=nt, row0=t0)
             freed[b].record(main)
             it += 1
-        self.mean_and_center()
+        if self.align_iterations > 0:
+            self.align()
+            self.center_on_mean()
+        else:
+            self.mean_and_center()
         self.gram()
         self.contact()
         self.reduce_and_epilogue()
@@ -183,7 +291,13 @@ class FramePipeline:
         a SINGLE all-reduce of [G || D || s].
 
         Like run_host, returns numpy views of the pipeline's pinned output buffers: they are
-        overwritten by the next run_host / run_host_streamed call -- copy what must outlive it."""
+        overwritten by the next run_host / run_host_streamed call -- copy what must outlive it.
+
+        Only for pre-aligned input (align_iterations == 0): the alignment needs every frame before
+        the first rotation is known, so nothing downstream of it can overlap the transfer."""
+        if self.align_iterations > 0:
+            raise ValueError("run_host_streamed cannot overlap K2/K3 with the transfer when K7 alignment is on; "
+                             "use run_host")
         main = torch.cuda.current_stream(self.dev)
         side = self.k23_stream
         if self._stage is None:

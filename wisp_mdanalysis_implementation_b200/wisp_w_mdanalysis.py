@@ -114,7 +114,8 @@ class WispRun:
         import numpy as np
         from wisp_mdanalysis_implementation_b200 import _adapt, _lib
         p = self.p
-        ctx = _lib.default_context()
+        # config key ``gpus``: frames sharded over that many GPUs inside the one C call (0 = all)
+        ctx = _lib.default_context(gpus=p['gpus']) if p['gpus'] != 1 else _lib.default_context()
         align_idx = np.asarray(self.universe.select_atoms(p['alignment_selection']).indices, dtype=np.int32)
         node_ptr, atom_idx = _adapt.selection_to_csr(self.nodes)
         blocks = []
@@ -132,6 +133,9 @@ class WispRun:
                            which_map=which if p['weight_by_contact_map_boolean'] else 0,
                            atomic=p['substrate_node_definition'].upper() == 'ATOMIC',
                            convergence_threshold=1E-5, maximum_num_iterations=100)
+        for iteration, residual, analysis_RMSD in out['alignment_log']:
+            print('Iteration ', iteration, ': RMSD btw alignment landmarks: ', residual,
+                  ', RMSD btw Node Positions: ', analysis_RMSD)
         textio.savetxt(self.out + 'average_node_positions.dat', out['avg'],
                        header='Shape: nNodes x 3 (%d x 3)' % len(self.nodes))
         textio.savetxt(self.out + 'binary_contact_map.dat', out['binary'], fmt='%i')
