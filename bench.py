@@ -253,6 +253,7 @@ def main():
     ap.add_argument("--stress-pairs", type=int, default=200)
     ap.add_argument("--stress-paths", type=int, default=1000)
     ap.add_argument("--apsp-nodes", type=int, default=10000, help="configs[2] APSP size (0 = skip)")
+    ap.add_argument("--apsp-sharded-nodes", type=int, default=30000, help="configs[3] sharded APSP size (0 = skip)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -719,16 +720,34 @@ def main():
             t0 = time.perf_counter()
             ctx.paths_prepare(W)
             t_prep = time.perf_counter() - t0
-            n_ret, exp_tot = 0, 0
+            # all pairs in ONE batched call: the cutoff passes of every unfinished query share the kernels
             t0 = time.perf_counter()
-            for (a, b) in sel:
-                n_ret += len(ctx.paths_query([int(a)], [int(b)], args.stress_paths))
-                exp_tot += ctx.paths_stats()["expansions"]
+            qoff, plen, poff, pnodes = ctx.paths_query_pairs(sel, args.stress_paths, packed=True)
             t_q = time.perf_counter() - t0
+            st_b = ctx.paths_stats()
+            # one pair at a time (round 1's form), on a subset, for the comparison
+            sub = sel[:20]
+            t0 = time.perf_counter()
+            n_sub = 0
+            for (a, b) in sub:
+                n_sub += len(ctx.paths_query([int(a)], [int(b)], args.stress_paths))
+            t_seq = time.perf_counter() - t0
+            same = True
+            for k, (a, b) in enumerate(sub[:5]):
+                one = ctx.paths_query([int(a)], [int(b)], args.stress_paths)
+                lo, hi = int(qoff[k]), int(qoff[k + 1])
+                same &= (hi - lo == len(one)) and all(
+                    plen[lo + j] == one[j][0] and pnodes[poff[lo + j]:poff[lo + j + 1]].tolist() == one[j][1:]
+                    for j in range(hi - lo))
             extra["stress_c5"] = {"pairs": int(len(sel)), "paths_each": args.stress_paths,
                                   "prepare_ms": t_prep * 1e3, "queries_wall_ms": t_q * 1e3,
-                                  "paths_returned": int(n_ret), "expansions": int(exp_tot),
-                                  "expansions_per_s": exp_tot / max(t_q, 1e-9)}
+                                  "api": "wisp_paths_query_pairs (one batched call)",
+                                  "paths_returned": int(len(plen)), "expansions": int(st_b["expansions"]),
+                                  "expansions_per_s": st_b["expansions"] / max(t_q, 1e-9),
+                                  "kernel_rounds": int(st_b["final_cutoff"]), "enumerate_ms": st_b["enumerate_ms"],
+                                  "host_ms": st_b["host_ms"],
+                                  "one_pair_at_a_time_ms_per_pair": t_seq * 1e3 / max(1, len(sub)),
+                                  "batched_equals_one_at_a_time_on_5_pairs": bool(same)}
 
     # ---- configs[4] over all ranks: pairs dealt round-robin, one APSP per rank, gather on rank 0 ----
     if world > 1 and not args.no_paths and args.stress_pairs > 0:
@@ -741,13 +760,29 @@ def main():
         sel = cand5[rng.choice(len(cand5), size=min(args.stress_pairs, len(cand5)), replace=False)]
         barrier()
         t0 = time.perf_counter()
-        res = paths_sharded.query_pairs(ctx, W, sel, args.stress_paths)
+        res = paths_sharded.query_pairs(ctx, W, sel, args.stress_paths, packed=True)
         barrier()
         t_all = max_over_ranks((time.perf_counter() - t0) * 1e3)
         if rank == 0:
+            t0 = time.perf_counter()
+            first = res[0]                       # Python lists are built on demand, per query
+            t_unpack = (time.perf_counter() - t0) * 1e3
             extra["stress_c5_sharded"] = {"ranks": world, "pairs": int(len(sel)), "paths_each": args.stress_paths,
                                           "wall_ms_incl_apsp_and_gather": t_all,
-                                          "paths_returned": int(sum(len(r) for r in res))}
+                                          "paths_returned": res.total_paths(),
+                                          "unpack_one_query_to_lists_ms": t_unpack, "first_query_paths": len(first),
+                                          "gather": "four packed arrays per rank (no per-path Python objects)"}
+
+    # ---- configs[3]: 30,000-node row-block sharded Floyd-Warshall over all ranks (look-ahead), checked on
+    # this hardware against the single-GPU matrix at 8,192 nodes ----
+    if args.apsp_sharded_nodes > 0 and not args.no_paths:
+        from wisp_mdanalysis_implementation_b200.apsp_sharded import run_sharded_benchmark
+        del d_coords
+        torch.cuda.empty_cache()
+        resc4 = run_sharded_benchmark(ctx, args.apsp_sharded_nodes, rank, world)
+        if rank == 0:
+            resc4["frac_of_dispatch_ceiling"] = resc4["trelax_per_s"] / world / load_peaks()["minplus_dispatch_ceiling_trelax"]
+            extra["apsp_sharded_c4"] = resc4
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle timed on the box's host cores ----
     cpu_baseline = None

@@ -931,10 +931,13 @@ def test_pipeline_multi_shard_with_alignment(ctx, shards, n, t, apn):
     assert len(got["alignment_log"]) == len(one["alignment_log"]) >= 2
     assert got["alignment_log"][-1][1] <= 1e-5
     # sharded vs single GPU: same arithmetic up to the order of the frame sums
-    np.testing.assert_allclose(got["nodes"], one["nodes"], rtol=0, atol=1e-7)
-    np.testing.assert_allclose(got["avg"], one["avg"], rtol=0, atol=1e-7)
-    assert_corr_close(got["corr"], one["corr"], rel=1e-7)
-    np.testing.assert_allclose(got["avgdist"], one["avgdist"], rtol=1e-7)
+    # (the float32 initial landmark sum is chained over the shards in frame order: bit-identical start)
+    np.testing.assert_allclose(got["nodes"], one["nodes"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(got["avg"], one["avg"], rtol=0, atol=1e-9)
+    assert_corr_close(got["corr"], one["corr"], rel=1e-8)
+    # K3 sums FP32 per-frame distances in FP32 over 128-frame groups before promoting to FP64; the groups
+    # fall differently in a shard, so the mean distances agree to the stated 1e-6, not to FP64 rounding
+    np.testing.assert_allclose(got["avgdist"], one["avgdist"], rtol=1e-6)
     assert np.all(np.diagonal(got["corr"]) == 1.0) and np.array_equal(got["corr"], got["corr"].T)
     # and against the oracle's traj_alignment_and_averaging -> covariance -> Pearson / contact map
     nodes, avg = oracle.traj_alignment_and_averaging(coords.copy(), system.masses, system.node_ptr,
@@ -961,13 +964,13 @@ def test_pipeline_multi_shard_without_alignment_and_errors(ctx):
     got = mctx.pipeline(coords, system.masses, system.node_ptr, system.atom_idx, system.align_idx, cutoff=12.0, which_map=2)
     assert got["alignment_log"] == []
     assert_corr_close(got["corr"], one["corr"], rel=1e-9)
-    np.testing.assert_allclose(got["avgdist"], one["avgdist"], rtol=1e-9)
+    np.testing.assert_allclose(got["avgdist"], one["avgdist"], rtol=1e-6)
     np.testing.assert_allclose(got["w"], one["w"], rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(got["avg"], one["avg"], rtol=0, atol=1e-11)
     # fewer frames than shards: the call still works (shards beyond the frame count stay idle)
     tiny = mctx.pipeline(coords[:3], system.masses, system.node_ptr, system.atom_idx, system.align_idx, cutoff=12.0)
     ref = ctx.pipeline(coords[:3], system.masses, system.node_ptr, system.atom_idx, system.align_idx, cutoff=12.0)
-    np.testing.assert_allclose(tiny["avgdist"], ref["avgdist"], rtol=1e-9)
+    np.testing.assert_allclose(tiny["avgdist"], ref["avgdist"], rtol=1e-6)
     # a failing shard fails the call loudly instead of hanging the others
     with pytest.raises(_lib.WispError):
         bad = system.atom_idx.copy(); bad[5] = 10 ** 6
@@ -1038,3 +1041,21 @@ def test_get_paths_duplicate_pairs(ctx):
         got = ctx.get_paths(W, so, si, K)
         assert [p[1:] for p in got] == [[int(x) for x in p[1:]] for p in want], (so, si, K)
         assert [p[0] for p in got] == [float(p[0]) for p in want]
+
+
+def test_multirank_nccl_paths():
+    """The NCCL multi-rank paths on real ranks (needs >= 2 GPUs; skipped on a one-GPU box, where the same
+    host logic is covered by the emulated-shard tests above and, on the CPU, by test_sharding_gloo.py):
+    tools/multirank_check.py asserts sharded APSP == single GPU, FramePipeline == wisp_pipeline with K7
+    on, query_pairs == serial get_paths, in-process multi-GPU wisp_pipeline == single GPU."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)),
+                        "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        os.path.join(root, "tools", "multirank_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]

@@ -64,3 +64,27 @@ def test_large_matrix_speed(tmp_path):
     t_l = time.perf_counter() - t0
     assert np.array_equal(a, b)
     assert t_c < 10 and t_l < 10
+
+
+def test_loadtxt_rejects_ragged_rows_and_squeezes_single_row(tmp_path):
+    """a short row must not borrow numbers from the next line, extra values are an error,
+    and a one-row file comes back 1-D like np.loadtxt."""
+    import pytest
+    from wisp_mdanalysis_implementation_b200 import _lib
+    f = tmp_path / "ragged.dat"
+    f.write_text("1.0 2.0 3.0\n4.0 5.0\n6.0 7.0 8.0 9.0\n")
+    with pytest.raises(_lib.WispError):
+        _lib.loadtxt(str(f))
+    f.write_text("1.0 2.0 3.0\n4.0 5.0 6.0 7.0\n")
+    with pytest.raises(_lib.WispError):
+        _lib.loadtxt(str(f))
+    f.write_text("1.0 2.0 x\n")
+    with pytest.raises(_lib.WispError):
+        _lib.loadtxt(str(f))
+    f.write_text("# header\n1.5e+00 -2.5e-01 inf nan +3.0\n")
+    got = _lib.loadtxt(str(f))
+    want = np.loadtxt(str(f))
+    assert got.shape == want.shape == (5,)
+    assert np.array_equal(got, want, equal_nan=True)
+    f.write_text("1 2\n3 4\n\n")
+    assert np.array_equal(_lib.loadtxt(str(f)), np.array([[1.0, 2.0], [3.0, 4.0]]))

@@ -510,7 +510,9 @@ def loadtxt(path):
     out = np.empty((rows.value, cols.value), dtype=np.float64)
     if lib().wisp_loadtxt_f64(os.fsencode(path), _ptr(out), out.size, C.byref(rows), C.byref(cols)) != 0:
         raise WispError(lib().wisp_last_error().decode())
-    return out[:, 0].copy() if cols.value == 1 else out
+    if cols.value == 1:
+        return out[:, 0].copy()
+    return out[0].copy() if rows.value == 1 else out      # np.loadtxt squeezes a single row too
 
 
 def node_ld(n_nodes):

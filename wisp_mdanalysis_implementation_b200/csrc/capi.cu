@@ -160,6 +160,7 @@ int upload_nodes(wisp_ctx* ctx, const double* nodes, int64_t T, int N, double** 
     void* p = nullptr;
     WISP_TRY(wisp_scratch(ctx, SCR_X, (size_t)Tpad * ld * 8, &p));
     cudaStream_t st = ctx->stream;
+    ctx->i8_stats_x = nullptr;                 // new content: statistics of an earlier centring pass are void
     WISP_CUDA(cudaMemsetAsync(p, 0, (size_t)Tpad * ld * 8, st));
     WISP_CUDA(cudaMemcpy2DAsync(p, (size_t)ld * 8, nodes, (size_t)3 * N * 8, (size_t)3 * N * 8, (size_t)T,
                                 cudaMemcpyHostToDevice, st));

@@ -77,6 +77,7 @@ struct wisp_ctx {
     int64_t i8_stats_T = 0;
     int i8_stats_parts = 0;
     cudaStream_t i8_stats_stream = nullptr;
+    int64_t i8_stats_launch = -1;
     // grow-only scratch buffers, keyed by slot
     DevBuf scratch[64];
     // get_paths results
@@ -123,8 +124,12 @@ int launch_colsum_finish(wisp_ctx* ctx, const double* d_part, int n_rows, int64_
                          double* d_colsum, cudaStream_t st);
 int launch_colsum_f32(wisp_ctx* ctx, const float* d_x, int64_t T, int64_t ld, int64_t ncols,
                       double* d_colsum, cudaStream_t st);
-// sums a host vector over the frame shards (in shard order; float32-chained when f32_chain)
-typedef std::function<int(double* buf, size_t n, bool f32_chain)> AlignReduce;
+// Cross-shard combination of small host vectors during the alignment.  f32_chain == false: buf <- sum
+// of buf over the frame shards, in shard order.  f32_chain == true: the shards run `step` one after the
+// other in frame order, each on the running totals left by its predecessor (zeros for the first), and
+// buf ends as the grand totals on every shard.
+typedef std::function<int(double* h_inout)> AlignStep;
+typedef std::function<int(double* buf, size_t n, bool f32_chain, const AlignStep& step)> AlignReduce;
 int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* d_nodes, int64_t ld,
                             int N, int64_t T, double threshold, int max_iter, double* d_work,
                             double* h_avg_nodes, double* log, int* n_iter_out, cudaStream_t st,

@@ -274,8 +274,10 @@ int launch_center(wisp_ctx* ctx, double* d_x, int64_t T, int64_t ld, int64_t nco
         ctx->i8_stats_T = T;
         ctx->i8_stats_parts = parts;
         ctx->i8_stats_stream = st;
+        ctx->i8_stats_launch = ctx->launches;      // valid only while no other launch of this library follows
         return 0;
     }
+    ctx->i8_stats_x = nullptr;                     // plain centring: no statistics for this content
     const int gx = (int)((ncols + 255) / 256);
     const int gy = (int)std::min<int64_t>(T, std::max<int64_t>(1, (int64_t)ctx->sm_count * 16 / gx));
     center_kernel<<<dim3(gx, gy), 256, 0, st>>>(d_x, T, ld, ncols, d_mean);

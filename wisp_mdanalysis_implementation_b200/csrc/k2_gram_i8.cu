@@ -358,8 +358,12 @@ int launch_gram_i8(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int 
         for (int p = 0; p < 4; ++p)
             WISP_CUDA(cudaMemsetAsync(planes + ((size_t)p * rows_total + 3 * T) * n_pad, 0,
                                       (size_t)(rows_total - 3 * T) * n_pad, st));
+    // the statistics left by the centring pass are trusted only if this Gram is the very next launch of
+    // the library on this context, on the same block and stream (any upload / COM / rotation / plain
+    // centring in between bumps the launch counter or clears the pointer); otherwise X is read once more
     const bool have_stats = ctx->i8_stats_x == (const void*)d_x && ctx->i8_stats_T == T &&
-                            ctx->i8_stats_stream == st && ld == 3 * (int64_t)n_pad;
+                            ctx->i8_stats_stream == st && ld == 3 * (int64_t)n_pad &&
+                            ctx->i8_stats_launch == ctx->launches;
     ctx->i8_stats_x = nullptr;                                   // single use
     // max error / sqrt(G_ii G_jj) ~ 6.5e-10 / (sqrt(rows) * rho_i * rho_j), rho^2 = mean(x^2) / max(x^2);
     // hold it below 5e-10 (half the 1e-9 absolute bar on C, tests/test_gpu_parity.py)

@@ -132,22 +132,25 @@ align_rotate_kernel(float* __restrict__ align, int n_align, const double* __rest
 }
 
 // np.sum(float32 array, axis=0) of the reference (:86): sequential float32 adds down the frames.
-// The raw float32 sum is returned (as a double holding a float), so that frame-sharded callers can
-// chain the shards' sums in float32 before the single float32 division by nSteps.
+// `inout` holds the running float32 totals of all EARLIER frames on entry (zeros for the first frame
+// block) and the totals including this block on exit (doubles holding floats): frame shards chain
+// their blocks in frame order and reproduce the single sequential sum bit for bit.
 __global__ void sum32_sequential_kernel(const float* __restrict__ a, int64_t T, int64_t ncols,
-                                        double* __restrict__ out) {
+                                        double* __restrict__ inout) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncols) return;
-    float s = 0.f;
+    float s = (float)inout[c];
     for (int64_t t = 0; t < T; ++t) s = __fadd_rn(s, a[t * ncols + c]);
-    out[c] = (double)s;
+    inout[c] = (double)s;
 }
 
 }  // namespace
 
 // ---- building blocks (also the device-level C ABI: wisp_dev_align_sums / wisp_dev_align_iter) ----
 // d_sums [na3 + nn3]: first the landmark column sums, then the node column sums of this frame block.
-// first == true: landmark sums as the reference's sequential float32 sums (initial average, :86).
+// first == true: landmark sums as the reference's sequential float32 sums (initial average, :86):
+// d_sums[0, na3) must hold the running totals of the earlier frame blocks on entry (zeros for the
+// first block) and holds the totals including this block on exit.
 int launch_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_nodes, int64_t ld,
                       int N, int64_t T, bool first, double* d_sums, cudaStream_t st) {
     const int64_t na3 = 3 * (int64_t)n_align, nn3 = 3 * (int64_t)N;
@@ -175,8 +178,8 @@ int launch_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double
 
 // d_align: float32 [T][n_align][3] (in/out); d_nodes: pitched float64 trajectory (in/out), T = the
 // frames of THIS shard, T_total = all frames.  `reduce` (may be empty) sums a host vector over the
-// frame shards in shard order, float32-chained when its last argument is true; every shard then
-// takes the same decisions from the same numbers.  d_work: [2 * round_up(na3,32) + round_up(nn3,32)].
+// frame shards in shard order (or, for the float32 chain, runs the shards' steps one after the other in
+// frame order); every shard then takes the same decisions from the same numbers.  d_work: [2 * round_up(na3,32) + round_up(nn3,32)].
 // Returns iterations run; log gets (iteration, residual, node RMSD) triples.
 int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* d_nodes, int64_t ld,
                             int N, int64_t T, double threshold, int max_iter, double* d_work,
@@ -187,10 +190,26 @@ int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* 
     double* d_avgA = d_work;                 // [na3]
     double* d_sums = d_avgA + round_up(na3, 32);   // [na3 + nn3]
     std::vector<double> avgA(na3), avgN(nn3), sums(na3 + nn3);
-    WISP_TRY(launch_align_sums(ctx, d_align, n_align, d_nodes, ld, N, T, true, d_sums, st));
-    WISP_CUDA(cudaMemcpyAsync(sums.data(), d_sums, (na3 + nn3) * 8, cudaMemcpyDeviceToHost, st));
-    WISP_CUDA(cudaStreamSynchronize(st));
-    if (reduce) { WISP_TRY(reduce(sums.data(), (size_t)na3, true)); WISP_TRY(reduce(sums.data() + na3, (size_t)nn3, false)); }
+    // initial landmark totals: float32, chained over the shards in frame order (`reduce` with
+    // f32_chain = true hands this shard the totals of the earlier shards, runs `step`, and returns the
+    // grand totals); node sums: plain float64 sums combined afterwards
+    auto step = [&](double* h_inout) -> int {
+        WISP_CUDA(cudaMemcpyAsync(d_sums, h_inout, na3 * 8, cudaMemcpyHostToDevice, st));
+        WISP_TRY(launch_align_sums(ctx, d_align, n_align, d_nodes, ld, N, T, true, d_sums, st));
+        WISP_CUDA(cudaMemcpyAsync(sums.data(), d_sums, (na3 + nn3) * 8, cudaMemcpyDeviceToHost, st));
+        WISP_CUDA(cudaStreamSynchronize(st));
+        memcpy(h_inout, sums.data(), na3 * 8);
+        return 0;
+    };
+    if (reduce) {
+        std::vector<double> chain(na3, 0.0);
+        WISP_TRY(reduce(chain.data(), (size_t)na3, true, step));
+        memcpy(sums.data(), chain.data(), na3 * 8);
+        WISP_TRY(reduce(sums.data() + na3, (size_t)nn3, false, AlignStep()));
+    } else {
+        std::vector<double> chain(na3, 0.0);
+        WISP_TRY(step(chain.data()));
+    }
     for (int64_t k = 0; k < na3; ++k) avgA[k] = (double)((float)sums[k] / (float)T_total);   // float32 mean (:86)
     for (int64_t k = 0; k < nn3; ++k) avgN[k] = sums[na3 + k] / (double)T_total;
     WISP_CUDA(cudaMemcpyAsync(d_avgA, avgA.data(), na3 * 8, cudaMemcpyHostToDevice, st));
@@ -201,7 +220,7 @@ int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* 
         WISP_TRY(launch_align_sums(ctx, d_align, n_align, d_nodes, ld, N, T, false, d_sums, st));
         WISP_CUDA(cudaMemcpyAsync(sums.data(), d_sums, (na3 + nn3) * 8, cudaMemcpyDeviceToHost, st));
         WISP_CUDA(cudaStreamSynchronize(st));
-        if (reduce) WISP_TRY(reduce(sums.data(), (size_t)(na3 + nn3), false));
+        if (reduce) WISP_TRY(reduce(sums.data(), (size_t)(na3 + nn3), false, AlignStep()));
         double ra = 0.0, rn = 0.0;
         for (int64_t k = 0; k < na3; ++k) { const double v = sums[k] / (double)T_total; const double d = avgA[k] - v; ra += d * d; avgA[k] = v; }
         for (int64_t k = 0; k < nn3; ++k) { const double v = sums[na3 + k] / (double)T_total; const double d = avgN[k] - v; rn += d * d; avgN[k] = v; }

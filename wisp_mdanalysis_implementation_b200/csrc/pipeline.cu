@@ -78,21 +78,30 @@ struct Shared {
 };
 
 // sum `buf` over the shards in shard order; every shard ends with the same numbers
-int reduce_host(Shared& S, int r, double* buf, size_t n, bool f32_chain) {
+int reduce_host(Shared& S, int r, double* buf, size_t n) {
     if (S.R == 1) return 0;
     S.slots[r].assign(buf, buf + n);
     WISP_CHECK(S.bar.wait(), "pipeline: another shard failed");
     for (size_t k = 0; k < n; ++k) {
-        if (f32_chain) {
-            float s = (float)S.slots[0][k];
-            for (int q = 1; q < S.R; ++q) s += (float)S.slots[q][k];
-            buf[k] = (double)s;
-        } else {
-            double s = S.slots[0][k];
-            for (int q = 1; q < S.R; ++q) s += S.slots[q][k];
-            buf[k] = s;
-        }
+        double s = S.slots[0][k];
+        for (int q = 1; q < S.R; ++q) s += S.slots[q][k];
+        buf[k] = s;
     }
+    WISP_CHECK(S.bar.wait(), "pipeline: another shard failed");
+    return 0;
+}
+
+// the shards run `step` one after the other in frame order, each starting from its predecessor's totals
+int chain_host(Shared& S, int r, double* buf, size_t n, const AlignStep& step) {
+    for (int q = 0; q < S.R; ++q) {
+        if (q == r) {
+            if (q > 0) memcpy(buf, S.slots[q - 1].data(), n * 8);
+            WISP_TRY(step(buf));
+            S.slots[r].assign(buf, buf + n);
+        }
+        WISP_CHECK(S.bar.wait(), "pipeline: another shard failed");
+    }
+    memcpy(buf, S.slots[S.R - 1].data(), n * 8);
     WISP_CHECK(S.bar.wait(), "pipeline: another shard failed");
     return 0;
 }
@@ -135,7 +144,9 @@ int shard_body(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
     bool have_mean = false;
     if (a.max_align_iterations > 0) {
         int n_iter = 0;
-        AlignReduce red = [&](double* buf, size_t n, bool f32) { return reduce_host(S, r, buf, n, f32); };
+        AlignReduce red = [&](double* buf, size_t n, bool f32, const AlignStep& step) {
+            return f32 ? chain_host(S, r, buf, n, step) : reduce_host(S, r, buf, n);
+        };
         WISP_TRY(run_iterative_alignment(ctx, d_align, a.n_align, d_x, ld, N, Tl, a.align_threshold,
                                          a.max_align_iterations, d_work, mean.data(), r == 0 ? a.out_log : nullptr,
                                          &n_iter, st, a.T, R > 1 ? red : AlignReduce()));
@@ -147,7 +158,7 @@ int shard_body(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
         WISP_TRY(launch_colsum(ctx, d_x, Tl, ld, nn3, d_sum, st));
         WISP_CUDA(cudaMemcpyAsync(mean.data(), d_sum, nn3 * 8, cudaMemcpyDeviceToHost, st));
         WISP_CUDA(cudaStreamSynchronize(st));
-        WISP_TRY(reduce_host(S, r, mean.data(), (size_t)nn3, false));
+        WISP_TRY(reduce_host(S, r, mean.data(), (size_t)nn3));
         for (auto& v : mean) v /= (double)a.T;
     }
     if (r == 0 && a.out_avg) memcpy(a.out_avg, mean.data(), nn3 * 8);

@@ -99,55 +99,76 @@ extern "C" int wisp_loadtxt_f64(const char* path, double* out, int64_t capacity,
     const size_t got = fread(&text[0], 1, (size_t)size, f);
     fclose(f);
     WISP_CHECK((long long)got == size, "loadtxt: short read on %s", path);
-    // line starts
-    std::vector<size_t> lines;
+    // data lines as [start, end): every row is parsed strictly inside its own line, so a short row can
+    // never borrow numbers from the next one (strtod alone skips '\n' as white space)
+    std::vector<std::pair<size_t, size_t>> lines;
     size_t pos = 0;
     while (pos < text.size()) {
         size_t end = text.find('\n', pos);
         if (end == std::string::npos) end = text.size();
         size_t p = pos;
         while (p < end && (text[p] == ' ' || text[p] == '\t' || text[p] == '\r')) ++p;
-        if (p < end && text[p] != '#') lines.push_back(pos);
+        if (p < end && text[p] != '#') lines.push_back({p, end});
         pos = end + 1;
     }
+    // one value: locale-independent (std::from_chars), accepts what np.savetxt writes (incl. inf / nan,
+    // a leading '+'); returns the position after the value or nullptr
+    auto parse = [](const char* p, const char* e, double* v) -> const char* {
+        while (p < e && (*p == ' ' || *p == '\t' || *p == ',' || *p == '\r')) ++p;
+        if (p >= e) return nullptr;
+        if (*p == '+') ++p;
+        const auto r = std::from_chars(p, e, *v);
+        if (r.ec != std::errc() && r.ec != std::errc::result_out_of_range) return nullptr;
+        return r.ptr;
+    };
+    auto count_cols = [&](size_t a0, size_t a1) -> int64_t {
+        const char *p = text.c_str() + a0, *e = text.c_str() + a1;
+        int64_t n = 0;
+        double v;
+        for (;;) {
+            const char* q = parse(p, e, &v);
+            if (!q) break;
+            ++n;
+            p = q;
+        }
+        while (p < e && (*p == ' ' || *p == '\t' || *p == ',' || *p == '\r')) ++p;
+        return p == e ? n : -1;          // trailing junk: not a numeric row
+    };
     const int64_t rows = (int64_t)lines.size();
     int64_t cols = 0;
     if (rows) {
-        const char* p = text.c_str() + lines[0];
-        const char* e = text.c_str() + std::min(text.find('\n', lines[0]), text.size());
-        while (p < e) {
-            char* q;
-            strtod(p, &q);
-            if (q == p) break;
-            ++cols;
-            p = q;
-            while (p < e && (*p == ' ' || *p == '\t' || *p == ',' || *p == '\r')) ++p;
-        }
+        cols = count_cols(lines[0].first, lines[0].second);
+        WISP_CHECK(cols > 0, "loadtxt: non-numeric first row in %s", path);
     }
     *rows_out = rows;
     *cols_out = cols;
     if (!out) return 0;
     WISP_CHECK(capacity >= rows * cols, "loadtxt: buffer too small (%lld < %lld)", (long long)capacity, (long long)(rows * cols));
     const int nt = n_threads_for(rows * cols);
-    std::vector<int> bad(nt, 0);
+    std::vector<int64_t> bad(nt, -1);
     std::vector<std::thread> th;
     for (int t = 0; t < nt; ++t) {
         const int64_t r0 = rows * t / nt, r1 = rows * (t + 1) / nt;
         th.emplace_back([&, t, r0, r1]() {
             for (int64_t r = r0; r < r1; ++r) {
-                const char* p = text.c_str() + lines[r];
-                for (int64_t c = 0; c < cols; ++c) {
-                    char* q;
-                    const double v = strtod(p, &q);
-                    if (q == p) { bad[t] = 1; return; }
-                    out[r * cols + c] = v;
+                const char *p = text.c_str() + lines[r].first, *e = text.c_str() + lines[r].second;
+                int64_t c = 0;
+                double v;
+                for (;;) {
+                    const char* q = parse(p, e, &v);
+                    if (!q) break;
+                    if (c < cols) out[r * cols + c] = v;
+                    ++c;
                     p = q;
-                    while (*p == ' ' || *p == '\t' || *p == ',' || *p == '\r') ++p;
                 }
+                while (p < e && (*p == ' ' || *p == '\t' || *p == ',' || *p == '\r')) ++p;
+                if (c != cols || p != e) { bad[t] = r; return; }      // too few, too many, or junk
             }
         });
     }
     for (auto& x : th) x.join();
-    for (int t = 0; t < nt; ++t) WISP_CHECK(!bad[t], "loadtxt: ragged or non-numeric row in %s", path);
+    for (int t = 0; t < nt; ++t)
+        WISP_CHECK(bad[t] < 0, "loadtxt: data row %lld of %s does not hold exactly %lld numbers (ragged or non-numeric row)",
+                   (long long)bad[t] + 1, path, (long long)cols);
     return 0;
 }

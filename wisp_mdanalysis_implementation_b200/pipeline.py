@@ -158,22 +158,23 @@ class FramePipeline:
         s = self._stream()
         na3, nn3 = 3 * self.n_align, 3 * self.N
         world = torch.distributed.get_world_size(self.group) if sharding.is_distributed(self.group) else 1
-        self.ctx.dev_align_sums(self.d_align.data_ptr(), self.n_align, self.d_x.data_ptr(), self.T, self.N, True,
-                                self.d_align_sums.data_ptr(), stream=s)
+        # initial landmark totals (:86): sequential float32 sums, chained over the ranks in frame order --
+        # rank q continues from the totals rank q-1 left -- so the result is the single sequential sum
+        self.d_align_sums.zero_()
+        for q in range(world):
+            if q == (torch.distributed.get_rank(self.group) if world > 1 else 0):
+                self.ctx.dev_align_sums(self.d_align.data_ptr(), self.n_align, self.d_x.data_ptr(), self.T, self.N,
+                                        True, self.d_align_sums.data_ptr(), stream=s)
+            if world > 1:
+                src = torch.distributed.get_global_rank(self.group, q) if self.group is not None else q
+                torch.distributed.broadcast(self.d_align_sums[:na3], src=src, group=self.group)
         if world > 1:
-            # the initial landmark average is a float32 sum chained over the ranks in rank order
-            allsums = torch.empty((world, na3 + nn3), dtype=torch.float64, device=self.dev)
-            torch.distributed.all_gather_into_tensor(allsums, self.d_align_sums, group=self.group)
-            h = allsums.cpu().numpy()
-            sa = h[0, :na3].astype(np.float32)
-            for r in range(1, world):
-                sa = sa + h[r, :na3].astype(np.float32)
-            sn = h[0, na3:].copy()
-            for r in range(1, world):
-                sn += h[r, na3:]
+            node_sums = self.d_align_sums[na3:].clone()
+            torch.distributed.all_reduce(node_sums, group=self.group)
+            sn = node_sums.cpu().numpy()
         else:
-            h = self.d_align_sums.cpu().numpy()
-            sa, sn = h[:na3].astype(np.float32), h[na3:].copy()
+            sn = self.d_align_sums[na3:].cpu().numpy().copy()
+        sa = self.d_align_sums[:na3].cpu().numpy().astype(np.float32)
         avg_a = (sa / np.float32(self.T_total)).astype(np.float64)
         avg_n = sn / float(self.T_total)
         self.alignment_log = []
