@@ -364,10 +364,11 @@ def main():
         b7.record()
         torch.cuda.synchronize()
         k7_ms = a7.elapsed_time(b7)
-        # per frame and iteration: landmarks read + written (float32), nodes read + written (float64),
-        # then both read again for the column sums; the first (float32-chained) sums read both once more
+        # per frame and iteration: landmarks read (solve), landmarks read + written (float32), nodes read +
+        # written (float64), the new column sums come out of the same pass; the initial (float32-chained)
+        # sums read both arrays once
         n_al = len(system.align_idx)
-        k7_bytes = T_local * ((n_it * 3 + 1) * (12.0 * n_al) + (n_it * 3 + 1) * (24.0 * N))
+        k7_bytes = T_local * ((n_it * 3 + 1) * (12.0 * n_al) + (n_it * 2 + 1) * (24.0 * N))
         k7 = {"ms": k7_ms, "iterations": n_it, "ms_per_iteration": k7_ms / max(1, n_it), "bound": "hbm",
               "achieved_gbs": k7_bytes / (k7_ms * 1e-3) / 1e9, "peak_gbs": load_peaks()["hbm_gbs"],
               "frac": k7_bytes / (k7_ms * 1e-3) / 1e9 / load_peaks()["hbm_gbs"],

@@ -198,12 +198,13 @@ int wisp_dev_com_align(wisp_ctx* ctx, wisp_com_plan* plan, const float* d_coords
 /* K7 building blocks for a frame-sharded alignment loop (trajectory_analysis_functions.py:86-126).
  * wisp_dev_align_sums: d_sums [3 n_align + 3 N] = column sums of this rank's landmarks, then of its
  * node rows; first != 0: the landmark sums are the reference's sequential float32 sums (:86).
- * wisp_dev_align_rotate: rotate every frame of this rank onto d_avg_align [3 n_align] in place.
+ * wisp_dev_align_rotate: rotate every frame of this rank onto d_avg_align [3 n_align] in place; d_sums
+ * (may be NULL) receives the column sums of the rotated block in the same layout, from the same pass.
  * The caller all-reduces the sums, divides by the total frame count and tests the RMSD (:118). */
 int wisp_dev_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_nodes,
                         int64_t T, int N, int first, double* d_sums, void* stream);
 int wisp_dev_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align,
-                          double* d_nodes, int64_t T, int N, void* stream);
+                          double* d_nodes, int64_t T, int N, double* d_sums, void* stream);
 /* X <- X - mean (in place), mean [ld]; pad columns / rows are left at zero.  When d_p32 is
  * not NULL it also receives the FP32 tile-referenced copy K3 reads:
  * float [T][wisp_gram_ld(N)/128][3][128], value = float(x - mean of the tile's middle node). */

@@ -66,7 +66,7 @@ SIGNATURES = {
     "wisp_dev_com": (_int, [_c_ctx, _P, _P, _i64, _int, _P, _P, _P]),
     "wisp_dev_com_align": (_int, [_c_ctx, _P, _P, _i64, _int, _P, _P, _P, _P]),
     "wisp_dev_align_sums": (_int, [_c_ctx, _P, _int, _P, _i64, _int, _int, _P, _P]),
-    "wisp_dev_align_rotate": (_int, [_c_ctx, _P, _int, _P, _P, _i64, _int, _P]),
+    "wisp_dev_align_rotate": (_int, [_c_ctx, _P, _int, _P, _P, _i64, _int, _P, _P]),
     "wisp_dev_center": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P]),
     "wisp_dev_colsum": (_int, [_c_ctx, _P, _i64, _int, _P, _P]),
     "wisp_dev_gram": (_int, [_c_ctx, _P, _i64, _i64, _int, _int, _P, _P]),
@@ -413,9 +413,9 @@ class Context:
         self._check(self._lib.wisp_dev_align_sums(self._ctx, _ptr(d_align), n_align, _ptr(d_nodes), T, N,
                                                   int(bool(first)), _ptr(d_sums), _ptr(stream)))
 
-    def dev_align_rotate(self, d_align, n_align, d_avg_align, d_nodes, T, N, stream=None):
+    def dev_align_rotate(self, d_align, n_align, d_avg_align, d_nodes, T, N, d_sums=None, stream=None):
         self._check(self._lib.wisp_dev_align_rotate(self._ctx, _ptr(d_align), n_align, _ptr(d_avg_align),
-                                                    _ptr(d_nodes), T, N, _ptr(stream)))
+                                                    _ptr(d_nodes), T, N, _ptr(d_sums), _ptr(stream)))
 
     def dev_center(self, d_nodes, T, N, d_mean, d_p32=None, stream=None):
         self._check(self._lib.wisp_dev_center(self._ctx, _ptr(d_nodes), T, N, _ptr(d_mean),

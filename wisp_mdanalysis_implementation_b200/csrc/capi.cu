@@ -534,10 +534,10 @@ extern "C" int wisp_dev_align_sums(wisp_ctx* ctx, const float* d_align, int n_al
 }
 
 extern "C" int wisp_dev_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align,
-                                     double* d_nodes, int64_t T, int N, void* stream) {
+                                     double* d_nodes, int64_t T, int N, double* d_sums, void* stream) {
     WISP_CHECK(ctx && d_align && d_avg_align && d_nodes && T > 0, "dev_align_rotate: bad argument");
     return launch_align_rotate(ctx, d_align, n_align, d_avg_align, d_nodes, wisp_node_ld(N), N, T,
-                               wisp_stream(ctx, stream));
+                               wisp_stream(ctx, stream), d_sums);
 }
 
 extern "C" int wisp_dev_center(wisp_ctx* ctx, double* d_nodes, int64_t T, int N, const double* d_mean,

@@ -100,7 +100,7 @@ enum ScratchSlot {
     SCR_APSP_D, SCR_APSP_P, SCR_ARENA, SCR_ALIGN, SCR_P32,
     SCR_MISC0, SCR_MISC1, SCR_MISC2, SCR_MISC3, SCR_MISC4, SCR_MISC5, SCR_MISC6, SCR_MISC7,
     SCR_MISC8, SCR_MISC9, SCR_I8_PLANES, SCR_I8_SMALL, SCR_I8_PART, SCR_I8_STATS, SCR_APSP_R, SCR_APSP_T, SCR_APSP_M,
-    SCR_PIPE_G, SCR_PIPE_D, SCR_PIPE_OUT, SCR_PIPE_STAGE0, SCR_PIPE_STAGE_LAST = SCR_PIPE_STAGE0 + 15, SCR_COUNT
+    SCR_ALIGN_ROT, SCR_ALIGN_PART, SCR_PIPE_G, SCR_PIPE_D, SCR_PIPE_OUT, SCR_PIPE_STAGE0, SCR_PIPE_STAGE_LAST = SCR_PIPE_STAGE0 + 15, SCR_COUNT
 };
 
 // ---- kernel launchers (one per .cu) -------------------------------------------------------
@@ -137,7 +137,7 @@ int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* 
 int launch_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_nodes, int64_t ld,
                       int N, int64_t T, bool first, double* d_sums, cudaStream_t st);
 int launch_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align, double* d_nodes,
-                        int64_t ld, int N, int64_t T, cudaStream_t st);
+                        int64_t ld, int N, int64_t T, cudaStream_t st, double* d_sums = nullptr);
 int launch_colsum(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int64_t ncols,
                   double* d_colsum, cudaStream_t st);
 // d_p32 != nullptr: also write the FP32 tile-referenced copy [T][n_tiles][3][128] for K3

@@ -368,9 +368,32 @@ contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
     }
 
     // ---------------- compute warps ----------------
+    // Thread -> pair block (8 i nodes x 4 j nodes).  Off-diagonal tiles: i nodes 4ti..4ti+3 and
+    // 64+4ti..+3, j nodes 4tj..4tj+3 (a warp = 8 j columns x all 128 i rows); warps whose 8 columns lie
+    // beyond the last real node (the padded part of the last tile) have nothing to do.  Diagonal tiles:
+    // the warps form a 4 x 4 grid of 32 x 32 sub-blocks and the 6 sub-blocks strictly below the diagonal
+    // (whose pairs the sub-blocks above it already cover) are idle.  Idle warps only keep the stage
+    // hand-shake going; the MUFU pipe of the SM is then shared by fewer warps, so the CTA ends earlier:
+    // 8.5 % less K3 time at C2 (16 diagonal tiles x 6/16 + 15 last-column tiles x 48/128).
     constexpr int JH = 2;
-    const int ti = tid & 15;     // i nodes: 4ti..4ti+3 and 64+4ti..64+4ti+3
-    const int tj = tid >> 4;     // j nodes: 4tj..4tj+3
+    int ib0, ib1, jb0;
+    bool idle;
+    {
+        const int w = tid >> 5, lane = tid & 31;
+        const int valid_i = min(kTile, N - kTile * bi), valid_j = min(kTile, N - kTile * bj);
+        if (bi == bj) {
+            const int wr = w >> 2, wc = w & 3;
+            ib0 = 32 * wr + 8 * (lane >> 3);
+            ib1 = ib0 + 4;
+            jb0 = 32 * wc + 4 * (lane & 7);
+            idle = wr > wc || 32 * wr >= valid_i || 32 * wc >= valid_j;
+        } else {
+            ib0 = 4 * (tid & 15);
+            ib1 = 64 + ib0;
+            jb0 = 4 * (tid >> 4);
+            idle = 8 * w >= valid_j;
+        }
+    }
     f32x2 acc[8][JH];
 #pragma unroll
     for (int a = 0; a < 8; ++a)
@@ -383,6 +406,11 @@ contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
         const int64_t f0 = f_begin + (int64_t)ch * kWsFC;
         const int nf = (int)((f_end - f0) < kWsFC ? (f_end - f0) : kWsFC);
         ws_mbar_wait(&sm.full[slot], ph);
+        if (idle) {
+            __syncwarp();
+            if ((tid & 31) == 0) ws_mbar_arrive(&sm.empty[slot]);
+            continue;
+        }
         const float* si = &sm.ring[slot][0][0][0][0];
         const float* sj = &sm.ring[slot][1][0][0][0];
 #pragma unroll UNROLL
@@ -392,21 +420,21 @@ contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
             {
                 const float* fi = si + fl * kTileFloats;
                 const float* fj = sj + fl * kTileFloats;
-                const float4 t0 = *reinterpret_cast<const float4*>(fi + 4 * ti);
-                const float4 t1 = *reinterpret_cast<const float4*>(fi + 64 + 4 * ti);
+                const float4 t0 = *reinterpret_cast<const float4*>(fi + ib0);
+                const float4 t1 = *reinterpret_cast<const float4*>(fi + ib1);
                 ax[0] = t0.x; ax[1] = t0.y; ax[2] = t0.z; ax[3] = t0.w;
                 ax[4] = t1.x; ax[5] = t1.y; ax[6] = t1.z; ax[7] = t1.w;
-                const float4 u0 = *reinterpret_cast<const float4*>(fi + kTile + 4 * ti);
-                const float4 u1 = *reinterpret_cast<const float4*>(fi + kTile + 64 + 4 * ti);
+                const float4 u0 = *reinterpret_cast<const float4*>(fi + kTile + ib0);
+                const float4 u1 = *reinterpret_cast<const float4*>(fi + kTile + ib1);
                 ay[0] = u0.x; ay[1] = u0.y; ay[2] = u0.z; ay[3] = u0.w;
                 ay[4] = u1.x; ay[5] = u1.y; ay[6] = u1.z; ay[7] = u1.w;
-                const float4 v0 = *reinterpret_cast<const float4*>(fi + 2 * kTile + 4 * ti);
-                const float4 v1 = *reinterpret_cast<const float4*>(fi + 2 * kTile + 64 + 4 * ti);
+                const float4 v0 = *reinterpret_cast<const float4*>(fi + 2 * kTile + ib0);
+                const float4 v1 = *reinterpret_cast<const float4*>(fi + 2 * kTile + ib1);
                 az[0] = v0.x; az[1] = v0.y; az[2] = v0.z; az[3] = v0.w;
                 az[4] = v1.x; az[5] = v1.y; az[6] = v1.z; az[7] = v1.w;
-                const float4 w0 = *reinterpret_cast<const float4*>(fj + 4 * tj);
-                const float4 w1 = *reinterpret_cast<const float4*>(fj + kTile + 4 * tj);
-                const float4 w2 = *reinterpret_cast<const float4*>(fj + 2 * kTile + 4 * tj);
+                const float4 w0 = *reinterpret_cast<const float4*>(fj + jb0);
+                const float4 w1 = *reinterpret_cast<const float4*>(fj + kTile + jb0);
+                const float4 w2 = *reinterpret_cast<const float4*>(fj + 2 * kTile + jb0);
                 bx[0] = pack2(w0.x, w0.y); bx[1] = pack2(w0.z, w0.w);
                 by[0] = pack2(w1.x, w1.y); by[1] = pack2(w1.z, w1.w);
                 bz[0] = pack2(w2.x, w2.y); bz[1] = pack2(w2.z, w2.w);
@@ -442,11 +470,13 @@ contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
         }
     }
 
+    // idle threads store the zeros their totals were initialised with: the partial tile is always
+    // completely defined (the entries below the diagonal of a diagonal tile are never read)
     double* o = out + (size_t)seg * out_ld * out_ld;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
-        const int64_t row = (int64_t)kTile * bi + ((a < 4) ? (4 * ti + a) : (64 + 4 * ti + (a - 4)));
-        const int64_t col0 = (int64_t)kTile * bj + 4 * tj;
+        const int64_t row = (int64_t)kTile * bi + ((a < 4) ? (ib0 + a) : (ib1 + (a - 4)));
+        const int64_t col0 = (int64_t)kTile * bj + jb0;
         double* p = o + row * out_ld + col0;
         const int pb = a * 2 * JH;
         *reinterpret_cast<double2*>(p) =

@@ -290,11 +290,26 @@ fw32_p3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict__ p
 #pragma unroll
         for (int b = 0; b < 8; ++b) m[a][b] = __int_as_float(0x7f800000);
     constexpr int kChunks = kT / kC;
+    static_assert(kChunks >= 3 && 2 * kP3StageFloats >= kT * kT, "the tile prefetch reuses two idle stages");
+    // the tile itself is not needed before the merge: it is prefetched (each thread its own 16 granules,
+    // laid out [granule][thread] -> conflict-free) into the two stages that are idle during the last chunk
+    float4* dpre = reinterpret_cast<float4*>(stages + (size_t)((kChunks - 1 + 1) % kP3Stages) * kP3StageFloats);
+    static_assert((kChunks - 1) % kP3Stages == 0, "stages 1 and 2 must be the idle, adjacent ones");
     for (int chunk = 0; chunk < kChunks; ++chunk) {
         if (chunk + 1 < kChunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                               // chunk landed for everyone; chunk-1 fully consumed
         if (chunk + 2 < kChunks) issue(chunk + 2);
+        if (chunk == kChunks - 1) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const int row = (a < 4) ? 4 * ty + a : 64 + 4 * ty + (a - 4);
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    cp_async16(dpre + (2 * a + h) * 256 + tid, dist + obase + row * ld + 64 * h + 4 * tx);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         const float* cs = stages + (size_t)(chunk % kP3Stages) * kP3StageFloats;
         const float* rs = cs + kT * kColLd;
 #pragma unroll 2
@@ -324,16 +339,16 @@ fw32_p3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict__ p
                 }
         }
     }
-    // merge: the tile is read only now (it was not needed during the loop), written only where it
-    // improved, and the round of the improvement is recorded
+    // merge: the prefetched tile (own granules only: no barrier needed) is compared with the new minima,
+    // written back only where it improved, and the round of the improvement is recorded
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     uint16_t* rt = rounds ? rounds + obase : nullptr;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
         const int row = (a < 4) ? 4 * ty + a : 64 + 4 * ty + (a - 4);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            float* p = dist + obase + row * ld + 64 * h + 4 * tx;
-            float4 d4 = *reinterpret_cast<const float4*>(p);
+            float4 d4 = dpre[(2 * a + h) * 256 + tid];
             float* dv = reinterpret_cast<float*>(&d4);
             bool any = false;
 #pragma unroll
@@ -343,7 +358,7 @@ fw32_p3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict__ p
                     any = true;
                     if (rt) rt[row * ld + 64 * h + 4 * tx + b] = (uint16_t)kb;
                 }
-            if (any) *reinterpret_cast<float4*>(p) = d4;
+            if (any) *reinterpret_cast<float4*>(dist + obase + row * ld + 64 * h + 4 * tx) = d4;
         }
     }
 }

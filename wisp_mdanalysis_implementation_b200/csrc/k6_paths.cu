@@ -373,6 +373,12 @@ struct GroupRequest {
     int cap = 0;
 };
 
+// fetched paths as they come off the device: path k = nodes[off[k] .. off[k] + n[k]) of pair `pair[k]`
+struct RawPaths {
+    std::vector<double> len;
+    std::vector<int32_t> pair, off, n, nodes;
+};
+
 struct EnumEngine {
     wisp_ctx* ctx;
     PathGraphState* g;
@@ -385,7 +391,7 @@ struct EnumEngine {
     // every pair's list sorted by (length, nodes) (:145).
     int pass(const std::vector<int32_t>& pairs, const std::vector<int32_t>& pair_group,
              const std::vector<GroupRequest>& req, std::vector<int64_t>* counts,
-             std::vector<std::vector<HostPath>>* paths_per_pair) {
+             std::vector<std::vector<HostPath>>* paths_per_pair, RawPaths* raw = nullptr) {
         const int n_pairs = (int)pair_group.size(), n_groups = (int)req.size();
         const int N = g->N;
         cudaStream_t st = ctx->stream;
@@ -492,7 +498,20 @@ struct EnumEngine {
             if (overflow) continue;
             expansions_total += hexp;
             counts->assign(hg.begin(), hg.end());
-            if (any_fetch && paths_per_pair) {
+            if (any_fetch && raw) {
+                // batched API: keep the paths packed (no per-path host objects)
+                const int np = hc[0], nn = hc[1];
+                raw->len.resize(np); raw->pair.resize(np); raw->off.resize(np); raw->n.resize(np); raw->nodes.resize(nn);
+                if (np) {
+                    WISP_CUDA(cudaMemcpyAsync(raw->len.data(), P.out_len, (size_t)np * 8, cudaMemcpyDeviceToHost, st));
+                    WISP_CUDA(cudaMemcpyAsync(raw->pair.data(), P.out_pair, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+                    WISP_CUDA(cudaMemcpyAsync(raw->off.data(), P.out_off, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+                    WISP_CUDA(cudaMemcpyAsync(raw->n.data(), P.out_n, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+                    WISP_CUDA(cudaMemcpyAsync(raw->nodes.data(), P.out_nodes, (size_t)nn * 4, cudaMemcpyDeviceToHost, st));
+                    WISP_CUDA(cudaStreamSynchronize(st));
+                }
+                enum_ms += now_ms() - te;
+            } else if (any_fetch && paths_per_pair) {
                 const int np = hc[0], nn = hc[1];
                 std::vector<double> hl(np);
                 std::vector<int32_t> hp(np), ho(np), hn(np), hnodes(nn);
@@ -735,22 +754,32 @@ extern "C" int wisp_paths_query_pairs(wisp_ctx* ctx, const int32_t* pairs_in, in
     std::vector<double> dist_rows;
     WISP_TRY(fetch_rows(ctx, g, rows, &pred_rows, &dist_rows));
     enum Phase { COUNT, BISECT, FETCH, DONE };
+    // A query is one (s, t) pair with s != t, so a pass never holds redundant paths (no reverse pair, no
+    // repeated pair) and the reference's ratchet reduces to: count passes, one fetch, then the final
+    // dedupe (which can only remove the seed's twin), sort and K / K+1 truncation.  The fetched paths
+    // stay packed: sorted index lists instead of per-path host objects.
     struct Query {
         Phase phase = COUNT;
-        std::vector<HostPath> paths;
+        std::vector<int32_t> seed;
+        double seed_len = 0.0;
         int64_t num_paths = 1, n_over = 0;
         double cutoff = 0.0, prev_cutoff = -1.0, lo = 0.0, hi = 0.0, req_cutoff = 0.0;
         int bisect_it = 0, passes = 0;
+        // fetched paths (sorted by (length, nodes)): lengths, node offsets, nodes
+        std::vector<double> len;
+        std::vector<int64_t> off;
+        std::vector<int32_t> nodes;
     };
     std::vector<Query> Q(n_queries);
     for (int q = 0; q < n_queries; ++q) {
         const int s = pairs_in[2 * q], t = pairs_in[2 * q + 1];
-        std::vector<int32_t> sp;
         double length = 0.0;
-        WISP_TRY(seed_path(g, pred_rows.data() + (size_t)row_of[s] * N, dist_rows.data() + (size_t)row_of[s] * N, s, t, &sp, &length));
-        Q[q].paths.push_back(HostPath{length, sp});
+        WISP_TRY(seed_path(g, pred_rows.data() + (size_t)row_of[s] * N, dist_rows.data() + (size_t)row_of[s] * N, s, t,
+                           &Q[q].seed, &length));
+        Q[q].seed_len = length;
         Q[q].cutoff = length;
         Q[q].req_cutoff = length;
+        Q[q].off.push_back(0);
         if (Q[q].num_paths >= K) Q[q].phase = DONE;         // K == 1: the seed alone (:56 is false at once)
     }
     EnumEngine eng{ctx, g, (flags & 1) ? 1 : 0};
@@ -763,11 +792,13 @@ extern "C" int wisp_paths_query_pairs(wisp_ctx* ctx, const int32_t* pairs_in, in
         std::vector<int32_t> pairs, pair_group;
         std::vector<GroupRequest> req;
         std::vector<int> who;
+        bool any_fetch = false;
         for (int q = 0; q < n_queries; ++q) {
             if (Q[q].phase == DONE) continue;
             GroupRequest r;
             r.cutoff = Q[q].req_cutoff;
             r.count_only = Q[q].phase != FETCH;
+            any_fetch |= !r.count_only;
             r.cap = cap_count;
             pairs.push_back(pairs_in[2 * q]); pairs.push_back(pairs_in[2 * q + 1]);
             pair_group.push_back((int32_t)req.size());
@@ -776,9 +807,14 @@ extern "C" int wisp_paths_query_pairs(wisp_ctx* ctx, const int32_t* pairs_in, in
         }
         if (who.empty()) break;
         std::vector<int64_t> counts;
-        std::vector<std::vector<HostPath>> per_pair;
-        WISP_TRY(eng.pass(pairs, pair_group, req, &counts, &per_pair));
+        RawPaths raw;
+        WISP_TRY(eng.pass(pairs, pair_group, req, &counts, nullptr, &raw));
         ++rounds;
+        double th = now_ms();
+        // fetched paths of this round, grouped by request, each group sorted by (length, nodes) (:145)
+        std::vector<std::vector<int32_t>> idx_of(any_fetch ? who.size() : 0);
+        if (any_fetch)
+            for (int32_t k = 0; k < (int32_t)raw.len.size(); ++k) idx_of[raw.pair[k]].push_back(k);
         for (size_t k = 0; k < who.size(); ++k) {
             Query& y = Q[who[k]];
             const int64_t n = counts[k];
@@ -820,12 +856,23 @@ extern "C" int wisp_paths_query_pairs(wisp_ctx* ctx, const int32_t* pairs_in, in
                     else { y.phase = FETCH; y.req_cutoff = y.hi; }      // massive ties: take everything up to hi
                 }
             } else {   // FETCH
-                for (auto& hp : per_pair[k]) y.paths.push_back(std::move(hp));
-                y.num_paths = y.n_over > 0 ? y.n_over : (int64_t)per_pair[k].size();
+                std::vector<int32_t>& idx = idx_of[k];
+                std::sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) {
+                    if (raw.len[a] != raw.len[b]) return raw.len[a] < raw.len[b];
+                    return std::lexicographical_compare(raw.nodes.begin() + raw.off[a], raw.nodes.begin() + raw.off[a] + raw.n[a],
+                                                        raw.nodes.begin() + raw.off[b], raw.nodes.begin() + raw.off[b] + raw.n[b]);
+                });
+                for (int32_t a : idx) {
+                    y.len.push_back(raw.len[a]);
+                    y.nodes.insert(y.nodes.end(), raw.nodes.begin() + raw.off[a], raw.nodes.begin() + raw.off[a] + raw.n[a]);
+                    y.off.push_back((int64_t)y.nodes.size());
+                }
+                y.num_paths = y.n_over > 0 ? y.n_over : (int64_t)idx.size();
                 y.n_over = 0;
                 WISP_TRY(finish_pass());
             }
         }
+        eng.host_ms += now_ms() - th;
     }
     double th = now_ms();
     ctx->path_len.clear(); ctx->path_off.clear(); ctx->path_nodes.clear(); ctx->path_query_off.clear();
@@ -833,11 +880,45 @@ extern "C" int wisp_paths_query_pairs(wisp_ctx* ctx, const int32_t* pairs_in, in
     int passes = 0;
     for (int q = 0; q < n_queries; ++q) {
         Query& y = Q[q];
-        if (y.paths.size() != 1) dedupe(y.paths);                            // :189
-        std::sort(y.paths.begin(), y.paths.end(), path_less);                // :209
-        if (y.num_paths != K && (int64_t)y.paths.size() > K) y.paths.resize(K);   // :211
+        // paths = [seed] + fetched (:186); dedupe (:189) keeps the first of two identical paths -- only the
+        // seed can have a twin; sort (:209): the seed takes its place by (length, nodes); truncate (:211)
+        const int64_t nf = (int64_t)y.len.size();
+        int64_t twin = -1;
+        for (int64_t k = 0; k < nf && twin < 0; ++k)
+            if (y.off[k + 1] - y.off[k] == (int64_t)y.seed.size() &&
+                std::equal(y.seed.begin(), y.seed.end(), y.nodes.begin() + y.off[k])) twin = k;
+        auto seed_before = [&](int64_t k) {     // Python list order of [len, nodes...]
+            if (y.seed_len != y.len[k]) return y.seed_len < y.len[k];
+            return std::lexicographical_compare(y.seed.begin(), y.seed.end(), y.nodes.begin() + y.off[k],
+                                                y.nodes.begin() + y.off[k + 1]);
+        };
+        int64_t total = nf + (twin < 0 ? 1 : 0);
+        int64_t keep = total;
+        if (y.num_paths != K && total > K) keep = K;
         ctx->path_query_off.push_back((int64_t)ctx->path_len.size());
-        store_result(ctx, y.paths);
+        bool seed_done = twin >= 0 && false;
+        int64_t emitted = 0;
+        auto emit = [&](double len, const int32_t* a, const int32_t* b) {
+            ctx->path_len.push_back(len);
+            ctx->path_nodes.insert(ctx->path_nodes.end(), a, b);
+            ctx->path_off.push_back((int64_t)ctx->path_nodes.size());
+            ++emitted;
+        };
+        for (int64_t k = 0; k < nf && emitted < keep; ++k) {
+            if (k == twin) {
+                // the seed's twin: the reference keeps the seed copy (first occurrence) -- same nodes; its
+                // length is the seed's own LR sum
+                emit(y.seed_len, y.seed.data(), y.seed.data() + y.seed.size());
+                continue;
+            }
+            if (twin < 0 && !seed_done && seed_before(k)) {
+                emit(y.seed_len, y.seed.data(), y.seed.data() + y.seed.size());
+                seed_done = true;
+                if (emitted >= keep) break;
+            }
+            emit(y.len[k], y.nodes.data() + y.off[k], y.nodes.data() + y.off[k + 1]);
+        }
+        if (twin < 0 && !seed_done && emitted < keep) emit(y.seed_len, y.seed.data(), y.seed.data() + y.seed.size());
         passes += y.passes;
     }
     ctx->path_query_off.push_back((int64_t)ctx->path_len.size());

@@ -3,16 +3,22 @@
 // Replaces the second half of traj_alignment_and_averaging
 // (trajectory_analysis_functions.py:86-126): up to 100 passes over all frames, each frame
 // needing MDAnalysis' rotation_matrix (QCP) and two numpy dots from Python.
-// One CTA per frame (grid-stride):
-//   1. S = sum_i a_i b_i^T over the alignment landmarks (a = this frame, b = current average)
-//      -- block reduction of 9 FP64 sums;
-//   2. thread 0 builds Horn's 4x4 quaternion matrix and diagonalises it with cyclic Jacobi
-//      rotations in FP64; the eigenvector of the largest eigenvalue is the optimal proper
-//      rotation (same minimiser as QCP / Kabsch with the reflection fix);
-//   3. all threads rotate the landmarks (stored back as float32, like the reference's float32
-//      all_pos_Align array, :106) and the node positions (float64, :107) in place.
-// New averages are column sums (k1_com.cu) divided by T; the host loop checks the RMSD
-// between successive landmark averages against the threshold (:118).
+// One iteration = two kernels:
+//   align_solve_kernel   one WARP per frame: S = sum_i a_i b_i^T over the alignment landmarks (a = this
+//                        frame, b = current average), 9 FP64 sums reduced by shuffles; lane 0 builds
+//                        Horn's 4x4 quaternion matrix and diagonalises it with cyclic Jacobi rotations
+//                        in FP64 -- the eigenvector of the largest eigenvalue is the optimal proper
+//                        rotation (same minimiser as QCP / Kabsch with the reflection fix) -- and
+//                        stores R[frame] (72 bytes).  64 frames per SM are in flight, so the serial
+//                        eigen-solve never leaves the memory system idle;
+//   align_apply_kernel   HBM-bound streaming pass: thread = one node (float64, :107) or one landmark
+//                        (float32 like the reference's all_pos_Align array, :106), walks a segment of
+//                        frames, rotates in place and keeps the running column sums of what it stores in
+//                        registers -- the new averages (:110-111) come out of the same pass (per-segment
+//                        partial rows, fixed-order finish: deterministic) instead of re-reading both arrays.
+// Round 1 ran one CTA per frame with a block reduction and thread 0 solving while 255 threads waited,
+// then two separate column-sum passes: 5.6 ms per iteration at C2; this form moves 7.2 GB per iteration.
+// The host loop checks the RMSD between successive landmark averages against the threshold (:118).
 #include "common.cuh"
 #include <cmath>
 
@@ -59,76 +65,89 @@ __device__ void jacobi4(double A[4][4], double V[4][4]) {
 }
 
 __global__ void __launch_bounds__(kAlThreads)
-align_rotate_kernel(float* __restrict__ align, int n_align, const double* __restrict__ avg_align,
-                    double* __restrict__ nodes, int64_t ld, int N, int64_t T) {
-    __shared__ double red[9][kAlThreads / 32];
-    __shared__ double Rm[9];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int64_t f = blockIdx.x; f < T; f += gridDim.x) {
-        float* fa = align + f * (int64_t)n_align * 3;
-        double s[9];
+align_solve_kernel(const float* __restrict__ align, int n_align, const double* __restrict__ avg_align, int64_t T,
+                   double* __restrict__ rot) {
+    const int lane = threadIdx.x & 31;
+    const int64_t f = (int64_t)blockIdx.x * (kAlThreads / 32) + (threadIdx.x >> 5);
+    if (f >= T) return;
+    const float* fa = align + f * (int64_t)n_align * 3;
+    double s[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) s[k] = 0.0;
-        for (int i = tid; i < n_align; i += kAlThreads) {
-            const double ax = fa[3 * i], ay = fa[3 * i + 1], az = fa[3 * i + 2];
-            const double bx = avg_align[3 * i], by = avg_align[3 * i + 1], bz = avg_align[3 * i + 2];
-            s[0] += ax * bx; s[1] += ax * by; s[2] += ax * bz;
-            s[3] += ay * bx; s[4] += ay * by; s[5] += ay * bz;
-            s[6] += az * bx; s[7] += az * by; s[8] += az * bz;
-        }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            double v = s[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) red[k][warp] = v;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double S[9];
-            for (int k = 0; k < 9; ++k) {
-                double v = 0.0;
-                for (int w = 0; w < kAlThreads / 32; ++w) v += red[k][w];
-                S[k] = v;
-            }
-            const double Sxx = S[0], Sxy = S[1], Sxz = S[2], Syx = S[3], Syy = S[4], Syz = S[5],
-                         Szx = S[6], Szy = S[7], Szz = S[8];
-            double A[4][4] = {
-                {Sxx + Syy + Szz, Syz - Szy, Szx - Sxz, Sxy - Syx},
-                {Syz - Szy, Sxx - Syy - Szz, Sxy + Syx, Szx + Sxz},
-                {Szx - Sxz, Sxy + Syx, -Sxx + Syy - Szz, Syz + Szy},
-                {Sxy - Syx, Szx + Sxz, Syz + Szy, -Sxx - Syy + Szz}};
-            double V[4][4];
-            jacobi4(A, V);
-            int best = 0;
-            for (int k = 1; k < 4; ++k)
-                if (A[k][k] > A[best][best]) best = k;
-            double q0 = V[0][best], qx = V[1][best], qy = V[2][best], qz = V[3][best];
-            const double nq = sqrt(q0 * q0 + qx * qx + qy * qy + qz * qz);
-            q0 /= nq; qx /= nq; qy /= nq; qz /= nq;
-            Rm[0] = q0 * q0 + qx * qx - qy * qy - qz * qz; Rm[1] = 2 * (qx * qy - q0 * qz); Rm[2] = 2 * (qx * qz + q0 * qy);
-            Rm[3] = 2 * (qy * qx + q0 * qz); Rm[4] = q0 * q0 - qx * qx + qy * qy - qz * qz; Rm[5] = 2 * (qy * qz - q0 * qx);
-            Rm[6] = 2 * (qz * qx - q0 * qy); Rm[7] = 2 * (qz * qy + q0 * qx); Rm[8] = q0 * q0 - qx * qx - qy * qy + qz * qz;
-        }
-        __syncthreads();
-        const double r0 = Rm[0], r1 = Rm[1], r2 = Rm[2], r3 = Rm[3], r4 = Rm[4], r5 = Rm[5],
-                     r6 = Rm[6], r7 = Rm[7], r8 = Rm[8];
-        // x <- x . R^T  (row vector times R transposed == R x)
-        for (int i = tid; i < n_align; i += kAlThreads) {
-            const double x = fa[3 * i], y = fa[3 * i + 1], z = fa[3 * i + 2];
-            fa[3 * i + 0] = (float)(x * r0 + y * r1 + z * r2);
-            fa[3 * i + 1] = (float)(x * r3 + y * r4 + z * r5);
-            fa[3 * i + 2] = (float)(x * r6 + y * r7 + z * r8);
-        }
-        double* fn = nodes + f * ld;
-        for (int i = tid; i < N; i += kAlThreads) {
-            const double x = fn[3 * i], y = fn[3 * i + 1], z = fn[3 * i + 2];
-            fn[3 * i + 0] = x * r0 + y * r1 + z * r2;
-            fn[3 * i + 1] = x * r3 + y * r4 + z * r5;
-            fn[3 * i + 2] = x * r6 + y * r7 + z * r8;
-        }
-        __syncthreads();
+    for (int k = 0; k < 9; ++k) s[k] = 0.0;
+    for (int i = lane; i < n_align; i += 32) {
+        const double ax = fa[3 * i], ay = fa[3 * i + 1], az = fa[3 * i + 2];
+        const double bx = __ldg(avg_align + 3 * i), by = __ldg(avg_align + 3 * i + 1), bz = __ldg(avg_align + 3 * i + 2);
+        s[0] += ax * bx; s[1] += ax * by; s[2] += ax * bz;
+        s[3] += ay * bx; s[4] += ay * by; s[5] += ay * bz;
+        s[6] += az * bx; s[7] += az * by; s[8] += az * bz;
     }
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    if (lane != 0) return;
+    const double Sxx = s[0], Sxy = s[1], Sxz = s[2], Syx = s[3], Syy = s[4], Syz = s[5],
+                 Szx = s[6], Szy = s[7], Szz = s[8];
+    double A[4][4] = {
+        {Sxx + Syy + Szz, Syz - Szy, Szx - Sxz, Sxy - Syx},
+        {Syz - Szy, Sxx - Syy - Szz, Sxy + Syx, Szx + Sxz},
+        {Szx - Sxz, Sxy + Syx, -Sxx + Syy - Szz, Syz + Szy},
+        {Sxy - Syx, Szx + Sxz, Syz + Szy, -Sxx - Syy + Szz}};
+    double V[4][4];
+    jacobi4(A, V);
+    int best = 0;
+    for (int k = 1; k < 4; ++k)
+        if (A[k][k] > A[best][best]) best = k;
+    double q0 = V[0][best], qx = V[1][best], qy = V[2][best], qz = V[3][best];
+    const double nq = sqrt(q0 * q0 + qx * qx + qy * qy + qz * qz);
+    q0 /= nq; qx /= nq; qy /= nq; qz /= nq;
+    double* R = rot + f * 9;
+    R[0] = q0 * q0 + qx * qx - qy * qy - qz * qz; R[1] = 2 * (qx * qy - q0 * qz); R[2] = 2 * (qx * qz + q0 * qy);
+    R[3] = 2 * (qy * qx + q0 * qz); R[4] = q0 * q0 - qx * qx + qy * qy - qz * qz; R[5] = 2 * (qy * qz - q0 * qx);
+    R[6] = 2 * (qz * qx - q0 * qy); R[7] = 2 * (qz * qy + q0 * qx); R[8] = q0 * q0 - qx * qx - qy * qy + qz * qz;
+}
+
+// x <- x . R^T (row vector times R transposed == R x) for every frame of segment blockIdx.y;
+// item = blockIdx.x * 128 + threadIdx.x: [0, n_align) landmarks (float32), then N nodes (float64).
+// part [n_seg][3 n_align + 3 N]: column sums of the values STORED by this segment.
+constexpr int kApplyThreads = 128;
+__global__ void __launch_bounds__(kApplyThreads)
+align_apply_kernel(float* __restrict__ align, int n_align, double* __restrict__ nodes, int64_t ld, int N,
+                   int64_t T, const double* __restrict__ rot, int64_t frames_per_seg, double* __restrict__ part) {
+    const int item = blockIdx.x * kApplyThreads + threadIdx.x;
+    if (item >= n_align + N) return;
+    const int64_t f0 = (int64_t)blockIdx.y * frames_per_seg, f1 = min(T, f0 + frames_per_seg);
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    if (item < n_align) {
+        float* p = align + 3 * (int64_t)item;
+        const int64_t stride = 3 * (int64_t)n_align;
+#pragma unroll 4
+        for (int64_t f = f0; f < f1; ++f) {
+            const double* R = rot + f * 9;
+            float* q = p + f * stride;
+            const double x = q[0], y = q[1], z = q[2];
+            const float ox = (float)(x * __ldg(R + 0) + y * __ldg(R + 1) + z * __ldg(R + 2));
+            const float oy = (float)(x * __ldg(R + 3) + y * __ldg(R + 4) + z * __ldg(R + 5));
+            const float oz = (float)(x * __ldg(R + 6) + y * __ldg(R + 7) + z * __ldg(R + 8));
+            q[0] = ox; q[1] = oy; q[2] = oz;
+            sx += (double)ox; sy += (double)oy; sz += (double)oz;
+        }
+    } else {
+        double* p = nodes + 3 * (int64_t)(item - n_align);
+#pragma unroll 4
+        for (int64_t f = f0; f < f1; ++f) {
+            const double* R = rot + f * 9;
+            double* q = p + f * ld;
+            const double x = q[0], y = q[1], z = q[2];
+            const double ox = x * __ldg(R + 0) + y * __ldg(R + 1) + z * __ldg(R + 2);
+            const double oy = x * __ldg(R + 3) + y * __ldg(R + 4) + z * __ldg(R + 5);
+            const double oz = x * __ldg(R + 6) + y * __ldg(R + 7) + z * __ldg(R + 8);
+            q[0] = ox; q[1] = oy; q[2] = oz;
+            sx += ox; sy += oy; sz += oz;
+        }
+    }
+    double* out = part + (int64_t)blockIdx.y * (3 * (int64_t)(n_align + N)) + 3 * (int64_t)item;
+    out[0] = sx; out[1] = sy; out[2] = sz;
 }
 
 // np.sum(float32 array, axis=0) of the reference (:86): sequential float32 adds down the frames.
@@ -165,14 +184,28 @@ int launch_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const do
     return 0;
 }
 
-// one alignment pass over this frame block: rotate every frame onto d_avg_align (in place)
+// one alignment pass over this frame block: rotate every frame onto d_avg_align (in place); d_sums
+// [3 n_align + 3 N] (may be NULL) receives the column sums of the rotated landmarks, then of the rotated
+// nodes -- what launch_align_sums(first = false) would compute, without reading either array again
 int launch_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align, double* d_nodes,
-                        int64_t ld, int N, int64_t T, cudaStream_t st) {
+                        int64_t ld, int N, int64_t T, cudaStream_t st, double* d_sums) {
     ctx->i8_stats_x = nullptr;               // the node trajectory is rotated in place
-    const int blocks = (int)std::min<int64_t>(T, (int64_t)ctx->sm_count * 8);
-    align_rotate_kernel<<<blocks, kAlThreads, 0, st>>>(d_align, n_align, d_avg_align, d_nodes, ld, N, T);
-    ctx->launches++;
+    void *pr = nullptr, *pp = nullptr;
+    WISP_TRY(wisp_scratch(ctx, SCR_ALIGN_ROT, (size_t)T * 9 * 8, &pr));
+    double* d_rot = (double*)pr;
+    align_solve_kernel<<<(unsigned)((T + kAlThreads / 32 - 1) / (kAlThreads / 32)), kAlThreads, 0, st>>>(
+        d_align, n_align, d_avg_align, T, d_rot);
+    const int items = n_align + N, gx = (items + kApplyThreads - 1) / kApplyThreads;
+    int n_seg = (int)std::max<int64_t>(1, std::min<int64_t>(T, (int64_t)ctx->sm_count * 6 / gx));
+    const int64_t per = (T + n_seg - 1) / n_seg;
+    n_seg = (int)((T + per - 1) / per);
+    const int64_t ncols = 3 * (int64_t)items;
+    WISP_TRY(wisp_scratch(ctx, SCR_ALIGN_PART, (size_t)n_seg * ncols * 8, &pp));
+    align_apply_kernel<<<dim3(gx, n_seg), kApplyThreads, 0, st>>>(d_align, n_align, d_nodes, ld, N, T, d_rot, per,
+                                                                 (double*)pp);
+    ctx->launches += 2;
     WISP_CUDA(cudaGetLastError());
+    if (d_sums) WISP_TRY(launch_colsum_finish(ctx, (const double*)pp, n_seg, ncols, ncols, d_sums, st));
     return 0;
 }
 
@@ -216,8 +249,7 @@ int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* 
     int iteration = 0;
     double residual = threshold + 9999.0;
     while (residual > threshold && iteration < max_iter) {
-        WISP_TRY(launch_align_rotate(ctx, d_align, n_align, d_avgA, d_nodes, ld, N, T, st));
-        WISP_TRY(launch_align_sums(ctx, d_align, n_align, d_nodes, ld, N, T, false, d_sums, st));
+        WISP_TRY(launch_align_rotate(ctx, d_align, n_align, d_avgA, d_nodes, ld, N, T, st, d_sums));
         WISP_CUDA(cudaMemcpyAsync(sums.data(), d_sums, (na3 + nn3) * 8, cudaMemcpyDeviceToHost, st));
         WISP_CUDA(cudaStreamSynchronize(st));
         if (reduce) WISP_TRY(reduce(sums.data(), (size_t)(na3 + nn3), false, AlignStep()));

@@ -182,9 +182,8 @@ class FramePipeline:
         while residual > self.align_threshold and it < self.align_iterations:
             self.d_avg_align.copy_(torch.from_numpy(avg_a))
             self.ctx.dev_align_rotate(self.d_align.data_ptr(), self.n_align, self.d_avg_align.data_ptr(),
-                                      self.d_x.data_ptr(), self.T, self.N, stream=s)
-            self.ctx.dev_align_sums(self.d_align.data_ptr(), self.n_align, self.d_x.data_ptr(), self.T, self.N,
-                                    False, self.d_align_sums.data_ptr(), stream=s)
+                                      self.d_x.data_ptr(), self.T, self.N, d_sums=self.d_align_sums.data_ptr(),
+                                      stream=s)
             sharding.reduce_sums(self.d_align_sums, group=self.group)
             h = self.d_align_sums.cpu().numpy() / float(self.T_total)
             new_a, new_n = h[:na3], h[na3:]
