@@ -252,6 +252,7 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
 
+template <bool TRACK>     // TRACK: record the round of every improvement (predecessor reconstruction)
 __global__ void __launch_bounds__(256, 2)
 fw32_p3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict__ panel, int64_t ldp,
                int kb, int skip, int nb, int nl, int part, int next_col, int next_row,
@@ -284,11 +285,22 @@ fw32_p3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict__ p
 
     issue(0);
     issue(1);
+    // TRACK: fresh minima, merged into the tile at the end (the comparison tells which entries improved);
+    // distance only: the tile itself is the accumulator, loaded under the first cp.async stages
     float m[8][8];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < 8; ++a) {
+        if (TRACK) {
 #pragma unroll
-        for (int b = 0; b < 8; ++b) m[a][b] = __int_as_float(0x7f800000);
+            for (int b = 0; b < 8; ++b) m[a][b] = __int_as_float(0x7f800000);
+        } else {
+            const int row = (a < 4) ? 4 * ty + a : 64 + 4 * ty + (a - 4);
+            const float4 v0 = *reinterpret_cast<const float4*>(dist + obase + row * ld + 4 * tx);
+            const float4 v1 = *reinterpret_cast<const float4*>(dist + obase + row * ld + 64 + 4 * tx);
+            m[a][0] = v0.x; m[a][1] = v0.y; m[a][2] = v0.z; m[a][3] = v0.w;
+            m[a][4] = v1.x; m[a][5] = v1.y; m[a][6] = v1.z; m[a][7] = v1.w;
+        }
+    }
     constexpr int kChunks = kT / kC;
     static_assert(kChunks >= 3 && 2 * kP3StageFloats >= kT * kT, "the tile prefetch reuses two idle stages");
     // the tile itself is not needed before the merge: it is prefetched (each thread its own 16 granules,
@@ -300,7 +312,7 @@ fw32_p3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict__ p
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                               // chunk landed for everyone; chunk-1 fully consumed
         if (chunk + 2 < kChunks) issue(chunk + 2);
-        if (chunk == kChunks - 1) {
+        if (TRACK && chunk == kChunks - 1) {
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
                 const int row = (a < 4) ? 4 * ty + a : 64 + 4 * ty + (a - 4);
@@ -339,10 +351,19 @@ fw32_p3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict__ p
                 }
         }
     }
+    if (!TRACK) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int row = (a < 4) ? 4 * ty + a : 64 + 4 * ty + (a - 4);
+            *reinterpret_cast<float4*>(dist + obase + row * ld + 4 * tx) = make_float4(m[a][0], m[a][1], m[a][2], m[a][3]);
+            *reinterpret_cast<float4*>(dist + obase + row * ld + 64 + 4 * tx) = make_float4(m[a][4], m[a][5], m[a][6], m[a][7]);
+        }
+        return;
+    }
     // merge: the prefetched tile (own granules only: no barrier needed) is compared with the new minima,
     // written back only where it improved, and the round of the improvement is recorded
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    uint16_t* rt = rounds ? rounds + obase : nullptr;
+    uint16_t* rt = rounds + obase;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
         const int row = (a < 4) ? 4 * ty + a : 64 + 4 * ty + (a - 4);
@@ -356,7 +377,7 @@ fw32_p3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict__ p
                 if (m[a][4 * h + b] < dv[b]) {
                     dv[b] = m[a][4 * h + b];
                     any = true;
-                    if (rt) rt[row * ld + 64 * h + 4 * tx + b] = (uint16_t)kb;
+                    rt[row * ld + 64 * h + 4 * tx + b] = (uint16_t)kb;
                 }
             if (any) *reinterpret_cast<float4*>(dist + obase + row * ld + 64 * h + 4 * tx) = d4;
         }
@@ -540,7 +561,10 @@ int fw_set_attrs() {
     WISP_CUDA(cudaFuncSetAttribute(fw_p1_kernel<T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw_p1_smem<T>()));
     WISP_CUDA(cudaFuncSetAttribute(fw_p2_kernel<T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw_p2_smem<T>()));
     if (sizeof(T) == 4)
-        WISP_CUDA(cudaFuncSetAttribute(fw32_p3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwCfg<float>::p3_smem()));
+    {
+        WISP_CUDA(cudaFuncSetAttribute(fw32_p3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwCfg<float>::p3_smem()));
+        WISP_CUDA(cudaFuncSetAttribute(fw32_p3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwCfg<float>::p3_smem()));
+    }
     else
         WISP_CUDA(cudaFuncSetAttribute(fw64_p3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwCfg<double>::p3_smem()));
     return 0;
@@ -549,8 +573,12 @@ int fw_set_attrs() {
 inline void launch_p3(float* dist, int64_t ld, const float* panel, int64_t ldp, int kb, int skip, int nb, int nl,
                       int part, int next_col, int next_row, uint16_t* rounds, cudaStream_t st) {
     const dim3 grid = part == 1 ? dim3(nl + nb) : dim3(nb, nl);
-    fw32_p3_kernel<<<grid, 256, FwCfg<float>::p3_smem(), st>>>(dist, ld, panel, ldp, kb, skip, nb, nl, part,
-                                                              next_col, next_row, rounds);
+    if (rounds)
+        fw32_p3_kernel<true><<<grid, 256, FwCfg<float>::p3_smem(), st>>>(dist, ld, panel, ldp, kb, skip, nb, nl, part,
+                                                                        next_col, next_row, rounds);
+    else
+        fw32_p3_kernel<false><<<grid, 256, FwCfg<float>::p3_smem(), st>>>(dist, ld, panel, ldp, kb, skip, nb, nl, part,
+                                                                         next_col, next_row, nullptr);
 }
 inline void launch_p3(double* dist, int64_t ld, const double* panel, int64_t ldp, int kb, int skip, int nb, int nl,
                       int part, int next_col, int next_row, uint16_t* rounds, cudaStream_t st) {
