@@ -548,11 +548,12 @@ def main():
             ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
             ea.record()
-            call_ms = []
+            call_ms, call_stages = [], []
             for _ in range(args.steps):
                 tc = time.perf_counter()
                 res_call = call()          # blocking: returns when every GPU's slice is in the host buffers
                 call_ms.append((time.perf_counter() - tc) * 1e3)
+                call_stages.append({k: round(v, 2) for k, v in mctx.pipeline_stats().items()})
             eb.record()
             torch.cuda.synchronize()
             wall_call = (time.perf_counter() - t0) * 1e3 / args.steps
@@ -564,7 +565,8 @@ def main():
         if rank == 0:
             h2d_total = T * A * 12
             e2e = {"value": float(N) * N * T / (ms_call * 1e-3), "unit": UNIT, "ms_per_step": ms_call,
-                   "wall_ms_per_step": wall_call, "wall_ms_each_call": call_ms, "h2d_bytes_per_step": h2d_total,
+                   "wall_ms_per_step": wall_call, "wall_ms_each_call": call_ms,
+                   "stages_of_each_call_ms": call_stages, "h2d_bytes_per_step": h2d_total,
                    "d2h_bytes_per_step": 4 * N * N * 8 + N * 24,
                    "api": "wisp_pipeline (C ABI, include/wisp_b200.h) on wisp_ctx_create_multi(%d): page-locked host "
                           "coordinates in; avg / corr / avgdist / binary / w in page-locked host buffers out; "

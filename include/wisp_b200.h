@@ -135,6 +135,11 @@ int wisp_pipeline_log(wisp_ctx* ctx, const float* coords, int64_t T, int A, cons
                       double* out_corr, double* out_avgdist, int64_t* out_binary, double* out_w,
                       double* out_nodes, double* out_log, int* out_n_iter);
 
+/* Host-clock stage times of the last wisp_pipeline on this context, as seen by the first GPU's thread:
+ * [0] H2D || K1, [1] K7 alignment, [2] centring + K2 + K3, [3] waiting for the slowest GPU,
+ * [4] fused cross-GPU epilogue + D2H, [5] total (ms); [7] GPUs used. */
+int wisp_pipeline_stats(wisp_ctx* ctx, double* out8);
+
 /* a6 (north-star APSP; the reference calls Dijkstra, network_analysis_functions.py:30,71-72).
  * w [N][N] cost matrix (non-zero = edge).  precision 64 or 32 (distances are returned as
  * float64 either way).  out_dist [N][N], out_pred [N][N] (-1 = none); pred may be NULL. */

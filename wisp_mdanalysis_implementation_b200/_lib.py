@@ -48,6 +48,7 @@ SIGNATURES = {
                              _dbl, _int, _P, _P, _P, _P, _P, _P]),
     "wisp_pipeline_log": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P, _int, _P, _int, _int, _dbl, _int,
                                  _dbl, _int, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_int)]),
+    "wisp_pipeline_stats": (_int, [_c_ctx, _P]),
     "wisp_apsp": (_int, [_c_ctx, _P, _int, _int, _P, _P]),
     "wisp_get_paths": (_int, [_c_ctx, _P, _int, _P, _int, _P, _int, _int, _int]),
     "wisp_paths_prepare": (_int, [_c_ctx, _P, _int, _int]),
@@ -313,6 +314,13 @@ class Context:
             out["nodes"] = nodes
         out["alignment_log"] = [(int(r[0]), float(r[1]), float(r[2])) for r in log[:n_iter.value]]
         return out
+
+    def pipeline_stats(self):
+        s = np.empty(8)
+        self._check(self._lib.wisp_pipeline_stats(self._ctx, _ptr(s)))
+        return dict(h2d_k1_ms=float(s[0]), k7_ms=float(s[1]), center_k2_k3_ms=float(s[2]),
+                    wait_for_slowest_gpu_ms=float(s[3]), epilogue_d2h_ms=float(s[4]), total_ms=float(s[5]),
+                    gpus=int(s[7]))
 
     def apsp(self, w, precision=64, want_pred=True):
         w = _arr(w, np.float64, "cost matrix")

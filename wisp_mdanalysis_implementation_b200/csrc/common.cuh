@@ -86,6 +86,7 @@ struct wisp_ctx {
     std::vector<int32_t> path_nodes;
     std::vector<int64_t> path_query_off;    // wisp_paths_query_pairs: first path of every query (+ end)
     double path_stats[6] = {0, 0, 0, 0, 0, 0};
+    double pipe_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     PathGraphState* pg = nullptr;            // graph + APSP state of wisp_paths_prepare
     void (*pg_free)(PathGraphState*) = nullptr;
 };

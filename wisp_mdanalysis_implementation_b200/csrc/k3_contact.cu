@@ -296,6 +296,10 @@ __device__ __forceinline__ void ws_bulk_g2s(void* dst, const void* src, uint32_t
         ::"r"(ws_smem_u32(dst)), "l"(src), "r"(bytes), "r"(ws_smem_u32(bar)) : "memory");
 }
 
+// diagonal tiles: 32 x 32 sub-block (row, column) of compute warp w; w < 10: on or above the diagonal
+__constant__ int kDiagSubRow[16] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 3, 1, 2, 2, 3, 3, 3};
+__constant__ int kDiagSubCol[16] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3, 0, 0, 1, 0, 1, 2};
+
 template <int UNROLL>
 __global__ void __launch_bounds__(kWsThreads, 1)
 contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const double* __restrict__ mean,
@@ -382,11 +386,14 @@ contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
         const int w = tid >> 5, lane = tid & 31;
         const int valid_i = min(kTile, N - kTile * bi), valid_j = min(kTile, N - kTile * bj);
         if (bi == bj) {
-            const int wr = w >> 2, wc = w & 3;
+            // the 10 sub-blocks on or above the diagonal go to warps 0..9, so that the four schedulers
+            // (warp % 4) carry 3, 3, 2, 2 of them; warps 10..15 own the 6 sub-blocks below the diagonal,
+            // stay idle and only store the zeros their totals were initialised with
+            const int wr = kDiagSubRow[w], wc = kDiagSubCol[w];
             ib0 = 32 * wr + 8 * (lane >> 3);
             ib1 = ib0 + 4;
             jb0 = 32 * wc + 4 * (lane & 7);
-            idle = wr > wc || 32 * wr >= valid_i || 32 * wc >= valid_j;
+            idle = w >= 10 || 32 * wr >= valid_i || 32 * wc >= valid_j;
         } else {
             ib0 = 4 * (tid & 15);
             ib1 = 64 + ib0;
@@ -471,7 +478,7 @@ contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
     }
 
     // idle threads store the zeros their totals were initialised with: the partial tile is always
-    // completely defined (the entries below the diagonal of a diagonal tile are never read)
+    // completely defined
     double* o = out + (size_t)seg * out_ld * out_ld;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {

@@ -384,56 +384,109 @@ fw32_p3_kernel(float* __restrict__ dist, int64_t ld, const float* __restrict__ p
     }
 }
 
-// ---- FP64 P3: 64 x 64 tile, 4 x 4 outputs per thread, whole 64-deep round staged at once (column tile
-// transposed so a thread's 4 rows are one pair of vector loads); DADD + DSETP.MIN per relaxation.
-constexpr int kB64 = 64;
+// ---- FP64 P3: 128 x 128 tile per CTA (two 64-wide pivot blocks fit in one tile edge), 8 x 8 outputs per
+// thread, the 64-deep round staged by cp.async in two halves (the second half lands while the first is
+// being used), both panels kept in their natural row-major layout and read as (k, k+1) / (j, j+1) double
+// pairs: 16 LDS.128 per 128 relaxations instead of the 32 of a 4 x 4 tile (round 1: shared-memory bound).
+// DADD + DSETP/select per relaxation.  The pivot rows / columns inside a tile are relaxed again -- a no-op,
+// P2 already closed them under this very relaxation, and nothing is written where nothing improves.
+constexpr int kB64 = 64;               // round width (pivot block) in FP64
+constexpr int kT64 = 128;              // P3 tile edge
+constexpr int kC64Ld = kB64 + 2;       // padded row of the column panel (doubles)
+constexpr int kP3Smem64 = (kT64 * kC64Ld + kB64 * kT64) * (int)sizeof(double);
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 1)
 fw64_p3_kernel(double* __restrict__ dist, int64_t ld, const double* __restrict__ panel, int64_t ldp,
                int kb, int skip, int nb, int nl, int part, int next_col, int next_row,
                uint16_t* __restrict__ rounds) {
+    // grid in 128-tiles: nb128 x nl128; kb / skip / next_* are in 64-blocks
+    const int nb2 = (nb + 1) / 2, nl2 = (nl + 1) / 2;
     int bi, bj;
-    if (!fw_p3_tile(part, nb, nl, kb, skip, next_col, next_row, bi, bj)) return;
+    {
+        const int nc = next_col >= 0 ? next_col / 2 : -1, nr = next_row >= 0 ? next_row / 2 : -1;
+        if (part == 1) {
+            const int x = blockIdx.x;
+            if (x < nl2) { if (nc < 0) return; bi = x; bj = nc; }
+            else { if (nr < 0) return; bi = nr; bj = x - nl2; if (bj == nc) return; }
+        } else {
+            bj = blockIdx.x; bi = blockIdx.y;
+            if (part == 2 && (bj == nc || bi == nr)) return;
+        }
+        if (bi >= nl2 || bj >= nb2) return;
+    }
     extern __shared__ __align__(16) unsigned char fw_smem[];
-    double* ct = reinterpret_cast<double*>(fw_smem);    // column tile transposed: ct[k][i]
-    double* rt = ct + kB64 * kB64;                       // row tile: rt[k][j]
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const double* cg = dist + (int64_t)bi * kB64 * ld + (int64_t)kb * kB64;
-    const double* rg = panel + (int64_t)bj * kB64;
-    const int64_t obase = (int64_t)bi * kB64 * ld + (int64_t)bj * kB64;
-    for (int e = threadIdx.x; e < kB64 * kB64; e += 256) {
-        const int r = e >> 6, c = e & 63;
-        ct[c * kB64 + r] = cg[(int64_t)r * ld + c];
-        rt[r * kB64 + c] = rg[(int64_t)r * ldp + c];
+    double* cs = reinterpret_cast<double*>(fw_smem);          // [128][kC64Ld]: column panel (i, k)
+    double* rs = cs + kT64 * kC64Ld;                           // [64][128]:     row panel (k, j)
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const double* cg = dist + (int64_t)bi * kT64 * ld + (int64_t)kb * kB64;
+    const double* rg = panel + (int64_t)bj * kT64;
+    const int64_t obase = (int64_t)bi * kT64 * ld + (int64_t)bj * kT64;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int e = tid + 256 * q;                       // 2048 granules per half and panel
+            const int i = e >> 4, g = (e & 15) + 16 * half;    // column panel: row i, granule g (2 doubles of k)
+            cp_async16(cs + i * kC64Ld + 2 * g, cg + (int64_t)i * ld + 2 * g);
+            const int k = (e >> 6) + 32 * half, h = e & 63;    // row panel: row k, granule h (2 doubles of j)
+            cp_async16(rs + k * kT64 + 2 * h, rg + (int64_t)k * ldp + 2 * h);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    double m[4][4];
+    double m[8][8];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) m[a][b] = inf_v<double>();
-    __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < kB64; ++k) {
-        const double2 ca = *reinterpret_cast<const double2*>(ct + k * kB64 + 4 * ty);
-        const double2 cb = *reinterpret_cast<const double2*>(ct + k * kB64 + 4 * ty + 2);
-        const double2 ra = *reinterpret_cast<const double2*>(rt + k * kB64 + 4 * tx);
-        const double2 rb = *reinterpret_cast<const double2*>(rt + k * kB64 + 4 * tx + 2);
-        const double cv[4] = {ca.x, ca.y, cb.x, cb.y}, rv[4] = {ra.x, ra.y, rb.x, rb.y};
+        for (int b = 0; b < 8; ++b) m[a][b] = inf_v<double>();
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        if (half == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+#pragma unroll 2
+        for (int k = 32 * half; k < 32 * half + 32; k += 2) {
+            double c1[8], c2[8], r1[8], r2[8];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) m[a][b] = fmin(m[a][b], cv[a] + rv[b]);
-    }
-    uint16_t* rr = rounds ? rounds + obase : nullptr;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        double* p = dist + obase + (int64_t)(4 * ty + a) * ld + 4 * tx;
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-            if (m[a][b] < p[b]) {
-                p[b] = m[a][b];
-                if (rr) rr[(int64_t)(4 * ty + a) * ld + 4 * tx + b] = (uint16_t)kb;
+            for (int a = 0; a < 8; ++a) {
+                const int row = (a < 4) ? 4 * ty + a : 64 + 4 * ty + (a - 4);
+                const double2 cc = *reinterpret_cast<const double2*>(cs + row * kC64Ld + k);
+                c1[a] = cc.x; c2[a] = cc.y;
             }
+#pragma unroll
+            for (int bp = 0; bp < 4; ++bp) {
+                const int col = (bp < 2) ? 4 * tx + 2 * bp : 64 + 4 * tx + 2 * (bp - 2);
+                const double2 ra = *reinterpret_cast<const double2*>(rs + k * kT64 + col);
+                const double2 rb = *reinterpret_cast<const double2*>(rs + (k + 1) * kT64 + col);
+                r1[2 * bp] = ra.x; r1[2 * bp + 1] = ra.y;
+                r2[2 * bp] = rb.x; r2[2 * bp + 1] = rb.y;
+            }
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) m[a][b] = fmin(m[a][b], fmin(c1[a] + r1[b], c2[a] + r2[b]));
+        }
+    }
+    // Pivot rows / columns inside this tile belong to P1 / P2 and other CTAs are reading them as operands:
+    // they are never written here (in exact arithmetic nothing would improve; skipping them keeps the
+    // result independent of rounding and of the order the CTAs run in).
+    uint16_t* rr = rounds ? rounds + obase : nullptr;
+    const int piv_row_half = (2 * bi == kb) ? 0 : (2 * bi + 1 == kb) ? 1 : -1;     // which 64-row half is pivot
+    const int piv_col_half = (2 * bj == kb) ? 0 : (2 * bj + 1 == kb) ? 1 : -1;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int row = (a < 4) ? 4 * ty + a : 64 + 4 * ty + (a - 4);
+        if ((a < 4 ? 0 : 1) == piv_row_half) continue;
+#pragma unroll
+        for (int bp = 0; bp < 4; ++bp) {
+            const int col = (bp < 2) ? 4 * tx + 2 * bp : 64 + 4 * tx + 2 * (bp - 2);
+            if ((bp < 2 ? 0 : 1) == piv_col_half) continue;
+            double* p = dist + obase + (int64_t)row * ld + col;
+            double2 d2 = *reinterpret_cast<const double2*>(p);
+            bool any = false;
+            if (m[a][2 * bp] < d2.x) { d2.x = m[a][2 * bp]; any = true; if (rr) rr[(int64_t)row * ld + col] = (uint16_t)kb; }
+            if (m[a][2 * bp + 1] < d2.y) { d2.y = m[a][2 * bp + 1]; any = true; if (rr) rr[(int64_t)row * ld + col + 1] = (uint16_t)kb; }
+            if (any) *reinterpret_cast<double2*>(p) = d2;
+        }
     }
 }
 
@@ -548,7 +601,7 @@ template <> struct FwCfg<float> {
 };
 template <> struct FwCfg<double> {
     static constexpr int B = kB64;
-    static int p3_smem() { return 2 * kB64 * kB64 * (int)sizeof(double); }
+    static int p3_smem() { return kP3Smem64; }
     static constexpr int p3_threads = 256;
 };
 
@@ -582,7 +635,8 @@ inline void launch_p3(float* dist, int64_t ld, const float* panel, int64_t ldp, 
 }
 inline void launch_p3(double* dist, int64_t ld, const double* panel, int64_t ldp, int kb, int skip, int nb, int nl,
                       int part, int next_col, int next_row, uint16_t* rounds, cudaStream_t st) {
-    const dim3 grid = part == 1 ? dim3(nl + nb) : dim3(nb, nl);
+    const int nb2 = (nb + 1) / 2, nl2 = (nl + 1) / 2;         // the FP64 P3 works on 128-tiles
+    const dim3 grid = part == 1 ? dim3(nl2 + nb2) : dim3(nb2, nl2);
     fw64_p3_kernel<<<grid, 256, FwCfg<double>::p3_smem(), st>>>(dist, ld, panel, ldp, kb, skip, nb, nl, part,
                                                                next_col, next_row, rounds);
 }

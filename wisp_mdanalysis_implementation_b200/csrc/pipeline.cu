@@ -26,9 +26,14 @@
 #include <condition_variable>
 #include <cstring>
 #include <mutex>
+#include <chrono>
 #include <thread>
 
 namespace {
+
+double host_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 // Host barrier over the shard threads.  abort() releases everybody, now and at every later wait():
 // a shard that fails can never leave the others blocked inside a reduction.
@@ -74,6 +79,8 @@ struct Shared {
     std::vector<std::vector<double>> slots;     // per-shard host vectors for the small reductions
     std::vector<const double*> d_gram, d_dsum;  // per-shard partial sums (device pointers)
     std::vector<int> can_p2p;                   // [R*R]
+    wisp_ctx* root = nullptr;                   // stage timings of shard 0 go to root->pipe_stats
+    double t_begin = 0.0;
     explicit Shared(int r) : R(r), bar(r), slots(r), d_gram(r, nullptr), d_dsum(r, nullptr) {}
 };
 
@@ -114,6 +121,7 @@ int shard_body(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
     const size_t nn = (size_t)N * N;
     WISP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    const double t_begin = host_ms();
     // ---- S1: H2D || K1 ----
     float* d_align = nullptr;
     if (a.max_align_iterations > 0) {
@@ -125,6 +133,7 @@ int shard_body(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
     int64_t ldx = 0;
     WISP_TRY(wisp_com_from_host(ctx, a.coords + (size_t)t0 * a.A * 3, Tl, a.A, a.masses, a.node_ptr, a.atom_idx, N,
                                 a.align_idx, a.n_align, a.atomic, &d_x, &ldx, d_align));
+    const double t_s1 = host_ms();
     // small device vectors + the partial sums live in this shard's arena
     void* pw = nullptr;
     const size_t work_d = (size_t)(2 * round_up(na3, 32) + round_up(nn3, 32)) + 2 * (size_t)ld;
@@ -153,6 +162,7 @@ int shard_body(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
         if (r == 0 && a.out_n_iter) *a.out_n_iter = n_iter;
         have_mean = true;       // the node average of the last iteration IS the frame mean (:112)
     }
+    const double t_s2 = host_ms();
     // ---- S3: mean, centring, K2, K3 ----
     if (!have_mean) {
         WISP_TRY(launch_colsum(ctx, d_x, Tl, ld, nn3, d_sum, st));
@@ -173,6 +183,11 @@ int shard_body(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
     WISP_TRY(launch_gram(ctx, d_x, Tl, ld, N, 3, d_gram, st));
     WISP_TRY(launch_contact_sum(ctx, (const float*)pp, Tl, N, d_mean, d_dsum, st));
     WISP_CUDA(cudaStreamSynchronize(st));     // `mean` (host) was the source of an async copy; partials complete
+    if (r == 0) {
+        double* ps = S.root->pipe_stats;
+        ps[0] = t_s1 - t_begin; ps[1] = t_s2 - t_s1; ps[2] = host_ms() - t_s2; ps[7] = (double)R;
+        S.t_begin = t_begin;
+    }
     return 0;
 }
 
@@ -181,6 +196,7 @@ int shard_finish(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
     const int64_t n_pad = round_up(N, kTile);
     WISP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    const double t_fin = host_ms();
     // row slice of the outputs this GPU produces
     const int row0 = (int)((int64_t)N * r / R), row1 = (int)((int64_t)N * (r + 1) / R), rows = row1 - row0;
     if (rows <= 0) return 0;
@@ -217,6 +233,12 @@ int shard_finish(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
     if (a.out_binary) WISP_CUDA(cudaMemcpyAsync(a.out_binary + off, d_binary, sl * 8, cudaMemcpyDeviceToHost, st));
     if (a.out_w) WISP_CUDA(cudaMemcpyAsync(a.out_w + off, d_w, sl * 8, cudaMemcpyDeviceToHost, st));
     WISP_CUDA(cudaStreamSynchronize(st));
+    if (r == 0) {
+        double* ps = S.root->pipe_stats;
+        ps[3] = t_fin - (S.t_begin + ps[0] + ps[1] + ps[2]);      // waiting for the slowest shard
+        ps[4] = host_ms() - t_fin;
+        ps[5] = host_ms() - S.t_begin;
+    }
     return 0;
 }
 
@@ -251,6 +273,7 @@ int wisp_pipeline_run(wisp_ctx* ctx, const float* coords, int64_t T, int A, cons
     R = std::min(R, N);
     ctxs.resize(R);
     Shared S(R);
+    S.root = ctx;
     S.can_p2p.assign((size_t)R * R, 1);
     for (int p = 0; p < R; ++p)
         for (int q = 0; q < R; ++q)
@@ -320,6 +343,14 @@ extern "C" int wisp_ctx_create_multi(int n_gpus, const int* devices, wisp_ctx** 
     }
     cudaSetDevice(devs[0]);
     *out = root;
+    return 0;
+}
+
+// shard 0's host-clock view of the last wisp_pipeline: [0] H2D || K1, [1] K7, [2] centring + K2 + K3,
+// [3] waiting for the slowest shard, [4] fused epilogue + D2H, [5] total (ms), [6] unused, [7] shards
+extern "C" int wisp_pipeline_stats(wisp_ctx* ctx, double* out8) {
+    WISP_CHECK(ctx && out8, "pipeline_stats: null argument");
+    memcpy(out8, ctx->pipe_stats, sizeof(ctx->pipe_stats));
     return 0;
 }
 
