@@ -138,7 +138,8 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
                   int P, const double* __restrict__ shift, const int4* __restrict__ node_info,
                   const double* __restrict__ ent_mass, const double* __restrict__ inv_node_mass,
                   double* __restrict__ nodes, int64_t ld, int64_t row0, int64_t total_bytes,
-                  double* __restrict__ colpart) {
+                  double* __restrict__ colpart, const int32_t* __restrict__ lm_ptr,
+                  const int2* __restrict__ lm_ent, float* __restrict__ align_out, int n_align) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full[kStStages], empty[kStStages];
     double* smass = reinterpret_cast<double*>(smem_raw + (size_t)kStStages * kStageBytes);
@@ -221,6 +222,7 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
 
     // ---------------- compute warps ----------------
     const uint32_t smem_base = smem_u32(smem_raw);
+    const int lm_lo = align_out ? __ldg(lm_ptr + p) : 0, lm_hi = align_out ? __ldg(lm_ptr + p + 1) : 0;
     double cs0 = 0.0, cs1 = 0.0;      // column sums of what this lane stores, over this CTA's frames
     for (int64_t k = 0; k < n_items; ++k) {
         const int slot = (int)(k % kStStages);
@@ -245,6 +247,19 @@ com_stream_kernel(const float* __restrict__ coords, int64_t T, int A, const Piec
                 ay = fma(m, vy, ay);
                 az = fma(m, vz, az);
                 u = (u + 1 == cnt_h) ? 0 : u + 1;
+            }
+        }
+        if (align_out) {
+            // the translated alignment landmarks of this piece (all_pos_Align, :72) leave from the staged
+            // copy as well: entry = (atom offset inside the piece, landmark index); no second gather
+            const uint32_t p_addr = smem_base + (uint32_t)slot * kStageBytes + (uint32_t)(src & 15);
+            float* ao = align_out + (row0 + f) * (int64_t)n_align * 3;
+            for (int e = lm_lo + tid; e < lm_hi; e += kStThreads) {
+                const int2 ent = __ldg(lm_ent + e);
+                const uint32_t qa = p_addr + 12u * (uint32_t)ent.x;
+                ao[3 * ent.y + 0] = __double2float_rn((double)lds_f32(qa) + hx);
+                ao[3 * ent.y + 1] = __double2float_rn((double)lds_f32(qa + 4) + hy);
+                ao[3 * ent.y + 2] = __double2float_rn((double)lds_f32(qa + 8) + hz);
             }
         }
         __syncwarp();
@@ -287,6 +302,11 @@ struct wisp_com_plan {
     double *d_align_mass = nullptr, *d_ent_mass = nullptr, *d_inv_node_mass = nullptr;
     int4* d_node_info = nullptr;
     Piece* d_pieces = nullptr;
+    // alignment landmarks grouped by the piece that stages their atom: lm_ptr [P+1], lm_ent = (atom
+    // offset inside the piece, landmark index); lm_fused: every landmark atom lies inside some piece
+    int32_t* d_lm_ptr = nullptr;
+    int2* d_lm_ent = nullptr;
+    bool lm_fused = false;
     double* d_shift = nullptr;
     int64_t shift_frames = 0;
 };
@@ -355,6 +375,31 @@ int com_plan_create(wisp_ctx* ctx, int A, const double* masses, const int32_t* n
     }
     pl->streaming = contiguous && !h_pieces.empty() && getenv("WISP_K1_GATHER") == nullptr;
     pl->P = (int)h_pieces.size();
+    std::vector<int32_t> h_lm_ptr(h_pieces.size() + 1, 0);
+    std::vector<int2> h_lm_ent;
+    if (pl->streaming) {
+        // piece of every landmark atom (pieces are sorted by atom0 and do not overlap)
+        std::vector<std::vector<int2>> per_piece(h_pieces.size());
+        bool all_inside = true;
+        for (int a = 0; a < n_align && all_inside; ++a) {
+            const int atom = align_idx[a];
+            int lo = 0, hi = (int)h_pieces.size() - 1, found = -1;
+            while (lo <= hi) {
+                const int mid = (lo + hi) / 2;
+                if (atom < h_pieces[mid].atom0) hi = mid - 1;
+                else if (atom >= h_pieces[mid].atom0 + h_pieces[mid].n_atoms) lo = mid + 1;
+                else { found = mid; break; }
+            }
+            if (found < 0) all_inside = false;
+            else per_piece[found].push_back(make_int2(atom - h_pieces[found].atom0, a));
+        }
+        pl->lm_fused = all_inside && getenv("WISP_K1_LANDMARK_GATHER") == nullptr;
+        if (pl->lm_fused)
+            for (size_t q = 0; q < h_pieces.size(); ++q) {
+                for (const int2& e : per_piece[q]) h_lm_ent.push_back(e);
+                h_lm_ptr[q + 1] = (int32_t)h_lm_ent.size();
+            }
+    }
     std::vector<int4> h_info(N);
     std::vector<double> h_inv(N);
     for (int n = 0; n < N; ++n) { h_info[n] = make_int4(node_ptr[n], node_ptr[n + 1] - node_ptr[n], 0, 0); h_inv[n] = 1.0 / h_node_mass[n]; }
@@ -363,7 +408,8 @@ int com_plan_create(wisp_ctx* ctx, int A, const double* masses, const int32_t* n
     int rc = upload(h_masses, &pl->d_masses) || upload(h_np, &pl->d_node_ptr) || upload(h_ai, &pl->d_atom_idx) ||
              upload(h_al, &pl->d_align_idx) || upload(h_align_mass, &pl->d_align_mass) ||
              upload(h_ent_mass, &pl->d_ent_mass) || upload(h_inv, &pl->d_inv_node_mass) ||
-             upload(h_info, &pl->d_node_info) || upload(h_pieces, &pl->d_pieces);
+             upload(h_info, &pl->d_node_info) || upload(h_pieces, &pl->d_pieces) ||
+             upload(h_lm_ptr, &pl->d_lm_ptr) || upload(h_lm_ent, &pl->d_lm_ent);
     if (rc) { com_plan_destroy(ctx, pl); return 1; }
     *out = pl;
     return 0;
@@ -376,6 +422,7 @@ void com_plan_destroy(wisp_ctx* ctx, wisp_com_plan* pl) {
     cudaFree(pl->d_masses); cudaFree(pl->d_node_ptr); cudaFree(pl->d_atom_idx); cudaFree(pl->d_align_idx);
     cudaFree(pl->d_align_mass); cudaFree(pl->d_ent_mass); cudaFree(pl->d_inv_node_mass);
     cudaFree(pl->d_node_info); cudaFree(pl->d_pieces); cudaFree(pl->d_shift);
+    cudaFree(pl->d_lm_ptr); cudaFree(pl->d_lm_ent);
     delete pl;
 }
 
@@ -400,9 +447,13 @@ int launch_com_plan(wisp_ctx* ctx, wisp_com_plan* pl, const float* d_coords, int
         WISP_CUDA(cudaMalloc((void**)&pl->d_shift, (size_t)T * 3 * 8));
         pl->shift_frames = T;
     }
+    // the landmark positions leave from the streaming kernel's staged copy when every landmark atom is
+    // inside a piece (the usual case: alignment atoms are node atoms); otherwise the gather kernel
+    // writes them (a second, sector-granular pass over the landmarks)
+    const bool lm_fused = d_align_out && pl->lm_fused;
     align_shift_kernel<<<(unsigned)((T + 7) / 8), 256, 0, st>>>(d_coords, T, pl->A, pl->d_align_idx,
                                                                pl->d_align_mass, pl->n_align, pl->d_shift,
-                                                               d_align_out, row0);
+                                                               lm_fused ? nullptr : d_align_out, row0);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
     const int smem = kStStages * kStageBytes + kPieceAtomsMax * 8;
@@ -418,7 +469,8 @@ int launch_com_plan(wisp_ctx* ctx, wisp_com_plan* pl, const float* d_coords, int
     }
     com_stream_kernel<<<P * per_piece, kStLaunchThreads, smem, st>>>(
         d_coords, T, pl->A, pl->d_pieces, P, pl->d_shift, pl->d_node_info, pl->d_ent_mass,
-        pl->d_inv_node_mass, d_nodes, ld, row0, (int64_t)T * pl->A * 12, d_colpart);
+        pl->d_inv_node_mass, d_nodes, ld, row0, (int64_t)T * pl->A * 12, d_colpart, pl->d_lm_ptr, pl->d_lm_ent,
+        lm_fused ? d_align_out : nullptr, pl->n_align);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
     if (d_colsum) WISP_TRY(launch_colsum_finish(ctx, d_colpart, per_piece, ld, 3 * (int64_t)pl->N, d_colsum, st));

@@ -303,7 +303,7 @@ __constant__ int kDiagSubCol[16] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3, 0, 0, 1, 0, 1,
 template <int UNROLL>
 __global__ void __launch_bounds__(kWsThreads, 1)
 contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const double* __restrict__ mean,
-                      int n_tiles, int n_seg, double* __restrict__ out, int64_t out_ld) {
+                      int n_tiles, int n_seg, double* __restrict__ out, int64_t out_ld, int allow_idle) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ContactWsSmem& sm = *reinterpret_cast<ContactWsSmem*>(smem_raw);
 
@@ -393,12 +393,12 @@ contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
             ib0 = 32 * wr + 8 * (lane >> 3);
             ib1 = ib0 + 4;
             jb0 = 32 * wc + 4 * (lane & 7);
-            idle = w >= 10 || 32 * wr >= valid_i || 32 * wc >= valid_j;
+            idle = (w >= 10 || 32 * wr >= valid_i || 32 * wc >= valid_j) && allow_idle;
         } else {
             ib0 = 4 * (tid & 15);
             ib1 = 64 + ib0;
             jb0 = 4 * (tid >> 4);
-            idle = 8 * w >= valid_j;
+            idle = 8 * w >= valid_j && allow_idle;
         }
     }
     f32x2 acc[8][JH];
@@ -512,6 +512,7 @@ int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, cons
     const int smem = (int)sizeof(ContactSmem);
     dim3 grid(n_items, n_seg);
     static const int variant = getenv("WISP_K3_VARIANT") ? atoi(getenv("WISP_K3_VARIANT")) : 58;
+    const int allow_idle = getenv("WISP_K3_NOIDLE") ? 0 : 1;      // experiment switch: every warp computes its block
 #define WISP_K3_LAUNCH(JH_, UN_)                                                                          \
     do {                                                                                                  \
         WISP_CUDA(cudaFuncSetAttribute(contact_sum_kernel<JH_, UN_>,                                      \
@@ -526,7 +527,7 @@ int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, cons
         WISP_CUDA(cudaFuncSetAttribute(contact_sum_ws_kernel<UN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        smem_ws));                                                               \
         contact_sum_ws_kernel<UN_><<<grid, kWsThreads, smem_ws, st>>>(d_p32, T, N, d_mean, n_tiles, n_seg, part, \
-                                                                      n_pad);                                   \
+                                                                      n_pad, allow_idle);                       \
     } while (0)
         if (variant == 51) WISP_K3_WS(1);      // frame loop not unrolled: 30.1 ms at C2 with 8-frame stages
         else WISP_K3_WS(8);                    // 58 (default)

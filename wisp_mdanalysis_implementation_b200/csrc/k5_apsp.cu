@@ -46,7 +46,7 @@ template <typename T> __device__ __forceinline__ T inf_v();
 template <> __device__ __forceinline__ float inf_v<float>() { return __int_as_float(0x7f800000); }
 template <> __device__ __forceinline__ double inf_v<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
 __device__ __forceinline__ float fw_min(float a, float b) { return fminf(a, b); }
-__device__ __forceinline__ double fw_min(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ double fw_min(double a, double b) { return b < a ? b : a; }     // fmin() lowers badly
 
 template <typename T>
 __global__ void fw_init_kernel(const double* __restrict__ w, int N, int64_t n_pad, int64_t row0, int64_t rows,
@@ -463,7 +463,13 @@ fw64_p3_kernel(double* __restrict__ dist, int64_t ld, const double* __restrict__
 #pragma unroll
             for (int a = 0; a < 8; ++a)
 #pragma unroll
-                for (int b = 0; b < 8; ++b) m[a][b] = fmin(m[a][b], fmin(c1[a] + r1[b], c2[a] + r2[b]));
+                for (int b = 0; b < 8; ++b) {
+                    // compare + select (DSETP + 2 FSEL); fmin() lowers to DSETP.MIN + SEL/FSEL + five moves
+                    const double u = c1[a] + r1[b], v = c2[a] + r2[b];
+                    double w = m[a][b];
+                    w = u < w ? u : w;
+                    m[a][b] = v < w ? v : w;
+                }
         }
     }
     // Pivot rows / columns inside this tile belong to P1 / P2 and other CTAs are reading them as operands:

@@ -107,47 +107,86 @@ align_solve_kernel(const float* __restrict__ align, int n_align, const double* _
     R[6] = 2 * (qz * qx - q0 * qy); R[7] = 2 * (qz * qy + q0 * qx); R[8] = q0 * q0 - qx * qx - qy * qy + qz * qz;
 }
 
-// x <- x . R^T (row vector times R transposed == R x) for every frame of segment blockIdx.y;
-// item = blockIdx.x * 128 + threadIdx.x: [0, n_align) landmarks (float32), then N nodes (float64).
-// part [n_seg][3 n_align + 3 N]: column sums of the values STORED by this segment.
+// x <- x . R^T (row vector times R transposed == R x) for every frame of segment blockIdx.y.
+// A CTA owns 128 consecutive landmarks (float32; blocks [0, gl)) or nodes (float64; blocks [gl, ..)),
+// i.e. 384 consecutive columns of a frame row.  Global traffic is fully coalesced: thread t moves columns
+// t, t+128, t+256 of the span (four frames per step, all loads in flight together), the (x, y, z) triples
+// are regrouped through shared memory, and the running sums of the columns a thread STORES stay in its
+// registers.  (A thread-per-node version with three stride-24-byte accesses per frame ran at 2.5 TB/s:
+// partial-sector stores.)  part [n_seg][3 n_align + 3 N]: column sums of the values stored by a segment.
 constexpr int kApplyThreads = 128;
+constexpr int kApplyFrames = 4;
+
+template <typename T>
+__device__ __forceinline__ void align_apply_block(T* __restrict__ base, int64_t row_stride, int n_items, int item0,
+                                                  int64_t f0, int64_t f1, const double* __restrict__ rot,
+                                                  double* __restrict__ part_cols, T (*sm)[3 * kApplyThreads]) {
+    const int t = threadIdx.x;
+    const int ncol = 3 * min(kApplyThreads, n_items - item0);
+    const int64_t col0 = 3 * (int64_t)item0;
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int64_t f = f0; f < f1; f += kApplyFrames) {
+        const int nf = (int)min((int64_t)kApplyFrames, f1 - f);
+        T v[kApplyFrames][3];
+#pragma unroll
+        for (int q = 0; q < kApplyFrames; ++q)
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int c = t + kApplyThreads * u;
+                v[q][u] = (q < nf && c < ncol) ? base[(f + q) * row_stride + col0 + c] : (T)0;
+            }
+#pragma unroll
+        for (int q = 0; q < kApplyFrames; ++q)
+#pragma unroll
+            for (int u = 0; u < 3; ++u) sm[q][t + kApplyThreads * u] = v[q][u];
+        __syncthreads();
+        if (3 * t < ncol) {
+#pragma unroll
+            for (int q = 0; q < kApplyFrames; ++q)
+                if (q < nf) {
+                    const double* R = rot + (f + q) * 9;
+                    const double x = (double)sm[q][3 * t], y = (double)sm[q][3 * t + 1], z = (double)sm[q][3 * t + 2];
+                    sm[q][3 * t + 0] = (T)(x * __ldg(R + 0) + y * __ldg(R + 1) + z * __ldg(R + 2));
+                    sm[q][3 * t + 1] = (T)(x * __ldg(R + 3) + y * __ldg(R + 4) + z * __ldg(R + 5));
+                    sm[q][3 * t + 2] = (T)(x * __ldg(R + 6) + y * __ldg(R + 7) + z * __ldg(R + 8));
+                }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kApplyFrames; ++q)
+            if (q < nf) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int c = t + kApplyThreads * u;
+                    if (c < ncol) {
+                        const T o = sm[q][c];
+                        base[(f + q) * row_stride + col0 + c] = o;
+                        s[u] += (double)o;
+                    }
+                }
+            }
+        // (the next step's shared-memory writes of this thread go to the very slots it has just read)
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        const int c = t + kApplyThreads * u;
+        if (c < ncol) part_cols[col0 + c] = s[u];
+    }
+}
+
 __global__ void __launch_bounds__(kApplyThreads)
 align_apply_kernel(float* __restrict__ align, int n_align, double* __restrict__ nodes, int64_t ld, int N,
                    int64_t T, const double* __restrict__ rot, int64_t frames_per_seg, double* __restrict__ part) {
-    const int item = blockIdx.x * kApplyThreads + threadIdx.x;
-    if (item >= n_align + N) return;
+    __shared__ __align__(16) double smd[kApplyFrames][3 * kApplyThreads];
+    const int gl = (n_align + kApplyThreads - 1) / kApplyThreads;      // landmark blocks come first
     const int64_t f0 = (int64_t)blockIdx.y * frames_per_seg, f1 = min(T, f0 + frames_per_seg);
-    double sx = 0.0, sy = 0.0, sz = 0.0;
-    if (item < n_align) {
-        float* p = align + 3 * (int64_t)item;
-        const int64_t stride = 3 * (int64_t)n_align;
-#pragma unroll 4
-        for (int64_t f = f0; f < f1; ++f) {
-            const double* R = rot + f * 9;
-            float* q = p + f * stride;
-            const double x = q[0], y = q[1], z = q[2];
-            const float ox = (float)(x * __ldg(R + 0) + y * __ldg(R + 1) + z * __ldg(R + 2));
-            const float oy = (float)(x * __ldg(R + 3) + y * __ldg(R + 4) + z * __ldg(R + 5));
-            const float oz = (float)(x * __ldg(R + 6) + y * __ldg(R + 7) + z * __ldg(R + 8));
-            q[0] = ox; q[1] = oy; q[2] = oz;
-            sx += (double)ox; sy += (double)oy; sz += (double)oz;
-        }
-    } else {
-        double* p = nodes + 3 * (int64_t)(item - n_align);
-#pragma unroll 4
-        for (int64_t f = f0; f < f1; ++f) {
-            const double* R = rot + f * 9;
-            double* q = p + f * ld;
-            const double x = q[0], y = q[1], z = q[2];
-            const double ox = x * __ldg(R + 0) + y * __ldg(R + 1) + z * __ldg(R + 2);
-            const double oy = x * __ldg(R + 3) + y * __ldg(R + 4) + z * __ldg(R + 5);
-            const double oz = x * __ldg(R + 6) + y * __ldg(R + 7) + z * __ldg(R + 8);
-            q[0] = ox; q[1] = oy; q[2] = oz;
-            sx += ox; sy += oy; sz += oz;
-        }
-    }
-    double* out = part + (int64_t)blockIdx.y * (3 * (int64_t)(n_align + N)) + 3 * (int64_t)item;
-    out[0] = sx; out[1] = sy; out[2] = sz;
+    double* prow = part + (int64_t)blockIdx.y * (3 * (int64_t)(n_align + N));
+    if ((int)blockIdx.x < gl)
+        align_apply_block<float>(align, 3 * (int64_t)n_align, n_align, blockIdx.x * kApplyThreads, f0, f1, rot, prow,
+                                 reinterpret_cast<float (*)[3 * kApplyThreads]>(smd));
+    else
+        align_apply_block<double>(nodes, ld, N, (blockIdx.x - gl) * kApplyThreads, f0, f1, rot,
+                                  prow + 3 * (int64_t)n_align, smd);
 }
 
 // np.sum(float32 array, axis=0) of the reference (:86): sequential float32 adds down the frames.
@@ -224,7 +263,8 @@ int launch_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double
     double* d_rot = (double*)pr;
     align_solve_kernel<<<(unsigned)((T + kAlThreads / 32 - 1) / (kAlThreads / 32)), kAlThreads, 0, st>>>(
         d_align, n_align, d_avg_align, T, d_rot);
-    const int items = n_align + N, gx = (items + kApplyThreads - 1) / kApplyThreads;
+    const int items = n_align + N;
+    const int gx = (n_align + kApplyThreads - 1) / kApplyThreads + (N + kApplyThreads - 1) / kApplyThreads;
     int n_seg = (int)std::max<int64_t>(1, std::min<int64_t>(T, (int64_t)ctx->sm_count * 6 / gx));
     const int64_t per = (T + n_seg - 1) / n_seg;
     n_seg = (int)((T + per - 1) / per);
