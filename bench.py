@@ -278,8 +278,13 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # a barrier that leaves the GPUs alone: while rank 0 drives all N GPUs through the in-process
+        # wisp_pipeline call, the other ranks must wait on the CPU (an NCCL barrier is a spinning kernel
+        # on every other GPU and gets time-sliced against the call's own kernels)
+        cpu_group = dist.new_group(backend="gloo")
     dev = torch.device("cuda", local_rank)
     ctx = _lib.default_context(local_rank)
 
@@ -310,6 +315,11 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def cpu_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
 
     def max_over_ranks(ms):
         if world == 1:
@@ -531,7 +541,7 @@ def main():
             torch.cuda.synchronize()
         else:
             h_np = h_local.numpy()
-        barrier()
+        cpu_barrier()
         if rank == 0:
             mctx = _lib.Context(gpus=world) if world > 1 else ctx
             outbuf = {"avg": pinned((N, 3), torch.float64).numpy(), "corr": pinned((N, N), torch.float64).numpy(),
@@ -561,7 +571,7 @@ def main():
             e2e_corr = res_call["corr"].copy()
             e2e_avgdist = res_call["avgdist"].copy()
             e2e_iters = len(res_call["alignment_log"])
-        barrier()
+        cpu_barrier()
         if rank == 0:
             h2d_total = T * A * 12
             e2e = {"value": float(N) * N * T / (ms_call * 1e-3), "unit": UNIT, "ms_per_step": ms_call,

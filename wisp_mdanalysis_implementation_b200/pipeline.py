@@ -175,25 +175,27 @@ class FramePipeline:
         else:
             sn = self.d_align_sums[na3:].cpu().numpy().copy()
         sa = self.d_align_sums[:na3].cpu().numpy().astype(np.float32)
-        avg_a = (sa / np.float32(self.T_total)).astype(np.float64)
-        avg_n = sn / float(self.T_total)
+        # averages stay on the device; one scalar pair per iteration comes back for the loop decision
+        d_avg_a = torch.from_numpy((sa / np.float32(self.T_total)).astype(np.float64)).to(self.dev)
+        d_avg_n = torch.from_numpy(sn / float(self.T_total)).to(self.dev)
         self.alignment_log = []
         residual, it = self.align_threshold + 9999.0, 0
         while residual > self.align_threshold and it < self.align_iterations:
-            self.d_avg_align.copy_(torch.from_numpy(avg_a))
+            self.d_avg_align.copy_(d_avg_a)
             self.ctx.dev_align_rotate(self.d_align.data_ptr(), self.n_align, self.d_avg_align.data_ptr(),
                                       self.d_x.data_ptr(), self.T, self.N, d_sums=self.d_align_sums.data_ptr(),
                                       stream=s)
             sharding.reduce_sums(self.d_align_sums, group=self.group)
-            h = self.d_align_sums.cpu().numpy() / float(self.T_total)
-            new_a, new_n = h[:na3], h[na3:]
-            residual = float(np.sqrt(np.sum((avg_a - new_a) ** 2) / self.n_align))
-            node_rmsd = float(np.sqrt(np.sum((avg_n - new_n) ** 2) / self.N))
-            avg_a, avg_n = new_a.copy(), new_n.copy()
+            new = self.d_align_sums / float(self.T_total)            # (same division as the reference, :112-113)
+            new_a, new_n = new[:na3], new[na3:]
+            both = torch.stack((((d_avg_a - new_a) ** 2).sum() / self.n_align,
+                                ((d_avg_n - new_n) ** 2).sum() / self.N)).sqrt().cpu()
+            residual, node_rmsd = float(both[0]), float(both[1])
+            d_avg_a, d_avg_n = new_a.clone(), new_n.clone()
             it += 1
             self.alignment_log.append((it, residual, node_rmsd))
         self.d_mean.zero_()
-        self.d_mean[:nn3].copy_(torch.from_numpy(avg_n))
+        self.d_mean[:nn3].copy_(d_avg_n)
         return it
 
     def center_on_mean(self):
