@@ -544,6 +544,7 @@ def main():
         cpu_barrier()
         if rank == 0:
             mctx = _lib.Context(gpus=world) if world > 1 else ctx
+            mctx_ingest = mctx.ingest_info()
             outbuf = {"avg": pinned((N, 3), torch.float64).numpy(), "corr": pinned((N, N), torch.float64).numpy(),
                       "avgdist": pinned((N, N), torch.float64).numpy(), "binary": pinned((N, N), torch.int64).numpy(),
                       "w": pinned((N, N), torch.float64).numpy()}
@@ -581,7 +582,7 @@ def main():
                    "api": "wisp_pipeline (C ABI, include/wisp_b200.h) on wisp_ctx_create_multi(%d): page-locked host "
                           "coordinates in; avg / corr / avgdist / binary / w in page-locked host buffers out; "
                           "K7 alignment included (%d iterations)" % (api_gpus, e2e_iters),
-                   "gpus_in_call": api_gpus,
+                   "gpus_in_call": api_gpus, "ingest": mctx_ingest,
                    "host_numa_node_per_shard": host_nodes,
                    "pcie_h2d_gbs_per_rank_concurrent": h2d_gbs_rank,
                    "pcie_h2d_gbs_aggregate_concurrent": h2d_gbs_aggregate,
@@ -727,6 +728,37 @@ def main():
         extra["get_paths"] = dict(source=s, sink=t, returned=len(paths), shortest=paths[0][0],
                                   longest=paths[-1][0], **ctx.paths_stats())
         extra["hops_apsp_wall_ms"] = t_hops * 1e3
+        # ---- the north-star run in one number: page-locked host coordinates -> wisp_pipeline on all N GPUs
+        # (K1, K7, K2, K3, fused cross-GPU K4) -> APSP (FP64, predecessors) + 500 suboptimal paths, with the
+        # matrices checked against the oracle on the frame prefix (parity) and the paths checked here ----
+        if e2e is not None:
+            import scipy.sparse
+            import scipy.sparse.csgraph
+            ok = len(paths) == args.paths or len(paths) == args.paths + 1
+            lens = [p[0] for p in paths]
+            ok &= all(lens[i] <= lens[i + 1] for i in range(len(lens) - 1))
+            seen = set()
+            for p in paths:
+                nodes = p[1:]
+                lr = 0.0
+                for a, b in zip(nodes[:-1], nodes[1:]):
+                    ok &= W[a, b] != 0
+                    lr += W[a, b]
+                ok &= nodes[0] == s and nodes[-1] == t and len(set(nodes)) == len(nodes) and lr == p[0]
+                ok &= tuple(nodes) not in seen
+                seen.add(tuple(nodes))
+            d_ref = scipy.sparse.csgraph.dijkstra(scipy.sparse.csr_matrix(W), directed=True, indices=[s])[0]
+            ok &= abs(paths[0][0] - d_ref[t]) <= 1e-12 * max(1.0, d_ref[t])
+            extra["north_star"] = {
+                "what": "coordinates (page-locked host memory) -> correlation + contacts on %d GPU(s) -> APSP -> %d "
+                        "suboptimal paths" % (world, args.paths),
+                "pipeline_call_ms": e2e["ms_per_step"], "apsp_and_paths_ms": extra["get_paths_wall_ms"],
+                "total_ms": e2e["ms_per_step"] + extra["get_paths_wall_ms"],
+                "matrices_checked": "parity (oracle on the %d-frame prefix)" % args.parity_frames,
+                "matrices_pass": bool(parity["pass"]) if parity else None,
+                "paths_checked": "count K or K+1, sorted, simple, every hop an edge, LR float64 lengths bit-exact, "
+                                 "no duplicates, shortest == scipy Dijkstra",
+                "paths_pass": bool(ok)}
         # configs[4]: 200 (source, sink) pairs x 1,000 suboptimal paths each, one APSP
         if args.stress_pairs > 0:
             rng = np.random.default_rng(1005)

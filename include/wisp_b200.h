@@ -38,6 +38,13 @@ int         wisp_ctx_create(int device, wisp_ctx** out);
  * uses the first device. */
 int         wisp_ctx_create_multi(int n_gpus, const int* devices, wisp_ctx** out);
 int         wisp_ctx_gpus(wisp_ctx* ctx);
+/* How the coordinates reach the GPUs of a multi-GPU context.  wisp_ctx_create_multi measures the
+ * concurrent host->device rate of every GPU (4+ distinct GPUs; $WISP_INGEST = auto | direct | relay); where a
+ * group of GPUs shares a slow upstream link and pulling through the fast GPUs alone moves more bytes per
+ * second, each slow GPU is fed by a fast partner: host -> partner HBM -> NVLink peer copy.
+ * via [n_gpus]: relaying GPU (shard index) of every shard (itself = direct); rates [2 n_gpus + 2]: GB/s per
+ * GPU with all GPUs pulling, with only the fast set pulling, then the two aggregates (zeros: no probe). */
+int         wisp_ctx_ingest_info(wisp_ctx* ctx, int* via, double* rates);
 /* Page-lock a caller-owned host range (e.g. the MemoryReader coordinate array) so that the chunked
  * H2D copies of wisp_pipeline / wisp_com_nodes run asynchronously at full PCIe rate from every GPU. */
 int         wisp_host_register(void* ptr, size_t bytes);

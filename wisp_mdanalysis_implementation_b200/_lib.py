@@ -24,6 +24,7 @@ SIGNATURES = {
     "wisp_ctx_create": (_int, [_int, C.POINTER(_c_ctx)]),
     "wisp_ctx_create_multi": (_int, [_int, _P, C.POINTER(_c_ctx)]),
     "wisp_ctx_gpus": (_int, [_c_ctx]),
+    "wisp_ctx_ingest_info": (_int, [_c_ctx, _P, _P]),
     "wisp_host_register": (_int, [_P, C.c_size_t]),
     "wisp_host_unregister": (_int, [_P]),
     "wisp_ctx_destroy": (None, [_c_ctx]),
@@ -150,6 +151,16 @@ class Context:
         if rc != 0:
             raise WispError(self._lib.wisp_last_error().decode())
         self.n_gpus = int(self._lib.wisp_ctx_gpus(self._ctx))
+
+    def ingest_info(self):
+        """How the coordinates reach the GPUs (see wisp_ctx_ingest_info)."""
+        n = self.n_gpus
+        via = np.zeros(n, dtype=np.int32)
+        rates = np.zeros(2 * n + 2)
+        self._check(self._lib.wisp_ctx_ingest_info(self._ctx, _ptr(via), _ptr(rates)))
+        return dict(via=via.tolist(), h2d_gbs_all_pulling=rates[:n].round(1).tolist(),
+                    h2d_gbs_fast_set_pulling=rates[n:2 * n].round(1).tolist(),
+                    aggregate_all=round(float(rates[2 * n]), 1), aggregate_fast_set=round(float(rates[2 * n + 1]), 1))
 
     def close(self):
         if getattr(self, "_ctx", None):

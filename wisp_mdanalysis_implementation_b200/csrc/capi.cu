@@ -61,6 +61,7 @@ extern "C" void wisp_ctx_destroy(wisp_ctx* ctx) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->relay_stream) cudaStreamDestroy(ctx->relay_stream);      // (lives on the relaying GPU; the handle is process-wide)
     for (auto& e : ctx->aux_events) if (e) cudaEventDestroy(e);
     delete ctx;
 }
@@ -176,14 +177,18 @@ int com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const do
                   int n_align, int atomic, double** d_x_out, int64_t* ld_out,
                   float* d_align_out = nullptr) {
     return wisp_com_from_host(ctx, coords, T, A, masses, node_ptr, atom_idx, N, align_idx, n_align, atomic,
-                              d_x_out, ld_out, d_align_out);
+                              d_x_out, ld_out, d_align_out, nullptr);
 }
 
 }  // namespace
 
+// `via` (may be NULL): another GPU's context through which this shard's coordinates travel -- host ->
+// via's HBM over via's PCIe link -> this GPU over NVLink (peer copy) -- used when this GPU's own host link
+// is the slow one of the box (pipeline.cu: ingest topology).
 int wisp_com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
                        const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
-                       int n_align, int atomic, double** d_x_out, int64_t* ld_out, float* d_align_out) {
+                       int n_align, int atomic, double** d_x_out, int64_t* ld_out, float* d_align_out,
+                       wisp_ctx* via) {
     const int64_t ld = wisp_node_ld(N), Tpad = wisp_frames_pad(T);
     wisp_com_plan* plan = nullptr;
     WISP_TRY(com_plan_create(ctx, A, masses, node_ptr, atom_idx, N, align_idx, n_align, atomic, &plan));
@@ -196,38 +201,68 @@ int wisp_com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, con
     int64_t chunk = std::max<int64_t>(1, ((size_t)128 << 20) / frame_bytes);
     chunk = std::min(chunk, T);
     void* bufs[2] = {nullptr, nullptr};
+    void* relay[2] = {nullptr, nullptr};
     cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
     // every CUDA call is checked; the first failure is reported with its own message after the
     // events and the plan have been released
     cudaError_t err = cudaMemsetAsync(d_x, 0, (size_t)Tpad * ld * 8, st);
     const char* what = "cudaMemsetAsync(node trajectory)";
+    auto step = [&](cudaError_t e, const char* w) { if (err == cudaSuccess && e != cudaSuccess) { err = e; what = w; } };
     rc = wisp_scratch(ctx, SCR_COORDS0, (size_t)chunk * frame_bytes + 64, &bufs[0]);
     if (!rc) rc = wisp_scratch(ctx, SCR_COORDS1, (size_t)chunk * frame_bytes + 64, &bufs[1]);
-    for (int b = 0; b < 2 && !rc && err == cudaSuccess; ++b) {
-        err = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
-        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming);
-        what = "cudaEventCreate";
+    for (int b = 0; b < 2 && !rc && err == cudaSuccess; ++b) step(cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming), "cudaEventCreate");
+    cudaStream_t vs = nullptr;
+    if (via && !rc && err == cudaSuccess) {
+        // relay buffers, stream and the "copied" events live on the relaying GPU (one relayed shard per
+        // slot pair: this shard's index picks the slots)
+        step(cudaSetDevice(via->device), "cudaSetDevice(relay)");
+        const int slot = SCR_RELAY0 + 2 * (ctx->shard_index % kMaxPeers);
+        rc = wisp_scratch(via, slot, (size_t)chunk * frame_bytes + 64, &relay[0]);
+        if (!rc) rc = wisp_scratch(via, slot + 1, (size_t)chunk * frame_bytes + 64, &relay[1]);
+        if (!ctx->relay_stream) step(cudaStreamCreateWithFlags(&ctx->relay_stream, cudaStreamNonBlocking), "cudaStreamCreate(relay)");
+        vs = ctx->relay_stream;
+        for (int b = 0; b < 2 && !rc && err == cudaSuccess; ++b) step(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming), "cudaEventCreate");
+        step(cudaSetDevice(ctx->device), "cudaSetDevice");
+    } else {
+        for (int b = 0; b < 2 && !rc && err == cudaSuccess; ++b) step(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming), "cudaEventCreate");
     }
-    auto step = [&](cudaError_t e, const char* w) { if (err == cudaSuccess && e != cudaSuccess) { err = e; what = w; } };
     int it = 0;
     for (int64_t t0 = 0; t0 < T && rc == 0 && err == cudaSuccess; t0 += chunk, ++it) {
         const int b = it & 1;
         const int64_t nt = std::min(chunk, T - t0);
-        if (it >= 2) step(cudaStreamWaitEvent(cs, freed[b], 0), "cudaStreamWaitEvent(copy stream)");
-        step(cudaMemcpyAsync(bufs[b], coords + (size_t)t0 * A * 3, (size_t)nt * frame_bytes, cudaMemcpyHostToDevice, cs),
-             "cudaMemcpyAsync(coordinates H2D)");
-        step(cudaEventRecord(copied[b], cs), "cudaEventRecord(copied)");
+        const float* src = coords + (size_t)t0 * A * 3;
+        if (via) {
+            step(cudaSetDevice(via->device), "cudaSetDevice(relay)");
+            if (it >= 2) step(cudaStreamWaitEvent(vs, freed[b], 0), "cudaStreamWaitEvent(relay stream)");
+            step(cudaMemcpyAsync(relay[b], src, (size_t)nt * frame_bytes, cudaMemcpyHostToDevice, vs),
+                 "cudaMemcpyAsync(coordinates H2D, relay)");
+            step(cudaMemcpyPeerAsync(bufs[b], ctx->device, relay[b], via->device, (size_t)nt * frame_bytes, vs),
+                 "cudaMemcpyPeerAsync(relay -> shard)");
+            step(cudaEventRecord(copied[b], vs), "cudaEventRecord(copied)");
+            step(cudaSetDevice(ctx->device), "cudaSetDevice");
+        } else {
+            if (it >= 2) step(cudaStreamWaitEvent(cs, freed[b], 0), "cudaStreamWaitEvent(copy stream)");
+            step(cudaMemcpyAsync(bufs[b], src, (size_t)nt * frame_bytes, cudaMemcpyHostToDevice, cs),
+                 "cudaMemcpyAsync(coordinates H2D)");
+            step(cudaEventRecord(copied[b], cs), "cudaEventRecord(copied)");
+        }
         step(cudaStreamWaitEvent(st, copied[b], 0), "cudaStreamWaitEvent(compute stream)");
         if (err != cudaSuccess) break;
         rc = launch_com_plan(ctx, plan, (const float*)bufs[b], nt, d_x, ld, t0, st, d_align_out);
         step(cudaEventRecord(freed[b], st), "cudaEventRecord(freed)");
     }
-    step(cudaStreamSynchronize(cs), "cudaStreamSynchronize(copy stream)");
-    step(cudaStreamSynchronize(st), "cudaStreamSynchronize(compute stream)");
-    for (int b = 0; b < 2; ++b) {
-        if (copied[b]) cudaEventDestroy(copied[b]);
-        if (freed[b]) cudaEventDestroy(freed[b]);
+    if (via) {
+        step(cudaSetDevice(via->device), "cudaSetDevice(relay)");
+        step(cudaStreamSynchronize(vs), "cudaStreamSynchronize(relay stream)");
+        step(cudaSetDevice(ctx->device), "cudaSetDevice");
+    } else {
+        step(cudaStreamSynchronize(cs), "cudaStreamSynchronize(copy stream)");
     }
+    step(cudaStreamSynchronize(st), "cudaStreamSynchronize(compute stream)");
+    if (via) cudaSetDevice(via->device);
+    for (int b = 0; b < 2; ++b) if (copied[b]) cudaEventDestroy(copied[b]);
+    cudaSetDevice(ctx->device);
+    for (int b = 0; b < 2; ++b) if (freed[b]) cudaEventDestroy(freed[b]);
     com_plan_destroy(ctx, plan);
     if (rc) return rc;
     if (err != cudaSuccess) {

@@ -70,6 +70,10 @@ struct wisp_ctx {
     std::vector<int> peer_devices;           // device id of every shard, in shard order
     std::vector<int> peer_ok;                // [R][R] peer access enabled from shard p to shard q
     int64_t launches_reported = 0;           // (children) launches already added to the root's counter
+    int shard_index = 0;                     // position of this context among the shards
+    std::vector<int> ingest_via;             // (root) shard -> shard whose PCIe link carries its coordinates
+    std::vector<double> ingest_probe;        // (root) what the topology probe measured, for reporting
+    cudaStream_t relay_stream = nullptr;     // stream on the relaying GPU that feeds this shard
     int gram_mode = -1;              // WISP_GRAM_*; -1 = read $WISP_K2_MODE on first use
     // column statistics left by the last centring pass (launch_center) for the INT8 K2 engine:
     // valid for ONE following launch_gram on the same block and stream
@@ -79,7 +83,7 @@ struct wisp_ctx {
     cudaStream_t i8_stats_stream = nullptr;
     int64_t i8_stats_launch = -1;
     // grow-only scratch buffers, keyed by slot
-    DevBuf scratch[64];
+    DevBuf scratch[96];
     // get_paths results
     std::vector<double> path_len;
     std::vector<int64_t> path_off;
@@ -101,7 +105,8 @@ enum ScratchSlot {
     SCR_APSP_D, SCR_APSP_P, SCR_ARENA, SCR_ALIGN, SCR_P32,
     SCR_MISC0, SCR_MISC1, SCR_MISC2, SCR_MISC3, SCR_MISC4, SCR_MISC5, SCR_MISC6, SCR_MISC7,
     SCR_MISC8, SCR_MISC9, SCR_I8_PLANES, SCR_I8_SMALL, SCR_I8_PART, SCR_I8_STATS, SCR_APSP_R, SCR_APSP_T, SCR_APSP_M,
-    SCR_ALIGN_ROT, SCR_ALIGN_PART, SCR_PIPE_G, SCR_PIPE_D, SCR_PIPE_OUT, SCR_PIPE_STAGE0, SCR_PIPE_STAGE_LAST = SCR_PIPE_STAGE0 + 15, SCR_COUNT
+    SCR_ALIGN_ROT, SCR_ALIGN_PART, SCR_PIPE_G, SCR_PIPE_D, SCR_PIPE_OUT, SCR_PIPE_STAGE0, SCR_PIPE_STAGE_LAST = SCR_PIPE_STAGE0 + 15,
+    SCR_RELAY0, SCR_RELAY_LAST = SCR_RELAY0 + 15, SCR_COUNT
 };
 
 // ---- kernel launchers (one per .cu) -------------------------------------------------------
@@ -179,7 +184,8 @@ int launch_epilogue_peers(wisp_ctx* ctx, const PeerSums& ps, int64_t T_total, in
                           int64_t* d_binary, double* d_w, cudaStream_t st);
 int wisp_com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
                        const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
-                       int n_align, int atomic, double** d_x_out, int64_t* ld_out, float* d_align_out);
+                       int n_align, int atomic, double** d_x_out, int64_t* ld_out, float* d_align_out,
+                       wisp_ctx* via = nullptr);
 int wisp_pipeline_run(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
                       const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
                       int n_align, int atomic, double align_threshold, int max_align_iterations,

@@ -80,6 +80,8 @@ struct Shared {
     std::vector<const double*> d_gram, d_dsum;  // per-shard partial sums (device pointers)
     std::vector<int> can_p2p;                   // [R*R]
     wisp_ctx* root = nullptr;                   // stage timings of shard 0 go to root->pipe_stats
+    std::vector<wisp_ctx*> ctxs;                // shard -> context
+    std::vector<int> via;                       // shard -> shard whose PCIe link carries its coordinates
     double t_begin = 0.0;
     explicit Shared(int r) : R(r), bar(r), slots(r), d_gram(r, nullptr), d_dsum(r, nullptr) {}
 };
@@ -131,8 +133,9 @@ int shard_body(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
     }
     double* d_x = nullptr;
     int64_t ldx = 0;
+    wisp_ctx* via = (S.via[r] != r) ? S.ctxs[S.via[r]] : nullptr;
     WISP_TRY(wisp_com_from_host(ctx, a.coords + (size_t)t0 * a.A * 3, Tl, a.A, a.masses, a.node_ptr, a.atom_idx, N,
-                                a.align_idx, a.n_align, a.atomic, &d_x, &ldx, d_align));
+                                a.align_idx, a.n_align, a.atomic, &d_x, &ldx, d_align, via));
     const double t_s1 = host_ms();
     // small device vectors + the partial sums live in this shard's arena
     void* pw = nullptr;
@@ -274,6 +277,12 @@ int wisp_pipeline_run(wisp_ctx* ctx, const float* coords, int64_t T, int A, cons
     ctxs.resize(R);
     Shared S(R);
     S.root = ctx;
+    S.ctxs = ctxs;
+    S.via.resize(R);
+    for (int r = 0; r < R; ++r) {
+        const int v = (int)ctx->ingest_via.size() == (int)ctx->children.size() + 1 ? ctx->ingest_via[r] : r;
+        S.via[r] = (v >= 0 && v < R) ? v : r;
+    }
     S.can_p2p.assign((size_t)R * R, 1);
     for (int p = 0; p < R; ++p)
         for (int q = 0; q < R; ++q)
@@ -297,6 +306,107 @@ int wisp_pipeline_run(wisp_ctx* ctx, const float* coords, int64_t T, int A, cons
 // ---------------------------------------------------------------------------------------
 // multi-GPU context
 // ---------------------------------------------------------------------------------------
+namespace {
+
+// Concurrent host -> device rate of every GPU in `active` (all pulling at once from one page-locked
+// buffer); rates in GB/s, 0 for inactive GPUs; returns the aggregate (total bytes / slowest finish).
+double probe_h2d(const std::vector<int>& devs, const std::vector<int>& active, void* h_buf, size_t bytes,
+                 std::vector<void*>& d_buf, std::vector<cudaStream_t>& st, std::vector<double>* rates) {
+    const int n = (int)devs.size(), reps = 3;
+    std::vector<cudaEvent_t> e0(n, nullptr), e1(n, nullptr);
+    for (int i = 0; i < n; ++i) {
+        if (!active[i]) continue;
+        cudaSetDevice(devs[i]);
+        cudaEventCreate(&e0[i]); cudaEventCreate(&e1[i]);
+        cudaMemcpyAsync(d_buf[i], h_buf, bytes, cudaMemcpyHostToDevice, st[i]);     // warm-up
+    }
+    for (int i = 0; i < n; ++i) if (active[i]) { cudaSetDevice(devs[i]); cudaStreamSynchronize(st[i]); }
+    for (int i = 0; i < n; ++i) {
+        if (!active[i]) continue;
+        cudaSetDevice(devs[i]);
+        cudaEventRecord(e0[i], st[i]);
+        for (int k = 0; k < reps; ++k) cudaMemcpyAsync(d_buf[i], h_buf, bytes, cudaMemcpyHostToDevice, st[i]);
+        cudaEventRecord(e1[i], st[i]);
+    }
+    double slowest = 0.0;
+    int n_active = 0;
+    rates->assign(n, 0.0);
+    for (int i = 0; i < n; ++i) {
+        if (!active[i]) continue;
+        cudaSetDevice(devs[i]);
+        cudaStreamSynchronize(st[i]);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0[i], e1[i]);
+        (*rates)[i] = reps * (double)bytes / (ms * 1e-3) / 1e9;
+        slowest = std::max(slowest, (double)ms);
+        ++n_active;
+        cudaEventDestroy(e0[i]); cudaEventDestroy(e1[i]);
+    }
+    return slowest > 0 ? n_active * reps * (double)bytes / (slowest * 1e-3) / 1e9 : 0.0;
+}
+
+// Which PCIe links should carry the coordinates?  On some hosts a group of GPUs shares an upstream
+// limit (measured on this pool: GPUs 0-3 get 29 GB/s each when they pull together, GPUs 4-7 55 GB/s each,
+// and all eight together only 186 GB/s against 220 GB/s for GPUs 4-7 alone).  When pulling through the
+// fast GPUs only beats pulling through all of them, every slow GPU is fed by a fast partner: host -> the
+// partner's HBM over the partner's link -> NVLink peer copy (700 GB/s, off the critical path).
+void probe_ingest_topology(wisp_ctx* root, const std::vector<int>& devs, bool force_relay) {
+    const int n = (int)devs.size();
+    const size_t bytes = (size_t)192 << 20;
+    void* h_buf = nullptr;
+    if (cudaHostAlloc(&h_buf, bytes, cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    memset(h_buf, 0, bytes);
+    std::vector<void*> d_buf(n, nullptr);
+    std::vector<cudaStream_t> st(n, nullptr);
+    bool ok = true;
+    for (int i = 0; i < n && ok; ++i) {
+        cudaSetDevice(devs[i]);
+        ok &= cudaMalloc(&d_buf[i], bytes) == cudaSuccess;
+        ok &= cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) == cudaSuccess;
+    }
+    if (ok) {
+        std::vector<int> all(n, 1), fast(n, 0);
+        std::vector<double> r_all, r_fast;
+        const double agg_all = probe_h2d(devs, all, h_buf, bytes, d_buf, st, &r_all);
+        const double best = *std::max_element(r_all.begin(), r_all.end());
+        int n_fast = 0;
+        for (int i = 0; i < n; ++i) { fast[i] = r_all[i] >= 0.8 * best; n_fast += fast[i]; }
+        if (force_relay && n_fast == n) {       // testing on a symmetric box: relay the second half anyway
+            for (int i = (n + 1) / 2; i < n; ++i) fast[i] = 0;
+            n_fast = (n + 1) / 2;
+        }
+        double agg_fast = 0.0;
+        r_fast.assign(n, 0.0);
+        if (n_fast < n && n_fast >= 1) agg_fast = probe_h2d(devs, fast, h_buf, bytes, d_buf, st, &r_fast);
+        root->ingest_probe = r_all;
+        root->ingest_probe.insert(root->ingest_probe.end(), r_fast.begin(), r_fast.end());
+        root->ingest_probe.push_back(agg_all);
+        root->ingest_probe.push_back(agg_fast);
+        if (n_fast < n && n_fast >= 1 && (force_relay || agg_fast > 1.08 * agg_all)) {
+            // every slow GPU gets a fast partner with peer access, dealt round-robin
+            std::vector<int> fl;
+            for (int i = 0; i < n; ++i) if (fast[i]) fl.push_back(i);
+            int k = 0;
+            for (int i = 0; i < n; ++i) {
+                if (fast[i]) continue;
+                for (int tries = 0; tries < (int)fl.size(); ++tries) {
+                    const int p = fl[(k + tries) % fl.size()];
+                    if (root->peer_ok[p * n + i]) { root->ingest_via[i] = p; k = (k + tries + 1) % (int)fl.size(); break; }
+                }
+            }
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        cudaSetDevice(devs[i]);
+        if (d_buf[i]) cudaFree(d_buf[i]);
+        if (st[i]) cudaStreamDestroy(st[i]);
+    }
+    cudaFreeHost(h_buf);
+    (void)cudaGetLastError();
+}
+
+}  // namespace
+
 extern "C" int wisp_ctx_create_multi(int n_gpus, const int* devices, wisp_ctx** out) {
     WISP_CHECK(out, "ctx_create_multi: null output pointer");
     int n_dev = 0;
@@ -341,8 +451,31 @@ extern "C" int wisp_ctx_create_multi(int n_gpus, const int* devices, wisp_ctx** 
             root->peer_ok[p * n_gpus + q] = ok;
         }
     }
+    root->shard_index = 0;
+    for (size_t k = 0; k < root->children.size(); ++k) root->children[k]->shard_index = (int)k + 1;
+    root->ingest_via.resize(n_gpus);
+    for (int i = 0; i < n_gpus; ++i) root->ingest_via[i] = i;
+    bool distinct = true;
+    for (int i = 0; i < n_gpus; ++i)
+        for (int j = 0; j < i; ++j) distinct &= devs[i] != devs[j];
+    const char* mode = getenv("WISP_INGEST");            // auto (default) | direct | relay
+    const bool force = mode && !strcmp(mode, "relay");
+    if (distinct && (n_gpus >= 4 || (force && n_gpus >= 2)) && !(mode && !strcmp(mode, "direct")))
+        probe_ingest_topology(root, devs, force);
     cudaSetDevice(devs[0]);
     *out = root;
+    return 0;
+}
+
+// ingest plan of a multi-GPU context: via [n] (shard -> relaying shard), rates [2n + 2] = concurrent H2D
+// GB/s per GPU with every GPU pulling, then with only the fast set pulling (0 for the others), then the
+// two aggregates.  Zeros when no probe ran.
+extern "C" int wisp_ctx_ingest_info(wisp_ctx* ctx, int* via, double* rates) {
+    WISP_CHECK(ctx, "ctx_ingest_info: null context");
+    const int n = 1 + (int)ctx->children.size();
+    for (int i = 0; i < n; ++i) if (via) via[i] = (int)ctx->ingest_via.size() == n ? ctx->ingest_via[i] : i;
+    if (rates)
+        for (int i = 0; i < 2 * n + 2; ++i) rates[i] = (int)ctx->ingest_probe.size() == 2 * n + 2 ? ctx->ingest_probe[i] : 0.0;
     return 0;
 }
 
