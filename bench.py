@@ -572,6 +572,20 @@ def main():
             e2e_corr = res_call["corr"].copy()
             e2e_avgdist = res_call["avgdist"].copy()
             e2e_iters = len(res_call["alignment_log"])
+            direct_ms = None
+            if any(v != i for i, v in enumerate(mctx_ingest["via"])):
+                # the same call with every GPU pulling its own shard over its own host link, for comparison
+                os.environ["WISP_INGEST"] = "direct"
+                dctx = _lib.Context(gpus=world)
+                os.environ.pop("WISP_INGEST")
+                keep, mctx = mctx, dctx
+                call()
+                td = time.perf_counter()
+                for _ in range(3):
+                    call()
+                direct_ms = (time.perf_counter() - td) * 1e3 / 3
+                mctx = keep
+                dctx.close()
         cpu_barrier()
         if rank == 0:
             h2d_total = T * A * 12
@@ -582,7 +596,7 @@ def main():
                    "api": "wisp_pipeline (C ABI, include/wisp_b200.h) on wisp_ctx_create_multi(%d): page-locked host "
                           "coordinates in; avg / corr / avgdist / binary / w in page-locked host buffers out; "
                           "K7 alignment included (%d iterations)" % (api_gpus, e2e_iters),
-                   "gpus_in_call": api_gpus, "ingest": mctx_ingest,
+                   "gpus_in_call": api_gpus, "ingest": mctx_ingest, "ms_per_step_with_direct_ingest": direct_ms,
                    "host_numa_node_per_shard": host_nodes,
                    "pcie_h2d_gbs_per_rank_concurrent": h2d_gbs_rank,
                    "pcie_h2d_gbs_aggregate_concurrent": h2d_gbs_aggregate,
