@@ -217,6 +217,11 @@ int wisp_dev_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const 
                         int64_t T, int N, int first, double* d_sums, void* stream);
 int wisp_dev_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align,
                           double* d_nodes, int64_t T, int N, double* d_sums, void* stream);
+/* After the caller has all-reduced d_sums: d_avg [3 n_align + 3 N] <- d_sums / T_total in place (the new
+ * landmark / node averages, :112-113) and d_res2 [2] = sum of squared differences old - new over the
+ * landmark columns and over the node columns (the RMSDs of :118-119 are sqrt(res2 / n)). */
+int wisp_dev_align_update(wisp_ctx* ctx, const double* d_sums, int64_t T_total, int n_align, int N,
+                          double* d_avg, double* d_res2, void* stream);
 /* X <- X - mean (in place), mean [ld]; pad columns / rows are left at zero.  When d_p32 is
  * not NULL it also receives the FP32 tile-referenced copy K3 reads:
  * float [T][wisp_gram_ld(N)/128][3][128], value = float(x - mean of the tile's middle node). */

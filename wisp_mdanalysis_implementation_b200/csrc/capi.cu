@@ -575,6 +575,12 @@ extern "C" int wisp_dev_align_rotate(wisp_ctx* ctx, float* d_align, int n_align,
                                wisp_stream(ctx, stream), d_sums);
 }
 
+extern "C" int wisp_dev_align_update(wisp_ctx* ctx, const double* d_sums, int64_t T_total, int n_align, int N,
+                                     double* d_avg, double* d_res2, void* stream) {
+    WISP_CHECK(ctx && d_sums && d_avg && d_res2 && T_total > 0, "dev_align_update: bad argument");
+    return launch_align_update(ctx, d_sums, T_total, n_align, N, d_avg, d_res2, wisp_stream(ctx, stream));
+}
+
 extern "C" int wisp_dev_center(wisp_ctx* ctx, double* d_nodes, int64_t T, int N, const double* d_mean,
                                float* d_p32, void* stream) {
     WISP_CHECK(ctx && d_nodes && d_mean, "dev_center: null argument");

@@ -142,6 +142,8 @@ int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* 
                             int64_t T_total = 0, const AlignReduce& reduce = AlignReduce());
 int launch_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_nodes, int64_t ld,
                       int N, int64_t T, bool first, double* d_sums, cudaStream_t st);
+int launch_align_update(wisp_ctx* ctx, const double* d_sums, int64_t T_total, int n_align, int N, double* d_avg,
+                        double* d_res2, cudaStream_t st);
 int launch_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align, double* d_nodes,
                         int64_t ld, int N, int64_t T, cudaStream_t st, double* d_sums = nullptr);
 int launch_colsum(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int64_t ncols,

@@ -526,10 +526,16 @@ fw_resolve_kernel(const T* __restrict__ dist, const T* __restrict__ distT, const
         T best = inf_v<T>();
         uint16_t r = kNoRound;
         if (i < N && i != j) r = rounds[(int64_t)i * n_pad + j];
-        if (r != kNoRound) {
-            const T* di = dist + (int64_t)i * n_pad;
-            const int k0 = (int)r * B;
-            for (int kk = l * V; kk < B; kk += 8 * V) {
+        // The scan of a group stops as soon as one of its lanes holds a candidate that reproduces
+        // dist[i][j] exactly (the usual case: the improving sum is recomputed from unchanged operands):
+        // any such k is a valid midpoint, and the loads of the remaining sub-blocks are skipped.
+        const T dij = (r != kNoRound) ? dj[i] : inf_v<T>();           // distT[j][i] == dist[i][j]
+        bool done = (r == kNoRound);
+        const unsigned gmask = 0xFFu << (threadIdx.x & 24);            // the 8 lanes of this group
+        for (int kk = l * V; kk < B; kk += 8 * V) {
+            if (!done) {
+                const T* di = dist + (int64_t)i * n_pad;
+                const int k0 = (int)r * B;
                 T a[V], b[V];
                 *reinterpret_cast<int4*>(a) = *reinterpret_cast<const int4*>(di + k0 + kk);
                 *reinterpret_cast<int4*>(b) = *reinterpret_cast<const int4*>(dj + k0 + kk);
@@ -540,6 +546,7 @@ fw_resolve_kernel(const T* __restrict__ dist, const T* __restrict__ distT, const
                     if (c < best && k != i && k != j) { best = c; best_k = k; }
                 }
             }
+            done = done || (__ballot_sync(0xffffffffu, best_k >= 0 && best <= dij) & gmask) != 0;
         }
         // argmin over the 8 lanes of the group (ties: smaller k); executed by every lane of the warp
 #pragma unroll

@@ -231,7 +231,41 @@ sum32_sequential_kernel(const float* __restrict__ a, int64_t T, int64_t ncols, d
     if (wrp == 0 && ok) inout[c] = (double)s;
 }
 
+// new averages and the two RMSDs' squared sums in ONE launch (a frame-sharded caller has just all-reduced
+// `sums`): avg <- sums / T_total in place; res2[0] = sum over landmark columns of (old - new)^2,
+// res2[1] = the same over the node columns.  Single CTA, fixed-order tree -> deterministic.
+__global__ void __launch_bounds__(1024)
+align_update_kernel(const double* __restrict__ sums, double T_total, int64_t na3, int64_t nn3,
+                    double* __restrict__ avg, double* __restrict__ res2) {
+    __shared__ double red[2][32];
+    double ra = 0.0, rn = 0.0;
+    for (int64_t c = threadIdx.x; c < na3 + nn3; c += blockDim.x) {
+        const double v = sums[c] / T_total, d = avg[c] - v;
+        if (c < na3) ra += d * d; else rn += d * d;
+        avg[c] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ra += __shfl_xor_sync(0xffffffffu, ra, o); rn += __shfl_xor_sync(0xffffffffu, rn, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ra; red[1][threadIdx.x >> 5] = rn; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        ra = threadIdx.x < (blockDim.x >> 5) ? red[0][threadIdx.x] : 0.0;
+        rn = threadIdx.x < (blockDim.x >> 5) ? red[1][threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { ra += __shfl_xor_sync(0xffffffffu, ra, o); rn += __shfl_xor_sync(0xffffffffu, rn, o); }
+        if (threadIdx.x == 0) { res2[0] = ra; res2[1] = rn; }
+    }
+}
+
 }  // namespace
+
+int launch_align_update(wisp_ctx* ctx, const double* d_sums, int64_t T_total, int n_align, int N, double* d_avg,
+                        double* d_res2, cudaStream_t st) {
+    align_update_kernel<<<1, 1024, 0, st>>>(d_sums, (double)T_total, 3 * (int64_t)n_align, 3 * (int64_t)N, d_avg, d_res2);
+    ctx->launches++;
+    WISP_CUDA(cudaGetLastError());
+    return 0;
+}
 
 // ---- building blocks (also the device-level C ABI: wisp_dev_align_sums / wisp_dev_align_iter) ----
 // d_sums [na3 + nn3]: first the landmark column sums, then the node column sums of this frame block.

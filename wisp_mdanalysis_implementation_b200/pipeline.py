@@ -121,7 +121,6 @@ class FramePipeline:
         if self.align_iterations > 0:
             self.d_align = torch.empty((self.T, self.n_align, 3), dtype=torch.float32, device=dev)
             self.d_align_sums = torch.zeros(3 * self.n_align + 3 * self.N, dtype=f64, device=dev)
-            self.d_avg_align = torch.zeros(3 * self.n_align, dtype=f64, device=dev)
         self.d_parts = None
         self.k23_stream = torch.cuda.Stream(device=dev)
         n = self.N
@@ -175,27 +174,28 @@ class FramePipeline:
         else:
             sn = self.d_align_sums[na3:].cpu().numpy().copy()
         sa = self.d_align_sums[:na3].cpu().numpy().astype(np.float32)
-        # averages stay on the device; one scalar pair per iteration comes back for the loop decision
-        d_avg_a = torch.from_numpy((sa / np.float32(self.T_total)).astype(np.float64)).to(self.dev)
-        d_avg_n = torch.from_numpy(sn / float(self.T_total)).to(self.dev)
+        # averages stay on the device ([landmarks || nodes], the layout of the sums); per iteration one
+        # kernel turns the all-reduced sums into the new averages and the two squared residual sums, and
+        # one pair of doubles comes back for the loop decision
+        d_avg = torch.from_numpy(np.concatenate(((sa / np.float32(self.T_total)).astype(np.float64),
+                                                 sn / float(self.T_total)))).to(self.dev)
+        d_res2 = torch.zeros(2, dtype=torch.float64, device=self.dev)
         self.alignment_log = []
         residual, it = self.align_threshold + 9999.0, 0
         while residual > self.align_threshold and it < self.align_iterations:
-            self.d_avg_align.copy_(d_avg_a)
-            self.ctx.dev_align_rotate(self.d_align.data_ptr(), self.n_align, self.d_avg_align.data_ptr(),
+            self.ctx.dev_align_rotate(self.d_align.data_ptr(), self.n_align, d_avg.data_ptr(),
                                       self.d_x.data_ptr(), self.T, self.N, d_sums=self.d_align_sums.data_ptr(),
                                       stream=s)
             sharding.reduce_sums(self.d_align_sums, group=self.group)
-            new = self.d_align_sums / float(self.T_total)            # (same division as the reference, :112-113)
-            new_a, new_n = new[:na3], new[na3:]
-            both = torch.stack((((d_avg_a - new_a) ** 2).sum() / self.n_align,
-                                ((d_avg_n - new_n) ** 2).sum() / self.N)).sqrt().cpu()
-            residual, node_rmsd = float(both[0]), float(both[1])
-            d_avg_a, d_avg_n = new_a.clone(), new_n.clone()
+            self.ctx.dev_align_update(self.d_align_sums.data_ptr(), self.T_total, self.n_align, self.N,
+                                      d_avg.data_ptr(), d_res2.data_ptr(), stream=s)
+            r2 = d_res2.cpu()
+            residual = float(np.sqrt(float(r2[0]) / self.n_align))
+            node_rmsd = float(np.sqrt(float(r2[1]) / self.N))
             it += 1
             self.alignment_log.append((it, residual, node_rmsd))
         self.d_mean.zero_()
-        self.d_mean[:nn3].copy_(d_avg_n)
+        self.d_mean[:nn3].copy_(d_avg[na3:])
         return it
 
     def center_on_mean(self):
