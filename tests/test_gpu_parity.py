@@ -1059,3 +1059,23 @@ def test_multirank_nccl_paths():
                         "--master-addr", "127.0.0.1", "--master-port", "29517",
                         os.path.join(root, "tools", "multirank_check.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_get_paths_longer_than_the_initial_record(ctx):
+    """Paths of 150+ nodes (a chain with three detours): the path record / per-warp path buffer starts at
+    96 nodes and grows on demand (it used to be a hard error)."""
+    n = 153
+    W = np.zeros((n, n))
+    for i in range(149):
+        W[i, i + 1] = W[i + 1, i] = 0.5
+    for k, i in enumerate((10, 50, 90)):
+        d = 150 + k
+        W[i, d] = W[d, i] = 0.3
+        W[d, i + 1] = W[i + 1, d] = 0.3
+    for K in (3, 8):
+        want = oracle.get_paths_pruned(W, [0], [149], K)
+        got = ctx.get_paths(W, [0], [149], K)
+        assert [p[1:] for p in got] == [[int(x) for x in p[1:]] for p in want]
+        assert [p[0] for p in got] == [float(p[0]) for p in want]
+        assert min(len(p) for p in got) > 150
+    assert ctx.paths_query_pairs([(0, 149), (149, 0)], 4) == [ctx.get_paths(W, [0], [149], 4), ctx.get_paths(W, [149], [0], 4)]

@@ -26,7 +26,7 @@
 
 namespace {
 
-constexpr int kMaxLen = 96;          // longest path (nodes) the enumerator supports
+constexpr int kMaxLen0 = 96;         // initial capacity of a path record (nodes); grows x4 on demand, up to N
 constexpr int kTargetPrefixes = 4096;
 constexpr int kMaxExpandLevels = 8;
 
@@ -47,6 +47,7 @@ struct EnumParams {
     int32_t* g_count;            // [G] paths found per group (both modes)
     int N;
     int quirk;
+    int max_len;             // capacity of a path record / a warp's path buffer (nodes)
     // outputs
     int32_t* out_count;      // [0] stored paths, [1] n node entries, [2] overflow flags
     unsigned long long* expansions;
@@ -78,7 +79,7 @@ __device__ __forceinline__ void emit_path(const EnumParams& P, int pair, const i
     P.out_nodes[off + depth] = last;
 }
 
-// frontier record layout: len[cap], meta[cap][2] = (pair, depth), nodes[cap][kMaxLen]
+// frontier record layout: len[cap], meta[cap][2] = (pair, depth), nodes[cap][max_len]
 __global__ void expand_level_kernel(EnumParams P, const double* __restrict__ fin_len,
                                     const int32_t* __restrict__ fin_meta,
                                     const int32_t* __restrict__ fin_nodes, int n_in,
@@ -91,7 +92,7 @@ __global__ void expand_level_kernel(EnumParams P, const double* __restrict__ fin
     const int s = P.pairs[2 * pair], t = P.pairs[2 * pair + 1];
     const int grp = P.pair_group[pair];
     const double cutoff = P.g_cutoff[grp], bound = P.g_bound[grp];
-    const int32_t* nodes = fin_nodes + (size_t)rec * kMaxLen;
+    const int32_t* nodes = fin_nodes + (size_t)rec * P.max_len;
     const double len = fin_len[rec];
     const int u = nodes[depth - 1];
     const double* dt = P.dist + (size_t)t * P.N;
@@ -110,13 +111,13 @@ __global__ void expand_level_kernel(EnumParams P, const double* __restrict__ fin
             continue;
         }
         if (nl > cutoff) continue;
-        if (depth + 1 >= kMaxLen) { atomicOr(&P.out_count[2], 2); continue; }
+        if (depth + 1 >= P.max_len) { atomicOr(&P.out_count[2], 2); continue; }
         const int slot = atomicAdd(fout_count, 1);
         if (slot >= cap_out) { atomicOr(&P.out_count[2], 4); continue; }
         fout_len[slot] = nl;
         fout_meta[2 * slot] = pair;
         fout_meta[2 * slot + 1] = depth + 1;
-        int32_t* dst = fout_nodes + (size_t)slot * kMaxLen;
+        int32_t* dst = fout_nodes + (size_t)slot * P.max_len;
         for (int k = 0; k < depth; ++k) dst[k] = nodes[k];
         dst[depth] = v;
     }
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kDfsWarps * 32)
 dfs_warp_kernel(EnumParams P, const double* __restrict__ f_len, const int32_t* __restrict__ f_meta,
                 const int32_t* __restrict__ f_nodes, int n_in, StackEntry* __restrict__ stacks,
                 int cap_stack) {
-    __shared__ int32_t spath[kDfsWarps][kMaxLen];
+    extern __shared__ int32_t spath[];      // [kDfsWarps][max_len]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int rec = blockIdx.x * kDfsWarps + wib;
     if (rec >= n_in) return;
@@ -152,11 +153,11 @@ dfs_warp_kernel(EnumParams P, const double* __restrict__ f_len, const int32_t* _
     const double cutoff = P.g_cutoff[grp], bound = P.g_bound[grp];
     const int count_only = P.g_count_only[grp], cap = P.g_cap[grp];
     const double* dt = P.dist + (size_t)t * P.N;
-    int32_t* path = spath[wib];
-    for (int k = lane; k < d0; k += 32) path[k] = f_nodes[(size_t)rec * kMaxLen + k];
+    int32_t* path = spath + (size_t)wib * P.max_len;
+    for (int k = lane; k < d0; k += 32) path[k] = f_nodes[(size_t)rec * P.max_len + k];
     StackEntry* stack = stacks + (size_t)rec * cap_stack;
     int sp = 0;
-    if (lane == 0) { stack[0].node = f_nodes[(size_t)rec * kMaxLen + d0 - 1]; stack[0].depth = d0 - 1; stack[0].len = f_len[rec]; }
+    if (lane == 0) { stack[0].node = f_nodes[(size_t)rec * P.max_len + d0 - 1]; stack[0].depth = d0 - 1; stack[0].len = f_len[rec]; }
     sp = 1;
     __syncwarp();
     unsigned long long nexp = 0;
@@ -224,7 +225,7 @@ dfs_warp_kernel(EnumParams P, const double* __restrict__ f_len, const int32_t* _
             const unsigned cmask = __ballot_sync(FULL, cont);
             if (cmask) {
                 const int nc = __popc(cmask);
-                if (depth + 1 >= kMaxLen) { if (lane == 0) atomicOr(&P.out_count[2], 2); }
+                if (depth + 1 >= P.max_len) { if (lane == 0) atomicOr(&P.out_count[2], 2); }
                 else if (sp + nc > cap_stack) { if (lane == 0) atomicOr(&P.out_count[2], 8); }
                 else {
                     if (cont) {
@@ -384,6 +385,7 @@ struct EnumEngine {
     PathGraphState* g;
     int quirk;
     int cap_paths = 4096, cap_front = 16 * kTargetPrefixes, cap_stack = 1024, target_prefixes = kTargetPrefixes;
+    int max_len = kMaxLen0;
     double enum_ms = 0.0, host_ms = 0.0;
     unsigned long long expansions_total = 0;
 
@@ -403,7 +405,7 @@ struct EnumEngine {
             void *d_out, *d_front, *d_small;
             const size_t out_bytes = (size_t)cap_paths * (8 + 4 + 4 + 4) + (size_t)cap_nodes * 4 + 256;
             WISP_TRY(wisp_scratch(ctx, SCR_MISC8, out_bytes, &d_out));
-            const size_t front_rec = 8 + 8 + (size_t)kMaxLen * 4;
+            const size_t front_rec = 8 + 8 + (size_t)max_len * 4;
             WISP_TRY(wisp_scratch(ctx, SCR_MISC9, 2 * (size_t)cap_front * front_rec + 256, &d_front));
             // small per-pass arrays in one block: pairs, pair_group, group params, counters
             const size_t o_pairs = 0, o_pg = round_up((int64_t)n_pairs * 8, 64), o_cut = o_pg + round_up((int64_t)n_pairs * 4, 64),
@@ -433,7 +435,7 @@ struct EnumEngine {
             P.g_cutoff = (const double*)(ds + o_cut); P.g_bound = (const double*)(ds + o_bnd);
             P.g_count_only = (const int32_t*)(ds + o_co); P.g_cap = (const int32_t*)(ds + o_cap);
             P.g_count = (int32_t*)(ds + o_gc);
-            P.N = N; P.quirk = quirk;
+            P.N = N; P.quirk = quirk; P.max_len = max_len;
             int32_t* cnt = (int32_t*)(ds + o_cnt);           // [0..2] out counters, [4] frontier count, [8..9] expansions
             P.out_count = cnt;
             P.expansions = (unsigned long long*)(cnt + 8);
@@ -448,16 +450,16 @@ struct EnumEngine {
             for (int bq = 0; bq < 2; ++bq) {
                 f_len[bq] = (double*)fb; fb += (size_t)cap_front * 8;
                 f_meta[bq] = (int32_t*)fb; fb += (size_t)cap_front * 8;
-                f_nodes[bq] = (int32_t*)fb; fb += (size_t)cap_front * kMaxLen * 4;
+                f_nodes[bq] = (int32_t*)fb; fb += (size_t)cap_front * max_len * 4;
             }
             if (n_pairs > cap_front) { cap_front = 2 * n_pairs; continue; }
             {   // seed frontier: one record [s] per pair
                 std::vector<double> hl(n_pairs, 0.0);
-                std::vector<int32_t> hm(2 * (size_t)n_pairs), hn((size_t)n_pairs * kMaxLen, 0);
-                for (int p = 0; p < n_pairs; ++p) { hm[2 * p] = p; hm[2 * p + 1] = 1; hn[(size_t)p * kMaxLen] = pairs[2 * p]; }
+                std::vector<int32_t> hm(2 * (size_t)n_pairs), hn((size_t)n_pairs * max_len, 0);
+                for (int p = 0; p < n_pairs; ++p) { hm[2 * p] = p; hm[2 * p + 1] = 1; hn[(size_t)p * max_len] = pairs[2 * p]; }
                 WISP_CUDA(cudaMemcpyAsync(f_len[0], hl.data(), (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
                 WISP_CUDA(cudaMemcpyAsync(f_meta[0], hm.data(), (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
-                WISP_CUDA(cudaMemcpyAsync(f_nodes[0], hn.data(), (size_t)n_pairs * kMaxLen * 4, cudaMemcpyHostToDevice, st));
+                WISP_CUDA(cudaMemcpyAsync(f_nodes[0], hn.data(), (size_t)n_pairs * max_len * 4, cudaMemcpyHostToDevice, st));
                 WISP_CUDA(cudaStreamSynchronize(st));     // the host vectors above and h_small go out of use
             }
             int n_front = n_pairs, cur = 0;
@@ -473,13 +475,17 @@ struct EnumEngine {
                 WISP_CUDA(cudaStreamSynchronize(st));
                 if (hc[2] & 4) { overflow = true; cap_front *= 4; break; }
                 if (hc[2] & 1) { overflow = true; cap_paths *= 4; break; }
+                if (hc[2] & 2) { overflow = true; break; }
                 n_front = hc[4];
                 cur ^= 1;
             }
             if (!overflow && n_front > 0) {
                 void* d_stack = nullptr;
                 WISP_TRY(wisp_scratch(ctx, SCR_MISC0, (size_t)n_front * cap_stack * sizeof(StackEntry) + 256, &d_stack));
-                dfs_warp_kernel<<<(n_front + kDfsWarps - 1) / kDfsWarps, kDfsWarps * 32, 0, st>>>(
+                const int dfs_smem = kDfsWarps * max_len * (int)sizeof(int32_t);
+                if (dfs_smem > 48 * 1024)
+                    WISP_CUDA(cudaFuncSetAttribute(dfs_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dfs_smem));
+                dfs_warp_kernel<<<(n_front + kDfsWarps - 1) / kDfsWarps, kDfsWarps * 32, dfs_smem, st>>>(
                     P, f_len[cur], f_meta[cur], f_nodes[cur], n_front, (StackEntry*)d_stack, cap_stack);
                 ctx->launches++;
             }
@@ -491,9 +497,17 @@ struct EnumEngine {
                 WISP_CUDA(cudaMemcpyAsync(hg.data(), P.g_count, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, st));
                 WISP_CUDA(cudaStreamSynchronize(st));
                 WISP_CUDA(cudaGetLastError());
-                WISP_CHECK(!(hc[2] & 2), "get_paths: a path exceeded the supported length of %d nodes", kMaxLen);
+                if (hc[2] & 2) overflow = true;
                 if (hc[2] & 1) { overflow = true; cap_paths = std::max(cap_paths * 4, hc[0] + 1024); }
                 if (hc[2] & 8) { overflow = true; cap_stack *= 4; }
+            }
+            if (overflow && (hc[2] & 2)) {
+                // a path outgrew the record: a simple path has at most N nodes, so the capacity grows x4 up
+                // to N + 1 and the pass is repeated
+                WISP_CHECK(max_len <= N, "get_paths: a simple path cannot have more than %d nodes", N);
+                max_len = std::min(4 * max_len, N + 1);
+                WISP_CHECK((size_t)kDfsWarps * max_len * 4 <= 200 * 1024,
+                           "get_paths: paths of more than %d nodes are not supported", 200 * 1024 / (4 * kDfsWarps));
             }
             if (overflow) continue;
             expansions_total += hexp;
