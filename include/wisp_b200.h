@@ -217,6 +217,18 @@ int wisp_dev_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const 
                         int64_t T, int N, int first, double* d_sums, void* stream);
 int wisp_dev_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align,
                           double* d_nodes, int64_t T, int N, double* d_sums, void* stream);
+/* One alignment iteration with the node rotation DEFERRED (what the library's own loop uses): the
+ * landmarks are rotated onto d_avg_align in place (:106), the frame's rotation is composed into
+ * d_rot_total [T][9] (first != 0: d_rot_total <- R, else R d_rot_total), and the node trajectory is only
+ * READ: d_sums [3 n_align + 3 N] (may be NULL) = column sums of the rotated landmarks, then of d_rot_total
+ * applied to the unchanged nodes (:110-111).  After the loop the caller applies d_rot_total once, either
+ * with wisp_dev_align_nodes (in place, :107) or fused into the centring pass (wisp_dev_center_rotated).
+ * d_nodes == NULL in wisp_dev_align_sums: only the landmark sums are formed (K1 already gave the node sums). */
+int wisp_dev_align_iter(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align,
+                        const double* d_nodes, int64_t T, int N, double* d_rot_total, int first,
+                        double* d_sums, void* stream);
+int wisp_dev_align_nodes(wisp_ctx* ctx, double* d_nodes, int64_t T, int N, const double* d_rot_total,
+                         void* stream);
 /* After the caller has all-reduced d_sums: d_avg [3 n_align + 3 N] <- d_sums / T_total in place (the new
  * landmark / node averages, :112-113) and d_res2 [2] = sum of squared differences old - new over the
  * landmark columns and over the node columns (the RMSDs of :118-119 are sqrt(res2 / n)). */
@@ -227,6 +239,10 @@ int wisp_dev_align_update(wisp_ctx* ctx, const double* d_sums, int64_t T_total, 
  * float [T][wisp_gram_ld(N)/128][3][128], value = float(x - mean of the tile's middle node). */
 int wisp_dev_center(wisp_ctx* ctx, double* d_nodes, int64_t T, int N, const double* d_mean,
                     float* d_p32, void* stream);
+/* The same with every frame first rotated by d_rot_total[t] (row-major 3x3; NULL = wisp_dev_center):
+ * X <- R[t] X - mean in one pass (trajectory_analysis_functions.py:107 with the composed rotation). */
+int wisp_dev_center_rotated(wisp_ctx* ctx, double* d_nodes, int64_t T, int N, const double* d_mean,
+                            const double* d_rot_total, float* d_p32, void* stream);
 /* column sums of the (possibly centred) trajectory: d_colsum [ld] */
 int wisp_dev_colsum(wisp_ctx* ctx, const double* d_nodes, int64_t T, int N, double* d_colsum,
                     void* stream);

@@ -1079,3 +1079,91 @@ def test_get_paths_longer_than_the_initial_record(ctx):
         assert [p[0] for p in got] == [float(p[0]) for p in want]
         assert min(len(p) for p in got) > 150
     assert ctx.paths_query_pairs([(0, 149), (149, 0)], 4) == [ctx.get_paths(W, [0], [149], 4), ctx.get_paths(W, [149], [0], 4)]
+
+
+@pytest.mark.parametrize("n,n_align_step,t", [(70, 1, 45), (257, 3, 130)])
+def test_k7_deferred_node_rotation_equals_in_place(ctx, n, n_align_step, t):
+    """K7 building blocks: one iteration with the node rotation deferred (wisp_dev_align_iter: landmarks
+    rotated in place, nodes only read, rotations composed) + the final in-place rotation
+    (wisp_dev_align_nodes) or the fused centring (wisp_dev_center_rotated) must equal the literal data
+    flow of trajectory_analysis_functions.py:102-111 (wisp_dev_align_rotate rotates both arrays every
+    iteration) -- and both must equal numpy on the same rotations."""
+    import torch
+    from wisp_mdanalysis_implementation_b200 import _lib
+    rng = np.random.default_rng(n)
+    n_align = (n + n_align_step - 1) // n_align_step
+    ld = _lib.node_ld(n)
+    npad = _lib.gram_ld(n)
+    base = rng.normal(size=(n, 3)) * np.array([12.0, 7.0, 4.0])
+    nodes0 = np.zeros((t, n, 3))
+    for f in range(t):
+        ang = rng.normal(size=3) * 0.3
+        cx, sx, cy, sy, cz, sz = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
+        R = (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+             @ np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]))
+        nodes0[f] = (base + rng.normal(size=(n, 3)) * 0.4) @ R.T
+    align0 = nodes0[:, ::n_align_step, :].astype(np.float32)
+    assert align0.shape[1] == n_align
+
+    def dev_nodes(a):
+        x = torch.zeros((_lib.frames_pad(t), ld), dtype=torch.float64, device="cuda")
+        x[:t, :3 * n] = torch.from_numpy(a.reshape(t, 3 * n)).cuda()
+        return x
+
+    avg = align0.astype(np.float64).mean(axis=0).reshape(-1)
+    # (a) literal: both arrays rotated in place, twice
+    xa, aa = dev_nodes(nodes0), torch.from_numpy(align0.copy()).cuda()
+    d_avg = torch.from_numpy(avg).cuda()
+    sums_a = torch.zeros(3 * (n_align + n), dtype=torch.float64, device="cuda")
+    ctx.dev_align_rotate(aa.data_ptr(), n_align, d_avg.data_ptr(), xa.data_ptr(), t, n, d_sums=sums_a.data_ptr(), stream=1)
+    avg2 = (sums_a[:3 * n_align] / t).clone()
+    sums_a1 = sums_a.clone()
+    ctx.dev_align_rotate(aa.data_ptr(), n_align, avg2.data_ptr(), xa.data_ptr(), t, n, d_sums=sums_a.data_ptr(), stream=1)
+    # (b) deferred
+    xb, ab = dev_nodes(nodes0), torch.from_numpy(align0.copy()).cuda()
+    rot = torch.empty((t, 9), dtype=torch.float64, device="cuda")
+    sums_b = torch.zeros_like(sums_a)
+    ctx.dev_align_iter(ab.data_ptr(), n_align, d_avg.data_ptr(), xb.data_ptr(), t, n, rot.data_ptr(), True,
+                       d_sums=sums_b.data_ptr(), stream=1)
+    torch.cuda.synchronize()
+    assert torch.equal(xb[:t, :3 * n].cpu(), torch.from_numpy(nodes0.reshape(t, 3 * n)))     # nodes untouched
+    np.testing.assert_allclose(sums_b.cpu().numpy(), sums_a1.cpu().numpy(), rtol=0, atol=1e-9)
+    rot1 = rot.cpu().numpy().reshape(t, 3, 3).copy()
+    ctx.dev_align_iter(ab.data_ptr(), n_align, avg2.data_ptr(), xb.data_ptr(), t, n, rot.data_ptr(), False,
+                       d_sums=sums_b.data_ptr(), stream=1)
+    torch.cuda.synchronize()
+    assert torch.equal(ab.cpu(), aa.cpu())                       # landmarks: identical arithmetic
+    np.testing.assert_allclose(sums_b.cpu().numpy(), sums_a.cpu().numpy(), rtol=0, atol=1e-9)
+    rot2 = rot.cpu().numpy().reshape(t, 3, 3)
+    assert np.abs(np.einsum("tij,tkj->tik", rot2, rot2) - np.eye(3)).max() < 1e-13
+    assert np.abs(np.linalg.det(rot2) - 1.0).max() < 1e-13
+    # numpy: first-iteration rotations are the Kabsch optimum of every frame against avg
+    want1 = np.einsum("tij,tnj->tni", rot1, nodes0)
+    ref_al = avg.reshape(n_align, 3)
+    for f in (0, t // 2, t - 1):
+        a = align0[f].astype(np.float64)
+        u, s, vt = np.linalg.svd(a.T @ ref_al)
+        d = np.sign(np.linalg.det(u @ vt))
+        Rk = (u @ np.diag([1, 1, d]) @ vt).T
+        np.testing.assert_allclose(rot1[f], Rk, rtol=0, atol=1e-10)
+    # final rotation in place ...
+    xc = xb.clone()
+    ctx.dev_align_nodes(xc.data_ptr(), t, n, rot.data_ptr(), stream=1)
+    torch.cuda.synchronize()
+    want2 = np.einsum("tij,tnj->tni", rot2, nodes0).reshape(t, 3 * n)
+    np.testing.assert_allclose(xc[:t, :3 * n].cpu().numpy(), want2, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(xc[:t, :3 * n].cpu().numpy(), xa[:t, :3 * n].cpu().numpy(), rtol=0, atol=1e-12)
+    assert float(xc[:, 3 * n:].abs().max()) == 0.0 if ld > 3 * n else True
+    del want1
+    # ... or fused into the centring pass (with the FP32 tile copy)
+    mean = torch.zeros(ld, dtype=torch.float64, device="cuda")
+    mean[:3 * n] = sums_b[3 * n_align:] / t
+    p_f = torch.zeros((t, npad // 128, 3, 128), dtype=torch.float32, device="cuda")
+    p_s = torch.zeros_like(p_f)
+    xd = xb.clone()
+    ctx.dev_center_rotated(xd.data_ptr(), t, n, mean.data_ptr(), rot.data_ptr(), d_p32=p_f.data_ptr(), stream=1)
+    ctx.dev_center(xc.data_ptr(), t, n, mean.data_ptr(), d_p32=p_s.data_ptr(), stream=1)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(xd[:t].cpu().numpy(), xc[:t].cpu().numpy(), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(p_f.cpu().numpy(), p_s.cpu().numpy(), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(xd[:t, :3 * n].cpu().numpy().sum(axis=0), 0.0, atol=1e-9 * t)

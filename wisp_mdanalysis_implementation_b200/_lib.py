@@ -69,6 +69,9 @@ SIGNATURES = {
     "wisp_dev_com_align": (_int, [_c_ctx, _P, _P, _i64, _int, _P, _P, _P, _P]),
     "wisp_dev_align_sums": (_int, [_c_ctx, _P, _int, _P, _i64, _int, _int, _P, _P]),
     "wisp_dev_align_rotate": (_int, [_c_ctx, _P, _int, _P, _P, _i64, _int, _P, _P]),
+    "wisp_dev_align_iter": (_int, [_c_ctx, _P, _int, _P, _P, _i64, _int, _P, _int, _P, _P]),
+    "wisp_dev_align_nodes": (_int, [_c_ctx, _P, _i64, _int, _P, _P]),
+    "wisp_dev_center_rotated": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P, _P]),
     "wisp_dev_align_update": (_int, [_c_ctx, _P, _i64, _int, _int, _P, _P, _P]),
     "wisp_dev_center": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P]),
     "wisp_dev_colsum": (_int, [_c_ctx, _P, _i64, _int, _P, _P]),
@@ -436,6 +439,21 @@ class Context:
     def dev_align_rotate(self, d_align, n_align, d_avg_align, d_nodes, T, N, d_sums=None, stream=None):
         self._check(self._lib.wisp_dev_align_rotate(self._ctx, _ptr(d_align), n_align, _ptr(d_avg_align),
                                                     _ptr(d_nodes), T, N, _ptr(d_sums), _ptr(stream)))
+
+    def dev_align_iter(self, d_align, n_align, d_avg_align, d_nodes, T, N, d_rot_total, first, d_sums=None,
+                       stream=None):
+        """One alignment iteration with the node rotation deferred (nodes are only read)."""
+        self._check(self._lib.wisp_dev_align_iter(self._ctx, _ptr(d_align), n_align, _ptr(d_avg_align),
+                                                  _ptr(d_nodes), T, N, _ptr(d_rot_total), int(bool(first)),
+                                                  _ptr(d_sums), _ptr(stream)))
+
+    def dev_align_nodes(self, d_nodes, T, N, d_rot_total, stream=None):
+        self._check(self._lib.wisp_dev_align_nodes(self._ctx, _ptr(d_nodes), T, N, _ptr(d_rot_total),
+                                                   _ptr(stream)))
+
+    def dev_center_rotated(self, d_nodes, T, N, d_mean, d_rot_total, d_p32=None, stream=None):
+        self._check(self._lib.wisp_dev_center_rotated(self._ctx, _ptr(d_nodes), T, N, _ptr(d_mean),
+                                                      _ptr(d_rot_total), _ptr(d_p32), _ptr(stream)))
 
     def dev_align_update(self, d_sums, T_total, n_align, N, d_avg, d_res2, stream=None):
         self._check(self._lib.wisp_dev_align_update(self._ctx, _ptr(d_sums), T_total, n_align, N, _ptr(d_avg),

@@ -38,7 +38,8 @@ def build(force=False, verbose=False):
     nvcc = _nvcc()
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "wisp_b200.h")]
+    headers = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")]
+    headers.append(os.path.join(HERE, "..", "include", "wisp_b200.h"))
     hdr_m = max(os.path.getmtime(h) for h in headers)
 
     def compile_one(src):

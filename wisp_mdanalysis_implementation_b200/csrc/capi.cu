@@ -175,9 +175,9 @@ int upload_nodes(wisp_ctx* ctx, const double* nodes, int64_t T, int N, double** 
 int com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
                   const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
                   int n_align, int atomic, double** d_x_out, int64_t* ld_out,
-                  float* d_align_out = nullptr) {
+                  float* d_align_out = nullptr, const double** d_colsum_out = nullptr) {
     return wisp_com_from_host(ctx, coords, T, A, masses, node_ptr, atom_idx, N, align_idx, n_align, atomic,
-                              d_x_out, ld_out, d_align_out, nullptr);
+                              d_x_out, ld_out, d_align_out, nullptr, d_colsum_out);
 }
 
 }  // namespace
@@ -188,7 +188,7 @@ int com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const do
 int wisp_com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
                        const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
                        int n_align, int atomic, double** d_x_out, int64_t* ld_out, float* d_align_out,
-                       wisp_ctx* via) {
+                       wisp_ctx* via, const double** d_colsum_out) {
     const int64_t ld = wisp_node_ld(N), Tpad = wisp_frames_pad(T);
     wisp_com_plan* plan = nullptr;
     WISP_TRY(com_plan_create(ctx, A, masses, node_ptr, atom_idx, N, align_idx, n_align, atomic, &plan));
@@ -200,6 +200,16 @@ int wisp_com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, con
     const size_t frame_bytes = (size_t)A * 12;
     int64_t chunk = std::max<int64_t>(1, ((size_t)128 << 20) / frame_bytes);
     chunk = std::min(chunk, T);
+    // d_colsum_out: the node column sums come out of K1 (one row per chunk, summed in chunk order at the
+    // end) -- the alignment's initial node average then needs no pass over the trajectory
+    const int64_t n_chunks = (T + chunk - 1) / chunk;
+    double* d_chunk_sums = nullptr;
+    if (d_colsum_out) {
+        void* pc = nullptr;
+        rc = wisp_scratch(ctx, SCR_COM_COLSUM, (size_t)(n_chunks + 1) * ld * 8, &pc);
+        if (rc) { com_plan_destroy(ctx, plan); return rc; }
+        d_chunk_sums = (double*)pc;
+    }
     void* bufs[2] = {nullptr, nullptr};
     void* relay[2] = {nullptr, nullptr};
     cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
@@ -248,8 +258,13 @@ int wisp_com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, con
         }
         step(cudaStreamWaitEvent(st, copied[b], 0), "cudaStreamWaitEvent(compute stream)");
         if (err != cudaSuccess) break;
-        rc = launch_com_plan(ctx, plan, (const float*)bufs[b], nt, d_x, ld, t0, st, d_align_out);
+        rc = launch_com_plan(ctx, plan, (const float*)bufs[b], nt, d_x, ld, t0, st, d_align_out,
+                             d_chunk_sums ? d_chunk_sums + (size_t)it * ld : nullptr);
         step(cudaEventRecord(freed[b], st), "cudaEventRecord(freed)");
+    }
+    if (d_chunk_sums && rc == 0 && err == cudaSuccess) {
+        rc = launch_colsum_finish(ctx, d_chunk_sums, (int)n_chunks, ld, 3 * (int64_t)N, d_chunk_sums + (size_t)n_chunks * ld, st);
+        *d_colsum_out = d_chunk_sums + (size_t)n_chunks * ld;
     }
     if (via) {
         step(cudaSetDevice(via->device), "cudaSetDevice(relay)");
@@ -563,7 +578,7 @@ extern "C" int wisp_dev_com_align(wisp_ctx* ctx, wisp_com_plan* plan, const floa
 
 extern "C" int wisp_dev_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_nodes,
                                    int64_t T, int N, int first, double* d_sums, void* stream) {
-    WISP_CHECK(ctx && d_align && d_nodes && d_sums && T > 0, "dev_align_sums: bad argument");
+    WISP_CHECK(ctx && d_align && d_sums && T > 0, "dev_align_sums: bad argument");
     return launch_align_sums(ctx, d_align, n_align, d_nodes, wisp_node_ld(N), N, T, first != 0, d_sums,
                              wisp_stream(ctx, stream));
 }
@@ -573,6 +588,20 @@ extern "C" int wisp_dev_align_rotate(wisp_ctx* ctx, float* d_align, int n_align,
     WISP_CHECK(ctx && d_align && d_avg_align && d_nodes && T > 0, "dev_align_rotate: bad argument");
     return launch_align_rotate(ctx, d_align, n_align, d_avg_align, d_nodes, wisp_node_ld(N), N, T,
                                wisp_stream(ctx, stream), d_sums);
+}
+
+extern "C" int wisp_dev_align_iter(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align,
+                                   const double* d_nodes, int64_t T, int N, double* d_rot_total, int first,
+                                   double* d_sums, void* stream) {
+    WISP_CHECK(ctx && d_align && d_avg_align && d_nodes && d_rot_total && T > 0, "dev_align_iter: bad argument");
+    return launch_align_iter(ctx, d_align, n_align, d_avg_align, d_nodes, wisp_node_ld(N), N, T, d_rot_total,
+                             first != 0, wisp_stream(ctx, stream), d_sums);
+}
+
+extern "C" int wisp_dev_align_nodes(wisp_ctx* ctx, double* d_nodes, int64_t T, int N, const double* d_rot_total,
+                                    void* stream) {
+    WISP_CHECK(ctx && d_nodes && d_rot_total && T > 0, "dev_align_nodes: bad argument");
+    return launch_align_nodes(ctx, d_nodes, wisp_node_ld(N), N, T, d_rot_total, wisp_stream(ctx, stream));
 }
 
 extern "C" int wisp_dev_align_update(wisp_ctx* ctx, const double* d_sums, int64_t T_total, int n_align, int N,
@@ -586,6 +615,13 @@ extern "C" int wisp_dev_center(wisp_ctx* ctx, double* d_nodes, int64_t T, int N,
     WISP_CHECK(ctx && d_nodes && d_mean, "dev_center: null argument");
     return launch_center(ctx, d_nodes, T, wisp_node_ld(N), 3 * (int64_t)N, d_mean, wisp_stream(ctx, stream),
                          d_p32, N);
+}
+
+extern "C" int wisp_dev_center_rotated(wisp_ctx* ctx, double* d_nodes, int64_t T, int N, const double* d_mean,
+                                       const double* d_rot_total, float* d_p32, void* stream) {
+    WISP_CHECK(ctx && d_nodes && d_mean, "dev_center_rotated: null argument");
+    return launch_center(ctx, d_nodes, T, wisp_node_ld(N), 3 * (int64_t)N, d_mean, wisp_stream(ctx, stream),
+                         d_p32, N, d_rot_total);
 }
 
 extern "C" int wisp_dev_colsum(wisp_ctx* ctx, const double* d_nodes, int64_t T, int N, double* d_colsum,

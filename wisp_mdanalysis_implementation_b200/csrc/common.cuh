@@ -105,9 +105,10 @@ enum ScratchSlot {
     SCR_APSP_D, SCR_APSP_P, SCR_ARENA, SCR_ALIGN, SCR_P32,
     SCR_MISC0, SCR_MISC1, SCR_MISC2, SCR_MISC3, SCR_MISC4, SCR_MISC5, SCR_MISC6, SCR_MISC7,
     SCR_MISC8, SCR_MISC9, SCR_I8_PLANES, SCR_I8_SMALL, SCR_I8_PART, SCR_I8_STATS, SCR_APSP_R, SCR_APSP_T, SCR_APSP_M,
-    SCR_ALIGN_ROT, SCR_ALIGN_PART, SCR_PIPE_G, SCR_PIPE_D, SCR_PIPE_OUT, SCR_PIPE_STAGE0, SCR_PIPE_STAGE_LAST = SCR_PIPE_STAGE0 + 15,
+    SCR_ALIGN_ROT, SCR_ALIGN_ROTTOT, SCR_ALIGN_PART, SCR_COM_COLSUM, SCR_PIPE_G, SCR_PIPE_D, SCR_PIPE_OUT, SCR_PIPE_STAGE0, SCR_PIPE_STAGE_LAST = SCR_PIPE_STAGE0 + 15,
     SCR_RELAY0, SCR_RELAY_LAST = SCR_RELAY0 + 15, SCR_COUNT
 };
+static_assert(SCR_COUNT <= 96, "wisp_ctx::scratch is too small for the slot list");
 
 // ---- kernel launchers (one per .cu) -------------------------------------------------------
 int launch_com(wisp_ctx* ctx, const float* d_coords, int64_t T, int A, const double* d_masses,
@@ -139,7 +140,13 @@ typedef std::function<int(double* buf, size_t n, bool f32_chain, const AlignStep
 int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* d_nodes, int64_t ld,
                             int N, int64_t T, double threshold, int max_iter, double* d_work,
                             double* h_avg_nodes, double* log, int* n_iter_out, cudaStream_t st,
-                            int64_t T_total = 0, const AlignReduce& reduce = AlignReduce());
+                            int64_t T_total = 0, const AlignReduce& reduce = AlignReduce(),
+                            const double* d_node_colsum = nullptr, const double** d_rot_out = nullptr);
+int launch_align_iter(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align, const double* d_nodes,
+                      int64_t ld, int N, int64_t T, double* d_rot_total, bool first, cudaStream_t st,
+                      double* d_sums = nullptr);
+int launch_align_nodes(wisp_ctx* ctx, double* d_nodes, int64_t ld, int N, int64_t T, const double* d_rot_total,
+                       cudaStream_t st);
 int launch_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_nodes, int64_t ld,
                       int N, int64_t T, bool first, double* d_sums, cudaStream_t st);
 int launch_align_update(wisp_ctx* ctx, const double* d_sums, int64_t T_total, int n_align, int N, double* d_avg,
@@ -148,9 +155,12 @@ int launch_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double
                         int64_t ld, int N, int64_t T, cudaStream_t st, double* d_sums = nullptr);
 int launch_colsum(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int64_t ncols,
                   double* d_colsum, cudaStream_t st);
-// d_p32 != nullptr: also write the FP32 tile-referenced copy [T][n_tiles][3][128] for K3
+// d_p32 != nullptr: also write the FP32 tile-referenced copy [T][n_tiles][3][128] for K3.
+// d_rot != nullptr ([T][9], needs N): every frame is first rotated by its matrix (the node rotation the
+// alignment loop deferred, k7_align.cu) -- x <- R[t] x - mean in the same pass.
 int launch_center(wisp_ctx* ctx, double* d_x, int64_t T, int64_t ld, int64_t ncols,
-                  const double* d_mean, cudaStream_t st, float* d_p32 = nullptr, int N = 0);
+                  const double* d_mean, cudaStream_t st, float* d_p32 = nullptr, int N = 0,
+                  const double* d_rot = nullptr);
 int launch_gram(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_out, int stride,
                 double* d_out, cudaStream_t st);
 int launch_gram_dmma(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_out, int stride,
@@ -187,7 +197,7 @@ int launch_epilogue_peers(wisp_ctx* ctx, const PeerSums& ps, int64_t T_total, in
 int wisp_com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
                        const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
                        int n_align, int atomic, double** d_x_out, int64_t* ld_out, float* d_align_out,
-                       wisp_ctx* via = nullptr);
+                       wisp_ctx* via = nullptr, const double** d_colsum_out = nullptr);
 int wisp_pipeline_run(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
                       const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
                       int n_align, int atomic, double align_threshold, int max_align_iterations,

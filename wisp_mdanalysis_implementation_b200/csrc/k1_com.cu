@@ -159,13 +159,18 @@ __global__ void center_kernel(double* __restrict__ x, int64_t T, int64_t ld, int
 // of X are read and written coalesced; the (node, component) -> (component, node) transpose of P
 // goes through shared memory, 1.5 KB coalesced writes.  Each thread also keeps max|x| and sum x^2
 // of its centred column: the statistics the INT8 K2 engine scales by.
+// ROT: x is first rotated by the frame's matrix rot[t] (the node rotation the K7 loop deferred:
+// trajectory_analysis_functions.py:107 applied once with the composed rotation) -- the thread of column
+// 3n + c picks up the node's other two components from shared memory and forms row c of R x.
 constexpr int kCcFrames = 4;
 
+template <bool ROT>
 __global__ void __launch_bounds__(384)
 center_convert_kernel(double* __restrict__ x, int64_t T, int64_t ld, int N,
                       const double* __restrict__ mean, float* __restrict__ p32, int n_tiles,
-                      double* __restrict__ stat) {
+                      double* __restrict__ stat, const double* __restrict__ rot) {
     __shared__ float s[kCcFrames][3][kTile + 1];
+    __shared__ double raw[ROT ? kCcFrames : 1][ROT ? 3 * kTile : 1];
     const int tile = blockIdx.x;
     const int k = threadIdx.x;
     const int64_t col = (int64_t)3 * kTile * tile + k;
@@ -178,7 +183,21 @@ center_convert_kernel(double* __restrict__ x, int64_t T, int64_t ld, int N,
     for (int64_t t0 = (int64_t)blockIdx.y * kCcFrames; t0 < T; t0 += (int64_t)gridDim.y * kCcFrames) {
         double v[kCcFrames];
 #pragma unroll
-        for (int f = 0; f < kCcFrames; ++f) v[f] = (t0 + f < T) ? x[(t0 + f) * ld + col] : m;
+        for (int f = 0; f < kCcFrames; ++f) v[f] = (t0 + f < T) ? x[(t0 + f) * ld + col] : (ROT ? 0.0 : m);
+        if (ROT) {
+#pragma unroll
+            for (int f = 0; f < kCcFrames; ++f) raw[f][k] = v[f];
+            __syncthreads();
+#pragma unroll
+            for (int f = 0; f < kCcFrames; ++f) {
+                if (t0 + f < T) {
+                    const double* R = rot + (t0 + f) * 9 + 3 * c;
+                    v[f] = raw[f][3 * n] * __ldg(R) + raw[f][3 * n + 1] * __ldg(R + 1) + raw[f][3 * n + 2] * __ldg(R + 2);
+                } else {
+                    v[f] = m;
+                }
+            }
+        }
 #pragma unroll
         for (int f = 0; f < kCcFrames; ++f) {
             const double xc = v[f] - m;
@@ -256,7 +275,12 @@ int launch_colsum_f32(wisp_ctx* ctx, const float* d_x, int64_t T, int64_t ld, in
 }
 
 int launch_center(wisp_ctx* ctx, double* d_x, int64_t T, int64_t ld, int64_t ncols,
-                  const double* d_mean, cudaStream_t st, float* d_p32, int N) {
+                  const double* d_mean, cudaStream_t st, float* d_p32, int N, const double* d_rot) {
+    if (d_rot && !d_p32) {
+        // no fused form without the FP32 copy: rotate in place, then centre
+        WISP_CHECK(N > 0, "center: the node count is needed to rotate");
+        WISP_TRY(launch_align_nodes(ctx, d_x, ld, N, T, d_rot, st));
+    }
     if (d_p32) {
         const int n_tiles = (int)(round_up(N, kTile) / kTile);
         const int gy = (int)std::min<int64_t>((T + kCcFrames - 1) / kCcFrames,
@@ -266,8 +290,12 @@ int launch_center(wisp_ctx* ctx, double* d_x, int64_t T, int64_t ld, int64_t nco
         // here instead of reading X once more, if the next wisp_dev_gram is on this very block
         void* p_stat = nullptr;
         WISP_TRY(wisp_scratch(ctx, SCR_I8_STATS, (size_t)parts * 2 * 3 * kTile * n_tiles * 8, &p_stat));
-        center_convert_kernel<<<dim3(n_tiles, gy), 384, 0, st>>>(d_x, T, ld, N, d_mean, d_p32, n_tiles,
-                                                                 (double*)p_stat);
+        if (d_rot)
+            center_convert_kernel<true><<<dim3(n_tiles, gy), 384, 0, st>>>(d_x, T, ld, N, d_mean, d_p32, n_tiles,
+                                                                           (double*)p_stat, d_rot);
+        else
+            center_convert_kernel<false><<<dim3(n_tiles, gy), 384, 0, st>>>(d_x, T, ld, N, d_mean, d_p32, n_tiles,
+                                                                            (double*)p_stat, nullptr);
         ctx->launches++;
         WISP_CUDA(cudaGetLastError());
         ctx->i8_stats_x = d_x;

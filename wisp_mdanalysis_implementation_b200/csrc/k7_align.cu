@@ -5,21 +5,32 @@
 // needing MDAnalysis' rotation_matrix (QCP) and two numpy dots from Python.
 // One iteration = two kernels:
 //   align_solve_kernel   one WARP per frame: S = sum_i a_i b_i^T over the alignment landmarks (a = this
-//                        frame, b = current average), 9 FP64 sums reduced by shuffles; lane 0 builds
-//                        Horn's 4x4 quaternion matrix and diagonalises it with cyclic Jacobi rotations
-//                        in FP64 -- the eigenvector of the largest eigenvalue is the optimal proper
-//                        rotation (same minimiser as QCP / Kabsch with the reflection fix) -- and
-//                        stores R[frame] (72 bytes).  64 frames per SM are in flight, so the serial
-//                        eigen-solve never leaves the memory system idle;
-//   align_apply_kernel   HBM-bound streaming pass: thread = one node (float64, :107) or one landmark
-//                        (float32 like the reference's all_pos_Align array, :106), walks a segment of
-//                        frames, rotates in place and keeps the running column sums of what it stores in
-//                        registers -- the new averages (:110-111) come out of the same pass (per-segment
-//                        partial rows, fixed-order finish: deterministic) instead of re-reading both arrays.
-// Round 1 ran one CTA per frame with a block reduction and thread 0 solving while 255 threads waited,
-// then two separate column-sum passes: 5.6 ms per iteration at C2; this form moves 7.2 GB per iteration.
+//                        frame, b = current average), 9 FP64 sums reduced by shuffles; lane 0 finds the
+//                        optimal proper rotation (align_solve.cuh: Newton on the quartic of Horn's
+//                        quaternion matrix + adjugate column + Rayleigh polish; Jacobi only for degenerate
+//                        spectra), stores R[frame] and composes it into the frame's TOTAL rotation
+//                        R_tot[frame] <- R R_tot[frame];
+//   align_apply_kernel   HBM-bound streaming pass, warp-autonomous (no block barrier anywhere): a warp
+//                        owns 32 landmarks (float32 like the reference's all_pos_Align array, :106) or 32
+//                        nodes (float64, :107) and a segment of frames.  Landmarks are rotated in place
+//                        by R; the NODE trajectory is only READ -- the column sums of R_tot x_original
+//                        are what the iteration needs of it (:111, the printed node RMSD and, after the
+//                        last iteration, the frame mean), so the 2.4 GB array is not rewritten every
+//                        iteration.  The one in-place rotation of the nodes is fused into the centring
+//                        pass that follows the loop (launch_center with d_rot), or done by
+//                        launch_align_nodes for callers that want the aligned trajectory itself.
+//                        Global traffic is fully coalesced (lane l moves columns l, l+32, l+64 of the
+//                        warp's 96-column span, four frames in flight), the (x, y, z) triples are regrouped
+//                        through a warp-private shared-memory patch, and the running sums of the columns
+//                        stay in registers (per-segment partial rows, fixed-order finish: deterministic).
+// Rounding: the reference rounds the nodes to float64 after every iteration's rotation; composing the
+// rotations first differs from that by ~1e-16 relative (the landmarks, whose float32 rounding per
+// iteration IS visible in the result, are rotated every iteration exactly as before).
+// Bytes per iteration and frame: 36 n_align (landmarks: read by the solve, read + written by the apply
+// pass) + 24 N (nodes read) -- round 2's first cut moved 36 n_align + 48 N and round 1 twice that.
 // The host loop checks the RMSD between successive landmark averages against the threshold (:118).
 #include "common.cuh"
+#include "align_solve.cuh"
 #include <cmath>
 
 int launch_colsum_f32(wisp_ctx* ctx, const float* d_x, int64_t T, int64_t ld, int64_t ncols,
@@ -29,44 +40,10 @@ namespace {
 
 constexpr int kAlThreads = 256;
 
-__device__ void jacobi4(double A[4][4], double V[4][4]) {
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
-    for (int sweep = 0; sweep < 32; ++sweep) {
-        double off = 0.0;
-        for (int p = 0; p < 4; ++p)
-            for (int q = p + 1; q < 4; ++q) off += A[p][q] * A[p][q];
-        double diag = 0.0;
-        for (int p = 0; p < 4; ++p) diag += A[p][p] * A[p][p];
-        if (off <= 1e-32 * diag || off == 0.0) break;
-        for (int p = 0; p < 4; ++p)
-            for (int q = p + 1; q < 4; ++q) {
-                if (A[p][q] == 0.0) continue;
-                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
-                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < 4; ++k) {
-                    const double akp = A[k][p], akq = A[k][q];
-                    A[k][p] = c * akp - s * akq;
-                    A[k][q] = s * akp + c * akq;
-                }
-                for (int k = 0; k < 4; ++k) {
-                    const double apk = A[p][k], aqk = A[q][k];
-                    A[p][k] = c * apk - s * aqk;
-                    A[q][k] = s * apk + c * aqk;
-                }
-                for (int k = 0; k < 4; ++k) {
-                    const double vkp = V[k][p], vkq = V[k][q];
-                    V[k][p] = c * vkp - s * vkq;
-                    V[k][q] = s * vkp + c * vkq;
-                }
-            }
-    }
-}
-
+// rot [T][9]: this iteration's rotation; rot_total [T][9] (may be NULL): compose != 0 ? R * rot_total : R
 __global__ void __launch_bounds__(kAlThreads)
 align_solve_kernel(const float* __restrict__ align, int n_align, const double* __restrict__ avg_align, int64_t T,
-                   double* __restrict__ rot) {
+                   double* __restrict__ rot, double* __restrict__ rot_total, int compose) {
     const int lane = threadIdx.x & 31;
     const int64_t f = (int64_t)blockIdx.x * (kAlThreads / 32) + (threadIdx.x >> 5);
     if (f >= T) return;
@@ -74,6 +51,7 @@ align_solve_kernel(const float* __restrict__ align, int n_align, const double* _
     double s[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) s[k] = 0.0;
+#pragma unroll 2
     for (int i = lane; i < n_align; i += 32) {
         const double ax = fa[3 * i], ay = fa[3 * i + 1], az = fa[3 * i + 2];
         const double bx = __ldg(avg_align + 3 * i), by = __ldg(avg_align + 3 * i + 1), bz = __ldg(avg_align + 3 * i + 2);
@@ -86,44 +64,43 @@ align_solve_kernel(const float* __restrict__ align, int n_align, const double* _
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
     if (lane != 0) return;
-    const double Sxx = s[0], Sxy = s[1], Sxz = s[2], Syx = s[3], Syy = s[4], Syz = s[5],
-                 Szx = s[6], Szy = s[7], Szz = s[8];
-    double A[4][4] = {
-        {Sxx + Syy + Szz, Syz - Szy, Szx - Sxz, Sxy - Syx},
-        {Syz - Szy, Sxx - Syy - Szz, Sxy + Syx, Szx + Sxz},
-        {Szx - Sxz, Sxy + Syx, -Sxx + Syy - Szz, Syz + Szy},
-        {Sxy - Syx, Szx + Sxz, Syz + Szy, -Sxx - Syy + Szz}};
-    double V[4][4];
-    jacobi4(A, V);
-    int best = 0;
-    for (int k = 1; k < 4; ++k)
-        if (A[k][k] > A[best][best]) best = k;
-    double q0 = V[0][best], qx = V[1][best], qy = V[2][best], qz = V[3][best];
-    const double nq = sqrt(q0 * q0 + qx * qx + qy * qy + qz * qz);
-    q0 /= nq; qx /= nq; qy /= nq; qz /= nq;
-    double* R = rot + f * 9;
-    R[0] = q0 * q0 + qx * qx - qy * qy - qz * qz; R[1] = 2 * (qx * qy - q0 * qz); R[2] = 2 * (qx * qz + q0 * qy);
-    R[3] = 2 * (qy * qx + q0 * qz); R[4] = q0 * q0 - qx * qx + qy * qy - qz * qz; R[5] = 2 * (qy * qz - q0 * qx);
-    R[6] = 2 * (qz * qx - q0 * qy); R[7] = 2 * (qz * qy + q0 * qx); R[8] = q0 * q0 - qx * qx - qy * qy + qz * qz;
+    double R[9];
+    horn_rotation(s, R);
+    double* out = rot + f * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out[k] = R[k];
+    if (rot_total) {
+        double* tot = rot_total + f * 9;
+        if (compose) {
+            double P[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) P[k] = tot[k];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    tot[3 * i + j] = R[3 * i] * P[j] + R[3 * i + 1] * P[3 + j] + R[3 * i + 2] * P[6 + j];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) tot[k] = R[k];
+        }
+    }
 }
 
-// x <- x . R^T (row vector times R transposed == R x) for every frame of segment blockIdx.y.
-// A CTA owns 128 consecutive landmarks (float32; blocks [0, gl)) or nodes (float64; blocks [gl, ..)),
-// i.e. 384 consecutive columns of a frame row.  Global traffic is fully coalesced: thread t moves columns
-// t, t+128, t+256 of the span (four frames per step, all loads in flight together), the (x, y, z) triples
-// are regrouped through shared memory, and the running sums of the columns a thread STORES stay in its
-// registers.  (A thread-per-node version with three stride-24-byte accesses per frame ran at 2.5 TB/s:
-// partial-sector stores.)  part [n_seg][3 n_align + 3 N]: column sums of the values stored by a segment.
-constexpr int kApplyThreads = 128;
+// x <- x . R^T (row vector times R transposed == R x) for the frames [f0, f1) and the 32 items
+// [item0, item0 + 32) of a [frame][item][3] array with row stride `row_stride`.
+// WRITE: store the rotated values (rounded to T) in place; SUMS: part_cols[3 item + c] = column sums of the
+// rotated values (of the STORED values when WRITE: the reference sums its float32 array, :110).
+constexpr int kApplyWarps = 8;
 constexpr int kApplyFrames = 4;
 
-template <typename T>
-__device__ __forceinline__ void align_apply_block(T* __restrict__ base, int64_t row_stride, int n_items, int item0,
-                                                  int64_t f0, int64_t f1, const double* __restrict__ rot,
-                                                  double* __restrict__ part_cols, T (*sm)[3 * kApplyThreads]) {
-    const int t = threadIdx.x;
-    const int ncol = 3 * min(kApplyThreads, n_items - item0);
-    const int64_t col0 = 3 * (int64_t)item0;
+template <typename T, bool WRITE, bool SUMS>
+__device__ __forceinline__ void align_apply_warp(T* __restrict__ base, int64_t row_stride, int n_items, int item0,
+                                                 int64_t f0, int64_t f1, const double* __restrict__ rot,
+                                                 double* __restrict__ part_cols, T (*sm)[96]) {
+    const int lane = threadIdx.x & 31;
+    const int ncol = 3 * min(32, n_items - item0);
+    T* col = base + 3 * (int64_t)item0;
     double s[3] = {0.0, 0.0, 0.0};
     for (int64_t f = f0; f < f1; f += kApplyFrames) {
         const int nf = (int)min((int64_t)kApplyFrames, f1 - f);
@@ -132,61 +109,88 @@ __device__ __forceinline__ void align_apply_block(T* __restrict__ base, int64_t 
         for (int q = 0; q < kApplyFrames; ++q)
 #pragma unroll
             for (int u = 0; u < 3; ++u) {
-                const int c = t + kApplyThreads * u;
-                v[q][u] = (q < nf && c < ncol) ? base[(f + q) * row_stride + col0 + c] : (T)0;
+                const int c = lane + 32 * u;
+                v[q][u] = (q < nf && c < ncol) ? col[(f + q) * row_stride + c] : (T)0;
             }
 #pragma unroll
         for (int q = 0; q < kApplyFrames; ++q)
 #pragma unroll
-            for (int u = 0; u < 3; ++u) sm[q][t + kApplyThreads * u] = v[q][u];
-        __syncthreads();
-        if (3 * t < ncol) {
+            for (int u = 0; u < 3; ++u) sm[q][lane + 32 * u] = v[q][u];
+        __syncwarp();
+        if (3 * lane < ncol) {
 #pragma unroll
             for (int q = 0; q < kApplyFrames; ++q)
                 if (q < nf) {
                     const double* R = rot + (f + q) * 9;
-                    const double x = (double)sm[q][3 * t], y = (double)sm[q][3 * t + 1], z = (double)sm[q][3 * t + 2];
-                    sm[q][3 * t + 0] = (T)(x * __ldg(R + 0) + y * __ldg(R + 1) + z * __ldg(R + 2));
-                    sm[q][3 * t + 1] = (T)(x * __ldg(R + 3) + y * __ldg(R + 4) + z * __ldg(R + 5));
-                    sm[q][3 * t + 2] = (T)(x * __ldg(R + 6) + y * __ldg(R + 7) + z * __ldg(R + 8));
-                }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < kApplyFrames; ++q)
-            if (q < nf) {
-#pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    const int c = t + kApplyThreads * u;
-                    if (c < ncol) {
-                        const T o = sm[q][c];
-                        base[(f + q) * row_stride + col0 + c] = o;
-                        s[u] += (double)o;
+                    const double x = (double)sm[q][3 * lane], y = (double)sm[q][3 * lane + 1], z = (double)sm[q][3 * lane + 2];
+                    const double rx = x * __ldg(R + 0) + y * __ldg(R + 1) + z * __ldg(R + 2);
+                    const double ry = x * __ldg(R + 3) + y * __ldg(R + 4) + z * __ldg(R + 5);
+                    const double rz = x * __ldg(R + 6) + y * __ldg(R + 7) + z * __ldg(R + 8);
+                    if (WRITE) {
+                        sm[q][3 * lane + 0] = (T)rx;
+                        sm[q][3 * lane + 1] = (T)ry;
+                        sm[q][3 * lane + 2] = (T)rz;
+                    } else if (SUMS) {
+                        s[0] += rx; s[1] += ry; s[2] += rz;
                     }
                 }
-            }
-        // (the next step's shared-memory writes of this thread go to the very slots it has just read)
-    }
+        }
+        if (WRITE) {
+            __syncwarp();
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
-        const int c = t + kApplyThreads * u;
-        if (c < ncol) part_cols[col0 + c] = s[u];
+            for (int q = 0; q < kApplyFrames; ++q)
+                if (q < nf) {
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int c = lane + 32 * u;
+                        if (c < ncol) {
+                            const T o = sm[q][c];
+                            col[(f + q) * row_stride + c] = o;
+                            if (SUMS) s[u] += (double)o;
+                        }
+                    }
+                }
+            // (a lane's next shared-memory writes go to the very slots it has just read)
+        } else {
+            __syncwarp();       // every lane has read its triple before the patch is overwritten
+        }
+    }
+    if (SUMS) {
+        if (WRITE) {            // lane owns columns lane, lane + 32, lane + 64 of the span
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int c = lane + 32 * u;
+                if (c < ncol) part_cols[3 * (int64_t)item0 + c] = s[u];
+            }
+        } else if (3 * lane < ncol) {   // lane owns item item0 + lane
+#pragma unroll
+            for (int u = 0; u < 3; ++u) part_cols[3 * (int64_t)(item0 + lane) + u] = s[u];
+        }
     }
 }
 
-__global__ void __launch_bounds__(kApplyThreads)
+// grid (ceil(groups / 8), n_seg); a warp = one group of 32 items; landmark groups come first.
+// NODE_WRITE: the nodes are rotated in place by rot_nodes (the old per-iteration behaviour and the final
+// in-place rotation); otherwise they are only read.  align == NULL: nodes only.  part == NULL: no sums.
+template <bool NODE_WRITE, bool SUMS>
+__global__ void __launch_bounds__(kApplyWarps * 32)
 align_apply_kernel(float* __restrict__ align, int n_align, double* __restrict__ nodes, int64_t ld, int N,
-                   int64_t T, const double* __restrict__ rot, int64_t frames_per_seg, double* __restrict__ part) {
-    __shared__ __align__(16) double smd[kApplyFrames][3 * kApplyThreads];
-    const int gl = (n_align + kApplyThreads - 1) / kApplyThreads;      // landmark blocks come first
+                   int64_t T, const double* __restrict__ rot, const double* __restrict__ rot_nodes,
+                   int64_t frames_per_seg, double* __restrict__ part) {
+    __shared__ __align__(16) double smd[kApplyWarps][kApplyFrames][96];
+    const int w = threadIdx.x >> 5;
+    const int gl = align ? (n_align + 31) / 32 : 0;
+    const int gn = (N + 31) / 32;
+    const int g = blockIdx.x * kApplyWarps + w;
+    if (g >= gl + gn) return;
     const int64_t f0 = (int64_t)blockIdx.y * frames_per_seg, f1 = min(T, f0 + frames_per_seg);
-    double* prow = part + (int64_t)blockIdx.y * (3 * (int64_t)(n_align + N));
-    if ((int)blockIdx.x < gl)
-        align_apply_block<float>(align, 3 * (int64_t)n_align, n_align, blockIdx.x * kApplyThreads, f0, f1, rot, prow,
-                                 reinterpret_cast<float (*)[3 * kApplyThreads]>(smd));
+    double* prow = SUMS ? part + (int64_t)blockIdx.y * (3 * (int64_t)((align ? n_align : 0) + N)) : nullptr;
+    if (g < gl)
+        align_apply_warp<float, true, SUMS>(align, 3 * (int64_t)n_align, n_align, g * 32, f0, f1, rot, prow,
+                                            reinterpret_cast<float (*)[96]>(smd[w]));
     else
-        align_apply_block<double>(nodes, ld, N, (blockIdx.x - gl) * kApplyThreads, f0, f1, rot,
-                                  prow + 3 * (int64_t)n_align, smd);
+        align_apply_warp<double, NODE_WRITE, SUMS>(nodes, ld, N, (g - gl) * 32, f0, f1, rot_nodes,
+                                                   SUMS ? prow + 3 * (int64_t)(align ? n_align : 0) : nullptr, smd[w]);
 }
 
 // np.sum(float32 array, axis=0) of the reference (:86): sequential float32 adds down the frames.
@@ -267,11 +271,13 @@ int launch_align_update(wisp_ctx* ctx, const double* d_sums, int64_t T_total, in
     return 0;
 }
 
-// ---- building blocks (also the device-level C ABI: wisp_dev_align_sums / wisp_dev_align_iter) ----
+// ---- building blocks (also the device-level C ABI: wisp_dev_align_sums / _iter / _nodes / _rotate) ----
 // d_sums [na3 + nn3]: first the landmark column sums, then the node column sums of this frame block.
 // first == true: landmark sums as the reference's sequential float32 sums (initial average, :86):
 // d_sums[0, na3) must hold the running totals of the earlier frame blocks on entry (zeros for the
 // first block) and holds the totals including this block on exit.
+// d_nodes == NULL: the caller already has the node column sums (K1 produces them, launch_com_plan's
+// d_colsum) and d_sums[na3, ..) is left alone.
 int launch_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_nodes, int64_t ld,
                       int N, int64_t T, bool first, double* d_sums, cudaStream_t st) {
     const int64_t na3 = 3 * (int64_t)n_align, nn3 = 3 * (int64_t)N;
@@ -282,56 +288,136 @@ int launch_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const do
     } else {
         WISP_TRY(launch_colsum_f32(ctx, d_align, T, na3, na3, d_sums, st));
     }
-    WISP_TRY(launch_colsum(ctx, d_nodes, T, ld, nn3, d_sums + na3, st));
+    if (d_nodes) WISP_TRY(launch_colsum(ctx, d_nodes, T, ld, nn3, d_sums + na3, st));
     return 0;
 }
 
-// one alignment pass over this frame block: rotate every frame onto d_avg_align (in place); d_sums
-// [3 n_align + 3 N] (may be NULL) receives the column sums of the rotated landmarks, then of the rotated
-// nodes -- what launch_align_sums(first = false) would compute, without reading either array again
+namespace {
+
+// segments of frames so that the apply grid fills the machine about six CTAs deep
+int apply_segments(wisp_ctx* ctx, int groups, int64_t T, int64_t* per_out) {
+    const int gx = (groups + kApplyWarps - 1) / kApplyWarps;
+    int n_seg = (int)std::max<int64_t>(1, std::min<int64_t>((T + 63) / 64, (int64_t)ctx->sm_count * 6 / gx));
+    const int64_t per = round_up((T + n_seg - 1) / n_seg, kApplyFrames);
+    *per_out = per;
+    return (int)((T + per - 1) / per);
+}
+
+int launch_solve(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_avg_align, int64_t T,
+                 double* d_rot, double* d_rot_total, bool compose, cudaStream_t st) {
+    align_solve_kernel<<<(unsigned)((T + kAlThreads / 32 - 1) / (kAlThreads / 32)), kAlThreads, 0, st>>>(
+        d_align, n_align, d_avg_align, T, d_rot, d_rot_total, compose ? 1 : 0);
+    ctx->launches++;
+    WISP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// One alignment iteration over this frame block with the node rotation DEFERRED: the landmarks are
+// rotated onto d_avg_align in place, d_rot_total [T][9] <- R (first) or R d_rot_total, and d_sums
+// [3 n_align + 3 N] (may be NULL) receives the column sums of the rotated landmarks, then of
+// d_rot_total applied to the (unchanged) nodes.
+int launch_align_iter(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align, const double* d_nodes,
+                      int64_t ld, int N, int64_t T, double* d_rot_total, bool first, cudaStream_t st, double* d_sums) {
+    void *pr = nullptr, *pp = nullptr;
+    WISP_TRY(wisp_scratch(ctx, SCR_ALIGN_ROT, (size_t)T * 9 * 8, &pr));
+    double* d_rot = (double*)pr;
+    WISP_TRY(launch_solve(ctx, d_align, n_align, d_avg_align, T, d_rot, d_rot_total, !first, st));
+    const int groups = (n_align + 31) / 32 + (N + 31) / 32;
+    int64_t per = 0;
+    const int n_seg = apply_segments(ctx, groups, T, &per);
+    const int64_t ncols = 3 * (int64_t)(n_align + N);
+    const dim3 grid((groups + kApplyWarps - 1) / kApplyWarps, n_seg);
+    if (d_sums) {
+        WISP_TRY(wisp_scratch(ctx, SCR_ALIGN_PART, (size_t)n_seg * ncols * 8, &pp));
+        align_apply_kernel<false, true><<<grid, kApplyWarps * 32, 0, st>>>(
+            d_align, n_align, const_cast<double*>(d_nodes), ld, N, T, d_rot, d_rot_total, per, (double*)pp);
+    } else {
+        // nothing to sum: only the landmarks move
+        const dim3 grid_l(((n_align + 31) / 32 + kApplyWarps - 1) / kApplyWarps, n_seg);
+        align_apply_kernel<false, false><<<grid_l, kApplyWarps * 32, 0, st>>>(
+            d_align, n_align, nullptr, ld, 0, T, d_rot, d_rot_total, per, nullptr);
+    }
+    ctx->launches++;
+    WISP_CUDA(cudaGetLastError());
+    if (d_sums) WISP_TRY(launch_colsum_finish(ctx, (const double*)pp, n_seg, ncols, ncols, d_sums, st));
+    return 0;
+}
+
+// the deferred node rotation, in place: x[f] <- d_rot_total[f] x[f]
+int launch_align_nodes(wisp_ctx* ctx, double* d_nodes, int64_t ld, int N, int64_t T, const double* d_rot_total,
+                       cudaStream_t st) {
+    ctx->i8_stats_x = nullptr;               // the node trajectory is rotated in place
+    const int groups = (N + 31) / 32;
+    int64_t per = 0;
+    const int n_seg = apply_segments(ctx, groups, T, &per);
+    align_apply_kernel<true, false><<<dim3((groups + kApplyWarps - 1) / kApplyWarps, n_seg), kApplyWarps * 32, 0, st>>>(
+        nullptr, 0, d_nodes, ld, N, T, nullptr, d_rot_total, per, nullptr);
+    ctx->launches++;
+    WISP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// one alignment pass over this frame block with BOTH arrays rotated in place (the reference's literal
+// data flow, :106-107): rotate every frame onto d_avg_align; d_sums [3 n_align + 3 N] (may be NULL) receives
+// the column sums of the rotated landmarks, then of the rotated nodes
 int launch_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align, double* d_nodes,
                         int64_t ld, int N, int64_t T, cudaStream_t st, double* d_sums) {
     ctx->i8_stats_x = nullptr;               // the node trajectory is rotated in place
     void *pr = nullptr, *pp = nullptr;
     WISP_TRY(wisp_scratch(ctx, SCR_ALIGN_ROT, (size_t)T * 9 * 8, &pr));
     double* d_rot = (double*)pr;
-    align_solve_kernel<<<(unsigned)((T + kAlThreads / 32 - 1) / (kAlThreads / 32)), kAlThreads, 0, st>>>(
-        d_align, n_align, d_avg_align, T, d_rot);
-    const int items = n_align + N;
-    const int gx = (n_align + kApplyThreads - 1) / kApplyThreads + (N + kApplyThreads - 1) / kApplyThreads;
-    int n_seg = (int)std::max<int64_t>(1, std::min<int64_t>(T, (int64_t)ctx->sm_count * 6 / gx));
-    const int64_t per = (T + n_seg - 1) / n_seg;
-    n_seg = (int)((T + per - 1) / per);
-    const int64_t ncols = 3 * (int64_t)items;
-    WISP_TRY(wisp_scratch(ctx, SCR_ALIGN_PART, (size_t)n_seg * ncols * 8, &pp));
-    align_apply_kernel<<<dim3(gx, n_seg), kApplyThreads, 0, st>>>(d_align, n_align, d_nodes, ld, N, T, d_rot, per,
-                                                                 (double*)pp);
-    ctx->launches += 2;
+    WISP_TRY(launch_solve(ctx, d_align, n_align, d_avg_align, T, d_rot, nullptr, false, st));
+    const int groups = (n_align + 31) / 32 + (N + 31) / 32;
+    int64_t per = 0;
+    const int n_seg = apply_segments(ctx, groups, T, &per);
+    const int64_t ncols = 3 * (int64_t)(n_align + N);
+    const dim3 grid((groups + kApplyWarps - 1) / kApplyWarps, n_seg);
+    if (d_sums) {
+        WISP_TRY(wisp_scratch(ctx, SCR_ALIGN_PART, (size_t)n_seg * ncols * 8, &pp));
+        align_apply_kernel<true, true><<<grid, kApplyWarps * 32, 0, st>>>(d_align, n_align, d_nodes, ld, N, T, d_rot,
+                                                                        d_rot, per, (double*)pp);
+    } else {
+        align_apply_kernel<true, false><<<grid, kApplyWarps * 32, 0, st>>>(d_align, n_align, d_nodes, ld, N, T, d_rot,
+                                                                         d_rot, per, nullptr);
+    }
+    ctx->launches++;
     WISP_CUDA(cudaGetLastError());
     if (d_sums) WISP_TRY(launch_colsum_finish(ctx, (const double*)pp, n_seg, ncols, ncols, d_sums, st));
     return 0;
 }
 
-// d_align: float32 [T][n_align][3] (in/out); d_nodes: pitched float64 trajectory (in/out), T = the
-// frames of THIS shard, T_total = all frames.  `reduce` (may be empty) sums a host vector over the
-// frame shards in shard order (or, for the float32 chain, runs the shards' steps one after the other in
-// frame order); every shard then takes the same decisions from the same numbers.  d_work: [2 * round_up(na3,32) + round_up(nn3,32)].
+// d_align: float32 [T][n_align][3] (in/out); d_nodes: pitched float64 trajectory, T = the frames of THIS
+// shard, T_total = all frames.  `reduce` (may be empty) sums a host vector over the frame shards in shard
+// order (or, for the float32 chain, runs the shards' steps one after the other in frame order); every shard
+// then takes the same decisions from the same numbers.  d_work: [2 * round_up(na3,32) + round_up(nn3,32)].
+// d_node_colsum (may be NULL): the node column sums of this shard, already on the device (from K1).
+// d_rot_out == NULL: the nodes are rotated in place before returning.  Otherwise they are left as they
+// came and *d_rot_out = the per-frame total rotations [T][9] (NULL when no iteration ran) for the caller
+// to apply (launch_center's d_rot, launch_align_nodes).
 // Returns iterations run; log gets (iteration, residual, node RMSD) triples.
 int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* d_nodes, int64_t ld,
                             int N, int64_t T, double threshold, int max_iter, double* d_work,
                             double* h_avg_nodes, double* log, int* n_iter_out, cudaStream_t st,
-                            int64_t T_total, const AlignReduce& reduce) {
+                            int64_t T_total, const AlignReduce& reduce, const double* d_node_colsum,
+                            const double** d_rot_out) {
     const int64_t na3 = 3 * (int64_t)n_align, nn3 = 3 * (int64_t)N;
     if (T_total <= 0) T_total = T;
     double* d_avgA = d_work;                 // [na3]
     double* d_sums = d_avgA + round_up(na3, 32);   // [na3 + nn3]
+    void* prt = nullptr;
+    WISP_TRY(wisp_scratch(ctx, SCR_ALIGN_ROTTOT, (size_t)T * 9 * 8, &prt));
+    double* d_rot_total = (double*)prt;
     std::vector<double> avgA(na3), avgN(nn3), sums(na3 + nn3);
     // initial landmark totals: float32, chained over the shards in frame order (`reduce` with
     // f32_chain = true hands this shard the totals of the earlier shards, runs `step`, and returns the
     // grand totals); node sums: plain float64 sums combined afterwards
     auto step = [&](double* h_inout) -> int {
         WISP_CUDA(cudaMemcpyAsync(d_sums, h_inout, na3 * 8, cudaMemcpyHostToDevice, st));
-        WISP_TRY(launch_align_sums(ctx, d_align, n_align, d_nodes, ld, N, T, true, d_sums, st));
+        WISP_TRY(launch_align_sums(ctx, d_align, n_align, d_node_colsum ? nullptr : d_nodes, ld, N, T, true, d_sums, st));
+        if (d_node_colsum)
+            WISP_CUDA(cudaMemcpyAsync(d_sums + na3, d_node_colsum, nn3 * 8, cudaMemcpyDeviceToDevice, st));
         WISP_CUDA(cudaMemcpyAsync(sums.data(), d_sums, (na3 + nn3) * 8, cudaMemcpyDeviceToHost, st));
         WISP_CUDA(cudaStreamSynchronize(st));
         memcpy(h_inout, sums.data(), na3 * 8);
@@ -352,7 +438,7 @@ int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* 
     int iteration = 0;
     double residual = threshold + 9999.0;
     while (residual > threshold && iteration < max_iter) {
-        WISP_TRY(launch_align_rotate(ctx, d_align, n_align, d_avgA, d_nodes, ld, N, T, st, d_sums));
+        WISP_TRY(launch_align_iter(ctx, d_align, n_align, d_avgA, d_nodes, ld, N, T, d_rot_total, iteration == 0, st, d_sums));
         WISP_CUDA(cudaMemcpyAsync(sums.data(), d_sums, (na3 + nn3) * 8, cudaMemcpyDeviceToHost, st));
         WISP_CUDA(cudaStreamSynchronize(st));
         if (reduce) WISP_TRY(reduce(sums.data(), (size_t)(na3 + nn3), false, AlignStep()));
@@ -365,6 +451,8 @@ int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* 
         WISP_CUDA(cudaMemcpyAsync(d_avgA, avgA.data(), na3 * 8, cudaMemcpyHostToDevice, st));
         if (log) { log[3 * (iteration - 1)] = iteration; log[3 * (iteration - 1) + 1] = residual; log[3 * (iteration - 1) + 2] = analysis; }
     }
+    if (d_rot_out) *d_rot_out = iteration > 0 ? d_rot_total : nullptr;
+    else if (iteration > 0) WISP_TRY(launch_align_nodes(ctx, d_nodes, ld, N, T, d_rot_total, st));
     WISP_CUDA(cudaStreamSynchronize(st));
     if (h_avg_nodes) memcpy(h_avg_nodes, avgN.data(), nn3 * 8);
     if (n_iter_out) *n_iter_out = iteration;

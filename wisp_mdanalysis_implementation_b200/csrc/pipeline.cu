@@ -134,8 +134,9 @@ int shard_body(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
     double* d_x = nullptr;
     int64_t ldx = 0;
     wisp_ctx* via = (S.via[r] != r) ? S.ctxs[S.via[r]] : nullptr;
+    const double* d_k1_colsum = nullptr;      // node column sums of this shard, out of K1
     WISP_TRY(wisp_com_from_host(ctx, a.coords + (size_t)t0 * a.A * 3, Tl, a.A, a.masses, a.node_ptr, a.atom_idx, N,
-                                a.align_idx, a.n_align, a.atomic, &d_x, &ldx, d_align, via));
+                                a.align_idx, a.n_align, a.atomic, &d_x, &ldx, d_align, via, &d_k1_colsum));
     const double t_s1 = host_ms();
     // small device vectors + the partial sums live in this shard's arena
     void* pw = nullptr;
@@ -154,6 +155,9 @@ int shard_body(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
     // ---- S2: K7 ----
     std::vector<double> mean(nn3);
     bool have_mean = false;
+    // the alignment leaves the nodes as K1 wrote them and hands back the per-frame total rotations: the one
+    // in-place rotation rides in the centring pass (unless the caller wants the aligned trajectory itself)
+    const double* d_rot = nullptr;
     if (a.max_align_iterations > 0) {
         int n_iter = 0;
         AlignReduce red = [&](double* buf, size_t n, bool f32, const AlignStep& step) {
@@ -161,15 +165,15 @@ int shard_body(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
         };
         WISP_TRY(run_iterative_alignment(ctx, d_align, a.n_align, d_x, ld, N, Tl, a.align_threshold,
                                          a.max_align_iterations, d_work, mean.data(), r == 0 ? a.out_log : nullptr,
-                                         &n_iter, st, a.T, R > 1 ? red : AlignReduce()));
+                                         &n_iter, st, a.T, R > 1 ? red : AlignReduce(), d_k1_colsum,
+                                         a.out_nodes ? nullptr : &d_rot));
         if (r == 0 && a.out_n_iter) *a.out_n_iter = n_iter;
         have_mean = true;       // the node average of the last iteration IS the frame mean (:112)
     }
     const double t_s2 = host_ms();
     // ---- S3: mean, centring, K2, K3 ----
     if (!have_mean) {
-        WISP_TRY(launch_colsum(ctx, d_x, Tl, ld, nn3, d_sum, st));
-        WISP_CUDA(cudaMemcpyAsync(mean.data(), d_sum, nn3 * 8, cudaMemcpyDeviceToHost, st));
+        WISP_CUDA(cudaMemcpyAsync(mean.data(), d_k1_colsum, nn3 * 8, cudaMemcpyDeviceToHost, st));
         WISP_CUDA(cudaStreamSynchronize(st));
         WISP_TRY(reduce_host(S, r, mean.data(), (size_t)nn3));
         for (auto& v : mean) v /= (double)a.T;
@@ -182,7 +186,7 @@ int shard_body(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
                                     (size_t)Tl, cudaMemcpyDeviceToHost, st));
     void* pp = nullptr;
     WISP_TRY(wisp_scratch(ctx, SCR_P32, (size_t)Tl * n_pad * 12, &pp));
-    WISP_TRY(launch_center(ctx, d_x, Tl, ld, nn3, d_mean, st, (float*)pp, N));
+    WISP_TRY(launch_center(ctx, d_x, Tl, ld, nn3, d_mean, st, (float*)pp, N, d_rot));
     WISP_TRY(launch_gram(ctx, d_x, Tl, ld, N, 3, d_gram, st));
     WISP_TRY(launch_contact_sum(ctx, (const float*)pp, Tl, N, d_mean, d_dsum, st));
     WISP_CUDA(cudaStreamSynchronize(st));     // `mean` (host) was the source of an async copy; partials complete

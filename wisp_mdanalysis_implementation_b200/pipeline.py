@@ -121,6 +121,10 @@ class FramePipeline:
         if self.align_iterations > 0:
             self.d_align = torch.empty((self.T, self.n_align, 3), dtype=torch.float32, device=dev)
             self.d_align_sums = torch.zeros(3 * self.n_align + 3 * self.N, dtype=f64, device=dev)
+            # total rotation of every frame (K7 composes, the centring pass applies it once)
+            self.d_rot_total = torch.empty((self.T, 9), dtype=f64, device=dev)
+            self.d_node_sums = torch.zeros(self.ld, dtype=f64, device=dev)
+        self._rotation_pending = False
         self.d_parts = None
         self.k23_stream = torch.cuda.Stream(device=dev)
         n = self.N
@@ -144,9 +148,17 @@ class FramePipeline:
         written in d_colsum (fused into the streaming kernel)."""
         t = self.T if frames is None else frames
         d_al = self.d_align.data_ptr() + row0 * self.n_align * 12 if self.align_iterations > 0 else None
+        # with K7 on, the node column sums K1 produces seed the alignment's initial node average
+        # (accumulated over the coordinate blocks of a streamed pass)
+        want_sums = colsum or self.align_iterations > 0
         self.ctx.dev_com_align(self.plan, d_coords.data_ptr(), t, self.N,
                                self.d_x.data_ptr() + row0 * self.ld * 8,
-                               self.d_colsum.data_ptr() if colsum else None, d_al, stream=self._stream())
+                               self.d_colsum.data_ptr() if want_sums else None, d_al, stream=self._stream())
+        if self.align_iterations > 0:
+            if row0 == 0:
+                self.d_node_sums.copy_(self.d_colsum)
+            else:
+                self.d_node_sums.add_(self.d_colsum)
 
     def align(self):
         """K7, frame-sharded: every rank rotates its frames onto the current landmark average; the
@@ -158,21 +170,20 @@ class FramePipeline:
         na3, nn3 = 3 * self.n_align, 3 * self.N
         world = torch.distributed.get_world_size(self.group) if sharding.is_distributed(self.group) else 1
         # initial landmark totals (:86): sequential float32 sums, chained over the ranks in frame order --
-        # rank q continues from the totals rank q-1 left -- so the result is the single sequential sum
+        # rank q continues from the totals rank q-1 left -- so the result is the single sequential sum.
+        # The node sums came out of K1 (com()).
         self.d_align_sums.zero_()
         for q in range(world):
             if q == (torch.distributed.get_rank(self.group) if world > 1 else 0):
-                self.ctx.dev_align_sums(self.d_align.data_ptr(), self.n_align, self.d_x.data_ptr(), self.T, self.N,
+                self.ctx.dev_align_sums(self.d_align.data_ptr(), self.n_align, None, self.T, self.N,
                                         True, self.d_align_sums.data_ptr(), stream=s)
             if world > 1:
                 src = torch.distributed.get_global_rank(self.group, q) if self.group is not None else q
                 torch.distributed.broadcast(self.d_align_sums[:na3], src=src, group=self.group)
+        node_sums = self.d_node_sums[:nn3].clone()
         if world > 1:
-            node_sums = self.d_align_sums[na3:].clone()
             torch.distributed.all_reduce(node_sums, group=self.group)
-            sn = node_sums.cpu().numpy()
-        else:
-            sn = self.d_align_sums[na3:].cpu().numpy().copy()
+        sn = node_sums.cpu().numpy()
         sa = self.d_align_sums[:na3].cpu().numpy().astype(np.float32)
         # averages stay on the device ([landmarks || nodes], the layout of the sums); per iteration one
         # kernel turns the all-reduced sums into the new averages and the two squared residual sums, and
@@ -183,9 +194,10 @@ class FramePipeline:
         self.alignment_log = []
         residual, it = self.align_threshold + 9999.0, 0
         while residual > self.align_threshold and it < self.align_iterations:
-            self.ctx.dev_align_rotate(self.d_align.data_ptr(), self.n_align, d_avg.data_ptr(),
-                                      self.d_x.data_ptr(), self.T, self.N, d_sums=self.d_align_sums.data_ptr(),
-                                      stream=s)
+            # landmarks rotated in place, nodes only read: their rotation is composed into d_rot_total
+            self.ctx.dev_align_iter(self.d_align.data_ptr(), self.n_align, d_avg.data_ptr(),
+                                    self.d_x.data_ptr(), self.T, self.N, self.d_rot_total.data_ptr(), it == 0,
+                                    d_sums=self.d_align_sums.data_ptr(), stream=s)
             sharding.reduce_sums(self.d_align_sums, group=self.group)
             self.ctx.dev_align_update(self.d_align_sums.data_ptr(), self.T_total, self.n_align, self.N,
                                       d_avg.data_ptr(), d_res2.data_ptr(), stream=s)
@@ -194,14 +206,22 @@ class FramePipeline:
             node_rmsd = float(np.sqrt(float(r2[1]) / self.N))
             it += 1
             self.alignment_log.append((it, residual, node_rmsd))
+        self._rotation_pending = it > 0
         self.d_mean.zero_()
         self.d_mean[:nn3].copy_(d_avg[na3:])
         return it
 
     def center_on_mean(self):
-        """Centre with the mean already in d_mean (after align())."""
-        self.ctx.dev_center(self.d_x.data_ptr(), self.T, self.N, self.d_mean.data_ptr(),
-                            d_p32=self.d_p32.data_ptr(), stream=self._stream())
+        """Centre with the mean already in d_mean (after align()); the node rotation the alignment
+        deferred is applied in the same pass."""
+        if self._rotation_pending:
+            self.ctx.dev_center_rotated(self.d_x.data_ptr(), self.T, self.N, self.d_mean.data_ptr(),
+                                        self.d_rot_total.data_ptr(), d_p32=self.d_p32.data_ptr(),
+                                        stream=self._stream())
+            self._rotation_pending = False
+        else:
+            self.ctx.dev_center(self.d_x.data_ptr(), self.T, self.N, self.d_mean.data_ptr(),
+                                d_p32=self.d_p32.data_ptr(), stream=self._stream())
 
     def mean_and_center(self, have_colsum=False):
         s = self._stream()
