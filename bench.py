@@ -374,16 +374,19 @@ def main():
         b7.record()
         torch.cuda.synchronize()
         k7_ms = a7.elapsed_time(b7)
-        # per frame and iteration: landmarks read (solve), landmarks read + written (float32), nodes read +
-        # written (float64), the new column sums come out of the same pass; the initial (float32-chained)
-        # sums read both arrays once
+        # per frame and iteration: landmarks read (solve), landmarks read + written (float32), nodes READ
+        # (float64; their rotation is composed and applied once, inside the centring pass), the new column
+        # sums come out of the same pass; the initial (float32-chained) sums read the landmarks once (the
+        # node sums came out of K1)
         n_al = len(system.align_idx)
-        k7_bytes = T_local * ((n_it * 3 + 1) * (12.0 * n_al) + (n_it * 2 + 1) * (24.0 * N))
+        k7_bytes = T_local * ((n_it * 3 + 1) * (12.0 * n_al) + n_it * (24.0 * N))
         k7 = {"ms": k7_ms, "iterations": n_it, "ms_per_iteration": k7_ms / max(1, n_it), "bound": "hbm",
               "achieved_gbs": k7_bytes / (k7_ms * 1e-3) / 1e9, "peak_gbs": load_peaks()["hbm_gbs"],
               "frac": k7_bytes / (k7_ms * 1e-3) / 1e9 / load_peaks()["hbm_gbs"],
               "residuals": [r[1] for r in pipe.alignment_log],
-              "note": "host loop: one all-reduce of 3(n_align+N) doubles and one D2H of the same per iteration"}
+              "bytes_per_frame_iteration": 36.0 * n_al + 24.0 * N,
+              "note": "nodes are only read per iteration (rotations composed, applied once by the centring pass); "
+                      "host loop: one all-reduce of 3(n_align+N) doubles and one 16-byte D2H per iteration"}
         pipe.center_on_mean()
     else:
         pipe.mean_and_center(have_colsum=True)
@@ -465,13 +468,16 @@ def main():
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": k1_gbs / peaks["hbm_gbs"], "traffic": None,
                     "peak_source": peaks["source_hbm"]}
     try:
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+        # DRAM bytes per launch from the newest committed `ncu --set full` capture (tools/ncu_summarize.py)
+        import glob
+        traffic_file = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_traffic_r*.json")))[-1]
+        ncu = json.load(open(traffic_file))
         roofline["traffic"] = ncu.get(roofline["kernel"].split("<")[0])
         roofline_tensor["traffic"] = ncu.get(roofline_tensor["kernel"].split("<")[0])
         roofline_hbm["traffic"] = ncu.get("com_stream_kernel", 0.0) + ncu.get("align_shift_kernel", 0.0)
         for rf in (roofline, roofline_tensor, roofline_hbm):
-            rf["traffic_source"] = ncu.get("_source", "profiles/ncu_traffic_r1.json (ncu --set full of the round-1 build; "
-                                                     "these kernels are unchanged since)")
+            rf["traffic_source"] = "profiles/%s: %s" % (os.path.basename(traffic_file), ncu.get(
+                "_source", "ncu --set full of the round-1 build; these kernels are unchanged since"))
     except Exception:
         pass
 

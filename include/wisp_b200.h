@@ -143,7 +143,8 @@ int wisp_pipeline_log(wisp_ctx* ctx, const float* coords, int64_t T, int A, cons
                       double* out_nodes, double* out_log, int* out_n_iter);
 
 /* Host-clock stage times of the last wisp_pipeline on this context, as seen by the first GPU's thread:
- * [0] H2D || K1, [1] K7 alignment, [2] centring + K2 + K3, [3] waiting for the slowest GPU,
+ * [0] H2D || K1 || K3 (pair distances are invariant under the alignment, so K3 runs block by block under the
+ * transfer), [1] K7 alignment, [2] centring + K2, [3] waiting for the slowest GPU,
  * [4] fused cross-GPU epilogue + D2H, [5] total (ms); [7] GPUs used. */
 int wisp_pipeline_stats(wisp_ctx* ctx, double* out8);
 
@@ -223,10 +224,13 @@ int wisp_dev_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const doub
  * READ: d_sums [3 n_align + 3 N] (may be NULL) = column sums of the rotated landmarks, then of d_rot_total
  * applied to the unchanged nodes (:110-111).  After the loop the caller applies d_rot_total once, either
  * with wisp_dev_align_nodes (in place, :107) or fused into the centring pass (wisp_dev_center_rotated).
- * d_nodes == NULL in wisp_dev_align_sums: only the landmark sums are formed (K1 already gave the node sums). */
+ * d_nodes == NULL in wisp_dev_align_sums: only the landmark sums are formed (K1 already gave the node sums).
+ * d_gate (may be NULL): a device flag; while it is non-zero every kernel of the iteration is a no-op, so a
+ * caller may launch iteration k + 1 before it has read the residual of iteration k (no idle GPU between
+ * iterations); wisp_dev_align_update_gated raises it. */
 int wisp_dev_align_iter(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align,
                         const double* d_nodes, int64_t T, int N, double* d_rot_total, int first,
-                        double* d_sums, void* stream);
+                        double* d_sums, const int* d_gate, void* stream);
 int wisp_dev_align_nodes(wisp_ctx* ctx, double* d_nodes, int64_t T, int N, const double* d_rot_total,
                          void* stream);
 /* After the caller has all-reduced d_sums: d_avg [3 n_align + 3 N] <- d_sums / T_total in place (the new
@@ -234,6 +238,11 @@ int wisp_dev_align_nodes(wisp_ctx* ctx, double* d_nodes, int64_t T, int N, const
  * landmark columns and over the node columns (the RMSDs of :118-119 are sqrt(res2 / n)). */
 int wisp_dev_align_update(wisp_ctx* ctx, const double* d_sums, int64_t T_total, int n_align, int N,
                           double* d_avg, double* d_res2, void* stream);
+/* wisp_dev_align_update with the loop decision on the device: nothing happens while *d_gate != 0; otherwise
+ * d_res3 [3] = the two squared sums as above and a running count of the iterations done, and *d_gate is set
+ * when sqrt(d_res3[0] / n_align) <= threshold (the loop condition of :96). */
+int wisp_dev_align_update_gated(wisp_ctx* ctx, const double* d_sums, int64_t T_total, int n_align, int N,
+                                double* d_avg, double* d_res3, double threshold, int* d_gate, void* stream);
 /* X <- X - mean (in place), mean [ld]; pad columns / rows are left at zero.  When d_p32 is
  * not NULL it also receives the FP32 tile-referenced copy K3 reads:
  * float [T][wisp_gram_ld(N)/128][3][128], value = float(x - mean of the tile's middle node). */

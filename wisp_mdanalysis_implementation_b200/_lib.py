@@ -69,7 +69,8 @@ SIGNATURES = {
     "wisp_dev_com_align": (_int, [_c_ctx, _P, _P, _i64, _int, _P, _P, _P, _P]),
     "wisp_dev_align_sums": (_int, [_c_ctx, _P, _int, _P, _i64, _int, _int, _P, _P]),
     "wisp_dev_align_rotate": (_int, [_c_ctx, _P, _int, _P, _P, _i64, _int, _P, _P]),
-    "wisp_dev_align_iter": (_int, [_c_ctx, _P, _int, _P, _P, _i64, _int, _P, _int, _P, _P]),
+    "wisp_dev_align_iter": (_int, [_c_ctx, _P, _int, _P, _P, _i64, _int, _P, _int, _P, _P, _P]),
+    "wisp_dev_align_update_gated": (_int, [_c_ctx, _P, _i64, _int, _int, _P, _P, _dbl, _P, _P]),
     "wisp_dev_align_nodes": (_int, [_c_ctx, _P, _i64, _int, _P, _P]),
     "wisp_dev_center_rotated": (_int, [_c_ctx, _P, _i64, _int, _P, _P, _P, _P]),
     "wisp_dev_align_update": (_int, [_c_ctx, _P, _i64, _int, _int, _P, _P, _P]),
@@ -333,7 +334,7 @@ class Context:
     def pipeline_stats(self):
         s = np.empty(8)
         self._check(self._lib.wisp_pipeline_stats(self._ctx, _ptr(s)))
-        return dict(h2d_k1_ms=float(s[0]), k7_ms=float(s[1]), center_k2_k3_ms=float(s[2]),
+        return dict(h2d_k1_k3_ms=float(s[0]), k7_ms=float(s[1]), center_k2_ms=float(s[2]),
                     wait_for_slowest_gpu_ms=float(s[3]), epilogue_d2h_ms=float(s[4]), total_ms=float(s[5]),
                     gpus=int(s[7]))
 
@@ -441,11 +442,16 @@ class Context:
                                                     _ptr(d_nodes), T, N, _ptr(d_sums), _ptr(stream)))
 
     def dev_align_iter(self, d_align, n_align, d_avg_align, d_nodes, T, N, d_rot_total, first, d_sums=None,
-                       stream=None):
-        """One alignment iteration with the node rotation deferred (nodes are only read)."""
+                       d_gate=None, stream=None):
+        """One alignment iteration with the node rotation deferred (nodes are only read); a no-op while
+        the device flag d_gate is set."""
         self._check(self._lib.wisp_dev_align_iter(self._ctx, _ptr(d_align), n_align, _ptr(d_avg_align),
                                                   _ptr(d_nodes), T, N, _ptr(d_rot_total), int(bool(first)),
-                                                  _ptr(d_sums), _ptr(stream)))
+                                                  _ptr(d_sums), _ptr(d_gate), _ptr(stream)))
+
+    def dev_align_update_gated(self, d_sums, T_total, n_align, N, d_avg, d_res3, threshold, d_gate, stream=None):
+        self._check(self._lib.wisp_dev_align_update_gated(self._ctx, _ptr(d_sums), T_total, n_align, N, _ptr(d_avg),
+                                                          _ptr(d_res3), float(threshold), _ptr(d_gate), _ptr(stream)))
 
     def dev_align_nodes(self, d_nodes, T, N, d_rot_total, stream=None):
         self._check(self._lib.wisp_dev_align_nodes(self._ctx, _ptr(d_nodes), T, N, _ptr(d_rot_total),

@@ -188,7 +188,7 @@ int com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const do
 int wisp_com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
                        const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
                        int n_align, int atomic, double** d_x_out, int64_t* ld_out, float* d_align_out,
-                       wisp_ctx* via, const double** d_colsum_out) {
+                       wisp_ctx* via, const double** d_colsum_out, const ComChunkHook* on_chunk) {
     const int64_t ld = wisp_node_ld(N), Tpad = wisp_frames_pad(T);
     wisp_com_plan* plan = nullptr;
     WISP_TRY(com_plan_create(ctx, A, masses, node_ptr, atom_idx, N, align_idx, n_align, atomic, &plan));
@@ -261,6 +261,8 @@ int wisp_com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, con
         rc = launch_com_plan(ctx, plan, (const float*)bufs[b], nt, d_x, ld, t0, st, d_align_out,
                              d_chunk_sums ? d_chunk_sums + (size_t)it * ld : nullptr);
         step(cudaEventRecord(freed[b], st), "cudaEventRecord(freed)");
+        // whatever the caller wants done with the node rows [t0, t0 + nt) while the next block is in flight
+        if (on_chunk && *on_chunk && rc == 0 && err == cudaSuccess) rc = (*on_chunk)(d_x, ld, t0, nt);
     }
     if (d_chunk_sums && rc == 0 && err == cudaSuccess) {
         rc = launch_colsum_finish(ctx, d_chunk_sums, (int)n_chunks, ld, 3 * (int64_t)N, d_chunk_sums + (size_t)n_chunks * ld, st);
@@ -592,10 +594,16 @@ extern "C" int wisp_dev_align_rotate(wisp_ctx* ctx, float* d_align, int n_align,
 
 extern "C" int wisp_dev_align_iter(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align,
                                    const double* d_nodes, int64_t T, int N, double* d_rot_total, int first,
-                                   double* d_sums, void* stream) {
+                                   double* d_sums, const int* d_gate, void* stream) {
     WISP_CHECK(ctx && d_align && d_avg_align && d_nodes && d_rot_total && T > 0, "dev_align_iter: bad argument");
     return launch_align_iter(ctx, d_align, n_align, d_avg_align, d_nodes, wisp_node_ld(N), N, T, d_rot_total,
-                             first != 0, wisp_stream(ctx, stream), d_sums);
+                             first != 0, wisp_stream(ctx, stream), d_sums, d_gate);
+}
+
+extern "C" int wisp_dev_align_update_gated(wisp_ctx* ctx, const double* d_sums, int64_t T_total, int n_align, int N,
+                                           double* d_avg, double* d_res3, double threshold, int* d_gate, void* stream) {
+    WISP_CHECK(ctx && d_sums && d_avg && d_res3 && d_gate && T_total > 0, "dev_align_update_gated: bad argument");
+    return launch_align_update(ctx, d_sums, T_total, n_align, N, d_avg, d_res3, wisp_stream(ctx, stream), threshold, d_gate);
 }
 
 extern "C" int wisp_dev_align_nodes(wisp_ctx* ctx, double* d_nodes, int64_t T, int N, const double* d_rot_total,

@@ -144,13 +144,13 @@ int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* 
                             const double* d_node_colsum = nullptr, const double** d_rot_out = nullptr);
 int launch_align_iter(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align, const double* d_nodes,
                       int64_t ld, int N, int64_t T, double* d_rot_total, bool first, cudaStream_t st,
-                      double* d_sums = nullptr);
+                      double* d_sums = nullptr, const int* d_gate = nullptr);
 int launch_align_nodes(wisp_ctx* ctx, double* d_nodes, int64_t ld, int N, int64_t T, const double* d_rot_total,
                        cudaStream_t st);
 int launch_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_nodes, int64_t ld,
                       int N, int64_t T, bool first, double* d_sums, cudaStream_t st);
 int launch_align_update(wisp_ctx* ctx, const double* d_sums, int64_t T_total, int n_align, int N, double* d_avg,
-                        double* d_res2, cudaStream_t st);
+                        double* d_res2, cudaStream_t st, double threshold = -1.0, int* d_gate = nullptr);
 int launch_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align, double* d_nodes,
                         int64_t ld, int N, int64_t T, cudaStream_t st, double* d_sums = nullptr);
 int launch_colsum(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int64_t ncols,
@@ -160,7 +160,9 @@ int launch_colsum(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int64
 // alignment loop deferred, k7_align.cu) -- x <- R[t] x - mean in the same pass.
 int launch_center(wisp_ctx* ctx, double* d_x, int64_t T, int64_t ld, int64_t ncols,
                   const double* d_mean, cudaStream_t st, float* d_p32 = nullptr, int N = 0,
-                  const double* d_rot = nullptr);
+                  const double* d_rot = nullptr, bool stats_without_p32 = false);
+int launch_p32_convert(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int N, const double* d_ref,
+                       float* d_p32, cudaStream_t st);
 int launch_gram(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_out, int stride,
                 double* d_out, cudaStream_t st);
 int launch_gram_dmma(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int n_out, int stride,
@@ -176,8 +178,10 @@ int launch_reduce_partials(wisp_ctx* ctx, const double* part, int n_seg, int64_t
                            double* out, int tile_r, int tile_c, cudaStream_t st,
                            const int* gate = nullptr, int gate_want = 0);
 int wisp_pick_segments(int items_per_seg, int stages_total, int sm_count, int min_stages);
+// accumulate: d_out += the sums of this frame block (one segment per tile, no partial buffer) instead of
+// overwriting it -- the streamed pipeline calls K3 once per coordinate block
 int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, const double* d_mean,
-                       double* d_out, cudaStream_t st);
+                       double* d_out, cudaStream_t st, bool accumulate = false);
 int launch_epilogue(wisp_ctx* ctx, const double* d_gram, const double* d_dsum, int64_t T_total,
                     int N, double cutoff, int which_map, double* d_var, double* d_ncov,
                     double* d_corr, double* d_avgdist, int64_t* d_binary, double* d_w,
@@ -194,10 +198,13 @@ struct PeerSums {
 int launch_epilogue_peers(wisp_ctx* ctx, const PeerSums& ps, int64_t T_total, int N, int row0, int row1,
                           double cutoff, int which_map, double* d_diag, double* d_corr, double* d_avgdist,
                           int64_t* d_binary, double* d_w, cudaStream_t st);
+// called on the compute stream's behalf after K1 of every coordinate block: node rows [t0, t0 + nt) of d_x
+typedef std::function<int(double* d_x, int64_t ld, int64_t t0, int64_t nt)> ComChunkHook;
 int wisp_com_from_host(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
                        const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
                        int n_align, int atomic, double** d_x_out, int64_t* ld_out, float* d_align_out,
-                       wisp_ctx* via = nullptr, const double** d_colsum_out = nullptr);
+                       wisp_ctx* via = nullptr, const double** d_colsum_out = nullptr,
+                       const ComChunkHook* on_chunk = nullptr);
 int wisp_pipeline_run(wisp_ctx* ctx, const float* coords, int64_t T, int A, const double* masses,
                       const int32_t* node_ptr, const int32_t* atom_idx, int N, const int32_t* align_idx,
                       int n_align, int atomic, double align_threshold, int max_align_iterations,

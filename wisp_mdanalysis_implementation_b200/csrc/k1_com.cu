@@ -164,12 +164,16 @@ __global__ void center_kernel(double* __restrict__ x, int64_t T, int64_t ld, int
 // 3n + c picks up the node's other two components from shared memory and forms row c of R x.
 constexpr int kCcFrames = 4;
 
-template <bool ROT>
+// CENTER == false: X is left alone and only P is written, against the references in `mean` (any fixed
+// point per tile will do for K3, which takes the tile-pair offset from the same vector): the conversion the
+// streamed pipeline runs on every coordinate block as it arrives (pipeline.cu), long before the mean is known.
+// WRITE_P == false: centring (+ rotation) + statistics only -- P was already consumed.
+template <bool ROT, bool CENTER, bool WRITE_P>
 __global__ void __launch_bounds__(384)
 center_convert_kernel(double* __restrict__ x, int64_t T, int64_t ld, int N,
                       const double* __restrict__ mean, float* __restrict__ p32, int n_tiles,
                       double* __restrict__ stat, const double* __restrict__ rot) {
-    __shared__ float s[kCcFrames][3][kTile + 1];
+    __shared__ float s[WRITE_P ? kCcFrames : 1][3][kTile + 1];
     __shared__ double raw[ROT ? kCcFrames : 1][ROT ? 3 * kTile : 1];
     const int tile = blockIdx.x;
     const int k = threadIdx.x;
@@ -177,7 +181,7 @@ center_convert_kernel(double* __restrict__ x, int64_t T, int64_t ld, int N,
     const int c = k % 3, n = k / 3;
     int nref = kTile * tile + kTile / 2;
     if (nref > N - 1) nref = N - 1;
-    const double m = mean[col];
+    const double m = CENTER ? mean[col] : 0.0;
     const double ref = mean[3 * nref + c];
     double amax = 0.0, ssq = 0.0;
     for (int64_t t0 = (int64_t)blockIdx.y * kCcFrames; t0 < T; t0 += (int64_t)gridDim.y * kCcFrames) {
@@ -200,20 +204,24 @@ center_convert_kernel(double* __restrict__ x, int64_t T, int64_t ld, int N,
         }
 #pragma unroll
         for (int f = 0; f < kCcFrames; ++f) {
-            const double xc = v[f] - m;
-            if (t0 + f < T) x[(t0 + f) * ld + col] = xc;
-            amax = fmax(amax, fabs(xc));
-            ssq = fma(xc, xc, ssq);
-            s[f][c][n] = (float)(v[f] - ref);
+            if (CENTER) {
+                const double xc = v[f] - m;
+                if (t0 + f < T) x[(t0 + f) * ld + col] = xc;
+                amax = fmax(amax, fabs(xc));
+                ssq = fma(xc, xc, ssq);
+            }
+            if (WRITE_P) s[f][c][n] = (float)(v[f] - ref);
         }
-        __syncthreads();
+        if (WRITE_P || ROT) __syncthreads();
+        if (WRITE_P) {
 #pragma unroll
-        for (int f = 0; f < kCcFrames; ++f)
-            if (t0 + f < T)
-                p32[((t0 + f) * n_tiles + tile) * (int64_t)(3 * kTile) + k] = s[f][k / kTile][k % kTile];
-        __syncthreads();
+            for (int f = 0; f < kCcFrames; ++f)
+                if (t0 + f < T)
+                    p32[((t0 + f) * n_tiles + tile) * (int64_t)(3 * kTile) + k] = s[f][k / kTile][k % kTile];
+            __syncthreads();
+        }
     }
-    if (stat) {                        // [gridDim.y][2][3 * 128 * n_tiles]
+    if (CENTER && stat) {              // [gridDim.y][2][3 * 128 * n_tiles]
         const int64_t w = (int64_t)3 * kTile * n_tiles;
         stat[((int64_t)blockIdx.y * 2 + 0) * w + col] = amax;
         stat[((int64_t)blockIdx.y * 2 + 1) * w + col] = ssq;
@@ -274,14 +282,30 @@ int launch_colsum_f32(wisp_ctx* ctx, const float* d_x, int64_t T, int64_t ld, in
     return launch_colsum_t<float>(ctx, d_x, T, ld, ncols, d_colsum, st);
 }
 
+// FP32 tile-referenced copy of the rows [0, T) of d_x against the references in d_ref (layout of a mean
+// vector); X is not modified.
+int launch_p32_convert(wisp_ctx* ctx, const double* d_x, int64_t T, int64_t ld, int N, const double* d_ref,
+                       float* d_p32, cudaStream_t st) {
+    const int n_tiles = (int)(round_up(N, kTile) / kTile);
+    const int gy = (int)std::min<int64_t>((T + kCcFrames - 1) / kCcFrames,
+                                          std::max<int64_t>(1, (int64_t)ctx->sm_count * 8 / n_tiles));
+    center_convert_kernel<false, false, true><<<dim3(n_tiles, gy), 384, 0, st>>>(
+        const_cast<double*>(d_x), T, ld, N, d_ref, d_p32, n_tiles, nullptr, nullptr);
+    ctx->launches++;
+    WISP_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_center(wisp_ctx* ctx, double* d_x, int64_t T, int64_t ld, int64_t ncols,
-                  const double* d_mean, cudaStream_t st, float* d_p32, int N, const double* d_rot) {
-    if (d_rot && !d_p32) {
+                  const double* d_mean, cudaStream_t st, float* d_p32, int N, const double* d_rot,
+                  bool stats_without_p32) {
+    if (d_rot && !d_p32 && !stats_without_p32) {
         // no fused form without the FP32 copy: rotate in place, then centre
         WISP_CHECK(N > 0, "center: the node count is needed to rotate");
         WISP_TRY(launch_align_nodes(ctx, d_x, ld, N, T, d_rot, st));
     }
-    if (d_p32) {
+    if (d_p32 || stats_without_p32) {
+        WISP_CHECK(N > 0, "center: the node count is needed for the fused centring pass");
         const int n_tiles = (int)(round_up(N, kTile) / kTile);
         const int gy = (int)std::min<int64_t>((T + kCcFrames - 1) / kCcFrames,
                                               std::max<int64_t>(1, (int64_t)ctx->sm_count * 8 / n_tiles));
@@ -290,12 +314,15 @@ int launch_center(wisp_ctx* ctx, double* d_x, int64_t T, int64_t ld, int64_t nco
         // here instead of reading X once more, if the next wisp_dev_gram is on this very block
         void* p_stat = nullptr;
         WISP_TRY(wisp_scratch(ctx, SCR_I8_STATS, (size_t)parts * 2 * 3 * kTile * n_tiles * 8, &p_stat));
-        if (d_rot)
-            center_convert_kernel<true><<<dim3(n_tiles, gy), 384, 0, st>>>(d_x, T, ld, N, d_mean, d_p32, n_tiles,
-                                                                           (double*)p_stat, d_rot);
-        else
-            center_convert_kernel<false><<<dim3(n_tiles, gy), 384, 0, st>>>(d_x, T, ld, N, d_mean, d_p32, n_tiles,
-                                                                            (double*)p_stat, nullptr);
+        const dim3 grid(n_tiles, gy);
+        double* ps = (double*)p_stat;
+        if (d_p32) {
+            if (d_rot) center_convert_kernel<true, true, true><<<grid, 384, 0, st>>>(d_x, T, ld, N, d_mean, d_p32, n_tiles, ps, d_rot);
+            else center_convert_kernel<false, true, true><<<grid, 384, 0, st>>>(d_x, T, ld, N, d_mean, d_p32, n_tiles, ps, nullptr);
+        } else {
+            if (d_rot) center_convert_kernel<true, true, false><<<grid, 384, 0, st>>>(d_x, T, ld, N, d_mean, nullptr, n_tiles, ps, d_rot);
+            else center_convert_kernel<false, true, false><<<grid, 384, 0, st>>>(d_x, T, ld, N, d_mean, nullptr, n_tiles, ps, nullptr);
+        }
         ctx->launches++;
         WISP_CUDA(cudaGetLastError());
         ctx->i8_stats_x = d_x;

@@ -303,7 +303,8 @@ __constant__ int kDiagSubCol[16] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3, 0, 0, 1, 0, 1,
 template <int UNROLL>
 __global__ void __launch_bounds__(kWsThreads, 1)
 contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const double* __restrict__ mean,
-                      int n_tiles, int n_seg, double* __restrict__ out, int64_t out_ld, int allow_idle) {
+                      int n_tiles, int n_seg, double* __restrict__ out, int64_t out_ld, int allow_idle,
+                      int accumulate) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ContactWsSmem& sm = *reinterpret_cast<ContactWsSmem*>(smem_raw);
 
@@ -478,7 +479,9 @@ contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
     }
 
     // idle threads store the zeros their totals were initialised with: the partial tile is always
-    // completely defined
+    // completely defined.  accumulate: the tile already holds the sums of earlier frame blocks (every
+    // entry belongs to exactly one thread and the launches are stream-ordered: plain read-modify-write)
+    if (accumulate && idle) return;
     double* o = out + (size_t)seg * out_ld * out_ld;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
@@ -486,10 +489,14 @@ contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
         const int64_t col0 = (int64_t)kTile * bj + jb0;
         double* p = o + row * out_ld + col0;
         const int pb = a * 2 * JH;
-        *reinterpret_cast<double2*>(p) =
-            make_double2(sm.tot[(pb + 0) * kWsComputeThreads + tid], sm.tot[(pb + 1) * kWsComputeThreads + tid]);
-        *reinterpret_cast<double2*>(p + 2) =
-            make_double2(sm.tot[(pb + 2) * kWsComputeThreads + tid], sm.tot[(pb + 3) * kWsComputeThreads + tid]);
+        double2 v0 = make_double2(sm.tot[(pb + 0) * kWsComputeThreads + tid], sm.tot[(pb + 1) * kWsComputeThreads + tid]);
+        double2 v1 = make_double2(sm.tot[(pb + 2) * kWsComputeThreads + tid], sm.tot[(pb + 3) * kWsComputeThreads + tid]);
+        if (accumulate) {
+            const double2 o0 = *reinterpret_cast<const double2*>(p), o1 = *reinterpret_cast<const double2*>(p + 2);
+            v0.x += o0.x; v0.y += o0.y; v1.x += o1.x; v1.y += o1.y;
+        }
+        *reinterpret_cast<double2*>(p) = v0;
+        *reinterpret_cast<double2*>(p + 2) = v1;
     }
 }
 
@@ -729,13 +736,14 @@ contact_sum_wn_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
 }  // namespace
 
 int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, const double* d_mean,
-                       double* d_out, cudaStream_t st) {
+                       double* d_out, cudaStream_t st, bool accumulate) {
     WISP_CHECK(T > 0 && N > 0, "contact: empty input (T=%lld, N=%d)", (long long)T, N);
     const int64_t n_pad = round_up(N, kTile);
     const int n_tiles = (int)(n_pad / kTile);
     const int n_items = n_tiles * (n_tiles + 1) / 2;
     const int chunks_total = (int)((T + kFC - 1) / kFC);
-    const int n_seg = wisp_pick_segments(n_items, chunks_total, ctx->sm_count, 16);
+    // accumulate: one segment per tile, the tile of d_out is the accumulator
+    const int n_seg = accumulate ? 1 : wisp_pick_segments(n_items, chunks_total, ctx->sm_count, 16);
     double* part = d_out;
     if (n_seg > 1) {
         void* p = nullptr;
@@ -744,7 +752,8 @@ int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, cons
     }
     const int smem = (int)sizeof(ContactSmem);
     dim3 grid(n_items, n_seg);
-    static const int variant = getenv("WISP_K3_VARIANT") ? atoi(getenv("WISP_K3_VARIANT")) : 58;
+    static const int variant_env = getenv("WISP_K3_VARIANT") ? atoi(getenv("WISP_K3_VARIANT")) : 58;
+    const int variant = accumulate ? 58 : variant_env;      // only the production kernel accumulates
     const int allow_idle = getenv("WISP_K3_NOIDLE") ? 0 : 1;      // experiment switch: every warp computes its block
 #define WISP_K3_LAUNCH(JH_, UN_)                                                                          \
     do {                                                                                                  \
@@ -765,7 +774,7 @@ int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, cons
         WISP_CUDA(cudaFuncSetAttribute(contact_sum_ws_kernel<UN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        smem_ws));                                                               \
         contact_sum_ws_kernel<UN_><<<grid, kWsThreads, smem_ws, st>>>(d_p32, T, N, d_mean, n_tiles, n_seg, part, \
-                                                                      n_pad, allow_idle);                       \
+                                                                      n_pad, allow_idle, accumulate ? 1 : 0);   \
     } while (0)
         if (variant == 51) WISP_K3_WS(1);      // frame loop not unrolled: 30.1 ms at C2 with 8-frame stages
         else WISP_K3_WS(8);                    // 58 (default)

@@ -546,7 +546,10 @@ fw_resolve_kernel(const T* __restrict__ dist, const T* __restrict__ distT, const
                     if (c < best && k != i && k != j) { best = c; best_k = k; }
                 }
             }
-            done = done || (__ballot_sync(0xffffffffu, best_k >= 0 && best <= dij) & gmask) != 0;
+            // every lane of the warp takes part in the vote, finished groups included (`done || ballot`
+            // would let them skip it by short-circuit evaluation and leave the others waiting forever)
+            const unsigned hit = __ballot_sync(0xffffffffu, best_k >= 0 && best <= dij);
+            done = done || (hit & gmask) != 0;
         }
         // argmin over the 8 lanes of the group (ties: smaller k); executed by every lane of the warp
 #pragma unroll

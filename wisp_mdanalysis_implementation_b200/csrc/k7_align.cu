@@ -40,10 +40,12 @@ namespace {
 
 constexpr int kAlThreads = 256;
 
-// rot [T][9]: this iteration's rotation; rot_total [T][9] (may be NULL): compose != 0 ? R * rot_total : R
+// rot [T][9]: this iteration's rotation; rot_total [T][9] (may be NULL): compose != 0 ? R * rot_total : R.
+// gate (may be NULL): device flag set by align_update_kernel once the residual is below the threshold.
 __global__ void __launch_bounds__(kAlThreads)
 align_solve_kernel(const float* __restrict__ align, int n_align, const double* __restrict__ avg_align, int64_t T,
-                   double* __restrict__ rot, double* __restrict__ rot_total, int compose) {
+                   double* __restrict__ rot, double* __restrict__ rot_total, int compose, const int* __restrict__ gate) {
+    if (gate && *gate) return;          // the loop has converged: a speculatively launched iteration is a no-op
     const int lane = threadIdx.x & 31;
     const int64_t f = (int64_t)blockIdx.x * (kAlThreads / 32) + (threadIdx.x >> 5);
     if (f >= T) return;
@@ -51,13 +53,28 @@ align_solve_kernel(const float* __restrict__ align, int n_align, const double* _
     double s[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) s[k] = 0.0;
-#pragma unroll 2
-    for (int i = lane; i < n_align; i += 32) {
-        const double ax = fa[3 * i], ay = fa[3 * i + 1], az = fa[3 * i + 2];
+    auto acc = [&](double ax, double ay, double az, int i) {
         const double bx = __ldg(avg_align + 3 * i), by = __ldg(avg_align + 3 * i + 1), bz = __ldg(avg_align + 3 * i + 2);
         s[0] += ax * bx; s[1] += ax * by; s[2] += ax * bz;
         s[3] += ay * bx; s[4] += ay * by; s[5] += ay * bz;
         s[6] += az * bx; s[7] += az * by; s[8] += az * bz;
+    };
+    if ((n_align & 3) == 0 && (reinterpret_cast<size_t>(align) & 15) == 0) {
+        // every frame starts on a 16-byte boundary: a lane takes four consecutive landmarks (48 bytes) as
+        // three 16-byte loads, two such groups in flight -- the pass is a pure stream of the landmark array
+        const float4* fv = reinterpret_cast<const float4*>(fa);
+        const int groups = n_align >> 2;
+#pragma unroll 2
+        for (int gI = lane; gI < groups; gI += 32) {
+            const float4 p = __ldg(fv + 3 * gI), q = __ldg(fv + 3 * gI + 1), r = __ldg(fv + 3 * gI + 2);
+            acc(p.x, p.y, p.z, 4 * gI);
+            acc(p.w, q.x, q.y, 4 * gI + 1);
+            acc(q.z, q.w, r.x, 4 * gI + 2);
+            acc(r.y, r.z, r.w, 4 * gI + 3);
+        }
+    } else {
+#pragma unroll 4
+        for (int i = lane; i < n_align; i += 32) acc(fa[3 * i], fa[3 * i + 1], fa[3 * i + 2], i);
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k)
@@ -176,8 +193,9 @@ template <bool NODE_WRITE, bool SUMS>
 __global__ void __launch_bounds__(kApplyWarps * 32)
 align_apply_kernel(float* __restrict__ align, int n_align, double* __restrict__ nodes, int64_t ld, int N,
                    int64_t T, const double* __restrict__ rot, const double* __restrict__ rot_nodes,
-                   int64_t frames_per_seg, double* __restrict__ part) {
+                   int64_t frames_per_seg, double* __restrict__ part, const int* __restrict__ gate) {
     __shared__ __align__(16) double smd[kApplyWarps][kApplyFrames][96];
+    if (gate && *gate) return;
     const int w = threadIdx.x >> 5;
     const int gl = align ? (n_align + 31) / 32 : 0;
     const int gn = (N + 31) / 32;
@@ -197,25 +215,26 @@ align_apply_kernel(float* __restrict__ align, int n_align, double* __restrict__ 
 // `inout` holds the running float32 totals of all EARLIER frames on entry (zeros for the first frame
 // block) and the totals including this block on exit (doubles holding floats): frame shards chain
 // their blocks in frame order and reproduce the single sequential sum bit for bit.
-// The add chain of a column is inherently serial, the memory traffic is not: a CTA owns 32 columns,
-// all 256 threads stream [256 frames][32 columns] tiles (one 128-byte row per warp load, the next
-// tile's loads in flight while the current one is summed) into shared memory, and warp 0 walks the
-// tile in frame order.  (One thread per column reading global memory directly took 6 ms at C2 for
+// The add chain of a column is inherently serial, the memory traffic is not: a CTA owns 16 columns
+// (375 CTAs at C2: two to three per SM, all resident), all 256 threads stream [512 frames][16 columns]
+// tiles (the next tile's 32 loads per thread in flight while the current one is summed) into shared
+// memory, and the first 16 threads walk the tile in frame order.  (One thread per column reading global memory directly took 6 ms at C2 for
 // 1.2 GB -- latency bound; this form is HBM bound.)
-constexpr int kSeqCols = 32, kSeqFrames = 256, kSeqThreads = 256;
+constexpr int kSeqCols = 16, kSeqFrames = 512, kSeqThreads = 256;
 __global__ void __launch_bounds__(kSeqThreads)
 sum32_sequential_kernel(const float* __restrict__ a, int64_t T, int64_t ncols, double* __restrict__ inout) {
     __shared__ float tile[kSeqFrames][kSeqCols];
-    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    const int64_t c = (int64_t)blockIdx.x * kSeqCols + lane;
+    const int tid = threadIdx.x, cl = tid % kSeqCols, rg = tid / kSeqCols;   // column, row group
+    constexpr int RG = kSeqThreads / kSeqCols;           // rows loaded per step by the CTA
+    constexpr int PER = kSeqFrames / RG;                 // rows of a tile each thread loads
+    const int64_t c = (int64_t)blockIdx.x * kSeqCols + cl;
     const bool ok = c < ncols;
-    float s = (wrp == 0 && ok) ? (float)inout[c] : 0.f;
-    constexpr int PER = kSeqFrames / (kSeqThreads / 32);      // rows of a tile each warp loads
+    float s = (rg == 0 && ok) ? (float)inout[c] : 0.f;
     float r[PER];
     auto load = [&](int64_t f0) {
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
-            const int64_t f = f0 + wrp + (int64_t)k * (kSeqThreads / 32);
+            const int64_t f = f0 + rg + (int64_t)k * RG;
             r[k] = (ok && f < T) ? a[f * ncols + c] : 0.f;
         }
     };
@@ -223,25 +242,28 @@ sum32_sequential_kernel(const float* __restrict__ a, int64_t T, int64_t ncols, d
     for (int64_t f0 = 0; f0 < T; f0 += kSeqFrames) {
         __syncthreads();                                   // the previous tile has been summed
 #pragma unroll
-        for (int k = 0; k < PER; ++k) tile[wrp + k * (kSeqThreads / 32)][lane] = r[k];
+        for (int k = 0; k < PER; ++k) tile[rg + k * RG][cl] = r[k];
         __syncthreads();
-        if (f0 + kSeqFrames < T) load(f0 + kSeqFrames);     // in flight while warp 0 sums this tile
-        if (wrp == 0) {
+        if (f0 + kSeqFrames < T) load(f0 + kSeqFrames);     // in flight while row group 0 sums this tile
+        if (rg == 0) {
             const int nf = (int)min((int64_t)kSeqFrames, T - f0);
 #pragma unroll 8
-            for (int f = 0; f < nf; ++f) s = __fadd_rn(s, tile[f][lane]);
+            for (int f = 0; f < nf; ++f) s = __fadd_rn(s, tile[f][cl]);
         }
     }
-    if (wrp == 0 && ok) inout[c] = (double)s;
+    if (rg == 0 && ok) inout[c] = (double)s;
 }
 
 // new averages and the two RMSDs' squared sums in ONE launch (a frame-sharded caller has just all-reduced
 // `sums`): avg <- sums / T_total in place; res2[0] = sum over landmark columns of (old - new)^2,
 // res2[1] = the same over the node columns.  Single CTA, fixed-order tree -> deterministic.
+// gate (may be NULL): when already set the kernel does nothing; otherwise res2[2] counts the iterations
+// run and the flag is raised once sqrt(res2[0] / n_align) <= threshold (:96).
 __global__ void __launch_bounds__(1024)
 align_update_kernel(const double* __restrict__ sums, double T_total, int64_t na3, int64_t nn3,
-                    double* __restrict__ avg, double* __restrict__ res2) {
+                    double* __restrict__ avg, double* __restrict__ res2, double threshold, int* __restrict__ gate) {
     __shared__ double red[2][32];
+    if (gate && *gate) return;
     double ra = 0.0, rn = 0.0;
     for (int64_t c = threadIdx.x; c < na3 + nn3; c += blockDim.x) {
         const double v = sums[c] / T_total, d = avg[c] - v;
@@ -257,15 +279,22 @@ align_update_kernel(const double* __restrict__ sums, double T_total, int64_t na3
         rn = threadIdx.x < (blockDim.x >> 5) ? red[1][threadIdx.x] : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { ra += __shfl_xor_sync(0xffffffffu, ra, o); rn += __shfl_xor_sync(0xffffffffu, rn, o); }
-        if (threadIdx.x == 0) { res2[0] = ra; res2[1] = rn; }
+        if (threadIdx.x == 0) {
+            res2[0] = ra; res2[1] = rn;
+            if (gate) {
+                res2[2] += 1.0;
+                if (sqrt(ra / (double)(na3 / 3)) <= threshold) *gate = 1;
+            }
+        }
     }
 }
 
 }  // namespace
 
 int launch_align_update(wisp_ctx* ctx, const double* d_sums, int64_t T_total, int n_align, int N, double* d_avg,
-                        double* d_res2, cudaStream_t st) {
-    align_update_kernel<<<1, 1024, 0, st>>>(d_sums, (double)T_total, 3 * (int64_t)n_align, 3 * (int64_t)N, d_avg, d_res2);
+                        double* d_res2, cudaStream_t st, double threshold, int* d_gate) {
+    align_update_kernel<<<1, 1024, 0, st>>>(d_sums, (double)T_total, 3 * (int64_t)n_align, 3 * (int64_t)N, d_avg, d_res2,
+                                            threshold, d_gate);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
     return 0;
@@ -304,9 +333,9 @@ int apply_segments(wisp_ctx* ctx, int groups, int64_t T, int64_t* per_out) {
 }
 
 int launch_solve(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_avg_align, int64_t T,
-                 double* d_rot, double* d_rot_total, bool compose, cudaStream_t st) {
+                 double* d_rot, double* d_rot_total, bool compose, cudaStream_t st, const int* d_gate = nullptr) {
     align_solve_kernel<<<(unsigned)((T + kAlThreads / 32 - 1) / (kAlThreads / 32)), kAlThreads, 0, st>>>(
-        d_align, n_align, d_avg_align, T, d_rot, d_rot_total, compose ? 1 : 0);
+        d_align, n_align, d_avg_align, T, d_rot, d_rot_total, compose ? 1 : 0, d_gate);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
     return 0;
@@ -318,12 +347,15 @@ int launch_solve(wisp_ctx* ctx, const float* d_align, int n_align, const double*
 // rotated onto d_avg_align in place, d_rot_total [T][9] <- R (first) or R d_rot_total, and d_sums
 // [3 n_align + 3 N] (may be NULL) receives the column sums of the rotated landmarks, then of
 // d_rot_total applied to the (unchanged) nodes.
+// d_gate (may be NULL): device flag; when set, every kernel of the iteration is a no-op (a caller that
+// launches iteration k + 1 before it has seen the residual of iteration k, see FramePipeline.align).
 int launch_align_iter(wisp_ctx* ctx, float* d_align, int n_align, const double* d_avg_align, const double* d_nodes,
-                      int64_t ld, int N, int64_t T, double* d_rot_total, bool first, cudaStream_t st, double* d_sums) {
+                      int64_t ld, int N, int64_t T, double* d_rot_total, bool first, cudaStream_t st, double* d_sums,
+                      const int* d_gate) {
     void *pr = nullptr, *pp = nullptr;
     WISP_TRY(wisp_scratch(ctx, SCR_ALIGN_ROT, (size_t)T * 9 * 8, &pr));
     double* d_rot = (double*)pr;
-    WISP_TRY(launch_solve(ctx, d_align, n_align, d_avg_align, T, d_rot, d_rot_total, !first, st));
+    WISP_TRY(launch_solve(ctx, d_align, n_align, d_avg_align, T, d_rot, d_rot_total, !first, st, d_gate));
     const int groups = (n_align + 31) / 32 + (N + 31) / 32;
     int64_t per = 0;
     const int n_seg = apply_segments(ctx, groups, T, &per);
@@ -332,12 +364,12 @@ int launch_align_iter(wisp_ctx* ctx, float* d_align, int n_align, const double* 
     if (d_sums) {
         WISP_TRY(wisp_scratch(ctx, SCR_ALIGN_PART, (size_t)n_seg * ncols * 8, &pp));
         align_apply_kernel<false, true><<<grid, kApplyWarps * 32, 0, st>>>(
-            d_align, n_align, const_cast<double*>(d_nodes), ld, N, T, d_rot, d_rot_total, per, (double*)pp);
+            d_align, n_align, const_cast<double*>(d_nodes), ld, N, T, d_rot, d_rot_total, per, (double*)pp, d_gate);
     } else {
         // nothing to sum: only the landmarks move
         const dim3 grid_l(((n_align + 31) / 32 + kApplyWarps - 1) / kApplyWarps, n_seg);
         align_apply_kernel<false, false><<<grid_l, kApplyWarps * 32, 0, st>>>(
-            d_align, n_align, nullptr, ld, 0, T, d_rot, d_rot_total, per, nullptr);
+            d_align, n_align, nullptr, ld, 0, T, d_rot, d_rot_total, per, nullptr, d_gate);
     }
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
@@ -353,7 +385,7 @@ int launch_align_nodes(wisp_ctx* ctx, double* d_nodes, int64_t ld, int N, int64_
     int64_t per = 0;
     const int n_seg = apply_segments(ctx, groups, T, &per);
     align_apply_kernel<true, false><<<dim3((groups + kApplyWarps - 1) / kApplyWarps, n_seg), kApplyWarps * 32, 0, st>>>(
-        nullptr, 0, d_nodes, ld, N, T, nullptr, d_rot_total, per, nullptr);
+        nullptr, 0, d_nodes, ld, N, T, nullptr, d_rot_total, per, nullptr, nullptr);
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
     return 0;
@@ -377,10 +409,10 @@ int launch_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double
     if (d_sums) {
         WISP_TRY(wisp_scratch(ctx, SCR_ALIGN_PART, (size_t)n_seg * ncols * 8, &pp));
         align_apply_kernel<true, true><<<grid, kApplyWarps * 32, 0, st>>>(d_align, n_align, d_nodes, ld, N, T, d_rot,
-                                                                        d_rot, per, (double*)pp);
+                                                                        d_rot, per, (double*)pp, nullptr);
     } else {
         align_apply_kernel<true, false><<<grid, kApplyWarps * 32, 0, st>>>(d_align, n_align, d_nodes, ld, N, T, d_rot,
-                                                                         d_rot, per, nullptr);
+                                                                         d_rot, per, nullptr, nullptr);
     }
     ctx->launches++;
     WISP_CUDA(cudaGetLastError());
@@ -438,7 +470,7 @@ int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* 
     int iteration = 0;
     double residual = threshold + 9999.0;
     while (residual > threshold && iteration < max_iter) {
-        WISP_TRY(launch_align_iter(ctx, d_align, n_align, d_avgA, d_nodes, ld, N, T, d_rot_total, iteration == 0, st, d_sums));
+        WISP_TRY(launch_align_iter(ctx, d_align, n_align, d_avgA, d_nodes, ld, N, T, d_rot_total, iteration == 0, st, d_sums, nullptr));
         WISP_CUDA(cudaMemcpyAsync(sums.data(), d_sums, (na3 + nn3) * 8, cudaMemcpyDeviceToHost, st));
         WISP_CUDA(cudaStreamSynchronize(st));
         if (reduce) WISP_TRY(reduce(sums.data(), (size_t)(na3 + nn3), false, AlignStep()));

@@ -124,7 +124,26 @@ int shard_body(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
     WISP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const double t_begin = host_ms();
-    // ---- S1: H2D || K1 ----
+    // small device vectors + the partial sums live in this shard's arena
+    void* pw = nullptr;
+    const size_t work_d = (size_t)(2 * round_up(na3, 32) + round_up(nn3, 32)) + 3 * (size_t)ld;
+    WISP_TRY(wisp_scratch(ctx, SCR_MISC1, work_d * 8, &pw));
+    double* d_work = (double*)pw;
+    double* d_ref = d_work + (2 * round_up(na3, 32) + round_up(nn3, 32));
+    double* d_mean = d_ref + 2 * ld;
+    void *pg = nullptr, *pd = nullptr;
+    WISP_TRY(wisp_scratch(ctx, SCR_PIPE_G, (size_t)n_pad * n_pad * 8, &pg));
+    WISP_TRY(wisp_scratch(ctx, SCR_PIPE_D, (size_t)n_pad * n_pad * 8, &pd));
+    double* d_gram = (double*)pg;
+    double* d_dsum = (double*)pd;
+    S.d_gram[r] = d_gram;
+    S.d_dsum[r] = d_dsum;
+    // ---- S1: H2D || K1 || K3 ----
+    // Pair distances do not change under the per-frame rigid motions of the alignment, so K3 -- 60 % of
+    // the device time of a pass -- does not have to wait for K7: every coordinate block goes K1 -> FP32
+    // tile-referenced copy (references = the block-0 positions of the tiles' middle nodes; any fixed point
+    // per tile serves) -> K3, accumulated into the shard's distance sums, while the next block is still
+    // crossing PCIe.  The P block is a few MB and never leaves L2.
     float* d_align = nullptr;
     if (a.max_align_iterations > 0) {
         void* pa = nullptr;
@@ -135,23 +154,19 @@ int shard_body(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
     int64_t ldx = 0;
     wisp_ctx* via = (S.via[r] != r) ? S.ctxs[S.via[r]] : nullptr;
     const double* d_k1_colsum = nullptr;      // node column sums of this shard, out of K1
+    ComChunkHook hook = [&](double* dx, int64_t ldc, int64_t c0, int64_t nt) -> int {
+        if (c0 == 0) {
+            WISP_CUDA(cudaMemsetAsync(d_dsum, 0, (size_t)n_pad * n_pad * 8, st));
+            WISP_CUDA(cudaMemcpyAsync(d_ref, dx, (size_t)ldc * 8, cudaMemcpyDeviceToDevice, st));   // frame 0 of the shard
+        }
+        void* pp = nullptr;
+        WISP_TRY(wisp_scratch(ctx, SCR_P32, (size_t)nt * n_pad * 12, &pp));
+        WISP_TRY(launch_p32_convert(ctx, dx + c0 * ldc, nt, ldc, N, d_ref, (float*)pp, st));
+        return launch_contact_sum(ctx, (const float*)pp, nt, N, d_ref, d_dsum, st, true);
+    };
     WISP_TRY(wisp_com_from_host(ctx, a.coords + (size_t)t0 * a.A * 3, Tl, a.A, a.masses, a.node_ptr, a.atom_idx, N,
-                                a.align_idx, a.n_align, a.atomic, &d_x, &ldx, d_align, via, &d_k1_colsum));
+                                a.align_idx, a.n_align, a.atomic, &d_x, &ldx, d_align, via, &d_k1_colsum, &hook));
     const double t_s1 = host_ms();
-    // small device vectors + the partial sums live in this shard's arena
-    void* pw = nullptr;
-    const size_t work_d = (size_t)(2 * round_up(na3, 32) + round_up(nn3, 32)) + 2 * (size_t)ld;
-    WISP_TRY(wisp_scratch(ctx, SCR_MISC1, work_d * 8, &pw));
-    double* d_work = (double*)pw;
-    double* d_sum = d_work + (2 * round_up(na3, 32) + round_up(nn3, 32));
-    double* d_mean = d_sum + ld;
-    void *pg = nullptr, *pd = nullptr;
-    WISP_TRY(wisp_scratch(ctx, SCR_PIPE_G, (size_t)n_pad * n_pad * 8, &pg));
-    WISP_TRY(wisp_scratch(ctx, SCR_PIPE_D, (size_t)n_pad * n_pad * 8, &pd));
-    double* d_gram = (double*)pg;
-    double* d_dsum = (double*)pd;
-    S.d_gram[r] = d_gram;
-    S.d_dsum[r] = d_dsum;
     // ---- S2: K7 ----
     std::vector<double> mean(nn3);
     bool have_mean = false;
@@ -184,11 +199,9 @@ int shard_body(Shared& S, int r, wisp_ctx* ctx, const PipeArgs& a) {
     if (a.out_nodes)   // un-centred node trajectory, as traj_alignment_and_averaging returns it
         WISP_CUDA(cudaMemcpy2DAsync(a.out_nodes + (size_t)t0 * nn3, (size_t)nn3 * 8, d_x, (size_t)ld * 8, (size_t)nn3 * 8,
                                     (size_t)Tl, cudaMemcpyDeviceToHost, st));
-    void* pp = nullptr;
-    WISP_TRY(wisp_scratch(ctx, SCR_P32, (size_t)Tl * n_pad * 12, &pp));
-    WISP_TRY(launch_center(ctx, d_x, Tl, ld, nn3, d_mean, st, (float*)pp, N, d_rot));
+    // centring (+ the deferred rotation) with the INT8 column statistics, no FP32 copy: K3 is already done
+    WISP_TRY(launch_center(ctx, d_x, Tl, ld, nn3, d_mean, st, nullptr, N, d_rot, true));
     WISP_TRY(launch_gram(ctx, d_x, Tl, ld, N, 3, d_gram, st));
-    WISP_TRY(launch_contact_sum(ctx, (const float*)pp, Tl, N, d_mean, d_dsum, st));
     WISP_CUDA(cudaStreamSynchronize(st));     // `mean` (host) was the source of an async copy; partials complete
     if (r == 0) {
         double* ps = S.root->pipe_stats;
@@ -485,6 +498,7 @@ extern "C" int wisp_ctx_ingest_info(wisp_ctx* ctx, int* via, double* rates) {
 
 // shard 0's host-clock view of the last wisp_pipeline: [0] H2D || K1, [1] K7, [2] centring + K2 + K3,
 // [3] waiting for the slowest shard, [4] fused epilogue + D2H, [5] total (ms), [6] unused, [7] shards
+// ([0] includes K3, which runs block by block under the transfer; [2] is centring + K2)
 extern "C" int wisp_pipeline_stats(wisp_ctx* ctx, double* out8) {
     WISP_CHECK(ctx && out8, "pipeline_stats: null argument");
     memcpy(out8, ctx->pipe_stats, sizeof(ctx->pipe_stats));

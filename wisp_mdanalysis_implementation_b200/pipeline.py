@@ -125,6 +125,7 @@ class FramePipeline:
             self.d_rot_total = torch.empty((self.T, 9), dtype=f64, device=dev)
             self.d_node_sums = torch.zeros(self.ld, dtype=f64, device=dev)
         self._rotation_pending = False
+        self._align_host = None
         self.d_parts = None
         self.k23_stream = torch.cuda.Stream(device=dev)
         n = self.N
@@ -190,22 +191,47 @@ class FramePipeline:
         # one pair of doubles comes back for the loop decision
         d_avg = torch.from_numpy(np.concatenate(((sa / np.float32(self.T_total)).astype(np.float64),
                                                  sn / float(self.T_total)))).to(self.dev)
-        d_res2 = torch.zeros(2, dtype=torch.float64, device=self.dev)
-        self.alignment_log = []
-        residual, it = self.align_threshold + 9999.0, 0
-        while residual > self.align_threshold and it < self.align_iterations:
-            # landmarks rotated in place, nodes only read: their rotation is composed into d_rot_total
+        # The loop decision lives on the device: align_update raises d_gate once the residual is below the
+        # threshold, and every kernel of an iteration is a no-op while it is set.  The host therefore
+        # launches iteration k + 1 BEFORE it has seen the residual of iteration k (one iteration of
+        # look-ahead: the GPU never waits for the 24-byte D2H + the launch latency); when iteration k
+        # turns out to be the last one, the already queued iteration k + 1 costs four empty launches.
+        # Every rank derives the flag from the same all-reduced sums, so the ranks stay in step.
+        d_res3 = torch.zeros(3, dtype=torch.float64, device=self.dev)
+        d_gate = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        max_it = self.align_iterations
+        if self._align_host is None or self._align_host.shape[0] < max_it:
+            self._align_host = torch.empty((max_it, 3), dtype=torch.float64).pin_memory()
+        h_res, events = self._align_host, []
+
+        def launch(k):
             self.ctx.dev_align_iter(self.d_align.data_ptr(), self.n_align, d_avg.data_ptr(),
-                                    self.d_x.data_ptr(), self.T, self.N, self.d_rot_total.data_ptr(), it == 0,
-                                    d_sums=self.d_align_sums.data_ptr(), stream=s)
+                                    self.d_x.data_ptr(), self.T, self.N, self.d_rot_total.data_ptr(), k == 0,
+                                    d_sums=self.d_align_sums.data_ptr(), d_gate=d_gate.data_ptr(), stream=s)
             sharding.reduce_sums(self.d_align_sums, group=self.group)
-            self.ctx.dev_align_update(self.d_align_sums.data_ptr(), self.T_total, self.n_align, self.N,
-                                      d_avg.data_ptr(), d_res2.data_ptr(), stream=s)
-            r2 = d_res2.cpu()
+            self.ctx.dev_align_update_gated(self.d_align_sums.data_ptr(), self.T_total, self.n_align, self.N,
+                                            d_avg.data_ptr(), d_res3.data_ptr(), self.align_threshold,
+                                            d_gate.data_ptr(), stream=s)
+            h_res[k].copy_(d_res3, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.dev))
+            events.append(ev)
+
+        self.alignment_log = []
+        it = 0
+        if max_it > 0:
+            launch(0)
+        while it < max_it:
+            if it + 1 < max_it:
+                launch(it + 1)                      # speculative: gated off on the device if `it` converges
+            events[it].synchronize()
+            r2 = h_res[it]
             residual = float(np.sqrt(float(r2[0]) / self.n_align))
             node_rmsd = float(np.sqrt(float(r2[1]) / self.N))
             it += 1
             self.alignment_log.append((it, residual, node_rmsd))
+            if not residual > self.align_threshold:
+                break
         self._rotation_pending = it > 0
         self.d_mean.zero_()
         self.d_mean[:nn3].copy_(d_avg[na3:])
