@@ -418,8 +418,10 @@ def test_frame_pipeline_matches_c_abi_pipeline(ctx):
     pipe.run_device(d_coords)
     torch.cuda.synchronize()
     np.testing.assert_allclose(pipe.d_corr.cpu().numpy(), ref["corr"], rtol=0, atol=1e-13)
-    np.testing.assert_allclose(pipe.d_avgdist.cpu().numpy(), ref["avgdist"], rtol=1e-12)
-    assert np.array_equal(pipe.d_binary.cpu().numpy(), ref["binary"])
+    # wisp_pipeline runs K3 block by block under the transfer (tile references = the first frame's positions,
+    # FP32 sums promoted per block); the resident pass references the tiles to the mean: FP32-level agreement
+    np.testing.assert_allclose(pipe.d_avgdist.cpu().numpy(), ref["avgdist"], rtol=1e-6)
+    assert_binary_equal_outside_ties(pipe.d_binary.cpu().numpy(), ref["avgdist"], 13.0, ref["binary"])
     h = torch.from_numpy(coords).pin_memory()
     out = pipe.run_host(h)
     np.testing.assert_allclose(out["corr"], ref["corr"], rtol=0, atol=1e-13)
@@ -429,7 +431,7 @@ def test_frame_pipeline_matches_c_abi_pipeline(ctx):
     assert_corr_close(out["corr"], ref["corr"], rel=1e-9, floor=1e-3)
     assert np.all(np.diagonal(out["corr"]) == 1.0)
     np.testing.assert_allclose(out["avgdist"], ref["avgdist"], rtol=1e-6)
-    assert np.array_equal(out["binary"], ref["binary"])
+    assert_binary_equal_outside_ties(out["binary"], ref["avgdist"], 13.0, ref["binary"])
     np.testing.assert_allclose(pipe.d_mean.cpu().numpy()[:900], ref["avg"].reshape(-1), rtol=0, atol=1e-11)
 
 

@@ -63,6 +63,7 @@ extern "C" void wisp_ctx_destroy(wisp_ctx* ctx) {
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->relay_stream) cudaStreamDestroy(ctx->relay_stream);      // (lives on the relaying GPU; the handle is process-wide)
     for (auto& e : ctx->aux_events) if (e) cudaEventDestroy(e);
+    if (ctx->align_host) cudaFreeHost(ctx->align_host);
     delete ctx;
 }
 

@@ -74,6 +74,8 @@ struct wisp_ctx {
     std::vector<int> ingest_via;             // (root) shard -> shard whose PCIe link carries its coordinates
     std::vector<double> ingest_probe;        // (root) what the topology probe measured, for reporting
     cudaStream_t relay_stream = nullptr;     // stream on the relaying GPU that feeds this shard
+    double* align_host = nullptr;            // page-locked [align_host_cap][3]: per-iteration K7 residuals
+    int align_host_cap = 0;
     int gram_mode = -1;              // WISP_GRAM_*; -1 = read $WISP_K2_MODE on first use
     // column statistics left by the last centring pass (launch_center) for the INT8 K2 engine:
     // valid for ONE following launch_gram on the same block and stream
@@ -105,7 +107,7 @@ enum ScratchSlot {
     SCR_APSP_D, SCR_APSP_P, SCR_ARENA, SCR_ALIGN, SCR_P32,
     SCR_MISC0, SCR_MISC1, SCR_MISC2, SCR_MISC3, SCR_MISC4, SCR_MISC5, SCR_MISC6, SCR_MISC7,
     SCR_MISC8, SCR_MISC9, SCR_I8_PLANES, SCR_I8_SMALL, SCR_I8_PART, SCR_I8_STATS, SCR_APSP_R, SCR_APSP_T, SCR_APSP_M,
-    SCR_ALIGN_ROT, SCR_ALIGN_ROTTOT, SCR_ALIGN_PART, SCR_COM_COLSUM, SCR_PIPE_G, SCR_PIPE_D, SCR_PIPE_OUT, SCR_PIPE_STAGE0, SCR_PIPE_STAGE_LAST = SCR_PIPE_STAGE0 + 15,
+    SCR_ALIGN_ROT, SCR_ALIGN_ROTTOT, SCR_ALIGN_PART, SCR_ALIGN_AVG, SCR_COM_COLSUM, SCR_PIPE_G, SCR_PIPE_D, SCR_PIPE_OUT, SCR_PIPE_STAGE0, SCR_PIPE_STAGE_LAST = SCR_PIPE_STAGE0 + 15,
     SCR_RELAY0, SCR_RELAY_LAST = SCR_RELAY0 + 15, SCR_COUNT
 };
 static_assert(SCR_COUNT <= 96, "wisp_ctx::scratch is too small for the slot list");

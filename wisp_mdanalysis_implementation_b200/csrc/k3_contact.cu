@@ -501,238 +501,6 @@ contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
 }
 
 
-// ---- norm form of the warp-specialised kernel ----------------------------------------------
-// |x_i - x_j|^2 = |x_i|^2 + |x_j|^2 - 2 x_i . x_j.  The producer warp turns the staged i rows into
-// (-2x, -2y, -2z, |x|^2) and the j rows (after the tile-pair offset) into (x, y, z, |x|^2); a pair-frame is
-// then 1 add + 3 fma + MUFU.SQRT + 1 add = 5 FP32 operations instead of 7, and the loop is bound by the MUFU
-// pipe alone (5 * 32 + 32 + 12 = 204 dispatch cycles per warp-frame against 256 MUFU cycles; the difference
-// form needs 265).  The price is cancellation: the rounding of r^2 is ~3 ulp of |x_i|^2 + |x_j|^2, i.e. a
-// relative error of ~1e-7 (R / d)^2 in one distance for a pair d apart, R from the tile reference --
-// up to ~2e-6 for a close pair at the edge of a 128-node tile, the size of the error the reference's own
-// float32 distance_array makes on absolute coordinates.  It is unbiased and averages with sqrt(frames), so
-// the MEAN distance is good to ~1e-8 from a few thousand frames up; launch_contact_sum therefore takes this
-// form only for long frame blocks and a bounded tile radius (contact_norm_gate_kernel), the difference form
-// otherwise.  sqrt takes |r^2| (free source modifier) so that rounding below zero cannot make a NaN; the
-// i == j entries of diagonal tiles are stored as exact zeros.
-constexpr int kWnFC = 8;                   // frames per stage (4 KB per tile-frame pair row set)
-constexpr int kWnStages = 3;
-constexpr int kWnRow = 4 * kTile;          // floats per staged tile-frame: 4 rows of 128
-
-struct ContactWnSmem {
-    double tot[kTile * kTile];
-    float ring[kWnStages][2][kWnFC][4][kTile];                // [stage][0 = i rows, 1 = j rows][frame][x y z n][node]
-    unsigned long long landed[kWnStages], full[kWnStages], empty[kWnStages];
-};
-
-template <int UNROLL>
-__global__ void __launch_bounds__(kWsThreads, 1)
-contact_sum_wn_kernel(const float* __restrict__ p32, int64_t T, int N, const double* __restrict__ mean,
-                      int n_tiles, int n_seg, double* __restrict__ out, int64_t out_ld, int allow_idle,
-                      const int* __restrict__ gate, int gate_want) {
-    if (gate && *gate != gate_want) return;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    ContactWnSmem& sm = *reinterpret_cast<ContactWnSmem*>(smem_raw);
-
-    int bi = 0, rem = blockIdx.x;
-    while (rem >= n_tiles - bi) { rem -= n_tiles - bi; ++bi; }
-    const int bj = bi + rem;
-    const int seg = blockIdx.y;
-    const int64_t f_begin = T * seg / n_seg;
-    const int64_t f_end = T * (seg + 1) / n_seg;
-    const int n_chunks = (int)((f_end - f_begin + kWnFC - 1) / kWnFC);
-    const int tid = threadIdx.x;
-
-    if (tid == 0) {
-        for (int s = 0; s < kWnStages; ++s) {
-            ws_mbar_init(&sm.landed[s], 1);
-            ws_mbar_init(&sm.full[s], 1);
-            ws_mbar_init(&sm.empty[s], kWsComputeThreads / 32);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (tid < kWsComputeThreads) {
-#pragma unroll
-        for (int p = 0; p < 32; ++p) sm.tot[p * kWsComputeThreads + tid] = 0.0;
-    }
-    __syncthreads();
-
-    if (tid >= kWsComputeThreads) {
-        // ---------------- producer warp ----------------
-        const int lane = tid & 31;
-        int ri = kTile * bi + kTile / 2, rj = kTile * bj + kTile / 2;
-        if (ri > N - 1) ri = N - 1;
-        if (rj > N - 1) rj = N - 1;
-        float roff[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) roff[c] = (float)(mean[3 * rj + c] - mean[3 * ri + c]);
-        for (int ch = 0; ch < n_chunks; ++ch) {
-            const int slot = ch % kWnStages;
-            const uint32_t ph = (uint32_t)((ch / kWnStages) & 1);
-            const int64_t f0 = f_begin + (int64_t)ch * kWnFC;
-            const int nf = (int)((f_end - f0) < kWnFC ? (f_end - f0) : kWnFC);
-            ws_mbar_wait(&sm.empty[slot], ph ^ 1);
-            if (lane == 0) {
-                ws_mbar_expect_tx(&sm.landed[slot], (uint32_t)nf * 2u * kTileFloats * 4u);
-                for (int fl = 0; fl < nf; ++fl) {
-                    const float* row = p32 + (f0 + fl) * (int64_t)n_tiles * kTileFloats;
-                    ws_bulk_g2s(&sm.ring[slot][0][fl][0][0], row + (int64_t)bi * kTileFloats, kTileFloats * 4, &sm.landed[slot]);
-                    ws_bulk_g2s(&sm.ring[slot][1][fl][0][0], row + (int64_t)bj * kTileFloats, kTileFloats * 4, &sm.landed[slot]);
-                }
-            }
-            ws_mbar_wait(&sm.landed[slot], ph);
-            float4* qi = reinterpret_cast<float4*>(&sm.ring[slot][0][0][0][0]);
-            float4* qj = reinterpret_cast<float4*>(&sm.ring[slot][1][0][0][0]);
-            for (int fl = 0; fl < nf; ++fl) {
-                // a lane owns nodes 4 lane .. 4 lane + 3 of both tiles; 128 float4 per staged tile-frame
-                float4 x = qi[fl * 128 + lane], y = qi[fl * 128 + 32 + lane], z = qi[fl * 128 + 64 + lane];
-                float4 n;
-                n.x = fmaf(z.x, z.x, fmaf(y.x, y.x, x.x * x.x));
-                n.y = fmaf(z.y, z.y, fmaf(y.y, y.y, x.y * x.y));
-                n.z = fmaf(z.z, z.z, fmaf(y.z, y.z, x.z * x.z));
-                n.w = fmaf(z.w, z.w, fmaf(y.w, y.w, x.w * x.w));
-                x.x *= -2.f; x.y *= -2.f; x.z *= -2.f; x.w *= -2.f;
-                y.x *= -2.f; y.y *= -2.f; y.z *= -2.f; y.w *= -2.f;
-                z.x *= -2.f; z.y *= -2.f; z.z *= -2.f; z.w *= -2.f;
-                qi[fl * 128 + lane] = x; qi[fl * 128 + 32 + lane] = y; qi[fl * 128 + 64 + lane] = z;
-                qi[fl * 128 + 96 + lane] = n;
-                // x_i - x_j = a_i - (b_j + (ref_J - ref_I)): shift the j rows once
-                x = qj[fl * 128 + lane]; y = qj[fl * 128 + 32 + lane]; z = qj[fl * 128 + 64 + lane];
-                x.x += roff[0]; x.y += roff[0]; x.z += roff[0]; x.w += roff[0];
-                y.x += roff[1]; y.y += roff[1]; y.z += roff[1]; y.w += roff[1];
-                z.x += roff[2]; z.y += roff[2]; z.z += roff[2]; z.w += roff[2];
-                n.x = fmaf(z.x, z.x, fmaf(y.x, y.x, x.x * x.x));
-                n.y = fmaf(z.y, z.y, fmaf(y.y, y.y, x.y * x.y));
-                n.z = fmaf(z.z, z.z, fmaf(y.z, y.z, x.z * x.z));
-                n.w = fmaf(z.w, z.w, fmaf(y.w, y.w, x.w * x.w));
-                if (bi != bj) { qj[fl * 128 + lane] = x; qj[fl * 128 + 32 + lane] = y; qj[fl * 128 + 64 + lane] = z; }
-                qj[fl * 128 + 96 + lane] = n;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // before the next TMA write here
-            __syncwarp();
-            if (lane == 0) ws_mbar_arrive(&sm.full[slot]);
-        }
-        return;
-    }
-
-    // ---------------- compute warps (thread -> pair block exactly as in contact_sum_ws_kernel) ----------------
-    constexpr int JH = 2;
-    int ib0, ib1, jb0;
-    bool idle;
-    {
-        const int w = tid >> 5, lane = tid & 31;
-        const int valid_i = min(kTile, N - kTile * bi), valid_j = min(kTile, N - kTile * bj);
-        if (bi == bj) {
-            const int wr = kDiagSubRow[w], wc = kDiagSubCol[w];
-            ib0 = 32 * wr + 8 * (lane >> 3);
-            ib1 = ib0 + 4;
-            jb0 = 32 * wc + 4 * (lane & 7);
-            idle = (w >= 10 || 32 * wr >= valid_i || 32 * wc >= valid_j) && allow_idle;
-        } else {
-            ib0 = 4 * (tid & 15);
-            ib1 = 64 + ib0;
-            jb0 = 4 * (tid >> 4);
-            idle = 8 * w >= valid_j && allow_idle;
-        }
-    }
-    f32x2 acc[8][JH];
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int h = 0; h < JH; ++h) acc[a][h] = pack2(0.f, 0.f);
-
-    for (int ch = 0; ch < n_chunks; ++ch) {
-        const int slot = ch % kWnStages;
-        const uint32_t ph = (uint32_t)((ch / kWnStages) & 1);
-        const int64_t f0 = f_begin + (int64_t)ch * kWnFC;
-        const int nf = (int)((f_end - f0) < kWnFC ? (f_end - f0) : kWnFC);
-        ws_mbar_wait(&sm.full[slot], ph);
-        if (idle) {
-            __syncwarp();
-            if ((tid & 31) == 0) ws_mbar_arrive(&sm.empty[slot]);
-            continue;
-        }
-        const float* si = &sm.ring[slot][0][0][0][0];
-        const float* sj = &sm.ring[slot][1][0][0][0];
-#pragma unroll UNROLL
-        for (int fl = 0; fl < nf; ++fl) {
-            float ax[8], ay[8], az[8], an[8];
-            f32x2 bx[JH], by[JH], bz[JH], bn[JH];
-            {
-                const float* fi = si + fl * kWnRow;
-                const float* fj = sj + fl * kWnRow;
-                const float4 t0 = *reinterpret_cast<const float4*>(fi + ib0);
-                const float4 t1 = *reinterpret_cast<const float4*>(fi + ib1);
-                ax[0] = t0.x; ax[1] = t0.y; ax[2] = t0.z; ax[3] = t0.w;
-                ax[4] = t1.x; ax[5] = t1.y; ax[6] = t1.z; ax[7] = t1.w;
-                const float4 u0 = *reinterpret_cast<const float4*>(fi + kTile + ib0);
-                const float4 u1 = *reinterpret_cast<const float4*>(fi + kTile + ib1);
-                ay[0] = u0.x; ay[1] = u0.y; ay[2] = u0.z; ay[3] = u0.w;
-                ay[4] = u1.x; ay[5] = u1.y; ay[6] = u1.z; ay[7] = u1.w;
-                const float4 v0 = *reinterpret_cast<const float4*>(fi + 2 * kTile + ib0);
-                const float4 v1 = *reinterpret_cast<const float4*>(fi + 2 * kTile + ib1);
-                az[0] = v0.x; az[1] = v0.y; az[2] = v0.z; az[3] = v0.w;
-                az[4] = v1.x; az[5] = v1.y; az[6] = v1.z; az[7] = v1.w;
-                const float4 n0 = *reinterpret_cast<const float4*>(fi + 3 * kTile + ib0);
-                const float4 n1 = *reinterpret_cast<const float4*>(fi + 3 * kTile + ib1);
-                an[0] = n0.x; an[1] = n0.y; an[2] = n0.z; an[3] = n0.w;
-                an[4] = n1.x; an[5] = n1.y; an[6] = n1.z; an[7] = n1.w;
-                const float4 w0 = *reinterpret_cast<const float4*>(fj + jb0);
-                const float4 w1 = *reinterpret_cast<const float4*>(fj + kTile + jb0);
-                const float4 w2 = *reinterpret_cast<const float4*>(fj + 2 * kTile + jb0);
-                const float4 w3 = *reinterpret_cast<const float4*>(fj + 3 * kTile + jb0);
-                bx[0] = pack2(w0.x, w0.y); bx[1] = pack2(w0.z, w0.w);
-                by[0] = pack2(w1.x, w1.y); by[1] = pack2(w1.z, w1.w);
-                bz[0] = pack2(w2.x, w2.y); bz[1] = pack2(w2.z, w2.w);
-                bn[0] = pack2(w3.x, w3.y); bn[1] = pack2(w3.z, w3.w);
-            }
-#pragma unroll
-            for (int a = 0; a < 8; ++a) {
-                const f32x2 axx = pack2(ax[a], ax[a]), ayy = pack2(ay[a], ay[a]), azz = pack2(az[a], az[a]);
-                const f32x2 ann = pack2(an[a], an[a]);
-#pragma unroll
-                for (int h = 0; h < JH; ++h) {
-                    const f32x2 d2 = fma2(azz, bz[h], fma2(ayy, by[h], fma2(axx, bx[h], add2(ann, bn[h]))));
-                    float lo, hi;
-                    unpack2(d2, lo, hi);
-                    acc[a][h] = add2(acc[a][h], pack2(fast_sqrt(fabsf(lo)), fast_sqrt(fabsf(hi))));
-                }
-            }
-        }
-        __syncwarp();
-        if ((tid & 31) == 0) ws_mbar_arrive(&sm.empty[slot]);        // this warp is done with the stage
-        if ((ch % (128 / kWnFC)) == (128 / kWnFC) - 1 || ch == n_chunks - 1) {      // every 128 frames
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-#pragma unroll
-                for (int h = 0; h < JH; ++h) {
-                    float lo, hi;
-                    unpack2(acc[a][h], lo, hi);
-                    sm.tot[(a * 2 * JH + 2 * h) * kWsComputeThreads + tid] += (double)lo;
-                    sm.tot[(a * 2 * JH + 2 * h + 1) * kWsComputeThreads + tid] += (double)hi;
-                    acc[a][h] = pack2(0.f, 0.f);
-                }
-        }
-    }
-
-    double* o = out + (size_t)seg * out_ld * out_ld;
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        const int rl = (a < 4) ? (ib0 + a) : (ib1 + (a - 4));          // row inside the tile
-        const int64_t row = (int64_t)kTile * bi + rl;
-        const int64_t col0 = (int64_t)kTile * bj + jb0;
-        double* p = o + row * out_ld + col0;
-        const int pb = a * 2 * JH;
-        double v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            v[k] = sm.tot[(pb + k) * kWsComputeThreads + tid];
-            if (bi == bj && rl == jb0 + k) v[k] = 0.0;                  // a node and itself: exactly zero
-        }
-        *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
-        *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
-    }
-}
-
 }  // namespace
 
 int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, const double* d_mean,
@@ -762,12 +530,7 @@ int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, cons
         contact_sum_kernel<JH_, UN_><<<grid, 1024 / JH_, smem, st>>>(d_p32, T, N, d_mean, n_tiles, n_seg, \
                                                                      part, n_pad);                        \
     } while (0)
-    if (variant >= 60 && variant < 70) {
-        const int smem_wn = (int)sizeof(ContactWnSmem);
-        WISP_CUDA(cudaFuncSetAttribute(contact_sum_wn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wn));
-        contact_sum_wn_kernel<8><<<grid, kWsThreads, smem_wn, st>>>(d_p32, T, N, d_mean, n_tiles, n_seg, part, n_pad,
-                                                                   allow_idle, nullptr, 0);
-    } else if (variant >= 50 && variant < 60) {
+    if (variant >= 50 && variant < 60) {
         const int smem_ws = (int)sizeof(ContactWsSmem);
 #define WISP_K3_WS(UN_)                                                                                         \
     do {                                                                                                        \

@@ -215,15 +215,17 @@ align_apply_kernel(float* __restrict__ align, int n_align, double* __restrict__ 
 // `inout` holds the running float32 totals of all EARLIER frames on entry (zeros for the first frame
 // block) and the totals including this block on exit (doubles holding floats): frame shards chain
 // their blocks in frame order and reproduce the single sequential sum bit for bit.
-// The add chain of a column is inherently serial, the memory traffic is not: a CTA owns 16 columns
-// (375 CTAs at C2: two to three per SM, all resident), all 256 threads stream [512 frames][16 columns]
-// tiles (the next tile's 32 loads per thread in flight while the current one is summed) into shared
-// memory, and the first 16 threads walk the tile in frame order.  (One thread per column reading global memory directly took 6 ms at C2 for
+// The add chain of a column is inherently serial, the memory traffic is not: a CTA owns 64 columns
+// (256-byte row segments: narrower ones -- 64 and 128 bytes were tried, 0.83 and 0.92 ms at C2 -- leave DRAM
+// fetching a fresh page for every couple of sectors), all 256 threads stream [256 frames][64 columns] tiles
+// (the next tile's 64 loads per thread in flight while the current one is summed) into shared memory, and
+// the first 64 threads walk the tile in frame order.  (One thread per column reading global memory directly took 6 ms at C2 for
 // 1.2 GB -- latency bound; this form is HBM bound.)
-constexpr int kSeqCols = 16, kSeqFrames = 512, kSeqThreads = 256;
+constexpr int kSeqCols = 64, kSeqFrames = 256, kSeqThreads = 256;
 __global__ void __launch_bounds__(kSeqThreads)
 sum32_sequential_kernel(const float* __restrict__ a, int64_t T, int64_t ncols, double* __restrict__ inout) {
-    __shared__ float tile[kSeqFrames][kSeqCols];
+    extern __shared__ __align__(16) float seq_tile_raw[];                     // 64 KB: dynamic
+    float (*tile)[kSeqCols] = reinterpret_cast<float (*)[kSeqCols]>(seq_tile_raw);
     const int tid = threadIdx.x, cl = tid % kSeqCols, rg = tid / kSeqCols;   // column, row group
     constexpr int RG = kSeqThreads / kSeqCols;           // rows loaded per step by the CTA
     constexpr int PER = kSeqFrames / RG;                 // rows of a tile each thread loads
@@ -289,6 +291,15 @@ align_update_kernel(const double* __restrict__ sums, double T_total, int64_t na3
     }
 }
 
+// initial averages from the initial sums (:86-87): landmarks float32(sum) / float32(T) -- the reference's
+// array is float32 --, nodes sum / T; avg [na3 + nn3]
+__global__ void align_init_avg_kernel(const double* __restrict__ sums, double T_total, int64_t na3, int64_t nn3,
+                                      double* __restrict__ avg) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= na3 + nn3) return;
+    avg[c] = c < na3 ? (double)__fdiv_rn((float)sums[c], (float)T_total) : sums[c] / T_total;
+}
+
 }  // namespace
 
 int launch_align_update(wisp_ctx* ctx, const double* d_sums, int64_t T_total, int n_align, int N, double* d_avg,
@@ -311,7 +322,9 @@ int launch_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const do
                       int N, int64_t T, bool first, double* d_sums, cudaStream_t st) {
     const int64_t na3 = 3 * (int64_t)n_align, nn3 = 3 * (int64_t)N;
     if (first) {
-        sum32_sequential_kernel<<<(int)((na3 + kSeqCols - 1) / kSeqCols), kSeqThreads, 0, st>>>(d_align, T, na3, d_sums);
+        const int seq_smem = kSeqFrames * kSeqCols * (int)sizeof(float);
+        WISP_CUDA(cudaFuncSetAttribute(sum32_sequential_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem));
+        sum32_sequential_kernel<<<(int)((na3 + kSeqCols - 1) / kSeqCols), kSeqThreads, seq_smem, st>>>(d_align, T, na3, d_sums);
         ctx->launches++;
         WISP_CUDA(cudaGetLastError());
     } else {
@@ -441,6 +454,64 @@ int run_iterative_alignment(wisp_ctx* ctx, float* d_align, int n_align, double* 
     void* prt = nullptr;
     WISP_TRY(wisp_scratch(ctx, SCR_ALIGN_ROTTOT, (size_t)T * 9 * 8, &prt));
     double* d_rot_total = (double*)prt;
+    if (!reduce) {
+        // ---- one shard: the whole loop stays on the device ----
+        // averages [landmarks || nodes], the two squared residual sums and the convergence flag live in
+        // HBM; per iteration 24 bytes come back for the log, and iteration k + 1 is launched BEFORE the
+        // residual of iteration k has been read (its kernels are no-ops once the flag is up), so the GPU
+        // never waits for the host between iterations.
+        void* pav = nullptr;
+        WISP_TRY(wisp_scratch(ctx, SCR_ALIGN_AVG, (size_t)(na3 + nn3 + 16) * 8, &pav));
+        double* d_avg = (double*)pav;
+        double* d_res3 = d_avg + na3 + nn3;
+        int* d_gate = (int*)(d_res3 + 4);
+        WISP_CUDA(cudaMemsetAsync(d_sums, 0, na3 * 8, st));
+        WISP_CUDA(cudaMemsetAsync(d_res3, 0, 8 * 8, st));
+        WISP_TRY(launch_align_sums(ctx, d_align, n_align, d_node_colsum ? nullptr : d_nodes, ld, N, T, true, d_sums, st));
+        if (d_node_colsum)
+            WISP_CUDA(cudaMemcpyAsync(d_sums + na3, d_node_colsum, nn3 * 8, cudaMemcpyDeviceToDevice, st));
+        align_init_avg_kernel<<<(unsigned)((na3 + nn3 + 255) / 256), 256, 0, st>>>(d_sums, (double)T_total, na3, nn3, d_avg);
+        ctx->launches++;
+        WISP_CUDA(cudaGetLastError());
+        if (ctx->align_host_cap < max_iter + 1) {
+            if (ctx->align_host) cudaFreeHost(ctx->align_host);
+            ctx->align_host = nullptr;
+            WISP_CUDA(cudaHostAlloc((void**)&ctx->align_host, (size_t)(max_iter + 1) * 3 * 8, cudaHostAllocDefault));
+            ctx->align_host_cap = max_iter + 1;
+        }
+        double* h_res = ctx->align_host;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        WISP_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+        WISP_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+        auto launch = [&](int k) -> int {
+            WISP_TRY(launch_align_iter(ctx, d_align, n_align, d_avg, d_nodes, ld, N, T, d_rot_total, k == 0, st, d_sums, d_gate));
+            WISP_TRY(launch_align_update(ctx, d_sums, T_total, n_align, N, d_avg, d_res3, st, threshold, d_gate));
+            WISP_CUDA(cudaMemcpyAsync(h_res + 3 * k, d_res3, 24, cudaMemcpyDeviceToHost, st));
+            WISP_CUDA(cudaEventRecord(ev[k & 1], st));
+            return 0;
+        };
+        int iteration = 0, rc = 0;
+        if (max_iter > 0) rc = launch(0);
+        while (!rc && iteration < max_iter) {
+            if (iteration + 1 < max_iter) rc = launch(iteration + 1);      // speculative
+            if (rc) break;
+            if (cudaEventSynchronize(ev[iteration & 1]) != cudaSuccess) { wisp_set_error("alignment: device error"); rc = 1; break; }
+            const double residual = std::sqrt(h_res[3 * iteration] / n_align);
+            const double analysis = std::sqrt(h_res[3 * iteration + 1] / N);
+            ++iteration;
+            if (log) { log[3 * (iteration - 1)] = iteration; log[3 * (iteration - 1) + 1] = residual; log[3 * (iteration - 1) + 2] = analysis; }
+            if (!(residual > threshold)) break;
+        }
+        cudaEventDestroy(ev[0]);
+        cudaEventDestroy(ev[1]);
+        if (rc) return rc;
+        if (d_rot_out) *d_rot_out = iteration > 0 ? d_rot_total : nullptr;
+        else if (iteration > 0) WISP_TRY(launch_align_nodes(ctx, d_nodes, ld, N, T, d_rot_total, st));
+        if (h_avg_nodes) WISP_CUDA(cudaMemcpyAsync(h_avg_nodes, d_avg + na3, nn3 * 8, cudaMemcpyDeviceToHost, st));
+        WISP_CUDA(cudaStreamSynchronize(st));
+        if (n_iter_out) *n_iter_out = iteration;
+        return 0;
+    }
     std::vector<double> avgA(na3), avgN(nn3), sums(na3 + nn3);
     // initial landmark totals: float32, chained over the shards in frame order (`reduce` with
     // f32_chain = true hands this shard the totals of the earlier shards, runs `step`, and returns the

@@ -184,13 +184,13 @@ class FramePipeline:
         node_sums = self.d_node_sums[:nn3].clone()
         if world > 1:
             torch.distributed.all_reduce(node_sums, group=self.group)
-        sn = node_sums.cpu().numpy()
-        sa = self.d_align_sums[:na3].cpu().numpy().astype(np.float32)
-        # averages stay on the device ([landmarks || nodes], the layout of the sums); per iteration one
-        # kernel turns the all-reduced sums into the new averages and the two squared residual sums, and
-        # one pair of doubles comes back for the loop decision
-        d_avg = torch.from_numpy(np.concatenate(((sa / np.float32(self.T_total)).astype(np.float64),
-                                                 sn / float(self.T_total)))).to(self.dev)
+        # averages stay on the device ([landmarks || nodes], the layout of the sums), formed by device-side
+        # tensor ops: nothing comes back to the host here.  The float32 mean of :86 is a float32 division by
+        # a DEVICE tensor (torch turns a division by a host scalar into a multiplication by its reciprocal,
+        # which rounds differently).
+        t32 = torch.full((1,), float(self.T_total), dtype=torch.float32, device=self.dev)
+        t64 = torch.full((1,), float(self.T_total), dtype=torch.float64, device=self.dev)
+        d_avg = torch.cat(((self.d_align_sums[:na3].to(torch.float32) / t32).to(torch.float64), node_sums / t64))
         # The loop decision lives on the device: align_update raises d_gate once the residual is below the
         # threshold, and every kernel of an iteration is a no-op while it is set.  The host therefore
         # launches iteration k + 1 BEFORE it has seen the residual of iteration k (one iteration of
