@@ -3,12 +3,13 @@
 // Replaces the second half of traj_alignment_and_averaging
 // (trajectory_analysis_functions.py:86-126): up to 100 passes over all frames, each frame
 // needing MDAnalysis' rotation_matrix (QCP) and two numpy dots from Python.
-// One iteration = two kernels:
-//   align_solve_kernel   one WARP per frame: S = sum_i a_i b_i^T over the alignment landmarks (a = this
-//                        frame, b = current average), 9 FP64 sums reduced by shuffles; lane 0 finds the
-//                        optimal proper rotation (align_solve.cuh: Newton on the quartic of Horn's
-//                        quaternion matrix + adjugate column + Rayleigh polish; Jacobi only for degenerate
-//                        spectra), stores R[frame] and composes it into the frame's TOTAL rotation
+// One iteration = three kernels:
+//   align_corr_kernel + align_quat_kernel
+//                        one WARP per frame: S = sum_i a_i b_i^T over the alignment landmarks (a = this
+//                        frame, b = current average), 9 FP64 sums reduced by shuffles; then one THREAD per
+//                        frame finds the optimal proper rotation (align_solve.cuh: Newton on the quartic of
+//                        Horn's quaternion matrix + adjugate column + Rayleigh polish; Jacobi only for
+//                        degenerate spectra), stores R[frame] and composes it into the frame's TOTAL rotation
 //                        R_tot[frame] <- R R_tot[frame];
 //   align_apply_kernel   HBM-bound streaming pass, warp-autonomous (no block barrier anywhere): a warp
 //                        owns 32 landmarks (float32 like the reference's all_pos_Align array, :106) or 32
@@ -40,11 +41,17 @@ namespace {
 
 constexpr int kAlThreads = 256;
 
-// rot [T][9]: this iteration's rotation; rot_total [T][9] (may be NULL): compose != 0 ? R * rot_total : R.
+// Two kernels per solve: the correlation sums are a pure stream of the landmark array and want many light
+// warps in flight; the eigen-solve is ~2 us of dependent FP64 arithmetic per frame on ~100 registers.  In
+// one kernel (one warp per frame, lane 0 solving) the solver's registers cut the occupancy to 16 warps per
+// SM and the stream ran at 3.0 TB/s (0.40 ms per iteration at C2); apart, the stream kernel keeps 40+
+// warps per SM busy and the solve kernel runs one THREAD per frame over all frames at once.
+//   align_corr_kernel   rot[f][0..9) <- S = sum_i a_i b_i^T (row-major), one warp per frame;
+//   align_quat_kernel   rot[f] <- R(S) in place; rot_total[f] (may be NULL) <- compose ? R rot_total[f] : R.
 // gate (may be NULL): device flag set by align_update_kernel once the residual is below the threshold.
 __global__ void __launch_bounds__(kAlThreads)
-align_solve_kernel(const float* __restrict__ align, int n_align, const double* __restrict__ avg_align, int64_t T,
-                   double* __restrict__ rot, double* __restrict__ rot_total, int compose, const int* __restrict__ gate) {
+align_corr_kernel(const float* __restrict__ align, int n_align, const double* __restrict__ avg_align, int64_t T,
+                  double* __restrict__ rot, const int* __restrict__ gate) {
     if (gate && *gate) return;          // the loop has converged: a speculatively launched iteration is a no-op
     const int lane = threadIdx.x & 31;
     const int64_t f = (int64_t)blockIdx.x * (kAlThreads / 32) + (threadIdx.x >> 5);
@@ -80,10 +87,25 @@ align_solve_kernel(const float* __restrict__ align, int n_align, const double* _
     for (int k = 0; k < 9; ++k)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
-    if (lane != 0) return;
-    double R[9];
-    horn_rotation(s, R);
+    if (lane < 9) {
+        double v = s[0];
+#pragma unroll
+        for (int k = 1; k < 9; ++k) v = (lane == k) ? s[k] : v;
+        rot[f * 9 + lane] = v;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+align_quat_kernel(int64_t T, double* __restrict__ rot, double* __restrict__ rot_total, int compose,
+                  const int* __restrict__ gate) {
+    if (gate && *gate) return;
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= T) return;
     double* out = rot + f * 9;
+    double s[9], R[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s[k] = out[k];
+    horn_rotation(s, R);
 #pragma unroll
     for (int k = 0; k < 9; ++k) out[k] = R[k];
     if (rot_total) {
@@ -215,17 +237,98 @@ align_apply_kernel(float* __restrict__ align, int n_align, double* __restrict__ 
 // `inout` holds the running float32 totals of all EARLIER frames on entry (zeros for the first frame
 // block) and the totals including this block on exit (doubles holding floats): frame shards chain
 // their blocks in frame order and reproduce the single sequential sum bit for bit.
-// The add chain of a column is inherently serial, the memory traffic is not: a CTA owns 64 columns
-// (256-byte row segments: narrower ones -- 64 and 128 bytes were tried, 0.83 and 0.92 ms at C2 -- leave DRAM
-// fetching a fresh page for every couple of sectors), all 256 threads stream [256 frames][64 columns] tiles
-// (the next tile's 64 loads per thread in flight while the current one is summed) into shared memory, and
-// the first 64 threads walk the tile in frame order.  (One thread per column reading global memory directly took 6 ms at C2 for
-// 1.2 GB -- latency bound; this form is HBM bound.)
-constexpr int kSeqCols = 64, kSeqFrames = 256, kSeqThreads = 256;
+// The add chain of a column is inherently serial (50,000 dependent FADDs = 0.1 ms), the memory traffic is
+// not -- but register-staged loads never got it flowing: [256 frames][32 columns] tiles with 32 loads per
+// thread in flight 0.92 ms at C2 for 1.2 GB, 16 columns 0.83 ms, 64 columns x 64 loads 1.03 ms (one SM does
+// not keep that many scalar loads outstanding).  sum32_tma_kernel therefore lets the TMA engine do the
+// staging: a CTA owns `cols` columns (chosen so that the CTAs just fill the SMs), a producer warp issues one
+// cp.async.bulk per row segment into a 4-stage ring of [128 rows][cols] tiles (completion on mbarriers, no
+// registers held), and `cols` consumer threads walk each tile in frame order.  It needs 16-byte aligned row
+// segments (3 n_align a multiple of 4); sum32_sequential_kernel is the fallback for any other shape.
+constexpr int kSqStages = 4, kSqRows = 128, kSqColsMax = 64;
+
+__device__ __forceinline__ uint32_t sq_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void sq_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sq_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void sq_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sq_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sq_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sq_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sq_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(sq_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sq_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(sq_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sq_smem_u32(bar)) : "memory");
+}
+
+// block = 32 (producer warp) + 64 (consumers); dynamic smem = kSqStages * kSqRows * cols floats
+__global__ void __launch_bounds__(96)
+sum32_tma_kernel(const float* __restrict__ a, int64_t T, int64_t ncols, int cols, double* __restrict__ inout) {
+    extern __shared__ __align__(128) float sq_ring[];
+    __shared__ uint64_t full[kSqStages], empty[kSqStages];
+    const int tid = threadIdx.x;
+    const int64_t c0 = (int64_t)blockIdx.x * cols;
+    const int nc = (int)min((int64_t)cols, ncols - c0);          // columns of this CTA (a multiple of 4)
+    const int64_t n_tiles = (T + kSqRows - 1) / kSqRows;
+    if (tid == 0) {
+        for (int s = 0; s < kSqStages; ++s) { sq_mbar_init(&full[s], 1); sq_mbar_init(&empty[s], 2); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid < 32) {
+        // ---------------- producer warp ----------------
+        for (int64_t k = 0; k < n_tiles; ++k) {
+            const int slot = (int)(k % kSqStages);
+            const uint32_t ph = (uint32_t)((k / kSqStages) & 1);
+            const int64_t f0 = k * kSqRows;
+            const int nr = (int)min((int64_t)kSqRows, T - f0);
+            sq_mbar_wait(&empty[slot], ph ^ 1);
+            if (tid == 0) sq_mbar_expect_tx(&full[slot], (uint32_t)nr * (uint32_t)nc * 4u);
+            __syncwarp();
+            float* dst = sq_ring + (size_t)slot * kSqRows * cols;
+            for (int r = tid; r < nr; r += 32)
+                sq_bulk_g2s(dst + (size_t)r * cols, a + (f0 + r) * ncols + c0, (uint32_t)nc * 4u, &full[slot]);
+        }
+        return;
+    }
+    // ---------------- consumers: thread = column ----------------
+    const int cl = tid - 32;
+    const bool ok = cl < nc;
+    float s = ok ? (float)inout[c0 + cl] : 0.f;
+    for (int64_t k = 0; k < n_tiles; ++k) {
+        const int slot = (int)(k % kSqStages);
+        const uint32_t ph = (uint32_t)((k / kSqStages) & 1);
+        const int nr = (int)min((int64_t)kSqRows, T - k * kSqRows);
+        sq_mbar_wait(&full[slot], ph);
+        if (ok) {
+            const float* tile = sq_ring + (size_t)slot * kSqRows * cols + cl;
+#pragma unroll 8
+            for (int r = 0; r < nr; ++r) s = __fadd_rn(s, tile[(size_t)r * cols]);
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) sq_mbar_arrive(&empty[slot]);
+    }
+    if (ok) inout[c0 + cl] = (double)s;
+}
+
+// fallback for row segments that are not 16-byte aligned: register-staged [512 frames][16 columns] tiles
+constexpr int kSeqCols = 16, kSeqFrames = 512, kSeqThreads = 256;
 __global__ void __launch_bounds__(kSeqThreads)
 sum32_sequential_kernel(const float* __restrict__ a, int64_t T, int64_t ncols, double* __restrict__ inout) {
-    extern __shared__ __align__(16) float seq_tile_raw[];                     // 64 KB: dynamic
-    float (*tile)[kSeqCols] = reinterpret_cast<float (*)[kSeqCols]>(seq_tile_raw);
+    __shared__ float tile[kSeqFrames][kSeqCols];
     const int tid = threadIdx.x, cl = tid % kSeqCols, rg = tid / kSeqCols;   // column, row group
     constexpr int RG = kSeqThreads / kSeqCols;           // rows loaded per step by the CTA
     constexpr int PER = kSeqFrames / RG;                 // rows of a tile each thread loads
@@ -322,9 +425,16 @@ int launch_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const do
                       int N, int64_t T, bool first, double* d_sums, cudaStream_t st) {
     const int64_t na3 = 3 * (int64_t)n_align, nn3 = 3 * (int64_t)N;
     if (first) {
-        const int seq_smem = kSeqFrames * kSeqCols * (int)sizeof(float);
-        WISP_CUDA(cudaFuncSetAttribute(sum32_sequential_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem));
-        sum32_sequential_kernel<<<(int)((na3 + kSeqCols - 1) / kSeqCols), kSeqThreads, seq_smem, st>>>(d_align, T, na3, d_sums);
+        if ((na3 & 3) == 0 && (reinterpret_cast<size_t>(d_align) & 15) == 0) {
+            // columns per CTA so that the CTAs just fill the SMs (at C2: 6000 columns -> 44 -> 137 CTAs)
+            int cols = (int)round_up((na3 + ctx->sm_count - 1) / ctx->sm_count, 4);
+            cols = std::max(16, std::min(kSqColsMax, cols));
+            const int smem = kSqStages * kSqRows * cols * (int)sizeof(float);
+            WISP_CUDA(cudaFuncSetAttribute(sum32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            sum32_tma_kernel<<<(int)((na3 + cols - 1) / cols), 96, smem, st>>>(d_align, T, na3, cols, d_sums);
+        } else {
+            sum32_sequential_kernel<<<(int)((na3 + kSeqCols - 1) / kSeqCols), kSeqThreads, 0, st>>>(d_align, T, na3, d_sums);
+        }
         ctx->launches++;
         WISP_CUDA(cudaGetLastError());
     } else {
@@ -336,10 +446,19 @@ int launch_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const do
 
 namespace {
 
-// segments of frames so that the apply grid fills the machine about six CTAs deep
-int apply_segments(wisp_ctx* ctx, int groups, int64_t T, int64_t* per_out) {
+// Segments of frames so that the apply grid is exactly ONE wave of resident CTAs: every CTA moves the
+// same number of bytes per frame (a landmark warp reads and writes 384 bytes, a node warp reads 768), so a
+// grid of 1.5 waves -- what a fixed "six CTAs per SM" gave at C2: 880 CTAs on 592 slots -- leaves half the
+// machine idle for the second half of the kernel (1.33 ms instead of 1.0 ms per iteration).
+template <typename Kernel>
+int apply_segments(wisp_ctx* ctx, Kernel kernel, int groups, int64_t T, int64_t* per_out) {
     const int gx = (groups + kApplyWarps - 1) / kApplyWarps;
-    int n_seg = (int)std::max<int64_t>(1, std::min<int64_t>((T + 63) / 64, (int64_t)ctx->sm_count * 6 / gx));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kApplyWarps * 32, 0) != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        per_sm = 4;
+    }
+    int n_seg = (int)std::max<int64_t>(1, std::min<int64_t>((T + 15) / 16, (int64_t)ctx->sm_count * per_sm / gx));
     const int64_t per = round_up((T + n_seg - 1) / n_seg, kApplyFrames);
     *per_out = per;
     return (int)((T + per - 1) / per);
@@ -347,9 +466,10 @@ int apply_segments(wisp_ctx* ctx, int groups, int64_t T, int64_t* per_out) {
 
 int launch_solve(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_avg_align, int64_t T,
                  double* d_rot, double* d_rot_total, bool compose, cudaStream_t st, const int* d_gate = nullptr) {
-    align_solve_kernel<<<(unsigned)((T + kAlThreads / 32 - 1) / (kAlThreads / 32)), kAlThreads, 0, st>>>(
-        d_align, n_align, d_avg_align, T, d_rot, d_rot_total, compose ? 1 : 0, d_gate);
-    ctx->launches++;
+    align_corr_kernel<<<(unsigned)((T + kAlThreads / 32 - 1) / (kAlThreads / 32)), kAlThreads, 0, st>>>(
+        d_align, n_align, d_avg_align, T, d_rot, d_gate);
+    align_quat_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(T, d_rot, d_rot_total, compose ? 1 : 0, d_gate);
+    ctx->launches += 2;
     WISP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -371,7 +491,8 @@ int launch_align_iter(wisp_ctx* ctx, float* d_align, int n_align, const double* 
     WISP_TRY(launch_solve(ctx, d_align, n_align, d_avg_align, T, d_rot, d_rot_total, !first, st, d_gate));
     const int groups = (n_align + 31) / 32 + (N + 31) / 32;
     int64_t per = 0;
-    const int n_seg = apply_segments(ctx, groups, T, &per);
+    const int n_seg = d_sums ? apply_segments(ctx, align_apply_kernel<false, true>, groups, T, &per)
+                             : apply_segments(ctx, align_apply_kernel<false, false>, (n_align + 31) / 32, T, &per);
     const int64_t ncols = 3 * (int64_t)(n_align + N);
     const dim3 grid((groups + kApplyWarps - 1) / kApplyWarps, n_seg);
     if (d_sums) {
@@ -396,7 +517,7 @@ int launch_align_nodes(wisp_ctx* ctx, double* d_nodes, int64_t ld, int N, int64_
     ctx->i8_stats_x = nullptr;               // the node trajectory is rotated in place
     const int groups = (N + 31) / 32;
     int64_t per = 0;
-    const int n_seg = apply_segments(ctx, groups, T, &per);
+    const int n_seg = apply_segments(ctx, align_apply_kernel<true, false>, groups, T, &per);
     align_apply_kernel<true, false><<<dim3((groups + kApplyWarps - 1) / kApplyWarps, n_seg), kApplyWarps * 32, 0, st>>>(
         nullptr, 0, d_nodes, ld, N, T, nullptr, d_rot_total, per, nullptr, nullptr);
     ctx->launches++;
@@ -416,7 +537,8 @@ int launch_align_rotate(wisp_ctx* ctx, float* d_align, int n_align, const double
     WISP_TRY(launch_solve(ctx, d_align, n_align, d_avg_align, T, d_rot, nullptr, false, st));
     const int groups = (n_align + 31) / 32 + (N + 31) / 32;
     int64_t per = 0;
-    const int n_seg = apply_segments(ctx, groups, T, &per);
+    const int n_seg = d_sums ? apply_segments(ctx, align_apply_kernel<true, true>, groups, T, &per)
+                             : apply_segments(ctx, align_apply_kernel<true, false>, groups, T, &per);
     const int64_t ncols = 3 * (int64_t)(n_align + N);
     const dim3 grid((groups + kApplyWarps - 1) / kApplyWarps, n_seg);
     if (d_sums) {
