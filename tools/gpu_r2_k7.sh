@@ -1,13 +1,10 @@
 #!/bin/bash
-# round 2, second session: the full GPU suite behind per-test timeouts, bench, K5 timings, launch list, ncu --set full
+# round 2, second session: the full GPU suite behind per-test timeouts, bench, launch list
 mkdir -p gpurun_out
 export PYTHONPATH=.
 timeout 700 python -u tools/gpu_tests_resilient.py --per-test 150 --budget 600 2>&1 | tail -3
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --apsp-sharded-nodes 0 > gpurun_out/bench_r2_i.json 2> gpurun_out/bench_r2_i.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_r2_i.err
-timeout 300 python tools/fw_time.py 2000 10000 2>&1 | tail -2 | tee gpurun_out/fw_time7.json
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-paths --apsp-sharded-nodes 0 > gpurun_out/bench_r2_j.json 2> gpurun_out/bench_r2_j.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_r2_j.err
 PASS="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-paths --no-e2e --parity-frames 0 --apsp-sharded-nodes 0"
 timeout 300 $PASS > gpurun_out/plain_pass.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_r2_k7.csv $PASS > gpurun_out/ncu_pass.log 2>&1
 echo "launch list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"contact_sum_ws|com_stream|align_shift|align_apply|align_solve|sum32_seq|gram_i8|center_convert|slice_planes" -c 26 -f -o gpurun_out/prof_r2_pass $PASS > gpurun_out/ncu_full_pass.log 2>&1
-echo "ncu full rc=$?"; ls -la gpurun_out/prof_r2_pass.ncu-rep
