@@ -33,6 +33,8 @@
 #include "common.cuh"
 #include "align_solve.cuh"
 #include <cmath>
+#include <cstdlib>
+#include <cuda.h>
 
 int launch_colsum_f32(wisp_ctx* ctx, const float* d_x, int64_t T, int64_t ld, int64_t ncols,
                       double* d_colsum, cudaStream_t st);
@@ -49,49 +51,66 @@ constexpr int kAlThreads = 256;
 //   align_corr_kernel   rot[f][0..9) <- S = sum_i a_i b_i^T (row-major), one warp per frame;
 //   align_quat_kernel   rot[f] <- R(S) in place; rot_total[f] (may be NULL) <- compose ? R rot_total[f] : R.
 // gate (may be NULL): device flag set by align_update_kernel once the residual is below the threshold.
+// SMEM_B: the reference landmarks live in shared memory, transposed to [12][n_align / 4] so that the lanes
+// of a warp (which own consecutive groups of four landmarks) read consecutive doubles.  Read through L1
+// instead (lane stride 96 bytes) every one of the 12 loads per group touches ~24 cache lines and the L1
+// wavefront rate, not HBM, sets the pace (0.37 ms per iteration at C2 against 0.2 ms for the stream).
+// Persistent CTAs: the 24 n_align bytes are staged once per CTA.
+template <bool SMEM_B>
 __global__ void __launch_bounds__(kAlThreads)
 align_corr_kernel(const float* __restrict__ align, int n_align, const double* __restrict__ avg_align, int64_t T,
                   double* __restrict__ rot, const int* __restrict__ gate) {
+    extern __shared__ __align__(16) double corr_b[];                 // [12][groups] when SMEM_B
     if (gate && *gate) return;          // the loop has converged: a speculatively launched iteration is a no-op
     const int lane = threadIdx.x & 31;
-    const int64_t f = (int64_t)blockIdx.x * (kAlThreads / 32) + (threadIdx.x >> 5);
-    if (f >= T) return;
-    const float* fa = align + f * (int64_t)n_align * 3;
-    double s[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) s[k] = 0.0;
-    auto acc = [&](double ax, double ay, double az, int i) {
-        const double bx = __ldg(avg_align + 3 * i), by = __ldg(avg_align + 3 * i + 1), bz = __ldg(avg_align + 3 * i + 2);
-        s[0] += ax * bx; s[1] += ax * by; s[2] += ax * bz;
-        s[3] += ay * bx; s[4] += ay * by; s[5] += ay * bz;
-        s[6] += az * bx; s[7] += az * by; s[8] += az * bz;
-    };
-    if ((n_align & 3) == 0 && (reinterpret_cast<size_t>(align) & 15) == 0) {
-        // every frame starts on a 16-byte boundary: a lane takes four consecutive landmarks (48 bytes) as
-        // three 16-byte loads, two such groups in flight -- the pass is a pure stream of the landmark array
-        const float4* fv = reinterpret_cast<const float4*>(fa);
-        const int groups = n_align >> 2;
-#pragma unroll 2
-        for (int gI = lane; gI < groups; gI += 32) {
-            const float4 p = __ldg(fv + 3 * gI), q = __ldg(fv + 3 * gI + 1), r = __ldg(fv + 3 * gI + 2);
-            acc(p.x, p.y, p.z, 4 * gI);
-            acc(p.w, q.x, q.y, 4 * gI + 1);
-            acc(q.z, q.w, r.x, 4 * gI + 2);
-            acc(r.y, r.z, r.w, 4 * gI + 3);
+    const int groups = n_align >> 2;
+    if (SMEM_B) {
+        for (int e = threadIdx.x; e < 3 * n_align; e += kAlThreads) {
+            const int g = e / 12, j = e - 12 * g;
+            corr_b[(size_t)j * groups + g] = avg_align[e];
         }
-    } else {
-#pragma unroll 4
-        for (int i = lane; i < n_align; i += 32) acc(fa[3 * i], fa[3 * i + 1], fa[3 * i + 2], i);
+        __syncthreads();
     }
+    const int64_t f_stride = (int64_t)gridDim.x * (kAlThreads / 32);
+    for (int64_t f = (int64_t)blockIdx.x * (kAlThreads / 32) + (threadIdx.x >> 5); f < T; f += f_stride) {
+        const float* fa = align + f * (int64_t)n_align * 3;
+        double s[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k)
+        for (int k = 0; k < 9; ++k) s[k] = 0.0;
+        auto acc3 = [&](double ax, double ay, double az, double bx, double by, double bz) {
+            s[0] += ax * bx; s[1] += ax * by; s[2] += ax * bz;
+            s[3] += ay * bx; s[4] += ay * by; s[5] += ay * bz;
+            s[6] += az * bx; s[7] += az * by; s[8] += az * bz;
+        };
+        if (SMEM_B) {
+            // every frame starts on a 16-byte boundary: a lane takes four consecutive landmarks (48 bytes) as
+            // three 16-byte loads, two such groups in flight -- the pass is a pure stream of the landmark array
+            const float4* fv = reinterpret_cast<const float4*>(fa);
+#pragma unroll 2
+            for (int gI = lane; gI < groups; gI += 32) {
+                const float4 p = __ldg(fv + 3 * gI), q = __ldg(fv + 3 * gI + 1), r = __ldg(fv + 3 * gI + 2);
+                const double* b = corr_b + gI;
+                acc3(p.x, p.y, p.z, b[0], b[groups], b[2 * (size_t)groups]);
+                acc3(p.w, q.x, q.y, b[3 * (size_t)groups], b[4 * (size_t)groups], b[5 * (size_t)groups]);
+                acc3(q.z, q.w, r.x, b[6 * (size_t)groups], b[7 * (size_t)groups], b[8 * (size_t)groups]);
+                acc3(r.y, r.z, r.w, b[9 * (size_t)groups], b[10 * (size_t)groups], b[11 * (size_t)groups]);
+            }
+        } else {
+#pragma unroll 4
+            for (int i = lane; i < n_align; i += 32)
+                acc3(fa[3 * i], fa[3 * i + 1], fa[3 * i + 2], __ldg(avg_align + 3 * i), __ldg(avg_align + 3 * i + 1),
+                     __ldg(avg_align + 3 * i + 2));
+        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
-    if (lane < 9) {
-        double v = s[0];
+        for (int k = 0; k < 9; ++k)
 #pragma unroll
-        for (int k = 1; k < 9; ++k) v = (lane == k) ? s[k] : v;
-        rot[f * 9 + lane] = v;
+            for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+        if (lane < 9) {
+            double v = s[0];
+#pragma unroll
+            for (int k = 1; k < 9; ++k) v = (lane == k) ? s[k] : v;
+            rot[f * 9 + lane] = v;
+        }
     }
 }
 
@@ -240,12 +259,16 @@ align_apply_kernel(float* __restrict__ align, int n_align, double* __restrict__ 
 // The add chain of a column is inherently serial (50,000 dependent FADDs = 0.1 ms), the memory traffic is
 // not -- but register-staged loads never got it flowing: [256 frames][32 columns] tiles with 32 loads per
 // thread in flight 0.92 ms at C2 for 1.2 GB, 16 columns 0.83 ms, 64 columns x 64 loads 1.03 ms (one SM does
-// not keep that many scalar loads outstanding).  sum32_tma_kernel therefore lets the TMA engine do the
-// staging: a CTA owns `cols` columns (chosen so that the CTAs just fill the SMs), a producer warp issues one
-// cp.async.bulk per row segment into a 4-stage ring of [128 rows][cols] tiles (completion on mbarriers, no
-// registers held), and `cols` consumer threads walk each tile in frame order.  It needs 16-byte aligned row
-// segments (3 n_align a multiple of 4); sum32_sequential_kernel is the fallback for any other shape.
-constexpr int kSqStages = 4, kSqRows = 128, kSqColsMax = 64;
+// not keep that many scalar loads outstanding), and one cp.async.bulk per 176-byte row segment 1.40 ms (the
+// TMA unit starts a copy every ~50 cycles, whatever its size).  sum32_tma_kernel therefore describes the
+// array to the TMA unit as a 2-D tensor and moves a whole [128 rows][48 columns] tile (24 KB) with ONE
+// cp.async.bulk.tensor instruction into a 4-stage ring (completion on mbarriers, no registers held); 48
+// consumer threads walk each tile in frame order; 125 CTAs at C2.  The tensor map needs a 16-byte multiple
+// as row pitch (3 n_align a multiple of 4); sum32_sequential_kernel is the fallback for any other shape.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+constexpr int kSqStages = 4, kSqRows = 128, kSqCols = 48;
 
 __device__ __forceinline__ uint32_t sq_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void sq_mbar_init(uint64_t* bar, uint32_t count) {
@@ -268,20 +291,23 @@ __device__ __forceinline__ void sq_mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n"
         "}\n" ::"r"(sq_smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void sq_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+__device__ __forceinline__ void sq_tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(sq_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sq_smem_u32(bar)) : "memory");
+        "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(sq_smem_u32(dst)), "l"(map), "r"(sq_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
-// block = 32 (producer warp) + 64 (consumers); dynamic smem = kSqStages * kSqRows * cols floats
+// block = 32 (producer warp) + 64 (consumers); dynamic smem = kSqStages * kSqRows * kSqCols floats.
+// tmap: the landmark array as a 2-D tensor {3 n_align columns, T rows}, box {kSqCols, kSqRows}; rows and
+// columns beyond the array are zero-filled by the TMA unit (and never added: the consumers stop at the last
+// real row, threads of columns beyond the array idle), and every box completes the full box byte count.
 __global__ void __launch_bounds__(96)
-sum32_tma_kernel(const float* __restrict__ a, int64_t T, int64_t ncols, int cols, double* __restrict__ inout) {
+sum32_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t T, int64_t ncols, double* __restrict__ inout) {
     extern __shared__ __align__(128) float sq_ring[];
     __shared__ uint64_t full[kSqStages], empty[kSqStages];
     const int tid = threadIdx.x;
-    const int64_t c0 = (int64_t)blockIdx.x * cols;
-    const int nc = (int)min((int64_t)cols, ncols - c0);          // columns of this CTA (a multiple of 4)
+    const int64_t c0 = (int64_t)blockIdx.x * kSqCols;
+    const int nc = (int)min((int64_t)kSqCols, ncols - c0);
     const int64_t n_tiles = (T + kSqRows - 1) / kSqRows;
     if (tid == 0) {
         for (int s = 0; s < kSqStages; ++s) { sq_mbar_init(&full[s], 1); sq_mbar_init(&empty[s], 2); }
@@ -289,18 +315,15 @@ sum32_tma_kernel(const float* __restrict__ a, int64_t T, int64_t ncols, int cols
     }
     __syncthreads();
     if (tid < 32) {
-        // ---------------- producer warp ----------------
-        for (int64_t k = 0; k < n_tiles; ++k) {
-            const int slot = (int)(k % kSqStages);
-            const uint32_t ph = (uint32_t)((k / kSqStages) & 1);
-            const int64_t f0 = k * kSqRows;
-            const int nr = (int)min((int64_t)kSqRows, T - f0);
-            sq_mbar_wait(&empty[slot], ph ^ 1);
-            if (tid == 0) sq_mbar_expect_tx(&full[slot], (uint32_t)nr * (uint32_t)nc * 4u);
-            __syncwarp();
-            float* dst = sq_ring + (size_t)slot * kSqRows * cols;
-            for (int r = tid; r < nr; r += 32)
-                sq_bulk_g2s(dst + (size_t)r * cols, a + (f0 + r) * ncols + c0, (uint32_t)nc * 4u, &full[slot]);
+        // ---------------- producer: one lane, one tensor copy per tile ----------------
+        if (tid == 0) {
+            for (int64_t k = 0; k < n_tiles; ++k) {
+                const int slot = (int)(k % kSqStages);
+                const uint32_t ph = (uint32_t)((k / kSqStages) & 1);
+                sq_mbar_wait(&empty[slot], ph ^ 1);
+                sq_mbar_expect_tx(&full[slot], (uint32_t)(kSqRows * kSqCols * sizeof(float)));
+                sq_tma_load_2d(sq_ring + (size_t)slot * kSqRows * kSqCols, &tmap, (int)c0, (int)(k * kSqRows), &full[slot]);
+            }
         }
         return;
     }
@@ -314,9 +337,9 @@ sum32_tma_kernel(const float* __restrict__ a, int64_t T, int64_t ncols, int cols
         const int nr = (int)min((int64_t)kSqRows, T - k * kSqRows);
         sq_mbar_wait(&full[slot], ph);
         if (ok) {
-            const float* tile = sq_ring + (size_t)slot * kSqRows * cols + cl;
+            const float* tile = sq_ring + (size_t)slot * kSqRows * kSqCols + cl;
 #pragma unroll 8
-            for (int r = 0; r < nr; ++r) s = __fadd_rn(s, tile[(size_t)r * cols]);
+            for (int r = 0; r < nr; ++r) s = __fadd_rn(s, tile[(size_t)r * kSqCols]);
         }
         __syncwarp();
         if ((tid & 31) == 0) sq_mbar_arrive(&empty[slot]);
@@ -425,13 +448,32 @@ int launch_align_sums(wisp_ctx* ctx, const float* d_align, int n_align, const do
                       int N, int64_t T, bool first, double* d_sums, cudaStream_t st) {
     const int64_t na3 = 3 * (int64_t)n_align, nn3 = 3 * (int64_t)N;
     if (first) {
-        if ((na3 & 3) == 0 && (reinterpret_cast<size_t>(d_align) & 15) == 0) {
-            // columns per CTA so that the CTAs just fill the SMs (at C2: 6000 columns -> 44 -> 137 CTAs)
-            int cols = (int)round_up((na3 + ctx->sm_count - 1) / ctx->sm_count, 4);
-            cols = std::max(16, std::min(kSqColsMax, cols));
-            const int smem = kSqStages * kSqRows * cols * (int)sizeof(float);
+        static EncodeTiledFn encode = nullptr;
+        static bool encode_tried = false;
+        if (!encode_tried) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+                qres == cudaDriverEntryPointSuccess) encode = (EncodeTiledFn)fn;
+            (void)cudaGetLastError();
+            encode_tried = true;
+        }
+        CUtensorMap tmap;
+        bool use_tma = encode && (na3 & 3) == 0 && (reinterpret_cast<size_t>(d_align) & 15) == 0 && T < (1ll << 31) &&
+                       getenv("WISP_K7_SUM_SEQ") == nullptr;
+        if (use_tma) {
+            const cuuint64_t dims[2] = {(cuuint64_t)na3, (cuuint64_t)T};
+            const cuuint64_t strides[1] = {(cuuint64_t)na3 * 4};
+            const cuuint32_t box[2] = {(cuuint32_t)kSqCols, (cuuint32_t)kSqRows};
+            const cuuint32_t estr[2] = {1, 1};
+            use_tma = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d_align), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        if (use_tma) {
+            const int smem = kSqStages * kSqRows * kSqCols * (int)sizeof(float);
             WISP_CUDA(cudaFuncSetAttribute(sum32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            sum32_tma_kernel<<<(int)((na3 + cols - 1) / cols), 96, smem, st>>>(d_align, T, na3, cols, d_sums);
+            sum32_tma_kernel<<<(int)((na3 + kSqCols - 1) / kSqCols), 96, smem, st>>>(tmap, T, na3, d_sums);
         } else {
             sum32_sequential_kernel<<<(int)((na3 + kSeqCols - 1) / kSeqCols), kSeqThreads, 0, st>>>(d_align, T, na3, d_sums);
         }
@@ -466,8 +508,21 @@ int apply_segments(wisp_ctx* ctx, Kernel kernel, int groups, int64_t T, int64_t*
 
 int launch_solve(wisp_ctx* ctx, const float* d_align, int n_align, const double* d_avg_align, int64_t T,
                  double* d_rot, double* d_rot_total, bool compose, cudaStream_t st, const int* d_gate = nullptr) {
-    align_corr_kernel<<<(unsigned)((T + kAlThreads / 32 - 1) / (kAlThreads / 32)), kAlThreads, 0, st>>>(
-        d_align, n_align, d_avg_align, T, d_rot, d_gate);
+    const int64_t ctas_all = (T + kAlThreads / 32 - 1) / (kAlThreads / 32);
+    const size_t b_bytes = (size_t)n_align * 24;
+    if ((n_align & 3) == 0 && (reinterpret_cast<size_t>(d_align) & 15) == 0 && b_bytes <= 96 * 1024) {
+        WISP_CUDA(cudaFuncSetAttribute(align_corr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_bytes));
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_corr_kernel<true>, kAlThreads, b_bytes) != cudaSuccess || per_sm < 1) {
+            (void)cudaGetLastError();
+            per_sm = 1;
+        }
+        const unsigned grid = (unsigned)std::min<int64_t>(ctas_all, (int64_t)ctx->sm_count * per_sm);
+        align_corr_kernel<true><<<grid, kAlThreads, b_bytes, st>>>(d_align, n_align, d_avg_align, T, d_rot, d_gate);
+    } else {
+        align_corr_kernel<false><<<(unsigned)std::min<int64_t>(ctas_all, (int64_t)ctx->sm_count * 16), kAlThreads, 0, st>>>(
+            d_align, n_align, d_avg_align, T, d_rot, d_gate);
+    }
     align_quat_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(T, d_rot, d_rot_total, compose ? 1 : 0, d_gate);
     ctx->launches += 2;
     WISP_CUDA(cudaGetLastError());
