@@ -160,24 +160,18 @@ __device__ __forceinline__ void align_apply_warp(T* __restrict__ base, int64_t r
     const int ncol = 3 * min(32, n_items - item0);
     T* col = base + 3 * (int64_t)item0;
     double s[3] = {0.0, 0.0, 0.0};
-    // software pipeline: the loads of step k + 1 are issued before step k is processed, so a warp always
-    // has a step's worth of memory requests in flight (without it the stream stalls for a memory
-    // round trip after every four frames: 4.3 instead of 5+ TB/s at C2)
-    T v[kApplyFrames][3], w[kApplyFrames][3];
-    auto load = [&](int64_t f, T (&dst)[kApplyFrames][3]) {
-        const int nfl = (int)min((int64_t)kApplyFrames, f1 - f);
+    // (issuing the loads of step k + 1 before step k is processed -- a register double buffer -- costs 16
+    // registers, drops the occupancy from 4 to 3 CTAs per SM and was slower: 1.26 instead of 1.11 ms at C2)
+    for (int64_t f = f0; f < f1; f += kApplyFrames) {
+        const int nf = (int)min((int64_t)kApplyFrames, f1 - f);
+        T v[kApplyFrames][3];
 #pragma unroll
         for (int q = 0; q < kApplyFrames; ++q)
 #pragma unroll
             for (int u = 0; u < 3; ++u) {
                 const int c = lane + 32 * u;
-                dst[q][u] = (q < nfl && c < ncol) ? col[(f + q) * row_stride + c] : (T)0;
+                v[q][u] = (q < nf && c < ncol) ? col[(f + q) * row_stride + c] : (T)0;
             }
-    };
-    if (f0 < f1) load(f0, v);
-    for (int64_t f = f0; f < f1; f += kApplyFrames) {
-        const int nf = (int)min((int64_t)kApplyFrames, f1 - f);
-        if (f + kApplyFrames < f1) load(f + kApplyFrames, w);
 #pragma unroll
         for (int q = 0; q < kApplyFrames; ++q)
 #pragma unroll
@@ -220,10 +214,6 @@ __device__ __forceinline__ void align_apply_warp(T* __restrict__ base, int64_t r
         } else {
             __syncwarp();       // every lane has read its triple before the patch is overwritten
         }
-#pragma unroll
-        for (int q = 0; q < kApplyFrames; ++q)
-#pragma unroll
-            for (int u = 0; u < 3; ++u) v[q][u] = w[q][u];
     }
     if (SUMS) {
         if (WRITE) {            // lane owns columns lane, lane + 32, lane + 64 of the span
@@ -243,7 +233,7 @@ __device__ __forceinline__ void align_apply_warp(T* __restrict__ base, int64_t r
 // NODE_WRITE: the nodes are rotated in place by rot_nodes (the old per-iteration behaviour and the final
 // in-place rotation); otherwise they are only read.  align == NULL: nodes only.  part == NULL: no sums.
 template <bool NODE_WRITE, bool SUMS>
-__global__ void __launch_bounds__(kApplyWarps * 32, 3)
+__global__ void __launch_bounds__(kApplyWarps * 32)
 align_apply_kernel(float* __restrict__ align, int n_align, double* __restrict__ nodes, int64_t ld, int N,
                    int64_t T, const double* __restrict__ rot, const double* __restrict__ rot_nodes,
                    int64_t frames_per_seg, double* __restrict__ part, const int* __restrict__ gate) {
