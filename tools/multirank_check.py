@@ -73,7 +73,8 @@ for aligned in (True, False):
         corr, avgdist, binary = pipe.d_corr.cpu().numpy(), pipe.d_avgdist.cpu().numpy(), pipe.d_binary.cpu().numpy()
         e_c = float((np.abs(corr - ref["corr"]) / np.maximum(np.abs(ref["corr"]), 1e-3)).max())
         e_d = float((np.abs(avgdist - ref["avgdist"]) / np.maximum(ref["avgdist"], 1e-9))[~np.eye(N, dtype=bool)].max())
-        mism = int((binary != ref["binary"]).sum())
+        near = np.abs(ref["avgdist"] - cutoff) <= 1e-6 * cutoff      # ties with the cutoff may fall either way
+        mism = int(((binary != ref["binary"]) & ~near).sum())
         ok = all_ok(e_c <= 1e-6 and e_d <= 1e-6 and mism == 0)
         report["%s_aligned_%s" % (name, aligned)] = {"max_rel_corr": e_c, "max_rel_dist": e_d, "topology_mismatches": mism}
         assert ok, (name, aligned, e_c, e_d, mism)
@@ -99,7 +100,8 @@ if rank == 0:
                         which_map=1, maximum_num_iterations=100)
     e_c = float((np.abs(out["corr"] - ref["corr"]) / np.maximum(np.abs(ref["corr"]), 1e-3)).max())
     e_d = float((np.abs(out["avgdist"] - ref["avgdist"]) / np.maximum(ref["avgdist"], 1e-9))[~np.eye(N, dtype=bool)].max())
-    mism = int((out["binary"] != ref["binary"]).sum())
+    near = np.abs(ref["avgdist"] - cutoff) <= 1e-6 * cutoff
+    mism = int(((out["binary"] != ref["binary"]) & ~near).sum())
     report["inprocess_multi_gpu_pipeline"] = {"gpus": mctx.n_gpus, "max_rel_corr": e_c, "max_rel_dist": e_d,
                                               "topology_mismatches": mism}
     assert e_c <= 1e-6 and e_d <= 1e-6 and mism == 0
