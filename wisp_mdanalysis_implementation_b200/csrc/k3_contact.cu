@@ -304,7 +304,7 @@ template <int UNROLL>
 __global__ void __launch_bounds__(kWsThreads, 1)
 contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const double* __restrict__ mean,
                       int n_tiles, int n_seg, double* __restrict__ out, int64_t out_ld, int allow_idle,
-                      int accumulate) {
+                      int accumulate, int balance) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ContactWsSmem& sm = *reinterpret_cast<ContactWsSmem*>(smem_raw);
 
@@ -380,28 +380,72 @@ contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
     // (whose pairs the sub-blocks above it already cover) are idle.  Idle warps only keep the stage
     // hand-shake going; the MUFU pipe of the SM is then shared by fewer warps, so the CTA ends earlier:
     // 8.5 % less K3 time at C2 (16 diagonal tiles x 6/16 + 15 last-column tiles x 48/128).
+    // balance: a tile with A < 16 active blocks leaves the four schedulers unevenly loaded (A = 10: 3, 3, 2, 2
+    // warps -- the CTA takes 3/4 of a full tile's time for 10/16 of its work).  The blocks are therefore dealt
+    // out again: 2A - 16 blocks keep a warp of their own, every other block is SHARED by two consecutive
+    // warps (different schedulers), one taking the even and one the odd frames of every stage; each scheduler
+    // then carries the same number of warps and within half a block the same work (A = 10: 2.5 blocks each).
+    // The two halves meet in the per-thread FP64 totals after the frame loop.
     constexpr int JH = 2;
     int ib0, ib1, jb0;
     bool idle;
-    {
-        const int w = tid >> 5, lane = tid & 31;
-        const int valid_i = min(kTile, N - kTile * bi), valid_j = min(kTile, N - kTile * bj);
+    int fstart = 0, fstep = 1;          // frames of a stage this warp takes
+    bool shared_primary = false, shared_secondary = false;
+    const int w = tid >> 5, lane = tid & 31;
+    const int valid_i = min(kTile, N - kTile * bi), valid_j = min(kTile, N - kTile * bj);
+    auto block_active = [&](int ow) -> bool {        // does the block of (original) warp ow hold real pairs?
+        if (bi == bj) return ow < 10 && 32 * kDiagSubRow[ow] < valid_i && 32 * kDiagSubCol[ow] < valid_j;
+        return 8 * ow < valid_j;
+    };
+    auto block_coords = [&](int ow, int& i0, int& i1, int& j0) {
         if (bi == bj) {
-            // the 10 sub-blocks on or above the diagonal go to warps 0..9, so that the four schedulers
-            // (warp % 4) carry 3, 3, 2, 2 of them; warps 10..15 own the 6 sub-blocks below the diagonal,
-            // stay idle and only store the zeros their totals were initialised with
-            const int wr = kDiagSubRow[w], wc = kDiagSubCol[w];
-            ib0 = 32 * wr + 8 * (lane >> 3);
-            ib1 = ib0 + 4;
-            jb0 = 32 * wc + 4 * (lane & 7);
-            idle = (w >= 10 || 32 * wr >= valid_i || 32 * wc >= valid_j) && allow_idle;
+            // the 10 sub-blocks on or above the diagonal belong to (original) warps 0..9; 10..15 own the 6
+            // sub-blocks below the diagonal, whose pairs the sub-blocks above it already cover
+            i0 = 32 * kDiagSubRow[ow] + 8 * (lane >> 3);
+            i1 = i0 + 4;
+            j0 = 32 * kDiagSubCol[ow] + 4 * (lane & 7);
         } else {
-            ib0 = 4 * (tid & 15);
-            ib1 = 64 + ib0;
-            jb0 = 4 * (tid >> 4);
-            idle = 8 * w >= valid_j && allow_idle;
+            const int vt = 32 * ow + lane;
+            i0 = 4 * (vt & 15);
+            i1 = 64 + i0;
+            j0 = 4 * (vt >> 4);
+        }
+    };
+    int task = w;
+    idle = !block_active(w) && allow_idle;
+    bool balanced = false;
+    if (balance && allow_idle) {
+        int n_active = 0;
+#pragma unroll
+        for (int ow = 0; ow < 16; ++ow) n_active += block_active(ow) ? 1 : 0;
+        if (n_active > 0 && n_active < 16) {
+            balanced = true;
+            const int n_own = n_active > 8 ? 2 * n_active - 16 : 0;
+            int k;                                           // which active block (in original warp order)
+            if (w < n_own) {
+                k = w;
+            } else {
+                const int h = w - n_own;
+                k = n_own + (h >> 1);
+                if (k < n_active) {
+                    fstart = h & 1;
+                    fstep = 2;
+                    shared_primary = (h & 1) == 0;
+                    shared_secondary = (h & 1) == 1;
+                }
+            }
+            idle = k >= n_active;
+            if (!idle) {
+                int seen = 0;
+                task = 0;
+#pragma unroll
+                for (int ow = 0; ow < 16; ++ow) {
+                    if (block_active(ow)) { if (seen == k) task = ow; ++seen; }
+                }
+            }
         }
     }
+    block_coords(task, ib0, ib1, jb0);
     f32x2 acc[8][JH];
 #pragma unroll
     for (int a = 0; a < 8; ++a)
@@ -422,7 +466,7 @@ contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
         const float* si = &sm.ring[slot][0][0][0][0];
         const float* sj = &sm.ring[slot][1][0][0][0];
 #pragma unroll UNROLL
-        for (int fl = 0; fl < nf; ++fl) {
+        for (int fl = fstart; fl < nf; fl += fstep) {
             float ax[8], ay[8], az[8];
             f32x2 bx[JH], by[JH], bz[JH];
             {
@@ -478,28 +522,46 @@ contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
         }
     }
 
-    // idle threads store the zeros their totals were initialised with: the partial tile is always
-    // completely defined.  accumulate: the tile already holds the sums of earlier frame blocks (every
-    // entry belongs to exactly one thread and the launches are stream-ordered: plain read-modify-write)
-    if (accumulate && idle) return;
+    // Store.  Without `accumulate` the partial tile must be completely defined: blocks without real pairs get
+    // zeros.  accumulate: the tile already holds the sums of earlier frame blocks (every entry belongs to
+    // exactly one thread and the launches are stream-ordered: plain read-modify-write).
     double* o = out + (size_t)seg * out_ld * out_ld;
+    auto store_block = [&](int i0, int i1, int j0, bool zeros, int partner) {
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        const int64_t row = (int64_t)kTile * bi + ((a < 4) ? (ib0 + a) : (ib1 + (a - 4)));
-        const int64_t col0 = (int64_t)kTile * bj + jb0;
-        double* p = o + row * out_ld + col0;
-        const int pb = a * 2 * JH;
-        double2 v0 = make_double2(sm.tot[(pb + 0) * kWsComputeThreads + tid], sm.tot[(pb + 1) * kWsComputeThreads + tid]);
-        double2 v1 = make_double2(sm.tot[(pb + 2) * kWsComputeThreads + tid], sm.tot[(pb + 3) * kWsComputeThreads + tid]);
-        if (accumulate) {
-            const double2 o0 = *reinterpret_cast<const double2*>(p), o1 = *reinterpret_cast<const double2*>(p + 2);
-            v0.x += o0.x; v0.y += o0.y; v1.x += o1.x; v1.y += o1.y;
+        for (int a = 0; a < 8; ++a) {
+            const int64_t row = (int64_t)kTile * bi + ((a < 4) ? (i0 + a) : (i1 + (a - 4)));
+            const int64_t col0 = (int64_t)kTile * bj + j0;
+            double* p = o + row * out_ld + col0;
+            const int pb = a * 2 * JH;
+            double v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[k] = zeros ? 0.0 : sm.tot[(pb + k) * kWsComputeThreads + tid];
+                if (partner >= 0) v[k] += sm.tot[(pb + k) * kWsComputeThreads + partner];
+            }
+            if (accumulate) {
+                const double2 o0 = *reinterpret_cast<const double2*>(p), o1 = *reinterpret_cast<const double2*>(p + 2);
+                v[0] += o0.x; v[1] += o0.y; v[2] += o1.x; v[3] += o1.y;
+            }
+            *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+            *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
         }
-        *reinterpret_cast<double2*>(p) = v0;
-        *reinterpret_cast<double2*>(p + 2) = v1;
+    };
+    if (!balanced) {
+        // every warp owns the block of its own index; idle threads store the zeros their totals were
+        // initialised with
+        if (accumulate && idle) return;
+        store_block(ib0, ib1, jb0, false, -1);
+        return;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kWsComputeThreads) : "memory");    // the halves of shared blocks are complete
+    if (!idle && !shared_secondary) store_block(ib0, ib1, jb0, false, shared_primary ? tid + 32 : -1);
+    if (!accumulate && !block_active(w)) {          // zeros for the block without real pairs that warp w would own
+        int z0, z1, zj;
+        block_coords(w, z0, z1, zj);
+        store_block(z0, z1, zj, true, -1);
     }
 }
-
 
 }  // namespace
 
@@ -523,6 +585,8 @@ int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, cons
     static const int variant_env = getenv("WISP_K3_VARIANT") ? atoi(getenv("WISP_K3_VARIANT")) : 58;
     const int variant = accumulate ? 58 : variant_env;      // only the production kernel accumulates
     const int allow_idle = getenv("WISP_K3_NOIDLE") ? 0 : 1;      // experiment switch: every warp computes its block
+    // WISP_K3_BALANCE=0|1: deal the active blocks of diagonal / padded tiles out evenly over the schedulers
+    static const int balance = getenv("WISP_K3_BALANCE") ? atoi(getenv("WISP_K3_BALANCE")) : 1;
 #define WISP_K3_LAUNCH(JH_, UN_)                                                                          \
     do {                                                                                                  \
         WISP_CUDA(cudaFuncSetAttribute(contact_sum_kernel<JH_, UN_>,                                      \
@@ -537,7 +601,8 @@ int launch_contact_sum(wisp_ctx* ctx, const float* d_p32, int64_t T, int N, cons
         WISP_CUDA(cudaFuncSetAttribute(contact_sum_ws_kernel<UN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        smem_ws));                                                               \
         contact_sum_ws_kernel<UN_><<<grid, kWsThreads, smem_ws, st>>>(d_p32, T, N, d_mean, n_tiles, n_seg, part, \
-                                                                      n_pad, allow_idle, accumulate ? 1 : 0);   \
+                                                                      n_pad, allow_idle, accumulate ? 1 : 0,    \
+                                                                      balance);                                 \
     } while (0)
         if (variant == 51) WISP_K3_WS(1);      // frame loop not unrolled: 30.1 ms at C2 with 8-frame stages
         else WISP_K3_WS(8);                    // 58 (default)
