@@ -465,13 +465,10 @@ contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
         }
         const float* si = &sm.ring[slot][0][0][0][0];
         const float* sj = &sm.ring[slot][1][0][0][0];
-#pragma unroll UNROLL
-        for (int fl = fstart; fl < nf; fl += fstep) {
+        auto frame_body = [&](const float* fi, const float* fj) {
             float ax[8], ay[8], az[8];
             f32x2 bx[JH], by[JH], bz[JH];
             {
-                const float* fi = si + fl * kTileFloats;
-                const float* fj = sj + fl * kTileFloats;
                 const float4 t0 = *reinterpret_cast<const float4*>(fi + ib0);
                 const float4 t1 = *reinterpret_cast<const float4*>(fi + ib1);
                 ax[0] = t0.x; ax[1] = t0.y; ax[2] = t0.z; ax[3] = t0.w;
@@ -505,6 +502,18 @@ contact_sum_ws_kernel(const float* __restrict__ p32, int64_t T, int N, const dou
                     acc[a][h] = add2(acc[a][h], pack2(fast_sqrt(lo), fast_sqrt(hi)));
                 }
             }
+        };
+        // two loops with compile-time strides: a run-time frame step in the unrolled loop costs integer
+        // address arithmetic in a loop that has no issue slot to spare (28.7 instead of 27.7 ms at C2)
+        if (fstep == 1) {
+#pragma unroll UNROLL
+            for (int fl = 0; fl < nf; ++fl) frame_body(si + fl * kTileFloats, sj + fl * kTileFloats);
+        } else {
+            const float* si2 = si + fstart * kTileFloats;
+            const float* sj2 = sj + fstart * kTileFloats;
+            const int nh = (nf - fstart + 1) >> 1;           // frames fstart, fstart + 2, ... < nf
+#pragma unroll UNROLL
+            for (int fl = 0; fl < nh; ++fl) frame_body(si2 + fl * (2 * kTileFloats), sj2 + fl * (2 * kTileFloats));
         }
         __syncwarp();
         if ((tid & 31) == 0) ws_mbar_arrive(&sm.empty[slot]);        // this warp is done with the stage
