@@ -148,3 +148,58 @@ def test_k7_rotation_solver_on_the_cpu(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "Jacobi fallbacks" in r.stdout
+
+
+def _k3_deal(diag, valid_i, valid_j):
+    """Python model of the block dealing in contact_sum_ws_kernel (csrc/k3_contact.cu, `balance`): returns
+    per warp (task block or None, frame parity: None = all frames / 0 = even / 1 = odd)."""
+    sub_row = [0, 0, 0, 0, 1, 1, 1, 2, 2, 3, 1, 2, 2, 3, 3, 3]
+    sub_col = [0, 1, 2, 3, 1, 2, 3, 2, 3, 3, 0, 0, 1, 0, 1, 2]
+
+    def active(ow):
+        if diag:
+            return ow < 10 and 32 * sub_row[ow] < valid_i and 32 * sub_col[ow] < valid_j
+        return 8 * ow < valid_j
+
+    act = [ow for ow in range(16) if active(ow)]
+    n_active = len(act)
+    if n_active == 0 or n_active == 16:
+        return [(w if active(w) else None, None) for w in range(16)], act
+    n_own = 2 * n_active - 16 if n_active > 8 else 0
+    deal = []
+    for w in range(16):
+        if w < n_own:
+            deal.append((act[w], None))
+        else:
+            h = w - n_own
+            k = n_own + (h >> 1)
+            deal.append((act[k], h & 1) if k < n_active else (None, None))
+    return deal, act
+
+
+def test_k3_block_dealing_model():
+    """Every active block of a diagonal / padded K3 tile is covered exactly once -- by one warp taking all
+    frames or by two consecutive warps taking the even and the odd frames -- and the four schedulers
+    (warp index mod 4) carry the same work to within half a block (10 active blocks: 2.5 each, where
+    idling six warps leaves 3, 3, 2, 2)."""
+    for diag in (False, True):
+        for valid in range(1, 129):
+            deal, act = _k3_deal(diag, valid if diag else 128, valid)
+            cover = {b: [] for b in act}
+            load = [0.0] * 4
+            for w, (task, parity) in enumerate(deal):
+                if task is None:
+                    continue
+                cover[task].append(parity)
+                load[w % 4] += 1.0 if parity is None else 0.5
+            for b, parts in cover.items():
+                assert parts == [None] or sorted(parts) == [0, 1], (diag, valid, b, parts)
+            for w in range(15):                      # the two halves of a block sit in consecutive warps
+                if deal[w][1] == 0:
+                    assert deal[w + 1] == (deal[w][0], 1)
+            assert abs(sum(load) - len(act)) < 1e-12
+            if 0 < len(act) < 16:
+                assert max(load) - min(load) <= 0.5 + 1e-12, (diag, valid, load)
+    # the C2 cases: 10 active blocks -> 2.5 per scheduler
+    deal, act = _k3_deal(True, 128, 128)
+    assert len(act) == 10 and sorted(p is None for _, p in deal if _ is not None).count(True) == 4
